@@ -1,0 +1,381 @@
+#!/usr/bin/env python3
+"""bench.py -- query bases/s of the kbo MS hot path (matches/find) on B200.
+
+Workload (BASELINE.json configs[1]): kbo::find of 10,000 synthetic 1 kbp gene queries (1 % SNPs)
+against a 5 Mbp reference, k = 31, p = 1e-7; the index (~10 MB) is L2 resident.  A "step" is one
+pass of the hot path over one batch of 10,000 queries (10^7 query bases).
+
+  value : whole-job throughput with the batch already resident in HBM (kbo_matches_batch_device:
+          K0 pack -> K1 matching statistics -> K2 derandomize+translate), CUDA events on the launch
+          stream, max over ranks.  Steps rotate through `--batches` distinct batches whose total
+          size exceeds L2, so queries always come from HBM while the index stays L2 resident.
+  e2e   : the same metric through the host-buffer C ABI call a kbo user makes (kbo_find_batch):
+          pinned host -> device copy, kernels, device -> host copy of the alignment, host RLE.
+  roofline     : K1 (ms_kernel), algorithmic bytes / its CUDA-event duration vs the
+                 measured HBM peak (MEASURED_PEAKS.json); random-sector L2/HBM rates beside it.
+  cpu_baseline : the C++ oracle (restatement of kbo 0.5.1 + sbwt 0.3.4 semantics) running kbo::find
+                 on all host cores over a bounded sample of the same workload.
+
+`--impl reference` times that CPU restatement alone (the reference crate cannot be built here: no
+Rust toolchain and its MS engine is the un-vendored crate sbwt 0.3.4).
+Multi-GPU (torchrun, one rank per GPU): the index is replicated, every rank processes its own
+batches (weak scaling), no collective on the data path; NCCL only carries the timing reduction.
+"""
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+sys.path.insert(0, os.path.join(ROOT, "tests"))
+
+K = 31
+P = 1e-7
+SECTOR = 32
+
+
+def parse_args():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=20)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--ref-len", type=int, default=5_000_000)
+    ap.add_argument("--queries", type=int, default=10_000)
+    ap.add_argument("--query-len", type=int, default=1000)
+    ap.add_argument("--batches", type=int, default=16, help="distinct batches rotated through (16 x 10 MB > L2)")
+    ap.add_argument("--chunk-len", type=int, default=0, help="MS chunk length (0 = automatic)")
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--cpu-seconds", type=float, default=12.0, help="target CPU work of the cpu_baseline sample")
+    return ap.parse_args()
+
+
+# ------------------------------------------------------------------------------------ helpers ---
+class ClockSampler:
+    """nvidia-smi clocks / throttle reasons during the timed region (B200_PROFILING.md recipe)."""
+    Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,"
+         "clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
+         "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, device):
+        self.device = device
+        self.proc = None
+        self.lines = []
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", "-i", str(self.device), "--query-gpu=" + self.Q,
+                                          "--format=csv,noheader,nounits", "-lms", "100"],
+                                         stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            self.thread = threading.Thread(target=self._read, daemon=True)
+            self.thread.start()
+        except Exception:
+            self.proc = None
+
+    def _read(self):
+        for ln in self.proc.stdout:
+            self.lines.append(ln.strip())
+
+    def stop(self):
+        if not self.proc:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        time.sleep(0.15)
+        self.proc.terminate()
+        try:
+            self.proc.wait(timeout=2)
+        except Exception:
+            self.proc.kill()
+        sm, smax, reasons = [], [], set()
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        for ln in self.lines:
+            f = [x.strip() for x in ln.split(",")]
+            if len(f) < 9:
+                continue
+            try:
+                sm.append(float(f[1]))
+                smax.append(float(f[2]))
+            except ValueError:
+                continue
+            for name, val in zip(names, f[5:9]):
+                if val.lower().startswith("active"):
+                    reasons.add(name)
+        return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": max(smax) if smax else None,
+                "samples": len(sm), "reasons": sorted(reasons)}
+
+
+def measured_peaks():
+    path = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(path):
+        try:
+            return float(json.load(open(path))["hbm_gbs"]), "MEASURED_PEAKS.json hbm_gbs (measured copy peak)"
+        except Exception:
+            pass
+    return 6650.0, "fallback 6.65 TB/s (B200_PROFILING.md; MEASURED_PEAKS.json absent)"
+
+
+def committed_traffic():
+    """dram bytes per ms_kernel launch from the committed ncu --set full capture, if present."""
+    path = os.path.join(ROOT, "profiles", "ms_kernel_traffic.json")
+    if os.path.exists(path):
+        try:
+            return json.load(open(path)).get("dram_bytes_per_launch")
+        except Exception:
+            return None
+    return None
+
+
+def workload(args, rank):
+    from kbo_b200 import synth
+    ref = synth.random_seq(args.ref_len, synth.SEED_C2_REF)
+    batches = []
+    for b in range(args.batches):
+        concat, offsets = synth.gene_queries(ref, args.queries, args.query_len,
+                                             synth.SEED_C2_GENES + 1000 * rank + b)
+        batches.append(concat)
+    return ref, batches, offsets
+
+
+def cpu_baseline(ref, concat, offsets, args, budget_s):
+    """kbo::find with the C++ oracle on all host cores over a bounded sample (rank 0 only)."""
+    import oracle_lib as O
+    cores = O.hardware_concurrency() or os.cpu_count() or 1
+    t0 = time.perf_counter()
+    oix = O.OracleIndex([ref.tobytes()], k=K)
+    build_s = time.perf_counter() - t0
+    nq_total = len(offsets) - 1
+    probe = min(nq_total, 50 * cores)
+    secs, _, _ = O.find_batch_timed(oix, concat, offsets[:probe + 1], P, 0, cores)
+    rate = probe / max(secs, 1e-6)
+    nq = int(min(nq_total, max(probe, rate * budget_s)))
+    secs, n_rle, _ = O.find_batch_timed(oix, concat, offsets[:nq + 1], P, 0, cores)
+    bases = int(offsets[nq] - offsets[0])
+    return {"value": bases / secs, "unit": "query bases/s", "cores": cores, "kind": "port",
+            "sample": "kbo::find of the first %d of %d queries (%d bases) in %.2f s on %d threads; "
+                      "oracle index build %.1f s excluded; C++ restatement of kbo 0.5.1 + sbwt 0.3.4 semantics "
+                      "(the reference crate needs Rust + sbwt, unavailable here)" % (nq, nq_total, bases, secs, cores,
+                                                                                   build_s)}, oix
+
+
+# ---------------------------------------------------------------------------------- reference arm ---
+def run_reference(args, rank, world):
+    if rank != 0:
+        return
+    import oracle_lib as O
+    O.build_oracle()
+    ref, batches, offsets = workload(args, 0)
+    cores = O.hardware_concurrency() or os.cpu_count() or 1
+    oix = O.OracleIndex([ref.tobytes()], k=K)
+    # bounded sample per step: sized from a probe so that steps+warmup finish within ~2 minutes
+    probe = min(len(offsets) - 1, 50 * cores)
+    secs, _, _ = O.find_batch_timed(oix, batches[0], offsets[:probe + 1], P, 0, cores)
+    per_step_budget = max(0.5, min(5.0, 100.0 / max(1, args.steps + args.warmup)))
+    nq = int(min(len(offsets) - 1, max(probe, probe / max(secs, 1e-6) * per_step_budget)))
+    for s in range(args.warmup):
+        O.find_batch_timed(oix, batches[s % len(batches)], offsets[:nq + 1], P, 0, cores)
+    total = 0.0
+    for s in range(args.steps):
+        t, _, _ = O.find_batch_timed(oix, batches[s % len(batches)], offsets[:nq + 1], P, 0, cores)
+        total += t
+    bases = int(offsets[nq] - offsets[0])
+    value = bases * args.steps / total
+    sample = ("each step = kbo::find of %d of %d queries (%d bases) on %d host threads; C++ restatement of "
+              "kbo 0.5.1 + sbwt 0.3.4 semantics" % (nq, len(offsets) - 1, bases, cores))
+    line = {"impl": "reference", "metric": "query bases/s (kbo find, whole box)", "value": value,
+            "unit": "query bases/s", "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup,
+            "ms_per_step": 1e3 * total / args.steps, "higher_is_better": True, "scaling": "weak",
+            "vs_baseline": None, "dtype": "u8", "data": "synthetic",
+            "config": config_dict(args, sample_note=sample),
+            "cpu_baseline": {"value": value, "unit": "query bases/s", "cores": cores, "kind": "port", "sample": sample},
+            "e2e": {"value": value, "unit": "query bases/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
+    print(json.dumps(line), flush=True)
+
+
+def config_dict(args, sample_note=None):
+    c = {"workload": "kbo::find of %d synthetic %d bp gene queries (1%% SNPs) vs a %d bp synthetic reference, k=%d, "
+                     "p=%g (BASELINE.json configs[1]; index L2-resident)" % (args.queries, args.query_len, args.ref_len,
+                                                                           K, P),
+         "queries_per_step": args.queries, "query_len": args.query_len, "ref_len": args.ref_len, "k": K,
+         "l2_policy": "inputs larger than L2: steps rotate through %d distinct batches (%d MB of queries); the index "
+                      "is L2-resident by the config's design" % (args.batches,
+                                                                 args.batches * args.queries * args.query_len // 10**6)}
+    if sample_note:
+        c["sample"] = sample_note
+    return c
+
+
+# --------------------------------------------------------------------------------------- our arm ---
+def run_ours(args, rank, local_rank, world):
+    import torch
+    from kbo_b200 import api, build
+    build.build_library()
+    api.load_library()
+    if not torch.cuda.is_available() or api.device_count() < 1:
+        raise SystemExit("bench.py: no CUDA device (kbo_b200 has no CPU fallback)")
+    dev = local_rank
+    torch.cuda.set_device(dev)
+    dist = None
+    if world > 1:
+        import torch.distributed as dist
+        dist.init_process_group("nccl", device_id=torch.device("cuda", dev))
+    api.set_chunk_len(args.chunk_len)
+
+    ref, batches, offsets = workload(args, rank)
+    hw = os.cpu_count() or 1
+    t0 = time.perf_counter()
+    index = api.build([ref], api.BuildOpts(k=K, num_threads=min(hw, 16)), device=dev)
+    index_build_s = time.perf_counter() - t0
+    nq = len(offsets) - 1
+    bases_per_step = int(offsets[nq])
+
+    stream = torch.cuda.current_stream()
+    sptr = stream.cuda_stream
+    d_off = torch.from_numpy(offsets.astype(np.int64)).cuda()
+    pinned_in = [torch.from_numpy(b).pin_memory() for b in batches]
+    d_in = [p.cuda(non_blocking=True) for p in pinned_in]
+    d_out = [torch.empty(bases_per_step + 16, dtype=torch.uint8, device="cuda") for _ in batches]
+    torch.cuda.synchronize()
+
+    def step_device(s):
+        b = s % len(batches)
+        api.matches_device(index, d_in[b].data_ptr(), d_off.data_ptr(), offsets, d_out[b].data_ptr(), P, sptr)
+
+    def barrier():
+        torch.cuda.synchronize()
+        if dist is not None:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    # ---- value: device-resident ---------------------------------------------------------------
+    for s in range(args.warmup):
+        step_device(s)
+    barrier()
+    api.set_kernel_timing(True)
+    sampler = ClockSampler(dev)
+    sampler.start()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    n0 = api.kernel_launch_count()
+    barrier()
+    e0.record(stream)
+    for s in range(args.steps):
+        step_device(args.warmup + s)
+    e1.record(stream)
+    barrier()
+    launches = api.kernel_launch_count() - n0
+    clocks = sampler.stop()
+    api.set_kernel_timing(False)
+    ms_total = e0.elapsed_time(e1)
+    ksum, kcalls = api.collect_kernel_times(index, sptr)
+    t = torch.tensor([ms_total], dtype=torch.float64, device="cuda")
+    lt = torch.tensor([float(launches)], dtype=torch.float64, device="cuda")
+    if dist is not None:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        dist.all_reduce(lt, op=dist.ReduceOp.SUM)
+    ms_max = float(t.item())
+    value = world * args.steps * bases_per_step / (ms_max * 1e-3)
+
+    # ---- e2e: host buffers through the public C ABI call (H2D + kernels + D2H + RLE) -----------
+    fbuf = api.FindBuffers(nq)
+    pinned_np = [p.numpy() for p in pinned_in]
+    for s in range(min(args.warmup, 2)):
+        api.find_csr(pinned_np[s % len(batches)], offsets, index, api.FindOpts(P, 0), fbuf)
+    barrier()
+    w0 = time.perf_counter()
+    n_rle = 0
+    for s in range(args.steps):
+        _, n_rle = api.find_csr(pinned_np[(args.warmup + s) % len(batches)], offsets, index, api.FindOpts(P, 0), fbuf)
+    torch.cuda.synchronize()
+    e2e_s = time.perf_counter() - w0
+    te = torch.tensor([e2e_s], dtype=torch.float64, device="cuda")
+    if dist is not None:
+        dist.all_reduce(te, op=dist.ReduceOp.MAX)
+    e2e_value = world * args.steps * bases_per_step / float(te.item())
+
+    # ---- roofline inputs: event counters of one batch (profiling build of K1, outside the timing) --
+    api.set_profile_counters(True)
+    out_host = api.matches_csr(pinned_np[0], offsets, index, P)
+    api.set_profile_counters(False)
+    cnt = index.ms_counters()
+    L = cnt["bases_emitted"]
+    alg_bytes = (SECTOR * (cnt["emit_extend_attempts"] + cnt["emit_extend_split_sector"]) +
+                 SECTOR * (cnt["emit_contractions"] + cnt["emit_contraction_extra_words"]) + 2 * L)
+    k1_ms = ksum["ms"] / max(kcalls, 1)
+    achieved = alg_bytes / (k1_ms * 1e-3) / 1e9 if k1_ms > 0 else 0.0
+    peak, peak_src = measured_peaks()
+    roof = {"bound": "hbm", "kernel": "ms_kernel", "achieved": achieved, "peak": peak, "unit": "GB/s",
+            "frac": achieved / peak, "traffic": committed_traffic(), "peak_source": peak_src,
+            "algorithmic_bytes_per_launch": alg_bytes, "algorithmic_bytes_per_base": alg_bytes / max(L, 1),
+            "kernel_ms": {"pack": ksum["pack"] / max(kcalls, 1), "ms": k1_ms,
+                          "derand_translate": ksum["derand_translate"] / max(kcalls, 1)},
+            "events_per_base": {"extend_attempts": cnt["emit_extend_attempts"] / max(L, 1),
+                                "contractions": cnt["emit_contractions"] / max(L, 1),
+                                "warmup_overhead": cnt["bases_processed"] / max(L, 1)},
+            "note": "the index is L2-resident in this config, so the HBM-peak fraction is not a ceiling; "
+                    "the measured random-sector rates below are the relevant denominators"}
+    if rank == 0:
+        try:
+            l2_dep = api.measure_random_sector_rate(8 << 20, True, dev)
+            l2_ind = api.measure_random_sector_rate(8 << 20, False, dev)
+            hbm_ind = api.measure_random_sector_rate(4 << 30, False, dev)
+            sectors_per_s = (cnt["emit_extend_attempts"] + cnt["emit_extend_split_sector"] + cnt["emit_contractions"] +
+                             cnt["emit_contraction_extra_words"]) / (k1_ms * 1e-3)
+            roof["random_sector"] = {"l2_dependent_chain_sectors_per_s": l2_dep, "l2_independent_sectors_per_s": l2_ind,
+                                     "hbm_independent_sectors_per_s": hbm_ind, "kernel_sectors_per_s": sectors_per_s,
+                                     "frac_of_l2_independent": sectors_per_s / l2_ind if l2_ind else None,
+                                     "frac_of_l2_dependent_chain": sectors_per_s / l2_dep if l2_dep else None}
+        except Exception as ex:  # instrumentation only
+            roof["random_sector"] = {"error": str(ex)}
+
+    # ---- cpu baseline + a parity spot check against it (rank 0, N = 1) --------------------------
+    cpu = None
+    if rank == 0 and world == 1 and not args.no_cpu_baseline:
+        cpu, oix = cpu_baseline(ref, batches[0], offsets, args, args.cpu_seconds)
+        nchk = min(nq, 200)
+        _, want, _ = oix.matches_batch(batches[0][:int(offsets[nchk])], offsets[:nchk + 1], P, n_threads=cpu["cores"])
+        if not np.array_equal(out_host[:int(offsets[nchk])], want):
+            raise SystemExit("bench.py: GPU output differs from the oracle on the first %d queries" % nchk)
+
+    if rank == 0:
+        cfg = config_dict(args)
+        cfg.update({"chunk_len": args.chunk_len or "auto", "index_device_bytes": index.device_bytes,
+                    "n_sets": index.n_sets, "index_build_s_host": round(index_build_s, 2), "rle_records_per_step": n_rle,
+                    "parallelism": "replicated index, %d rank(s) x own batches" % world})
+        line = {"metric": "query bases/s (kbo find, whole box)", "value": value, "unit": "query bases/s",
+                "n_gpus": world, "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms_max / args.steps,
+                "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "u8", "data": "synthetic",
+                "config": cfg, "clocks": clocks,
+                "e2e": {"value": e2e_value, "unit": "query bases/s",
+                        "h2d_bytes_per_step": bases_per_step + 8 * (nq + 1), "d2h_bytes_per_step": bases_per_step,
+                        "api": "kbo_find_batch (pinned host buffers; host RLE pass inside the call)"},
+                "gpu_launches": int(lt.item()), "roofline": roof}
+        if cpu is not None:
+            line["cpu_baseline"] = cpu
+        print(json.dumps(line), flush=True)
+    if dist is not None:
+        dist.barrier()
+        dist.destroy_process_group()
+
+
+def main():
+    args = parse_args()
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    if args.gpus > 1 and world == 1:
+        # convenience: re-launch under torchrun like the driver does
+        cmd = [sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node", str(args.gpus),
+               "--master-addr", "127.0.0.1", "--master-port", "29533", os.path.abspath(__file__)] + sys.argv[1:]
+        raise SystemExit(subprocess.call(cmd))
+    if args.impl == "reference":
+        run_reference(args, rank, world)
+    else:
+        run_ours(args, rank, local_rank, world)
+
+
+if __name__ == "__main__":
+    main()

@@ -1,0 +1,198 @@
+/* ===========================================================================
+ * kbo_b200.h -- C ABI of the B200-native (sm_100a) implementation of kbo's
+ * k-bounded matching statistics hot path.
+ *
+ * This is the drop-in boundary: every entry point replaces one function of the
+ * reference crate tmaklin/kbo 0.5.1 (paths below are relative to the reference
+ * checkout) and is what a thin Rust `kbo-b200-sys` FFI crate would bind (see
+ * INTEGRATION.md).  Plain pointers and sizes only; no C++/torch types.
+ *
+ * Conventions
+ *  - Every function returning `int` returns a kbo_status (0 = ok).  Where the
+ *    reference PANICS (assert!/unwrap) the ABI returns a distinct non-zero code
+ *    and never aborts or throws; kbo_last_error_message() gives the text and
+ *    the reference file:line of the violated precondition.  The Rust shim turns
+ *    non-zero into panic!().
+ *  - Inputs are borrowed for the duration of the call only; outputs are caller
+ *    allocated.  The library never frees caller memory.
+ *  - Host-pointer entry points copy host->device and device->host inside the
+ *    call.  `_device` entry points take CUDA device pointers (same device as
+ *    the index) and an optional cudaStream_t (as void*; NULL = the library's
+ *    own stream) and are asynchronous only with respect to that stream.
+ *  - Widths: the device works in u8 (MS length, alignment characters) and u32
+ *    (colex ranks, n_sets < 2^32).  Entry points without a `_compact` suffix
+ *    widen to the reference's usize/i64 on the way out; alignment characters
+ *    are 1 byte each (Rust `char` is 4; the shim widens).
+ *  - All functions are thread-safe; an index handle is immutable after
+ *    creation and may be shared by concurrent callers (reference functions take
+ *    `&SbwtIndexVariant`, src/lib.rs:612-617).
+ *  - There is no CPU fallback: without a CUDA device every compute entry point
+ *    fails with KBO_ERR_CUDA.
+ * ======================================================================== */
+#ifndef KBO_B200_H
+#define KBO_B200_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+typedef enum kbo_status {
+    KBO_OK = 0,
+    KBO_ERR_EMPTY_INPUT = 1,      /* index.rs:60 assert!(!slices.is_empty()); index.rs:248 assert!(!query.is_empty()) */
+    KBO_ERR_BAD_THRESHOLD = 2,    /* derandomize.rs:228,275; translate.rs:186,269: threshold > 1 */
+    KBO_ERR_TOO_SHORT = 3,        /* derandomize.rs:276; translate.rs:270: len > 2 */
+    KBO_ERR_BAD_K = 4,            /* derandomize.rs:227,274 k > 0; this build: k <= KBO_MAX_K */
+    KBO_ERR_K_MISMATCH = 5,       /* lib.rs:559, lib.rs:729 */
+    KBO_ERR_BAD_PROB = 6,         /* derandomize.rs:136-137: 0 < max_error_prob <= 1 */
+    KBO_ERR_BAD_ARGUMENT = 7,     /* null pointer, n_kmers == 0 (derandomize.rs:96,134), alphabet == 0, MS value > k (derandomize.rs:229) */
+    KBO_ERR_CUDA = 8,             /* no device / CUDA runtime error */
+    KBO_ERR_OOM = 9,              /* host or device allocation failed */
+    KBO_ERR_INDEX_TOO_LARGE = 10, /* n_sets >= 2^32 */
+    KBO_ERR_BUFFER_TOO_SMALL = 11,/* caller capacity too small (count is still returned) */
+    KBO_ERR_PANIC = 12            /* the reference would panic on these inputs (index out of bounds etc.) */
+} kbo_status;
+
+#define KBO_MAX_K 64 /* packed k-mers are two 64-bit words; reference tests use k <= 63 */
+
+/* src/lib.rs:259-313 BuildOpts (fields this implementation does not need are accepted and ignored) */
+typedef struct kbo_build_opts {
+    uint32_t k;              /* default 31 */
+    int32_t add_revcomp;     /* default 0 */
+    uint32_t num_threads;    /* default 1 (host-side sort threads) */
+    uint32_t prefix_precalc; /* default 8; ignored (no prefix table is needed on the device) */
+    int32_t build_select;    /* default 0; access_kmer is always available here */
+    uint32_t mem_gb;         /* ignored */
+    int32_t dedup_batches;   /* ignored */
+    const char* temp_dir;    /* ignored (always in memory) */
+} kbo_build_opts;
+
+/* src/format.rs:17-33 RLE */
+typedef struct kbo_rle {
+    uint64_t start, end, matches, mismatches, jumps, gap_bases, gap_opens;
+} kbo_rle;
+
+/* Opaque: (SbwtIndexVariant::SubsetMatrix, sbwt::LcsArray) resident on one GPU in the
+ * interleaved rank/LCS layout (DESIGN.md "Index layout"). */
+typedef struct kbo_index kbo_index;
+
+/* ---- library ------------------------------------------------------------ */
+const char* kbo_last_error_message(void);       /* thread-local */
+int kbo_device_count(int* out);
+void kbo_default_build_opts(kbo_build_opts* o); /* lib.rs:294-312 */
+/* pinned host staging buffers for callers that want full-speed PCIe copies */
+int kbo_alloc_pinned(size_t bytes, void** out);
+int kbo_free_pinned(void* p);
+
+/* ---- index: src/index.rs ------------------------------------------------ */
+/* index::build_sbwt_from_vecs (index.rs:56-99) / kbo::build (lib.rs:501-506) */
+int kbo_index_build(const uint8_t* const* seqs, const uint64_t* lens, uint64_t n_seqs, const kbo_build_opts* opts,
+                    int device, kbo_index** out);
+/* Upload an index built elsewhere (e.g. by the sbwt crate): 4 subset-matrix bit rows of
+ * ceil(n_sets/64) little-endian u64 words (bit i of row c = node i has outgoing label c,
+ * A,C,G,T order) and n_sets LCS bytes.  `kmers_colex` may be NULL (then access_kmer walks
+ * the index); otherwise it is ignored in this version. */
+int kbo_index_from_parts(uint32_t k, uint64_t n_sets, uint64_t n_kmers, const uint64_t* const rows[4],
+                         const uint8_t* lcs, int device, kbo_index** out);
+void kbo_index_free(kbo_index* ix);
+uint32_t kbo_index_k(const kbo_index* ix);        /* SbwtIndex::k()       lib.rs:618 */
+uint64_t kbo_index_n_kmers(const kbo_index* ix);  /* SbwtIndex::n_kmers() lib.rs:620 */
+uint64_t kbo_index_n_sets(const kbo_index* ix);   /* SbwtIndex::n_sets()  */
+int kbo_index_device(const kbo_index* ix);
+uint64_t kbo_index_device_bytes(const kbo_index* ix);
+/* Read the index back in the kbo_index_from_parts format (for verification / serialization). */
+int kbo_index_export_parts(const kbo_index* ix, uint64_t* rows[4], uint8_t* lcs, uint64_t C_out[4]);
+/* SbwtIndex::access_kmer (variant_calling.rs:276, gap_filling.rs:144): k bytes, '$' padded. */
+int kbo_index_access_kmer(const kbo_index* ix, uint64_t colex, uint8_t* out_k);
+/* SbwtIndex::search (gap_filling.rs:217): *found = 0 when the pattern does not occur. */
+int kbo_index_search(const kbo_index* ix, const uint8_t* pattern, uint64_t len, int* found, uint64_t* l, uint64_t* r);
+
+/* index::query_sbwt (index.rs:243-256) = StreamingIndex::matching_statistics: per query
+ * position (d, l..r).  l_out/r_out may be NULL (lengths only, as lib.rs:624 uses it). */
+int kbo_query_sbwt(const kbo_index* ix, const uint8_t* query, uint64_t len, uint64_t* d_out, uint64_t* l_out,
+                   uint64_t* r_out);
+/* Batched form over a CSR batch: query i = concat[offsets[i] .. offsets[i+1]); outputs indexed like concat. */
+int kbo_query_sbwt_batch_compact(const kbo_index* ix, const uint8_t* concat, const uint64_t* offsets,
+                                 uint64_t n_queries, uint8_t* d_out, uint32_t* l_out, uint32_t* r_out);
+
+/* ---- derandomize: src/derandomize.rs ------------------------------------ */
+int kbo_log_rm_max_cdf(uint64_t t, uint64_t alphabet_size, uint64_t n_kmers, double* out);      /* :91-100  (host, f64) */
+int kbo_random_match_threshold(uint64_t k, uint64_t n_kmers, uint64_t alphabet_size, double max_error_prob,
+                               uint64_t* out);                                                   /* :127-145 (host, f64) */
+/* derandomize_ms_vec (:269-288) on the GPU for an arbitrary MS vector (values <= k). */
+int kbo_derandomize_ms_vec(const uint64_t* noisy_ms, uint64_t n, uint64_t k, uint64_t threshold, int64_t* out,
+                           int device);
+
+/* ---- translate: src/translate.rs ---------------------------------------- */
+/* translate_ms_vec (:263-293) on the GPU; one byte per alignment character ('M','-','X','R'). */
+int kbo_translate_ms_vec(const int64_t* derand_ms, uint64_t n, uint64_t k, uint64_t threshold, uint8_t* chars_out,
+                         int device);
+
+/* ---- format: src/format.rs ---------------------------------------------- */
+/* run_lengths_gapped (:143-193); max_gap_len == 0 gives run_lengths (:98-102).  Writes at most
+ * `cap` entries, *n_out = number of RLEs found. */
+int kbo_run_lengths_gapped(const uint8_t* aln, uint64_t n, uint64_t max_gap_len, kbo_rle* out, uint64_t cap,
+                           uint64_t* n_out);
+/* relative_to_ref (:266-287) */
+int kbo_relative_to_ref(const uint8_t* ref_seq, const uint8_t* aln, uint64_t n, uint8_t* out);
+
+/* ---- API: src/lib.rs ----------------------------------------------------- */
+/* kbo::matches (lib.rs:612-628): threshold -> MS -> derandomize -> translate, fused on the device. */
+int kbo_matches(const kbo_index* ix, const uint8_t* query, uint64_t len, double max_error_prob, uint8_t* chars_out);
+/* Same for a CSR batch of queries in ONE launch sequence; chars_out indexed like concat. */
+int kbo_matches_batch(const kbo_index* ix, const uint8_t* concat, const uint64_t* offsets, uint64_t n_queries,
+                      double max_error_prob, uint8_t* chars_out);
+/* Device-resident form: d_concat (total bytes), d_offsets (n_queries+1 u64) and d_chars_out are device
+ * pointers on the index's device; host_offsets is the same offsets array on the host (needed for
+ * precondition checks and sizing).  Asynchronous on `stream`. */
+int kbo_matches_batch_device(const kbo_index* ix, const uint8_t* d_concat, const uint64_t* d_offsets,
+                             const uint64_t* host_offsets, uint64_t n_queries, double max_error_prob,
+                             uint8_t* d_chars_out, void* stream);
+/* kbo::find (lib.rs:808-821) for a CSR batch: matches + run_lengths[_gapped].  RLEs of query i are
+ * rle_out[rle_offsets[i] .. rle_offsets[i+1]) (rle_offsets has n_queries+1 entries). */
+int kbo_find_batch(const kbo_index* ix, const uint8_t* concat, const uint64_t* offsets, uint64_t n_queries,
+                   double max_error_prob, uint64_t max_gap_len, kbo_rle* rle_out, uint64_t rle_cap,
+                   uint64_t* rle_offsets);
+/* kbo::map without refinement (lib.rs:726-738,756-760 with fill_gaps = call_variants = false):
+ * `format` != 0 applies relative_to_ref, else the raw translation characters are returned. */
+int kbo_map_unrefined(const kbo_index* query_index, const uint8_t* ref_seq, uint64_t len, double max_error_prob,
+                      int format, uint8_t* out);
+
+/* ---- instrumentation ------------------------------------------------------ */
+/* Event counters of the last MS launch sequence on this index when profiling counters are enabled
+ * (kbo_set_profile_counters(1)): extend attempts, attempts whose two rank probes fell in different
+ * 32-byte sectors, LCS contractions, extra LCS words touched, query bases incl. chunk warm-up,
+ * query bases emitted.  Used for the roofline's algorithmic-bytes figure. */
+typedef struct kbo_ms_counters {
+    /* all work, including the k-1 warm-up bases of every chunk */
+    uint64_t extend_attempts, extend_split_sector, contractions, contraction_extra_words, bases_processed,
+        bases_emitted;
+    /* only the events of emitted positions: the algorithmic figure the roofline uses */
+    uint64_t emit_extend_attempts, emit_extend_split_sector, emit_contractions, emit_contraction_extra_words;
+} kbo_ms_counters;
+int kbo_set_profile_counters(int enabled);
+int kbo_get_ms_counters(const kbo_index* ix, kbo_ms_counters* out);
+/* Tuning knob: bases per MS chunk (0 = automatic).  Results never depend on it. */
+int kbo_set_chunk_len(uint32_t chunk_len);
+/* Number of kernel launches issued by this library since load (for bench.py's gpu_launches). */
+uint64_t kbo_kernel_launch_count(void);
+/* Elapsed device time of the last host-pointer call's kernel section in ms (CUDA events). */
+float kbo_last_kernel_ms(const kbo_index* ix);
+/* Per-kernel timing of kbo_matches_batch_device calls: when enabled, CUDA events are recorded on the
+ * caller's stream around K0 (pack), K1 (MS) and K2 (derandomize+translate) of every call (up to 512
+ * calls between collections).  kbo_collect_kernel_times must be called after the stream has been
+ * synchronised; it returns the SUMMED elapsed ms per kernel and the number of calls, and resets. */
+int kbo_set_kernel_timing(int enabled);
+int kbo_collect_kernel_times(const kbo_index* ix, void* stream, double sum_ms_out[3], uint64_t* n_calls);
+/* Roofline denominators that MEASURED_PEAKS.json does not hold: throughput of 8-byte loads that each
+ * touch a random 32-byte sector of a `buffer_bytes` buffer (small buffer = L2-resident, large = HBM),
+ * issued like K1 issues them (one dependent chain per lane, every resident lane busy) when
+ * `dependent` != 0, or as independent loads when 0.  Result: sectors per second. */
+int kbo_measure_random_sector_rate(int device, uint64_t buffer_bytes, int dependent, double* sectors_per_s);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* KBO_B200_H */

@@ -1,0 +1,486 @@
+"""Host-side mirror of the reference crate's public functions for the MS hot path, over the C ABI
+of include/kbo_b200.h (ctypes; no torch types cross the boundary).
+
+Names, argument meaning and error behaviour follow tmaklin/kbo 0.5.1:
+  build / matches / find / map            src/lib.rs:501, 612, 808, 720
+  query_sbwt                              src/index.rs:243
+  random_match_threshold, log_rm_max_cdf,
+  derandomize_ms_vec                      src/derandomize.rs:127, 91, 269
+  translate_ms_vec                        src/translate.rs:263
+  run_lengths, run_lengths_gapped,
+  relative_to_ref                         src/format.rs:98, 143, 266
+Where the reference panics, these raise KboPanic(status, message).
+
+There is no CPU fallback: importing works without the shared library, but the first call raises
+if kbo_b200/libkbo_b200.so has not been built (python -m kbo_b200.build) or no CUDA device exists.
+"""
+import ctypes as C
+import os
+from dataclasses import dataclass, field
+from typing import Optional
+
+import numpy as np
+
+_LIB_PATH = os.path.join(os.path.dirname(os.path.abspath(__file__)), "libkbo_b200.so")
+_lib = None
+
+u8p, u32p, u64p, i64p = C.POINTER(C.c_uint8), C.POINTER(C.c_uint32), C.POINTER(C.c_uint64), C.POINTER(C.c_int64)
+
+STATUS_NAMES = {0: "OK", 1: "EMPTY_INPUT", 2: "BAD_THRESHOLD", 3: "TOO_SHORT", 4: "BAD_K", 5: "K_MISMATCH",
+                6: "BAD_PROB", 7: "BAD_ARGUMENT", 8: "CUDA", 9: "OOM", 10: "INDEX_TOO_LARGE", 11: "BUFFER_TOO_SMALL",
+                12: "PANIC"}
+
+# every symbol include/kbo_b200.h declares (tests check that the library exports all of them)
+EXPORTED_SYMBOLS = [
+    "kbo_last_error_message", "kbo_device_count", "kbo_default_build_opts", "kbo_alloc_pinned", "kbo_free_pinned",
+    "kbo_index_build", "kbo_index_from_parts", "kbo_index_free", "kbo_index_k", "kbo_index_n_kmers",
+    "kbo_index_n_sets", "kbo_index_device", "kbo_index_device_bytes", "kbo_index_export_parts",
+    "kbo_index_access_kmer", "kbo_index_search", "kbo_query_sbwt", "kbo_query_sbwt_batch_compact",
+    "kbo_log_rm_max_cdf", "kbo_random_match_threshold", "kbo_derandomize_ms_vec", "kbo_translate_ms_vec",
+    "kbo_run_lengths_gapped", "kbo_relative_to_ref", "kbo_matches", "kbo_matches_batch", "kbo_matches_batch_device",
+    "kbo_find_batch", "kbo_map_unrefined", "kbo_set_profile_counters", "kbo_get_ms_counters", "kbo_set_chunk_len",
+    "kbo_kernel_launch_count", "kbo_last_kernel_ms", "kbo_set_kernel_timing", "kbo_collect_kernel_times",
+    "kbo_measure_random_sector_rate",
+]
+
+
+class KboPanic(RuntimeError):
+    """Raised where the reference implementation would panic (or on a CUDA failure)."""
+
+    def __init__(self, status, message):
+        super().__init__("kbo_b200 status %d (%s): %s" % (status, STATUS_NAMES.get(status, "?"), message))
+        self.status = status
+
+
+class BuildOptsC(C.Structure):
+    _fields_ = [("k", C.c_uint32), ("add_revcomp", C.c_int32), ("num_threads", C.c_uint32),
+                ("prefix_precalc", C.c_uint32), ("build_select", C.c_int32), ("mem_gb", C.c_uint32),
+                ("dedup_batches", C.c_int32), ("temp_dir", C.c_char_p)]
+
+
+class RleC(C.Structure):
+    _fields_ = [(n, C.c_uint64) for n in ("start", "end", "matches", "mismatches", "jumps", "gap_bases", "gap_opens")]
+
+
+class MsCountersC(C.Structure):
+    _fields_ = [(n, C.c_uint64) for n in ("extend_attempts", "extend_split_sector", "contractions",
+                                          "contraction_extra_words", "bases_processed", "bases_emitted",
+                                          "emit_extend_attempts", "emit_extend_split_sector", "emit_contractions",
+                                          "emit_contraction_extra_words")]
+
+
+def load_library():
+    """Loads kbo_b200/libkbo_b200.so; raises loudly when it is missing (no fallback exists)."""
+    global _lib
+    if _lib is not None:
+        return _lib
+    if not os.path.exists(_LIB_PATH):
+        raise RuntimeError("kbo_b200: %s is missing -- build it with `python -m kbo_b200.build` "
+                           "(there is no CPU fallback)" % _LIB_PATH)
+    L = C.CDLL(_LIB_PATH)
+    L.kbo_last_error_message.restype = C.c_char_p
+    L.kbo_device_count.argtypes = [C.POINTER(C.c_int)]
+    L.kbo_default_build_opts.argtypes = [C.POINTER(BuildOptsC)]
+    L.kbo_alloc_pinned.argtypes = [C.c_size_t, C.POINTER(C.c_void_p)]
+    L.kbo_free_pinned.argtypes = [C.c_void_p]
+    L.kbo_index_build.argtypes = [C.POINTER(u8p), u64p, C.c_uint64, C.POINTER(BuildOptsC), C.c_int,
+                                  C.POINTER(C.c_void_p)]
+    L.kbo_index_from_parts.argtypes = [C.c_uint32, C.c_uint64, C.c_uint64, C.POINTER(u64p), u8p, C.c_int,
+                                       C.POINTER(C.c_void_p)]
+    L.kbo_index_free.argtypes = [C.c_void_p]
+    L.kbo_index_free.restype = None
+    L.kbo_index_k.argtypes = [C.c_void_p]
+    L.kbo_index_k.restype = C.c_uint32
+    for f in ("kbo_index_n_kmers", "kbo_index_n_sets", "kbo_index_device_bytes"):
+        getattr(L, f).argtypes = [C.c_void_p]
+        getattr(L, f).restype = C.c_uint64
+    L.kbo_index_device.argtypes = [C.c_void_p]
+    L.kbo_index_export_parts.argtypes = [C.c_void_p, C.POINTER(u64p), u8p, u64p]
+    L.kbo_index_access_kmer.argtypes = [C.c_void_p, C.c_uint64, u8p]
+    L.kbo_index_search.argtypes = [C.c_void_p, u8p, C.c_uint64, C.POINTER(C.c_int), u64p, u64p]
+    L.kbo_query_sbwt.argtypes = [C.c_void_p, u8p, C.c_uint64, u64p, u64p, u64p]
+    L.kbo_query_sbwt_batch_compact.argtypes = [C.c_void_p, u8p, u64p, C.c_uint64, u8p, u32p, u32p]
+    L.kbo_log_rm_max_cdf.argtypes = [C.c_uint64, C.c_uint64, C.c_uint64, C.POINTER(C.c_double)]
+    L.kbo_random_match_threshold.argtypes = [C.c_uint64, C.c_uint64, C.c_uint64, C.c_double, u64p]
+    L.kbo_derandomize_ms_vec.argtypes = [u64p, C.c_uint64, C.c_uint64, C.c_uint64, i64p, C.c_int]
+    L.kbo_translate_ms_vec.argtypes = [i64p, C.c_uint64, C.c_uint64, C.c_uint64, u8p, C.c_int]
+    L.kbo_run_lengths_gapped.argtypes = [u8p, C.c_uint64, C.c_uint64, C.POINTER(RleC), C.c_uint64, u64p]
+    L.kbo_relative_to_ref.argtypes = [u8p, u8p, C.c_uint64, u8p]
+    L.kbo_matches.argtypes = [C.c_void_p, u8p, C.c_uint64, C.c_double, u8p]
+    L.kbo_matches_batch.argtypes = [C.c_void_p, u8p, u64p, C.c_uint64, C.c_double, u8p]
+    L.kbo_matches_batch_device.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, u64p, C.c_uint64, C.c_double,
+                                           C.c_void_p, C.c_void_p]
+    L.kbo_find_batch.argtypes = [C.c_void_p, u8p, u64p, C.c_uint64, C.c_double, C.c_uint64, C.POINTER(RleC),
+                                 C.c_uint64, u64p]
+    L.kbo_map_unrefined.argtypes = [C.c_void_p, u8p, C.c_uint64, C.c_double, C.c_int, u8p]
+    L.kbo_set_profile_counters.argtypes = [C.c_int]
+    L.kbo_get_ms_counters.argtypes = [C.c_void_p, C.POINTER(MsCountersC)]
+    L.kbo_set_chunk_len.argtypes = [C.c_uint32]
+    L.kbo_kernel_launch_count.restype = C.c_uint64
+    L.kbo_last_kernel_ms.argtypes = [C.c_void_p]
+    L.kbo_last_kernel_ms.restype = C.c_float
+    L.kbo_set_kernel_timing.argtypes = [C.c_int]
+    L.kbo_collect_kernel_times.argtypes = [C.c_void_p, C.c_void_p, C.POINTER(C.c_double), u64p]
+    L.kbo_measure_random_sector_rate.argtypes = [C.c_int, C.c_uint64, C.c_int, C.POINTER(C.c_double)]
+    _lib = L
+    return L
+
+
+def _check(rc):
+    if rc != 0:
+        raise KboPanic(rc, load_library().kbo_last_error_message().decode())
+
+
+def _p(a, ty):
+    return a.ctypes.data_as(C.POINTER(ty))
+
+
+def _u8(x):
+    if isinstance(x, (bytes, bytearray)):
+        return np.frombuffer(bytes(x), dtype=np.uint8)
+    if isinstance(x, str):
+        return np.frombuffer(x.encode(), dtype=np.uint8)
+    return np.ascontiguousarray(x, dtype=np.uint8)
+
+
+def csr(queries):
+    """List of sequences -> (concat uint8 array, offsets uint64 array)."""
+    qs = [_u8(q) for q in queries]
+    offsets = np.zeros(len(qs) + 1, dtype=np.uint64)
+    if qs:
+        offsets[1:] = np.cumsum([len(q) for q in qs])
+    concat = np.concatenate(qs) if qs else np.zeros(0, dtype=np.uint8)
+    return np.ascontiguousarray(concat), offsets
+
+
+# ------------------------------------------------------------------ option structs (lib.rs:259-466) ---
+@dataclass
+class BuildOpts:
+    k: int = 31
+    add_revcomp: bool = False
+    num_threads: int = 1
+    prefix_precalc: int = 8
+    build_select: bool = False
+    mem_gb: int = 4
+    dedup_batches: bool = False
+    temp_dir: Optional[str] = None
+
+
+@dataclass
+class MatchOpts:
+    max_error_prob: float = 0.0000001
+
+
+@dataclass
+class FindOpts:
+    max_error_prob: float = 0.0000001
+    max_gap_len: int = 0
+
+
+@dataclass
+class MapOpts:
+    max_error_prob: float = 0.0000001
+    fill_gaps: bool = True
+    call_variants: bool = True
+    format: bool = True
+    sbwt_build_opts: BuildOpts = field(default_factory=lambda: BuildOpts(build_select=True))
+
+
+@dataclass(frozen=True)
+class RLE:
+    start: int
+    end: int
+    matches: int
+    mismatches: int
+    jumps: int
+    gap_bases: int
+    gap_opens: int
+
+
+# ------------------------------------------------------------------------------------- index ---
+class Index:
+    """(SbwtIndexVariant::SubsetMatrix, LcsArray) resident on one GPU."""
+
+    def __init__(self, handle):
+        self._h = C.c_void_p(handle)
+        L = load_library()
+        self.k = L.kbo_index_k(self._h)
+        self.n_kmers = L.kbo_index_n_kmers(self._h)
+        self.n_sets = L.kbo_index_n_sets(self._h)
+        self.device = L.kbo_index_device(self._h)
+        self.device_bytes = L.kbo_index_device_bytes(self._h)
+
+    def close(self):
+        if self._h:
+            load_library().kbo_index_free(self._h)
+            self._h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def export_parts(self):
+        nw = (self.n_sets + 63) // 64
+        rows = [np.zeros(nw, dtype=np.uint64) for _ in range(4)]
+        lcs = np.zeros(self.n_sets, dtype=np.uint8)
+        Cc = np.zeros(4, dtype=np.uint64)
+        ptrs = (u64p * 4)(*[_p(r, C.c_uint64) for r in rows])
+        _check(load_library().kbo_index_export_parts(self._h, ptrs, _p(lcs, C.c_uint8), _p(Cc, C.c_uint64)))
+        return rows, lcs, Cc
+
+    def access_kmer(self, colex):
+        out = np.zeros(self.k, dtype=np.uint8)
+        _check(load_library().kbo_index_access_kmer(self._h, colex, _p(out, C.c_uint8)))
+        return out.tobytes()
+
+    def search(self, pattern):
+        p = _u8(pattern)
+        found, l, r = C.c_int(0), C.c_uint64(0), C.c_uint64(0)
+        _check(load_library().kbo_index_search(self._h, _p(p, C.c_uint8), len(p), C.byref(found), C.byref(l),
+                                               C.byref(r)))
+        return (l.value, r.value) if found.value else None
+
+    def ms_counters(self):
+        c = MsCountersC()
+        _check(load_library().kbo_get_ms_counters(self._h, C.byref(c)))
+        return {n: int(getattr(c, n)) for n, _ in MsCountersC._fields_}
+
+    def last_kernel_ms(self):
+        return float(load_library().kbo_last_kernel_ms(self._h))
+
+
+def build(seq_data, build_opts=None, device=0):
+    """kbo::build (lib.rs:501-506) / index::build_sbwt_from_vecs (index.rs:56-99)."""
+    L = load_library()
+    o = build_opts or BuildOpts()
+    seqs = [_u8(s) for s in seq_data]
+    n = len(seqs)
+    ptrs = (u8p * max(n, 1))(*[_p(s, C.c_uint8) for s in seqs])
+    lens = np.array([len(s) for s in seqs], dtype=np.uint64)
+    co = BuildOptsC(o.k, int(o.add_revcomp), o.num_threads, o.prefix_precalc, int(o.build_select), o.mem_gb,
+                    int(o.dedup_batches), o.temp_dir.encode() if o.temp_dir else None)
+    h = C.c_void_p()
+    _check(L.kbo_index_build(ptrs, _p(lens, C.c_uint64), n, C.byref(co), device, C.byref(h)))
+    return Index(h.value)
+
+
+def index_from_parts(k, n_sets, n_kmers, rows, lcs, device=0):
+    L = load_library()
+    rows = [np.ascontiguousarray(r, dtype=np.uint64) for r in rows]
+    lcs = _u8(lcs)
+    ptrs = (u64p * 4)(*[_p(r, C.c_uint64) for r in rows])
+    h = C.c_void_p()
+    _check(L.kbo_index_from_parts(k, n_sets, n_kmers, ptrs, _p(lcs, C.c_uint8), device, C.byref(h)))
+    return Index(h.value)
+
+
+# -------------------------------------------------------------------------------- index.rs ---
+def query_sbwt(query, index, intervals=True):
+    """index::query_sbwt (index.rs:243-256): (d, l, r) arrays, one entry per query base."""
+    q = _u8(query)
+    n = len(q)
+    d = np.zeros(max(n, 1), dtype=np.uint64)
+    l = np.zeros(max(n, 1), dtype=np.uint64) if intervals else None
+    r = np.zeros(max(n, 1), dtype=np.uint64) if intervals else None
+    _check(load_library().kbo_query_sbwt(index._h, _p(q, C.c_uint8), n, _p(d, C.c_uint64),
+                                         _p(l, C.c_uint64) if intervals else None,
+                                         _p(r, C.c_uint64) if intervals else None))
+    return (d[:n], l[:n], r[:n]) if intervals else (d[:n], None, None)
+
+
+def query_sbwt_batch(queries, index, intervals=True):
+    concat, offsets = csr(queries)
+    n = len(concat)
+    d = np.zeros(max(n, 1), dtype=np.uint8)
+    l = np.zeros(max(n, 1), dtype=np.uint32) if intervals else None
+    r = np.zeros(max(n, 1), dtype=np.uint32) if intervals else None
+    _check(load_library().kbo_query_sbwt_batch_compact(index._h, _p(concat, C.c_uint8), _p(offsets, C.c_uint64),
+                                                       len(queries), _p(d, C.c_uint8),
+                                                       _p(l, C.c_uint32) if intervals else None,
+                                                       _p(r, C.c_uint32) if intervals else None))
+    return d[:n], (l[:n] if intervals else None), (r[:n] if intervals else None), offsets
+
+
+# -------------------------------------------------------------------------- derandomize.rs ---
+def log_rm_max_cdf(t, alphabet_size, n_kmers):
+    out = C.c_double(0)
+    _check(load_library().kbo_log_rm_max_cdf(t, alphabet_size, n_kmers, C.byref(out)))
+    return out.value
+
+
+def random_match_threshold(k, n_kmers, alphabet_size, max_error_prob):
+    out = C.c_uint64(0)
+    _check(load_library().kbo_random_match_threshold(k, n_kmers, alphabet_size, max_error_prob, C.byref(out)))
+    return out.value
+
+
+def derandomize_ms_vec(noisy_ms, k, threshold, device=0):
+    ms = np.ascontiguousarray(noisy_ms, dtype=np.uint64)
+    out = np.zeros(max(len(ms), 1), dtype=np.int64)
+    _check(load_library().kbo_derandomize_ms_vec(_p(ms, C.c_uint64), len(ms), k, threshold, _p(out, C.c_int64),
+                                                 device))
+    return out[:len(ms)]
+
+
+# ---------------------------------------------------------------------------- translate.rs ---
+def translate_ms_vec(derand_ms, k, threshold, device=0):
+    d = np.ascontiguousarray(derand_ms, dtype=np.int64)
+    out = np.zeros(max(len(d), 1), dtype=np.uint8)
+    _check(load_library().kbo_translate_ms_vec(_p(d, C.c_int64), len(d), k, threshold, _p(out, C.c_uint8), device))
+    return out[:len(d)].tobytes()
+
+
+# ------------------------------------------------------------------------------- format.rs ---
+def run_lengths_gapped(aln, max_gap_len):
+    a = _u8(aln)
+    cap = len(a) + 1
+    buf = (RleC * cap)()
+    n = C.c_uint64(0)
+    _check(load_library().kbo_run_lengths_gapped(_p(a, C.c_uint8), len(a), max_gap_len, buf, cap, C.byref(n)))
+    return [RLE(*[int(getattr(buf[i], f)) for f, _ in RleC._fields_]) for i in range(n.value)]
+
+
+def run_lengths(aln):
+    return run_lengths_gapped(aln, 0)
+
+
+def relative_to_ref(ref_seq, alignment):
+    r, a = _u8(ref_seq), _u8(alignment)
+    n = min(len(r), len(a))
+    out = np.zeros(max(n, 1), dtype=np.uint8)
+    _check(load_library().kbo_relative_to_ref(_p(r, C.c_uint8), _p(a, C.c_uint8), n, _p(out, C.c_uint8)))
+    return out[:n].tobytes()
+
+
+# ---------------------------------------------------------------------------------- lib.rs ---
+def matches(query_seq, index, match_opts=None):
+    """kbo::matches (lib.rs:612-628) -> alignment characters as bytes ('M', '-', 'X', 'R')."""
+    o = match_opts or MatchOpts()
+    q = _u8(query_seq)
+    out = np.zeros(max(len(q), 1), dtype=np.uint8)
+    _check(load_library().kbo_matches(index._h, _p(q, C.c_uint8), len(q), o.max_error_prob, _p(out, C.c_uint8)))
+    return out[:len(q)].tobytes()
+
+
+def matches_batch(queries, index, match_opts=None):
+    """matches() for many queries in one launch sequence; returns a list of bytes."""
+    o = match_opts or MatchOpts()
+    concat, offsets = csr(queries)
+    out = matches_csr(concat, offsets, index, o.max_error_prob)
+    return [out[int(offsets[i]):int(offsets[i + 1])].tobytes() for i in range(len(queries))]
+
+
+def matches_csr(concat, offsets, index, max_error_prob=0.0000001, out=None):
+    """CSR form used by bench.py: host arrays in, host array out (copies inside the call)."""
+    if out is None:
+        out = np.zeros(max(len(concat), 1), dtype=np.uint8)
+    _check(load_library().kbo_matches_batch(index._h, _p(concat, C.c_uint8), _p(offsets, C.c_uint64),
+                                            len(offsets) - 1, max_error_prob, _p(out, C.c_uint8)))
+    return out
+
+
+def find(query_seq, index, find_opts=None):
+    """kbo::find (lib.rs:808-821) -> list of RLE."""
+    return find_batch([query_seq], index, find_opts)[0]
+
+
+def find_batch(queries, index, find_opts=None):
+    o = find_opts or FindOpts()
+    concat, offsets = csr(queries)
+    cap = len(concat) + 1
+    buf = (RleC * cap)()
+    roff = np.zeros(len(queries) + 1, dtype=np.uint64)
+    _check(load_library().kbo_find_batch(index._h, _p(concat, C.c_uint8), _p(offsets, C.c_uint64), len(queries),
+                                         o.max_error_prob, o.max_gap_len, buf, cap, _p(roff, C.c_uint64)))
+    res = []
+    for i in range(len(queries)):
+        res.append([RLE(*[int(getattr(buf[j], f)) for f, _ in RleC._fields_])
+                    for j in range(int(roff[i]), int(roff[i + 1]))])
+    return res
+
+
+class FindBuffers:
+    """Reusable output buffers for find_csr (avoids reallocating per call in a timed loop)."""
+
+    def __init__(self, n_queries, cap=None):
+        self.cap = cap or (8 * n_queries + 1024)
+        self.rle = (RleC * self.cap)()
+        self.rle_offsets = np.zeros(n_queries + 1, dtype=np.uint64)
+
+
+def find_csr(concat, offsets, index, find_opts=None, buffers=None):
+    """kbo::find for a CSR batch with host arrays in (e.g. pinned) and RLE records out.
+    Returns (FindBuffers, n_rle): RLEs of query i are buffers.rle[rle_offsets[i]:rle_offsets[i+1]]."""
+    o = find_opts or FindOpts()
+    nq = len(offsets) - 1
+    buf = buffers or FindBuffers(nq)
+    rc = load_library().kbo_find_batch(index._h, _p(concat, C.c_uint8), _p(offsets, C.c_uint64), nq,
+                                       o.max_error_prob, o.max_gap_len, buf.rle, buf.cap, _p(buf.rle_offsets, C.c_uint64))
+    if rc == 11:  # KBO_ERR_BUFFER_TOO_SMALL: grow once and retry
+        buf = FindBuffers(nq, cap=int(buf.rle_offsets[nq]) + 1024)
+        rc = load_library().kbo_find_batch(index._h, _p(concat, C.c_uint8), _p(offsets, C.c_uint64), nq,
+                                           o.max_error_prob, o.max_gap_len, buf.rle, buf.cap,
+                                           _p(buf.rle_offsets, C.c_uint64))
+    _check(rc)
+    return buf, int(buf.rle_offsets[nq])
+
+
+def map(ref_seq, query_index, map_opts=None):
+    """kbo::map (lib.rs:720-761).  Refinement (fill_gaps / call_variants) is not on the device path yet:
+    requesting it raises NotImplementedError instead of silently returning an unrefined alignment."""
+    o = map_opts or MapOpts()
+    if o.fill_gaps or o.call_variants:
+        raise NotImplementedError("map(): fill_gaps / call_variants are 'next' rows (SURVEY 8f); "
+                                  "use MapOpts(fill_gaps=False, call_variants=False)")
+    r = _u8(ref_seq)
+    out = np.zeros(max(len(r), 1), dtype=np.uint8)
+    _check(load_library().kbo_map_unrefined(query_index._h, _p(r, C.c_uint8), len(r), o.max_error_prob,
+                                            int(o.format), _p(out, C.c_uint8)))
+    return out[:len(r)].tobytes()
+
+
+# ---------------------------------------------------------------------------- instrumentation ---
+def set_profile_counters(enabled):
+    _check(load_library().kbo_set_profile_counters(int(enabled)))
+
+
+def set_chunk_len(chunk_len):
+    _check(load_library().kbo_set_chunk_len(int(chunk_len)))
+
+
+def kernel_launch_count():
+    return int(load_library().kbo_kernel_launch_count())
+
+
+def set_kernel_timing(enabled):
+    _check(load_library().kbo_set_kernel_timing(int(enabled)))
+
+
+def collect_kernel_times(index, stream=0):
+    """After synchronising `stream`: ({'pack','ms','derand_translate'} summed ms, number of timed calls)."""
+    sums = (C.c_double * 3)()
+    n = C.c_uint64(0)
+    _check(load_library().kbo_collect_kernel_times(index._h, C.c_void_p(stream), sums, C.byref(n)))
+    return {"pack": sums[0], "ms": sums[1], "derand_translate": sums[2]}, int(n.value)
+
+
+def measure_random_sector_rate(buffer_bytes, dependent, device=0):
+    out = C.c_double(0)
+    _check(load_library().kbo_measure_random_sector_rate(device, buffer_bytes, int(dependent), C.byref(out)))
+    return out.value
+
+
+def matches_device(index, d_concat_ptr, d_offsets_ptr, host_offsets, d_out_ptr, max_error_prob=0.0000001, stream=0):
+    """kbo_matches_batch_device: raw device pointers (ints) on the index's device; async on `stream`."""
+    off = np.ascontiguousarray(host_offsets, dtype=np.uint64)
+    _check(load_library().kbo_matches_batch_device(index._h, C.c_void_p(d_concat_ptr), C.c_void_p(d_offsets_ptr),
+                                                   _p(off, C.c_uint64), len(off) - 1, max_error_prob,
+                                                   C.c_void_p(d_out_ptr), C.c_void_p(stream)))
+
+
+def device_count():
+    n = C.c_int(0)
+    rc = load_library().kbo_device_count(C.byref(n))
+    return n.value if rc == 0 else 0

@@ -1,0 +1,983 @@
+// ===========================================================================
+// kbo_b200/csrc/capi.cu -- implementation of include/kbo_b200.h
+//
+// Host orchestration of the hot path: stage a CSR batch of queries, run
+// K0 (pack) -> K1 (matching statistics) -> K2 (derandomize + translate) on one
+// stream, copy the result back.  No CPU fallback exists: every compute entry
+// point needs a CUDA device and fails with KBO_ERR_CUDA otherwise.
+// ===========================================================================
+#include <atomic>
+#include <cmath>
+#include <cstring>
+#include <mutex>
+#include <string>
+#include <unordered_map>
+#include <vector>
+
+#include "../../include/kbo_b200.h"
+#include "kernels.cuh"
+#include "host_layout.hpp"
+#include "sbwt_host.hpp"
+
+using namespace kbo_b200;
+
+// ---------------------------------------------------------------------------
+// errors, globals
+// ---------------------------------------------------------------------------
+static thread_local std::string g_err;
+static std::atomic<uint64_t> g_launches(0);
+static std::atomic<int> g_profile_counters(0);
+static std::atomic<uint32_t> g_chunk_len(0);
+static std::atomic<int> g_kernel_timing(0);
+
+static int fail(int code, const std::string& msg) {
+    g_err = msg;
+    return code;
+}
+#define CUDA_TRY(expr)                                                                                        \
+    do {                                                                                                      \
+        cudaError_t _e = (expr);                                                                              \
+        if (_e != cudaSuccess)                                                                                \
+            return fail(_e == cudaErrorMemoryAllocation ? KBO_ERR_OOM : KBO_ERR_CUDA,                         \
+                        std::string("CUDA error: ") + cudaGetErrorString(_e) + " at " #expr);                 \
+    } while (0)
+#define LAUNCHED() (g_launches.fetch_add(1, std::memory_order_relaxed))
+
+// ---------------------------------------------------------------------------
+// device buffers / workspaces
+// ---------------------------------------------------------------------------
+struct DevBuf {
+    void* p = nullptr;
+    size_t cap = 0;
+    cudaError_t ensure(size_t bytes, cudaStream_t st) {
+        if (bytes <= cap) return cudaSuccess;
+        if (p) {
+            cudaError_t e = cudaStreamSynchronize(st);
+            if (e != cudaSuccess) return e;
+            cudaFree(p);
+            p = nullptr;
+            cap = 0;
+        }
+        size_t want = bytes + bytes / 4 + 256;
+        cudaError_t e = cudaMalloc(&p, want);
+        if (e != cudaSuccess) { p = nullptr; return e; }
+        cap = want;
+        return cudaSuccess;
+    }
+    void release() { if (p) cudaFree(p); p = nullptr; cap = 0; }
+    template <typename T> T* as() const { return reinterpret_cast<T*>(p); }
+};
+
+struct Workspace {
+    cudaStream_t stream = nullptr;
+    bool own_stream = false;
+    cudaEvent_t ev0 = nullptr, ev1 = nullptr;
+    DevBuf ascii, offsets, pack, inv, sep, wq, ms, l, r, out, out2, out3, tmp64, tmp64b, tmp32, tmp32b, counters;
+    std::vector<cudaEvent_t> timing;  // 4 events per timed call (before K0, after K0, after K1, after K2)
+    size_t timed_calls = 0;
+    void destroy() {
+        for (cudaEvent_t e : timing) cudaEventDestroy(e);
+        DevBuf* all[] = {&ascii, &offsets, &pack, &inv, &sep, &wq, &ms, &l, &r, &out, &out2, &out3,
+                         &tmp64, &tmp64b, &tmp32, &tmp32b, &counters};
+        for (DevBuf* b : all) b->release();
+        if (ev0) cudaEventDestroy(ev0);
+        if (ev1) cudaEventDestroy(ev1);
+        if (own_stream && stream) cudaStreamDestroy(stream);
+    }
+};
+
+struct PinnedBuf {
+    void* p = nullptr;
+    size_t cap = 0;
+};
+
+struct kbo_index {
+    int device = 0;
+    std::vector<PinnedBuf> pinned_pool;  // host staging for find (guarded by mu)
+    HostIndex host;
+    uint64_t* d_rank = nullptr;
+    uint8_t* d_lcs = nullptr;
+    uint64_t rank_stride = 0;
+    uint64_t device_bytes = 0;
+    IndexView view;
+    std::mutex mu;
+    std::vector<Workspace*> pool;                             // idle workspaces with their own stream
+    std::unordered_map<cudaStream_t, Workspace*> by_stream;  // workspaces bound to caller streams
+    kbo_ms_counters last_counters = {0, 0, 0, 0, 0, 0, 0, 0, 0, 0};
+    float last_kernel_ms = 0.f;
+};
+
+static int acquire_ws(kbo_index* ix, Workspace** out) {
+    {
+        std::lock_guard<std::mutex> g(ix->mu);
+        if (!ix->pool.empty()) {
+            *out = ix->pool.back();
+            ix->pool.pop_back();
+            return KBO_OK;
+        }
+    }
+    Workspace* ws = new Workspace();
+    ws->own_stream = true;
+    CUDA_TRY(cudaStreamCreateWithFlags(&ws->stream, cudaStreamNonBlocking));
+    CUDA_TRY(cudaEventCreate(&ws->ev0));
+    CUDA_TRY(cudaEventCreate(&ws->ev1));
+    *out = ws;
+    return KBO_OK;
+}
+static void release_ws(kbo_index* ix, Workspace* ws) {
+    std::lock_guard<std::mutex> g(ix->mu);
+    ix->pool.push_back(ws);
+}
+static int stream_ws(kbo_index* ix, cudaStream_t st, Workspace** out) {
+    std::lock_guard<std::mutex> g(ix->mu);
+    auto it = ix->by_stream.find(st);
+    if (it != ix->by_stream.end()) { *out = it->second; return KBO_OK; }
+    Workspace* ws = new Workspace();
+    ws->stream = st;
+    ws->own_stream = false;
+    ix->by_stream[st] = ws;
+    *out = ws;
+    return KBO_OK;
+}
+
+struct DeviceGuard {
+    int prev = -1;
+    bool ok = true;
+    explicit DeviceGuard(int dev) {
+        if (cudaGetDevice(&prev) != cudaSuccess) { ok = false; return; }
+        if (prev != dev && cudaSetDevice(dev) != cudaSuccess) ok = false;
+    }
+    ~DeviceGuard() { if (prev >= 0) cudaSetDevice(prev); }
+};
+
+// ---------------------------------------------------------------------------
+// host-only pieces of the path (derandomize.rs:91-145: f64, once per index)
+// ---------------------------------------------------------------------------
+static double host_log_rm_max_cdf(uint64_t t, uint64_t alphabet_size, uint64_t n_kmers) {
+    // n_kmers * ln_1p(-(exp(ln 1 - ln s))^(t+1))      derandomize.rs:99
+    const double q = std::exp(std::log(1.0) - std::log((double)alphabet_size));
+    return (double)n_kmers * std::log1p(-__builtin_powi(q, (int)t + 1));
+}
+
+static int host_threshold(uint64_t k, uint64_t n_kmers, uint64_t alphabet, double p, uint64_t* out) {
+    if (k == 0) return fail(KBO_ERR_BAD_K, "k must be > 0 (derandomize.rs:133)");
+    if (n_kmers == 0) return fail(KBO_ERR_BAD_ARGUMENT, "n_kmers must be > 0 (derandomize.rs:134)");
+    if (alphabet == 0) return fail(KBO_ERR_BAD_ARGUMENT, "alphabet_size must be > 0 (derandomize.rs:135)");
+    if (!(p <= 1.0) || !(p > 0.0)) return fail(KBO_ERR_BAD_PROB, "0 < max_error_prob <= 1 (derandomize.rs:136-137)");
+    const double bound = std::log1p(-p);
+    for (uint64_t i = 1; i < k; ++i) {
+        if (host_log_rm_max_cdf(i, alphabet, n_kmers) > bound) { *out = i; return KBO_OK; }
+    }
+    *out = k;
+    return KBO_OK;
+}
+
+// ---------------------------------------------------------------------------
+// index upload: SubsetMatrix rows + LCS -> interleaved rank words + padded LCS
+// ---------------------------------------------------------------------------
+static int upload_index(kbo_index* ix) {
+    const HostIndex& h = ix->host;
+    const uint64_t n = h.n_sets;
+    if (n >= (1ull << 32) - 64) return fail(KBO_ERR_INDEX_TOO_LARGE, "n_sets must be < 2^32");
+    if (h.k == 0 || h.k > 127) return fail(KBO_ERR_BAD_K, "device LCS compare needs 1 <= k <= 127");
+    DeviceLayout lay;
+    build_device_layout(h, &lay);
+    const std::vector<uint64_t>& rank = lay.rank;
+    const std::vector<uint8_t>& lcs = lay.lcs;
+    const uint64_t stride = lay.stride;
+    CUDA_TRY(cudaMalloc((void**)&ix->d_rank, rank.size() * 8));
+    CUDA_TRY(cudaMalloc((void**)&ix->d_lcs, lcs.size()));
+    CUDA_TRY(cudaMemcpy(ix->d_rank, rank.data(), rank.size() * 8, cudaMemcpyHostToDevice));
+    CUDA_TRY(cudaMemcpy(ix->d_lcs, lcs.data(), lcs.size(), cudaMemcpyHostToDevice));
+    ix->rank_stride = stride;
+    ix->device_bytes = rank.size() * 8 + lcs.size();
+    ix->view.rank = ix->d_rank;
+    ix->view.rank_stride = stride;
+    ix->view.lcs = ix->d_lcs;
+    ix->view.n = (uint32_t)n;
+    ix->view.k = h.k;
+    return KBO_OK;
+}
+
+// ---------------------------------------------------------------------------
+// batch geometry
+// ---------------------------------------------------------------------------
+static Geometry make_geometry(uint64_t total, uint64_t nq) { return kbo_b200::make_geometry(total, nq, g_chunk_len.load()); }
+
+static int check_offsets(const uint64_t* offsets, uint64_t nq, uint64_t min_len, uint64_t* total) {
+    if (!offsets) return fail(KBO_ERR_BAD_ARGUMENT, "offsets is null");
+    if (nq == 0) return fail(KBO_ERR_EMPTY_INPUT, "no queries (index.rs:248 assert!(!query.is_empty()))");
+    for (uint64_t i = 0; i < nq; ++i) {
+        if (offsets[i + 1] < offsets[i]) return fail(KBO_ERR_BAD_ARGUMENT, "offsets must be non-decreasing");
+        const uint64_t len = offsets[i + 1] - offsets[i];
+        if (len == 0) return fail(KBO_ERR_EMPTY_INPUT, "empty query (index.rs:248 assert!(!query.is_empty()))");
+        if (len < min_len) return fail(KBO_ERR_TOO_SHORT, "query shorter than 3 bases (derandomize.rs:276 len > 2)");
+    }
+    *total = offsets[nq] - offsets[0];
+    return KBO_OK;
+}
+
+// ---------------------------------------------------------------------------
+// kernel sequences (all on ws->stream)
+// ---------------------------------------------------------------------------
+static int run_pack(Workspace* ws, const uint8_t* d_ascii, const uint64_t* d_offsets, uint64_t nq, const Geometry& g,
+                    QueryView* qv) {
+    cudaStream_t st = ws->stream;
+    CUDA_TRY(ws->pack.ensure(g.n_words * 8, st));
+    CUDA_TRY(ws->inv.ensure(g.n_words * 4, st));
+    CUDA_TRY(ws->sep.ensure(g.n_words * 4, st));
+    CUDA_TRY(ws->wq.ensure(g.n_words * 4, st));
+    qv->pack = ws->pack.as<uint64_t>();
+    qv->inv = ws->inv.as<uint32_t>();
+    qv->sep = ws->sep.as<uint32_t>();
+    qv->wq = ws->wq.as<uint32_t>();
+    qv->Lp = g.Lp;
+    qv->n_words = g.n_words;
+    const unsigned threads = 128;
+    const unsigned blocks = (unsigned)((g.n_words + threads - 1) / threads);
+    pack_queries_kernel<<<blocks, threads, 0, st>>>(d_ascii, d_offsets, nq, *qv, ws->pack.as<uint64_t>(),
+                                                    ws->inv.as<uint32_t>(), ws->sep.as<uint32_t>(),
+                                                    ws->wq.as<uint32_t>());
+    LAUNCHED();
+    CUDA_TRY(cudaGetLastError());
+    return KBO_OK;
+}
+
+static int run_ms(kbo_index* ix, Workspace* ws, const QueryView& qv, const Geometry& g, bool intervals) {
+    cudaStream_t st = ws->stream;
+    CUDA_TRY(ws->ms.ensure(g.ms_bytes, st));
+    if (intervals) {
+        CUDA_TRY(ws->l.ensure(g.n_words * 32 * 4, st));
+        CUDA_TRY(ws->r.ensure(g.n_words * 32 * 4, st));
+    }
+    const bool count = g_profile_counters.load() != 0;
+    if (count) {
+        CUDA_TRY(ws->counters.ensure(CNT_N * 8, st));
+        CUDA_TRY(cudaMemsetAsync(ws->counters.p, 0, CNT_N * 8, st));
+    }
+    MsParams mp;
+    mp.ix = ix->view;
+    mp.q = qv;
+    mp.chunk_len = g.chunk_len;
+    mp.n_chunks = g.n_chunks;
+    mp.ms = ws->ms.as<uint8_t>();
+    mp.l_out = intervals ? ws->l.as<uint32_t>() : nullptr;
+    mp.r_out = intervals ? ws->r.as<uint32_t>() : nullptr;
+    mp.counters = count ? ws->counters.as<unsigned long long>() : nullptr;
+    const unsigned threads = 256;
+    const unsigned blocks = (unsigned)((g.n_chunks + threads - 1) / threads);
+    if (intervals) {
+        if (count) ms_kernel<true, true><<<blocks, threads, 0, st>>>(mp);
+        else ms_kernel<true, false><<<blocks, threads, 0, st>>>(mp);
+    } else {
+        if (count) ms_kernel<false, true><<<blocks, threads, 0, st>>>(mp);
+        else ms_kernel<false, false><<<blocks, threads, 0, st>>>(mp);
+    }
+    LAUNCHED();
+    CUDA_TRY(cudaGetLastError());
+    return KBO_OK;
+}
+
+static int run_derand_translate(kbo_index* ix, Workspace* ws, const QueryView& qv, const Geometry& g, uint32_t thr,
+                                uint8_t* d_out, uint64_t off0) {
+    TrParams tp;
+    tp.ms = ws->ms.as<uint8_t>();
+    tp.q = qv;
+    tp.k = ix->host.k;
+    tp.thr = thr;
+    tp.out = d_out;
+    tp.off0 = off0;
+    tp.n_tiles = g.n_tiles;
+    const unsigned blocks = (unsigned)((g.n_tiles + K2_WARPS - 1) / K2_WARPS);
+    derand_translate_kernel<<<blocks, K2_WARPS * 32, 0, ws->stream>>>(tp);
+    LAUNCHED();
+    CUDA_TRY(cudaGetLastError());
+    return KBO_OK;
+}
+
+template <typename T>
+__global__ void unpad_kernel(const T* __restrict__ in, QueryView q, T* __restrict__ out) {
+    const uint64_t pp = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (pp >= q.Lp) return;
+    const uint32_t sw = __ldg(q.sep + (pp >> 5));
+    if ((sw >> (pp & 31)) & 1u) return;
+    const uint64_t nsep = __ldg(q.wq + (pp >> 5)) + __popc(sw & ((1u << (pp & 31)) - 1u));
+    out[pp - nsep] = in[pp];
+}
+
+static int fetch_counters(kbo_index* ix, Workspace* ws) {
+    if (!g_profile_counters.load() || !ws->counters.p) return KBO_OK;
+    unsigned long long h[CNT_N];
+    CUDA_TRY(cudaMemcpyAsync(h, ws->counters.p, sizeof(h), cudaMemcpyDeviceToHost, ws->stream));
+    CUDA_TRY(cudaStreamSynchronize(ws->stream));
+    std::lock_guard<std::mutex> g(ix->mu);
+    ix->last_counters.extend_attempts = h[CNT_ATTEMPTS];
+    ix->last_counters.extend_split_sector = h[CNT_SPLIT];
+    ix->last_counters.contractions = h[CNT_CONTRACT];
+    ix->last_counters.contraction_extra_words = h[CNT_EXTRA_LCS];
+    ix->last_counters.bases_processed = h[CNT_PROCESSED];
+    ix->last_counters.bases_emitted = h[CNT_EMITTED];
+    ix->last_counters.emit_extend_attempts = h[CNT_ATT_EMIT];
+    ix->last_counters.emit_extend_split_sector = h[CNT_SPLIT_EMIT];
+    ix->last_counters.emit_contractions = h[CNT_CON_EMIT];
+    ix->last_counters.emit_contraction_extra_words = h[CNT_EXTRA_EMIT];
+    return KBO_OK;
+}
+
+// matches for a batch whose inputs are already on the device (ws->stream)
+static int matches_device(kbo_index* ix, Workspace* ws, const uint8_t* d_concat, const uint64_t* d_offsets,
+                          uint64_t nq, const Geometry& g, uint32_t thr, uint8_t* d_out, uint64_t off0) {
+    QueryView qv;
+    cudaEvent_t* ev = nullptr;
+    if (g_kernel_timing.load() && ws->timed_calls < 512) {
+        const size_t need = (ws->timed_calls + 1) * 4;
+        while (ws->timing.size() < need) {
+            cudaEvent_t e;
+            CUDA_TRY(cudaEventCreate(&e));
+            ws->timing.push_back(e);
+        }
+        ev = ws->timing.data() + ws->timed_calls * 4;
+        ws->timed_calls++;
+    }
+    if (ev) CUDA_TRY(cudaEventRecord(ev[0], ws->stream));
+    int rc = run_pack(ws, d_concat, d_offsets, nq, g, &qv);
+    if (rc) return rc;
+    if (ev) CUDA_TRY(cudaEventRecord(ev[1], ws->stream));
+    rc = run_ms(ix, ws, qv, g, false);
+    if (rc) return rc;
+    if (ev) CUDA_TRY(cudaEventRecord(ev[2], ws->stream));
+    rc = run_derand_translate(ix, ws, qv, g, thr, d_out, off0);
+    if (rc) return rc;
+    if (ev) CUDA_TRY(cudaEventRecord(ev[3], ws->stream));
+    return KBO_OK;
+}
+
+// ---------------------------------------------------------------------------
+// random-sector load micro-benchmark (roofline denominators for L2 / HBM)
+// ---------------------------------------------------------------------------
+template <bool DEPENDENT>
+__global__ void __launch_bounds__(256) random_sector_kernel(const uint64_t* __restrict__ buf, uint32_t n_sectors,
+                                                            uint32_t iters, unsigned long long* sink) {
+    const uint32_t tid = blockIdx.x * blockDim.x + threadIdx.x;
+    uint32_t x = tid * 2654435761u + 12345u;
+    uint64_t acc = 0;
+    if (DEPENDENT) {
+        for (uint32_t i = 0; i < iters; ++i) {
+            x = x * 1664525u + 1013904223u;
+            const uint32_t s = (uint32_t)(((uint64_t)(x ^ (uint32_t)acc) * n_sectors) >> 32);
+            acc += __ldg(buf + (size_t)s * 4 + (x & 3));  // the next address depends on this value
+        }
+    } else {
+        for (uint32_t i = 0; i < iters; i += 8) {
+            uint64_t v[8];
+#pragma unroll
+            for (int j = 0; j < 8; ++j) {
+                x = x * 1664525u + 1013904223u;
+                const uint32_t s = (uint32_t)(((uint64_t)x * n_sectors) >> 32);
+                v[j] = __ldg(buf + (size_t)s * 4 + (x & 3));
+            }
+#pragma unroll
+            for (int j = 0; j < 8; ++j) acc += v[j];
+        }
+    }
+    if (acc == 0x123456789abcdefull) atomicAdd(sink, 1ull);
+}
+
+// ---------------------------------------------------------------------------
+// extern "C"
+// ---------------------------------------------------------------------------
+extern "C" {
+
+const char* kbo_last_error_message(void) { return g_err.c_str(); }
+
+int kbo_device_count(int* out) {
+    if (!out) return fail(KBO_ERR_BAD_ARGUMENT, "out is null");
+    int n = 0;
+    cudaError_t e = cudaGetDeviceCount(&n);
+    if (e != cudaSuccess) { *out = 0; return fail(KBO_ERR_CUDA, std::string("no CUDA device: ") + cudaGetErrorString(e)); }
+    *out = n;
+    return KBO_OK;
+}
+
+void kbo_default_build_opts(kbo_build_opts* o) {
+    if (!o) return;
+    o->k = 31;
+    o->add_revcomp = 0;
+    o->num_threads = 1;
+    o->prefix_precalc = 8;
+    o->build_select = 0;
+    o->mem_gb = 4;
+    o->dedup_batches = 0;
+    o->temp_dir = nullptr;
+}
+
+int kbo_alloc_pinned(size_t bytes, void** out) {
+    if (!out) return fail(KBO_ERR_BAD_ARGUMENT, "out is null");
+    CUDA_TRY(cudaHostAlloc(out, bytes ? bytes : 1, cudaHostAllocDefault));
+    return KBO_OK;
+}
+int kbo_free_pinned(void* p) {
+    if (p) CUDA_TRY(cudaFreeHost(p));
+    return KBO_OK;
+}
+
+static int finish_index(kbo_index* ix, int device, kbo_index** out) {
+    int ndev = 0;
+    if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev == 0) {
+        delete ix;
+        return fail(KBO_ERR_CUDA, "no CUDA device available (this library has no CPU fallback)");
+    }
+    if (device < 0 || device >= ndev) { delete ix; return fail(KBO_ERR_BAD_ARGUMENT, "device ordinal out of range"); }
+    ix->device = device;
+    DeviceGuard dg(device);
+    if (!dg.ok) { delete ix; return fail(KBO_ERR_CUDA, "cudaSetDevice failed"); }
+    int rc = upload_index(ix);
+    if (rc) { kbo_index_free(ix); return rc; }
+    *out = ix;
+    return KBO_OK;
+}
+
+int kbo_index_build(const uint8_t* const* seqs, const uint64_t* lens, uint64_t n_seqs, const kbo_build_opts* opts,
+                    int device, kbo_index** out) {
+    if (!out) return fail(KBO_ERR_BAD_ARGUMENT, "out is null");
+    *out = nullptr;
+    if (!seqs || !lens || n_seqs == 0) return fail(KBO_ERR_EMPTY_INPUT, "no input sequences (index.rs:60)");
+    kbo_build_opts o;
+    if (opts) o = *opts; else kbo_default_build_opts(&o);
+    if (o.k == 0 || o.k > KBO_MAX_K) return fail(KBO_ERR_BAD_K, "1 <= k <= 64 in this build");
+    kbo_index* ix = new kbo_index();
+    std::string err = build_host_index(seqs, lens, n_seqs, o.k, o.add_revcomp != 0, o.num_threads ? o.num_threads : 1,
+                                       &ix->host);
+    if (!err.empty()) { delete ix; return fail(KBO_ERR_INDEX_TOO_LARGE, err); }
+    return finish_index(ix, device, out);
+}
+
+int kbo_index_from_parts(uint32_t k, uint64_t n_sets, uint64_t n_kmers, const uint64_t* const rows[4],
+                         const uint8_t* lcs, int device, kbo_index** out) {
+    if (!out) return fail(KBO_ERR_BAD_ARGUMENT, "out is null");
+    *out = nullptr;
+    if (!rows || !lcs || !rows[0] || !rows[1] || !rows[2] || !rows[3]) return fail(KBO_ERR_BAD_ARGUMENT, "null part");
+    if (k == 0 || k > 127) return fail(KBO_ERR_BAD_K, "1 <= k <= 127");
+    if (n_sets == 0) return fail(KBO_ERR_EMPTY_INPUT, "n_sets == 0");
+    kbo_index* ix = new kbo_index();
+    HostIndex& h = ix->host;
+    h.k = k;
+    h.n_sets = n_sets;
+    h.n_kmers = n_kmers;
+    const size_t nw = (size_t)(n_sets + 63) / 64;
+    for (int c = 0; c < 4; ++c) {
+        h.rows[c].assign(nw + 1, 0);
+        std::memcpy(h.rows[c].data(), rows[c], nw * 8);
+        if (n_sets & 63) h.rows[c][nw - 1] &= ~0ull >> (64 - (n_sets & 63));
+    }
+    h.lcs.assign(lcs, lcs + n_sets);
+    h.finalize();
+    return finish_index(ix, device, out);
+}
+
+void kbo_index_free(kbo_index* ix) {
+    if (!ix) return;
+    {
+        DeviceGuard dg(ix->device);
+        for (Workspace* ws : ix->pool) { ws->destroy(); delete ws; }
+        for (auto& kv : ix->by_stream) { kv.second->destroy(); delete kv.second; }
+        for (PinnedBuf& pb : ix->pinned_pool) if (pb.p) cudaFreeHost(pb.p);
+        if (ix->d_rank) cudaFree(ix->d_rank);
+        if (ix->d_lcs) cudaFree(ix->d_lcs);
+    }
+    delete ix;
+}
+
+uint32_t kbo_index_k(const kbo_index* ix) { return ix ? ix->host.k : 0; }
+uint64_t kbo_index_n_kmers(const kbo_index* ix) { return ix ? ix->host.n_kmers : 0; }
+uint64_t kbo_index_n_sets(const kbo_index* ix) { return ix ? ix->host.n_sets : 0; }
+int kbo_index_device(const kbo_index* ix) { return ix ? ix->device : -1; }
+uint64_t kbo_index_device_bytes(const kbo_index* ix) { return ix ? ix->device_bytes : 0; }
+
+int kbo_index_export_parts(const kbo_index* ix, uint64_t* rows[4], uint8_t* lcs, uint64_t C_out[4]) {
+    if (!ix) return fail(KBO_ERR_BAD_ARGUMENT, "index is null");
+    const size_t nw = (size_t)(ix->host.n_sets + 63) / 64;
+    if (rows)
+        for (int c = 0; c < 4; ++c)
+            if (rows[c]) std::memcpy(rows[c], ix->host.rows[c].data(), nw * 8);
+    if (lcs) std::memcpy(lcs, ix->host.lcs.data(), (size_t)ix->host.n_sets);
+    if (C_out)
+        for (int c = 0; c < 4; ++c) C_out[c] = ix->host.C[c];
+    return KBO_OK;
+}
+
+int kbo_index_access_kmer(const kbo_index* ix, uint64_t colex, uint8_t* out_k) {
+    if (!ix || !out_k) return fail(KBO_ERR_BAD_ARGUMENT, "null argument");
+    if (colex >= ix->host.n_sets) return fail(KBO_ERR_PANIC, "access_kmer: colex rank out of range");
+    ix->host.access_kmer(colex, out_k);
+    return KBO_OK;
+}
+
+int kbo_index_search(const kbo_index* ix, const uint8_t* pattern, uint64_t len, int* found, uint64_t* l, uint64_t* r) {
+    if (!ix || !found || (!pattern && len)) return fail(KBO_ERR_BAD_ARGUMENT, "null argument");
+    uint64_t a = 0, b = 0;
+    *found = ix->host.search(pattern, len, &a, &b) ? 1 : 0;
+    if (*found) {
+        if (l) *l = a;
+        if (r) *r = b;
+    }
+    return KBO_OK;
+}
+
+// ---- derandomize.rs host functions --------------------------------------------
+int kbo_log_rm_max_cdf(uint64_t t, uint64_t alphabet_size, uint64_t n_kmers, double* out) {
+    if (!out) return fail(KBO_ERR_BAD_ARGUMENT, "out is null");
+    if (n_kmers == 0) return fail(KBO_ERR_BAD_ARGUMENT, "n_kmers must be > 0 (derandomize.rs:96)");
+    if (alphabet_size == 0) return fail(KBO_ERR_BAD_ARGUMENT, "alphabet_size must be > 0 (derandomize.rs:97)");
+    *out = host_log_rm_max_cdf(t, alphabet_size, n_kmers);
+    return KBO_OK;
+}
+
+int kbo_random_match_threshold(uint64_t k, uint64_t n_kmers, uint64_t alphabet_size, double max_error_prob,
+                               uint64_t* out) {
+    if (!out) return fail(KBO_ERR_BAD_ARGUMENT, "out is null");
+    return host_threshold(k, n_kmers, alphabet_size, max_error_prob, out);
+}
+
+// ---- query_sbwt -------------------------------------------------------------------
+int kbo_query_sbwt_batch_compact(const kbo_index* cix, const uint8_t* concat, const uint64_t* offsets,
+                                 uint64_t n_queries, uint8_t* d_out, uint32_t* l_out, uint32_t* r_out) {
+    kbo_index* ix = const_cast<kbo_index*>(cix);
+    if (!ix || !concat || !d_out) return fail(KBO_ERR_BAD_ARGUMENT, "null argument");
+    uint64_t total = 0;
+    int rc = check_offsets(offsets, n_queries, 1, &total);
+    if (rc) return rc;
+    DeviceGuard dg(ix->device);
+    if (!dg.ok) return fail(KBO_ERR_CUDA, "cudaSetDevice failed");
+    Workspace* ws = nullptr;
+    rc = acquire_ws(ix, &ws);
+    if (rc) return rc;
+    const Geometry g = make_geometry(total, n_queries);
+    const bool intervals = l_out || r_out;
+    cudaStream_t st = ws->stream;
+    auto body = [&]() -> int {
+        CUDA_TRY(ws->ascii.ensure(total, st));
+        CUDA_TRY(ws->offsets.ensure((n_queries + 1) * 8, st));
+        CUDA_TRY(ws->out.ensure(total, st));
+        if (intervals) {
+            CUDA_TRY(ws->out2.ensure(total * 4, st));
+            CUDA_TRY(ws->out3.ensure(total * 4, st));
+        }
+        CUDA_TRY(cudaMemcpyAsync(ws->ascii.p, concat + offsets[0], total, cudaMemcpyHostToDevice, st));
+        std::vector<uint64_t> rel(n_queries + 1);
+        for (uint64_t i = 0; i <= n_queries; ++i) rel[i] = offsets[i] - offsets[0];
+        CUDA_TRY(cudaMemcpyAsync(ws->offsets.p, rel.data(), (n_queries + 1) * 8, cudaMemcpyHostToDevice, st));
+        CUDA_TRY(cudaEventRecord(ws->ev0, st));
+        QueryView qv;
+        int rc2 = run_pack(ws, ws->ascii.as<uint8_t>(), ws->offsets.as<uint64_t>(), n_queries, g, &qv);
+        if (rc2) return rc2;
+        rc2 = run_ms(ix, ws, qv, g, intervals);
+        if (rc2) return rc2;
+        const unsigned threads = 256;
+        const unsigned blocks = (unsigned)((g.Lp + threads - 1) / threads);
+        unpad_kernel<uint8_t><<<blocks, threads, 0, st>>>(ws->ms.as<uint8_t>(), qv, ws->out.as<uint8_t>());
+        LAUNCHED();
+        if (intervals) {
+            unpad_kernel<uint32_t><<<blocks, threads, 0, st>>>(ws->l.as<uint32_t>(), qv, ws->out2.as<uint32_t>());
+            LAUNCHED();
+            unpad_kernel<uint32_t><<<blocks, threads, 0, st>>>(ws->r.as<uint32_t>(), qv, ws->out3.as<uint32_t>());
+            LAUNCHED();
+        }
+        CUDA_TRY(cudaGetLastError());
+        CUDA_TRY(cudaEventRecord(ws->ev1, st));
+        CUDA_TRY(cudaMemcpyAsync(d_out + offsets[0], ws->out.p, total, cudaMemcpyDeviceToHost, st));
+        if (l_out) CUDA_TRY(cudaMemcpyAsync(l_out + offsets[0], ws->out2.p, total * 4, cudaMemcpyDeviceToHost, st));
+        if (r_out) CUDA_TRY(cudaMemcpyAsync(r_out + offsets[0], ws->out3.p, total * 4, cudaMemcpyDeviceToHost, st));
+        CUDA_TRY(cudaStreamSynchronize(st));
+        float ms = 0.f;
+        cudaEventElapsedTime(&ms, ws->ev0, ws->ev1);
+        ix->last_kernel_ms = ms;
+        return fetch_counters(ix, ws);
+    };
+    rc = body();
+    release_ws(ix, ws);
+    return rc;
+}
+
+int kbo_query_sbwt(const kbo_index* ix, const uint8_t* query, uint64_t len, uint64_t* d_out, uint64_t* l_out,
+                   uint64_t* r_out) {
+    if (!ix || !d_out) return fail(KBO_ERR_BAD_ARGUMENT, "null argument");
+    if (!query || len == 0) return fail(KBO_ERR_EMPTY_INPUT, "empty query (index.rs:248 assert!(!query.is_empty()))");
+    const uint64_t offsets[2] = {0, len};
+    std::vector<uint8_t> d(len);
+    std::vector<uint32_t> l, r;
+    const bool intervals = l_out || r_out;
+    if (intervals) { l.resize(len); r.resize(len); }
+    int rc = kbo_query_sbwt_batch_compact(ix, query, offsets, 1, d.data(), intervals ? l.data() : nullptr,
+                                          intervals ? r.data() : nullptr);
+    if (rc) return rc;
+    for (uint64_t i = 0; i < len; ++i) d_out[i] = d[i];
+    if (l_out) for (uint64_t i = 0; i < len; ++i) l_out[i] = l[i];
+    if (r_out) for (uint64_t i = 0; i < len; ++i) r_out[i] = r[i];
+    return KBO_OK;
+}
+
+// ---- matches / find / map ----------------------------------------------------------
+static int matches_prologue(kbo_index* ix, const uint64_t* offsets, uint64_t nq, double p, uint64_t* total,
+                            uint32_t* thr) {
+    if (!ix) return fail(KBO_ERR_BAD_ARGUMENT, "index is null");
+    uint64_t t = 0;
+    int rc = host_threshold(ix->host.k, ix->host.n_kmers, 4, p, &t);  // lib.rs:620
+    if (rc) return rc;
+    rc = check_offsets(offsets, nq, 1, total);                          // index.rs:248
+    if (rc) return rc;
+    if (t <= 1) return fail(KBO_ERR_BAD_THRESHOLD, "threshold must be > 1 (derandomize.rs:275)");
+    rc = check_offsets(offsets, nq, 3, total);                          // derandomize.rs:276
+    if (rc) return rc;
+    *thr = (uint32_t)t;
+    return KBO_OK;
+}
+
+int kbo_matches_batch(const kbo_index* cix, const uint8_t* concat, const uint64_t* offsets, uint64_t n_queries,
+                      double max_error_prob, uint8_t* chars_out) {
+    kbo_index* ix = const_cast<kbo_index*>(cix);
+    if (!concat || !chars_out) return fail(KBO_ERR_BAD_ARGUMENT, "null argument");
+    uint64_t total = 0;
+    uint32_t thr = 0;
+    int rc = matches_prologue(ix, offsets, n_queries, max_error_prob, &total, &thr);
+    if (rc) return rc;
+    DeviceGuard dg(ix->device);
+    if (!dg.ok) return fail(KBO_ERR_CUDA, "cudaSetDevice failed");
+    Workspace* ws = nullptr;
+    rc = acquire_ws(ix, &ws);
+    if (rc) return rc;
+    const Geometry g = make_geometry(total, n_queries);
+    cudaStream_t st = ws->stream;
+    auto body = [&]() -> int {
+        CUDA_TRY(ws->ascii.ensure(total, st));
+        CUDA_TRY(ws->offsets.ensure((n_queries + 1) * 8, st));
+        CUDA_TRY(ws->out.ensure(total + 16, st));
+        CUDA_TRY(cudaMemcpyAsync(ws->ascii.p, concat + offsets[0], total, cudaMemcpyHostToDevice, st));
+        std::vector<uint64_t> rel(n_queries + 1);
+        for (uint64_t i = 0; i <= n_queries; ++i) rel[i] = offsets[i] - offsets[0];
+        CUDA_TRY(cudaMemcpyAsync(ws->offsets.p, rel.data(), (n_queries + 1) * 8, cudaMemcpyHostToDevice, st));
+        CUDA_TRY(cudaEventRecord(ws->ev0, st));
+        int rc2 = matches_device(ix, ws, ws->ascii.as<uint8_t>(), ws->offsets.as<uint64_t>(), n_queries, g, thr,
+                                 ws->out.as<uint8_t>(), 0);
+        if (rc2) return rc2;
+        CUDA_TRY(cudaEventRecord(ws->ev1, st));
+        CUDA_TRY(cudaMemcpyAsync(chars_out + offsets[0], ws->out.p, total, cudaMemcpyDeviceToHost, st));
+        CUDA_TRY(cudaStreamSynchronize(st));
+        float ms = 0.f;
+        cudaEventElapsedTime(&ms, ws->ev0, ws->ev1);
+        ix->last_kernel_ms = ms;
+        return fetch_counters(ix, ws);
+    };
+    rc = body();
+    release_ws(ix, ws);
+    return rc;
+}
+
+int kbo_matches(const kbo_index* ix, const uint8_t* query, uint64_t len, double max_error_prob, uint8_t* chars_out) {
+    const uint64_t offsets[2] = {0, len};
+    if (!query && len) return fail(KBO_ERR_BAD_ARGUMENT, "query is null");
+    return kbo_matches_batch(ix, query ? query : (const uint8_t*)"", offsets, 1, max_error_prob, chars_out);
+}
+
+int kbo_matches_batch_device(const kbo_index* cix, const uint8_t* d_concat, const uint64_t* d_offsets,
+                             const uint64_t* host_offsets, uint64_t n_queries, double max_error_prob,
+                             uint8_t* d_chars_out, void* stream) {
+    kbo_index* ix = const_cast<kbo_index*>(cix);
+    if (!d_concat || !d_offsets || !d_chars_out) return fail(KBO_ERR_BAD_ARGUMENT, "null argument");
+    uint64_t total = 0;
+    uint32_t thr = 0;
+    int rc = matches_prologue(ix, host_offsets, n_queries, max_error_prob, &total, &thr);
+    if (rc) return rc;
+    if (host_offsets[0] != 0) return fail(KBO_ERR_BAD_ARGUMENT, "device batches must have offsets[0] == 0");
+    DeviceGuard dg(ix->device);
+    if (!dg.ok) return fail(KBO_ERR_CUDA, "cudaSetDevice failed");
+    Workspace* ws = nullptr;
+    rc = stream_ws(ix, (cudaStream_t)stream, &ws);
+    if (rc) return rc;
+    const Geometry g = make_geometry(total, n_queries);
+    rc = matches_device(ix, ws, d_concat, d_offsets, n_queries, g, thr, d_chars_out, 0);
+    if (rc) return rc;
+    if (g_profile_counters.load()) return fetch_counters(ix, ws);
+    return KBO_OK;
+}
+
+// format.rs:143-193 restated as a host pass over one alignment
+static int host_run_lengths(const uint8_t* a, uint64_t n, uint64_t max_gap_len, std::vector<kbo_rle>* out) {
+    uint64_t i = 0;
+    while (i < n) {
+        if (a[i] == '-' || a[i] == ' ') { ++i; continue; }
+        kbo_rle e = {i, 0, 0, 0, 0, 0, 0};
+        uint64_t gap_run = 0;
+        bool in_gap = false;
+        while (i < n && a[i] != ' ') {
+            const uint8_t ch = a[i];
+            const bool true_gap = ch == '-';
+            if (true_gap && !in_gap) { in_gap = true; ++e.gap_opens; gap_run = 0; }
+            if (!true_gap) in_gap = false;
+            const bool is_match = ch == 'M' || ch == 'R' || ch == 'I';
+            const bool is_gap = true_gap || ch == 'D';
+            e.matches += is_match;
+            e.gap_bases += is_gap;
+            e.mismatches += (!is_match && !is_gap);
+            if (!is_gap) e.end = i + 1;
+            if (ch == 'R') {
+                if (i == 0) return fail(KBO_ERR_PANIC, "alignment starts with 'R' (format.rs:176 aln[i - 1])");
+                e.jumps += (a[i - 1] == 'R');
+            }
+            gap_run += true_gap;
+            ++i;
+            if (gap_run > max_gap_len || (is_gap && i == n && e.gap_opens > 0)) {
+                if (e.gap_opens == 0 || e.gap_bases < gap_run)
+                    return fail(KBO_ERR_PANIC, "usize underflow (format.rs:181-182)");
+                --e.gap_opens;
+                e.gap_bases -= gap_run;
+                break;
+            }
+        }
+        out->push_back(e);
+    }
+    return KBO_OK;
+}
+
+int kbo_run_lengths_gapped(const uint8_t* aln, uint64_t n, uint64_t max_gap_len, kbo_rle* out, uint64_t cap,
+                           uint64_t* n_out) {
+    if ((!aln && n) || !n_out) return fail(KBO_ERR_BAD_ARGUMENT, "null argument");
+    std::vector<kbo_rle> v;
+    int rc = host_run_lengths(aln, n, max_gap_len, &v);
+    if (rc) return rc;
+    *n_out = v.size();
+    if (v.size() > cap) return fail(KBO_ERR_BUFFER_TOO_SMALL, "rle capacity too small");
+    if (out) std::memcpy(out, v.data(), v.size() * sizeof(kbo_rle));
+    return KBO_OK;
+}
+
+int kbo_relative_to_ref(const uint8_t* ref_seq, const uint8_t* aln, uint64_t n, uint8_t* out) {
+    if (n && (!ref_seq || !aln || !out)) return fail(KBO_ERR_BAD_ARGUMENT, "null argument");
+    for (uint64_t i = 0; i < n; ++i) {  // format.rs:270-286
+        const uint8_t a = aln[i];
+        if (a == 'M' || a == 'R' || a == 'I') out[i] = ref_seq[i];
+        else if (a == 'X' || a == 'D' || a == '-') out[i] = '-';
+        else out[i] = a;
+    }
+    return KBO_OK;
+}
+
+int kbo_find_batch(const kbo_index* ix, const uint8_t* concat, const uint64_t* offsets, uint64_t n_queries,
+                   double max_error_prob, uint64_t max_gap_len, kbo_rle* rle_out, uint64_t rle_cap,
+                   uint64_t* rle_offsets) {
+    if (!rle_offsets) return fail(KBO_ERR_BAD_ARGUMENT, "rle_offsets is null");
+    uint64_t total = 0;
+    int rc = check_offsets(offsets, n_queries, 1, &total);
+    if (rc) return rc;
+    // alignment characters land in a pooled PINNED buffer so the device->host copy runs at PCIe speed
+    kbo_index* mix = const_cast<kbo_index*>(ix);
+    if (!mix) return fail(KBO_ERR_BAD_ARGUMENT, "index is null");
+    PinnedBuf pb;
+    {
+        std::lock_guard<std::mutex> g(mix->mu);
+        if (!mix->pinned_pool.empty()) { pb = mix->pinned_pool.back(); mix->pinned_pool.pop_back(); }
+    }
+    const size_t need = (size_t)offsets[n_queries] + 1;
+    if (pb.cap < need) {
+        if (pb.p) cudaFreeHost(pb.p);
+        pb.p = nullptr;
+        pb.cap = 0;
+        CUDA_TRY(cudaHostAlloc(&pb.p, need + need / 4, cudaHostAllocDefault));
+        pb.cap = need + need / 4;
+    }
+    uint8_t* aln = (uint8_t*)pb.p;
+    auto give_back = [&]() { std::lock_guard<std::mutex> g(mix->mu); mix->pinned_pool.push_back(pb); };
+    rc = kbo_matches_batch(ix, concat, offsets, n_queries, max_error_prob, aln);
+    if (rc) { give_back(); return rc; }
+    std::vector<kbo_rle> all;
+    rle_offsets[0] = 0;
+    for (uint64_t q = 0; q < n_queries; ++q) {
+        rc = host_run_lengths(aln + offsets[q], offsets[q + 1] - offsets[q], max_gap_len, &all);
+        if (rc) { give_back(); return rc; }
+        rle_offsets[q + 1] = all.size();
+    }
+    give_back();
+    if (all.size() > rle_cap) return fail(KBO_ERR_BUFFER_TOO_SMALL, "rle capacity too small");
+    if (rle_out && !all.empty()) std::memcpy(rle_out, all.data(), all.size() * sizeof(kbo_rle));
+    return KBO_OK;
+}
+
+int kbo_map_unrefined(const kbo_index* query_index, const uint8_t* ref_seq, uint64_t len, double max_error_prob,
+                      int format, uint8_t* out) {
+    if (!out) return fail(KBO_ERR_BAD_ARGUMENT, "out is null");
+    int rc = kbo_matches(query_index, ref_seq, len, max_error_prob, out);
+    if (rc) return rc;
+    if (format) return kbo_relative_to_ref(ref_seq, out, len, out);
+    return KBO_OK;
+}
+
+// ---- standalone derandomize / translate ------------------------------------------------
+static int pick_device(int device) {
+    int ndev = 0;
+    if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev == 0)
+        return fail(KBO_ERR_CUDA, "no CUDA device available (this library has no CPU fallback)");
+    if (device < 0 || device >= ndev) return fail(KBO_ERR_BAD_ARGUMENT, "device ordinal out of range");
+    return KBO_OK;
+}
+
+int kbo_derandomize_ms_vec(const uint64_t* noisy_ms, uint64_t n, uint64_t k, uint64_t threshold, int64_t* out,
+                           int device) {
+    if (k == 0) return fail(KBO_ERR_BAD_K, "k must be > 0 (derandomize.rs:274)");
+    if (threshold <= 1) return fail(KBO_ERR_BAD_THRESHOLD, "threshold must be > 1 (derandomize.rs:275)");
+    if (n <= 2) return fail(KBO_ERR_TOO_SHORT, "len must be > 2 (derandomize.rs:276)");
+    if (!noisy_ms || !out) return fail(KBO_ERR_BAD_ARGUMENT, "null argument");
+    if (k > 0xffffffffull) return fail(KBO_ERR_BAD_K, "k too large");
+    for (uint64_t i = 0; i < n; ++i)
+        if (noisy_ms[i] > k) return fail(KBO_ERR_BAD_ARGUMENT, "MS value > k (derandomize.rs:229)");
+    int rc = pick_device(device);
+    if (rc) return rc;
+    DeviceGuard dg(device);
+    if (!dg.ok) return fail(KBO_ERR_CUDA, "cudaSetDevice failed");
+    const uint64_t n_tiles = (n + G_TILE - 1) / G_TILE;
+    const uint32_t thr = (uint32_t)std::min<uint64_t>(threshold, 0xffffffffull);
+    uint64_t* d_ms = nullptr;
+    int64_t *d_out = nullptr, *d_tmax = nullptr, *d_min = nullptr;
+    uint32_t *d_tpar = nullptr, *d_eps = nullptr;
+    auto cleanup = [&]() {
+        cudaFree(d_ms); cudaFree(d_out); cudaFree(d_tmax); cudaFree(d_min); cudaFree(d_tpar); cudaFree(d_eps);
+    };
+    auto body = [&]() -> int {
+        CUDA_TRY(cudaMalloc((void**)&d_ms, n * 8));
+        CUDA_TRY(cudaMalloc((void**)&d_out, n * 8));
+        CUDA_TRY(cudaMalloc((void**)&d_tmax, n_tiles * 8));
+        CUDA_TRY(cudaMalloc((void**)&d_min, n_tiles * 8));
+        CUDA_TRY(cudaMalloc((void**)&d_tpar, n_tiles * 4));
+        CUDA_TRY(cudaMalloc((void**)&d_eps, n_tiles * 4));
+        CUDA_TRY(cudaMemcpy(d_ms, noisy_ms, n * 8, cudaMemcpyHostToDevice));
+        g1_tile_max_kernel<<<(unsigned)n_tiles, G_THREADS>>>(d_ms, n, (uint32_t)k, thr, d_tmax);
+        LAUNCHED();
+        g2_scan_max_kernel<<<1, 32>>>(d_tmax, n_tiles, d_min);
+        LAUNCHED();
+        g35_tile_kernel<false><<<(unsigned)n_tiles, G_THREADS>>>(d_ms, n, (uint32_t)k, thr, d_min, d_tpar, nullptr, nullptr);
+        LAUNCHED();
+        g4_scan_par_kernel<<<1, 32>>>(d_tpar, n_tiles, d_eps);
+        LAUNCHED();
+        g35_tile_kernel<true><<<(unsigned)n_tiles, G_THREADS>>>(d_ms, n, (uint32_t)k, thr, d_min, nullptr, d_eps, d_out);
+        LAUNCHED();
+        CUDA_TRY(cudaGetLastError());
+        CUDA_TRY(cudaMemcpy(out, d_out, n * 8, cudaMemcpyDeviceToHost));
+        return KBO_OK;
+    };
+    rc = body();
+    cleanup();
+    return rc;
+}
+
+int kbo_translate_ms_vec(const int64_t* derand_ms, uint64_t n, uint64_t k, uint64_t threshold, uint8_t* chars_out,
+                         int device) {
+    if (k == 0) return fail(KBO_ERR_BAD_K, "k must be > 0 (translate.rs:268)");
+    if (threshold <= 1) return fail(KBO_ERR_BAD_THRESHOLD, "threshold must be > 1 (translate.rs:269)");
+    if (n <= 2) return fail(KBO_ERR_TOO_SHORT, "len must be > 2 (translate.rs:270)");
+    if (!derand_ms || !chars_out) return fail(KBO_ERR_BAD_ARGUMENT, "null argument");
+    int rc = pick_device(device);
+    if (rc) return rc;
+    DeviceGuard dg(device);
+    if (!dg.ok) return fail(KBO_ERR_CUDA, "cudaSetDevice failed");
+    int64_t* d_in = nullptr;
+    uint8_t* d_out = nullptr;
+    auto body = [&]() -> int {
+        CUDA_TRY(cudaMalloc((void**)&d_in, n * 8));
+        CUDA_TRY(cudaMalloc((void**)&d_out, n));
+        CUDA_TRY(cudaMemcpy(d_in, derand_ms, n * 8, cudaMemcpyHostToDevice));
+        const uint32_t kk = (uint32_t)std::min<uint64_t>(k, 0x7fffffffull);
+        const uint32_t tt = (uint32_t)std::min<uint64_t>(threshold, 0x7fffffffull);
+        translate_i64_kernel<<<(unsigned)((n + 255) / 256), 256>>>(d_in, n, kk, tt, d_out);
+        LAUNCHED();
+        CUDA_TRY(cudaGetLastError());
+        CUDA_TRY(cudaMemcpy(chars_out, d_out, n, cudaMemcpyDeviceToHost));
+        return KBO_OK;
+    };
+    rc = body();
+    cudaFree(d_in);
+    cudaFree(d_out);
+    return rc;
+}
+
+// ---- instrumentation ------------------------------------------------------------------
+int kbo_set_profile_counters(int enabled) { g_profile_counters = enabled ? 1 : 0; return KBO_OK; }
+int kbo_get_ms_counters(const kbo_index* cix, kbo_ms_counters* out) {
+    kbo_index* ix = const_cast<kbo_index*>(cix);
+    if (!ix || !out) return fail(KBO_ERR_BAD_ARGUMENT, "null argument");
+    std::lock_guard<std::mutex> g(ix->mu);
+    *out = ix->last_counters;
+    return KBO_OK;
+}
+int kbo_set_chunk_len(uint32_t chunk_len) { g_chunk_len = chunk_len; return KBO_OK; }
+uint64_t kbo_kernel_launch_count(void) { return g_launches.load(); }
+float kbo_last_kernel_ms(const kbo_index* ix) { return ix ? ix->last_kernel_ms : 0.f; }
+
+int kbo_set_kernel_timing(int enabled) { g_kernel_timing = enabled ? 1 : 0; return KBO_OK; }
+
+int kbo_collect_kernel_times(const kbo_index* cix, void* stream, double sum_ms_out[3], uint64_t* n_calls) {
+    kbo_index* ix = const_cast<kbo_index*>(cix);
+    if (!ix || !sum_ms_out || !n_calls) return fail(KBO_ERR_BAD_ARGUMENT, "null argument");
+    DeviceGuard dg(ix->device);
+    Workspace* ws = nullptr;
+    int rc = stream_ws(ix, (cudaStream_t)stream, &ws);
+    if (rc) return rc;
+    sum_ms_out[0] = sum_ms_out[1] = sum_ms_out[2] = 0.0;
+    for (size_t c = 0; c < ws->timed_calls; ++c) {
+        cudaEvent_t* ev = ws->timing.data() + c * 4;
+        for (int j = 0; j < 3; ++j) {
+            float ms = 0.f;
+            CUDA_TRY(cudaEventElapsedTime(&ms, ev[j], ev[j + 1]));
+            sum_ms_out[j] += ms;
+        }
+    }
+    *n_calls = ws->timed_calls;
+    ws->timed_calls = 0;
+    return KBO_OK;
+}
+
+int kbo_measure_random_sector_rate(int device, uint64_t buffer_bytes, int dependent, double* sectors_per_s) {
+    if (!sectors_per_s) return fail(KBO_ERR_BAD_ARGUMENT, "out is null");
+    int rc = pick_device(device);
+    if (rc) return rc;
+    DeviceGuard dg(device);
+    if (!dg.ok) return fail(KBO_ERR_CUDA, "cudaSetDevice failed");
+    const uint64_t n_sectors64 = buffer_bytes / 32;
+    if (n_sectors64 == 0 || n_sectors64 > 0xffffffffull) return fail(KBO_ERR_BAD_ARGUMENT, "buffer size out of range");
+    const uint32_t n_sectors = (uint32_t)n_sectors64;
+    uint64_t* buf = nullptr;
+    unsigned long long* sink = nullptr;
+    cudaEvent_t e0 = nullptr, e1 = nullptr;
+    auto body = [&]() -> int {
+        CUDA_TRY(cudaMalloc((void**)&buf, (size_t)n_sectors * 32));
+        CUDA_TRY(cudaMalloc((void**)&sink, 8));
+        CUDA_TRY(cudaMemset(buf, 0x5a, (size_t)n_sectors * 32));
+        CUDA_TRY(cudaMemset(sink, 0, 8));
+        CUDA_TRY(cudaEventCreate(&e0));
+        CUDA_TRY(cudaEventCreate(&e1));
+        const unsigned blocks = 148 * 8, threads = 256;  // 2048 resident lanes per SM, like K1
+        const uint32_t iters = dependent ? 256 : 1024;
+        double best = 0.0;
+        for (int rep = 0; rep < 5; ++rep) {
+            CUDA_TRY(cudaEventRecord(e0));
+            if (dependent) random_sector_kernel<true><<<blocks, threads>>>(buf, n_sectors, iters, sink);
+            else random_sector_kernel<false><<<blocks, threads>>>(buf, n_sectors, iters, sink);
+            LAUNCHED();
+            CUDA_TRY(cudaEventRecord(e1));
+            CUDA_TRY(cudaEventSynchronize(e1));
+            CUDA_TRY(cudaGetLastError());
+            float ms = 0.f;
+            CUDA_TRY(cudaEventElapsedTime(&ms, e0, e1));
+            const double rate = (double)blocks * threads * iters / (ms * 1e-3);
+            if (rep > 0 && rate > best) best = rate;  // first repetition warms the cache
+        }
+        *sectors_per_s = best;
+        return KBO_OK;
+    };
+    rc = body();
+    if (buf) cudaFree(buf);
+    if (sink) cudaFree(sink);
+    if (e0) cudaEventDestroy(e0);
+    if (e1) cudaEventDestroy(e1);
+    return rc;
+}
+
+}  // extern "C"

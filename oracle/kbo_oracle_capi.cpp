@@ -332,6 +332,44 @@ double kbo_oracle_matches_batch(void* h, const uint8_t* concat, const uint64_t* 
     return std::chrono::duration<double>(t1 - t0).count();
 }
 
+// Same driver for kbo::find (lib.rs:808-821): matches + run_lengths[_gapped] per query.
+// n_rle_out (optional) receives the total number of RLE records.
+double kbo_oracle_find_batch(void* h, const uint8_t* concat, const uint64_t* offsets, uint64_t n_queries, double p,
+                             uint64_t max_gap_len, int n_threads, uint64_t* n_rle_out, uint64_t* checksum) {
+    Index& ix = *(Index*)h;
+    if (n_threads < 1) n_threads = 1;
+    std::atomic<uint64_t> next(0), sum(0), nrle(0);
+    std::atomic<int> failed(0);
+    auto t0 = std::chrono::steady_clock::now();
+    auto work = [&]() {
+        uint64_t local = 0, cnt = 0;
+        for (;;) {
+            uint64_t qi = next.fetch_add(1);
+            if (qi >= n_queries) break;
+            try {
+                auto rl = find(ix, concat + offsets[qi], offsets[qi + 1] - offsets[qi], p, max_gap_len);
+                cnt += rl.size();
+                for (const RLE& r : rl)
+                    local = local * 1099511628211ULL + r.start + 3 * r.end + 5 * r.matches + 7 * r.mismatches +
+                            11 * r.jumps + 13 * r.gap_bases + 17 * r.gap_opens + qi;
+            } catch (...) {
+                failed = 1;
+            }
+        }
+        sum += local;
+        nrle += cnt;
+    };
+    std::vector<std::thread> th;
+    for (int i = 1; i < n_threads; ++i) th.emplace_back(work);
+    work();
+    for (auto& t : th) t.join();
+    auto t1 = std::chrono::steady_clock::now();
+    if (checksum) *checksum = sum.load();
+    if (n_rle_out) *n_rle_out = nrle.load();
+    if (failed) return -1.0;
+    return std::chrono::duration<double>(t1 - t0).count();
+}
+
 int kbo_oracle_hardware_concurrency() { return (int)std::thread::hardware_concurrency(); }
 
 }  // extern "C"

@@ -1,0 +1,217 @@
+// ===========================================================================
+// tests/emu/emu_driver.cpp -- TEST INFRASTRUCTURE, NOT PRODUCT CODE.
+//
+// Runs the kernels of kbo_b200/csrc/kernels.cuh on the CPU through
+// tests/emu/host_emu.hpp, with the same launch sequence and buffer geometry as
+// kbo_b200/csrc/capi.cu, so that tests can compare the kernel LOGIC with the
+// oracle in a GPU-less container.  Also exposes the product's host-side index
+// builder (plain C++) for CPU tests.  Built into tests/emu/libkbo_emu.so by
+// tests/emu_lib.py; never loaded by the kbo_b200 package.
+// ===========================================================================
+#define KBO_HOST_EMU 1
+#include <algorithm>
+#include <cstdio>
+#include <string>
+
+#include "../../kbo_b200/csrc/host_layout.hpp"
+#include "../../kbo_b200/csrc/kernels.cuh"
+#include "../../kbo_b200/csrc/sbwt_host.hpp"
+
+using namespace kbo_b200;
+
+struct EmuIndex {
+    HostIndex host;
+    DeviceLayout lay;
+    IndexView view;
+};
+
+static void finish(EmuIndex* e) {
+    build_device_layout(e->host, &e->lay);
+    e->view.rank = e->lay.rank.data();
+    e->view.rank_stride = e->lay.stride;
+    e->view.lcs = e->lay.lcs.data();
+    e->view.n = (uint32_t)e->host.n_sets;
+    e->view.k = e->host.k;
+}
+
+struct Staged {
+    Geometry g;
+    std::vector<uint64_t> pack;
+    std::vector<uint32_t> inv, sep, wq;
+    std::vector<uint8_t> ms;
+    std::vector<uint32_t> l, r;
+    QueryView qv;
+};
+
+static void stage_and_ms(EmuIndex* e, const uint8_t* concat, const uint64_t* offsets, uint64_t nq, uint32_t chunk_len,
+                         bool intervals, unsigned long long* counters, Staged* s) {
+    const uint64_t total = offsets[nq] - offsets[0];
+    s->g = make_geometry(total, nq, chunk_len);
+    const Geometry& g = s->g;
+    s->pack.assign(g.n_words, 0xdeadbeefdeadbeefull);
+    s->inv.assign(g.n_words, 0xdeadbeef);
+    s->sep.assign(g.n_words, 0xdeadbeef);
+    s->wq.assign(g.n_words, 0xdeadbeef);
+    s->ms.assign(g.ms_bytes, 0xAB);  // garbage where K1 does not write, like uninitialised device memory
+    if (intervals) {
+        s->l.assign(g.n_words * 32, 0xdeadbeef);
+        s->r.assign(g.n_words * 32, 0xdeadbeef);
+    }
+    QueryView& qv = s->qv;
+    qv.pack = s->pack.data();
+    qv.inv = s->inv.data();
+    qv.sep = s->sep.data();
+    qv.wq = s->wq.data();
+    qv.Lp = g.Lp;
+    qv.n_words = g.n_words;
+    {
+        const unsigned threads = 128, blocks = (unsigned)((g.n_words + threads - 1) / threads);
+        emu_launch_seq(blocks, threads, [&]() {
+            pack_queries_kernel(concat, offsets, nq, qv, s->pack.data(), s->inv.data(), s->sep.data(), s->wq.data());
+        });
+    }
+    MsParams mp;
+    mp.ix = e->view;
+    mp.q = qv;
+    mp.chunk_len = g.chunk_len;
+    mp.n_chunks = g.n_chunks;
+    mp.ms = s->ms.data();
+    mp.l_out = intervals ? s->l.data() : nullptr;
+    mp.r_out = intervals ? s->r.data() : nullptr;
+    mp.counters = counters;
+    const unsigned threads = 256, blocks = (unsigned)((g.n_chunks + threads - 1) / threads);
+    emu_launch_seq(blocks, threads, [&]() {
+        if (intervals) {
+            if (counters) ms_kernel<true, true>(mp); else ms_kernel<true, false>(mp);
+        } else {
+            if (counters) ms_kernel<false, true>(mp); else ms_kernel<false, false>(mp);
+        }
+    });
+}
+
+template <typename T>
+static void unpad(const T* in, const QueryView& q, T* out) {
+    for (uint64_t pp = 0; pp < q.Lp; ++pp) {
+        const uint32_t sw = q.sep[pp >> 5];
+        if ((sw >> (pp & 31)) & 1u) continue;
+        const uint64_t nsep = q.wq[pp >> 5] + __builtin_popcount(sw & ((1u << (pp & 31)) - 1u));
+        out[pp - nsep] = in[pp];
+    }
+}
+
+extern "C" {
+
+void* emu_host_build(const uint8_t* const* seqs, const uint64_t* lens, uint64_t n_seqs, uint32_t k, int revcomp,
+                     uint32_t threads, char* err, uint64_t err_cap) {
+    EmuIndex* e = new EmuIndex();
+    std::string msg = build_host_index(seqs, lens, n_seqs, k, revcomp != 0, threads, &e->host);
+    if (!msg.empty()) {
+        std::snprintf(err, err_cap, "%s", msg.c_str());
+        delete e;
+        return nullptr;
+    }
+    finish(e);
+    return e;
+}
+
+void* emu_from_parts(uint32_t k, uint64_t n_sets, uint64_t n_kmers, const uint64_t* const rows[4], const uint8_t* lcs) {
+    EmuIndex* e = new EmuIndex();
+    HostIndex& h = e->host;
+    h.k = k;
+    h.n_sets = n_sets;
+    h.n_kmers = n_kmers;
+    const size_t nw = (size_t)(n_sets + 63) / 64;
+    for (int c = 0; c < 4; ++c) {
+        h.rows[c].assign(nw + 1, 0);
+        std::memcpy(h.rows[c].data(), rows[c], nw * 8);
+        if (n_sets & 63) h.rows[c][nw - 1] &= ~0ull >> (64 - (n_sets & 63));
+    }
+    h.lcs.assign(lcs, lcs + n_sets);
+    h.finalize();
+    finish(e);
+    return e;
+}
+
+void emu_free(void* h) { delete (EmuIndex*)h; }
+uint64_t emu_n_sets(void* h) { return ((EmuIndex*)h)->host.n_sets; }
+uint64_t emu_n_kmers(void* h) { return ((EmuIndex*)h)->host.n_kmers; }
+uint32_t emu_k(void* h) { return ((EmuIndex*)h)->host.k; }
+void emu_export(void* h, uint64_t* a, uint64_t* c, uint64_t* g, uint64_t* t, uint8_t* lcs, uint64_t* C4) {
+    HostIndex& hi = ((EmuIndex*)h)->host;
+    const size_t nw = (size_t)(hi.n_sets + 63) / 64;
+    uint64_t* outs[4] = {a, c, g, t};
+    for (int ch = 0; ch < 4; ++ch) std::memcpy(outs[ch], hi.rows[ch].data(), nw * 8);
+    std::memcpy(lcs, hi.lcs.data(), (size_t)hi.n_sets);
+    for (int ch = 0; ch < 4; ++ch) C4[ch] = hi.C[ch];
+}
+void emu_access_kmer(void* h, uint64_t colex, uint8_t* out) { ((EmuIndex*)h)->host.access_kmer(colex, out); }
+int emu_search(void* h, const uint8_t* pat, uint64_t len, uint64_t* l, uint64_t* r) {
+    return ((EmuIndex*)h)->host.search(pat, len, l, r) ? 1 : 0;
+}
+
+// K0 + K1 (+ unpad): index::query_sbwt for a CSR batch, compact outputs indexed like concat
+void emu_query_sbwt_batch(void* h, const uint8_t* concat, const uint64_t* offsets, uint64_t nq, uint32_t chunk_len,
+                          uint8_t* d_out, uint32_t* l_out, uint32_t* r_out, unsigned long long* counters10) {
+    Staged s;
+    if (counters10) std::memset(counters10, 0, CNT_N * sizeof(unsigned long long));
+    stage_and_ms((EmuIndex*)h, concat + offsets[0], offsets, nq, chunk_len, l_out || r_out, counters10, &s);
+    unpad<uint8_t>(s.ms.data(), s.qv, d_out + offsets[0]);
+    if (l_out) unpad<uint32_t>(s.l.data(), s.qv, l_out + offsets[0]);
+    if (r_out) unpad<uint32_t>(s.r.data(), s.qv, r_out + offsets[0]);
+}
+
+// K0 + K1 + K2: kbo::matches for a CSR batch
+void emu_matches_batch(void* h, const uint8_t* concat, const uint64_t* offsets, uint64_t nq, uint32_t thr,
+                       uint32_t chunk_len, uint8_t* chars_out) {
+    EmuIndex* e = (EmuIndex*)h;
+    Staged s;
+    stage_and_ms(e, concat + offsets[0], offsets, nq, chunk_len, false, nullptr, &s);
+    TrParams tp;
+    tp.ms = s.ms.data();
+    tp.q = s.qv;
+    tp.k = e->host.k;
+    tp.thr = thr;
+    tp.out = chars_out;
+    tp.off0 = offsets[0];
+    tp.n_tiles = s.g.n_tiles;
+    const unsigned blocks = (unsigned)((s.g.n_tiles + K2_WARPS - 1) / K2_WARPS);
+    emu_launch_par(blocks, K2_WARPS * 32, [&]() { derand_translate_kernel(tp); });
+}
+
+// K2 alone on a caller-supplied u8 MS vector of ONE query (no separators except the final one)
+void emu_derand_translate_u8(const uint8_t* ms, uint64_t n, uint32_t k, uint32_t thr, uint8_t* chars_out) {
+    const uint64_t offsets[2] = {0, n};
+    Geometry g = make_geometry(n, 1, 0);
+    std::vector<uint64_t> pack(g.n_words);
+    std::vector<uint32_t> inv(g.n_words), sep(g.n_words), wq(g.n_words);
+    std::vector<uint8_t> ascii(n, 'A'), msbuf(g.ms_bytes, 0xAB);
+    std::memcpy(msbuf.data(), ms, n);
+    QueryView qv;
+    qv.pack = pack.data(); qv.inv = inv.data(); qv.sep = sep.data(); qv.wq = wq.data();
+    qv.Lp = g.Lp; qv.n_words = g.n_words;
+    emu_launch_seq((unsigned)((g.n_words + 127) / 128), 128, [&]() {
+        pack_queries_kernel(ascii.data(), offsets, 1, qv, pack.data(), inv.data(), sep.data(), wq.data());
+    });
+    TrParams tp;
+    tp.ms = msbuf.data(); tp.q = qv; tp.k = k; tp.thr = thr; tp.out = chars_out; tp.off0 = 0; tp.n_tiles = g.n_tiles;
+    emu_launch_par((unsigned)((g.n_tiles + K2_WARPS - 1) / K2_WARPS), K2_WARPS * 32, [&]() { derand_translate_kernel(tp); });
+}
+
+void emu_derandomize_general(const uint64_t* ms, uint64_t n, uint32_t k, uint32_t thr, int64_t* out) {
+    const uint64_t n_tiles = (n + G_TILE - 1) / G_TILE;
+    std::vector<int64_t> tmax(n_tiles), min_(n_tiles);
+    std::vector<uint32_t> tpar(n_tiles), eps(n_tiles);
+    emu_launch_par((unsigned)n_tiles, G_THREADS, [&]() { g1_tile_max_kernel(ms, n, k, thr, tmax.data()); });
+    emu_launch_seq(1, 32, [&]() { g2_scan_max_kernel(tmax.data(), n_tiles, min_.data()); });
+    emu_launch_par((unsigned)n_tiles, G_THREADS,
+                   [&]() { g35_tile_kernel<false>(ms, n, k, thr, min_.data(), tpar.data(), nullptr, nullptr); });
+    emu_launch_seq(1, 32, [&]() { g4_scan_par_kernel(tpar.data(), n_tiles, eps.data()); });
+    emu_launch_par((unsigned)n_tiles, G_THREADS,
+                   [&]() { g35_tile_kernel<true>(ms, n, k, thr, min_.data(), nullptr, eps.data(), out); });
+}
+
+void emu_translate_i64(const int64_t* d, uint64_t n, uint32_t k, uint32_t thr, uint8_t* out) {
+    emu_launch_seq((unsigned)((n + 255) / 256), 256, [&]() { translate_i64_kernel(d, n, k, thr, out); });
+}
+
+}  // extern "C"

@@ -82,6 +82,10 @@ def lib():
                                      C.c_int, u8p]
         L.kbo_oracle_matches_batch.restype = C.c_double
         L.kbo_oracle_matches_batch.argtypes = [C.c_void_p, u8p, u64p, C.c_uint64, C.c_double, u8p, C.c_int, u64p]
+        L.kbo_oracle_find_batch.restype = C.c_double
+        L.kbo_oracle_find_batch.argtypes = [C.c_void_p, u8p, u64p, C.c_uint64, C.c_double, C.c_uint64, C.c_int, u64p,
+                                            u64p]
+        L.kbo_oracle_hardware_concurrency.restype = C.c_int
         _lib = L
     return _lib
 
@@ -252,6 +256,22 @@ class OracleIndex:
         if secs < 0:
             raise OraclePanic("matches_batch: a query panicked")
         return secs, out, cs.value
+
+
+def find_batch_timed(ix, concat, offsets, max_error_prob=1e-7, max_gap_len=0, n_threads=1):
+    """kbo::find over a CSR batch with n_threads host threads: (seconds, n_rle, checksum)."""
+    cc = _u8(concat)
+    off = np.ascontiguousarray(offsets, dtype=np.uint64)
+    cs, nr = C.c_uint64(0), C.c_uint64(0)
+    secs = lib().kbo_oracle_find_batch(ix.h, _p(cc, C.c_uint8), _p(off, C.c_uint64), len(off) - 1, max_error_prob,
+                                       max_gap_len, n_threads, C.byref(nr), C.byref(cs))
+    if secs < 0:
+        raise OraclePanic("find_batch: a query panicked")
+    return secs, nr.value, cs.value
+
+
+def hardware_concurrency():
+    return int(lib().kbo_oracle_hardware_concurrency())
 
 
 def call_variants(ix_ref, ix_query, query, max_error_prob):

@@ -1,0 +1,133 @@
+"""CPU-only checks of the drop-in boundary: the shared library loads, exports every symbol that
+include/kbo_b200.h declares, its host-side functions reproduce the reference's golden vectors, and
+compute entry points FAIL LOUDLY without a GPU (no CPU fallback)."""
+import ctypes as C
+import math
+import os
+import re
+
+import numpy as np
+import pytest
+
+from kbo_b200 import api, build
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+@pytest.fixture(scope="module")
+def lib():
+    build.build_library()
+    return api.load_library()
+
+
+def header_functions():
+    src = open(os.path.join(ROOT, "include", "kbo_b200.h")).read()
+    src = re.sub(r"/\*.*?\*/", "", src, flags=re.S)
+    return sorted(set(re.findall(r"\b(kbo_[a-z0-9_]+)\s*\(", src)))
+
+
+def test_library_exports_every_declared_symbol(lib):
+    names = header_functions()
+    assert len(names) >= 30
+    for n in names:
+        assert hasattr(lib, n), "missing export: " + n
+    assert sorted(api.EXPORTED_SYMBOLS) == names
+
+
+def test_no_torch_types_in_header():
+    src = open(os.path.join(ROOT, "include", "kbo_b200.h")).read()
+    assert "torch" not in src.lower().replace("no c++/torch types", "") and "at::" not in src and "std::" not in src
+
+
+def test_log_rm_max_cdf_golden(lib):
+    # derandomize.rs:298-304
+    expected = [-1306319.1078024083, -318761.2492719044, -79220.9269610741, -19776.1823255263, -4942.2344281681,
+                -1235.4454790664, -308.8543003470, -77.2131332649, -19.3032557026, -4.8258121998, -1.2064529421,
+                -0.3016132288, -0.0754033068, -0.0188508267, -0.0047127067, -0.0011781767, -0.0002945442,
+                -0.0000736360, -0.0000184090, -0.0000046023, -0.0000011506, -0.0000002876, -0.0000000719,
+                -0.0000000180, -0.0000000045, 0.0, 0.0, 0.0, 0.0, 0.0, 0.0]
+    for t in range(1, 32):
+        assert abs(api.log_rm_max_cdf(t, 4, 20240921) - expected[t - 1]) < 1e-8
+
+
+def test_random_match_threshold_golden(lib):
+    # derandomize.rs:307-314
+    for i, want in enumerate([15, 18, 22, 25, 28], start=1):
+        assert api.random_match_threshold(31, 20240921, 4, math.pow(0.01, float(i))) == want
+    assert api.random_match_threshold(3, 13, 4, 1e-7) == 3      # lib.rs:600-610 degenerate case
+    assert api.random_match_threshold(31, 1176, 4, 1e-7) == 16  # lib.rs:786-806
+
+
+def test_threshold_precondition_codes(lib):
+    for args, status in [((0, 1, 4, 0.1), 4), ((31, 0, 4, 0.1), 7), ((31, 1, 0, 0.1), 7), ((31, 1, 4, 1.5), 6),
+                         ((31, 1, 4, 0.0), 6)]:
+        with pytest.raises(api.KboPanic) as e:
+            api.random_match_threshold(*args)
+        assert e.value.status == status
+
+
+def test_run_lengths_goldens(lib):
+    t = lambda rl: [(r.start, r.end, r.matches, r.mismatches, r.jumps, r.gap_bases, r.gap_opens) for r in rl]
+    aln = b"XMMRRMMXMMM--MMM--"
+    assert t(api.run_lengths(aln)) == [(0, 11, 9, 2, 1, 0, 0), (13, 16, 3, 0, 0, 0, 0)]  # format.rs:77-95
+    assert t(api.run_lengths_gapped(aln, 3)) == [(0, 16, 12, 2, 1, 2, 1)]                  # format.rs:122-140
+    with pytest.raises(api.KboPanic) as e:                                                 # format.rs:176
+        api.run_lengths(b"RRMM")
+    assert e.value.status == 12
+
+
+def test_run_lengths_vs_oracle_random(lib):
+    import oracle_lib as O
+    rng = np.random.default_rng(5)
+    alphabet = np.frombuffer(b"MMMMMM--XRIDACGT ", dtype=np.uint8)
+    for n in (1, 2, 17, 300, 2000):
+        for gap in (0, 1, 3, 50):
+            for _ in range(20):
+                a = alphabet[rng.integers(0, len(alphabet), size=n)].tobytes()
+                try:
+                    want = O.run_lengths_gapped(a, gap)
+                except O.OraclePanic:
+                    with pytest.raises(api.KboPanic):
+                        api.run_lengths_gapped(a, gap)
+                    continue
+                got = api.run_lengths_gapped(a, gap)
+                assert [(r.start, r.end, r.matches, r.mismatches, r.jumps, r.gap_bases, r.gap_opens)
+                        for r in got] == want
+
+
+def test_relative_to_ref_goldens(lib):
+    # format.rs:251-263
+    assert api.relative_to_ref(b"AAAGAACCATCAGGGCG", b"CMMR--RMMMMMMMM--") == b"CAAG--CCATCAGGG--"
+    assert api.relative_to_ref(b"TTGATTGGCTGGGCAGAGCTG", b"MMMM--MMMMMMMXMMMMMMM") == b"TTGA--GGCTGGG-AGAGCTG"
+
+
+def test_compute_fails_loudly_without_gpu(lib):
+    if api.device_count() > 0:
+        pytest.skip("a GPU is present")
+    with pytest.raises(api.KboPanic) as e:
+        api.build([b"ACGTACGTACGT"], api.BuildOpts(k=3))
+    assert e.value.status == 8  # KBO_ERR_CUDA: there is no CPU fallback
+    with pytest.raises(api.KboPanic) as e:
+        api.derandomize_ms_vec([1, 2, 3, 3], 3, 2)
+    assert e.value.status == 8
+    with pytest.raises(api.KboPanic) as e:
+        api.translate_ms_vec([1, 2, 3, 3], 3, 2)
+    assert e.value.status == 8
+
+
+def test_argument_validation_before_any_device_work(lib):
+    with pytest.raises(api.KboPanic) as e:
+        api.derandomize_ms_vec([1, 2, 3], 3, 1)
+    assert e.value.status == 2  # derandomize.rs:275
+    with pytest.raises(api.KboPanic) as e:
+        api.derandomize_ms_vec([1, 2], 3, 2)
+    assert e.value.status == 3  # derandomize.rs:276
+    with pytest.raises(api.KboPanic) as e:
+        api.translate_ms_vec([1, 2], 3, 2)
+    assert e.value.status == 3  # translate.rs:270
+    with pytest.raises(api.KboPanic) as e:
+        api.build([], api.BuildOpts(k=3))
+    assert e.value.status == 1  # index.rs:60
+    with pytest.raises(api.KboPanic) as e:
+        api.build([b"ACGT"], api.BuildOpts(k=65))
+    assert e.value.status == 4

@@ -1,0 +1,214 @@
+"""CPU-side checks of the product's host builder and of the kernel LOGIC (kernels.cuh compiled
+through tests/emu/host_emu.hpp) against the oracle.  The real parity tests run the CUDA build on
+a B200 (tests/test_gpu_parity.py, -m gpu); these exist so that logic errors are found here first.
+"""
+import json
+import os
+
+import numpy as np
+import pytest
+
+import emu_lib as E
+import oracle_lib as O
+from kbo_b200 import synth
+
+GOLD = json.load(open(os.path.join(os.path.dirname(__file__), "golden", "reference_vectors.json")))
+REF_K3 = b"AAAGAACCA-TCAGGGCG"
+
+
+def rand_seq(n, seed):
+    return synth.random_seq(n, seed).tobytes()
+
+
+def with_ns(seq, seed, rate=0.01):
+    a = np.frombuffer(seq, dtype=np.uint8).copy()
+    rng = np.random.default_rng(seed)
+    a[rng.random(len(a)) < rate] = ord("N")
+    return a.tobytes()
+
+
+def assert_same_index(seqs, k, revcomp=False, threads=1):
+    o = O.OracleIndex(seqs, k=k, add_revcomp=revcomp)
+    e = E.EmuIndex.build(seqs, k=k, add_revcomp=revcomp, threads=threads)
+    assert (e.k, e.n_sets, e.n_kmers) == (o.k, o.n_sets, o.n_kmers)
+    rows, lcs, Cc = e.export()
+    for a, b in zip(rows, o.rows()):
+        assert np.array_equal(a, b)
+    assert np.array_equal(lcs, o.lcs())
+    assert np.array_equal(Cc, o.C())
+    return o, e
+
+
+# ------------------------------------------------------------- host builder ---
+@pytest.mark.parametrize("k", [1, 2, 3, 4, 7, 20, 31, 32, 33, 51, 63, 64])
+def test_host_builder_matches_oracle_small(k):
+    seqs = [REF_K3, rand_seq(300, 1), b"ACGTNNACGTTTGACCANGGTA" * 3, rand_seq(70, 2)]
+    o, e = assert_same_index(seqs, k)
+    for i in range(0, o.n_sets, max(1, o.n_sets // 50)):
+        assert e.access_kmer(i) == o.access_kmer(i)
+
+
+def test_host_builder_golden_find_index():
+    b = GOLD["lib.rs::doc@779"]
+    o, e = assert_same_index([b["gene1"].encode(), b["gene2_rc"].encode()], 31)
+    assert (e.n_kmers, e.n_sets) == (1176, 1237)
+
+
+@pytest.mark.parametrize("k,revcomp,threads", [(31, False, 1), (31, True, 3), (15, False, 4), (47, True, 1)])
+def test_host_builder_matches_oracle_medium(k, revcomp, threads):
+    ref = with_ns(rand_seq(120_000, 7), 8, rate=0.0005)
+    seqs = [ref[:50_000], ref[50_000:], ref[1000:3000]]  # duplicated region
+    o, e = assert_same_index(seqs, k, revcomp, threads)
+    rng = np.random.default_rng(3)
+    for i in rng.integers(0, o.n_sets, size=200).tolist():
+        assert e.access_kmer(i) == o.access_kmer(i)
+    for s in rng.integers(0, 49_000, size=50).tolist():
+        pat = ref[s:s + int(rng.integers(1, k + 1))]
+        assert e.search(pat) == o.search(pat)
+    assert e.search(b"ACGTN") is None
+
+
+def test_repetitive_sequences():
+    seqs = [b"A" * 200 + b"C" * 5 + b"AC" * 100, b"T" * 64, b"ACGT" * 50]
+    for k in (5, 31):
+        assert_same_index(seqs, k)
+
+
+# ----------------------------------------------------------------- K1: MS ---
+def check_ms(o, e, queries, chunk_len):
+    d, l, r, off, _ = e.query_sbwt_batch(queries, chunk_len=chunk_len)
+    for i, q in enumerate(queries):
+        od, ol, orr = o.query_sbwt(q)
+        a, b = int(off[i]), int(off[i + 1])
+        assert np.array_equal(d[a:b].astype(np.uint64), od), (i, chunk_len)
+        assert np.array_equal(l[a:b].astype(np.uint64), ol), (i, chunk_len)
+        assert np.array_equal(r[a:b].astype(np.uint64), orr), (i, chunk_len)
+
+
+def test_ms_golden_k3():
+    o = O.OracleIndex([REF_K3], k=3)
+    e = E.EmuIndex.build([REF_K3], k=3)
+    d, l, r, off, _ = e.query_sbwt_batch([b"CAAGCCACTCATTGGGTC"], chunk_len=32)
+    assert d.tolist() == [1, 2, 2, 3, 2, 2, 3, 2, 1, 2, 3, 1, 1, 1, 2, 3, 1, 2]  # index.rs:264-274
+    check_ms(o, e, [b"CAAGCCACTCATTGGGTC", b"A", b"NNNN", b"GTGACTATGAGGAT"], 32)
+
+
+@pytest.mark.parametrize("k", [3, 7, 20, 31, 51, 63])
+def test_ms_matches_oracle(k):
+    ref = rand_seq(30_000, 11)
+    asm = synth.mutate(np.frombuffer(ref, dtype=np.uint8), 12).tobytes()
+    o = O.OracleIndex([asm], k=k)
+    e = E.EmuIndex.build([asm], k=k)
+    queries = [ref[:5000], with_ns(ref[5000:9000], 5, 0.02), rand_seq(700, 13), ref[10_000:10_003], b"N",
+               ref[20_000:20_257], b"ACGT" * 40 + b"$" + ref[100:400]]
+    for chunk_len in (32, 64, 256, 1024):
+        check_ms(o, e, queries, chunk_len)
+
+
+def test_ms_tiny_index_and_counters():
+    o = O.OracleIndex([b"ACG"], k=3)
+    e = E.EmuIndex.build([b"ACG"], k=3)
+    assert o.n_sets < 64
+    check_ms(o, e, [b"ACGACGTTACG", b"TTTT"], 32)
+    d, l, r, off, cnt = e.query_sbwt_batch([b"ACGACGTTACG" * 30], chunk_len=64, counters=True)
+    assert cnt[5] == 330 + 1  # emitted = padded positions (incl. the separator)
+    assert cnt[4] >= cnt[5] and cnt[0] >= 330
+
+
+# -------------------------------------------------- K2: derandomize+translate ---
+def valid_ms_vector(rng, n, k, thr):
+    """Random vector obeying ms[i+1] <= ms[i] + 1 with long flat / rising runs above and below thr."""
+    out = np.zeros(n, dtype=np.int64)
+    cur = int(rng.integers(0, k + 1))
+    for i in range(n):
+        out[i] = cur
+        u = rng.random()
+        if u < 0.45:
+            cur = min(cur + 1, k)
+        elif u < 0.80:
+            cur = cur
+        elif u < 0.9:
+            cur = int(rng.integers(0, cur + 1))
+        else:
+            cur = max(cur - int(rng.integers(1, 4)), 0)
+    return out
+
+
+@pytest.mark.parametrize("k,thr", [(3, 2), (31, 15), (31, 22), (31, 30), (63, 24), (7, 6)])
+def test_k2_on_valid_ms(k, thr):
+    rng = np.random.default_rng(k * 100 + thr)
+    for n in (3, 4, 31, 32, 33, 511, 512, 513, 1024, 5000):
+        ms = valid_ms_vector(rng, n, k, thr)
+        want = O.translate_ms_vec(O.derandomize_ms_vec(ms, k, thr), k, thr)
+        got = E.derand_translate_u8(ms.astype(np.uint8), k, thr)
+        assert got == want, (n, k, thr)
+
+
+def test_k2_long_flat_and_noise_runs():
+    k, thr = 31, 15
+    for ms in ([20] * 3000 + [5, 5, 5], [5] * 2000 + [31] * 40 + [3] * 1500, [20] * 8 + [5, 5, 5],
+               [16] * 700 + [17] * 700 + [31] * 5 + [0] * 900, [31] * 2048, [0] * 2048):
+        ms = np.array(ms, dtype=np.int64)
+        want = O.translate_ms_vec(O.derandomize_ms_vec(ms, k, thr), k, thr)
+        assert E.derand_translate_u8(ms.astype(np.uint8), k, thr) == want
+
+
+# ------------------------------------------------------- K0+K1+K2: matches ---
+def test_matches_goldens():
+    o = O.OracleIndex([REF_K3], k=3)
+    e = E.EmuIndex.build([REF_K3], k=3)
+    assert e.matches_batch([b"GTGACTATGAGGAT"], 3, 32) == [b"---------MMM--"]  # lib.rs:600-610
+    b = GOLD["lib.rs::doc@779"]
+    o = O.OracleIndex([b["gene1"].encode(), b["gene2_rc"].encode()], k=31)
+    e = E.EmuIndex.build([b["gene1"].encode(), b["gene2_rc"].encode()], k=31)
+    q = b["query"].encode()
+    assert e.matches_batch([q], 16, 64) == [o.matches(q)]
+
+
+@pytest.mark.parametrize("k,p", [(31, 1e-7), (20, 1e-3), (51, 1e-7)])
+def test_matches_batch_matches_oracle(k, p):
+    ref = np.frombuffer(rand_seq(40_000, 21), dtype=np.uint8)
+    o = O.OracleIndex([ref.tobytes()], k=k)
+    e = E.EmuIndex.build([ref.tobytes()], k=k)
+    thr = O.random_match_threshold(k, o.n_kmers, 4, p)
+    genes, off = synth.gene_queries(ref, 40, 1000, 22)
+    queries = [genes[int(off[i]):int(off[i + 1])].tobytes() for i in range(40)]
+    asm = synth.mutate(ref, 23).tobytes()
+    queries += [asm[:7000], rand_seq(1500, 24), with_ns(asm[7000:9000], 25, 0.01), asm[9000:9003], asm[9100:9611],
+                asm[10_000:10_512], asm[11_000:11_513]]
+    for chunk_len in (64, 512):
+        got = e.matches_batch(queries, thr, chunk_len)
+        for g_, q in zip(got, queries):
+            assert g_ == o.matches(q, p)
+
+
+# -------------------------------------------- standalone derandomize / translate ---
+@pytest.mark.parametrize("k,thr", [(3, 2), (31, 15), (31, 22), (63, 40), (5, 4)])
+def test_general_derandomize_arbitrary_vectors(k, thr):
+    rng = np.random.default_rng(k + thr)
+    for n in (3, 5, 255, 256, 257, 1023, 1024, 1025, 4097, 10_000):
+        for kind in range(3):
+            if kind == 0:
+                ms = rng.integers(0, k + 1, size=n)
+            elif kind == 1:
+                ms = np.clip(rng.integers(thr - 2, thr + 4, size=n), 0, k)
+            else:
+                ms = valid_ms_vector(rng, n, k, thr)
+            want = O.derandomize_ms_vec(ms, k, thr)
+            got = E.derandomize_general(ms, k, thr)
+            assert np.array_equal(got, want), (n, kind)
+
+
+def test_general_derandomize_golden():
+    got = E.derandomize_general([1, 2, 2, 3, 2, 2, 3, 2, 1, 2, 3, 1, 1, 1, 2, 3, 1, 2], 3, 2)
+    assert got.tolist() == [0, 1, 2, 3, 1, 2, 3, 0, 1, 2, 3, -1, 0, 1, 2, 3, -1, 0]  # derandomize.rs:373-379
+
+
+@pytest.mark.parametrize("k,thr", [(3, 2), (31, 15)])
+def test_translate_i64_arbitrary_vectors(k, thr):
+    rng = np.random.default_rng(99)
+    assert E.translate_i64([0, 1, 2, 3, 1, 2, 3, 0, 1, 2, 3, -1, 0, 1, 2, 3, -1, 0], 3, 2) == b"XMMRRMMXMMM--MMM--"
+    for n in (3, 4, 5, 100, 3000):
+        for _ in range(20):
+            d = rng.integers(-5, k + 1, size=n)
+            assert E.translate_i64(d, k, thr) == O.translate_ms_vec(d, k, thr)

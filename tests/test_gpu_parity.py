@@ -1,0 +1,286 @@
+"""Parity tests proper: the CUDA path, called through the C ABI (kbo_b200.api over
+libkbo_b200.so), against the CPU oracle and the reference's golden vectors, bit-exact.
+Needs a B200:  python -m pytest tests -m gpu
+"""
+import json
+import os
+
+import numpy as np
+import pytest
+
+import oracle_lib as O
+from kbo_b200 import api, build, synth
+
+pytestmark = pytest.mark.gpu
+
+GOLD = json.load(open(os.path.join(os.path.dirname(__file__), "golden", "reference_vectors.json")))
+REF_K3 = b"AAAGAACCA-TCAGGGCG"
+
+
+@pytest.fixture(scope="module", autouse=True)
+def _lib():
+    build.build_library()
+    api.load_library()
+    assert api.device_count() >= 1, "no CUDA device: the gpu tests must not pass on a fallback"
+    api.set_chunk_len(0)
+    yield
+    api.set_chunk_len(0)
+
+
+def g(block, var):
+    return GOLD[block][var].encode()
+
+
+def rand_seq(n, seed):
+    return synth.random_seq(n, seed).tobytes()
+
+
+def with_ns(seq, seed, rate=0.01):
+    a = np.frombuffer(seq, dtype=np.uint8).copy()
+    rng = np.random.default_rng(seed)
+    a[rng.random(len(a)) < rate] = ord("N")
+    return a.tobytes()
+
+
+def rle_tuples(rl):
+    return [(r.start, r.end, r.matches, r.mismatches, r.jumps, r.gap_bases, r.gap_opens) for r in rl]
+
+
+# ---------------------------------------------------------------- goldens through the ABI ---
+def test_golden_query_sbwt_k3():
+    ix = api.build([REF_K3], api.BuildOpts(k=3))  # index.rs:264-274
+    d, l, r = api.query_sbwt(b"CAAGCCACTCATTGGGTC", ix)
+    assert d.tolist() == [1, 2, 2, 3, 2, 2, 3, 2, 1, 2, 3, 1, 1, 1, 2, 3, 1, 2]
+    assert (ix.n_kmers, ix.n_sets) == (13, 16)
+
+
+def test_golden_matches_k3():
+    ix = api.build([REF_K3], api.BuildOpts(k=3))  # lib.rs:600-610
+    assert api.matches(b"GTGACTATGAGGAT", ix) == b"---------MMM--"
+
+
+def test_golden_map_unrefined_k7():
+    b = "lib.rs::doc@664"  # lib.rs:670-689, :698-717
+    ix = api.build([g(b, "query")], api.BuildOpts(k=7, build_select=True))
+    o = api.MapOpts(max_error_prob=0.1, fill_gaps=False, call_variants=False)
+    assert api.map(g(b, "reference"), ix, o) == g(b, "expected")
+    o.format = False
+    assert api.map(g(b, "reference"), ix, o) == g("lib.rs::doc@692", "expected")
+
+
+def test_golden_find_k31():
+    b = "lib.rs::doc@779"  # lib.rs:786-806
+    ix = api.build([g(b, "gene1"), g(b, "gene2_rc")], api.BuildOpts(k=31))
+    assert (ix.n_kmers, ix.n_sets) == (1176, 1237)
+    got = api.find(g(b, "query"), ix, api.FindOpts(max_gap_len=50))
+    assert rle_tuples(got) == [(0, 513, 512, 1, 0, 0, 0), (593, 1340, 709, 0, 0, 38, 3)]
+
+
+def test_golden_derandomize_translate_standalone():
+    ms = [1, 2, 2, 3, 2, 2, 3, 2, 1, 2, 3, 1, 1, 1, 2, 3, 1, 2]  # derandomize.rs:373-379
+    d = api.derandomize_ms_vec(ms, 3, 2)
+    assert d.tolist() == [0, 1, 2, 3, 1, 2, 3, 0, 1, 2, 3, -1, 0, 1, 2, 3, -1, 0]
+    assert api.translate_ms_vec(d, 3, 2) == b"XMMRRMMXMMM--MMM--"  # translate.rs:501-515
+    assert api.translate_ms_vec([1, 2, 3, 1, 2, 3, 3, 3, 3, 1, 2, 3], 3, 2) == b"MMRRMMMMRRMM"  # :518-532
+    # format.rs:229-247 chain, k=4 thr=3
+    ms4 = [1, 2, 3, 4, 1, 2, 3, 3, 3, 4, 4, 4, 4, 3, 1, 2, 3, 4, 4, 4, 4]
+    d4 = api.derandomize_ms_vec(ms4, 4, 3)
+    assert d4.tolist() == [1, 2, 3, 4, -1, 0, 1, 2, 3, 4, 4, 4, 4, 0, 1, 2, 3, 4, 4, 4, 4]
+    assert api.translate_ms_vec(d4, 4, 3) == b"MMMM--MMMMMMMXMMMMMMM"
+
+
+def test_golden_intervals_pin_unique_kmers():
+    # gap_filling.rs:535-564: the unique interval at position 16 decodes to CAGACAGCT (k=9)
+    b = "gap_filling.rs::nearest_unique_context"
+    ix = api.build([g(b, "query")], api.BuildOpts(k=9, build_select=True))
+    d, l, r = api.query_sbwt(g(b, "reference"), ix)
+    idx = 16
+    while r[idx] - l[idx] != 1:
+        idx -= 1
+    assert idx == 16 and ix.access_kmer(int(l[idx])) == b"CAGACAGCT"
+    # gap_filling.rs:567-600: search + access_kmer
+    b = "gap_filling.rs::left_extend_kmer"
+    ix = api.build([g(b, "sequence")], api.BuildOpts(k=6, build_select=True))
+    lo, hi = ix.search(g(b, "query"))
+    assert hi - lo == 1 and ix.access_kmer(lo) == b"GACTGC"
+
+
+# --------------------------------------------------------------------- index vs oracle ---
+@pytest.mark.parametrize("k,revcomp", [(3, False), (31, False), (31, True), (51, False), (64, False)])
+def test_index_build_matches_oracle(k, revcomp):
+    ref = with_ns(rand_seq(60_000, 7), 8, rate=0.0005)
+    seqs = [ref[:30_000], ref[30_000:], ref[500:900]]
+    o = O.OracleIndex(seqs, k=k, add_revcomp=revcomp)
+    ix = api.build(seqs, api.BuildOpts(k=k, add_revcomp=revcomp, num_threads=2))
+    assert (ix.k, ix.n_sets, ix.n_kmers) == (o.k, o.n_sets, o.n_kmers)
+    rows, lcs, Cc = ix.export_parts()
+    for a, b_ in zip(rows, o.rows()):
+        assert np.array_equal(a, b_)
+    assert np.array_equal(lcs, o.lcs()) and np.array_equal(Cc, o.C())
+
+
+def test_index_from_parts_roundtrip():
+    ref = rand_seq(20_000, 3)
+    o = O.OracleIndex([ref], k=31)
+    ix = api.index_from_parts(31, o.n_sets, o.n_kmers, o.rows(), o.lcs())
+    q = synth.mutate(np.frombuffer(ref, dtype=np.uint8), 4).tobytes()[:6000]
+    d, l, r = api.query_sbwt(q, ix)
+    od, ol, orr = o.query_sbwt(q)
+    assert np.array_equal(d, od) and np.array_equal(l, ol) and np.array_equal(r, orr)
+    for i in (0, 1, 17, o.n_sets - 1):
+        assert ix.access_kmer(i) == o.access_kmer(i)
+
+
+# ------------------------------------------------------------------------ MS vs oracle ---
+@pytest.mark.parametrize("k", [3, 7, 20, 31, 51, 63])
+def test_query_sbwt_matches_oracle(k):
+    ref = rand_seq(50_000, 11)
+    asm = synth.mutate(np.frombuffer(ref, dtype=np.uint8), 12).tobytes()
+    o = O.OracleIndex([asm], k=k)
+    ix = api.build([asm], api.BuildOpts(k=k))
+    queries = [ref[:20_000], with_ns(ref[20_000:26_000], 5, 0.02), rand_seq(3000, 13), ref[30_000:30_003], b"N",
+               ref[31_000:31_257], b"ACGT" * 40 + b"$" + ref[100:400], b"acgtacgt" + ref[40_000:40_100]]
+    for chunk_len in (32, 128, 1024):
+        api.set_chunk_len(chunk_len)
+        d, l, r, off = api.query_sbwt_batch(queries, ix)
+        for i, q in enumerate(queries):
+            od, ol, orr = o.query_sbwt(q)
+            a, b_ = int(off[i]), int(off[i + 1])
+            assert np.array_equal(d[a:b_].astype(np.uint64), od), (k, chunk_len, i)
+            assert np.array_equal(l[a:b_].astype(np.uint64), ol), (k, chunk_len, i)
+            assert np.array_equal(r[a:b_].astype(np.uint64), orr), (k, chunk_len, i)
+    api.set_chunk_len(0)
+    with pytest.raises(api.KboPanic) as e:  # index.rs:248
+        api.query_sbwt(b"", ix)
+    assert e.value.status == 1
+
+
+def test_ms_invariants_large():
+    """Size-independent properties at a larger size: chunking never changes the result, MS grows by
+    at most one per base, intervals are non-empty and inside [0, n_sets]."""
+    ref = synth.random_seq(600_000, 31)
+    asm = synth.mutate(ref, 32)
+    ix = api.build([asm.tobytes()], api.BuildOpts(k=31, num_threads=4))
+    outs = []
+    for chunk_len in (64, 256, 4096):
+        api.set_chunk_len(chunk_len)
+        outs.append(api.query_sbwt_batch([ref.tobytes()], ix))
+    api.set_chunk_len(0)
+    d, l, r, _ = outs[0]
+    for d2, l2, r2, _ in outs[1:]:
+        assert np.array_equal(d, d2) and np.array_equal(l, l2) and np.array_equal(r, r2)
+    di = d.astype(np.int64)
+    assert (di[1:] <= di[:-1] + 1).all() and di.max() == 31
+    assert (l < r).all() and (r <= ix.n_sets).all()
+    assert ((d > 0) | ((l == 0) & (r == ix.n_sets))).all()
+
+
+# ------------------------------------------------------------------- matches vs oracle ---
+@pytest.mark.parametrize("k,p", [(31, 1e-7), (20, 1e-3), (51, 1e-7), (7, 0.1)])
+def test_matches_batch_matches_oracle(k, p):
+    ref = synth.random_seq(80_000, 21)
+    o = O.OracleIndex([ref.tobytes()], k=k)
+    ix = api.build([ref.tobytes()], api.BuildOpts(k=k))
+    genes, off = synth.gene_queries(ref, 200, 1000, 22)
+    queries = [genes[int(off[i]):int(off[i + 1])].tobytes() for i in range(200)]
+    asm = synth.mutate(ref, 23).tobytes()
+    queries += [asm[:30_000], rand_seq(5000, 24), with_ns(asm[30_000:34_000], 25, 0.01), asm[40_000:40_003],
+                asm[41_000:41_511], asm[42_000:42_512], asm[43_000:43_513], b"A" * 3000, b"AC" * 2000]
+    for chunk_len in (64, 0):
+        api.set_chunk_len(chunk_len)
+        got = api.matches_batch(queries, ix, api.MatchOpts(max_error_prob=p))
+        for i, (g_, q) in enumerate(zip(got, queries)):
+            assert g_ == o.matches(q, p), (k, p, chunk_len, i)
+    api.set_chunk_len(0)
+
+
+def test_matches_preconditions():
+    ix = api.build([rand_seq(5000, 1)], api.BuildOpts(k=31))
+    for q, status in [(b"", 1), (b"AC", 3)]:  # index.rs:248, derandomize.rs:276
+        with pytest.raises(api.KboPanic) as e:
+            api.matches(q, ix)
+        assert e.value.status == status
+    with pytest.raises(api.KboPanic) as e:   # derandomize.rs:136-137
+        api.matches(b"ACGTACGT", ix, api.MatchOpts(max_error_prob=0.0))
+    assert e.value.status == 6
+    tiny = api.build([b"ACGT"], api.BuildOpts(k=2))
+    with pytest.raises(api.KboPanic) as e:   # threshold 1 -> derandomize.rs:275
+        api.matches(b"ACGTACGT", tiny, api.MatchOpts(max_error_prob=0.9999))
+    assert e.value.status == 2
+
+
+def test_matches_config2_shape_checksum():
+    """BASELINE config 2 shape at 1/10 scale through the batch API: every query equals the oracle."""
+    ref = synth.random_seq(500_000, synth.SEED_C2_REF)
+    o = O.OracleIndex([ref.tobytes()], k=31)
+    ix = api.build([ref.tobytes()], api.BuildOpts(k=31, num_threads=4))
+    concat, off = synth.gene_queries(ref, 1000, 1000, synth.SEED_C2_GENES)
+    got = api.matches_csr(concat, off, ix)
+    _, want, _ = o.matches_batch(concat, off, n_threads=4)
+    assert np.array_equal(got[:len(concat)], want)
+    frac_m = (got[:len(concat)] == ord("M")).mean()
+    assert 0.5 < frac_m < 1.0
+
+
+# ----------------------------------------------------- standalone derandomize / translate ---
+def valid_ms_vector(rng, n, k):
+    out = np.zeros(n, dtype=np.int64)
+    cur = int(rng.integers(0, k + 1))
+    for i in range(n):
+        out[i] = cur
+        u = rng.random()
+        if u < 0.45:
+            cur = min(cur + 1, k)
+        elif u < 0.80:
+            pass
+        elif u < 0.9:
+            cur = int(rng.integers(0, cur + 1))
+        else:
+            cur = max(cur - int(rng.integers(1, 4)), 0)
+    return out
+
+
+@pytest.mark.parametrize("k,thr", [(3, 2), (31, 15), (31, 22), (63, 40), (3, 3)])
+def test_derandomize_translate_arbitrary_vectors(k, thr):
+    rng = np.random.default_rng(k + thr)
+    for n in (3, 255, 1024, 1025, 20_000):
+        for kind in range(3):
+            ms = (rng.integers(0, k + 1, size=n) if kind == 0 else
+                  np.clip(rng.integers(thr - 2, thr + 4, size=n), 0, k) if kind == 1 else valid_ms_vector(rng, n, k))
+            want = O.derandomize_ms_vec(ms, k, thr)
+            got = api.derandomize_ms_vec(ms, k, thr)
+            assert np.array_equal(got, want), (n, kind)
+            assert api.translate_ms_vec(got, k, thr) == O.translate_ms_vec(want, k, thr)
+        d = rng.integers(-5, k + 1, size=n)
+        assert api.translate_ms_vec(d, k, thr) == O.translate_ms_vec(d, k, thr)
+    with pytest.raises(api.KboPanic) as e:  # derandomize.rs:229
+        api.derandomize_ms_vec([1, 2, k + 1], k, thr)
+    assert e.value.status == 7
+
+
+def test_find_batch_matches_oracle():
+    ref = synth.random_seq(100_000, 41)
+    o = O.OracleIndex([ref.tobytes()], k=31)
+    ix = api.build([ref.tobytes()], api.BuildOpts(k=31))
+    asm = synth.mutate(ref, 42, snp=0.02, indel=0.002).tobytes()
+    queries = [asm[i * 3000:(i + 1) * 3000] for i in range(20)] + [rand_seq(2000, 43)]
+    for gap in (0, 50):
+        got = api.find_batch(queries, ix, api.FindOpts(max_gap_len=gap))
+        for g_, q in zip(got, queries):
+            assert rle_tuples(g_) == o.find(q, max_gap_len=gap)
+
+
+def test_counters_and_launch_count():
+    ref = synth.random_seq(50_000, 51)
+    ix = api.build([ref.tobytes()], api.BuildOpts(k=31))
+    api.set_profile_counters(True)
+    n0 = api.kernel_launch_count()
+    q = synth.mutate(ref, 52).tobytes()[:40_000]
+    api.matches(q, ix)
+    api.set_profile_counters(False)
+    assert api.kernel_launch_count() - n0 == 3  # pack, MS, derandomize+translate
+    c = ix.ms_counters()
+    assert c["bases_emitted"] == len(q) + 1
+    assert c["bases_processed"] >= c["bases_emitted"]
+    assert c["extend_attempts"] >= len(q) * 0.9
+    assert ix.last_kernel_ms() > 0

@@ -155,6 +155,13 @@ int kbo_matches_batch_device(const kbo_index* ix, const uint8_t* d_concat, const
 int kbo_find_batch(const kbo_index* ix, const uint8_t* concat, const uint64_t* offsets, uint64_t n_queries,
                    double max_error_prob, uint64_t max_gap_len, kbo_rle* rle_out, uint64_t rle_cap,
                    uint64_t* rle_offsets);
+/* Device-resident form of kbo_find_batch: d_concat, d_offsets, d_rle_out (rle_cap records) and d_rle_offsets
+ * (n_queries+1 u64) are device pointers; asynchronous on `stream`.  If more than rle_cap records are found
+ * only the first rle_cap are stored; d_rle_offsets[n_queries] always holds the true count. */
+int kbo_find_batch_device(const kbo_index* ix, const uint8_t* d_concat, const uint64_t* d_offsets,
+                          const uint64_t* host_offsets, uint64_t n_queries, double max_error_prob,
+                          uint64_t max_gap_len, kbo_rle* d_rle_out, uint64_t rle_cap, uint64_t* d_rle_offsets,
+                          void* stream);
 /* kbo::map without refinement (lib.rs:726-738,756-760 with fill_gaps = call_variants = false):
  * `format` != 0 applies relative_to_ref, else the raw translation characters are returned. */
 int kbo_map_unrefined(const kbo_index* query_index, const uint8_t* ref_seq, uint64_t len, double max_error_prob,

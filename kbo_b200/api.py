@@ -38,7 +38,7 @@ EXPORTED_SYMBOLS = [
     "kbo_index_access_kmer", "kbo_index_search", "kbo_query_sbwt", "kbo_query_sbwt_batch_compact",
     "kbo_log_rm_max_cdf", "kbo_random_match_threshold", "kbo_derandomize_ms_vec", "kbo_translate_ms_vec",
     "kbo_run_lengths_gapped", "kbo_relative_to_ref", "kbo_matches", "kbo_matches_batch", "kbo_matches_batch_device",
-    "kbo_find_batch", "kbo_map_unrefined", "kbo_set_profile_counters", "kbo_get_ms_counters", "kbo_set_chunk_len",
+    "kbo_find_batch", "kbo_find_batch_device", "kbo_map_unrefined", "kbo_set_profile_counters", "kbo_get_ms_counters", "kbo_set_chunk_len",
     "kbo_kernel_launch_count", "kbo_last_kernel_ms", "kbo_set_kernel_timing", "kbo_collect_kernel_times",
     "kbo_measure_random_sector_rate",
 ]
@@ -112,6 +112,8 @@ def load_library():
                                            C.c_void_p, C.c_void_p]
     L.kbo_find_batch.argtypes = [C.c_void_p, u8p, u64p, C.c_uint64, C.c_double, C.c_uint64, C.POINTER(RleC),
                                  C.c_uint64, u64p]
+    L.kbo_find_batch_device.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, u64p, C.c_uint64, C.c_double, C.c_uint64,
+                                        C.c_void_p, C.c_uint64, C.c_void_p, C.c_void_p]
     L.kbo_map_unrefined.argtypes = [C.c_void_p, u8p, C.c_uint64, C.c_double, C.c_int, u8p]
     L.kbo_set_profile_counters.argtypes = [C.c_int]
     L.kbo_get_ms_counters.argtypes = [C.c_void_p, C.POINTER(MsCountersC)]
@@ -470,6 +472,16 @@ def measure_random_sector_rate(buffer_bytes, dependent, device=0):
     out = C.c_double(0)
     _check(load_library().kbo_measure_random_sector_rate(device, buffer_bytes, int(dependent), C.byref(out)))
     return out.value
+
+
+def find_device(index, d_concat_ptr, d_offsets_ptr, host_offsets, d_rle_ptr, rle_cap, d_rle_offsets_ptr,
+                max_error_prob=0.0000001, max_gap_len=0, stream=0):
+    """kbo_find_batch_device: raw device pointers (ints); async on `stream`."""
+    off = np.ascontiguousarray(host_offsets, dtype=np.uint64)
+    _check(load_library().kbo_find_batch_device(index._h, C.c_void_p(d_concat_ptr), C.c_void_p(d_offsets_ptr),
+                                                _p(off, C.c_uint64), len(off) - 1, max_error_prob, max_gap_len,
+                                                C.c_void_p(d_rle_ptr), rle_cap, C.c_void_p(d_rle_offsets_ptr),
+                                                C.c_void_p(stream)))
 
 
 def matches_device(index, d_concat_ptr, d_offsets_ptr, host_offsets, d_out_ptr, max_error_prob=0.0000001, stream=0):

@@ -762,44 +762,117 @@ int kbo_relative_to_ref(const uint8_t* ref_seq, const uint8_t* aln, uint64_t n, 
     return KBO_OK;
 }
 
-int kbo_find_batch(const kbo_index* ix, const uint8_t* concat, const uint64_t* offsets, uint64_t n_queries,
+// K4 launches: per-query segment counts -> exclusive scan -> records (all on ws->stream)
+static int run_rle_count_scan(Workspace* ws, const uint8_t* d_aln, const uint64_t* d_offsets, uint64_t nq,
+                              uint32_t max_gap_len, uint64_t* d_rle_offsets) {
+    cudaStream_t st = ws->stream;
+    CUDA_TRY(ws->tmp32.ensure(nq * 4, st));
+    const unsigned threads = 128;
+    const unsigned blocks = (unsigned)((nq * 32 + threads - 1) / threads);
+    rle_kernel<false><<<blocks, threads, 0, st>>>(d_aln, d_offsets, nq, max_gap_len, ws->tmp32.as<uint32_t>(), nullptr,
+                                                  nullptr, 0);
+    LAUNCHED();
+    rle_scan_kernel<<<1, 1024, 0, st>>>(ws->tmp32.as<uint32_t>(), nq, d_rle_offsets);
+    LAUNCHED();
+    CUDA_TRY(cudaGetLastError());
+    return KBO_OK;
+}
+static int run_rle_write(Workspace* ws, const uint8_t* d_aln, const uint64_t* d_offsets, uint64_t nq,
+                         uint32_t max_gap_len, const uint64_t* d_rle_offsets, RleRecord* d_out, uint64_t cap) {
+    const unsigned threads = 128;
+    const unsigned blocks = (unsigned)((nq * 32 + threads - 1) / threads);
+    rle_kernel<true><<<blocks, threads, 0, ws->stream>>>(d_aln, d_offsets, nq, max_gap_len, nullptr, d_rle_offsets,
+                                                         d_out, cap);
+    LAUNCHED();
+    CUDA_TRY(cudaGetLastError());
+    return KBO_OK;
+}
+static_assert(sizeof(RleRecord) == sizeof(kbo_rle), "device and ABI RLE records must agree");
+
+int kbo_find_batch(const kbo_index* cix, const uint8_t* concat, const uint64_t* offsets, uint64_t n_queries,
                    double max_error_prob, uint64_t max_gap_len, kbo_rle* rle_out, uint64_t rle_cap,
                    uint64_t* rle_offsets) {
-    if (!rle_offsets) return fail(KBO_ERR_BAD_ARGUMENT, "rle_offsets is null");
+    kbo_index* ix = const_cast<kbo_index*>(cix);
+    if (!rle_offsets || !concat) return fail(KBO_ERR_BAD_ARGUMENT, "null argument");
     uint64_t total = 0;
-    int rc = check_offsets(offsets, n_queries, 1, &total);
+    uint32_t thr = 0;
+    int rc = matches_prologue(ix, offsets, n_queries, max_error_prob, &total, &thr);
     if (rc) return rc;
-    // alignment characters land in a pooled PINNED buffer so the device->host copy runs at PCIe speed
-    kbo_index* mix = const_cast<kbo_index*>(ix);
-    if (!mix) return fail(KBO_ERR_BAD_ARGUMENT, "index is null");
-    PinnedBuf pb;
-    {
-        std::lock_guard<std::mutex> g(mix->mu);
-        if (!mix->pinned_pool.empty()) { pb = mix->pinned_pool.back(); mix->pinned_pool.pop_back(); }
-    }
-    const size_t need = (size_t)offsets[n_queries] + 1;
-    if (pb.cap < need) {
-        if (pb.p) cudaFreeHost(pb.p);
-        pb.p = nullptr;
-        pb.cap = 0;
-        CUDA_TRY(cudaHostAlloc(&pb.p, need + need / 4, cudaHostAllocDefault));
-        pb.cap = need + need / 4;
-    }
-    uint8_t* aln = (uint8_t*)pb.p;
-    auto give_back = [&]() { std::lock_guard<std::mutex> g(mix->mu); mix->pinned_pool.push_back(pb); };
-    rc = kbo_matches_batch(ix, concat, offsets, n_queries, max_error_prob, aln);
-    if (rc) { give_back(); return rc; }
-    std::vector<kbo_rle> all;
-    rle_offsets[0] = 0;
-    for (uint64_t q = 0; q < n_queries; ++q) {
-        rc = host_run_lengths(aln + offsets[q], offsets[q + 1] - offsets[q], max_gap_len, &all);
-        if (rc) { give_back(); return rc; }
-        rle_offsets[q + 1] = all.size();
-    }
-    give_back();
-    if (all.size() > rle_cap) return fail(KBO_ERR_BUFFER_TOO_SMALL, "rle capacity too small");
-    if (rle_out && !all.empty()) std::memcpy(rle_out, all.data(), all.size() * sizeof(kbo_rle));
-    return KBO_OK;
+    const uint32_t gap = (uint32_t)std::min<uint64_t>(max_gap_len, 0x7fffffffull);
+    DeviceGuard dg(ix->device);
+    if (!dg.ok) return fail(KBO_ERR_CUDA, "cudaSetDevice failed");
+    Workspace* ws = nullptr;
+    rc = acquire_ws(ix, &ws);
+    if (rc) return rc;
+    const Geometry g = make_geometry(total, n_queries);
+    cudaStream_t st = ws->stream;
+    auto body = [&]() -> int {
+        CUDA_TRY(ws->ascii.ensure(total, st));
+        CUDA_TRY(ws->offsets.ensure((n_queries + 1) * 8, st));
+        CUDA_TRY(ws->out.ensure(total + 16, st));
+        CUDA_TRY(ws->tmp64.ensure((n_queries + 1) * 8, st));
+        CUDA_TRY(cudaMemcpyAsync(ws->ascii.p, concat + offsets[0], total, cudaMemcpyHostToDevice, st));
+        std::vector<uint64_t> rel(n_queries + 1);
+        for (uint64_t i = 0; i <= n_queries; ++i) rel[i] = offsets[i] - offsets[0];
+        CUDA_TRY(cudaMemcpyAsync(ws->offsets.p, rel.data(), (n_queries + 1) * 8, cudaMemcpyHostToDevice, st));
+        CUDA_TRY(cudaEventRecord(ws->ev0, st));
+        int rc2 = matches_device(ix, ws, ws->ascii.as<uint8_t>(), ws->offsets.as<uint64_t>(), n_queries, g, thr,
+                                 ws->out.as<uint8_t>(), 0);
+        if (rc2) return rc2;
+        rc2 = run_rle_count_scan(ws, ws->out.as<uint8_t>(), ws->offsets.as<uint64_t>(), n_queries, gap,
+                                 ws->tmp64.as<uint64_t>());
+        if (rc2) return rc2;
+        CUDA_TRY(cudaMemcpyAsync(rle_offsets, ws->tmp64.p, (n_queries + 1) * 8, cudaMemcpyDeviceToHost, st));
+        CUDA_TRY(cudaStreamSynchronize(st));
+        const uint64_t n_rle = rle_offsets[n_queries];
+        if (n_rle > rle_cap) return fail(KBO_ERR_BUFFER_TOO_SMALL, "rle capacity too small");
+        if (n_rle) {
+            if (!rle_out) return fail(KBO_ERR_BAD_ARGUMENT, "rle_out is null");
+            CUDA_TRY(ws->out2.ensure(n_rle * sizeof(RleRecord), st));
+            rc2 = run_rle_write(ws, ws->out.as<uint8_t>(), ws->offsets.as<uint64_t>(), n_queries, gap,
+                                ws->tmp64.as<uint64_t>(), ws->out2.as<RleRecord>(), n_rle);
+            if (rc2) return rc2;
+            CUDA_TRY(cudaEventRecord(ws->ev1, st));
+            CUDA_TRY(cudaMemcpyAsync(rle_out, ws->out2.p, n_rle * sizeof(RleRecord), cudaMemcpyDeviceToHost, st));
+        } else {
+            CUDA_TRY(cudaEventRecord(ws->ev1, st));
+        }
+        CUDA_TRY(cudaStreamSynchronize(st));
+        float ms = 0.f;
+        cudaEventElapsedTime(&ms, ws->ev0, ws->ev1);
+        ix->last_kernel_ms = ms;
+        return fetch_counters(ix, ws);
+    };
+    rc = body();
+    release_ws(ix, ws);
+    return rc;
+}
+
+int kbo_find_batch_device(const kbo_index* cix, const uint8_t* d_concat, const uint64_t* d_offsets,
+                          const uint64_t* host_offsets, uint64_t n_queries, double max_error_prob,
+                          uint64_t max_gap_len, kbo_rle* d_rle_out, uint64_t rle_cap, uint64_t* d_rle_offsets,
+                          void* stream) {
+    kbo_index* ix = const_cast<kbo_index*>(cix);
+    if (!d_concat || !d_offsets || !d_rle_out || !d_rle_offsets) return fail(KBO_ERR_BAD_ARGUMENT, "null argument");
+    uint64_t total = 0;
+    uint32_t thr = 0;
+    int rc = matches_prologue(ix, host_offsets, n_queries, max_error_prob, &total, &thr);
+    if (rc) return rc;
+    if (host_offsets[0] != 0) return fail(KBO_ERR_BAD_ARGUMENT, "device batches must have offsets[0] == 0");
+    const uint32_t gap = (uint32_t)std::min<uint64_t>(max_gap_len, 0x7fffffffull);
+    DeviceGuard dg(ix->device);
+    if (!dg.ok) return fail(KBO_ERR_CUDA, "cudaSetDevice failed");
+    Workspace* ws = nullptr;
+    rc = stream_ws(ix, (cudaStream_t)stream, &ws);
+    if (rc) return rc;
+    const Geometry g = make_geometry(total, n_queries);
+    CUDA_TRY(ws->out.ensure(total + 16, ws->stream));
+    rc = matches_device(ix, ws, d_concat, d_offsets, n_queries, g, thr, ws->out.as<uint8_t>(), 0);
+    if (rc) return rc;
+    rc = run_rle_count_scan(ws, ws->out.as<uint8_t>(), d_offsets, n_queries, gap, d_rle_offsets);
+    if (rc) return rc;
+    return run_rle_write(ws, ws->out.as<uint8_t>(), d_offsets, n_queries, gap, d_rle_offsets,
+                         reinterpret_cast<RleRecord*>(d_rle_out), rle_cap);
 }
 
 int kbo_map_unrefined(const kbo_index* query_index, const uint8_t* ref_seq, uint64_t len, double max_error_prob,

@@ -532,6 +532,123 @@ __global__ void __launch_bounds__(K2_WARPS * 32) derand_translate_kernel(TrParam
 }
 
 // ---------------------------------------------------------------------------
+// K4: format::run_lengths_gapped (format.rs:143-193) on the PLAIN translation
+// K2 produces (alphabet M - X R only), one warp per query.  The warp walks the
+// query 32 characters per round; the four ballots of a round are consumed by
+// a warp-uniform state machine over the runs of gap / non-gap characters:
+//   a gap run inside a segment is "pending" until the next aligned character;
+//   it closes the segment as soon as it grows past max_gap_len, and a trailing
+//   gap run is dropped (format.rs:180-184).  jumps counts 'R' preceded by 'R'.
+// WRITE == false counts the segments of each query; after an exclusive scan of
+// the counts (rle_scan_kernel) WRITE == true stores the records in query order.
+// ---------------------------------------------------------------------------
+struct RleRecord {
+    uint64_t start, end, matches, mismatches, jumps, gap_bases, gap_opens;  // == kbo_rle
+};
+
+template <bool WRITE>
+__global__ void __launch_bounds__(128) rle_kernel(const uint8_t* __restrict__ aln, const uint64_t* __restrict__ offsets,
+                                                  uint64_t nq, uint32_t max_gap_len, uint32_t* __restrict__ counts,
+                                                  const uint64_t* __restrict__ rle_offsets,
+                                                  RleRecord* __restrict__ out, uint64_t cap) {
+    const int lane = threadIdx.x & 31;
+    const uint64_t q = ((uint64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+    if (q >= nq) return;  // warp-uniform
+    const uint64_t a = offsets[q] - offsets[0];
+    const uint64_t len = offsets[q + 1] - offsets[q];
+    uint64_t slot = WRITE ? rle_offsets[q] : 0;
+    uint32_t n_seg = 0;
+    bool in_seg = false;
+    uint64_t start = 0, end = 0;
+    uint32_t nm = 0, nx = 0, nj = 0, gb = 0, go = 0, pend = 0, prev_r = 0;
+    for (uint64_t base = 0; base < len; base += 32) {
+        const uint64_t i = base + lane;
+        const uint8_t ch = i < len ? aln[a + i] : 0;
+        const uint32_t nv = len - base < 32 ? (uint32_t)(len - base) : 32u;
+        const uint32_t valid = nv == 32 ? 0xffffffffu : ((1u << nv) - 1u);
+        const uint32_t G = __ballot_sync(0xffffffffu, ch == '-') & valid;
+        const uint32_t N = valid & ~G;
+        const uint32_t Mm = __ballot_sync(0xffffffffu, ch == 'M' || ch == 'R' || ch == 'I') & N;
+        const uint32_t Rm = __ballot_sync(0xffffffffu, ch == 'R') & N;
+        const uint32_t J = Rm & ((Rm << 1) | prev_r);
+        prev_r = Rm >> 31;
+        uint32_t pos = 0;
+        while (pos < nv) {
+            if ((G >> pos) & 1u) {
+                const uint32_t rest = ~G >> pos;  // first zero of G at or after pos
+                uint32_t g = rest ? (uint32_t)(__ffs((int)rest) - 1) : 32u - pos;
+                if (g > nv - pos) g = nv - pos;
+                if (in_seg) {
+                    pend += g;
+                    if (pend > max_gap_len) {  // the gap outgrew max_gap_len: close without it
+                        if (WRITE && lane == 0 && slot < cap) {
+                            RleRecord rec = {start, end, nm, nx, nj, gb, go};
+                            out[slot] = rec;
+                        }
+                        ++slot; ++n_seg;
+                        in_seg = false;
+                        pend = 0;
+                    }
+                }
+                pos += g;
+            } else {
+                const uint32_t rest = ~N >> pos;
+                uint32_t n = rest ? (uint32_t)(__ffs((int)rest) - 1) : 32u - pos;
+                if (n > nv - pos) n = nv - pos;
+                const uint32_t run = (n == 32 ? 0xffffffffu : ((1u << n) - 1u)) << pos;
+                if (!in_seg) {
+                    in_seg = true;
+                    start = base + pos;
+                    nm = nx = nj = gb = go = 0;
+                } else if (pend) {
+                    gb += pend;
+                    go += 1;
+                }
+                pend = 0;
+                nm += __popc(Mm & run);
+                nx += __popc(N & ~Mm & run);
+                nj += __popc(J & run);
+                end = base + pos + n;
+                pos += n;
+            }
+        }
+    }
+    if (in_seg) {  // a trailing gap run is dropped
+        if (WRITE && lane == 0 && slot < cap) {
+            RleRecord rec = {start, end, nm, nx, nj, gb, go};
+            out[slot] = rec;
+        }
+        ++n_seg;
+    }
+    if (!WRITE && lane == 0) counts[q] = n_seg;
+}
+
+// exclusive scan of the per-query segment counts -> rle_offsets[0..nq]; one block
+__global__ void __launch_bounds__(1024) rle_scan_kernel(const uint32_t* __restrict__ counts, uint64_t nq,
+                                                        uint64_t* __restrict__ rle_offsets) {
+    __shared__ uint64_t part[1024];
+    const uint32_t t = threadIdx.x;
+    const uint64_t per = (nq + 1023) / 1024;
+    const uint64_t lo = (uint64_t)t * per, hi = lo + per < nq ? lo + per : nq;
+    uint64_t s = 0;
+    for (uint64_t i = lo; i < hi; ++i) s += counts[i];
+    part[t] = s;
+    __syncthreads();
+    for (uint32_t off = 1; off < 1024; off <<= 1) {
+        uint64_t o = t >= off ? part[t - off] : 0;
+        __syncthreads();
+        part[t] += o;
+        __syncthreads();
+    }
+    uint64_t run = t ? part[t - 1] : 0;
+    for (uint64_t i = lo; i < hi; ++i) {
+        rle_offsets[i] = run;
+        run += counts[i];
+    }
+    if (t == 1023) rle_offsets[nq] = part[1023];
+}
+
+// ---------------------------------------------------------------------------
 // K3: translate_ms_vec (translate.rs:263-293) for one arbitrary i64 vector.
 // ---------------------------------------------------------------------------
 __global__ void translate_i64_kernel(const int64_t* __restrict__ d, uint64_t n, uint32_t k, uint32_t thr,

@@ -210,6 +210,21 @@ void emu_derandomize_general(const uint64_t* ms, uint64_t n, uint32_t k, uint32_
                    [&]() { g35_tile_kernel<true>(ms, n, k, thr, min_.data(), nullptr, eps.data(), out); });
 }
 
+// K4: run_lengths_gapped on plain translations, CSR batch; returns the number of records (out has `cap` slots of 7 u64)
+uint64_t emu_rle_batch(const uint8_t* aln, const uint64_t* offsets, uint64_t nq, uint32_t max_gap_len, uint64_t* out7,
+                       uint64_t cap, uint64_t* rle_offsets) {
+    std::vector<uint32_t> counts(nq);
+    const unsigned threads = 128, blocks = (unsigned)((nq * 32 + threads - 1) / threads);
+    emu_launch_par(blocks, threads, [&]() {
+        rle_kernel<false>(aln, offsets, nq, max_gap_len, counts.data(), nullptr, nullptr, 0);
+    });
+    emu_launch_par(1, 1024, [&]() { rle_scan_kernel(counts.data(), nq, rle_offsets); });
+    emu_launch_par(blocks, threads, [&]() {
+        rle_kernel<true>(aln, offsets, nq, max_gap_len, nullptr, rle_offsets, (RleRecord*)out7, cap);
+    });
+    return rle_offsets[nq];
+}
+
 void emu_translate_i64(const int64_t* d, uint64_t n, uint32_t k, uint32_t thr, uint8_t* out) {
     emu_launch_seq((unsigned)((n + 255) / 256), 256, [&]() { translate_i64_kernel(d, n, k, thr, out); });
 }

@@ -54,6 +54,8 @@ def lib():
         L.emu_derand_translate_u8.argtypes = [u8p, C.c_uint64, C.c_uint32, C.c_uint32, u8p]
         L.emu_derandomize_general.argtypes = [u64p, C.c_uint64, C.c_uint32, C.c_uint32, i64p]
         L.emu_translate_i64.argtypes = [i64p, C.c_uint64, C.c_uint32, C.c_uint32, u8p]
+        L.emu_rle_batch.restype = C.c_uint64
+        L.emu_rle_batch.argtypes = [u8p, u64p, C.c_uint64, C.c_uint32, u64p, C.c_uint64, u64p]
         _lib = L
     return _lib
 
@@ -165,3 +167,16 @@ def translate_i64(d, k, thr):
     out = np.zeros(len(dd), dtype=np.uint8)
     lib().emu_translate_i64(_p(dd, C.c_int64), len(dd), k, thr, _p(out, C.c_uint8))
     return out.tobytes()
+
+
+def rle_batch(alns, max_gap_len):
+    """K4 on a list of plain translations; returns a list (per query) of 7-tuples."""
+    concat, offsets = csr(alns)
+    cap = len(concat) + 1
+    out = np.zeros(7 * cap, dtype=np.uint64)
+    roff = np.zeros(len(alns) + 1, dtype=np.uint64)
+    n = lib().emu_rle_batch(_p(concat, C.c_uint8), _p(offsets, C.c_uint64), len(alns), max_gap_len,
+                            _p(out, C.c_uint64), cap, _p(roff, C.c_uint64))
+    assert n == roff[-1]
+    return [[tuple(int(x) for x in out[7 * j:7 * j + 7]) for j in range(int(roff[i]), int(roff[i + 1]))]
+            for i in range(len(alns))]

@@ -212,3 +212,29 @@ def test_translate_i64_arbitrary_vectors(k, thr):
         for _ in range(20):
             d = rng.integers(-5, k + 1, size=n)
             assert E.translate_i64(d, k, thr) == O.translate_ms_vec(d, k, thr)
+
+
+# ------------------------------------------------------------------- K4: device RLE ---
+def test_rle_kernel_goldens():
+    aln = b"XMMRRMMXMMM--MMM--"
+    assert E.rle_batch([aln], 0) == [[(0, 11, 9, 2, 1, 0, 0), (13, 16, 3, 0, 0, 0, 0)]]  # format.rs:77-95
+    assert E.rle_batch([aln], 3) == [[(0, 16, 12, 2, 1, 2, 1)]]                            # format.rs:122-140
+    big = GOLD["format.rs::run_lengths"]["input"].encode()                                 # format.rs:295-330
+    assert E.rle_batch([big], 0) == [[(5, 33, 28, 0, 0, 0, 0), (81, 207, 126, 0, 0, 0, 0), (372, 423, 51, 0, 0, 0, 0),
+                                      (487, 512, 25, 0, 0, 0, 0)]]
+
+
+def test_rle_kernel_random_plain_alignments():
+    rng = np.random.default_rng(17)
+    for weights in ([8, 1, 1, 0.3], [2, 6, 1, 1], [1, 1, 1, 1]):
+        p = np.array(weights, dtype=float) / sum(weights)
+        for gap in (0, 1, 2, 5, 40):
+            alns = []
+            for n in (1, 2, 3, 31, 32, 33, 64, 65, 100, 1000, 1500):
+                a = np.frombuffer(b"M-XR", dtype=np.uint8)[rng.choice(4, size=n, p=p)].copy()
+                if a[0] == ord("R"):
+                    a[0] = ord("M")  # format.rs:176 panics on a leading 'R'
+                alns.append(a.tobytes())
+            got = E.rle_batch(alns, gap)
+            for g_, a in zip(got, alns):
+                assert g_ == O.run_lengths_gapped(a, gap), (gap, a[:80])

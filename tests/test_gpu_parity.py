@@ -270,6 +270,35 @@ def test_find_batch_matches_oracle():
             assert rle_tuples(g_) == o.find(q, max_gap_len=gap)
 
 
+def test_device_pointer_entry_points_match_host_entry_points():
+    """kbo_matches_batch_device / kbo_find_batch_device on torch-owned device memory and stream."""
+    import torch
+    ref = synth.random_seq(100_000, 61)
+    o = O.OracleIndex([ref.tobytes()], k=31)
+    ix = api.build([ref.tobytes()], api.BuildOpts(k=31))
+    concat, off = synth.gene_queries(ref, 300, 700, 62, snp=0.03)
+    d_in = torch.from_numpy(concat).cuda()
+    d_off = torch.from_numpy(off.astype(np.int64)).cuda()
+    d_out = torch.zeros(len(concat) + 16, dtype=torch.uint8, device="cuda")
+    stream = torch.cuda.Stream()
+    with torch.cuda.stream(stream):
+        api.matches_device(ix, d_in.data_ptr(), d_off.data_ptr(), off, d_out.data_ptr(), 1e-7, stream.cuda_stream)
+        cap = 4096
+        d_rle = torch.zeros(cap * 7, dtype=torch.int64, device="cuda")
+        d_roff = torch.zeros(len(off), dtype=torch.int64, device="cuda")
+        api.find_device(ix, d_in.data_ptr(), d_off.data_ptr(), off, d_rle.data_ptr(), cap, d_roff.data_ptr(), 1e-7, 25,
+                        stream.cuda_stream)
+    stream.synchronize()
+    _, want, _ = o.matches_batch(concat, off, n_threads=4)
+    assert np.array_equal(d_out.cpu().numpy()[:len(concat)], want)
+    roff = d_roff.cpu().numpy()
+    rle = d_rle.cpu().numpy().reshape(-1, 7)
+    assert roff[-1] <= cap
+    for q in range(300):
+        got = [tuple(int(x) for x in rle[j]) for j in range(int(roff[q]), int(roff[q + 1]))]
+        assert got == o.find(concat[int(off[q]):int(off[q + 1])].tobytes(), max_gap_len=25)
+
+
 def test_counters_and_launch_count():
     ref = synth.random_seq(50_000, 51)
     ix = api.build([ref.tobytes()], api.BuildOpts(k=31))

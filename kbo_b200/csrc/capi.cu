@@ -192,7 +192,7 @@ static int upload_index(kbo_index* ix) {
     ix->rank_stride = stride;
     ix->device_bytes = rank.size() * 8 + lcs.size();
     ix->view.rank = ix->d_rank;
-    ix->view.rank_stride = stride;
+    ix->view.rank_stride = (uint32_t)stride;
     ix->view.lcs = ix->d_lcs;
     ix->view.n = (uint32_t)n;
     ix->view.k = h.k;

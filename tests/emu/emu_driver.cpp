@@ -28,7 +28,7 @@ struct EmuIndex {
 static void finish(EmuIndex* e) {
     build_device_layout(e->host, &e->lay);
     e->view.rank = e->lay.rank.data();
-    e->view.rank_stride = e->lay.stride;
+    e->view.rank_stride = (uint32_t)e->lay.stride;
     e->view.lcs = e->lay.lcs.data();
     e->view.n = (uint32_t)e->host.n_sets;
     e->view.k = e->host.k;

@@ -767,10 +767,11 @@ static int run_rle_count_scan(Workspace* ws, const uint8_t* d_aln, const uint64_
                               uint32_t max_gap_len, uint64_t* d_rle_offsets) {
     cudaStream_t st = ws->stream;
     CUDA_TRY(ws->tmp32.ensure(nq * 4, st));
+    CUDA_TRY(ws->out3.ensure(nq * RLE_STAGE * sizeof(RleRecord), st));
     const unsigned threads = 128;
     const unsigned blocks = (unsigned)((nq * 32 + threads - 1) / threads);
-    rle_kernel<false><<<blocks, threads, 0, st>>>(d_aln, d_offsets, nq, max_gap_len, ws->tmp32.as<uint32_t>(), nullptr,
-                                                  nullptr, 0);
+    rle_kernel<false><<<blocks, threads, 0, st>>>(d_aln, d_offsets, nq, max_gap_len, ws->tmp32.as<uint32_t>(),
+                                                  ws->out3.as<RleRecord>(), nullptr, nullptr, 0);
     LAUNCHED();
     rle_scan_kernel<<<1, 1024, 0, st>>>(ws->tmp32.as<uint32_t>(), nq, d_rle_offsets);
     LAUNCHED();
@@ -781,8 +782,8 @@ static int run_rle_write(Workspace* ws, const uint8_t* d_aln, const uint64_t* d_
                          uint32_t max_gap_len, const uint64_t* d_rle_offsets, RleRecord* d_out, uint64_t cap) {
     const unsigned threads = 128;
     const unsigned blocks = (unsigned)((nq * 32 + threads - 1) / threads);
-    rle_kernel<true><<<blocks, threads, 0, ws->stream>>>(d_aln, d_offsets, nq, max_gap_len, nullptr, d_rle_offsets,
-                                                         d_out, cap);
+    rle_kernel<true><<<blocks, threads, 0, ws->stream>>>(d_aln, d_offsets, nq, max_gap_len, ws->tmp32.as<uint32_t>(),
+                                                         ws->out3.as<RleRecord>(), d_rle_offsets, d_out, cap);
     LAUNCHED();
     CUDA_TRY(cudaGetLastError());
     return KBO_OK;

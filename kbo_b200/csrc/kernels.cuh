@@ -546,81 +546,137 @@ struct RleRecord {
     uint64_t start, end, matches, mismatches, jumps, gap_bases, gap_opens;  // == kbo_rle
 };
 
+enum { RLE_STAGE = 8 };  // records per query kept in the staging buffer by the counting pass
+
+struct RleState {
+    uint64_t start, end;
+    uint32_t nm, nx, nj, gb, go, pend, prev_r, n_seg;
+    bool in_seg;
+};
+
+// Stores one finished record: staging slot (counting pass) or final slot (write pass).
+template <bool WRITE>
+__device__ __forceinline__ void rle_emit(const RleState& st, int lane, RleRecord* __restrict__ dst, uint64_t slot0,
+                                         uint64_t cap) {
+    const uint64_t slot = slot0 + st.n_seg;
+    const bool ok = WRITE ? (slot < cap) : (st.n_seg < RLE_STAGE);
+    if (lane == 0 && ok) {
+        RleRecord rec = {st.start, st.end, st.nm, st.nx, st.nj, st.gb, st.go};
+        dst[slot] = rec;
+    }
+}
+
+// One round of 32 characters (lane i holds character base+i; `nv` of them are valid).
+template <bool WRITE>
+__device__ __forceinline__ void rle_round(RleState& st, uint8_t ch, uint64_t base, uint32_t nv, uint32_t max_gap_len,
+                                          int lane, RleRecord* __restrict__ dst, uint64_t slot0, uint64_t cap) {
+    const uint32_t valid = nv == 32 ? 0xffffffffu : ((1u << nv) - 1u);
+    const uint32_t G = __ballot_sync(0xffffffffu, ch == '-') & valid;
+    const uint32_t N = valid & ~G;
+    const uint32_t Mm = __ballot_sync(0xffffffffu, ch == 'M' || ch == 'R' || ch == 'I') & N;
+    const uint32_t Rm = __ballot_sync(0xffffffffu, ch == 'R') & N;
+    const uint32_t J = Rm & ((Rm << 1) | st.prev_r);
+    st.prev_r = Rm >> 31;
+    if (G == 0 && nv == 32 && st.in_seg && st.pend == 0) {  // fast path: 32 aligned characters inside a segment
+        st.nm += __popc(Mm);
+        st.nx += __popc(~Mm);
+        st.nj += __popc(J);
+        st.end = base + 32;
+        return;
+    }
+    uint32_t pos = 0;
+    while (pos < nv) {
+        if ((G >> pos) & 1u) {
+            const uint32_t rest = ~G >> pos;  // first zero of G at or after pos
+            uint32_t g = rest ? (uint32_t)(__ffs((int)rest) - 1) : 32u - pos;
+            if (g > nv - pos) g = nv - pos;
+            if (st.in_seg) {
+                st.pend += g;
+                if (st.pend > max_gap_len) {  // the gap outgrew max_gap_len: close without it
+                    rle_emit<WRITE>(st, lane, dst, slot0, cap);
+                    ++st.n_seg;
+                    st.in_seg = false;
+                    st.pend = 0;
+                }
+            }
+            pos += g;
+        } else {
+            const uint32_t rest = ~N >> pos;
+            uint32_t n = rest ? (uint32_t)(__ffs((int)rest) - 1) : 32u - pos;
+            if (n > nv - pos) n = nv - pos;
+            const uint32_t run = (n == 32 ? 0xffffffffu : ((1u << n) - 1u)) << pos;
+            if (!st.in_seg) {
+                st.in_seg = true;
+                st.start = base + pos;
+                st.nm = st.nx = st.nj = st.gb = st.go = 0;
+            } else if (st.pend) {
+                st.gb += st.pend;
+                st.go += 1;
+            }
+            st.pend = 0;
+            st.nm += __popc(Mm & run);
+            st.nx += __popc(N & ~Mm & run);
+            st.nj += __popc(J & run);
+            st.end = base + pos + n;
+            pos += n;
+        }
+    }
+}
+
+// WRITE == false: count the segments of each query and keep the first RLE_STAGE records in `stage`.
+// WRITE == true : copy the staged records to their final slots; a query with more than RLE_STAGE
+//                 segments is recomputed and written directly.
 template <bool WRITE>
 __global__ void __launch_bounds__(128) rle_kernel(const uint8_t* __restrict__ aln, const uint64_t* __restrict__ offsets,
                                                   uint64_t nq, uint32_t max_gap_len, uint32_t* __restrict__ counts,
+                                                  RleRecord* __restrict__ stage,
                                                   const uint64_t* __restrict__ rle_offsets,
                                                   RleRecord* __restrict__ out, uint64_t cap) {
     const int lane = threadIdx.x & 31;
     const uint64_t q = ((uint64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
     if (q >= nq) return;  // warp-uniform
+    uint64_t slot0 = 0;
+    RleRecord* dst = stage + q * RLE_STAGE;
+    if (WRITE) {
+        slot0 = rle_offsets[q];
+        const uint32_t cnt = counts[q];
+        if (cnt <= RLE_STAGE) {  // common case: move the staged records (7 words each)
+            const uint64_t* src = reinterpret_cast<const uint64_t*>(stage + q * RLE_STAGE);
+            uint64_t* d64 = reinterpret_cast<uint64_t*>(out + slot0);
+            for (uint32_t w = lane; w < cnt * 7; w += 32)
+                if (slot0 + w / 7 < cap) d64[w] = src[w];
+            return;
+        }
+        dst = out;
+    }
     const uint64_t a = offsets[q] - offsets[0];
     const uint64_t len = offsets[q + 1] - offsets[q];
-    uint64_t slot = WRITE ? rle_offsets[q] : 0;
-    uint32_t n_seg = 0;
-    bool in_seg = false;
-    uint64_t start = 0, end = 0;
-    uint32_t nm = 0, nx = 0, nj = 0, gb = 0, go = 0, pend = 0, prev_r = 0;
-    for (uint64_t base = 0; base < len; base += 32) {
-        const uint64_t i = base + lane;
-        const uint8_t ch = i < len ? aln[a + i] : 0;
-        const uint32_t nv = len - base < 32 ? (uint32_t)(len - base) : 32u;
-        const uint32_t valid = nv == 32 ? 0xffffffffu : ((1u << nv) - 1u);
-        const uint32_t G = __ballot_sync(0xffffffffu, ch == '-') & valid;
-        const uint32_t N = valid & ~G;
-        const uint32_t Mm = __ballot_sync(0xffffffffu, ch == 'M' || ch == 'R' || ch == 'I') & N;
-        const uint32_t Rm = __ballot_sync(0xffffffffu, ch == 'R') & N;
-        const uint32_t J = Rm & ((Rm << 1) | prev_r);
-        prev_r = Rm >> 31;
-        uint32_t pos = 0;
-        while (pos < nv) {
-            if ((G >> pos) & 1u) {
-                const uint32_t rest = ~G >> pos;  // first zero of G at or after pos
-                uint32_t g = rest ? (uint32_t)(__ffs((int)rest) - 1) : 32u - pos;
-                if (g > nv - pos) g = nv - pos;
-                if (in_seg) {
-                    pend += g;
-                    if (pend > max_gap_len) {  // the gap outgrew max_gap_len: close without it
-                        if (WRITE && lane == 0 && slot < cap) {
-                            RleRecord rec = {start, end, nm, nx, nj, gb, go};
-                            out[slot] = rec;
-                        }
-                        ++slot; ++n_seg;
-                        in_seg = false;
-                        pend = 0;
-                    }
-                }
-                pos += g;
-            } else {
-                const uint32_t rest = ~N >> pos;
-                uint32_t n = rest ? (uint32_t)(__ffs((int)rest) - 1) : 32u - pos;
-                if (n > nv - pos) n = nv - pos;
-                const uint32_t run = (n == 32 ? 0xffffffffu : ((1u << n) - 1u)) << pos;
-                if (!in_seg) {
-                    in_seg = true;
-                    start = base + pos;
-                    nm = nx = nj = gb = go = 0;
-                } else if (pend) {
-                    gb += pend;
-                    go += 1;
-                }
-                pend = 0;
-                nm += __popc(Mm & run);
-                nx += __popc(N & ~Mm & run);
-                nj += __popc(J & run);
-                end = base + pos + n;
-                pos += n;
+    RleState st;
+    st.start = st.end = 0;
+    st.nm = st.nx = st.nj = st.gb = st.go = st.pend = st.prev_r = st.n_seg = 0;
+    st.in_seg = false;
+    for (uint64_t base = 0; base < len; base += 128) {
+        // four rounds of loads in flight before the first ballot
+        uint8_t ch[4];
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+            const uint64_t i = base + 32 * j + lane;
+            ch[j] = i < len ? aln[a + i] : 0;
+        }
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+            const uint64_t b = base + 32 * j;
+            if (b < len) {
+                const uint32_t nv = len - b < 32 ? (uint32_t)(len - b) : 32u;
+                rle_round<WRITE>(st, ch[j], b, nv, max_gap_len, lane, dst, slot0, cap);
             }
         }
     }
-    if (in_seg) {  // a trailing gap run is dropped
-        if (WRITE && lane == 0 && slot < cap) {
-            RleRecord rec = {start, end, nm, nx, nj, gb, go};
-            out[slot] = rec;
-        }
-        ++n_seg;
+    if (st.in_seg) {  // a trailing gap run is dropped
+        rle_emit<WRITE>(st, lane, dst, slot0, cap);
+        ++st.n_seg;
     }
-    if (!WRITE && lane == 0) counts[q] = n_seg;
+    if (!WRITE && lane == 0) counts[q] = st.n_seg;
 }
 
 // exclusive scan of the per-query segment counts -> rle_offsets[0..nq]; one block

@@ -29,6 +29,7 @@ static std::atomic<uint64_t> g_launches(0);
 static std::atomic<int> g_profile_counters(0);
 static std::atomic<uint32_t> g_chunk_len(0);
 static std::atomic<int> g_kernel_timing(0);
+static std::atomic<uint32_t> g_probe_iters(3);
 
 static int fail(int code, const std::string& msg) {
     g_err = msg;
@@ -259,6 +260,7 @@ static int run_ms(kbo_index* ix, Workspace* ws, const QueryView& qv, const Geome
     mp.ix = ix->view;
     mp.q = qv;
     mp.chunk_len = g.chunk_len;
+    mp.probe_iters = g_probe_iters.load();
     mp.n_chunks = g.n_chunks;
     mp.ms = ws->ms.as<uint8_t>();
     mp.l_out = intervals ? ws->l.as<uint32_t>() : nullptr;
@@ -982,6 +984,7 @@ int kbo_get_ms_counters(const kbo_index* cix, kbo_ms_counters* out) {
     return KBO_OK;
 }
 int kbo_set_chunk_len(uint32_t chunk_len) { g_chunk_len = chunk_len; return KBO_OK; }
+int kbo_set_probe_iters(uint32_t iters) { g_probe_iters = iters ? iters : 1; return KBO_OK; }
 uint64_t kbo_kernel_launch_count(void) { return g_launches.load(); }
 float kbo_last_kernel_ms(const kbo_index* ix) { return ix ? ix->last_kernel_ms : 0.f; }
 

@@ -127,7 +127,8 @@ __global__ void pack_queries_kernel(const uint8_t* __restrict__ ascii, const uin
 struct MsParams {
     IndexView ix;
     QueryView q;
-    uint32_t chunk_len;  // multiple of 32
+    uint32_t chunk_len;    // multiple of 32
+    uint32_t probe_iters;  // probe iterations per contraction phase (>= 1)
     uint64_t n_chunks;
     uint8_t* ms;         // padded space, 1 byte per position
     uint32_t* l_out;     // optional (INTERVALS)
@@ -135,12 +136,15 @@ struct MsParams {
     unsigned long long* counters;  // optional (COUNT)
 };
 
-__device__ __forceinline__ uint64_t lcs_lt_mask(uint64_t w, uint64_t t_rep) {
+__device__ __forceinline__ uint32_t lcs_lt_mask32(uint32_t w, uint32_t t_rep) {
     // 0x80 in every byte of w that is < t (bytes and t are < 128)
-    const uint64_t H = 0x8080808080808080ull;
-    return ~((w | H) - t_rep) & H;
+    return ~((w | 0x80808080u) - t_rep) & 0x80808080u;
 }
 
+// Loop structure: `probe_iters` probe iterations (lanes whose extension failed sit out the rest of
+// the group), then ONE contraction phase executed together by every lane that failed.  The divergent
+// contraction code (~40 % of the static loop body, used by ~10 % of the lanes per iteration) is thus
+// issued once per group instead of once per iteration.  All position arithmetic is 32-bit.
 template <bool INTERVALS, bool COUNT>
 __global__ void __launch_bounds__(256) ms_kernel(MsParams p) {
     const uint64_t g = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
@@ -149,98 +153,113 @@ __global__ void __launch_bounds__(256) ms_kernel(MsParams p) {
     if (g < p.n_chunks) {
         const uint32_t n = p.ix.n, k = p.ix.k;
         const uint64_t start = g * p.chunk_len;
-        uint64_t end = start + p.chunk_len;
-        if (end > p.q.Lp) end = p.q.Lp;
-        uint64_t pos = start >= (uint64_t)(k - 1) ? start - (k - 1) : 0;
-        uint64_t qw = __ldg(p.q.pack + (pos >> 5)) >> (2 * (pos & 31));
-        uint32_t iw = __ldg(p.q.inv + (pos >> 5)) >> (pos & 31);
-        uint32_t l = 0, r = n, d = 0;
-        uint32_t acc = 0;
-        while (pos < end) {
-            bool advance;
-            if (iw & 1) {
-                l = 0; r = n; d = 0;
-                advance = true;
-            } else {
-                const uint32_t rowoff = ((uint32_t)qw & 3u) * p.ix.rank_stride;  // 32-bit word index
-                const uint32_t bl = l >> 5, br = r >> 5;
-                const uint64_t wl = __ldg(p.ix.rank + (rowoff + bl));
-                const uint64_t wr = (br == bl) ? wl : __ldg(p.ix.rank + (rowoff + br));
-                const uint32_t nl = (uint32_t)(wl >> 32) + __popc((uint32_t)wl & ((1u << (l & 31)) - 1u));
-                const uint32_t nr = (uint32_t)(wr >> 32) + __popc((uint32_t)wr & ((1u << (r & 31)) - 1u));
-                if (COUNT) {
-                    const bool sp = (bl >> 2) != (br >> 2);
-                    ++cnt_att; cnt_split += sp;
-                    if (pos >= start) { ++cnt_att_e; cnt_split_e += sp; }
-                }
-                if (nl < nr) {
-                    l = nl; r = nr;
-                    d = d + 1 < k ? d + 1 : k;
+        const uint64_t remain = p.q.Lp - start;
+        const uint32_t len = remain < p.chunk_len ? (uint32_t)remain : p.chunk_len;
+        const uint32_t warm = start >= (uint64_t)(k - 1) ? k - 1 : (uint32_t)start;  // warm-up bases
+        const uint64_t pos0 = start - warm;
+        const uint64_t wbase = pos0 >> 5;
+        const uint64_t* __restrict__ qptr = p.q.pack + wbase;
+        const uint32_t* __restrict__ iptr = p.q.inv + wbase;
+        uint8_t* msw = p.ms + (wbase << 5);        // address of "bit position" 0 of this chunk
+        uint32_t bp = (uint32_t)(pos0 & 31);       // position relative to the first loaded query word
+        const uint32_t bp_emit = bp + warm;        // first emitted position
+        const uint32_t bp_end = bp_emit + len;
+        uint64_t qw = __ldg(qptr) >> (2 * bp);
+        uint32_t iw = __ldg(iptr) >> bp;
+        uint32_t l = 0, r = n, d = 0, acc = 0;
+        bool failed = false;
+        while (bp < bp_end) {
+            // ---- probe phase ------------------------------------------------------------------
+#pragma unroll 1
+            for (uint32_t it = 0; it < p.probe_iters; ++it) {
+                if (failed || bp >= bp_end) continue;
+                bool advance;
+                if (iw & 1u) {
+                    l = 0; r = n; d = 0;
                     advance = true;
-                } else if (d == 0) {
-                    advance = true;  // state stays (0,[0,n))
                 } else {
-                    // contract_left to the largest target that changes the interval
-                    advance = false;
-                    uint32_t bl8 = l & ~7u, br8 = r & ~7u;
-                    uint64_t Wl = *reinterpret_cast<const uint64_t*>(p.ix.lcs + bl8);
-                    uint64_t Wr = (br8 == bl8) ? Wl : *reinterpret_cast<const uint64_t*>(p.ix.lcs + br8);
-                    const uint32_t vl = (uint32_t)(Wl >> (8 * (l & 7))) & 0xffu;
-                    const uint32_t vr = (uint32_t)(Wr >> (8 * (r & 7))) & 0xffu;  // LCS[n] reads the zero padding
-                    uint32_t t = vl > vr ? vl : vr;
-                    if (t > d - 1) t = d - 1;  // cannot happen for a maximal interval; keeps the literal bound
+                    const uint32_t rowoff = ((uint32_t)qw & 3u) * p.ix.rank_stride;  // 32-bit word index
+                    const uint32_t bl = l >> 5, br = r >> 5;
+                    const uint64_t wl = __ldg(p.ix.rank + (rowoff + bl));
+                    const uint64_t wr = (br == bl) ? wl : __ldg(p.ix.rank + (rowoff + br));
+                    const uint32_t nl = (uint32_t)(wl >> 32) + __popc((uint32_t)wl & ((1u << (l & 31)) - 1u));
+                    const uint32_t nr = (uint32_t)(wr >> 32) + __popc((uint32_t)wr & ((1u << (r & 31)) - 1u));
                     if (COUNT) {
-                        ++cnt_con; cnt_extra += (br8 != bl8);
-                        if (pos >= start) { ++cnt_con_e; cnt_extra_e += (br8 != bl8); }
+                        const bool sp = (bl >> 2) != (br >> 2);
+                        ++cnt_att; cnt_split += sp;
+                        if (bp >= bp_emit) { ++cnt_att_e; cnt_split_e += sp; }
                     }
-                    if (t == 0) {
-                        l = 0; r = n; d = 0;
+                    if (nl < nr) {
+                        l = nl; r = nr;
+                        d = d + 1 < k ? d + 1 : k;
+                        advance = true;
+                    } else if (d == 0) {
+                        advance = true;  // state stays (0,[0,n))
                     } else {
-                        d = t;
-                        const uint64_t T = (uint64_t)t * 0x0101010101010101ull;
-                        // left: largest p <= l with LCS[p] < t (LCS[0] = 0 stops the scan)
-                        uint64_t m = lcs_lt_mask(Wl, T);
-                        if ((l & 7) != 7) m &= (1ull << (8 * ((l & 7) + 1))) - 1ull;
-                        while (m == 0) {
-                            bl8 -= 8;
-                            Wl = *reinterpret_cast<const uint64_t*>(p.ix.lcs + bl8);
-                            m = lcs_lt_mask(Wl, T);
-                            if (COUNT) { ++cnt_extra; cnt_extra_e += (pos >= start); }
+                        advance = false;
+                        failed = true;
+                    }
+                }
+                if (advance) {
+                    if (COUNT) ++cnt_proc;
+                    if (bp >= bp_emit) {
+                        if (COUNT) ++cnt_emit;
+                        acc |= d << (8 * (bp & 3));
+                        if ((bp & 3) == 3 || bp + 1 == bp_end) {
+                            *reinterpret_cast<uint32_t*>(msw + (bp & ~3u)) = acc;
+                            acc = 0;
                         }
-                        l = bl8 + ((63 - __clzll((long long)m)) >> 3);
-                        // right: smallest p >= r with LCS[p] < t (zero padding at n stops the scan)
-                        m = lcs_lt_mask(Wr, T);
-                        m &= ~0ull << (8 * (r & 7));
-                        while (m == 0) {
-                            br8 += 8;
-                            Wr = *reinterpret_cast<const uint64_t*>(p.ix.lcs + br8);
-                            m = lcs_lt_mask(Wr, T);
-                            if (COUNT) { ++cnt_extra; cnt_extra_e += (pos >= start); }
+                        if (INTERVALS) {
+                            p.l_out[(wbase << 5) + bp] = l;
+                            p.r_out[(wbase << 5) + bp] = r;
                         }
-                        r = br8 + ((__ffsll((long long)m) - 1) >> 3);
+                    }
+                    ++bp;
+                    qw >>= 2;
+                    iw >>= 1;
+                    if ((bp & 31) == 0 && bp < bp_end) {
+                        qw = __ldg(qptr + (bp >> 5));
+                        iw = __ldg(iptr + (bp >> 5));
                     }
                 }
             }
-            if (advance) {
-                if (COUNT) ++cnt_proc;
-                if (pos >= start) {
-                    if (COUNT) ++cnt_emit;
-                    acc |= d << (8 * (pos & 3));
-                    if ((pos & 3) == 3 || pos + 1 == end) {
-                        *reinterpret_cast<uint32_t*>(p.ms + (pos & ~3ull)) = acc;
-                        acc = 0;
-                    }
-                    if (INTERVALS) {
-                        p.l_out[pos] = l;
-                        p.r_out[pos] = r;
-                    }
+            // ---- contraction phase: contract_left to the largest target that changes the interval ----
+            if (failed) {
+                failed = false;
+                const uint32_t bl4 = l & ~3u, br4 = r & ~3u;
+                const uint32_t Wl = *reinterpret_cast<const uint32_t*>(p.ix.lcs + bl4);
+                const uint32_t Wr = (br4 == bl4) ? Wl : *reinterpret_cast<const uint32_t*>(p.ix.lcs + br4);
+                if (COUNT) {
+                    ++cnt_con; cnt_extra += (br4 != bl4);
+                    if (bp >= bp_emit) { ++cnt_con_e; cnt_extra_e += (br4 != bl4); }
                 }
-                ++pos;
-                qw >>= 2;
-                iw >>= 1;
-                if ((pos & 31) == 0 && pos < end) {
-                    qw = __ldg(p.q.pack + (pos >> 5));
-                    iw = __ldg(p.q.inv + (pos >> 5));
+                const uint32_t vl = (Wl >> (8 * (l & 3))) & 0xffu;
+                const uint32_t vr = (Wr >> (8 * (r & 3))) & 0xffu;  // LCS[n] reads the zero padding
+                uint32_t t = vl > vr ? vl : vr;
+                if (t > d - 1) t = d - 1;  // cannot happen for a maximal interval; keeps the literal bound
+                if (t == 0) {
+                    l = 0; r = n; d = 0;
+                } else {
+                    d = t;
+                    const uint32_t T = t * 0x01010101u;
+                    // left: largest q <= l with LCS[q] < t (LCS[0] = 0 stops the scan)
+                    uint32_t m = lcs_lt_mask32(Wl, T) & ((2u << (8 * (l & 3) + 7)) - 1u);
+                    uint32_t b = bl4;
+                    while (m == 0) {
+                        b -= 4;
+                        m = lcs_lt_mask32(*reinterpret_cast<const uint32_t*>(p.ix.lcs + b), T);
+                        if (COUNT) { ++cnt_extra; cnt_extra_e += (bp >= bp_emit); }
+                    }
+                    l = b + ((31 - __clz((int)m)) >> 3);
+                    // right: smallest q >= r with LCS[q] < t (the zero padding at n stops the scan)
+                    m = lcs_lt_mask32(Wr, T) & (0xffffffffu << (8 * (r & 3)));
+                    b = br4;
+                    while (m == 0) {
+                        b += 4;
+                        m = lcs_lt_mask32(*reinterpret_cast<const uint32_t*>(p.ix.lcs + b), T);
+                        if (COUNT) { ++cnt_extra; cnt_extra_e += (bp >= bp_emit); }
+                    }
+                    r = b + ((__ffs((int)m) - 1) >> 3);
                 }
             }
         }

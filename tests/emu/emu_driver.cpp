@@ -19,6 +19,9 @@
 
 using namespace kbo_b200;
 
+static uint32_t g_emu_probe_iters = 3;
+extern "C" void emu_set_probe_iters(uint32_t v) { g_emu_probe_iters = v ? v : 1; }
+
 struct EmuIndex {
     HostIndex host;
     DeviceLayout lay;
@@ -74,6 +77,7 @@ static void stage_and_ms(EmuIndex* e, const uint8_t* concat, const uint64_t* off
     mp.ix = e->view;
     mp.q = qv;
     mp.chunk_len = g.chunk_len;
+    mp.probe_iters = g_emu_probe_iters;
     mp.n_chunks = g.n_chunks;
     mp.ms = s->ms.data();
     mp.l_out = intervals ? s->l.data() : nullptr;

@@ -136,9 +136,10 @@ struct MsParams {
     unsigned long long* counters;  // optional (COUNT)
 };
 
-__device__ __forceinline__ uint32_t lcs_lt_mask32(uint32_t w, uint32_t t_rep) {
+__device__ __forceinline__ uint64_t lcs_lt_mask64(uint64_t w, uint64_t t_rep) {
     // 0x80 in every byte of w that is < t (bytes and t are < 128)
-    return ~((w | 0x80808080u) - t_rep) & 0x80808080u;
+    const uint64_t H = 0x8080808080808080ull;
+    return ~((w | H) - t_rep) & H;
 }
 
 // Loop structure: `probe_iters` probe iterations (lanes whose extension failed sit out the rest of
@@ -146,7 +147,7 @@ __device__ __forceinline__ uint32_t lcs_lt_mask32(uint32_t w, uint32_t t_rep) {
 // contraction code (~40 % of the static loop body, used by ~10 % of the lanes per iteration) is thus
 // issued once per group instead of once per iteration.  All position arithmetic is 32-bit.
 template <bool INTERVALS, bool COUNT>
-__global__ void __launch_bounds__(256) ms_kernel(MsParams p) {
+__global__ void __launch_bounds__(256, 4) ms_kernel(MsParams p) {
     const uint64_t g = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
     unsigned long long cnt_att = 0, cnt_split = 0, cnt_con = 0, cnt_extra = 0, cnt_proc = 0, cnt_emit = 0;
     unsigned long long cnt_att_e = 0, cnt_split_e = 0, cnt_con_e = 0, cnt_extra_e = 0;
@@ -166,7 +167,7 @@ __global__ void __launch_bounds__(256) ms_kernel(MsParams p) {
         const uint32_t bp_end = bp_emit + len;
         uint64_t qw = __ldg(qptr) >> (2 * bp);
         uint32_t iw = __ldg(iptr) >> bp;
-        uint32_t l = 0, r = n, d = 0, acc = 0;
+        uint32_t l = 0, r = n, d = 0;
         bool failed = false;
         while (bp < bp_end) {
             // ---- probe phase ------------------------------------------------------------------
@@ -204,11 +205,7 @@ __global__ void __launch_bounds__(256) ms_kernel(MsParams p) {
                     if (COUNT) ++cnt_proc;
                     if (bp >= bp_emit) {
                         if (COUNT) ++cnt_emit;
-                        acc |= d << (8 * (bp & 3));
-                        if ((bp & 3) == 3 || bp + 1 == bp_end) {
-                            *reinterpret_cast<uint32_t*>(msw + (bp & ~3u)) = acc;
-                            acc = 0;
-                        }
+                        msw[bp] = (uint8_t)d;
                         if (INTERVALS) {
                             p.l_out[(wbase << 5) + bp] = l;
                             p.r_out[(wbase << 5) + bp] = r;
@@ -226,40 +223,54 @@ __global__ void __launch_bounds__(256) ms_kernel(MsParams p) {
             // ---- contraction phase: contract_left to the largest target that changes the interval ----
             if (failed) {
                 failed = false;
-                const uint32_t bl4 = l & ~3u, br4 = r & ~3u;
-                const uint32_t Wl = *reinterpret_cast<const uint32_t*>(p.ix.lcs + bl4);
-                const uint32_t Wr = (br4 == bl4) ? Wl : *reinterpret_cast<const uint32_t*>(p.ix.lcs + br4);
+                // 16 LCS cells on each side are requested at once (two aligned 8-byte words per side), so the
+                // scans below almost never need a further, dependent load
+                const uint64_t* __restrict__ L8 = reinterpret_cast<const uint64_t*>(p.ix.lcs);
+                const uint32_t wl_i = l >> 3, wr_i = r >> 3;
+                const uint64_t Wl1 = L8[wl_i];
+                const uint64_t Wl0 = L8[wl_i ? wl_i - 1 : 0];
+                const uint64_t Wr0 = (wr_i == wl_i) ? Wl1 : L8[wr_i];
+                const uint64_t Wr1 = L8[wr_i + 1];  // the zero padding past n makes this readable
                 if (COUNT) {
-                    ++cnt_con; cnt_extra += (br4 != bl4);
-                    if (bp >= bp_emit) { ++cnt_con_e; cnt_extra_e += (br4 != bl4); }
+                    ++cnt_con; cnt_extra += (wr_i != wl_i);
+                    if (bp >= bp_emit) { ++cnt_con_e; cnt_extra_e += (wr_i != wl_i); }
                 }
-                const uint32_t vl = (Wl >> (8 * (l & 3))) & 0xffu;
-                const uint32_t vr = (Wr >> (8 * (r & 3))) & 0xffu;  // LCS[n] reads the zero padding
+                const uint32_t vl = (uint32_t)(Wl1 >> (8 * (l & 7))) & 0xffu;
+                const uint32_t vr = (uint32_t)(Wr0 >> (8 * (r & 7))) & 0xffu;  // LCS[n] reads the zero padding
                 uint32_t t = vl > vr ? vl : vr;
                 if (t > d - 1) t = d - 1;  // cannot happen for a maximal interval; keeps the literal bound
                 if (t == 0) {
                     l = 0; r = n; d = 0;
                 } else {
                     d = t;
-                    const uint32_t T = t * 0x01010101u;
+                    const uint64_t T = (uint64_t)t * 0x0101010101010101ull;
                     // left: largest q <= l with LCS[q] < t (LCS[0] = 0 stops the scan)
-                    uint32_t m = lcs_lt_mask32(Wl, T) & ((2u << (8 * (l & 3) + 7)) - 1u);
-                    uint32_t b = bl4;
-                    while (m == 0) {
-                        b -= 4;
-                        m = lcs_lt_mask32(*reinterpret_cast<const uint32_t*>(p.ix.lcs + b), T);
-                        if (COUNT) { ++cnt_extra; cnt_extra_e += (bp >= bp_emit); }
+                    uint64_t m = lcs_lt_mask64(Wl1, T);
+                    if ((l & 7) != 7) m &= (1ull << (8 * ((l & 7) + 1))) - 1ull;
+                    uint32_t b = wl_i;
+                    if (m == 0) {
+                        m = lcs_lt_mask64(Wl0, T);
+                        --b;
+                        while (m == 0) {
+                            --b;
+                            m = lcs_lt_mask64(L8[b], T);
+                            if (COUNT) { ++cnt_extra; cnt_extra_e += (bp >= bp_emit); }
+                        }
                     }
-                    l = b + ((31 - __clz((int)m)) >> 3);
+                    l = (b << 3) + ((63 - __clzll((long long)m)) >> 3);
                     // right: smallest q >= r with LCS[q] < t (the zero padding at n stops the scan)
-                    m = lcs_lt_mask32(Wr, T) & (0xffffffffu << (8 * (r & 3)));
-                    b = br4;
-                    while (m == 0) {
-                        b += 4;
-                        m = lcs_lt_mask32(*reinterpret_cast<const uint32_t*>(p.ix.lcs + b), T);
-                        if (COUNT) { ++cnt_extra; cnt_extra_e += (bp >= bp_emit); }
+                    m = lcs_lt_mask64(Wr0, T) & (~0ull << (8 * (r & 7)));
+                    b = wr_i;
+                    if (m == 0) {
+                        m = lcs_lt_mask64(Wr1, T);
+                        ++b;
+                        while (m == 0) {
+                            ++b;
+                            m = lcs_lt_mask64(L8[b], T);
+                            if (COUNT) { ++cnt_extra; cnt_extra_e += (bp >= bp_emit); }
+                        }
                     }
-                    r = b + ((__ffs((int)m) - 1) >> 3);
+                    r = (b << 3) + ((__ffsll((long long)m) - 1) >> 3);
                 }
             }
         }

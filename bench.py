@@ -52,6 +52,7 @@ def parse_args():
     ap.add_argument("--batches", type=int, default=16, help="distinct batches rotated through (16 x 10 MB > L2)")
     ap.add_argument("--chunk-len", type=int, default=0, help="MS chunk length (0 = automatic)")
     ap.add_argument("--probe-iters", type=int, default=0, help="K1 probe iterations per contraction phase (0 = default)")
+    ap.add_argument("--ms-flags", type=int, default=0, help="K1 experiment switches")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--cpu-seconds", type=float, default=20.0, help="target CPU work (core-seconds) of the cpu_baseline sample")
     return ap.parse_args()
@@ -228,6 +229,8 @@ def run_ours(args, rank, local_rank, world):
     api.set_chunk_len(args.chunk_len)
     if args.probe_iters:
         api.set_probe_iters(args.probe_iters)
+    if args.ms_flags:
+        api.set_ms_flags(args.ms_flags)
 
     ref, batches, offsets = workload(args, rank)
     hw = os.cpu_count() or 1

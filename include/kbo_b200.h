@@ -185,6 +185,8 @@ int kbo_get_ms_counters(const kbo_index* ix, kbo_ms_counters* out);
 int kbo_set_chunk_len(uint32_t chunk_len);
 /* Tuning knob: probe iterations of K1 between two contraction phases (>= 1).  Results never depend on it. */
 int kbo_set_probe_iters(uint32_t iters);
+/* Experiment switches of K1 (bit 0: population count on the ALU pipe).  Results never depend on them. */
+int kbo_set_ms_flags(uint32_t flags);
 /* Number of kernel launches issued by this library since load (for bench.py's gpu_launches). */
 uint64_t kbo_kernel_launch_count(void);
 /* Elapsed device time of the last host-pointer call's kernel section in ms (CUDA events). */

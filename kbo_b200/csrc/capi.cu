@@ -29,7 +29,9 @@ static std::atomic<uint64_t> g_launches(0);
 static std::atomic<int> g_profile_counters(0);
 static std::atomic<uint32_t> g_chunk_len(0);
 static std::atomic<int> g_kernel_timing(0);
-static std::atomic<uint32_t> g_probe_iters(3);
+static std::atomic<uint32_t> g_probe_iters(2);
+static std::atomic<uint32_t> g_ms_flags(0);
+static std::atomic<uint32_t> g_ms_block(128);
 
 static int fail(int code, const std::string& msg) {
     g_err = msg;
@@ -261,12 +263,13 @@ static int run_ms(kbo_index* ix, Workspace* ws, const QueryView& qv, const Geome
     mp.q = qv;
     mp.chunk_len = g.chunk_len;
     mp.probe_iters = g_probe_iters.load();
+    mp.flags = g_ms_flags.load();
     mp.n_chunks = g.n_chunks;
     mp.ms = ws->ms.as<uint8_t>();
     mp.l_out = intervals ? ws->l.as<uint32_t>() : nullptr;
     mp.r_out = intervals ? ws->r.as<uint32_t>() : nullptr;
     mp.counters = count ? ws->counters.as<unsigned long long>() : nullptr;
-    const unsigned threads = 256;
+    const unsigned threads = g_ms_block.load();
     const unsigned blocks = (unsigned)((g.n_chunks + threads - 1) / threads);
     if (intervals) {
         if (count) ms_kernel<true, true><<<blocks, threads, 0, st>>>(mp);
@@ -985,6 +988,12 @@ int kbo_get_ms_counters(const kbo_index* cix, kbo_ms_counters* out) {
 }
 int kbo_set_chunk_len(uint32_t chunk_len) { g_chunk_len = chunk_len; return KBO_OK; }
 int kbo_set_probe_iters(uint32_t iters) { g_probe_iters = iters ? iters : 1; return KBO_OK; }
+int kbo_set_ms_flags(uint32_t flags) {
+    g_ms_flags = flags & 0xffu;
+    const uint32_t blk = (flags >> 8) & 0x3ffu;  // bits 8..17: K1 block size (experiment)
+    if (blk == 64 || blk == 128 || blk == 256) g_ms_block = blk;
+    return KBO_OK;
+}
 uint64_t kbo_kernel_launch_count(void) { return g_launches.load(); }
 float kbo_last_kernel_ms(const kbo_index* ix) { return ix ? ix->last_kernel_ms : 0.f; }
 

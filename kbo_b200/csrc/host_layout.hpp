@@ -53,11 +53,12 @@ struct Geometry {
 };
 
 inline uint32_t auto_chunk_len(uint64_t Lp) {
-    // enough chunks to fill 148 SMs x 2048 resident lanes; warm-up costs (k-1)/chunk_len extra work
-    uint64_t c = Lp / (148ull * 2048ull);
-    c = (c + 31) & ~31ull;
-    if (c < 128) c = 128;
-    if (c > 1024) c = 1024;
+    // Measured on B200 (profiles/README.md): for a 10^7-base batch 64 beats 32/96/128; K1 is bound by
+    // instruction issue, so the warm-up overhead (k-1)/chunk_len and the number of chunks in flight
+    // (one per lane, 148 SMs x 1024 lanes wanted) are traded here.
+    uint64_t c = (Lp / (148ull * 1024ull)) & ~31ull;
+    if (c < 64) c = 64;
+    if (c > 512) c = 512;
     return (uint32_t)c;
 }
 

@@ -129,12 +129,20 @@ struct MsParams {
     QueryView q;
     uint32_t chunk_len;    // multiple of 32
     uint32_t probe_iters;  // probe iterations per contraction phase (>= 1)
+    uint32_t flags;        // experiment switches: bit0 = population count on the ALU pipe instead of POPC (XU pipe)
     uint64_t n_chunks;
     uint8_t* ms;         // padded space, 1 byte per position
     uint32_t* l_out;     // optional (INTERVALS)
     uint32_t* r_out;
     unsigned long long* counters;  // optional (COUNT)
 };
+
+__device__ __forceinline__ uint32_t popc_alu(uint32_t x) {
+    x = x - ((x >> 1) & 0x55555555u);
+    x = (x & 0x33333333u) + ((x >> 2) & 0x33333333u);
+    x = (x + (x >> 4)) & 0x0f0f0f0fu;
+    return (x * 0x01010101u) >> 24;
+}
 
 __device__ __forceinline__ uint64_t lcs_lt_mask64(uint64_t w, uint64_t t_rep) {
     // 0x80 in every byte of w that is < t (bytes and t are < 128)
@@ -147,7 +155,7 @@ __device__ __forceinline__ uint64_t lcs_lt_mask64(uint64_t w, uint64_t t_rep) {
 // contraction code (~40 % of the static loop body, used by ~10 % of the lanes per iteration) is thus
 // issued once per group instead of once per iteration.  All position arithmetic is 32-bit.
 template <bool INTERVALS, bool COUNT>
-__global__ void __launch_bounds__(256, 4) ms_kernel(MsParams p) {
+__global__ void __launch_bounds__(256, 8) ms_kernel(MsParams p) {
     const uint64_t g = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
     unsigned long long cnt_att = 0, cnt_split = 0, cnt_con = 0, cnt_extra = 0, cnt_proc = 0, cnt_emit = 0;
     unsigned long long cnt_att_e = 0, cnt_split_e = 0, cnt_con_e = 0, cnt_extra_e = 0;
@@ -167,7 +175,7 @@ __global__ void __launch_bounds__(256, 4) ms_kernel(MsParams p) {
         const uint32_t bp_end = bp_emit + len;
         uint64_t qw = __ldg(qptr) >> (2 * bp);
         uint32_t iw = __ldg(iptr) >> bp;
-        uint32_t l = 0, r = n, d = 0;
+        uint32_t l = 0, r = n, d = 0, acc = 0;
         bool failed = false;
         while (bp < bp_end) {
             // ---- probe phase ------------------------------------------------------------------
@@ -183,8 +191,15 @@ __global__ void __launch_bounds__(256, 4) ms_kernel(MsParams p) {
                     const uint32_t bl = l >> 5, br = r >> 5;
                     const uint64_t wl = __ldg(p.ix.rank + (rowoff + bl));
                     const uint64_t wr = (br == bl) ? wl : __ldg(p.ix.rank + (rowoff + br));
-                    const uint32_t nl = (uint32_t)(wl >> 32) + __popc((uint32_t)wl & ((1u << (l & 31)) - 1u));
-                    const uint32_t nr = (uint32_t)(wr >> 32) + __popc((uint32_t)wr & ((1u << (r & 31)) - 1u));
+                    const uint32_t ml = (uint32_t)wl & ((1u << (l & 31)) - 1u), mr = (uint32_t)wr & ((1u << (r & 31)) - 1u);
+                    uint32_t nl, nr;
+                    if (p.flags & 1u) {
+                        nl = (uint32_t)(wl >> 32) + popc_alu(ml);
+                        nr = (uint32_t)(wr >> 32) + popc_alu(mr);
+                    } else {
+                        nl = (uint32_t)(wl >> 32) + __popc(ml);
+                        nr = (uint32_t)(wr >> 32) + __popc(mr);
+                    }
                     if (COUNT) {
                         const bool sp = (bl >> 2) != (br >> 2);
                         ++cnt_att; cnt_split += sp;
@@ -205,7 +220,11 @@ __global__ void __launch_bounds__(256, 4) ms_kernel(MsParams p) {
                     if (COUNT) ++cnt_proc;
                     if (bp >= bp_emit) {
                         if (COUNT) ++cnt_emit;
-                        msw[bp] = (uint8_t)d;
+                        acc |= d << (8 * (bp & 3));
+                        if ((bp & 3) == 3 || bp + 1 == bp_end) {
+                            *reinterpret_cast<uint32_t*>(msw + (bp & ~3u)) = acc;
+                            acc = 0;
+                        }
                         if (INTERVALS) {
                             p.l_out[(wbase << 5) + bp] = l;
                             p.r_out[(wbase << 5) + bp] = r;

@@ -20,6 +20,8 @@
 using namespace kbo_b200;
 
 static uint32_t g_emu_probe_iters = 3;
+static uint32_t g_emu_flags = 0;
+extern "C" void emu_set_ms_flags(uint32_t v) { g_emu_flags = v; }
 extern "C" void emu_set_probe_iters(uint32_t v) { g_emu_probe_iters = v ? v : 1; }
 
 struct EmuIndex {
@@ -78,6 +80,7 @@ static void stage_and_ms(EmuIndex* e, const uint8_t* concat, const uint64_t* off
     mp.q = qv;
     mp.chunk_len = g.chunk_len;
     mp.probe_iters = g_emu_probe_iters;
+    mp.flags = g_emu_flags;
     mp.n_chunks = g.n_chunks;
     mp.ms = s->ms.data();
     mp.l_out = intervals ? s->l.data() : nullptr;

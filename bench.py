@@ -224,6 +224,8 @@ def run_ours(args, rank, local_rank, world):
     torch.cuda.set_device(dev)
     dist = None
     if world > 1:
+        if os.environ.get("NCCL_DEBUG", "").upper() == "VERSION":
+            os.environ["NCCL_DEBUG"] = "WARN"  # the version banner goes to stdout, ahead of the JSON line
         import torch.distributed as dist
         dist.init_process_group("nccl", device_id=torch.device("cuda", dev))
     api.set_chunk_len(args.chunk_len)

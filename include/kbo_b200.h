@@ -167,6 +167,17 @@ int kbo_find_batch_device(const kbo_index* ix, const uint8_t* d_concat, const ui
 int kbo_map_unrefined(const kbo_index* query_index, const uint8_t* ref_seq, uint64_t len, double max_error_prob,
                       int format, uint8_t* out);
 
+/* kbo::call (lib.rs:547-573): builds the SBWT of ref_seq with `sbwt_build_opts` (NULL = CallOpts default:
+ * BuildOpts::default() with build_select), then variant_calling::call_variants (variant_calling.rs:249-294)
+ * on GPU matching statistics.  Variant i = (pos[i], query_chars, ref_chars); the characters of all variants
+ * are concatenated in qchars / rchars with lengths qlen[i] / rlen[i]. */
+int kbo_call(const kbo_index* query_index, const uint8_t* ref_seq, uint64_t len, double max_error_prob,
+             const kbo_build_opts* sbwt_build_opts, uint64_t* pos, uint32_t* qlen, uint32_t* rlen, uint8_t* qchars,
+             uint8_t* rchars, uint64_t cap_variants, uint64_t cap_chars, uint64_t* n_variants);
+/* kbo::map (lib.rs:720-761) with MapOpts {max_error_prob, fill_gaps, call_variants, format, sbwt_build_opts}. */
+int kbo_map(const kbo_index* query_index, const uint8_t* ref_seq, uint64_t len, double max_error_prob,
+            int fill_gaps, int call_variants, int format, const kbo_build_opts* sbwt_build_opts, uint8_t* out);
+
 /* ---- instrumentation ------------------------------------------------------ */
 /* Event counters of the last MS launch sequence on this index when profiling counters are enabled
  * (kbo_set_profile_counters(1)): extend attempts, attempts whose two rank probes fell in different

@@ -38,7 +38,7 @@ EXPORTED_SYMBOLS = [
     "kbo_index_access_kmer", "kbo_index_search", "kbo_query_sbwt", "kbo_query_sbwt_batch_compact",
     "kbo_log_rm_max_cdf", "kbo_random_match_threshold", "kbo_derandomize_ms_vec", "kbo_translate_ms_vec",
     "kbo_run_lengths_gapped", "kbo_relative_to_ref", "kbo_matches", "kbo_matches_batch", "kbo_matches_batch_device",
-    "kbo_find_batch", "kbo_find_batch_device", "kbo_map_unrefined", "kbo_set_profile_counters", "kbo_get_ms_counters", "kbo_set_chunk_len", "kbo_set_probe_iters", "kbo_set_ms_flags",
+    "kbo_find_batch", "kbo_find_batch_device", "kbo_map_unrefined", "kbo_call", "kbo_map", "kbo_set_profile_counters", "kbo_get_ms_counters", "kbo_set_chunk_len", "kbo_set_probe_iters", "kbo_set_ms_flags",
     "kbo_kernel_launch_count", "kbo_last_kernel_ms", "kbo_set_kernel_timing", "kbo_collect_kernel_times",
     "kbo_measure_random_sector_rate",
 ]
@@ -114,6 +114,10 @@ def load_library():
                                  C.c_uint64, u64p]
     L.kbo_find_batch_device.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, u64p, C.c_uint64, C.c_double, C.c_uint64,
                                         C.c_void_p, C.c_uint64, C.c_void_p, C.c_void_p]
+    L.kbo_call.argtypes = [C.c_void_p, u8p, C.c_uint64, C.c_double, C.POINTER(BuildOptsC), u64p, u32p, u32p, u8p, u8p,
+                           C.c_uint64, C.c_uint64, u64p]
+    L.kbo_map.argtypes = [C.c_void_p, u8p, C.c_uint64, C.c_double, C.c_int, C.c_int, C.c_int, C.POINTER(BuildOptsC),
+                          u8p]
     L.kbo_map_unrefined.argtypes = [C.c_void_p, u8p, C.c_uint64, C.c_double, C.c_int, u8p]
     L.kbo_set_profile_counters.argtypes = [C.c_int]
     L.kbo_get_ms_counters.argtypes = [C.c_void_p, C.POINTER(MsCountersC)]
@@ -179,6 +183,19 @@ class MatchOpts:
 class FindOpts:
     max_error_prob: float = 0.0000001
     max_gap_len: int = 0
+
+
+@dataclass
+class CallOpts:
+    max_error_prob: float = 0.0000001
+    sbwt_build_opts: BuildOpts = field(default_factory=lambda: BuildOpts(build_select=True))
+
+
+@dataclass(frozen=True)
+class Variant:
+    query_pos: int
+    query_chars: bytes
+    ref_chars: bytes
 
 
 @dataclass
@@ -431,17 +448,41 @@ def find_csr(concat, offsets, index, find_opts=None, buffers=None):
     return buf, int(buf.rle_offsets[nq])
 
 
+def _build_opts_c(o):
+    return BuildOptsC(o.k, int(o.add_revcomp), o.num_threads, o.prefix_precalc, int(o.build_select), o.mem_gb,
+                      int(o.dedup_batches), o.temp_dir.encode() if o.temp_dir else None)
+
+
+def call(query_index, ref_seq, call_opts=None):
+    """kbo::call (lib.rs:547-573) -> list of Variant."""
+    o = call_opts or CallOpts()
+    r = _u8(ref_seq)
+    cap = len(r) + 1
+    capc = 4 * len(r) + 64
+    pos = np.zeros(cap, dtype=np.uint64)
+    ql, rl = np.zeros(cap, dtype=np.uint32), np.zeros(cap, dtype=np.uint32)
+    qc, rc = np.zeros(capc, dtype=np.uint8), np.zeros(capc, dtype=np.uint8)
+    n = C.c_uint64(0)
+    co = _build_opts_c(o.sbwt_build_opts)
+    _check(load_library().kbo_call(query_index._h, _p(r, C.c_uint8), len(r), o.max_error_prob, C.byref(co),
+                                   _p(pos, C.c_uint64), _p(ql, C.c_uint32), _p(rl, C.c_uint32), _p(qc, C.c_uint8),
+                                   _p(rc, C.c_uint8), cap, capc, C.byref(n)))
+    out, qo, ro = [], 0, 0
+    for i in range(n.value):
+        out.append(Variant(int(pos[i]), bytes(qc[qo:qo + ql[i]]), bytes(rc[ro:ro + rl[i]])))
+        qo += int(ql[i])
+        ro += int(rl[i])
+    return out
+
+
 def map(ref_seq, query_index, map_opts=None):
-    """kbo::map (lib.rs:720-761).  Refinement (fill_gaps / call_variants) is not on the device path yet:
-    requesting it raises NotImplementedError instead of silently returning an unrefined alignment."""
+    """kbo::map (lib.rs:720-761)."""
     o = map_opts or MapOpts()
-    if o.fill_gaps or o.call_variants:
-        raise NotImplementedError("map(): fill_gaps / call_variants are 'next' rows (SURVEY 8f); "
-                                  "use MapOpts(fill_gaps=False, call_variants=False)")
     r = _u8(ref_seq)
     out = np.zeros(max(len(r), 1), dtype=np.uint8)
-    _check(load_library().kbo_map_unrefined(query_index._h, _p(r, C.c_uint8), len(r), o.max_error_prob,
-                                            int(o.format), _p(out, C.c_uint8)))
+    co = _build_opts_c(o.sbwt_build_opts)
+    _check(load_library().kbo_map(query_index._h, _p(r, C.c_uint8), len(r), o.max_error_prob, int(o.fill_gaps),
+                                  int(o.call_variants), int(o.format), C.byref(co), _p(out, C.c_uint8)))
     return out[:len(r)].tobytes()
 
 

@@ -17,6 +17,7 @@
 #include "../../include/kbo_b200.h"
 #include "kernels.cuh"
 #include "host_layout.hpp"
+#include "refine_host.hpp"
 #include "sbwt_host.hpp"
 
 using namespace kbo_b200;
@@ -887,6 +888,163 @@ int kbo_map_unrefined(const kbo_index* query_index, const uint8_t* ref_seq, uint
     int rc = kbo_matches(query_index, ref_seq, len, max_error_prob, out);
     if (rc) return rc;
     if (format) return kbo_relative_to_ref(ref_seq, out, len, out);
+    return KBO_OK;
+}
+
+// ---- call / map with refinement (lib.rs:547-573, 720-761) ---------------------------------------
+struct HostMs {
+    std::vector<uint8_t> d, chars;
+    std::vector<uint32_t> l, r;
+};
+
+// One query through K0 -> K1 (with intervals) [-> K2 when thr != 0]; results copied to the host.
+static int run_single_full(kbo_index* ix, const uint8_t* seq, uint64_t len, uint32_t thr, HostMs* out) {
+    DeviceGuard dg(ix->device);
+    if (!dg.ok) return fail(KBO_ERR_CUDA, "cudaSetDevice failed");
+    Workspace* ws = nullptr;
+    int rc = acquire_ws(ix, &ws);
+    if (rc) return rc;
+    const Geometry g = make_geometry(len, 1);
+    cudaStream_t st = ws->stream;
+    const uint64_t offsets[2] = {0, len};
+    out->d.resize(len);
+    out->l.resize(len);
+    out->r.resize(len);
+    if (thr) out->chars.resize(len);
+    auto body = [&]() -> int {
+        CUDA_TRY(ws->ascii.ensure(len, st));
+        CUDA_TRY(ws->offsets.ensure(16, st));
+        CUDA_TRY(ws->out.ensure(len + 16, st));
+        CUDA_TRY(cudaMemcpyAsync(ws->ascii.p, seq, len, cudaMemcpyHostToDevice, st));
+        CUDA_TRY(cudaMemcpyAsync(ws->offsets.p, offsets, 16, cudaMemcpyHostToDevice, st));
+        QueryView qv;
+        int rc2 = run_pack(ws, ws->ascii.as<uint8_t>(), ws->offsets.as<uint64_t>(), 1, g, &qv);
+        if (rc2) return rc2;
+        rc2 = run_ms(ix, ws, qv, g, true);
+        if (rc2) return rc2;
+        if (thr) {
+            rc2 = run_derand_translate(ix, ws, qv, g, thr, ws->out.as<uint8_t>(), 0);
+            if (rc2) return rc2;
+            CUDA_TRY(cudaMemcpyAsync(out->chars.data(), ws->out.p, len, cudaMemcpyDeviceToHost, st));
+        }
+        // a single query has its only separator at position len: padded == unpadded below len
+        CUDA_TRY(cudaMemcpyAsync(out->d.data(), ws->ms.p, len, cudaMemcpyDeviceToHost, st));
+        CUDA_TRY(cudaMemcpyAsync(out->l.data(), ws->l.p, len * 4, cudaMemcpyDeviceToHost, st));
+        CUDA_TRY(cudaMemcpyAsync(out->r.data(), ws->r.p, len * 4, cudaMemcpyDeviceToHost, st));
+        CUDA_TRY(cudaStreamSynchronize(st));
+        return KBO_OK;
+    };
+    rc = body();
+    release_ws(ix, ws);
+    return rc;
+}
+
+// lib.rs:547-573 given the full-length MS of ref_seq against the assembly index (computed by the caller)
+static int call_impl(kbo_index* query_index, const uint8_t* ref_seq, uint64_t len, double max_error_prob,
+                     const kbo_build_opts* opts, const HostMs& ms, std::vector<VariantRec>* variants) {
+    kbo_build_opts o;
+    if (opts) o = *opts; else { kbo_default_build_opts(&o); o.build_select = 1; }
+    uint64_t thr = 0;
+    int rc = host_threshold(query_index->host.k, query_index->host.n_kmers, 4, max_error_prob, &thr);  // variant_calling.rs:260
+    if (rc) return rc;
+    kbo_index* ref_index = nullptr;
+    const uint8_t* seqs[1] = {ref_seq};
+    const uint64_t lens[1] = {len};
+    rc = kbo_index_build(seqs, lens, 1, &o, query_index->device, &ref_index);  // lib.rs:553
+    if (rc) return rc;
+    if (ref_index->host.k != query_index->host.k) {  // lib.rs:559
+        kbo_index_free(ref_index);
+        return fail(KBO_ERR_K_MISMATCH, "k of the reference index differs from k of the query index (lib.rs:559)");
+    }
+    int inner_rc = KBO_OK;
+    KmerMsFn kmer_ms = [&](int which, const uint8_t* kmers, uint64_t n_kmers, uint32_t k, uint8_t* d_out) {
+        std::vector<uint64_t> off(n_kmers + 1);
+        for (uint64_t i = 0; i <= n_kmers; ++i) off[i] = i * k;
+        int r2 = kbo_query_sbwt_batch_compact(which == 0 ? query_index : ref_index, kmers, off.data(), n_kmers, d_out,
+                                              nullptr, nullptr);
+        if (r2 && !inner_rc) inner_rc = r2;
+    };
+    MsArrays view;
+    view.d = ms.d.data();
+    view.l = ms.l.data();
+    view.r = ms.r.data();
+    view.n = len;
+    try {
+        *variants = call_variants(query_index->host, view, ref_seq, len, thr, kmer_ms);
+    } catch (const RefinePanic& p) {
+        kbo_index_free(ref_index);
+        return fail(KBO_ERR_PANIC, p.what);
+    }
+    kbo_index_free(ref_index);
+    return inner_rc;
+}
+
+int kbo_call(const kbo_index* cix, const uint8_t* ref_seq, uint64_t len, double max_error_prob,
+             const kbo_build_opts* sbwt_build_opts, uint64_t* pos, uint32_t* qlen, uint32_t* rlen, uint8_t* qchars,
+             uint8_t* rchars, uint64_t cap_variants, uint64_t cap_chars, uint64_t* n_variants) {
+    kbo_index* ix = const_cast<kbo_index*>(cix);
+    if (!ix || !n_variants) return fail(KBO_ERR_BAD_ARGUMENT, "null argument");
+    if (!ref_seq || len == 0) return fail(KBO_ERR_EMPTY_INPUT, "empty reference sequence");
+    HostMs ms;
+    int rc = run_single_full(ix, ref_seq, len, 0, &ms);  // variant_calling.rs:266
+    if (rc) return rc;
+    std::vector<VariantRec> vars;
+    rc = call_impl(ix, ref_seq, len, max_error_prob, sbwt_build_opts, ms, &vars);
+    if (rc) return rc;
+    *n_variants = vars.size();
+    if (vars.size() > cap_variants) return fail(KBO_ERR_BUFFER_TOO_SMALL, "variant capacity too small");
+    uint64_t qo = 0, ro = 0;
+    for (size_t i = 0; i < vars.size(); ++i) {
+        const VariantRec& v = vars[i];
+        if (qo + v.query_chars.size() > cap_chars || ro + v.ref_chars.size() > cap_chars)
+            return fail(KBO_ERR_BUFFER_TOO_SMALL, "variant character capacity too small");
+        pos[i] = v.query_pos;
+        qlen[i] = (uint32_t)v.query_chars.size();
+        rlen[i] = (uint32_t)v.ref_chars.size();
+        if (!v.query_chars.empty()) std::memcpy(qchars + qo, v.query_chars.data(), v.query_chars.size());
+        if (!v.ref_chars.empty()) std::memcpy(rchars + ro, v.ref_chars.data(), v.ref_chars.size());
+        qo += v.query_chars.size();
+        ro += v.ref_chars.size();
+    }
+    return KBO_OK;
+}
+
+int kbo_map(const kbo_index* cix, const uint8_t* ref_seq, uint64_t len, double max_error_prob, int do_fill_gaps,
+            int do_call_variants, int format, const kbo_build_opts* sbwt_build_opts, uint8_t* out) {
+    kbo_index* ix = const_cast<kbo_index*>(cix);
+    if (!ix || !out) return fail(KBO_ERR_BAD_ARGUMENT, "null argument");
+    kbo_build_opts o;
+    if (sbwt_build_opts) o = *sbwt_build_opts; else { kbo_default_build_opts(&o); o.build_select = 1; }
+    if (do_call_variants && ix->host.k != o.k)  // lib.rs:729
+        return fail(KBO_ERR_K_MISMATCH, "index k differs from sbwt_build_opts.k (lib.rs:729)");
+    const uint64_t offsets[2] = {0, len};
+    uint64_t total = 0;
+    uint32_t thr = 0;
+    if (!ref_seq && len) return fail(KBO_ERR_BAD_ARGUMENT, "ref_seq is null");
+    int rc = matches_prologue(ix, offsets, 1, max_error_prob, &total, &thr);  // lib.rs:731-738 preconditions
+    if (rc) return rc;
+    HostMs ms;
+    rc = run_single_full(ix, ref_seq, len, thr, &ms);
+    if (rc) return rc;
+    std::vector<uint8_t> aln = ms.chars;
+    MsArrays view;
+    view.d = ms.d.data();
+    view.l = ms.l.data();
+    view.r = ms.r.data();
+    view.n = len;
+    try {
+        if (do_fill_gaps) fill_gaps(&aln, view, ref_seq, len, ix->host, thr, max_error_prob);  // lib.rs:743-744
+        if (do_call_variants) {                                                             // lib.rs:749-751
+            std::vector<VariantRec> vars;
+            rc = call_impl(ix, ref_seq, len, max_error_prob, &o, ms, &vars);
+            if (rc) return rc;
+            add_variants(&aln, vars);
+        }
+    } catch (const RefinePanic& p) {
+        return fail(KBO_ERR_PANIC, p.what);
+    }
+    if (format) return kbo_relative_to_ref(ref_seq, aln.data(), len, out);  // lib.rs:756-760
+    std::memcpy(out, aln.data(), len);
     return KBO_OK;
 }
 

@@ -15,6 +15,7 @@
 
 #include "../../kbo_b200/csrc/host_layout.hpp"
 #include "../../kbo_b200/csrc/kernels.cuh"
+#include "../../kbo_b200/csrc/refine_host.hpp"
 #include "../../kbo_b200/csrc/sbwt_host.hpp"
 
 using namespace kbo_b200;
@@ -231,6 +232,102 @@ uint64_t emu_rle_batch(const uint8_t* aln, const uint64_t* offsets, uint64_t nq,
         rle_kernel<true>(aln, offsets, nq, max_gap_len, counts.data(), stage.data(), rle_offsets, (RleRecord*)out7, cap);
     });
     return rle_offsets[nq];
+}
+
+// ---- host refinement logic (refine_host.cpp) driven by emulated-kernel MS -------------------------
+static void emu_single_ms(EmuIndex* e, const uint8_t* seq, uint64_t len, uint32_t thr, std::vector<uint8_t>* d,
+                          std::vector<uint32_t>* l, std::vector<uint32_t>* r, std::vector<uint8_t>* chars) {
+    const uint64_t offsets[2] = {0, len};
+    Staged s;
+    stage_and_ms(e, seq, offsets, 1, 0, true, nullptr, &s);
+    d->assign(s.ms.begin(), s.ms.begin() + len);
+    l->assign(s.l.begin(), s.l.begin() + len);
+    r->assign(s.r.begin(), s.r.begin() + len);
+    if (thr) {
+        chars->assign(len + 16, 0);
+        TrParams tp;
+        tp.ms = s.ms.data(); tp.q = s.qv; tp.k = e->host.k; tp.thr = thr; tp.out = chars->data(); tp.off0 = 0;
+        tp.n_tiles = s.g.n_tiles;
+        emu_launch_par((unsigned)((s.g.n_tiles + K2_WARPS - 1) / K2_WARPS), K2_WARPS * 32,
+                       [&]() { derand_translate_kernel(tp); });
+        chars->resize(len);
+    }
+}
+
+static std::vector<VariantRec> emu_call_impl(EmuIndex* q, const uint8_t* ref_seq, uint64_t len, uint64_t thr,
+                                             uint32_t build_k, int revcomp, const MsArrays& ms) {
+    EmuIndex refix;
+    const uint8_t* seqs[1] = {ref_seq};
+    const uint64_t lens[1] = {len};
+    std::string msg = build_host_index(seqs, lens, 1, build_k, revcomp != 0, 1, &refix.host);
+    if (!msg.empty()) throw RefinePanic{msg};
+    finish(&refix);
+    if (refix.host.k != q->host.k) throw RefinePanic{"lib.rs:559 k mismatch"};
+    KmerMsFn fn = [&](int which, const uint8_t* kmers, uint64_t n_kmers, uint32_t k, uint8_t* d_out) {
+        std::vector<uint64_t> off(n_kmers + 1);
+        for (uint64_t i = 0; i <= n_kmers; ++i) off[i] = i * k;
+        Staged s;
+        stage_and_ms(which == 0 ? q : &refix, kmers, off.data(), n_kmers, 0, false, nullptr, &s);
+        unpad<uint8_t>(s.ms.data(), s.qv, d_out);
+    };
+    return call_variants(q->host, ms, ref_seq, len, thr, fn);
+}
+
+static int64_t emu_pack_variants(const std::vector<VariantRec>& vs, uint64_t* pos, uint32_t* qlen, uint32_t* rlen,
+                                 uint8_t* qchars, uint8_t* rchars) {
+    size_t qo = 0, ro = 0;
+    for (size_t i = 0; i < vs.size(); ++i) {
+        pos[i] = vs[i].query_pos;
+        qlen[i] = (uint32_t)vs[i].query_chars.size();
+        rlen[i] = (uint32_t)vs[i].ref_chars.size();
+        std::memcpy(qchars + qo, vs[i].query_chars.data(), qlen[i]);
+        std::memcpy(rchars + ro, vs[i].ref_chars.data(), rlen[i]);
+        qo += qlen[i];
+        ro += rlen[i];
+    }
+    return (int64_t)vs.size();
+}
+
+// kbo::call with the product's host logic; returns the number of variants or -1 (panic)
+int64_t emu_call(void* h_query, const uint8_t* ref_seq, uint64_t len, uint64_t thr, uint32_t build_k, int revcomp,
+                 uint64_t* pos, uint32_t* qlen, uint32_t* rlen, uint8_t* qchars, uint8_t* rchars) {
+    EmuIndex* q = (EmuIndex*)h_query;
+    try {
+        std::vector<uint8_t> d, chars;
+        std::vector<uint32_t> l, r;
+        emu_single_ms(q, ref_seq, len, 0, &d, &l, &r, &chars);
+        MsArrays ms;
+        ms.d = d.data(); ms.l = l.data(); ms.r = r.data(); ms.n = len;
+        return emu_pack_variants(emu_call_impl(q, ref_seq, len, thr, build_k, revcomp, ms), pos, qlen, rlen, qchars,
+                                 rchars);
+    } catch (const RefinePanic&) {
+        return -1;
+    }
+}
+
+// kbo::map with the product's host logic; returns 0 or -1 (panic)
+int emu_map(void* h_query, const uint8_t* ref_seq, uint64_t len, uint32_t thr, uint32_t call_thr, double p, int do_fill,
+            int do_call, int format, uint32_t build_k, int revcomp, uint8_t* out) {
+    EmuIndex* q = (EmuIndex*)h_query;
+    try {
+        std::vector<uint8_t> d, chars;
+        std::vector<uint32_t> l, r;
+        emu_single_ms(q, ref_seq, len, thr, &d, &l, &r, &chars);
+        MsArrays ms;
+        ms.d = d.data(); ms.l = l.data(); ms.r = r.data(); ms.n = len;
+        if (do_fill) fill_gaps(&chars, ms, ref_seq, len, q->host, thr, p);
+        if (do_call) add_variants(&chars, emu_call_impl(q, ref_seq, len, call_thr ? call_thr : thr, build_k, revcomp, ms));
+        for (uint64_t i = 0; i < len; ++i) {
+            const uint8_t a = chars[i];
+            if (!format) out[i] = a;
+            else if (a == 'M' || a == 'R' || a == 'I') out[i] = ref_seq[i];
+            else if (a == 'X' || a == 'D' || a == '-') out[i] = '-';
+            else out[i] = a;
+        }
+        return 0;
+    } catch (const RefinePanic&) {
+        return -1;
+    }
 }
 
 void emu_translate_i64(const int64_t* d, uint64_t n, uint32_t k, uint32_t thr, uint8_t* out) {

@@ -17,12 +17,13 @@ _CSRC = os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 
 def build_emu():
     srcs = [os.path.join(_DIR, "emu_driver.cpp"), os.path.join(_DIR, "host_emu.hpp")] + [
-        os.path.join(_CSRC, f) for f in ("kernels.cuh", "host_layout.hpp", "sbwt_host.hpp", "sbwt_host.cpp")]
+        os.path.join(_CSRC, f) for f in ("kernels.cuh", "host_layout.hpp", "sbwt_host.hpp", "sbwt_host.cpp", "refine_host.hpp",
+                                        "refine_host.cpp")]
     stale = (not os.path.exists(_SO)) or any(os.path.getmtime(s) > os.path.getmtime(_SO) for s in srcs)
     if stale:
         subprocess.check_call(["g++", "-O2", "-std=c++20", "-march=x86-64-v3", "-fPIC", "-shared", "-pthread",
                                "-I", _DIR, "-o", _SO, os.path.join(_DIR, "emu_driver.cpp"),
-                               os.path.join(_CSRC, "sbwt_host.cpp")])
+                               os.path.join(_CSRC, "sbwt_host.cpp"), os.path.join(_CSRC, "refine_host.cpp")])
     return _SO
 
 
@@ -54,6 +55,10 @@ def lib():
         L.emu_derand_translate_u8.argtypes = [u8p, C.c_uint64, C.c_uint32, C.c_uint32, u8p]
         L.emu_derandomize_general.argtypes = [u64p, C.c_uint64, C.c_uint32, C.c_uint32, i64p]
         L.emu_translate_i64.argtypes = [i64p, C.c_uint64, C.c_uint32, C.c_uint32, u8p]
+        L.emu_call.restype = C.c_int64
+        L.emu_call.argtypes = [C.c_void_p, u8p, C.c_uint64, C.c_uint64, C.c_uint32, C.c_int, u64p, u32p, u32p, u8p, u8p]
+        L.emu_map.argtypes = [C.c_void_p, u8p, C.c_uint64, C.c_uint32, C.c_uint32, C.c_double, C.c_int, C.c_int, C.c_int,
+                              C.c_uint32, C.c_int, u8p]
         L.emu_rle_batch.restype = C.c_uint64
         L.emu_rle_batch.argtypes = [u8p, u64p, C.c_uint64, C.c_uint32, u64p, C.c_uint64, u64p]
         _lib = L
@@ -139,6 +144,33 @@ class EmuIndex:
                                    _p(d, C.c_uint8), _p(l, C.c_uint32) if intervals else None,
                                    _p(r, C.c_uint32) if intervals else None, _p(cnt, C.c_uint64) if counters else None)
         return d, l, r, offsets, cnt
+
+    def call(self, ref_seq, thr, build_k, revcomp=False):
+        r = _u8(ref_seq)
+        cap, capc = len(r) + 1, 4 * len(r) + 64
+        pos = np.zeros(cap, dtype=np.uint64)
+        ql, rl = np.zeros(cap, dtype=np.uint32), np.zeros(cap, dtype=np.uint32)
+        qc, rc = np.zeros(capc, dtype=np.uint8), np.zeros(capc, dtype=np.uint8)
+        n = lib().emu_call(self.h, _p(r, C.c_uint8), len(r), thr, build_k, int(revcomp), _p(pos, C.c_uint64),
+                           _p(ql, C.c_uint32), _p(rl, C.c_uint32), _p(qc, C.c_uint8), _p(rc, C.c_uint8))
+        if n < 0:
+            raise RuntimeError("panic")
+        out, qo, ro = [], 0, 0
+        for i in range(n):
+            out.append((int(pos[i]), bytes(qc[qo:qo + ql[i]]), bytes(rc[ro:ro + rl[i]])))
+            qo += int(ql[i])
+            ro += int(rl[i])
+        return out
+
+    def map(self, ref_seq, thr, p, fill_gaps=True, call_variants=True, format=True, build_k=31, revcomp=False,
+            call_thr=0):
+        r = _u8(ref_seq)
+        out = np.zeros(len(r), dtype=np.uint8)
+        rc = lib().emu_map(self.h, _p(r, C.c_uint8), len(r), thr, call_thr, p, int(fill_gaps), int(call_variants), int(format),
+                           build_k, int(revcomp), _p(out, C.c_uint8))
+        if rc < 0:
+            raise RuntimeError("panic")
+        return out.tobytes()
 
     def matches_batch(self, queries, thr, chunk_len=0):
         concat, offsets = csr(queries)

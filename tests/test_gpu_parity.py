@@ -299,6 +299,42 @@ def test_device_pointer_entry_points_match_host_entry_points():
         assert got == o.find(concat[int(off[q]):int(off[q + 1])].tobytes(), max_gap_len=25)
 
 
+# ------------------------------------------------------ call / map with refinement ---
+def test_golden_call_and_map_full():
+    b = "lib.rs::doc@519"  # lib.rs:526-545
+    ix = api.build([g(b, "query")], api.BuildOpts(k=20, build_select=True))
+    got = api.call(ix, g(b, "reference"), api.CallOpts(0.001, api.BuildOpts(k=20, build_select=True)))
+    assert [(v.query_pos, v.query_chars, v.ref_chars) for v in got] == \
+        [(22, bytes([65, 71, 71]), b""), (42, bytes([84]), bytes([67])), (60, b"", bytes([67]))]
+    ix3 = api.build([REF_K3], api.BuildOpts(k=3, build_select=True))  # lib.rs:647-661
+    o = api.MapOpts(sbwt_build_opts=api.BuildOpts(k=3, build_select=True))
+    assert list(api.map(b"GTGACTATGAGGAT", ix3, o)) == [45, 45, 45, 45, 45, 45, 45, 45, 45, 65, 71, 71, 45, 45]
+    with pytest.raises(api.KboPanic) as e:  # lib.rs:729
+        api.map(b"GTGACTATGAGGAT", ix3, api.MapOpts())
+    assert e.value.status == 5
+    b = "gap_filling.rs::fill_gaps_default_build_opts"  # gap_filling.rs:892-922 (threshold from the index)
+    ixg = api.build([g(b, "query")], api.BuildOpts(build_select=True))
+    got = api.map(g(b, "reference"), ixg, api.MapOpts(fill_gaps=True, call_variants=False, format=False))
+    assert got == g(b, "expected")
+
+
+@pytest.mark.parametrize("k,p,seed", [(31, 1e-7, 1), (51, 1e-7, 3), (63, 1e-8, 4)])
+def test_map_and_call_match_oracle(k, p, seed):
+    ref = synth.random_seq(200_000, 100 + seed)
+    asm = synth.mutate(ref, 200 + seed, snp=0.01, indel=0.001)
+    o = O.OracleIndex([asm.tobytes()], k=k)
+    ix = api.build([asm.tobytes()], api.BuildOpts(k=k, build_select=True, num_threads=4))
+    r = ref.tobytes()
+    bo = api.BuildOpts(k=k, build_select=True)
+    want_vars = o.call(r, max_error_prob=p, build_k=k)
+    assert len(want_vars) > 1000 or k < 51
+    got = api.call(ix, r, api.CallOpts(p, bo))
+    assert [(v.query_pos, v.query_chars, v.ref_chars) for v in got] == want_vars
+    for fill, callv, fmt in ((True, True, True), (True, False, False), (False, True, False)):
+        want = o.map(r, max_error_prob=p, fill_gaps=fill, call_variants=callv, format=fmt, build_k=k)
+        assert api.map(r, ix, api.MapOpts(p, fill, callv, fmt, bo)) == want, (fill, callv, fmt)
+
+
 def test_counters_and_launch_count():
     ref = synth.random_seq(50_000, 51)
     ix = api.build([ref.tobytes()], api.BuildOpts(k=31))

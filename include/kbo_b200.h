@@ -194,6 +194,8 @@ int kbo_set_profile_counters(int enabled);
 int kbo_get_ms_counters(const kbo_index* ix, kbo_ms_counters* out);
 /* Tuning knob: bases per MS chunk (0 = automatic).  Results never depend on it. */
 int kbo_set_chunk_len(uint32_t chunk_len);
+/* Index construction runs on the GPU for 2 <= k <= 32; enabled != 0 forces the host builder (for comparison). */
+int kbo_set_host_builder(int enabled);
 /* Tuning knob: probe iterations of K1 between two contraction phases (>= 1).  Results never depend on it. */
 int kbo_set_probe_iters(uint32_t iters);
 /* Experiment switches of K1 (bit 0: population count on the ALU pipe).  Results never depend on them. */

@@ -16,6 +16,7 @@
 
 #include "../../include/kbo_b200.h"
 #include "kernels.cuh"
+#include "index_build.cuh"
 #include "host_layout.hpp"
 #include "refine_host.hpp"
 #include "sbwt_host.hpp"
@@ -32,6 +33,7 @@ static std::atomic<uint32_t> g_chunk_len(0);
 static std::atomic<int> g_kernel_timing(0);
 static std::atomic<uint32_t> g_probe_iters(2);
 static std::atomic<uint32_t> g_ms_flags(0);
+static std::atomic<int> g_host_builder(0);
 static std::atomic<uint32_t> g_ms_block(128);
 
 static int fail(int code, const std::string& msg) {
@@ -200,6 +202,180 @@ static int upload_index(kbo_index* ix) {
     ix->view.lcs = ix->d_lcs;
     ix->view.n = (uint32_t)n;
     ix->view.k = h.k;
+    return KBO_OK;
+}
+
+// ---------------------------------------------------------------------------
+// index construction on the device (index_build.cuh), 2 <= k <= 32
+// ---------------------------------------------------------------------------
+struct TmpBufs {
+    std::vector<void*> ptrs;
+    ~TmpBufs() { for (void* p : ptrs) cudaFree(p); }
+    template <typename T> cudaError_t alloc(T** out, size_t count) {
+        void* p = nullptr;
+        cudaError_t e = cudaMalloc(&p, (count ? count : 1) * sizeof(T));
+        if (e == cudaSuccess) { ptrs.push_back(p); *out = (T*)p; }
+        return e;
+    }
+};
+
+static int build_index_gpu(kbo_index* ix, const uint8_t* const* seqs, const uint64_t* lens, uint64_t n_seqs, uint32_t k,
+                           bool revcomp) {
+    uint64_t total = 0;
+    std::vector<uint64_t> offsets(n_seqs + 1, 0);
+    for (uint64_t i = 0; i < n_seqs; ++i) { total += lens[i]; offsets[i + 1] = total; }
+    const Geometry g = kbo_b200::make_geometry(total, n_seqs, 64);
+    TmpBufs tmp;
+    uint8_t *d_ascii, *d_flags, *d_nopred, *d_Dlen = nullptr, *d_Plen;
+    uint64_t *d_off, *d_pack, *d_keys, *d_keys_rc = nullptr, *d_sel, *d_sorted, *d_R, *d_src, *d_Dkey = nullptr, *d_Pkey, *d_count;
+    uint32_t *d_inv, *d_sep, *d_wq, *d_rows32, *d_pc, *d_prefix;
+    CUDA_TRY(tmp.alloc(&d_ascii, total));
+    CUDA_TRY(tmp.alloc(&d_off, n_seqs + 1));
+    CUDA_TRY(tmp.alloc(&d_pack, g.n_words));
+    CUDA_TRY(tmp.alloc(&d_inv, g.n_words));
+    CUDA_TRY(tmp.alloc(&d_sep, g.n_words));
+    CUDA_TRY(tmp.alloc(&d_wq, g.n_words));
+    CUDA_TRY(tmp.alloc(&d_count, 2));
+    {   // sequences may live anywhere on the host: stage them contiguously
+        uint64_t at = 0;
+        for (uint64_t i = 0; i < n_seqs; ++i) {
+            if (lens[i]) CUDA_TRY(cudaMemcpy(d_ascii + at, seqs[i], lens[i], cudaMemcpyHostToDevice));
+            at += lens[i];
+        }
+    }
+    CUDA_TRY(cudaMemcpy(d_off, offsets.data(), (n_seqs + 1) * 8, cudaMemcpyHostToDevice));
+    QueryView qv;
+    qv.pack = d_pack; qv.inv = d_inv; qv.sep = d_sep; qv.wq = d_wq; qv.Lp = g.Lp; qv.n_words = g.n_words;
+    pack_queries_kernel<<<(unsigned)((g.n_words + 127) / 128), 128>>>(d_ascii, d_off, n_seqs, qv, d_pack, d_inv, d_sep, d_wq);
+    LAUNCHED();
+    const uint64_t Lp = g.Lp;
+    const uint64_t n_cand = revcomp ? 2 * Lp : Lp;
+    CUDA_TRY(tmp.alloc(&d_keys, Lp));
+    if (revcomp) CUDA_TRY(tmp.alloc(&d_keys_rc, Lp));
+    CUDA_TRY(tmp.alloc(&d_flags, Lp));
+    CUDA_TRY(tmp.alloc(&d_sel, n_cand));
+    CUDA_TRY(tmp.alloc(&d_sorted, n_cand));
+    CUDA_TRY(tmp.alloc(&d_R, n_cand));
+    kmer_keys_kernel<<<(unsigned)((Lp + 255) / 256), 256>>>(d_pack, d_inv, Lp, k, revcomp ? 1 : 0, d_keys, d_keys_rc, d_flags);
+    LAUNCHED();
+    CUDA_TRY(cudaGetLastError());
+    // compaction of the valid k-mers (forward, then reverse complements)
+    size_t tb = 0, need = 0;
+    void* d_tmp = nullptr;
+    cub::DeviceSelect::Flagged(nullptr, need, d_keys, d_flags, d_sel, d_count, (int64_t)Lp); tb = std::max(tb, need);
+    cub::DeviceRadixSort::SortKeys(nullptr, need, d_sel, d_sorted, (int64_t)n_cand, 64 - 2 * (int)k, 64); tb = std::max(tb, need);
+    cub::DeviceSelect::Unique(nullptr, need, d_sorted, d_R, d_count, (int64_t)n_cand); tb = std::max(tb, need);
+    CUDA_TRY(cudaMalloc(&d_tmp, tb ? tb : 1));
+    tmp.ptrs.push_back(d_tmp);
+    uint64_t h_count = 0, n_valid = 0;
+    need = tb;
+    CUDA_TRY(cub::DeviceSelect::Flagged(d_tmp, need, d_keys, d_flags, d_sel, d_count, (int64_t)Lp));
+    CUDA_TRY(cudaMemcpy(&h_count, d_count, 8, cudaMemcpyDeviceToHost));
+    n_valid = h_count;
+    if (revcomp) {
+        need = tb;
+        CUDA_TRY(cub::DeviceSelect::Flagged(d_tmp, need, d_keys_rc, d_flags, d_sel + n_valid, d_count, (int64_t)Lp));
+        CUDA_TRY(cudaMemcpy(&h_count, d_count, 8, cudaMemcpyDeviceToHost));
+        n_valid += h_count;
+    }
+    LAUNCHED(); LAUNCHED();
+    uint64_t nR = 0;
+    if (n_valid) {
+        need = tb;
+        CUDA_TRY(cub::DeviceRadixSort::SortKeys(d_tmp, need, d_sel, d_sorted, (int64_t)n_valid, 64 - 2 * (int)k, 64));
+        need = tb;
+        CUDA_TRY(cub::DeviceSelect::Unique(d_tmp, need, d_sorted, d_R, d_count, (int64_t)n_valid));
+        CUDA_TRY(cudaMemcpy(&nR, d_count, 8, cudaMemcpyDeviceToHost));
+    }
+    // dummy nodes: few, made on the host from the k-mers that have no predecessor
+    std::vector<uint64_t> h_src;
+    if (nR) {
+        CUDA_TRY(tmp.alloc(&d_nopred, nR));
+        CUDA_TRY(tmp.alloc(&d_src, nR));
+        no_predecessor_kernel<<<(unsigned)((nR + 255) / 256), 256>>>(d_R, nR, k, d_nopred);
+        LAUNCHED();
+        need = tb;
+        CUDA_TRY(cub::DeviceSelect::Flagged(d_tmp, need, d_R, d_nopred, d_src, d_count, (int64_t)nR));
+        uint64_t n_src = 0;
+        CUDA_TRY(cudaMemcpy(&n_src, d_count, 8, cudaMemcpyDeviceToHost));
+        h_src.resize(n_src);
+        if (n_src) CUDA_TRY(cudaMemcpy(h_src.data(), d_src, n_src * 8, cudaMemcpyDeviceToHost));
+    }
+    std::vector<std::pair<uint64_t, uint8_t>> dummies;
+    dummies.push_back({0ull, (uint8_t)0});
+    for (uint64_t x : h_src)
+        for (uint32_t j = 1; j < k; ++j) dummies.push_back({x << (2 * (k - j)), (uint8_t)j});
+    std::sort(dummies.begin(), dummies.end());
+    dummies.erase(std::unique(dummies.begin(), dummies.end()), dummies.end());
+    const uint64_t nD = dummies.size();
+    const uint64_t n = nR + nD;
+    if (n >= (1ull << 32) - 64) return fail(KBO_ERR_INDEX_TOO_LARGE, "n_sets must be < 2^32");
+    std::vector<uint64_t> h_Dkey(nD);
+    std::vector<uint8_t> h_Dlen(nD);
+    for (uint64_t i = 0; i < nD; ++i) { h_Dkey[i] = dummies[i].first; h_Dlen[i] = dummies[i].second; }
+    CUDA_TRY(tmp.alloc(&d_Dkey, nD));
+    CUDA_TRY(tmp.alloc(&d_Dlen, nD));
+    CUDA_TRY(cudaMemcpy(d_Dkey, h_Dkey.data(), nD * 8, cudaMemcpyHostToDevice));
+    CUDA_TRY(cudaMemcpy(d_Dlen, h_Dlen.data(), nD, cudaMemcpyHostToDevice));
+    CUDA_TRY(tmp.alloc(&d_Pkey, n));
+    CUDA_TRY(tmp.alloc(&d_Plen, n));
+    merge_nodes_kernel<<<(unsigned)((n + 255) / 256), 256>>>(d_R, nR, d_Dkey, d_Dlen, nD, k, d_Pkey, d_Plen);
+    LAUNCHED();
+    // final device arrays
+    const uint64_t nblk = (n >> 5) + 2;
+    const uint64_t stride = (nblk + 3) & ~3ull;
+    const uint64_t lcs_bytes = ((n + 8) & ~7ull) + 16;
+    CUDA_TRY(cudaMalloc((void**)&ix->d_rank, 4 * stride * 8));
+    CUDA_TRY(cudaMalloc((void**)&ix->d_lcs, lcs_bytes));
+    CUDA_TRY(cudaMemset(ix->d_lcs, 0, lcs_bytes));
+    CUDA_TRY(tmp.alloc(&d_rows32, 4 * stride));
+    CUDA_TRY(tmp.alloc(&d_pc, 4 * stride));
+    CUDA_TRY(tmp.alloc(&d_prefix, 4 * stride));
+    CUDA_TRY(cudaMemset(d_rows32, 0, 4 * stride * 4));
+    lcs_kernel<<<(unsigned)((n + 255) / 256), 256>>>(d_Pkey, d_Plen, n, ix->d_lcs);
+    LAUNCHED();
+    labels_kernel<<<(unsigned)((n + 255) / 256), 256>>>(d_Pkey, d_Plen, n, k, d_rows32, stride);
+    LAUNCHED();
+    row_popc_kernel<<<(unsigned)((4 * stride + 255) / 256), 256>>>(d_rows32, 4 * stride, d_pc);
+    LAUNCHED();
+    size_t scan_need = 0;
+    cub::DeviceScan::ExclusiveSum(nullptr, scan_need, d_pc, d_prefix, (int64_t)(4 * stride));
+    void* d_scan_tmp = d_tmp;
+    if (scan_need > tb) {
+        CUDA_TRY(cudaMalloc(&d_scan_tmp, scan_need));
+        tmp.ptrs.push_back(d_scan_tmp);
+    }
+    CUDA_TRY(cub::DeviceScan::ExclusiveSum(d_scan_tmp, scan_need, d_pc, d_prefix, (int64_t)(4 * stride)));
+    LAUNCHED();
+    compose_rank_kernel<<<(unsigned)((4 * stride + 255) / 256), 256>>>(d_rows32, d_prefix, 4 * stride, ix->d_rank);
+    LAUNCHED();
+    CUDA_TRY(cudaGetLastError());
+    // host copy of the plain SubsetMatrix form (search / access_kmer / export)
+    HostIndex& h = ix->host;
+    h.k = k;
+    h.n_sets = n;
+    h.n_kmers = nR;
+    std::vector<uint32_t> rows32((size_t)(4 * stride));
+    CUDA_TRY(cudaMemcpy(rows32.data(), d_rows32, 4 * stride * 4, cudaMemcpyDeviceToHost));
+    h.lcs.resize((size_t)n);
+    CUDA_TRY(cudaMemcpy(h.lcs.data(), ix->d_lcs, n, cudaMemcpyDeviceToHost));
+    const size_t nw64 = (size_t)(n + 63) / 64 + 1;
+    for (int c = 0; c < 4; ++c) {
+        h.rows[c].assign(nw64, 0);
+        for (size_t w = 0; w < nw64; ++w) {
+            const uint64_t lo = 2 * w < stride ? rows32[(size_t)(c * stride + 2 * w)] : 0;
+            const uint64_t hi = 2 * w + 1 < stride ? rows32[(size_t)(c * stride + 2 * w + 1)] : 0;
+            h.rows[c][w] = lo | (hi << 32);
+        }
+    }
+    h.finalize();
+    ix->rank_stride = stride;
+    ix->device_bytes = 4 * stride * 8 + lcs_bytes;
+    ix->view.rank = ix->d_rank;
+    ix->view.rank_stride = (uint32_t)stride;
+    ix->view.lcs = ix->d_lcs;
+    ix->view.n = (uint32_t)n;
+    ix->view.k = k;
     return KBO_OK;
 }
 
@@ -452,6 +628,21 @@ int kbo_index_build(const uint8_t* const* seqs, const uint64_t* lens, uint64_t n
     if (opts) o = *opts; else kbo_default_build_opts(&o);
     if (o.k == 0 || o.k > KBO_MAX_K) return fail(KBO_ERR_BAD_K, "1 <= k <= 64 in this build");
     kbo_index* ix = new kbo_index();
+    if (o.k >= 2 && o.k <= 32 && !g_host_builder.load()) {  // device construction (index_build.cuh)
+        int ndev = 0;
+        if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev == 0) {
+            delete ix;
+            return fail(KBO_ERR_CUDA, "no CUDA device available (this library has no CPU fallback)");
+        }
+        if (device < 0 || device >= ndev) { delete ix; return fail(KBO_ERR_BAD_ARGUMENT, "device ordinal out of range"); }
+        ix->device = device;
+        DeviceGuard dg(device);
+        if (!dg.ok) { delete ix; return fail(KBO_ERR_CUDA, "cudaSetDevice failed"); }
+        int rc = build_index_gpu(ix, seqs, lens, n_seqs, o.k, o.add_revcomp != 0);
+        if (rc) { kbo_index_free(ix); return rc; }
+        *out = ix;
+        return KBO_OK;
+    }
     std::string err = build_host_index(seqs, lens, n_seqs, o.k, o.add_revcomp != 0, o.num_threads ? o.num_threads : 1,
                                        &ix->host);
     if (!err.empty()) { delete ix; return fail(KBO_ERR_INDEX_TOO_LARGE, err); }
@@ -1145,6 +1336,7 @@ int kbo_get_ms_counters(const kbo_index* cix, kbo_ms_counters* out) {
     return KBO_OK;
 }
 int kbo_set_chunk_len(uint32_t chunk_len) { g_chunk_len = chunk_len; return KBO_OK; }
+int kbo_set_host_builder(int enabled) { g_host_builder = enabled ? 1 : 0; return KBO_OK; }
 int kbo_set_probe_iters(uint32_t iters) { g_probe_iters = iters ? iters : 1; return KBO_OK; }
 int kbo_set_ms_flags(uint32_t flags) {
     g_ms_flags = flags & 0xffu;

@@ -1,0 +1,158 @@
+// ===========================================================================
+// kbo_b200/csrc/index_build.cuh -- SBWT + LCS construction on the GPU
+// (index::build_sbwt_from_vecs, reference src/index.rs:56-99 -> sbwt builder;
+// semantics: SURVEY.md section 8c).  Used for k <= 32 (one 64-bit word per
+// k-mer); larger k takes the host builder in sbwt_host.cpp.
+//
+//   1. K0 packs the input sequences (2 bits/base + "not ACGT" mask; inputs are
+//      separated exactly like queries, so no k-mer spans two inputs);
+//   2. one thread per position emits the colex-packed k-mer ending there (and its
+//      reverse complement), flagged valid iff the k positions are all ACGT;
+//   3. compaction, radix sort and unique give the k-mer set R        [CUB];
+//   4. k-mers whose (k-1)-prefix is nobody's (k-1)-suffix are found by binary
+//      search; their few '$'-padded prefixes (dummy nodes) are made on the host;
+//   5. R and the dummies are merged by rank (binary searches) into P;
+//   6. LCS from neighbouring keys; one thread per node finds the source group
+//      of its incoming edge by binary search and sets the label bit;
+//   7. popcounts are prefix-summed over the four rows laid end to end, which
+//      directly yields C[c] + rank_c(32b) for the interleaved rank words.
+// Sorting / scanning / compaction use CUB (library code); nothing here is on the
+// query hot path.
+// ===========================================================================
+#pragma once
+#include <cub/cub.cuh>
+
+#include <algorithm>
+#include <vector>
+
+#include "kernels.cuh"
+#include "sbwt_host.hpp"
+
+namespace kbo_b200 {
+
+// k-mer ending at padded position i: bases [i-k+1, i], first base in the lowest bits of the 2k-bit window,
+// so (window << (64-2k)) compares colexicographically.
+__global__ void kmer_keys_kernel(const uint64_t* __restrict__ pack, const uint32_t* __restrict__ inv, uint64_t Lp,
+                                 uint32_t k, int revcomp, uint64_t* __restrict__ keys, uint64_t* __restrict__ keys_rc,
+                                 uint8_t* __restrict__ flags) {
+    const uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= Lp) return;
+    uint8_t ok = 0;
+    uint64_t key = 0, key_rc = 0;
+    if (i + 1 >= k) {
+        const uint64_t j0 = i + 1 - k;
+        // invalid bits of positions [j0, i]
+        const uint64_t w0 = j0 >> 5;
+        const uint32_t sh = (uint32_t)(j0 & 31);
+        uint64_t bad = (uint64_t)inv[w0] >> sh;
+        bad |= (uint64_t)inv[w0 + 1] << (32 - sh);
+        if (sh) bad |= (uint64_t)inv[w0 + 2] << (64 - sh);
+        const uint64_t kmask = k == 64 ? ~0ull : ((1ull << k) - 1ull);
+        if ((bad & kmask) == 0) {
+            ok = 1;
+            uint64_t win = pack[w0] >> (2 * sh);
+            if (sh) win |= pack[w0 + 1] << (64 - 2 * sh);
+            const uint64_t wmask = k == 32 ? ~0ull : ((1ull << (2 * k)) - 1ull);
+            win &= wmask;
+            key = win << (64 - 2 * k);
+            if (revcomp) {
+                // reverse the 2-bit groups of the window and complement them
+                uint64_t rv = __brevll(win);                                         // bit reversal: groups reversed, bits swapped
+                rv = ((rv & 0x5555555555555555ull) << 1) | ((rv >> 1) & 0x5555555555555555ull);  // swap back within groups
+                rv = ~rv;                                                            // complement (3 - code)
+                key_rc = rv & (~0ull << (64 - 2 * k));                               // reversed window sits in the top 2k bits
+            }
+        }
+    }
+    flags[i] = ok;
+    keys[i] = key;
+    if (revcomp) keys_rc[i] = key_rc;
+}
+
+// flag[a] = 1 iff no k-mer of R ends with the first k-1 characters of R[a]
+__global__ void no_predecessor_kernel(const uint64_t* __restrict__ R, uint64_t n, uint32_t k, uint8_t* __restrict__ flag) {
+    const uint64_t a = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (a >= n) return;
+    const uint64_t want = R[a] << 2;
+    const uint64_t sufmask = ~0ull << (64 - 2 * (k - 1));
+    uint64_t lo = 0, hi = n;
+    while (lo < hi) {
+        const uint64_t mid = (lo + hi) >> 1;
+        if (R[mid] < want) lo = mid + 1; else hi = mid;
+    }
+    flag[a] = !(lo < n && (R[lo] & sufmask) == want);
+}
+
+// P = R merged with the dummies D (both sorted by (key, len)); node order = (key, len)
+__global__ void merge_nodes_kernel(const uint64_t* __restrict__ R, uint64_t nR, const uint64_t* __restrict__ Dkey,
+                                   const uint8_t* __restrict__ Dlen, uint64_t nD, uint32_t k,
+                                   uint64_t* __restrict__ Pkey, uint8_t* __restrict__ Plen) {
+    const uint64_t t = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (t < nR) {
+        const uint64_t key = R[t];
+        uint64_t lo = 0, hi = nD;  // dummies with key' <= key all precede this k-mer (their len < k)
+        while (lo < hi) {
+            const uint64_t mid = (lo + hi) >> 1;
+            if (Dkey[mid] <= key) lo = mid + 1; else hi = mid;
+        }
+        Pkey[t + lo] = key;
+        Plen[t + lo] = (uint8_t)k;
+    } else if (t < nR + nD) {
+        const uint64_t b = t - nR;
+        const uint64_t key = Dkey[b];
+        uint64_t lo = 0, hi = nR;  // k-mers with key < key' precede this dummy
+        while (lo < hi) {
+            const uint64_t mid = (lo + hi) >> 1;
+            if (R[mid] < key) lo = mid + 1; else hi = mid;
+        }
+        Pkey[b + lo] = key;
+        Plen[b + lo] = Dlen[b];
+    }
+}
+
+__global__ void lcs_kernel(const uint64_t* __restrict__ Pkey, const uint8_t* __restrict__ Plen, uint64_t n,
+                           uint8_t* __restrict__ lcs) {
+    const uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    uint32_t v = 0;
+    if (i > 0) {
+        const uint64_t x = Pkey[i - 1] ^ Pkey[i];
+        const uint32_t same = (x ? (uint32_t)__clzll((long long)x) : 64u) >> 1;
+        const uint32_t lim = Plen[i - 1] < Plen[i] ? Plen[i - 1] : Plen[i];
+        v = same < lim ? same : lim;
+    }
+    lcs[i] = (uint8_t)v;
+}
+
+// node t (not the root) receives its edge from the first node of the group that ends with t's first k-1
+// characters; that node gets label (last character of t)
+__global__ void labels_kernel(const uint64_t* __restrict__ Pkey, const uint8_t* __restrict__ Plen, uint64_t n,
+                              uint32_t k, uint32_t* __restrict__ rows32, uint64_t row_words32) {
+    const uint64_t t = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (t == 0 || t >= n) return;
+    const uint64_t key = Pkey[t];
+    const uint32_t c = (uint32_t)(key >> 62);
+    const uint64_t ukey = key << 2;
+    const uint32_t ulen = (uint32_t)Plen[t] - 1u;
+    uint64_t lo = 0, hi = n;  // first node >= (ukey, ulen)
+    while (lo < hi) {
+        const uint64_t mid = (lo + hi) >> 1;
+        const uint64_t mk = Pkey[mid];
+        if (mk < ukey || (mk == ukey && Plen[mid] < ulen)) lo = mid + 1; else hi = mid;
+    }
+    atomicOr(rows32 + (uint64_t)c * row_words32 + (lo >> 5), 1u << (lo & 31));
+}
+
+__global__ void row_popc_kernel(const uint32_t* __restrict__ rows32, uint64_t total_words, uint32_t* __restrict__ pc) {
+    const uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < total_words) pc[i] = __popc(rows32[i]);
+}
+
+// rank word b of row c = (1 + ones before it in the four rows laid end to end) << 32 | bits
+__global__ void compose_rank_kernel(const uint32_t* __restrict__ rows32, const uint32_t* __restrict__ prefix,
+                                    uint64_t total_words, uint64_t* __restrict__ rank) {
+    const uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < total_words) rank[i] = ((uint64_t)(1u + prefix[i]) << 32) | rows32[i];
+}
+
+}  // namespace kbo_b200

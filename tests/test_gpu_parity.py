@@ -119,6 +119,40 @@ def test_index_build_matches_oracle(k, revcomp):
     assert np.array_equal(lcs, o.lcs()) and np.array_equal(Cc, o.C())
 
 
+@pytest.mark.parametrize("k,revcomp", [(2, False), (5, True), (16, False), (32, False), (32, True)])
+def test_gpu_and_host_builders_agree_with_oracle(k, revcomp):
+    """k <= 32 is built on the device (index_build.cuh); the host builder is forced for comparison."""
+    ref = with_ns(rand_seq(40_000, 17), 18, rate=0.001)
+    seqs = [ref[:25_000], ref[25_000:], b"ACGT" * 20, b"AC", ref[100:160]]
+    o = O.OracleIndex(seqs, k=k, add_revcomp=revcomp)
+    parts = []
+    for host in (False, True):
+        api.set_host_builder(host)
+        try:
+            ix = api.build(seqs, api.BuildOpts(k=k, add_revcomp=revcomp))
+        finally:
+            api.set_host_builder(False)
+        assert (ix.k, ix.n_sets, ix.n_kmers) == (o.k, o.n_sets, o.n_kmers), host
+        rows, lcs, Cc = ix.export_parts()
+        for a, b_ in zip(rows, o.rows()):
+            assert np.array_equal(a, b_), host
+        assert np.array_equal(lcs, o.lcs()) and np.array_equal(Cc, o.C()), host
+        q = synth.mutate(np.frombuffer(ref.replace(b"N", b"A"), dtype=np.uint8), 19).tobytes()[:5000]
+        parts.append(api.query_sbwt(q, ix))
+        od, ol, orr = o.query_sbwt(q)
+        assert np.array_equal(parts[-1][0], od) and np.array_equal(parts[-1][1], ol)
+    assert all(np.array_equal(a, b_) for a, b_ in zip(parts[0], parts[1]))
+
+
+def test_index_build_degenerate_inputs():
+    for seqs, k in (([b"AC"], 31), ([b"NNNN", b""], 5), ([b"ACGTACGTAC"], 10)):
+        o = O.OracleIndex(seqs, k=k)
+        ix = api.build(seqs, api.BuildOpts(k=k))
+        assert (ix.n_sets, ix.n_kmers) == (o.n_sets, o.n_kmers)
+        rows, lcs, Cc = ix.export_parts()
+        assert np.array_equal(lcs, o.lcs()) and all(np.array_equal(a, b_) for a, b_ in zip(rows, o.rows()))
+
+
 def test_index_from_parts_roundtrip():
     ref = rand_seq(20_000, 3)
     o = O.OracleIndex([ref], k=31)

@@ -830,6 +830,10 @@ static int matches_prologue(kbo_index* ix, const uint64_t* offsets, uint64_t nq,
     return KBO_OK;
 }
 
+static std::vector<uint64_t> split_queries(const uint64_t* offsets, uint64_t nq, uint64_t parts);
+
+// kbo::matches for a host CSR batch; large batches are pipelined over sub-batches on separate streams
+// (copy-in of part i+1 and copy-out of part i-1 overlap the kernels of part i).
 int kbo_matches_batch(const kbo_index* cix, const uint8_t* concat, const uint64_t* offsets, uint64_t n_queries,
                       double max_error_prob, uint8_t* chars_out) {
     kbo_index* ix = const_cast<kbo_index*>(cix);
@@ -840,33 +844,50 @@ int kbo_matches_batch(const kbo_index* cix, const uint8_t* concat, const uint64_
     if (rc) return rc;
     DeviceGuard dg(ix->device);
     if (!dg.ok) return fail(KBO_ERR_CUDA, "cudaSetDevice failed");
-    Workspace* ws = nullptr;
-    rc = acquire_ws(ix, &ws);
-    if (rc) return rc;
-    const Geometry g = make_geometry(total, n_queries);
-    cudaStream_t st = ws->stream;
-    auto body = [&]() -> int {
-        CUDA_TRY(ws->ascii.ensure(total, st));
-        CUDA_TRY(ws->offsets.ensure((n_queries + 1) * 8, st));
-        CUDA_TRY(ws->out.ensure(total + 16, st));
-        CUDA_TRY(cudaMemcpyAsync(ws->ascii.p, concat + offsets[0], total, cudaMemcpyHostToDevice, st));
-        std::vector<uint64_t> rel(n_queries + 1);
-        for (uint64_t i = 0; i <= n_queries; ++i) rel[i] = offsets[i] - offsets[0];
-        CUDA_TRY(cudaMemcpyAsync(ws->offsets.p, rel.data(), (n_queries + 1) * 8, cudaMemcpyHostToDevice, st));
-        CUDA_TRY(cudaEventRecord(ws->ev0, st));
-        int rc2 = matches_device(ix, ws, ws->ascii.as<uint8_t>(), ws->offsets.as<uint64_t>(), n_queries, g, thr,
-                                 ws->out.as<uint8_t>(), 0);
-        if (rc2) return rc2;
-        CUDA_TRY(cudaEventRecord(ws->ev1, st));
-        CUDA_TRY(cudaMemcpyAsync(chars_out + offsets[0], ws->out.p, total, cudaMemcpyDeviceToHost, st));
-        CUDA_TRY(cudaStreamSynchronize(st));
+    const uint64_t want_parts = g_profile_counters.load() ? 1 : std::min<uint64_t>(4, std::max<uint64_t>(1, total >> 21));
+    const std::vector<uint64_t> cut = split_queries(offsets, n_queries, want_parts);
+    const size_t np = cut.size() - 1;
+    std::vector<Workspace*> wss(np, nullptr);
+    std::vector<std::vector<uint64_t>> rels(np);
+    for (size_t s = 0; s < np && !rc; ++s) {
+        rc = acquire_ws(ix, &wss[s]);
+        if (rc) break;
+        Workspace* ws = wss[s];
+        cudaStream_t st = ws->stream;
+        const uint64_t q0 = cut[s], q1 = cut[s + 1], nq = q1 - q0;
+        const uint64_t bytes = offsets[q1] - offsets[q0];
+        const Geometry g = make_geometry(bytes, nq);
+        std::vector<uint64_t>& rel = rels[s];
+        rel.resize(nq + 1);
+        for (uint64_t i = 0; i <= nq; ++i) rel[i] = offsets[q0 + i] - offsets[q0];
+        auto body = [&]() -> int {
+            CUDA_TRY(ws->ascii.ensure(bytes, st));
+            CUDA_TRY(ws->offsets.ensure((nq + 1) * 8, st));
+            CUDA_TRY(ws->out.ensure(bytes + 16, st));
+            CUDA_TRY(cudaMemcpyAsync(ws->ascii.p, concat + offsets[q0], bytes, cudaMemcpyHostToDevice, st));
+            CUDA_TRY(cudaMemcpyAsync(ws->offsets.p, rel.data(), (nq + 1) * 8, cudaMemcpyHostToDevice, st));
+            CUDA_TRY(cudaEventRecord(ws->ev0, st));
+            int rc2 = matches_device(ix, ws, ws->ascii.as<uint8_t>(), ws->offsets.as<uint64_t>(), nq, g, thr,
+                                     ws->out.as<uint8_t>(), 0);
+            if (rc2) return rc2;
+            CUDA_TRY(cudaEventRecord(ws->ev1, st));
+            CUDA_TRY(cudaMemcpyAsync(chars_out + offsets[q0], ws->out.p, bytes, cudaMemcpyDeviceToHost, st));
+            return KBO_OK;
+        };
+        rc = body();
+    }
+    for (size_t s = 0; s < np; ++s) {
+        if (!wss[s]) continue;
+        cudaError_t e = cudaStreamSynchronize(wss[s]->stream);
+        if (e != cudaSuccess && !rc) rc = fail(KBO_ERR_CUDA, std::string("CUDA error: ") + cudaGetErrorString(e));
+    }
+    if (!rc && np == 1) {
         float ms = 0.f;
-        cudaEventElapsedTime(&ms, ws->ev0, ws->ev1);
+        cudaEventElapsedTime(&ms, wss[0]->ev0, wss[0]->ev1);
         ix->last_kernel_ms = ms;
-        return fetch_counters(ix, ws);
-    };
-    rc = body();
-    release_ws(ix, ws);
+        rc = fetch_counters(ix, wss[0]);
+    }
+    for (Workspace* w : wss) if (w) release_ws(ix, w);
     return rc;
 }
 
@@ -987,6 +1008,23 @@ static int run_rle_write(Workspace* ws, const uint8_t* d_aln, const uint64_t* d_
 }
 static_assert(sizeof(RleRecord) == sizeof(kbo_rle), "device and ABI RLE records must agree");
 
+// Splits a CSR batch into up to `parts` contiguous query ranges of similar base counts.
+static std::vector<uint64_t> split_queries(const uint64_t* offsets, uint64_t nq, uint64_t parts) {
+    std::vector<uint64_t> cut(1, 0);
+    const uint64_t total = offsets[nq] - offsets[0];
+    for (uint64_t s = 1; s < parts; ++s) {
+        const uint64_t target = offsets[0] + total * s / parts;
+        uint64_t q = (uint64_t)(std::lower_bound(offsets, offsets + nq + 1, target) - offsets);
+        if (q < cut.back()) q = cut.back();
+        if (q > nq) q = nq;
+        if (q != cut.back()) cut.push_back(q);
+    }
+    if (cut.back() != nq) cut.push_back(nq);
+    return cut;
+}
+
+// kbo::find for a host CSR batch.  Large batches are cut into sub-batches that run on their own streams, so
+// the host->device copy of sub-batch i+1 overlaps the kernels of sub-batch i.
 int kbo_find_batch(const kbo_index* cix, const uint8_t* concat, const uint64_t* offsets, uint64_t n_queries,
                    double max_error_prob, uint64_t max_gap_len, kbo_rle* rle_out, uint64_t rle_cap,
                    uint64_t* rle_offsets) {
@@ -999,50 +1037,92 @@ int kbo_find_batch(const kbo_index* cix, const uint8_t* concat, const uint64_t* 
     const uint32_t gap = (uint32_t)std::min<uint64_t>(max_gap_len, 0x7fffffffull);
     DeviceGuard dg(ix->device);
     if (!dg.ok) return fail(KBO_ERR_CUDA, "cudaSetDevice failed");
-    Workspace* ws = nullptr;
-    rc = acquire_ws(ix, &ws);
-    if (rc) return rc;
-    const Geometry g = make_geometry(total, n_queries);
-    cudaStream_t st = ws->stream;
-    auto body = [&]() -> int {
-        CUDA_TRY(ws->ascii.ensure(total, st));
-        CUDA_TRY(ws->offsets.ensure((n_queries + 1) * 8, st));
-        CUDA_TRY(ws->out.ensure(total + 16, st));
-        CUDA_TRY(ws->tmp64.ensure((n_queries + 1) * 8, st));
-        CUDA_TRY(cudaMemcpyAsync(ws->ascii.p, concat + offsets[0], total, cudaMemcpyHostToDevice, st));
-        std::vector<uint64_t> rel(n_queries + 1);
-        for (uint64_t i = 0; i <= n_queries; ++i) rel[i] = offsets[i] - offsets[0];
-        CUDA_TRY(cudaMemcpyAsync(ws->offsets.p, rel.data(), (n_queries + 1) * 8, cudaMemcpyHostToDevice, st));
-        CUDA_TRY(cudaEventRecord(ws->ev0, st));
-        int rc2 = matches_device(ix, ws, ws->ascii.as<uint8_t>(), ws->offsets.as<uint64_t>(), n_queries, g, thr,
-                                 ws->out.as<uint8_t>(), 0);
-        if (rc2) return rc2;
-        rc2 = run_rle_count_scan(ws, ws->out.as<uint8_t>(), ws->offsets.as<uint64_t>(), n_queries, gap,
-                                 ws->tmp64.as<uint64_t>());
-        if (rc2) return rc2;
-        CUDA_TRY(cudaMemcpyAsync(rle_offsets, ws->tmp64.p, (n_queries + 1) * 8, cudaMemcpyDeviceToHost, st));
-        CUDA_TRY(cudaStreamSynchronize(st));
-        const uint64_t n_rle = rle_offsets[n_queries];
-        if (n_rle > rle_cap) return fail(KBO_ERR_BUFFER_TOO_SMALL, "rle capacity too small");
-        if (n_rle) {
-            if (!rle_out) return fail(KBO_ERR_BAD_ARGUMENT, "rle_out is null");
-            CUDA_TRY(ws->out2.ensure(n_rle * sizeof(RleRecord), st));
-            rc2 = run_rle_write(ws, ws->out.as<uint8_t>(), ws->offsets.as<uint64_t>(), n_queries, gap,
-                                ws->tmp64.as<uint64_t>(), ws->out2.as<RleRecord>(), n_rle);
+    const uint64_t want_parts = g_profile_counters.load() ? 1 : std::min<uint64_t>(4, std::max<uint64_t>(1, total >> 21));
+    const std::vector<uint64_t> cut = split_queries(offsets, n_queries, want_parts);
+    const size_t np = cut.size() - 1;
+    std::vector<Workspace*> wss(np, nullptr);
+    std::vector<std::vector<uint64_t>> rels(np);
+    auto give_back = [&]() { for (Workspace* w : wss) if (w) release_ws(ix, w); };
+    // phase 1: enqueue copy-in, K0, K1, K2, K4 count + scan and the copy-out of the per-query offsets
+    for (size_t s = 0; s < np && !rc; ++s) {
+        rc = acquire_ws(ix, &wss[s]);
+        if (rc) break;
+        Workspace* ws = wss[s];
+        cudaStream_t st = ws->stream;
+        const uint64_t q0 = cut[s], q1 = cut[s + 1], nq = q1 - q0;
+        const uint64_t bytes = offsets[q1] - offsets[q0];
+        const Geometry g = make_geometry(bytes, nq);
+        std::vector<uint64_t>& rel = rels[s];
+        rel.resize(nq + 1);
+        for (uint64_t i = 0; i <= nq; ++i) rel[i] = offsets[q0 + i] - offsets[q0];
+        auto body = [&]() -> int {
+            CUDA_TRY(ws->ascii.ensure(bytes, st));
+            CUDA_TRY(ws->offsets.ensure((nq + 1) * 8, st));
+            CUDA_TRY(ws->out.ensure(bytes + 16, st));
+            CUDA_TRY(ws->tmp64.ensure((nq + 1) * 8, st));
+            CUDA_TRY(cudaMemcpyAsync(ws->ascii.p, concat + offsets[q0], bytes, cudaMemcpyHostToDevice, st));
+            CUDA_TRY(cudaMemcpyAsync(ws->offsets.p, rel.data(), (nq + 1) * 8, cudaMemcpyHostToDevice, st));
+            if (s == 0) CUDA_TRY(cudaEventRecord(ws->ev0, st));
+            int rc2 = matches_device(ix, ws, ws->ascii.as<uint8_t>(), ws->offsets.as<uint64_t>(), nq, g, thr,
+                                     ws->out.as<uint8_t>(), 0);
             if (rc2) return rc2;
-            CUDA_TRY(cudaEventRecord(ws->ev1, st));
-            CUDA_TRY(cudaMemcpyAsync(rle_out, ws->out2.p, n_rle * sizeof(RleRecord), cudaMemcpyDeviceToHost, st));
-        } else {
-            CUDA_TRY(cudaEventRecord(ws->ev1, st));
-        }
-        CUDA_TRY(cudaStreamSynchronize(st));
+            rc2 = run_rle_count_scan(ws, ws->out.as<uint8_t>(), ws->offsets.as<uint64_t>(), nq, gap,
+                                     ws->tmp64.as<uint64_t>());
+            if (rc2) return rc2;
+            // part-relative record offsets land in the caller's array; rebased in phase 2
+            CUDA_TRY(cudaMemcpyAsync(rle_offsets + q0 + (s ? 1 : 0), ws->tmp64.as<uint64_t>() + (s ? 1 : 0),
+                                     (nq + (s ? 0 : 1)) * 8, cudaMemcpyDeviceToHost, st));
+            return KBO_OK;
+        };
+        rc = body();
+    }
+    // phase 2: per sub-batch, in order: record count -> write pass -> copy-out of the records
+    uint64_t base = 0;
+    for (size_t s = 0; s < np && !rc; ++s) {
+        Workspace* ws = wss[s];
+        cudaStream_t st = ws->stream;
+        const uint64_t q0 = cut[s], q1 = cut[s + 1], nq = q1 - q0;
+        auto body = [&]() -> int {
+            CUDA_TRY(cudaStreamSynchronize(st));
+            const uint64_t n_rle = rle_offsets[q1];  // still part-relative
+            if (base + n_rle > rle_cap) {
+                // report the true total: finish counting the remaining parts
+                uint64_t tot = base + n_rle;
+                for (size_t t = s + 1; t < np; ++t) {
+                    CUDA_TRY(cudaStreamSynchronize(wss[t]->stream));
+                    tot += rle_offsets[cut[t + 1]];
+                }
+                rle_offsets[n_queries] = tot;
+                return fail(KBO_ERR_BUFFER_TOO_SMALL, "rle capacity too small");
+            }
+            if (n_rle) {
+                if (!rle_out) return fail(KBO_ERR_BAD_ARGUMENT, "rle_out is null");
+                CUDA_TRY(ws->out2.ensure(n_rle * sizeof(RleRecord), st));
+                int rc2 = run_rle_write(ws, ws->out.as<uint8_t>(), ws->offsets.as<uint64_t>(), nq, gap,
+                                        ws->tmp64.as<uint64_t>(), ws->out2.as<RleRecord>(), n_rle);
+                if (rc2) return rc2;
+                CUDA_TRY(cudaMemcpyAsync(rle_out + base, ws->out2.p, n_rle * sizeof(RleRecord), cudaMemcpyDeviceToHost,
+                                         st));
+            }
+            if (base) for (uint64_t q = q0 + 1; q <= q1; ++q) rle_offsets[q] += base;
+            base += n_rle;
+            return KBO_OK;
+        };
+        rc = body();
+    }
+    for (size_t s = 0; s < np; ++s) {
+        if (!wss[s]) continue;
+        if (s + 1 == np && !rc) cudaEventRecord(wss[s]->ev1, wss[s]->stream);
+        cudaError_t e = cudaStreamSynchronize(wss[s]->stream);
+        if (e != cudaSuccess && !rc) rc = fail(KBO_ERR_CUDA, std::string("CUDA error: ") + cudaGetErrorString(e));
+    }
+    if (!rc && np == 1) {
         float ms = 0.f;
-        cudaEventElapsedTime(&ms, ws->ev0, ws->ev1);
+        cudaEventElapsedTime(&ms, wss[0]->ev0, wss[0]->ev1);
         ix->last_kernel_ms = ms;
-        return fetch_counters(ix, ws);
-    };
-    rc = body();
-    release_ws(ix, ws);
+        rc = fetch_counters(ix, wss[0]);
+    }
+    give_back();
     return rc;
 }
 

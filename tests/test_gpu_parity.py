@@ -256,6 +256,36 @@ def test_matches_config2_shape_checksum():
     assert 0.5 < frac_m < 1.0
 
 
+def test_pipelined_sub_batches_match_oracle():
+    """Batches above 2 MB are cut into sub-batches on separate streams (copy/compute overlap): the result and
+    the RLE offsets must be identical to the unsplit computation."""
+    ref = synth.random_seq(300_000, 71)
+    o = O.OracleIndex([ref.tobytes()], k=31)
+    ix = api.build([ref.tobytes()], api.BuildOpts(k=31))
+    concat, off = synth.gene_queries(ref, 7000, 1000, 72, snp=0.02)  # 7 MB -> 3 parts
+    # ragged lengths so that part borders are not multiples of anything
+    lens = np.full(7000, 1000, dtype=np.int64)
+    lens[::7] = 333
+    pieces = [concat[int(off[i]):int(off[i]) + int(lens[i])] for i in range(7000)]
+    concat = np.concatenate(pieces)
+    off = np.concatenate([[0], np.cumsum(lens)]).astype(np.uint64)
+    got = api.matches_csr(concat, off, ix)
+    _, want, _ = o.matches_batch(concat, off, n_threads=8)
+    assert np.array_equal(got[:len(concat)], want)
+    buf, n = api.find_csr(concat, off, ix, api.FindOpts(max_gap_len=10))
+    assert n == int(buf.rle_offsets[-1]) and (np.diff(buf.rle_offsets.astype(np.int64)) >= 0).all()
+    for q in list(range(0, 7000, 97)) + [6999]:
+        a, b_ = int(buf.rle_offsets[q]), int(buf.rle_offsets[q + 1])
+        got_q = [tuple(int(getattr(buf.rle[j], f)) for f, _ in api.RleC._fields_) for j in range(a, b_)]
+        assert got_q == o.find(concat[int(off[q]):int(off[q + 1])].tobytes(), max_gap_len=10), q
+    small = api.FindBuffers(7000, cap=10)  # capacity error still reports the true count
+    with pytest.raises(api.KboPanic) as e:
+        api._check(api.load_library().kbo_find_batch(ix._h, api._p(concat, api.C.c_uint8), api._p(off, api.C.c_uint64),
+                                                     7000, 1e-7, 10, small.rle, small.cap,
+                                                     api._p(small.rle_offsets, api.C.c_uint64)))
+    assert e.value.status == 11 and int(small.rle_offsets[-1]) == n
+
+
 # ----------------------------------------------------- standalone derandomize / translate ---
 def valid_ms_vector(rng, n, k):
     out = np.zeros(n, dtype=np.int64)

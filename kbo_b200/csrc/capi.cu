@@ -74,7 +74,25 @@ struct DevBuf {
     template <typename T> T* as() const { return reinterpret_cast<T*>(p); }
 };
 
+struct PinnedBuf {  // page-locked host staging: copies to/from it are truly asynchronous
+    void* p = nullptr;
+    size_t cap = 0;
+    cudaError_t ensure(size_t bytes) {
+        if (bytes <= cap) return cudaSuccess;
+        if (p) cudaFreeHost(p);
+        p = nullptr;
+        cap = 0;
+        const size_t want = bytes + bytes / 4 + 256;
+        cudaError_t e = cudaHostAlloc(&p, want, cudaHostAllocDefault);
+        if (e == cudaSuccess) cap = want;
+        return e;
+    }
+    void release() { if (p) cudaFreeHost(p); p = nullptr; cap = 0; }
+    template <typename T> T* as() const { return reinterpret_cast<T*>(p); }
+};
+
 struct Workspace {
+    PinnedBuf h_rel, h_roff, h_rle;
     cudaStream_t stream = nullptr;
     bool own_stream = false;
     cudaEvent_t ev0 = nullptr, ev1 = nullptr;
@@ -83,6 +101,7 @@ struct Workspace {
     size_t timed_calls = 0;
     void destroy() {
         for (cudaEvent_t e : timing) cudaEventDestroy(e);
+        h_rel.release(); h_roff.release(); h_rle.release();
         DevBuf* all[] = {&ascii, &offsets, &pack, &inv, &sep, &wq, &ms, &l, &r, &out, &out2, &out3,
                          &tmp64, &tmp64b, &tmp32, &tmp32b, &counters};
         for (DevBuf* b : all) b->release();
@@ -90,11 +109,6 @@ struct Workspace {
         if (ev1) cudaEventDestroy(ev1);
         if (own_stream && stream) cudaStreamDestroy(stream);
     }
-};
-
-struct PinnedBuf {
-    void* p = nullptr;
-    size_t cap = 0;
 };
 
 struct kbo_index {
@@ -848,7 +862,6 @@ int kbo_matches_batch(const kbo_index* cix, const uint8_t* concat, const uint64_
     const std::vector<uint64_t> cut = split_queries(offsets, n_queries, want_parts);
     const size_t np = cut.size() - 1;
     std::vector<Workspace*> wss(np, nullptr);
-    std::vector<std::vector<uint64_t>> rels(np);
     for (size_t s = 0; s < np && !rc; ++s) {
         rc = acquire_ws(ix, &wss[s]);
         if (rc) break;
@@ -857,15 +870,15 @@ int kbo_matches_batch(const kbo_index* cix, const uint8_t* concat, const uint64_
         const uint64_t q0 = cut[s], q1 = cut[s + 1], nq = q1 - q0;
         const uint64_t bytes = offsets[q1] - offsets[q0];
         const Geometry g = make_geometry(bytes, nq);
-        std::vector<uint64_t>& rel = rels[s];
-        rel.resize(nq + 1);
-        for (uint64_t i = 0; i <= nq; ++i) rel[i] = offsets[q0 + i] - offsets[q0];
         auto body = [&]() -> int {
             CUDA_TRY(ws->ascii.ensure(bytes, st));
             CUDA_TRY(ws->offsets.ensure((nq + 1) * 8, st));
             CUDA_TRY(ws->out.ensure(bytes + 16, st));
+            CUDA_TRY(ws->h_rel.ensure((nq + 1) * 8));
+            uint64_t* rel = ws->h_rel.as<uint64_t>();
+            for (uint64_t i = 0; i <= nq; ++i) rel[i] = offsets[q0 + i] - offsets[q0];
             CUDA_TRY(cudaMemcpyAsync(ws->ascii.p, concat + offsets[q0], bytes, cudaMemcpyHostToDevice, st));
-            CUDA_TRY(cudaMemcpyAsync(ws->offsets.p, rel.data(), (nq + 1) * 8, cudaMemcpyHostToDevice, st));
+            CUDA_TRY(cudaMemcpyAsync(ws->offsets.p, rel, (nq + 1) * 8, cudaMemcpyHostToDevice, st));
             CUDA_TRY(cudaEventRecord(ws->ev0, st));
             int rc2 = matches_device(ix, ws, ws->ascii.as<uint8_t>(), ws->offsets.as<uint64_t>(), nq, g, thr,
                                      ws->out.as<uint8_t>(), 0);
@@ -1041,7 +1054,6 @@ int kbo_find_batch(const kbo_index* cix, const uint8_t* concat, const uint64_t* 
     const std::vector<uint64_t> cut = split_queries(offsets, n_queries, want_parts);
     const size_t np = cut.size() - 1;
     std::vector<Workspace*> wss(np, nullptr);
-    std::vector<std::vector<uint64_t>> rels(np);
     auto give_back = [&]() { for (Workspace* w : wss) if (w) release_ws(ix, w); };
     // phase 1: enqueue copy-in, K0, K1, K2, K4 count + scan and the copy-out of the per-query offsets
     for (size_t s = 0; s < np && !rc; ++s) {
@@ -1052,16 +1064,17 @@ int kbo_find_batch(const kbo_index* cix, const uint8_t* concat, const uint64_t* 
         const uint64_t q0 = cut[s], q1 = cut[s + 1], nq = q1 - q0;
         const uint64_t bytes = offsets[q1] - offsets[q0];
         const Geometry g = make_geometry(bytes, nq);
-        std::vector<uint64_t>& rel = rels[s];
-        rel.resize(nq + 1);
-        for (uint64_t i = 0; i <= nq; ++i) rel[i] = offsets[q0 + i] - offsets[q0];
         auto body = [&]() -> int {
             CUDA_TRY(ws->ascii.ensure(bytes, st));
             CUDA_TRY(ws->offsets.ensure((nq + 1) * 8, st));
             CUDA_TRY(ws->out.ensure(bytes + 16, st));
             CUDA_TRY(ws->tmp64.ensure((nq + 1) * 8, st));
+            CUDA_TRY(ws->h_rel.ensure((nq + 1) * 8));
+            CUDA_TRY(ws->h_roff.ensure((nq + 1) * 8));
+            uint64_t* rel = ws->h_rel.as<uint64_t>();
+            for (uint64_t i = 0; i <= nq; ++i) rel[i] = offsets[q0 + i] - offsets[q0];
             CUDA_TRY(cudaMemcpyAsync(ws->ascii.p, concat + offsets[q0], bytes, cudaMemcpyHostToDevice, st));
-            CUDA_TRY(cudaMemcpyAsync(ws->offsets.p, rel.data(), (nq + 1) * 8, cudaMemcpyHostToDevice, st));
+            CUDA_TRY(cudaMemcpyAsync(ws->offsets.p, rel, (nq + 1) * 8, cudaMemcpyHostToDevice, st));
             if (s == 0) CUDA_TRY(cudaEventRecord(ws->ev0, st));
             int rc2 = matches_device(ix, ws, ws->ascii.as<uint8_t>(), ws->offsets.as<uint64_t>(), nq, g, thr,
                                      ws->out.as<uint8_t>(), 0);
@@ -1069,52 +1082,49 @@ int kbo_find_batch(const kbo_index* cix, const uint8_t* concat, const uint64_t* 
             rc2 = run_rle_count_scan(ws, ws->out.as<uint8_t>(), ws->offsets.as<uint64_t>(), nq, gap,
                                      ws->tmp64.as<uint64_t>());
             if (rc2) return rc2;
-            // part-relative record offsets land in the caller's array; rebased in phase 2
-            CUDA_TRY(cudaMemcpyAsync(rle_offsets + q0 + (s ? 1 : 0), ws->tmp64.as<uint64_t>() + (s ? 1 : 0),
-                                     (nq + (s ? 0 : 1)) * 8, cudaMemcpyDeviceToHost, st));
+            CUDA_TRY(cudaMemcpyAsync(ws->h_roff.p, ws->tmp64.p, (nq + 1) * 8, cudaMemcpyDeviceToHost, st));
             return KBO_OK;
         };
         rc = body();
     }
-    // phase 2: per sub-batch, in order: record count -> write pass -> copy-out of the records
+    // phase 2: per sub-batch, in order: record count -> write pass -> asynchronous copy-out of the records
     uint64_t base = 0;
+    std::vector<uint64_t> part_base(np, 0), part_n(np, 0);
+    rle_offsets[0] = 0;
     for (size_t s = 0; s < np && !rc; ++s) {
         Workspace* ws = wss[s];
         cudaStream_t st = ws->stream;
         const uint64_t q0 = cut[s], q1 = cut[s + 1], nq = q1 - q0;
         auto body = [&]() -> int {
             CUDA_TRY(cudaStreamSynchronize(st));
-            const uint64_t n_rle = rle_offsets[q1];  // still part-relative
-            if (base + n_rle > rle_cap) {
-                // report the true total: finish counting the remaining parts
-                uint64_t tot = base + n_rle;
-                for (size_t t = s + 1; t < np; ++t) {
-                    CUDA_TRY(cudaStreamSynchronize(wss[t]->stream));
-                    tot += rle_offsets[cut[t + 1]];
-                }
-                rle_offsets[n_queries] = tot;
-                return fail(KBO_ERR_BUFFER_TOO_SMALL, "rle capacity too small");
-            }
+            const uint64_t* roff = ws->h_roff.as<uint64_t>();
+            const uint64_t n_rle = roff[nq];
+            for (uint64_t i = 1; i <= nq; ++i) rle_offsets[q0 + i] = base + roff[i];
+            part_base[s] = base;
+            part_n[s] = n_rle;
+            base += n_rle;
+            if (base > rle_cap) return KBO_OK;  // keep counting; reported below
             if (n_rle) {
                 if (!rle_out) return fail(KBO_ERR_BAD_ARGUMENT, "rle_out is null");
                 CUDA_TRY(ws->out2.ensure(n_rle * sizeof(RleRecord), st));
+                CUDA_TRY(ws->h_rle.ensure(n_rle * sizeof(RleRecord)));
                 int rc2 = run_rle_write(ws, ws->out.as<uint8_t>(), ws->offsets.as<uint64_t>(), nq, gap,
                                         ws->tmp64.as<uint64_t>(), ws->out2.as<RleRecord>(), n_rle);
                 if (rc2) return rc2;
-                CUDA_TRY(cudaMemcpyAsync(rle_out + base, ws->out2.p, n_rle * sizeof(RleRecord), cudaMemcpyDeviceToHost,
-                                         st));
+                CUDA_TRY(cudaMemcpyAsync(ws->h_rle.p, ws->out2.p, n_rle * sizeof(RleRecord), cudaMemcpyDeviceToHost, st));
             }
-            if (base) for (uint64_t q = q0 + 1; q <= q1; ++q) rle_offsets[q] += base;
-            base += n_rle;
             return KBO_OK;
         };
         rc = body();
     }
+    if (!rc && base > rle_cap) rc = fail(KBO_ERR_BUFFER_TOO_SMALL, "rle capacity too small");
+    // phase 3: collect the records
     for (size_t s = 0; s < np; ++s) {
         if (!wss[s]) continue;
         if (s + 1 == np && !rc) cudaEventRecord(wss[s]->ev1, wss[s]->stream);
         cudaError_t e = cudaStreamSynchronize(wss[s]->stream);
         if (e != cudaSuccess && !rc) rc = fail(KBO_ERR_CUDA, std::string("CUDA error: ") + cudaGetErrorString(e));
+        if (!rc && part_n[s]) std::memcpy(rle_out + part_base[s], wss[s]->h_rle.p, part_n[s] * sizeof(RleRecord));
     }
     if (!rc && np == 1) {
         float ms = 0.f;

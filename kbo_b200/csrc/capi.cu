@@ -34,6 +34,7 @@ static std::atomic<int> g_kernel_timing(0);
 static std::atomic<uint32_t> g_probe_iters(2);
 static std::atomic<uint32_t> g_ms_flags(0);
 static std::atomic<int> g_host_builder(0);
+static std::atomic<uint32_t> g_parts(0);
 static std::atomic<uint32_t> g_ms_block(128);
 
 static int fail(int code, const std::string& msg) {
@@ -858,7 +859,7 @@ int kbo_matches_batch(const kbo_index* cix, const uint8_t* concat, const uint64_
     if (rc) return rc;
     DeviceGuard dg(ix->device);
     if (!dg.ok) return fail(KBO_ERR_CUDA, "cudaSetDevice failed");
-    const uint64_t want_parts = g_profile_counters.load() ? 1 : std::min<uint64_t>(4, std::max<uint64_t>(1, total >> 21));
+    const uint64_t want_parts = g_profile_counters.load() ? 1 : (g_parts.load() ? g_parts.load() : std::min<uint64_t>(4, std::max<uint64_t>(1, total >> 21)));
     const std::vector<uint64_t> cut = split_queries(offsets, n_queries, want_parts);
     const size_t np = cut.size() - 1;
     std::vector<Workspace*> wss(np, nullptr);
@@ -1050,7 +1051,7 @@ int kbo_find_batch(const kbo_index* cix, const uint8_t* concat, const uint64_t* 
     const uint32_t gap = (uint32_t)std::min<uint64_t>(max_gap_len, 0x7fffffffull);
     DeviceGuard dg(ix->device);
     if (!dg.ok) return fail(KBO_ERR_CUDA, "cudaSetDevice failed");
-    const uint64_t want_parts = g_profile_counters.load() ? 1 : std::min<uint64_t>(4, std::max<uint64_t>(1, total >> 21));
+    const uint64_t want_parts = g_profile_counters.load() ? 1 : (g_parts.load() ? g_parts.load() : std::min<uint64_t>(4, std::max<uint64_t>(1, total >> 21)));
     const std::vector<uint64_t> cut = split_queries(offsets, n_queries, want_parts);
     const size_t np = cut.size() - 1;
     std::vector<Workspace*> wss(np, nullptr);
@@ -1426,6 +1427,7 @@ int kbo_get_ms_counters(const kbo_index* cix, kbo_ms_counters* out) {
     return KBO_OK;
 }
 int kbo_set_chunk_len(uint32_t chunk_len) { g_chunk_len = chunk_len; return KBO_OK; }
+int kbo_set_pipeline_parts(uint32_t parts) { g_parts = parts > 64 ? 64 : parts; return KBO_OK; }
 int kbo_set_host_builder(int enabled) { g_host_builder = enabled ? 1 : 0; return KBO_OK; }
 int kbo_set_probe_iters(uint32_t iters) { g_probe_iters = iters ? iters : 1; return KBO_OK; }
 int kbo_set_ms_flags(uint32_t flags) {

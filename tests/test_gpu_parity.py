@@ -256,6 +256,50 @@ def test_matches_config2_shape_checksum():
     assert 0.5 < frac_m < 1.0
 
 
+def test_config2_full_size_bit_exact():
+    """BASELINE.json configs[1] at FULL size (10,000 x 1 kbp vs 5 Mbp, k = 31): every alignment character and
+    every RLE record equals the oracle's; plus size-independent properties of the MS vector."""
+    ref = synth.random_seq(5_000_000, synth.SEED_C2_REF)
+    o = O.OracleIndex([ref.tobytes()], k=31)
+    ix = api.build([ref], api.BuildOpts(k=31))
+    assert (ix.n_sets, ix.n_kmers) == (o.n_sets, o.n_kmers)
+    concat, off = synth.gene_queries(ref, 10_000, 1000, synth.SEED_C2_GENES)
+    got = api.matches_csr(concat, off, ix)
+    _, want, _ = o.matches_batch(concat, off, n_threads=16)
+    assert np.array_equal(got[:len(concat)], want)
+    buf, n = api.find_csr(concat, off, ix)
+    secs, n_want, _ = O.find_batch_timed(o, concat, off, 1e-7, 0, 16)
+    assert n == n_want
+    for q in range(0, 10_000, 501):
+        a, b_ = int(buf.rle_offsets[q]), int(buf.rle_offsets[q + 1])
+        got_q = [tuple(int(getattr(buf.rle[j], f)) for f, _ in api.RleC._fields_) for j in range(a, b_)]
+        assert got_q == o.find(concat[int(off[q]):int(off[q + 1])].tobytes()), q
+    d, _, _, _ = api.query_sbwt_batch([concat[:2_000_000].tobytes()], ix, intervals=False)
+    di = d.astype(np.int64)
+    assert (di[1:] <= di[:-1] + 1).all() and di.max() == 31
+
+
+def test_hbm_resident_index_regime():
+    """An index well beyond L2 (120 Mbp -> 240 MB on the device): chunking-independence and oracle parity on a
+    sample of queries (the oracle index of this size takes too long to build in a unit test, so parity is checked
+    against a 3 Mbp sub-index for queries drawn from that part, whose MS can only be >= there)."""
+    big = synth.random_seq(120_000_000, 81)
+    ix = api.build([big], api.BuildOpts(k=31))
+    assert ix.device_bytes > 200_000_000
+    concat, off = synth.gene_queries(big[:3_000_000], 2000, 1000, 82)
+    outs = []
+    for chunk_len in (64, 512):
+        api.set_chunk_len(chunk_len)
+        outs.append(api.matches_csr(concat, off, ix).copy())
+    api.set_chunk_len(0)
+    assert np.array_equal(outs[0], outs[1])
+    sub = O.OracleIndex([big[:3_000_000].tobytes()], k=31)
+    d_big, _, _, _ = api.query_sbwt_batch([concat[:200_000].tobytes()], ix, intervals=False)
+    d_sub, _, _ = sub.query_sbwt(concat[:200_000].tobytes())
+    assert (d_big.astype(np.int64) >= d_sub.astype(np.int64)).all()
+    assert (d_big == 31).mean() > 0.5
+
+
 def test_pipelined_sub_batches_match_oracle():
     """Batches above 2 MB are cut into sub-batches on separate streams (copy/compute overlap): the result and
     the RLE offsets must be identical to the unsplit computation."""

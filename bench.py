@@ -5,12 +5,12 @@ Workload (BASELINE.json configs[1]): kbo::find of 10,000 synthetic 1 kbp gene qu
 against a 5 Mbp reference, k = 31, p = 1e-7; the index (~10 MB) is L2 resident.  A "step" is one
 pass of the hot path over one batch of 10,000 queries (10^7 query bases).
 
-  value : whole-job throughput with the batch already resident in HBM (kbo_matches_batch_device:
-          K0 pack -> K1 matching statistics -> K2 derandomize+translate), CUDA events on the launch
-          stream, max over ranks.  Steps rotate through `--batches` distinct batches whose total
+  value : whole-job throughput with the batch already resident in HBM (kbo_find_batch_device:
+          K0 pack -> K1 matching statistics -> K2 derandomize+translate -> K4 run-length records),
+          CUDA events on the launch stream, max over ranks.  Steps rotate through `--batches` distinct batches whose total
           size exceeds L2, so queries always come from HBM while the index stays L2 resident.
   e2e   : the same metric through the host-buffer C ABI call a kbo user makes (kbo_find_batch):
-          pinned host -> device copy, kernels, device -> host copy of the alignment, host RLE.
+          pinned host -> device copy of the queries, kernels, device -> host copy of the RLE records.
   roofline     : K1 (ms_kernel), algorithmic bytes / its CUDA-event duration vs the
                  measured HBM peak (MEASURED_PEAKS.json); random-sector L2/HBM rates beside it.
   cpu_baseline : the C++ oracle (restatement of kbo 0.5.1 + sbwt 0.3.4 semantics) running kbo::find
@@ -362,8 +362,10 @@ def run_ours(args, rank, local_rank, world):
                 "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "u8", "data": "synthetic",
                 "config": cfg, "clocks": clocks,
                 "e2e": {"value": e2e_value, "unit": "query bases/s",
-                        "h2d_bytes_per_step": bases_per_step + 8 * (nq + 1), "d2h_bytes_per_step": bases_per_step,
-                        "api": "kbo_find_batch (pinned host buffers; host RLE pass inside the call)"},
+                        "h2d_bytes_per_step": bases_per_step + 8 * (nq + 1),
+                        "d2h_bytes_per_step": 8 * (nq + 1) + 56 * n_rle,
+                        "api": "kbo_find_batch: pinned host queries in, RLE records + per-query offsets out "
+                               "(matches and run lengths computed on the device; sub-batches pipelined on 4 streams)"},
                 "gpu_launches": int(lt.item()), "roofline": roof}
         if cpu is not None:
             line["cpu_baseline"] = cpu

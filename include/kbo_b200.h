@@ -194,6 +194,8 @@ int kbo_set_profile_counters(int enabled);
 int kbo_get_ms_counters(const kbo_index* ix, kbo_ms_counters* out);
 /* Tuning knob: bases per MS chunk (0 = automatic).  Results never depend on it. */
 int kbo_set_chunk_len(uint32_t chunk_len);
+/* Tuning knob: number of concurrent sub-batches inside the device-pointer batch calls (0 = automatic). */
+int kbo_set_device_parts(uint32_t parts);
 /* Tuning knob: number of sub-batches the host-buffer batch calls are pipelined over (0 = automatic). */
 int kbo_set_pipeline_parts(uint32_t parts);
 /* Index construction runs on the GPU for 2 <= k <= 32; enabled != 0 forces the host builder (for comparison). */

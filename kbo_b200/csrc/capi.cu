@@ -35,6 +35,7 @@ static std::atomic<uint32_t> g_probe_iters(2);
 static std::atomic<uint32_t> g_ms_flags(0);
 static std::atomic<int> g_host_builder(0);
 static std::atomic<uint32_t> g_parts(0);
+static std::atomic<uint32_t> g_dev_parts(0);
 static std::atomic<uint32_t> g_ms_block(128);
 
 static int fail(int code, const std::string& msg) {
@@ -94,6 +95,9 @@ struct PinnedBuf {  // page-locked host staging: copies to/from it are truly asy
 
 struct Workspace {
     PinnedBuf h_rel, h_roff, h_rle;
+    std::vector<Workspace*> subs;          // per-part workspaces with their own streams (device-pointer calls)
+    cudaEvent_t ev_fork = nullptr;
+    std::vector<cudaEvent_t> ev_join;
     cudaStream_t stream = nullptr;
     bool own_stream = false;
     cudaEvent_t ev0 = nullptr, ev1 = nullptr;
@@ -103,6 +107,9 @@ struct Workspace {
     void destroy() {
         for (cudaEvent_t e : timing) cudaEventDestroy(e);
         h_rel.release(); h_roff.release(); h_rle.release();
+        for (Workspace* w : subs) { w->destroy(); delete w; }
+        if (ev_fork) cudaEventDestroy(ev_fork);
+        for (cudaEvent_t e : ev_join) cudaEventDestroy(e);
         DevBuf* all[] = {&ascii, &offsets, &pack, &inv, &sep, &wq, &ms, &l, &r, &out, &out2, &out3,
                          &tmp64, &tmp64b, &tmp32, &tmp32b, &counters};
         for (DevBuf* b : all) b->release();
@@ -911,6 +918,69 @@ int kbo_matches(const kbo_index* ix, const uint8_t* query, uint64_t len, double 
     return kbo_matches_batch(ix, query ? query : (const uint8_t*)"", offsets, 1, max_error_prob, chars_out);
 }
 
+// Device-resident batch: the batch is cut into sub-batches that run K0 -> K1 -> K2 (-> K4 count) on their own
+// streams, forked from and joined back into the caller's stream.  K1 alone does not fill the machine (it is
+// bound by instruction issue at ~50 % occupancy), so the streaming kernels of one part overlap K1 of another.
+// `counts` / `stage` (optional) receive the per-query segment counts and staged records for kbo::find.
+static int matches_device_forked(kbo_index* ix, Workspace* ws, const uint8_t* d_concat, const uint64_t* d_offsets,
+                                 const uint64_t* host_offsets, uint64_t nq, uint32_t thr, uint8_t* d_chars,
+                                 bool want_rle, uint32_t gap) {
+    const uint64_t total = host_offsets[nq];
+    uint64_t want = g_dev_parts.load();
+    if (!want) want = std::min<uint64_t>(4, std::max<uint64_t>(1, total >> 21));
+    if (g_profile_counters.load() || g_kernel_timing.load()) want = 1;  // instrumentation passes stay serial
+    const std::vector<uint64_t> cut = split_queries(host_offsets, nq, want);
+    const size_t np = cut.size() - 1;
+    cudaStream_t user = ws->stream;
+    if (want_rle) {
+        CUDA_TRY(ws->tmp32.ensure(nq * 4, user));
+        CUDA_TRY(ws->out3.ensure(nq * RLE_STAGE * sizeof(RleRecord), user));
+    }
+    auto rle_count = [&](Workspace* w, uint64_t q0, uint64_t n) -> int {
+        const unsigned threads = 128;
+        const unsigned blocks = (unsigned)((n * 32 + threads - 1) / threads);
+        rle_kernel<false><<<blocks, threads, 0, w->stream>>>(d_chars + host_offsets[q0], d_offsets + q0, n, gap,
+                                                             ws->tmp32.as<uint32_t>() + q0,
+                                                             ws->out3.as<RleRecord>() + q0 * RLE_STAGE, nullptr,
+                                                             nullptr, 0);
+        LAUNCHED();
+        CUDA_TRY(cudaGetLastError());
+        return KBO_OK;
+    };
+    if (np == 1) {
+        const Geometry g = make_geometry(total, nq);
+        int rc = matches_device(ix, ws, d_concat, d_offsets, nq, g, thr, d_chars, 0);
+        if (rc) return rc;
+        return want_rle ? rle_count(ws, 0, nq) : KBO_OK;
+    }
+    while (ws->subs.size() < np) {
+        Workspace* sub = new Workspace();
+        sub->own_stream = true;
+        ws->subs.push_back(sub);
+        CUDA_TRY(cudaStreamCreateWithFlags(&sub->stream, cudaStreamNonBlocking));
+        cudaEvent_t e;
+        CUDA_TRY(cudaEventCreateWithFlags(&e, cudaEventDisableTiming));
+        ws->ev_join.push_back(e);
+    }
+    if (!ws->ev_fork) CUDA_TRY(cudaEventCreateWithFlags(&ws->ev_fork, cudaEventDisableTiming));
+    CUDA_TRY(cudaEventRecord(ws->ev_fork, user));
+    for (size_t s = 0; s < np; ++s) {
+        Workspace* sub = ws->subs[s];
+        const uint64_t q0 = cut[s], q1 = cut[s + 1], n = q1 - q0;
+        const Geometry g = make_geometry(host_offsets[q1] - host_offsets[q0], n);
+        CUDA_TRY(cudaStreamWaitEvent(sub->stream, ws->ev_fork, 0));
+        int rc = matches_device(ix, sub, d_concat, d_offsets + q0, n, g, thr, d_chars, host_offsets[q0]);
+        if (rc) return rc;
+        if (want_rle) {
+            rc = rle_count(sub, q0, n);
+            if (rc) return rc;
+        }
+        CUDA_TRY(cudaEventRecord(ws->ev_join[s], sub->stream));
+        CUDA_TRY(cudaStreamWaitEvent(user, ws->ev_join[s], 0));
+    }
+    return KBO_OK;
+}
+
 int kbo_matches_batch_device(const kbo_index* cix, const uint8_t* d_concat, const uint64_t* d_offsets,
                              const uint64_t* host_offsets, uint64_t n_queries, double max_error_prob,
                              uint8_t* d_chars_out, void* stream) {
@@ -926,8 +996,7 @@ int kbo_matches_batch_device(const kbo_index* cix, const uint8_t* d_concat, cons
     Workspace* ws = nullptr;
     rc = stream_ws(ix, (cudaStream_t)stream, &ws);
     if (rc) return rc;
-    const Geometry g = make_geometry(total, n_queries);
-    rc = matches_device(ix, ws, d_concat, d_offsets, n_queries, g, thr, d_chars_out, 0);
+    rc = matches_device_forked(ix, ws, d_concat, d_offsets, host_offsets, n_queries, thr, d_chars_out, false, 0);
     if (rc) return rc;
     if (g_profile_counters.load()) return fetch_counters(ix, ws);
     return KBO_OK;
@@ -1154,12 +1223,13 @@ int kbo_find_batch_device(const kbo_index* cix, const uint8_t* d_concat, const u
     Workspace* ws = nullptr;
     rc = stream_ws(ix, (cudaStream_t)stream, &ws);
     if (rc) return rc;
-    const Geometry g = make_geometry(total, n_queries);
     CUDA_TRY(ws->out.ensure(total + 16, ws->stream));
-    rc = matches_device(ix, ws, d_concat, d_offsets, n_queries, g, thr, ws->out.as<uint8_t>(), 0);
+    rc = matches_device_forked(ix, ws, d_concat, d_offsets, host_offsets, n_queries, thr, ws->out.as<uint8_t>(), true,
+                               gap);
     if (rc) return rc;
-    rc = run_rle_count_scan(ws, ws->out.as<uint8_t>(), d_offsets, n_queries, gap, d_rle_offsets);
-    if (rc) return rc;
+    rle_scan_kernel<<<1, 1024, 0, ws->stream>>>(ws->tmp32.as<uint32_t>(), n_queries, d_rle_offsets);
+    LAUNCHED();
+    CUDA_TRY(cudaGetLastError());
     return run_rle_write(ws, ws->out.as<uint8_t>(), d_offsets, n_queries, gap, d_rle_offsets,
                          reinterpret_cast<RleRecord*>(d_rle_out), rle_cap);
 }
@@ -1427,6 +1497,7 @@ int kbo_get_ms_counters(const kbo_index* cix, kbo_ms_counters* out) {
     return KBO_OK;
 }
 int kbo_set_chunk_len(uint32_t chunk_len) { g_chunk_len = chunk_len; return KBO_OK; }
+int kbo_set_device_parts(uint32_t parts) { g_dev_parts = parts > 16 ? 16 : parts; return KBO_OK; }
 int kbo_set_pipeline_parts(uint32_t parts) { g_parts = parts > 64 ? 64 : parts; return KBO_OK; }
 int kbo_set_host_builder(int enabled) { g_host_builder = enabled ? 1 : 0; return KBO_OK; }
 int kbo_set_probe_iters(uint32_t iters) { g_probe_iters = iters ? iters : 1; return KBO_OK; }

@@ -53,6 +53,8 @@ def parse_args():
     ap.add_argument("--chunk-len", type=int, default=0, help="MS chunk length (0 = automatic)")
     ap.add_argument("--probe-iters", type=int, default=0, help="K1 probe iterations per contraction phase (0 = default)")
     ap.add_argument("--ms-flags", type=int, default=0, help="K1 experiment switches")
+    ap.add_argument("--streams", type=int, default=4,
+                    help="CUDA streams the device-resident steps are issued round-robin on (independent batches)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--cpu-seconds", type=float, default=20.0, help="target CPU work (core-seconds) of the cpu_baseline sample")
     return ap.parse_args()
@@ -252,10 +254,13 @@ def run_ours(args, rank, local_rank, world):
     d_rle_off = [torch.empty(nq + 1, dtype=torch.int64, device="cuda") for _ in batches]
     torch.cuda.synchronize()
 
-    def step_device(s):
+    workers = [torch.cuda.Stream() for _ in range(max(1, args.streams))]
+
+    def step_device(s, on=None):
         b = s % len(batches)
+        st = on if on is not None else workers[s % len(workers)].cuda_stream
         api.find_device(index, d_in[b].data_ptr(), d_off.data_ptr(), offsets, d_rle[b].data_ptr(), rle_cap,
-                        d_rle_off[b].data_ptr(), P, 0, sptr)
+                        d_rle_off[b].data_ptr(), P, 0, st)
 
     def barrier():
         torch.cuda.synchronize()
@@ -264,7 +269,9 @@ def run_ours(args, rank, local_rank, world):
         torch.cuda.synchronize()
 
     # ---- value: device-resident ---------------------------------------------------------------
-    for s in range(args.warmup):
+    # Steps are independent batches; they are issued round-robin on `--streams` streams that fork from and
+    # join into the timing stream, so the CUDA events on that stream bracket exactly the K steps.
+    for s in range(max(args.warmup, len(workers))):
         step_device(s)
     barrier()
     sampler = ClockSampler(dev)
@@ -273,8 +280,14 @@ def run_ours(args, rank, local_rank, world):
     n0 = api.kernel_launch_count()
     barrier()
     e0.record(stream)
+    for w in workers:
+        w.wait_event(e0)
     for s in range(args.steps):
         step_device(args.warmup + s)
+    for w in workers:
+        done = torch.cuda.Event()
+        done.record(w)
+        stream.wait_event(done)
     e1.record(stream)
     barrier()
     launches = api.kernel_launch_count() - n0
@@ -284,8 +297,11 @@ def run_ours(args, rank, local_rank, world):
     # library runs these instrumented calls serially (no sub-batch concurrency), so a kernel's elapsed time
     # is its own duration
     api.set_kernel_timing(True)
+    step_device(0, on=sptr)  # sizes the serial workspace; discarded
+    torch.cuda.synchronize()
+    api.collect_kernel_times(index, sptr)
     for s in range(args.steps):
-        step_device(args.warmup + s)
+        step_device(args.warmup + s, on=sptr)
     torch.cuda.synchronize()
     api.set_kernel_timing(False)
     ksum, kcalls = api.collect_kernel_times(index, sptr)
@@ -331,7 +347,7 @@ def run_ours(args, rank, local_rank, world):
             "kernel_ms": {"pack": ksum["pack"] / max(kcalls, 1), "ms": k1_ms,
                           "derand_translate": ksum["derand_translate"] / max(kcalls, 1),
                           "how": "CUDA events around each kernel over %d serial instrumented steps on the launch "
-                                 "stream (the timed `value` region overlaps sub-batches on 4 streams)" % kcalls},
+                                 "stream (the timed `value` region overlaps independent steps on %d streams)" % (kcalls, len(workers))},
             "events_per_base": {"extend_attempts": cnt["emit_extend_attempts"] / max(L, 1),
                                 "contractions": cnt["emit_contractions"] / max(L, 1),
                                 "warmup_overhead": cnt["bases_processed"] / max(L, 1)},
@@ -364,6 +380,7 @@ def run_ours(args, rank, local_rank, world):
         cfg = config_dict(args)
         cfg.update({"chunk_len": args.chunk_len or "auto", "index_device_bytes": index.device_bytes,
                     "n_sets": index.n_sets, "index_build_s_host": round(index_build_s, 2), "rle_records_per_step": n_rle,
+                    "streams": len(workers),
                     "parallelism": "replicated index, %d rank(s) x own batches" % world})
         line = {"metric": "query bases/s (kbo find, whole box)", "value": value, "unit": "query bases/s",
                 "n_gpus": world, "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms_max / args.steps,

@@ -927,7 +927,7 @@ static int matches_device_forked(kbo_index* ix, Workspace* ws, const uint8_t* d_
                                  bool want_rle, uint32_t gap) {
     const uint64_t total = host_offsets[nq];
     uint64_t want = g_dev_parts.load();
-    if (!want) want = std::min<uint64_t>(4, std::max<uint64_t>(1, total >> 21));
+    if (!want) want = std::min<uint64_t>(2, std::max<uint64_t>(1, total >> 22));
     if (g_profile_counters.load() || g_kernel_timing.load()) want = 1;  // instrumentation passes stay serial
     const std::vector<uint64_t> cut = split_queries(host_offsets, nq, want);
     const size_t np = cut.size() - 1;

@@ -43,7 +43,7 @@ SECTOR = 32
 def parse_args():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
-    ap.add_argument("--steps", type=int, default=20)
+    ap.add_argument("--steps", type=int, default=400)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--ref-len", type=int, default=5_000_000)
@@ -55,6 +55,8 @@ def parse_args():
     ap.add_argument("--ms-flags", type=int, default=0, help="K1 experiment switches")
     ap.add_argument("--streams", type=int, default=4,
                     help="CUDA streams the device-resident steps are issued round-robin on (independent batches)")
+    ap.add_argument("--e2e-threads", type=int, default=2,
+                    help="host threads issuing the end-to-end calls concurrently (kbo-cli style per-query threading)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--cpu-seconds", type=float, default=20.0, help="target CPU work (core-seconds) of the cpu_baseline sample")
     return ap.parse_args()
@@ -75,7 +77,7 @@ class ClockSampler:
     def start(self):
         try:
             self.proc = subprocess.Popen(["nvidia-smi", "-i", str(self.device), "--query-gpu=" + self.Q,
-                                          "--format=csv,noheader,nounits", "-lms", "100"],
+                                          "--format=csv,noheader,nounits", "-lms", "20"],
                                          stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
             self.thread = threading.Thread(target=self._read, daemon=True)
             self.thread.start()
@@ -314,21 +316,34 @@ def run_ours(args, rank, local_rank, world):
     value = world * args.steps * bases_per_step / (ms_max * 1e-3)
 
     # ---- e2e: host buffers through the public C ABI call (H2D + kernels + D2H + RLE) -----------
-    fbuf = api.FindBuffers(nq)
     pinned_np = [p.numpy() for p in pinned_in]
-    for s in range(min(args.warmup, 2)):
-        api.find_csr(pinned_np[s % len(batches)], offsets, index, api.FindOpts(P, 0), fbuf)
+    n_thr = max(1, args.e2e_threads)
+    fbufs = [api.FindBuffers(nq) for _ in range(n_thr)]
+    for s in range(min(args.warmup, 2) * n_thr):
+        api.find_csr(pinned_np[s % len(batches)], offsets, index, api.FindOpts(P, 0), fbufs[s % n_thr])
     barrier()
+    e2e_steps = args.steps
+    n_rle_box = [0] * n_thr
+
+    def e2e_worker(t):
+        # every call copies its batch host->device, runs the kernels and copies the RLE records back
+        for s in range(t, e2e_steps, n_thr):
+            _, n_rle_box[t] = api.find_csr(pinned_np[(args.warmup + s) % len(batches)], offsets, index,
+                                           api.FindOpts(P, 0), fbufs[t])
+
+    threads = [threading.Thread(target=e2e_worker, args=(t,)) for t in range(n_thr)]
     w0 = time.perf_counter()
-    n_rle = 0
-    for s in range(args.steps):
-        _, n_rle = api.find_csr(pinned_np[(args.warmup + s) % len(batches)], offsets, index, api.FindOpts(P, 0), fbuf)
+    for th in threads:
+        th.start()
+    for th in threads:
+        th.join()
     torch.cuda.synchronize()
     e2e_s = time.perf_counter() - w0
+    n_rle = n_rle_box[0]
     te = torch.tensor([e2e_s], dtype=torch.float64, device="cuda")
     if dist is not None:
         dist.all_reduce(te, op=dist.ReduceOp.MAX)
-    e2e_value = world * args.steps * bases_per_step / float(te.item())
+    e2e_value = world * e2e_steps * bases_per_step / float(te.item())
 
     # ---- roofline inputs: event counters of one batch (profiling build of K1, outside the timing) --
     api.set_profile_counters(True)
@@ -390,7 +405,8 @@ def run_ours(args, rank, local_rank, world):
                         "h2d_bytes_per_step": bases_per_step + 8 * (nq + 1),
                         "d2h_bytes_per_step": 8 * (nq + 1) + 56 * n_rle,
                         "api": "kbo_find_batch: pinned host queries in, RLE records + per-query offsets out "
-                               "(matches and run lengths computed on the device; sub-batches pipelined on 4 streams)"},
+                               "(matches and run lengths computed on the device; sub-batches pipelined on 4 streams); "
+                               "%d steps issued by %d host threads" % (e2e_steps, n_thr)},
                 "gpu_launches": int(lt.item()), "roofline": roof}
         if cpu is not None:
             line["cpu_baseline"] = cpu

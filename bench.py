@@ -55,7 +55,7 @@ def parse_args():
     ap.add_argument("--ms-flags", type=int, default=0, help="K1 experiment switches")
     ap.add_argument("--streams", type=int, default=4,
                     help="CUDA streams the device-resident steps are issued round-robin on (independent batches)")
-    ap.add_argument("--e2e-threads", type=int, default=2,
+    ap.add_argument("--e2e-threads", type=int, default=3,
                     help="host threads issuing the end-to-end calls concurrently (kbo-cli style per-query threading)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--cpu-seconds", type=float, default=20.0, help="target CPU work (core-seconds) of the cpu_baseline sample")

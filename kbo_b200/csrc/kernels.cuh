@@ -156,6 +156,7 @@ __device__ __forceinline__ uint64_t lcs_lt_mask64(uint64_t w, uint64_t t_rep) {
 // issued once per group instead of once per iteration.  All position arithmetic is 32-bit.
 template <bool INTERVALS, bool COUNT>
 __global__ void __launch_bounds__(256, 8) ms_kernel(MsParams p) {
+    __shared__ __align__(16) uint8_t ms_stage[256 * 36];
     const uint64_t g = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
     unsigned long long cnt_att = 0, cnt_split = 0, cnt_con = 0, cnt_extra = 0, cnt_proc = 0, cnt_emit = 0;
     unsigned long long cnt_att_e = 0, cnt_split_e = 0, cnt_con_e = 0, cnt_extra_e = 0;
@@ -175,8 +176,11 @@ __global__ void __launch_bounds__(256, 8) ms_kernel(MsParams p) {
         const uint32_t bp_end = bp_emit + len;
         uint64_t qw = __ldg(qptr) >> (2 * bp);
         uint32_t iw = __ldg(iptr) >> bp;
-        uint32_t l = 0, r = n, d = 0, acc = 0;
+        uint32_t l = 0, r = n, d = 0;
         bool failed = false;
+        // emitted MS bytes are staged in shared memory (36-byte stride per lane: conflict-free word access) and
+        // flushed as two 16-byte stores per 32 positions; chunk starts are multiples of 32, so flushes are aligned
+        uint8_t* const stg = ms_stage + threadIdx.x * 36u;
         while (bp < bp_end) {
             // ---- probe phase ------------------------------------------------------------------
 #pragma unroll 1
@@ -220,11 +224,7 @@ __global__ void __launch_bounds__(256, 8) ms_kernel(MsParams p) {
                     if (COUNT) ++cnt_proc;
                     if (bp >= bp_emit) {
                         if (COUNT) ++cnt_emit;
-                        acc |= d << (8 * (bp & 3));
-                        if ((bp & 3) == 3 || bp + 1 == bp_end) {
-                            *reinterpret_cast<uint32_t*>(msw + (bp & ~3u)) = acc;
-                            acc = 0;
-                        }
+                        stg[bp & 31u] = (uint8_t)d;
                         if (INTERVALS) {
                             p.l_out[(wbase << 5) + bp] = l;
                             p.r_out[(wbase << 5) + bp] = r;
@@ -233,9 +233,17 @@ __global__ void __launch_bounds__(256, 8) ms_kernel(MsParams p) {
                     ++bp;
                     qw >>= 2;
                     iw >>= 1;
-                    if ((bp & 31) == 0 && bp < bp_end) {
-                        qw = __ldg(qptr + (bp >> 5));
-                        iw = __ldg(iptr + (bp >> 5));
+                    if ((bp & 31) == 0 || bp == bp_end) {
+                        if (bp > bp_emit) {  // flush the 32 (or last, partial) staged positions
+                            const uint32_t* w = reinterpret_cast<const uint32_t*>(stg);
+                            uint4* dst = reinterpret_cast<uint4*>(msw + ((bp - 1) & ~31u));
+                            dst[0] = make_uint4(w[0], w[1], w[2], w[3]);
+                            dst[1] = make_uint4(w[4], w[5], w[6], w[7]);
+                        }
+                        if (bp < bp_end) {
+                            qw = __ldg(qptr + (bp >> 5));
+                            iw = __ldg(iptr + (bp >> 5));
+                        }
                     }
                 }
             }

@@ -25,6 +25,9 @@ struct uint4 {
     uint32_t x, y, z, w;
 };
 
+inline uint4 make_uint4(uint32_t x, uint32_t y, uint32_t z, uint32_t w) { return uint4{x, y, z, w}; }
+#define __align__(n) __attribute__((aligned(n)))
+
 inline thread_local dim3 threadIdx, blockIdx, blockDim, gridDim;
 
 #define __global__

@@ -528,11 +528,6 @@ static int fetch_counters(kbo_index* ix, Workspace* ws) {
     return KBO_OK;
 }
 
-// K4 variant choice: many short queries -> one thread per query; few long queries -> one warp per query
-static inline bool rle_thread_per_query(uint64_t nq, uint64_t total_bases) {
-    return nq >= 4096 && total_bases / nq <= 8192;
-}
-
 // matches for a batch whose inputs are already on the device (ws->stream)
 static int matches_device(kbo_index* ix, Workspace* ws, const uint8_t* d_concat, const uint64_t* d_offsets,
                           uint64_t nq, const Geometry& g, uint32_t thr, uint8_t* d_out, uint64_t off0) {
@@ -943,15 +938,11 @@ static int matches_device_forked(kbo_index* ix, Workspace* ws, const uint8_t* d_
     }
     auto rle_count = [&](Workspace* w, uint64_t q0, uint64_t n) -> int {
         const unsigned threads = 128;
-        if (rle_thread_per_query(nq, total)) {
-            rle_thread_kernel<false><<<(unsigned)((n + threads - 1) / threads), threads, 0, w->stream>>>(
-                d_chars + host_offsets[q0], d_offsets + q0, n, gap, ws->tmp32.as<uint32_t>() + q0,
-                ws->out3.as<RleRecord>() + q0 * RLE_STAGE, nullptr, nullptr, 0);
-        } else {
-            rle_kernel<false><<<(unsigned)((n * 32 + threads - 1) / threads), threads, 0, w->stream>>>(
-                d_chars + host_offsets[q0], d_offsets + q0, n, gap, ws->tmp32.as<uint32_t>() + q0,
-                ws->out3.as<RleRecord>() + q0 * RLE_STAGE, nullptr, nullptr, 0);
-        }
+        const unsigned blocks = (unsigned)((n * 32 + threads - 1) / threads);
+        rle_kernel<false><<<blocks, threads, 0, w->stream>>>(d_chars + host_offsets[q0], d_offsets + q0, n, gap,
+                                                             ws->tmp32.as<uint32_t>() + q0,
+                                                             ws->out3.as<RleRecord>() + q0 * RLE_STAGE, nullptr,
+                                                             nullptr, 0);
         LAUNCHED();
         CUDA_TRY(cudaGetLastError());
         return KBO_OK;
@@ -1074,17 +1065,14 @@ int kbo_relative_to_ref(const uint8_t* ref_seq, const uint8_t* aln, uint64_t n, 
 
 // K4 launches: per-query segment counts -> exclusive scan -> records (all on ws->stream)
 static int run_rle_count_scan(Workspace* ws, const uint8_t* d_aln, const uint64_t* d_offsets, uint64_t nq,
-                              uint64_t total_bases, uint32_t max_gap_len, uint64_t* d_rle_offsets) {
+                              uint32_t max_gap_len, uint64_t* d_rle_offsets) {
     cudaStream_t st = ws->stream;
     CUDA_TRY(ws->tmp32.ensure(nq * 4, st));
     CUDA_TRY(ws->out3.ensure(nq * RLE_STAGE * sizeof(RleRecord), st));
     const unsigned threads = 128;
-    if (rle_thread_per_query(nq, total_bases))
-        rle_thread_kernel<false><<<(unsigned)((nq + threads - 1) / threads), threads, 0, st>>>(
-            d_aln, d_offsets, nq, max_gap_len, ws->tmp32.as<uint32_t>(), ws->out3.as<RleRecord>(), nullptr, nullptr, 0);
-    else
-        rle_kernel<false><<<(unsigned)((nq * 32 + threads - 1) / threads), threads, 0, st>>>(
-            d_aln, d_offsets, nq, max_gap_len, ws->tmp32.as<uint32_t>(), ws->out3.as<RleRecord>(), nullptr, nullptr, 0);
+    const unsigned blocks = (unsigned)((nq * 32 + threads - 1) / threads);
+    rle_kernel<false><<<blocks, threads, 0, st>>>(d_aln, d_offsets, nq, max_gap_len, ws->tmp32.as<uint32_t>(),
+                                                  ws->out3.as<RleRecord>(), nullptr, nullptr, 0);
     LAUNCHED();
     rle_scan_kernel<<<1, 1024, 0, st>>>(ws->tmp32.as<uint32_t>(), nq, d_rle_offsets);
     LAUNCHED();
@@ -1092,17 +1080,11 @@ static int run_rle_count_scan(Workspace* ws, const uint8_t* d_aln, const uint64_
     return KBO_OK;
 }
 static int run_rle_write(Workspace* ws, const uint8_t* d_aln, const uint64_t* d_offsets, uint64_t nq,
-                         uint64_t total_bases, uint32_t max_gap_len, const uint64_t* d_rle_offsets, RleRecord* d_out,
-                         uint64_t cap) {
+                         uint32_t max_gap_len, const uint64_t* d_rle_offsets, RleRecord* d_out, uint64_t cap) {
     const unsigned threads = 128;
-    if (rle_thread_per_query(nq, total_bases))
-        rle_thread_kernel<true><<<(unsigned)((nq + threads - 1) / threads), threads, 0, ws->stream>>>(
-            d_aln, d_offsets, nq, max_gap_len, ws->tmp32.as<uint32_t>(), ws->out3.as<RleRecord>(), d_rle_offsets, d_out,
-            cap);
-    else
-        rle_kernel<true><<<(unsigned)((nq * 32 + threads - 1) / threads), threads, 0, ws->stream>>>(
-            d_aln, d_offsets, nq, max_gap_len, ws->tmp32.as<uint32_t>(), ws->out3.as<RleRecord>(), d_rle_offsets, d_out,
-            cap);
+    const unsigned blocks = (unsigned)((nq * 32 + threads - 1) / threads);
+    rle_kernel<true><<<blocks, threads, 0, ws->stream>>>(d_aln, d_offsets, nq, max_gap_len, ws->tmp32.as<uint32_t>(),
+                                                         ws->out3.as<RleRecord>(), d_rle_offsets, d_out, cap);
     LAUNCHED();
     CUDA_TRY(cudaGetLastError());
     return KBO_OK;
@@ -1167,7 +1149,7 @@ int kbo_find_batch(const kbo_index* cix, const uint8_t* concat, const uint64_t* 
             int rc2 = matches_device(ix, ws, ws->ascii.as<uint8_t>(), ws->offsets.as<uint64_t>(), nq, g, thr,
                                      ws->out.as<uint8_t>(), 0);
             if (rc2) return rc2;
-            rc2 = run_rle_count_scan(ws, ws->out.as<uint8_t>(), ws->offsets.as<uint64_t>(), nq, bytes, gap,
+            rc2 = run_rle_count_scan(ws, ws->out.as<uint8_t>(), ws->offsets.as<uint64_t>(), nq, gap,
                                      ws->tmp64.as<uint64_t>());
             if (rc2) return rc2;
             CUDA_TRY(cudaMemcpyAsync(ws->h_roff.p, ws->tmp64.p, (nq + 1) * 8, cudaMemcpyDeviceToHost, st));
@@ -1196,9 +1178,8 @@ int kbo_find_batch(const kbo_index* cix, const uint8_t* concat, const uint64_t* 
                 if (!rle_out) return fail(KBO_ERR_BAD_ARGUMENT, "rle_out is null");
                 CUDA_TRY(ws->out2.ensure(n_rle * sizeof(RleRecord), st));
                 CUDA_TRY(ws->h_rle.ensure(n_rle * sizeof(RleRecord)));
-                int rc2 = run_rle_write(ws, ws->out.as<uint8_t>(), ws->offsets.as<uint64_t>(), nq,
-                                        offsets[q1] - offsets[q0], gap, ws->tmp64.as<uint64_t>(),
-                                        ws->out2.as<RleRecord>(), n_rle);
+                int rc2 = run_rle_write(ws, ws->out.as<uint8_t>(), ws->offsets.as<uint64_t>(), nq, gap,
+                                        ws->tmp64.as<uint64_t>(), ws->out2.as<RleRecord>(), n_rle);
                 if (rc2) return rc2;
                 CUDA_TRY(cudaMemcpyAsync(ws->h_rle.p, ws->out2.p, n_rle * sizeof(RleRecord), cudaMemcpyDeviceToHost, st));
             }
@@ -1249,7 +1230,7 @@ int kbo_find_batch_device(const kbo_index* cix, const uint8_t* d_concat, const u
     rle_scan_kernel<<<1, 1024, 0, ws->stream>>>(ws->tmp32.as<uint32_t>(), n_queries, d_rle_offsets);
     LAUNCHED();
     CUDA_TRY(cudaGetLastError());
-    return run_rle_write(ws, ws->out.as<uint8_t>(), d_offsets, n_queries, total, gap, d_rle_offsets,
+    return run_rle_write(ws, ws->out.as<uint8_t>(), d_offsets, n_queries, gap, d_rle_offsets,
                          reinterpret_cast<RleRecord*>(d_rle_out), rle_cap);
 }
 

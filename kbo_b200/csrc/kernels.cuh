@@ -736,74 +736,6 @@ __global__ void __launch_bounds__(128) rle_kernel(const uint8_t* __restrict__ al
     if (!WRITE && lane == 0) counts[q] = st.n_seg;
 }
 
-// Thread-per-query form of the same state machine, for batches of many short queries: the work is then
-// parallel across lanes instead of being repeated by every lane of a warp (13x fewer warp instructions for
-// 10,000 x 1 kbp).  Same staging contract as rle_kernel.
-template <bool WRITE>
-__global__ void __launch_bounds__(128) rle_thread_kernel(const uint8_t* __restrict__ aln,
-                                                         const uint64_t* __restrict__ offsets, uint64_t nq,
-                                                         uint32_t max_gap_len, uint32_t* __restrict__ counts,
-                                                         RleRecord* __restrict__ stage,
-                                                         const uint64_t* __restrict__ rle_offsets,
-                                                         RleRecord* __restrict__ out, uint64_t cap) {
-    const uint64_t q = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
-    if (q >= nq) return;
-    RleRecord* dst = stage + q * RLE_STAGE;
-    uint64_t slot0 = 0;
-    if (WRITE) {
-        slot0 = rle_offsets[q];
-        const uint32_t cnt = counts[q];
-        if (cnt <= RLE_STAGE) {
-            for (uint32_t i = 0; i < cnt; ++i)
-                if (slot0 + i < cap) out[slot0 + i] = dst[i];
-            return;
-        }
-        dst = out;
-    }
-    const uint8_t* a = aln + (offsets[q] - offsets[0]);
-    const uint64_t len = offsets[q + 1] - offsets[q];
-    uint32_t n_seg = 0, nm = 0, nx = 0, nj = 0, gb = 0, go = 0, pend = 0;
-    uint64_t start = 0, end = 0;
-    bool in_seg = false;
-    uint8_t prev = 0;
-    auto emit = [&]() {
-        const uint64_t slot = slot0 + n_seg;
-        if (WRITE ? (slot < cap) : (n_seg < RLE_STAGE)) {
-            RleRecord rec = {start, end, nm, nx, nj, gb, go};
-            dst[slot] = rec;
-        }
-        ++n_seg;
-    };
-    for (uint64_t i = 0; i < len; ++i) {
-        const uint8_t ch = a[i];
-        if (ch == '-') {
-            if (in_seg && ++pend > max_gap_len) {  // the gap outgrew max_gap_len: close without it
-                emit();
-                in_seg = false;
-                pend = 0;
-            }
-        } else {
-            if (!in_seg) {
-                in_seg = true;
-                start = i;
-                nm = nx = nj = gb = go = 0;
-            } else if (pend) {
-                gb += pend;
-                go += 1;
-            }
-            pend = 0;
-            const bool is_match = ch == 'M' || ch == 'R' || ch == 'I';
-            nm += is_match;
-            nx += !is_match;
-            nj += (ch == 'R' && prev == 'R');
-            end = i + 1;
-        }
-        prev = ch;
-    }
-    if (in_seg) emit();  // a trailing gap run is dropped
-    if (!WRITE) counts[q] = n_seg;
-}
-
 // exclusive scan of the per-query segment counts -> rle_offsets[0..nq]; one block
 __global__ void __launch_bounds__(1024) rle_scan_kernel(const uint32_t* __restrict__ counts, uint64_t nq,
                                                         uint64_t* __restrict__ rle_offsets) {

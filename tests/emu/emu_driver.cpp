@@ -220,21 +220,7 @@ void emu_derandomize_general(const uint64_t* ms, uint64_t n, uint32_t k, uint32_
 
 // K4: run_lengths_gapped on plain translations, CSR batch; returns the number of records (out has `cap` slots of 7 u64)
 uint64_t emu_rle_batch(const uint8_t* aln, const uint64_t* offsets, uint64_t nq, uint32_t max_gap_len, uint64_t* out7,
-                       uint64_t cap, uint64_t* rle_offsets, int per_thread) {
-    if (per_thread) {
-        std::vector<uint32_t> counts(nq);
-        std::vector<RleRecord> stage(nq * RLE_STAGE);
-        const unsigned threads = 128, blocks = (unsigned)((nq + threads - 1) / threads);
-        emu_launch_seq(blocks, threads, [&]() {
-            rle_thread_kernel<false>(aln, offsets, nq, max_gap_len, counts.data(), stage.data(), nullptr, nullptr, 0);
-        });
-        emu_launch_par(1, 1024, [&]() { rle_scan_kernel(counts.data(), nq, rle_offsets); });
-        emu_launch_seq(blocks, threads, [&]() {
-            rle_thread_kernel<true>(aln, offsets, nq, max_gap_len, counts.data(), stage.data(), rle_offsets,
-                                    (RleRecord*)out7, cap);
-        });
-        return rle_offsets[nq];
-    }
+                       uint64_t cap, uint64_t* rle_offsets) {
     std::vector<uint32_t> counts(nq);
     std::vector<RleRecord> stage(nq * RLE_STAGE);
     const unsigned threads = 128, blocks = (unsigned)((nq * 32 + threads - 1) / threads);

@@ -60,7 +60,7 @@ def lib():
         L.emu_map.argtypes = [C.c_void_p, u8p, C.c_uint64, C.c_uint32, C.c_uint32, C.c_double, C.c_int, C.c_int, C.c_int,
                               C.c_uint32, C.c_int, u8p]
         L.emu_rle_batch.restype = C.c_uint64
-        L.emu_rle_batch.argtypes = [u8p, u64p, C.c_uint64, C.c_uint32, u64p, C.c_uint64, u64p, C.c_int]
+        L.emu_rle_batch.argtypes = [u8p, u64p, C.c_uint64, C.c_uint32, u64p, C.c_uint64, u64p]
         _lib = L
     return _lib
 
@@ -201,14 +201,14 @@ def translate_i64(d, k, thr):
     return out.tobytes()
 
 
-def rle_batch(alns, max_gap_len, per_thread=False):
+def rle_batch(alns, max_gap_len):
     """K4 on a list of plain translations; returns a list (per query) of 7-tuples."""
     concat, offsets = csr(alns)
     cap = len(concat) + 1
     out = np.zeros(7 * cap, dtype=np.uint64)
     roff = np.zeros(len(alns) + 1, dtype=np.uint64)
     n = lib().emu_rle_batch(_p(concat, C.c_uint8), _p(offsets, C.c_uint64), len(alns), max_gap_len,
-                            _p(out, C.c_uint64), cap, _p(roff, C.c_uint64), int(per_thread))
+                            _p(out, C.c_uint64), cap, _p(roff, C.c_uint64))
     assert n == roff[-1]
     return [[tuple(int(x) for x in out[7 * j:7 * j + 7]) for j in range(int(roff[i]), int(roff[i + 1]))]
             for i in range(len(alns))]

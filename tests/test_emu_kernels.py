@@ -235,10 +235,9 @@ def test_rle_kernel_random_plain_alignments():
                 if a[0] == ord("R"):
                     a[0] = ord("M")  # format.rs:176 panics on a leading 'R'
                 alns.append(a.tobytes())
-            for per_thread in (False, True):
-                got = E.rle_batch(alns, gap, per_thread)
-                for g_, a in zip(got, alns):
-                    assert g_ == O.run_lengths_gapped(a, gap), (gap, per_thread, a[:80])
+            got = E.rle_batch(alns, gap)
+            for g_, a in zip(got, alns):
+                assert g_ == O.run_lengths_gapped(a, gap), (gap, a[:80])
 
 
 def test_ms_independent_of_probe_iters_and_flags():

@@ -279,6 +279,24 @@ def test_config2_full_size_bit_exact():
     assert (di[1:] <= di[:-1] + 1).all() and di.max() == 31
 
 
+def test_config1_full_size_map_bit_exact():
+    """BASELINE.json configs[0] at FULL size: kbo::map of a 4.6 Mbp reference against the index of a mutated
+    4.6 Mbp assembly (1 % SNPs + short indels), k = 31, MapOpts::default(): output identical to the oracle."""
+    ref = synth.random_seq(4_600_000, synth.SEED_C1_REF)
+    asm = synth.mutate(ref, synth.SEED_C1_ASM)
+    o = O.OracleIndex([asm.tobytes()], k=31)
+    ix = api.build([asm], api.BuildOpts(k=31, build_select=True))
+    assert (ix.n_sets, ix.n_kmers) == (o.n_sets, o.n_kmers)
+    r = ref.tobytes()
+    want = o.map(r, build_k=31)
+    got = api.map(r, ix, api.MapOpts())
+    assert got == want
+    frac_gap = got.count(b"-") / len(got)
+    assert 0.005 < frac_gap < 0.2
+    # the unformatted translation as well (fill_gaps on, variants on)
+    assert api.map(r, ix, api.MapOpts(format=False)) == o.map(r, format=False, build_k=31)
+
+
 def test_hbm_resident_index_regime():
     """An index well beyond L2 (120 Mbp -> 240 MB on the device): chunking-independence and oracle parity on a
     sample of queries (the oracle index of this size takes too long to build in a unit test, so parity is checked

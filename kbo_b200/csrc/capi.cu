@@ -230,12 +230,27 @@ static int upload_index(kbo_index* ix) {
 // ---------------------------------------------------------------------------
 // index construction on the device (index_build.cuh), 2 <= k <= 32
 // ---------------------------------------------------------------------------
+// Scratch of one index construction: stream-ordered allocations from the device's default memory pool
+// (kept warm between builds), so that the ~25 temporaries cost microseconds instead of a cudaMalloc /
+// cudaFree (device synchronisation) each.
 struct TmpBufs {
     std::vector<void*> ptrs;
-    ~TmpBufs() { for (void* p : ptrs) cudaFree(p); }
+    ~TmpBufs() { for (void* p : ptrs) cudaFreeAsync(p, 0); }
+    static void warm_pool(int device) {
+        static std::mutex mu;
+        static std::vector<int> done;
+        std::lock_guard<std::mutex> g(mu);
+        if (std::find(done.begin(), done.end(), device) != done.end()) return;
+        cudaMemPool_t pool;
+        if (cudaDeviceGetDefaultMemPool(&pool, device) == cudaSuccess) {
+            uint64_t keep = ~0ull;
+            cudaMemPoolSetAttribute(pool, cudaMemPoolAttrReleaseThreshold, &keep);
+        }
+        done.push_back(device);
+    }
     template <typename T> cudaError_t alloc(T** out, size_t count) {
         void* p = nullptr;
-        cudaError_t e = cudaMalloc(&p, (count ? count : 1) * sizeof(T));
+        cudaError_t e = cudaMallocAsync(&p, (count ? count : 1) * sizeof(T), 0);
         if (e == cudaSuccess) { ptrs.push_back(p); *out = (T*)p; }
         return e;
     }
@@ -247,6 +262,7 @@ static int build_index_gpu(kbo_index* ix, const uint8_t* const* seqs, const uint
     std::vector<uint64_t> offsets(n_seqs + 1, 0);
     for (uint64_t i = 0; i < n_seqs; ++i) { total += lens[i]; offsets[i + 1] = total; }
     const Geometry g = kbo_b200::make_geometry(total, n_seqs, 64);
+    TmpBufs::warm_pool(ix->device);
     TmpBufs tmp;
     uint8_t *d_ascii, *d_flags, *d_nopred, *d_Dlen = nullptr, *d_Plen;
     uint64_t *d_off, *d_pack, *d_keys, *d_keys_rc = nullptr, *d_sel, *d_sorted, *d_R, *d_src, *d_Dkey = nullptr, *d_Pkey, *d_count;
@@ -287,7 +303,7 @@ static int build_index_gpu(kbo_index* ix, const uint8_t* const* seqs, const uint
     cub::DeviceSelect::Flagged(nullptr, need, d_keys, d_flags, d_sel, d_count, (int64_t)Lp); tb = std::max(tb, need);
     cub::DeviceRadixSort::SortKeys(nullptr, need, d_sel, d_sorted, (int64_t)n_cand, 64 - 2 * (int)k, 64); tb = std::max(tb, need);
     cub::DeviceSelect::Unique(nullptr, need, d_sorted, d_R, d_count, (int64_t)n_cand); tb = std::max(tb, need);
-    CUDA_TRY(cudaMalloc(&d_tmp, tb ? tb : 1));
+    CUDA_TRY(cudaMallocAsync(&d_tmp, tb ? tb : 1, 0));
     tmp.ptrs.push_back(d_tmp);
     uint64_t h_count = 0, n_valid = 0;
     need = tb;
@@ -364,7 +380,7 @@ static int build_index_gpu(kbo_index* ix, const uint8_t* const* seqs, const uint
     cub::DeviceScan::ExclusiveSum(nullptr, scan_need, d_pc, d_prefix, (int64_t)(4 * stride));
     void* d_scan_tmp = d_tmp;
     if (scan_need > tb) {
-        CUDA_TRY(cudaMalloc(&d_scan_tmp, scan_need));
+        CUDA_TRY(cudaMallocAsync(&d_scan_tmp, scan_need, 0));
         tmp.ptrs.push_back(d_scan_tmp);
     }
     CUDA_TRY(cub::DeviceScan::ExclusiveSum(d_scan_tmp, scan_need, d_pc, d_prefix, (int64_t)(4 * stride)));

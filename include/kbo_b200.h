@@ -63,7 +63,8 @@ typedef struct kbo_build_opts {
     int32_t add_revcomp;     /* default 0 */
     uint32_t num_threads;    /* default 1 (host-side sort threads) */
     uint32_t prefix_precalc; /* default 8; ignored (no prefix table is needed on the device) */
-    int32_t build_select;    /* default 0; access_kmer is always available here */
+    int32_t build_select;    /* default 0; != 0 keeps the sorted nodes on the host for O(1) access_kmer (map/call);
+                              * without it access_kmer walks the index (slower, same result) */
     uint32_t mem_gb;         /* ignored */
     int32_t dedup_batches;   /* ignored */
     const char* temp_dir;    /* ignored (always in memory) */

@@ -257,7 +257,7 @@ struct TmpBufs {
 };
 
 static int build_index_gpu(kbo_index* ix, const uint8_t* const* seqs, const uint64_t* lens, uint64_t n_seqs, uint32_t k,
-                           bool revcomp) {
+                           bool revcomp, bool keep_nodes) {
     uint64_t total = 0;
     std::vector<uint64_t> offsets(n_seqs + 1, 0);
     for (uint64_t i = 0; i < n_seqs; ++i) { total += lens[i]; offsets[i + 1] = total; }
@@ -407,6 +407,12 @@ static int build_index_gpu(kbo_index* ix, const uint8_t* const* seqs, const uint
         }
     }
     h.finalize();
+    if (keep_nodes) {  // "select support": the nodes themselves, for O(1) access_kmer on the host
+        h.node_hi.resize((size_t)n);
+        h.node_len.resize((size_t)n);
+        CUDA_TRY(cudaMemcpy(h.node_hi.data(), d_Pkey, n * 8, cudaMemcpyDeviceToHost));
+        CUDA_TRY(cudaMemcpy(h.node_len.data(), d_Plen, n, cudaMemcpyDeviceToHost));
+    }
     ix->rank_stride = stride;
     ix->device_bytes = 4 * stride * 8 + lcs_bytes;
     ix->view.rank = ix->d_rank;
@@ -676,13 +682,13 @@ int kbo_index_build(const uint8_t* const* seqs, const uint64_t* lens, uint64_t n
         ix->device = device;
         DeviceGuard dg(device);
         if (!dg.ok) { delete ix; return fail(KBO_ERR_CUDA, "cudaSetDevice failed"); }
-        int rc = build_index_gpu(ix, seqs, lens, n_seqs, o.k, o.add_revcomp != 0);
+        int rc = build_index_gpu(ix, seqs, lens, n_seqs, o.k, o.add_revcomp != 0, o.build_select != 0);
         if (rc) { kbo_index_free(ix); return rc; }
         *out = ix;
         return KBO_OK;
     }
     std::string err = build_host_index(seqs, lens, n_seqs, o.k, o.add_revcomp != 0, o.num_threads ? o.num_threads : 1,
-                                       &ix->host);
+                                       &ix->host, o.build_select != 0);
     if (!err.empty()) { delete ix; return fail(KBO_ERR_INDEX_TOO_LARGE, err); }
     return finish_index(ix, device, out);
 }

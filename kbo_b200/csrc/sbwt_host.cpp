@@ -80,7 +80,7 @@ struct PNode {
 
 template <typename K>
 std::string build_typed(const uint8_t* const* seqs, const uint64_t* lens, uint64_t n_seqs, uint32_t k,
-                        bool add_revcomp, uint32_t num_threads, HostIndex* out) {
+                        bool add_revcomp, uint32_t num_threads, bool keep_nodes, HostIndex* out) {
     constexpr int BITS = KeyTraits<K>::BITS;
     const int top = BITS - 2;                 // bit offset of the last character
     const int first_shift = BITS - 2 * (int)k;  // bit offset of the first character
@@ -190,6 +190,20 @@ std::string build_typed(const uint8_t* const* seqs, const uint64_t* lens, uint64
     }
     for (int c = 0; c < 4; ++c)
         if (cur[c] != sec[c + 1]) return "internal error: label merge did not consume every node";
+    if (keep_nodes) {
+        out->node_hi.resize((size_t)n);
+        out->node_len.resize((size_t)n);
+        if (BITS == 128) out->node_lo.resize((size_t)n);
+        for (uint64_t i = 0; i < n; ++i) {
+            if (BITS == 128) {
+                out->node_hi[i] = (uint64_t)((u128)P[i].key >> 64);
+                out->node_lo[i] = (uint64_t)P[i].key;
+            } else {
+                out->node_hi[i] = (uint64_t)P[i].key;
+            }
+            out->node_len[i] = P[i].len;
+        }
+    }
     out->finalize();
     return std::string();
 }
@@ -254,6 +268,20 @@ bool HostIndex::search(const uint8_t* pat, uint64_t len, uint64_t* l, uint64_t* 
 
 void HostIndex::access_kmer(uint64_t colex, uint8_t* out_k) const {
     static const char letters[4] = {'A', 'C', 'G', 'T'};
+    if (!node_len.empty()) {  // decode the stored node
+        const uint64_t hi = node_hi[colex], lo = node_lo.empty() ? 0 : node_lo[colex];
+        const uint32_t len = node_len[colex];
+        for (uint32_t t = 0; t < k; ++t) {
+            uint8_t ch = '$';
+            if (t < len) {
+                const uint32_t code = t < 32 ? (uint32_t)(hi >> (62 - 2 * t)) & 3u : (uint32_t)(lo >> (62 - 2 * (t - 32))) & 3u;
+                ch = (uint8_t)letters[code];
+            }
+            out_k[k - 1 - t] = ch;
+        }
+        return;
+    }
+    // no stored nodes: walk the incoming edges back k times
     uint64_t node = colex;
     for (uint32_t t = 0; t < k; ++t) {
         uint8_t ch = '$';
@@ -268,9 +296,9 @@ void HostIndex::access_kmer(uint64_t colex, uint8_t* out_k) const {
 }
 
 std::string build_host_index(const uint8_t* const* seqs, const uint64_t* lens, uint64_t n_seqs, uint32_t k,
-                             bool add_revcomp, uint32_t num_threads, HostIndex* out) {
-    if (k <= 32) return build_typed<uint64_t>(seqs, lens, n_seqs, k, add_revcomp, num_threads, out);
-    return build_typed<u128>(seqs, lens, n_seqs, k, add_revcomp, num_threads, out);
+                             bool add_revcomp, uint32_t num_threads, HostIndex* out, bool keep_nodes) {
+    if (k <= 32) return build_typed<uint64_t>(seqs, lens, n_seqs, k, add_revcomp, num_threads, keep_nodes, out);
+    return build_typed<u128>(seqs, lens, n_seqs, k, add_revcomp, num_threads, keep_nodes, out);
 }
 
 }  // namespace kbo_b200

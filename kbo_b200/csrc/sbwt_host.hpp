@@ -22,6 +22,10 @@ struct HostIndex {
     std::vector<uint64_t> rows[4];      // ceil(n_sets/64)+1 words each
     std::vector<uint32_t> row_cum[4];   // set bits before each 64-bit word (for host rank/select)
     std::vector<uint8_t> lcs;           // n_sets bytes
+    // optional "select support" (BuildOpts.build_select): the colex-sorted nodes themselves, letters packed
+    // 2 bits each with the LAST base in the top bits of (hi, lo); node_len = number of non-'$' bases
+    std::vector<uint64_t> node_hi, node_lo;
+    std::vector<uint8_t> node_len;
 
     uint64_t rank(int c, uint64_t p) const;                  // set bits of row c in [0,p)
     uint64_t select(int c, uint64_t j) const;                // position of the j-th (0-based) set bit of row c
@@ -32,7 +36,8 @@ struct HostIndex {
 };
 
 // Returns empty string on success, else an error message.
+// keep_nodes: also keep the sorted nodes for O(1) access_kmer (BuildOpts.build_select).
 std::string build_host_index(const uint8_t* const* seqs, const uint64_t* lens, uint64_t n_seqs, uint32_t k,
-                             bool add_revcomp, uint32_t num_threads, HostIndex* out);
+                             bool add_revcomp, uint32_t num_threads, HostIndex* out, bool keep_nodes = true);
 
 }  // namespace kbo_b200

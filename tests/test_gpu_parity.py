@@ -144,6 +144,21 @@ def test_gpu_and_host_builders_agree_with_oracle(k, revcomp):
     assert all(np.array_equal(a, b_) for a, b_ in zip(parts[0], parts[1]))
 
 
+@pytest.mark.parametrize("k", [9, 31, 40])
+def test_access_kmer_with_and_without_stored_nodes(k):
+    """build_select keeps the sorted nodes on the host (O(1) access_kmer); without it access_kmer walks the
+    incoming edges back.  Both must decode every node like the oracle, dummies included."""
+    seqs = [rand_seq(3000, 5), b"ACGTTGCA" * 10, rand_seq(90, 6)]
+    o = O.OracleIndex(seqs, k=k)
+    fast = api.build(seqs, api.BuildOpts(k=k, build_select=True))
+    slow = api.build(seqs, api.BuildOpts(k=k, build_select=False))
+    for i in list(range(0, o.n_sets, 7)) + [o.n_sets - 1]:
+        want = o.access_kmer(i)
+        assert fast.access_kmer(i) == want and slow.access_kmer(i) == want, i
+    with pytest.raises(api.KboPanic):
+        fast.access_kmer(o.n_sets)
+
+
 def test_index_build_degenerate_inputs():
     for seqs, k in (([b"AC"], 31), ([b"NNNN", b""], 5), ([b"ACGTACGTAC"], 10)):
         o = O.OracleIndex(seqs, k=k)

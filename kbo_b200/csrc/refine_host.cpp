@@ -77,27 +77,43 @@ uint64_t unique_context(const MsArrays& ms, const HostIndex& ix, uint64_t range_
 }
 
 // prepend bases while exactly one base extends the k-mer's first k-1 characters to a unique node
-// (gap_filling.rs:205-232)
+// (gap_filling.rs:205-232).  The reference searches the four k-length patterns c + S (S = those k-1
+// characters); a k-length pattern matches at most one node, and the nodes ending with S are exactly the
+// interval of S, so ONE search of S answers all four: the candidates are the full (non-dummy) nodes of that
+// interval and their first characters.
 Bytes extend_left(const Bytes& start, const HostIndex& ix, uint64_t max_extension) {
     require(!start.empty(), "gap_filling.rs:210");
-    static const uint8_t letters[4] = {'A', 'C', 'G', 'T'};
     Bytes kmer = start;
+    Bytes node(ix.k);
     for (uint64_t ext = 0; ext < max_extension; ++ext) {
+        const uint64_t slen = kmer.size() - ext - 1;  // = k - 1 when `start` is a k-mer
         int hits = 0;
         uint8_t hit_base = 0;
-        uint64_t hit_width = 0;
-        Bytes probe(kmer.size() - ext);  // c + kmer[0 .. len-(ext+1))
-        std::copy(kmer.begin(), kmer.begin() + (probe.size() - 1), probe.begin() + 1);
-        for (uint8_t c : letters) {
-            probe[0] = c;
+        if (slen + 1 == ix.k) {
             uint64_t l = 0, r = 0;
-            if (ix.search(probe.data(), probe.size(), &l, &r)) {
-                ++hits;
-                hit_base = c;
-                hit_width = r - l;
+            if (ix.search(kmer.data(), slen, &l, &r)) {
+                for (uint64_t v = l; v < r; ++v) {
+                    ix.access_kmer(v, node.data());
+                    if (node[0] != '$') { ++hits; hit_base = node[0]; }
+                }
             }
+        } else {  // general pattern length: the literal four searches
+            static const uint8_t letters[4] = {'A', 'C', 'G', 'T'};
+            uint64_t hit_width = 0;
+            Bytes probe(slen + 1);
+            std::copy(kmer.begin(), kmer.begin() + slen, probe.begin() + 1);
+            for (uint8_t c : letters) {
+                probe[0] = c;
+                uint64_t l = 0, r = 0;
+                if (ix.search(probe.data(), probe.size(), &l, &r)) {
+                    ++hits;
+                    hit_base = c;
+                    hit_width = r - l;
+                }
+            }
+            if (hit_width != 1) hits = 0;
         }
-        if (hits != 1 || hit_width != 1) break;
+        if (hits != 1) break;
         kmer.insert(kmer.begin(), hit_base);
     }
     return kmer;

@@ -61,11 +61,38 @@ enum { CNT_ATTEMPTS = 0, CNT_SPLIT = 1, CNT_CONTRACT = 2, CNT_EXTRA_LCS = 3, CNT
        CNT_ATT_EMIT = 6, CNT_SPLIT_EMIT = 7, CNT_CON_EMIT = 8, CNT_EXTRA_EMIT = 9, CNT_N = 10 };
 
 // ---------------------------------------------------------------------------
-// K0: pack.  One thread per 32 padded positions.
+// K0: pack.  One thread per 32 padded positions.  The bases of a word are read
+// eight at a time (aligned 8-byte loads, shifted together when the source is
+// misaligned) and converted four per 32-bit register with byte-parallel
+// arithmetic; a word that holds separators is cut into its runs of bases.
 // ---------------------------------------------------------------------------
 __device__ __forceinline__ uint64_t sep_pos(const uint64_t* offsets, uint64_t q) {
     // padded position of the separator that follows query q
     return offsets[q + 1] - offsets[0] + q;
+}
+
+// Four ASCII bytes -> 8 bits of 2-bit codes (base i at bits [2i,2i+2), 0 where the byte is not ACGT)
+// and 4 bits of "not ACGT" flags.
+__device__ __forceinline__ void swar_pack4(uint32_t v, uint32_t& code8, uint32_t& inv4) {
+    const uint32_t x = (v >> 1) & 0x03030303u;           // A0 C1 T2 G3
+    const uint32_t x1 = (x >> 1) & 0x01010101u;
+    uint32_t code = x ^ x1;                              // A0 C1 G2 T3
+    const uint32_t is_t = x1 & ~x;                       // 1 in the bytes with x == 2
+    const uint32_t expect = is_t * 0x0fu + 0x41414141u;  // the byte without bits 1,2: 0x41 (A C G) or 0x50 (T)
+    const uint32_t diff = (v & 0xf9f9f9f9u) ^ expect;    // non-zero byte <=> not ACGT
+    const uint32_t nz = (((diff & 0x7f7f7f7fu) + 0x7f7f7f7fu) | diff) & 0x80808080u;
+    code &= ~((nz >> 6) | (nz >> 7));
+    code8 = (code * 0x01041040u) >> 24;                  // bits 8i+{0,1} -> 24+2i+{0,1}, no two terms collide
+    inv4 = (nz * 0x00204081u) >> 28;                     // bits 8i+7 -> 28+i
+}
+
+// n (1..8) bytes starting at src, little endian; touches only the aligned 8-byte words that hold them
+__device__ __forceinline__ uint64_t load_bytes8(const uint8_t* src, uint32_t n) {
+    const uintptr_t a = reinterpret_cast<uintptr_t>(src) & ~(uintptr_t)7;
+    const uint32_t mis = (uint32_t)(reinterpret_cast<uintptr_t>(src) & 7u);
+    uint64_t v = *reinterpret_cast<const uint64_t*>(a) >> (8 * mis);
+    if (mis + n > 8) v |= *reinterpret_cast<const uint64_t*>(a + 8) << (64 - 8 * mis);
+    return v;
 }
 
 __global__ void pack_queries_kernel(const uint8_t* __restrict__ ascii, const uint64_t* __restrict__ offsets,
@@ -84,26 +111,38 @@ __global__ void pack_queries_kernel(const uint8_t* __restrict__ ascii, const uin
     uint64_t q = lo;
     wq[w] = (uint32_t)q;
     const uint64_t off0 = offsets[0];
-    uint64_t next_sep = q < nq ? sep_pos(offsets, q) : ~0ull;
     uint64_t pk = 0;
     uint32_t iv = 0, sp = 0;
-    for (int j = 0; j < 32; ++j) {
-        uint64_t pp = pp0 + j;
-        if (q >= nq) {
-            iv |= 1u << j;
-            sp |= 1u << j;
-        } else if (pp == next_sep) {
+    uint32_t j = 0;
+    while (j < 32) {
+        if (q >= nq) {  // past the last separator: the tail is all separator
+            iv |= ~0u << j;
+            sp |= ~0u << j;
+            break;
+        }
+        const uint64_t pp = pp0 + j;
+        const uint64_t next_sep = sep_pos(offsets, q);
+        if (pp == next_sep) {
             iv |= 1u << j;
             sp |= 1u << j;
             ++q;
-            next_sep = q < nq ? sep_pos(offsets, q) : ~0ull;
-        } else {
-            uint32_t ch = ascii[off0 + pp - q];
-            uint32_t x = (ch >> 1) & 3;      // A0 C1 T2 G3
-            uint32_t code = x ^ (x >> 1);    // A0 C1 G2 T3
-            bool ok = (ch == 'A') | (ch == 'C') | (ch == 'G') | (ch == 'T');
-            if (ok) pk |= (uint64_t)code << (2 * j); else iv |= 1u << j;
+            ++j;
+            continue;
         }
+        uint64_t n64 = next_sep - pp;
+        uint32_t n = 32 - j;
+        if (n64 < n) n = (uint32_t)n64;
+        if (n > 8) n = 8;
+        const uint64_t v = load_bytes8(ascii + off0 + pp - q, n);
+        uint32_t c0, c1, i0, i1;
+        swar_pack4((uint32_t)v, c0, i0);
+        swar_pack4((uint32_t)(v >> 32), c1, i1);
+        const uint32_t keep = (1u << n) - 1u;  // drop what was read past the run
+        const uint32_t code16 = (c0 | (c1 << 8)) & ((1u << (2 * n)) - 1u);
+        const uint32_t inv8 = (i0 | (i1 << 4)) & keep;
+        pk |= (uint64_t)code16 << (2 * j);
+        iv |= inv8 << j;
+        j += n;
     }
     pack[w] = pk;
     inv[w] = iv;

@@ -168,6 +168,19 @@ void emu_query_sbwt_batch(void* h, const uint8_t* concat, const uint64_t* offset
     if (r_out) unpad<uint32_t>(s.r.data(), s.qv, r_out + offsets[0]);
 }
 
+// K0 alone: the packed form of a CSR batch (n_words = make_geometry(total, nq).n_words entries per array)
+uint64_t emu_pack(const uint8_t* ascii, const uint64_t* offsets, uint64_t nq, uint64_t* pack, uint32_t* inv,
+                  uint32_t* sep, uint32_t* wq) {
+    const Geometry g = make_geometry(offsets[nq] - offsets[0], nq, 0);
+    if (!pack) return g.n_words;
+    QueryView qv;
+    qv.pack = pack; qv.inv = inv; qv.sep = sep; qv.wq = wq;
+    qv.Lp = g.Lp; qv.n_words = g.n_words;
+    emu_launch_seq((unsigned)((g.n_words + 127) / 128), 128,
+                   [&]() { pack_queries_kernel(ascii, offsets, nq, qv, pack, inv, sep, wq); });
+    return g.n_words;
+}
+
 // K0 + K1 + K2: kbo::matches for a CSR batch
 void emu_matches_batch(void* h, const uint8_t* concat, const uint64_t* offsets, uint64_t nq, uint32_t thr,
                        uint32_t chunk_len, uint8_t* chars_out) {

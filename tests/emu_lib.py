@@ -51,6 +51,8 @@ def lib():
         L.emu_access_kmer.argtypes = [C.c_void_p, C.c_uint64, u8p]
         L.emu_search.argtypes = [C.c_void_p, u8p, C.c_uint64, u64p, u64p]
         L.emu_query_sbwt_batch.argtypes = [C.c_void_p, u8p, u64p, C.c_uint64, C.c_uint32, u8p, u32p, u32p, u64p]
+        L.emu_pack.restype = C.c_uint64
+        L.emu_pack.argtypes = [u8p, u64p, C.c_uint64, u64p, u32p, u32p, u32p]
         L.emu_matches_batch.argtypes = [C.c_void_p, u8p, u64p, C.c_uint64, C.c_uint32, C.c_uint32, u8p]
         L.emu_derand_translate_u8.argtypes = [u8p, C.c_uint64, C.c_uint32, C.c_uint32, u8p]
         L.emu_derandomize_general.argtypes = [u64p, C.c_uint64, C.c_uint32, C.c_uint32, i64p]
@@ -178,6 +180,19 @@ class EmuIndex:
         lib().emu_matches_batch(self.h, _p(concat, C.c_uint8), _p(offsets, C.c_uint64), len(queries), thr, chunk_len,
                                 _p(out, C.c_uint8))
         return [out[int(offsets[i]):int(offsets[i + 1])].tobytes() for i in range(len(queries))]
+
+
+def pack(concat, offsets):
+    """K0 on a CSR batch: (pack u64, inv u32, sep u32, wq u32) arrays in padded space."""
+    concat = np.ascontiguousarray(concat, dtype=np.uint8)
+    offsets = np.ascontiguousarray(offsets, dtype=np.uint64)
+    nq = len(offsets) - 1
+    nw = int(lib().emu_pack(_p(concat, C.c_uint8), _p(offsets, C.c_uint64), nq, None, None, None, None))
+    pk = np.zeros(nw, dtype=np.uint64)
+    iv, sp, wq = (np.zeros(nw, dtype=np.uint32) for _ in range(3))
+    lib().emu_pack(_p(concat, C.c_uint8), _p(offsets, C.c_uint64), nq, _p(pk, C.c_uint64), _p(iv, C.c_uint32),
+                   _p(sp, C.c_uint32), _p(wq, C.c_uint32))
+    return pk, iv, sp, wq
 
 
 def derand_translate_u8(ms, k, thr):

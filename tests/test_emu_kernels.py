@@ -254,3 +254,48 @@ def test_ms_independent_of_probe_iters_and_flags():
     finally:
         E.lib().emu_set_probe_iters(3)
         E.lib().emu_set_ms_flags(0)
+
+
+# ---------------------------------------------------------------------------
+# K0 alone: arbitrary bytes, empty queries, misaligned batch start
+# ---------------------------------------------------------------------------
+def _pack_model(concat, offsets):
+    """Per-position model of the packed layout (kernels.cuh QueryView)."""
+    nq = len(offsets) - 1
+    off0 = int(offsets[0])
+    lens = [int(offsets[i + 1] - offsets[i]) for i in range(nq)]
+    Lp = sum(lens) + nq
+    code, inv, sep, nsep_before = [], [], [], []
+    seen = 0
+    for i in range(nq):
+        for b in concat[int(offsets[i]):int(offsets[i + 1])]:
+            c = {65: 0, 67: 1, 71: 2, 84: 3}.get(int(b))
+            code.append(c or 0); inv.append(c is None); sep.append(False); nsep_before.append(seen)
+        code.append(0); inv.append(True); sep.append(True); nsep_before.append(seen)
+        seen += 1
+    assert len(code) == Lp and off0 >= 0
+    return code, inv, sep, nsep_before
+
+
+@pytest.mark.parametrize("seed", [1, 2, 3])
+def test_pack_kernel_matches_position_model(seed):
+    rng = np.random.default_rng(seed)
+    lens = [0, 1, 7, 8, 9, 31, 32, 33, 0, 0, 64, 5, 100, 257, 3, 0] + [int(x) for x in rng.integers(0, 70, 40)]
+    rng.shuffle(lens)
+    body = rng.integers(0, 256, sum(lens), dtype=np.uint8)
+    acgt = np.frombuffer(b"ACGT", dtype=np.uint8)[rng.integers(0, 4, len(body))]
+    body = np.where(rng.random(len(body)) < 0.7, acgt, body).astype(np.uint8)
+    lead = seed  # the batch starts `lead` bytes into the buffer
+    concat = np.concatenate([np.zeros(lead, dtype=np.uint8), body])
+    offsets = np.concatenate([[lead], lead + np.cumsum(lens)]).astype(np.uint64)
+    pk, iv, sp, wq = E.pack(concat, offsets)
+    code, inv, sep, nsb = _pack_model(concat, offsets)
+    Lp = len(code)
+    for pp in range(len(pk) * 32):
+        w, j = pp >> 5, pp & 31
+        got = (int(pk[w]) >> (2 * j)) & 3, bool((int(iv[w]) >> j) & 1), bool((int(sp[w]) >> j) & 1)
+        want = (code[pp], inv[pp], sep[pp]) if pp < Lp else (0, True, True)
+        assert got == want, (pp, got, want)
+    for w in range(len(pk)):
+        pp = 32 * w
+        assert int(wq[w]) == (nsb[pp] if pp < Lp else len(lens))

@@ -102,6 +102,8 @@ struct Workspace {
     bool own_stream = false;
     cudaEvent_t ev0 = nullptr, ev1 = nullptr;
     DevBuf ascii, offsets, pack, inv, sep, wq, ms, l, r, out, out2, out3, tmp64, tmp64b, tmp32, tmp32b, counters;
+    DevBuf masks, rle_words, rle_cnt, rle_cse, cub_tmp;  // K2b<false> masks and the K4 arrays
+    RleParams rle;                                       // filled by run_rle_offsets, reused by run_rle_records
     std::vector<cudaEvent_t> timing;  // 4 events per timed call (before K0, after K0, after K1, after K2)
     size_t timed_calls = 0;
     void destroy() {
@@ -111,7 +113,7 @@ struct Workspace {
         if (ev_fork) cudaEventDestroy(ev_fork);
         for (cudaEvent_t e : ev_join) cudaEventDestroy(e);
         DevBuf* all[] = {&ascii, &offsets, &pack, &inv, &sep, &wq, &ms, &l, &r, &out, &out2, &out3,
-                         &tmp64, &tmp64b, &tmp32, &tmp32b, &counters};
+                         &tmp64, &tmp64b, &tmp32, &tmp32b, &counters, &masks, &rle_words, &rle_cnt, &rle_cse, &cub_tmp};
         for (DevBuf* b : all) b->release();
         if (ev0) cudaEventDestroy(ev0);
         if (ev1) cudaEventDestroy(ev1);
@@ -504,8 +506,11 @@ static int run_ms(kbo_index* ix, Workspace* ws, const QueryView& qv, const Geome
     return KBO_OK;
 }
 
+// K2 / K2b.  want_masks == false: characters to d_out (unpadded, at off0).  want_masks == true: the three
+// per-position masks K4 consumes, in ws->masks (gap | match | r, n_tiles_b * 32 words each).
 static int run_derand_translate(kbo_index* ix, Workspace* ws, const QueryView& qv, const Geometry& g, uint32_t thr,
-                                uint8_t* d_out, uint64_t off0) {
+                                uint8_t* d_out, uint64_t off0, bool want_masks = false) {
+    cudaStream_t st = ws->stream;
     TrParams tp;
     tp.ms = ws->ms.as<uint8_t>();
     tp.q = qv;
@@ -513,13 +518,100 @@ static int run_derand_translate(kbo_index* ix, Workspace* ws, const QueryView& q
     tp.thr = thr;
     tp.out = d_out;
     tp.off0 = off0;
-    tp.n_tiles = g.n_tiles;
-    const unsigned blocks = (unsigned)((g.n_tiles + K2_WARPS - 1) / K2_WARPS);
-    derand_translate_kernel<<<blocks, K2_WARPS * 32, 0, ws->stream>>>(tp);
+    tp.out_gap = tp.out_match = tp.out_r = nullptr;
+    const uint64_t nw = g.n_tiles_b * 32;
+    if (want_masks) {
+        CUDA_TRY(ws->masks.ensure(nw * 3 * 4, st));
+        tp.out_gap = ws->masks.as<uint32_t>();
+        tp.out_match = tp.out_gap + nw;
+        tp.out_r = tp.out_match + nw;
+    }
+    if (k2b_supported(tp.k, tp.thr) && !(g_ms_flags.load() & 2u)) {  // flag bit1: force K2 (experiments / tests)
+        tp.n_tiles = g.n_tiles_b;
+        const unsigned blocks = (unsigned)((g.n_tiles_b + K2B_WARPS - 1) / K2B_WARPS);
+        if (want_masks) derand_translate_bits_kernel<false><<<blocks, K2B_WARPS * 32, 0, st>>>(tp);
+        else derand_translate_bits_kernel<true><<<blocks, K2B_WARPS * 32, 0, st>>>(tp);
+        LAUNCHED();
+    } else {
+        if (want_masks) {  // K2 writes characters; a second kernel turns them into masks
+            CUDA_TRY(ws->out.ensure(g.total + 16, st));
+            tp.out = ws->out.as<uint8_t>();
+            tp.off0 = 0;
+        }
+        tp.n_tiles = g.n_tiles;
+        const unsigned blocks = (unsigned)((g.n_tiles + K2_WARPS - 1) / K2_WARPS);
+        derand_translate_kernel<<<blocks, K2_WARPS * 32, 0, st>>>(tp);
+        LAUNCHED();
+        if (want_masks) {
+            chars_to_masks_kernel<<<(unsigned)(nw * 32 / 128), 128, 0, st>>>(tp.out, 0, qv.sep, qv.wq, nw, tp.out_gap,
+                                                                             tp.out_match, tp.out_r);
+            LAUNCHED();
+        }
+    }
+    CUDA_TRY(cudaGetLastError());
+    return KBO_OK;
+}
+
+// K4 up to the per-query record offsets: word counts -> scan -> START/END marks -> scan -> offsets.
+// d_offsets are the batch's own CSR offsets (offsets[0] may be non-zero); d_rle_offsets gets nq + 1 entries.
+static int run_rle_offsets(Workspace* ws, const QueryView& qv, const Geometry& g, const uint64_t* d_offsets, uint64_t nq,
+                           uint32_t max_gap_len, uint64_t* d_rle_offsets) {
+    cudaStream_t st = ws->stream;
+    const uint64_t nw = g.n_tiles_b * 32;
+    CUDA_TRY(ws->rle_words.ensure(nw * 4 * 4, st));
+    CUDA_TRY(ws->rle_cnt.ensure((nw + 1) * sizeof(RleCounts), st));
+    CUDA_TRY(ws->rle_cse.ensure((nw + 1) * 8, st));
+    RleParams& p = ws->rle;
+    p.gap = ws->masks.as<uint32_t>();
+    p.match = p.gap + nw;
+    p.rr = p.match + nw;
+    p.sep = qv.sep;
+    p.wq = qv.wq;
+    p.n_words = nw;
+    p.offsets = d_offsets;
+    p.nq = nq;
+    p.window = max_gap_len + 1;
+    p.jump = ws->rle_words.as<uint32_t>();
+    p.gopen = p.jump + nw;
+    p.start = p.gopen + nw;
+    p.end = p.start + nw;
+    p.cnt = ws->rle_cnt.as<RleCounts>();
+    p.cse = ws->rle_cse.as<uint64_t>();
+    p.rle_offsets = d_rle_offsets;
+    p.out = nullptr;
+    p.cap = 0;
+    size_t tmp_a = 0, tmp_b = 0;
+    const RleCounts zero = {0, 0, 0, 0};
+    CUDA_TRY(cub::DeviceScan::ExclusiveScan(nullptr, tmp_a, p.cnt, p.cnt, RleCountsSum(), zero, (int)(nw + 1), st));
+    CUDA_TRY(cub::DeviceScan::ExclusiveSum(nullptr, tmp_b, p.cse, p.cse, (int)(nw + 1), st));
+    size_t tmp = std::max(tmp_a, tmp_b);
+    CUDA_TRY(ws->cub_tmp.ensure(tmp, st));
+    const unsigned threads = 128;
+    const unsigned blocks = (unsigned)((nw + 1 + threads - 1) / threads);
+    rle_word_counts_kernel<<<blocks, threads, 0, st>>>(p);
+    LAUNCHED();
+    CUDA_TRY(cub::DeviceScan::ExclusiveScan(ws->cub_tmp.p, tmp, p.cnt, p.cnt, RleCountsSum(), zero, (int)(nw + 1), st));
+    rle_mark_kernel<<<blocks, threads, 0, st>>>(p);
+    LAUNCHED();
+    CUDA_TRY(cub::DeviceScan::ExclusiveSum(ws->cub_tmp.p, tmp, p.cse, p.cse, (int)(nw + 1), st));
+    rle_query_offsets_kernel<<<(unsigned)((nq + 1 + threads - 1) / threads), threads, 0, st>>>(p);
     LAUNCHED();
     CUDA_TRY(cudaGetLastError());
     return KBO_OK;
 }
+
+// K4 records (after run_rle_offsets on the same workspace): slots >= cap are dropped
+static int run_rle_records(Workspace* ws, RleRecord* d_out, uint64_t cap) {
+    RleParams& p = ws->rle;
+    p.out = d_out;
+    p.cap = cap;
+    const unsigned threads = 128;
+    rle_records_kernel<<<(unsigned)((p.n_words + threads - 1) / threads), threads, 0, ws->stream>>>(p);
+    LAUNCHED();
+    CUDA_TRY(cudaGetLastError());
+    return KBO_OK;
+}
+static_assert(sizeof(RleRecord) == sizeof(kbo_rle), "device and ABI RLE records must agree");
 
 template <typename T>
 __global__ void unpad_kernel(const T* __restrict__ in, QueryView q, T* __restrict__ out) {
@@ -552,7 +644,8 @@ static int fetch_counters(kbo_index* ix, Workspace* ws) {
 
 // matches for a batch whose inputs are already on the device (ws->stream)
 static int matches_device(kbo_index* ix, Workspace* ws, const uint8_t* d_concat, const uint64_t* d_offsets,
-                          uint64_t nq, const Geometry& g, uint32_t thr, uint8_t* d_out, uint64_t off0) {
+                          uint64_t nq, const Geometry& g, uint32_t thr, uint8_t* d_out, uint64_t off0,
+                          bool want_masks = false, QueryView* qv_out = nullptr) {
     QueryView qv;
     cudaEvent_t* ev = nullptr;
     if (g_kernel_timing.load() && ws->timed_calls < 512) {
@@ -572,9 +665,10 @@ static int matches_device(kbo_index* ix, Workspace* ws, const uint8_t* d_concat,
     rc = run_ms(ix, ws, qv, g, false);
     if (rc) return rc;
     if (ev) CUDA_TRY(cudaEventRecord(ev[2], ws->stream));
-    rc = run_derand_translate(ix, ws, qv, g, thr, d_out, off0);
+    rc = run_derand_translate(ix, ws, qv, g, thr, d_out, off0, want_masks);
     if (rc) return rc;
     if (ev) CUDA_TRY(cudaEventRecord(ev[3], ws->stream));
+    if (qv_out) *qv_out = qv;
     return KBO_OK;
 }
 
@@ -945,8 +1039,7 @@ int kbo_matches(const kbo_index* ix, const uint8_t* query, uint64_t len, double 
 // bound by instruction issue at ~50 % occupancy), so the streaming kernels of one part overlap K1 of another.
 // `counts` / `stage` (optional) receive the per-query segment counts and staged records for kbo::find.
 static int matches_device_forked(kbo_index* ix, Workspace* ws, const uint8_t* d_concat, const uint64_t* d_offsets,
-                                 const uint64_t* host_offsets, uint64_t nq, uint32_t thr, uint8_t* d_chars,
-                                 bool want_rle, uint32_t gap) {
+                                 const uint64_t* host_offsets, uint64_t nq, uint32_t thr, uint8_t* d_chars) {
     const uint64_t total = host_offsets[nq];
     uint64_t want = g_dev_parts.load();
     if (!want) want = std::min<uint64_t>(2, std::max<uint64_t>(1, total >> 22));
@@ -954,26 +1047,9 @@ static int matches_device_forked(kbo_index* ix, Workspace* ws, const uint8_t* d_
     const std::vector<uint64_t> cut = split_queries(host_offsets, nq, want);
     const size_t np = cut.size() - 1;
     cudaStream_t user = ws->stream;
-    if (want_rle) {
-        CUDA_TRY(ws->tmp32.ensure(nq * 4, user));
-        CUDA_TRY(ws->out3.ensure(nq * RLE_STAGE * sizeof(RleRecord), user));
-    }
-    auto rle_count = [&](Workspace* w, uint64_t q0, uint64_t n) -> int {
-        const unsigned threads = 128;
-        const unsigned blocks = (unsigned)((n * 32 + threads - 1) / threads);
-        rle_kernel<false><<<blocks, threads, 0, w->stream>>>(d_chars + host_offsets[q0], d_offsets + q0, n, gap,
-                                                             ws->tmp32.as<uint32_t>() + q0,
-                                                             ws->out3.as<RleRecord>() + q0 * RLE_STAGE, nullptr,
-                                                             nullptr, 0);
-        LAUNCHED();
-        CUDA_TRY(cudaGetLastError());
-        return KBO_OK;
-    };
     if (np == 1) {
         const Geometry g = make_geometry(total, nq);
-        int rc = matches_device(ix, ws, d_concat, d_offsets, nq, g, thr, d_chars, 0);
-        if (rc) return rc;
-        return want_rle ? rle_count(ws, 0, nq) : KBO_OK;
+        return matches_device(ix, ws, d_concat, d_offsets, nq, g, thr, d_chars, 0);
     }
     while (ws->subs.size() < np) {
         Workspace* sub = new Workspace();
@@ -993,10 +1069,6 @@ static int matches_device_forked(kbo_index* ix, Workspace* ws, const uint8_t* d_
         CUDA_TRY(cudaStreamWaitEvent(sub->stream, ws->ev_fork, 0));
         int rc = matches_device(ix, sub, d_concat, d_offsets + q0, n, g, thr, d_chars, host_offsets[q0]);
         if (rc) return rc;
-        if (want_rle) {
-            rc = rle_count(sub, q0, n);
-            if (rc) return rc;
-        }
         CUDA_TRY(cudaEventRecord(ws->ev_join[s], sub->stream));
         CUDA_TRY(cudaStreamWaitEvent(user, ws->ev_join[s], 0));
     }
@@ -1018,7 +1090,7 @@ int kbo_matches_batch_device(const kbo_index* cix, const uint8_t* d_concat, cons
     Workspace* ws = nullptr;
     rc = stream_ws(ix, (cudaStream_t)stream, &ws);
     if (rc) return rc;
-    rc = matches_device_forked(ix, ws, d_concat, d_offsets, host_offsets, n_queries, thr, d_chars_out, false, 0);
+    rc = matches_device_forked(ix, ws, d_concat, d_offsets, host_offsets, n_queries, thr, d_chars_out);
     if (rc) return rc;
     if (g_profile_counters.load()) return fetch_counters(ix, ws);
     return KBO_OK;
@@ -1085,34 +1157,6 @@ int kbo_relative_to_ref(const uint8_t* ref_seq, const uint8_t* aln, uint64_t n, 
     return KBO_OK;
 }
 
-// K4 launches: per-query segment counts -> exclusive scan -> records (all on ws->stream)
-static int run_rle_count_scan(Workspace* ws, const uint8_t* d_aln, const uint64_t* d_offsets, uint64_t nq,
-                              uint32_t max_gap_len, uint64_t* d_rle_offsets) {
-    cudaStream_t st = ws->stream;
-    CUDA_TRY(ws->tmp32.ensure(nq * 4, st));
-    CUDA_TRY(ws->out3.ensure(nq * RLE_STAGE * sizeof(RleRecord), st));
-    const unsigned threads = 128;
-    const unsigned blocks = (unsigned)((nq * 32 + threads - 1) / threads);
-    rle_kernel<false><<<blocks, threads, 0, st>>>(d_aln, d_offsets, nq, max_gap_len, ws->tmp32.as<uint32_t>(),
-                                                  ws->out3.as<RleRecord>(), nullptr, nullptr, 0);
-    LAUNCHED();
-    rle_scan_kernel<<<1, 1024, 0, st>>>(ws->tmp32.as<uint32_t>(), nq, d_rle_offsets);
-    LAUNCHED();
-    CUDA_TRY(cudaGetLastError());
-    return KBO_OK;
-}
-static int run_rle_write(Workspace* ws, const uint8_t* d_aln, const uint64_t* d_offsets, uint64_t nq,
-                         uint32_t max_gap_len, const uint64_t* d_rle_offsets, RleRecord* d_out, uint64_t cap) {
-    const unsigned threads = 128;
-    const unsigned blocks = (unsigned)((nq * 32 + threads - 1) / threads);
-    rle_kernel<true><<<blocks, threads, 0, ws->stream>>>(d_aln, d_offsets, nq, max_gap_len, ws->tmp32.as<uint32_t>(),
-                                                         ws->out3.as<RleRecord>(), d_rle_offsets, d_out, cap);
-    LAUNCHED();
-    CUDA_TRY(cudaGetLastError());
-    return KBO_OK;
-}
-static_assert(sizeof(RleRecord) == sizeof(kbo_rle), "device and ABI RLE records must agree");
-
 // Splits a CSR batch into up to `parts` contiguous query ranges of similar base counts.
 static std::vector<uint64_t> split_queries(const uint64_t* offsets, uint64_t nq, uint64_t parts) {
     std::vector<uint64_t> cut(1, 0);
@@ -1147,7 +1191,7 @@ int kbo_find_batch(const kbo_index* cix, const uint8_t* concat, const uint64_t* 
     const size_t np = cut.size() - 1;
     std::vector<Workspace*> wss(np, nullptr);
     auto give_back = [&]() { for (Workspace* w : wss) if (w) release_ws(ix, w); };
-    // phase 1: enqueue copy-in, K0, K1, K2, K4 count + scan and the copy-out of the per-query offsets
+    // phase 1: enqueue copy-in, K0, K1, K2b (masks), K4 up to the per-query offsets, and their copy-out
     for (size_t s = 0; s < np && !rc; ++s) {
         rc = acquire_ws(ix, &wss[s]);
         if (rc) break;
@@ -1159,7 +1203,6 @@ int kbo_find_batch(const kbo_index* cix, const uint8_t* concat, const uint64_t* 
         auto body = [&]() -> int {
             CUDA_TRY(ws->ascii.ensure(bytes, st));
             CUDA_TRY(ws->offsets.ensure((nq + 1) * 8, st));
-            CUDA_TRY(ws->out.ensure(bytes + 16, st));
             CUDA_TRY(ws->tmp64.ensure((nq + 1) * 8, st));
             CUDA_TRY(ws->h_rel.ensure((nq + 1) * 8));
             CUDA_TRY(ws->h_roff.ensure((nq + 1) * 8));
@@ -1168,18 +1211,18 @@ int kbo_find_batch(const kbo_index* cix, const uint8_t* concat, const uint64_t* 
             CUDA_TRY(cudaMemcpyAsync(ws->ascii.p, concat + offsets[q0], bytes, cudaMemcpyHostToDevice, st));
             CUDA_TRY(cudaMemcpyAsync(ws->offsets.p, rel, (nq + 1) * 8, cudaMemcpyHostToDevice, st));
             if (s == 0) CUDA_TRY(cudaEventRecord(ws->ev0, st));
-            int rc2 = matches_device(ix, ws, ws->ascii.as<uint8_t>(), ws->offsets.as<uint64_t>(), nq, g, thr,
-                                     ws->out.as<uint8_t>(), 0);
+            QueryView qv;
+            int rc2 = matches_device(ix, ws, ws->ascii.as<uint8_t>(), ws->offsets.as<uint64_t>(), nq, g, thr, nullptr, 0,
+                                     true, &qv);
             if (rc2) return rc2;
-            rc2 = run_rle_count_scan(ws, ws->out.as<uint8_t>(), ws->offsets.as<uint64_t>(), nq, gap,
-                                     ws->tmp64.as<uint64_t>());
+            rc2 = run_rle_offsets(ws, qv, g, ws->offsets.as<uint64_t>(), nq, gap, ws->tmp64.as<uint64_t>());
             if (rc2) return rc2;
             CUDA_TRY(cudaMemcpyAsync(ws->h_roff.p, ws->tmp64.p, (nq + 1) * 8, cudaMemcpyDeviceToHost, st));
             return KBO_OK;
         };
         rc = body();
     }
-    // phase 2: per sub-batch, in order: record count -> write pass -> asynchronous copy-out of the records
+    // phase 2: per sub-batch, in order: record count -> K4 records -> asynchronous copy-out of the records
     uint64_t base = 0;
     std::vector<uint64_t> part_base(np, 0), part_n(np, 0);
     rle_offsets[0] = 0;
@@ -1200,8 +1243,7 @@ int kbo_find_batch(const kbo_index* cix, const uint8_t* concat, const uint64_t* 
                 if (!rle_out) return fail(KBO_ERR_BAD_ARGUMENT, "rle_out is null");
                 CUDA_TRY(ws->out2.ensure(n_rle * sizeof(RleRecord), st));
                 CUDA_TRY(ws->h_rle.ensure(n_rle * sizeof(RleRecord)));
-                int rc2 = run_rle_write(ws, ws->out.as<uint8_t>(), ws->offsets.as<uint64_t>(), nq, gap,
-                                        ws->tmp64.as<uint64_t>(), ws->out2.as<RleRecord>(), n_rle);
+                int rc2 = run_rle_records(ws, ws->out2.as<RleRecord>(), n_rle);
                 if (rc2) return rc2;
                 CUDA_TRY(cudaMemcpyAsync(ws->h_rle.p, ws->out2.p, n_rle * sizeof(RleRecord), cudaMemcpyDeviceToHost, st));
             }
@@ -1245,15 +1287,16 @@ int kbo_find_batch_device(const kbo_index* cix, const uint8_t* d_concat, const u
     Workspace* ws = nullptr;
     rc = stream_ws(ix, (cudaStream_t)stream, &ws);
     if (rc) return rc;
-    CUDA_TRY(ws->out.ensure(total + 16, ws->stream));
-    rc = matches_device_forked(ix, ws, d_concat, d_offsets, host_offsets, n_queries, thr, ws->out.as<uint8_t>(), true,
-                               gap);
+    const Geometry g = make_geometry(total, n_queries);
+    QueryView qv;
+    rc = matches_device(ix, ws, d_concat, d_offsets, n_queries, g, thr, nullptr, 0, true, &qv);
     if (rc) return rc;
-    rle_scan_kernel<<<1, 1024, 0, ws->stream>>>(ws->tmp32.as<uint32_t>(), n_queries, d_rle_offsets);
-    LAUNCHED();
-    CUDA_TRY(cudaGetLastError());
-    return run_rle_write(ws, ws->out.as<uint8_t>(), d_offsets, n_queries, gap, d_rle_offsets,
-                         reinterpret_cast<RleRecord*>(d_rle_out), rle_cap);
+    rc = run_rle_offsets(ws, qv, g, d_offsets, n_queries, gap, d_rle_offsets);
+    if (rc) return rc;
+    rc = run_rle_records(ws, reinterpret_cast<RleRecord*>(d_rle_out), rle_cap);
+    if (rc) return rc;
+    if (g_profile_counters.load()) return fetch_counters(ix, ws);
+    return KBO_OK;
 }
 
 int kbo_map_unrefined(const kbo_index* query_index, const uint8_t* ref_seq, uint64_t len, double max_error_prob,

@@ -46,6 +46,7 @@ struct Geometry {
     uint64_t total = 0;    // sum of query lengths
     uint64_t Lp = 0;       // padded length = total + n_queries
     uint64_t n_tiles = 0;  // K2 tiles of 512 positions
+    uint64_t n_tiles_b = 0;  // K2b tiles of 1024 positions
     uint64_t n_words = 0;  // 32-position words written by K0 (all tiles + 4 slack words)
     uint32_t chunk_len = 0;
     uint64_t n_chunks = 0;
@@ -67,7 +68,8 @@ inline Geometry make_geometry(uint64_t total, uint64_t nq, uint32_t forced_chunk
     g.total = total;
     g.Lp = total + nq;
     g.n_tiles = (g.Lp + 511) / 512;
-    g.n_words = g.n_tiles * 16 + 4;
+    g.n_tiles_b = (g.Lp + 1023) / 1024;
+    g.n_words = g.n_tiles_b * 32 + 4;
     g.chunk_len = forced_chunk_len ? ((forced_chunk_len + 31u) & ~31u) : auto_chunk_len(g.Lp);
     g.n_chunks = (g.Lp + g.chunk_len - 1) / g.chunk_len;
     g.ms_bytes = (size_t)(g.n_words * 32 + 64);

@@ -168,7 +168,8 @@ struct MsParams {
     QueryView q;
     uint32_t chunk_len;    // multiple of 32
     uint32_t probe_iters;  // probe iterations per contraction phase (>= 1)
-    uint32_t flags;        // experiment switches: bit0 = population count on the ALU pipe instead of POPC (XU pipe)
+    uint32_t flags;        // experiment switches: bit0 = population count on the ALU pipe instead of POPC (XU pipe);
+                           // bit1 (host side) = run K2 where K2b would be picked
     uint64_t n_chunks;
     uint8_t* ms;         // padded space, 1 byte per position
     uint32_t* l_out;     // optional (INTERVALS)
@@ -379,8 +380,14 @@ struct TrParams {
     uint32_t k, thr;
     uint8_t* out;       // out[off0 + pp - (#separators before pp)]
     uint64_t off0;
-    uint64_t n_tiles;
+    uint64_t n_tiles;   // tiles of the kernel that is launched (K2: 512 positions, K2b: 1024)
+    uint32_t* out_gap;  // K2b<false>: one bit per padded position, '-'
+    uint32_t* out_match;  //                                         'M' or 'R'
+    uint32_t* out_r;      //                                         'R'
 };
+
+// K2b covers this parameter range; K2 everything else
+__host__ __device__ inline bool k2b_supported(uint32_t k, uint32_t thr) { return thr >= 2 && thr < k && k <= 127; }
 
 enum { K2_PER_LANE = 16, K2_TILE = 512, K2_WARPS = 4 };
 enum { OP_KEEP = 0, OP_TOGGLE = 1, OP_SET0 = 2 };
@@ -628,176 +635,490 @@ __global__ void __launch_bounds__(K2_WARPS * 32) derand_translate_kernel(TrParam
 }
 
 // ---------------------------------------------------------------------------
+// K2b: the same function as K2, bit-parallel.  One LANE per 32 padded positions,
+// one warp per tile of 1024.  Valid for 2 <= thr < k <= 127 (the host picks K2
+// otherwise); within that range
+//   * MS bytes are < 128, so four of them are compared per 32-bit operation and
+//     the per-byte flags are gathered into per-position bit masks with one
+//     multiplication;
+//   * an eligible position has m > thr, hence c = m - eps >= thr >= 2: it is
+//     never in the classes "c == 0", "c == 1", "0 < c < thr", and it leaves
+//     "c > thr" only for m == thr + 1 with eps == 1;
+//   * eps is a segmented suffix XOR over the TOGGLE mask (5 shift steps);
+//   * the positions below the threshold form runs that end at a source (eligible
+//     position, last position of a query, or the value entering the word from
+//     the right); inside a run c = max(v - distance, 0), so each class is a bit
+//     range computed from the run's end and v.
+// translate_ms_vec's rules then are a dozen logic operations on the class masks.
+// CHARS == true stores the characters (unpadded, like K2); CHARS == false stores
+// the three masks K4b consumes ('-', match-like, 'R') in padded space.
+// ---------------------------------------------------------------------------
+enum { K2B_TILE = 1024, K2B_WARPS = 4 };
+
+__device__ __forceinline__ uint32_t bits_le(int t) {  // bits 0..t
+    return t < 0 ? 0u : (t >= 31 ? ~0u : ((2u << t) - 1u));
+}
+__device__ __forceinline__ uint32_t bits_ge(int t) {  // bits t..31
+    return t <= 0 ? ~0u : (t >= 32 ? 0u : (~0u << t));
+}
+__device__ __forceinline__ uint32_t funnel_r(uint32_t lo, uint32_t hi, uint32_t bits) {  // bits in [0,31]
+    return bits ? ((lo >> bits) | (hi << (32 - bits))) : lo;
+}
+
+// copy n bytes from shared memory (any alignment) to global memory, one warp
+__device__ __forceinline__ void warp_copy_out(const uint8_t* st, uint32_t src_off, uint8_t* dst, uint32_t n, int lane) {
+    const uint32_t head0 = (uint32_t)((4 - (reinterpret_cast<uintptr_t>(dst) & 3)) & 3);
+    const uint32_t head = head0 < n ? head0 : n;
+    if ((uint32_t)lane < head) dst[lane] = st[src_off + lane];
+    const uint32_t nwords = (n - head) >> 2;
+    for (uint32_t w = lane; w < nwords; w += 32) {
+        const uint32_t so = src_off + head + 4 * w;
+        const uint32_t* a = reinterpret_cast<const uint32_t*>(st + (so & ~3u));
+        *reinterpret_cast<uint32_t*>(dst + head + 4 * w) = funnel_r(a[0], a[1], 8 * (so & 3u));
+    }
+    const uint32_t done = head + 4 * nwords;
+    if (done + lane < n) dst[done + lane] = st[src_off + done + lane];
+}
+
+template <bool CHARS>
+__global__ void __launch_bounds__(K2B_WARPS * 32) derand_translate_bits_kernel(TrParams p) {
+    __shared__ uint32_t lut[256];                                     // (4 bits b0, 4 bits b1) -> 4 characters
+    __shared__ __align__(16) uint8_t stage[K2B_WARPS][K2B_TILE + 16];
+    if (CHARS) {
+        for (uint32_t i = threadIdx.x; i < 256; i += blockDim.x) {
+            uint32_t v = 0;
+            for (int j = 0; j < 4; ++j) {
+                const uint32_t code = ((i >> j) & 1u) | (((i >> (4 + j)) & 1u) << 1);  // 0 M, 1 -, 2 X, 3 R
+                const uint32_t ch = code == 0 ? 'M' : (code == 1 ? '-' : (code == 2 ? 'X' : 'R'));
+                v |= ch << (8 * j);
+            }
+            lut[i] = v;
+        }
+        __syncthreads();
+    }
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const uint64_t tile = (uint64_t)blockIdx.x * K2B_WARPS + warp;
+    if (tile >= p.n_tiles) return;  // warp-uniform
+    const uint64_t s = tile * K2B_TILE, e = s + K2B_TILE;
+    const uint64_t P = s + 32ull * lane;
+    const uint32_t k = p.k, thr = p.thr;
+    const uint32_t H = 0x80808080u;
+
+    // ---- loads: 32 MS bytes + the first four of the next word; separator bits around the word -------------
+    uint32_t mw[9];
+    {
+        const uint4 va = *reinterpret_cast<const uint4*>(p.ms + P);
+        const uint4 vb = *reinterpret_cast<const uint4*>(p.ms + P + 16);
+        mw[0] = va.x; mw[1] = va.y; mw[2] = va.z; mw[3] = va.w;
+        mw[4] = vb.x; mw[5] = vb.y; mw[6] = vb.z; mw[7] = vb.w;
+#pragma unroll
+        for (int j = 0; j < 8; ++j) mw[j] &= 0x7f7f7f7fu;  // bytes of separators / the tail may hold anything
+        mw[8] = __shfl_down_sync(0xffffffffu, mw[0], 1);
+        if (lane == 31) mw[8] = *reinterpret_cast<const uint32_t*>(p.ms + P + 32) & 0x7f7f7f7fu;
+    }
+    const uint32_t S = __ldg(p.q.sep + (P >> 5));
+    uint32_t s_next = __shfl_down_sync(0xffffffffu, S, 1) & 1u;  // separator bit of P+32
+    if (lane == 31) s_next = sep_bit(p.q, (int64_t)e);
+    uint32_t s_prev = __shfl_up_sync(0xffffffffu, S, 1) >> 30;   // bit0 = sep(P-2), bit1 = sep(P-1)
+    if (lane == 0) s_prev = sep_bit(p.q, (int64_t)P - 2) | (sep_bit(p.q, (int64_t)P - 1) << 1);
+
+    // ---- value entering the tile from the right ---------------------------------------------------------------
+    const uint32_t c_e = lookahead_c(p, e, lane);
+    const uint32_t m_e = p.ms[e] & 0x7fu;
+    const bool e_sep = sep_bit(p.q, (int64_t)e);
+    const bool e_last = !e_sep && sep_bit(p.q, (int64_t)e + 1);
+    const uint32_t eps_e = (!e_sep && !e_last && (m_e > thr || m_e == k)) ? (m_e - c_e) & 1u : 0u;
+
+    // ---- byte-parallel comparisons -> per-position masks ----------------------------------------------------
+    uint32_t GT = 0, GT1 = 0, NEK = 0, GE = 0, B0 = 0;
+    {
+        const uint32_t thr1 = (thr + 1) * 0x01010101u, thr2 = (thr + 2) * 0x01010101u, krep = k * 0x01010101u;
+#pragma unroll
+        for (int j = 0; j < 8; ++j) {
+            const uint32_t w = mw[j];
+            const uint32_t nx = (w >> 8) | (mw[j + 1] << 24);  // the right neighbours of the four positions
+            const uint32_t gt = ((w | H) - thr1) & H;           // m >= thr+1
+            const uint32_t gt1 = ((w | H) - thr2) & H;          // m >= thr+2
+            const uint32_t nek = ((w ^ krep) + 0x7f7f7f7fu) & H;  // m != k
+            const uint32_t d = (nx | H) - w;                    // byte = 128 + m1 - m0
+            GT |= ((gt * 0x00204081u) >> 28) << (4 * j);
+            GT1 |= ((gt1 * 0x00204081u) >> 28) << (4 * j);
+            NEK |= ((nek * 0x00204081u) >> 28) << (4 * j);
+            GE |= (((d & H) * 0x00204081u) >> 28) << (4 * j);   // m1 >= m0
+            B0 |= (((d & 0x01010101u) * 0x10204080u) >> 28) << (4 * j);  // with m1 >= m0: m1 == m0 + 1
+        }
+    }
+    const uint32_t L = ~S & ((S >> 1) | (s_next << 31));  // last position of its query
+    const uint32_t E = ~S & ~L & GT;                       // eligible (m == k implies m > thr here)
+    const uint32_t Z = ~E | ~NEK | ~GE;                    // parity op SET0
+    const uint32_t T = E & ~Z & ~B0;                       // parity op TOGGLE (m1 == m0)
+
+    // ---- eps: segmented suffix XOR of T inside the word, then across the warp -------------------------------
+    uint32_t x = T, open = ~Z;  // open[i]: no SET0 in the window examined so far
+#pragma unroll
+    for (int sft = 1; sft < 32; sft <<= 1) {
+        x ^= open & (x >> sft);
+        open &= (open >> sft) | (~0u << (32 - sft));
+    }
+    // now x[i] = eps[i] if nothing entered from the right, open[i] = no SET0 in [i, 31]
+    uint32_t G = (Z ? 2u : 0u) | (x & 1u);
+#pragma unroll
+    for (int off = 1; off < 32; off <<= 1) {
+        const uint32_t o = __shfl_down_sync(0xffffffffu, G, off);
+        if (lane + off < 32) G = par_compose(G, o);
+    }
+    uint32_t Gn = __shfl_down_sync(0xffffffffu, G, 1);
+    if (lane == 31) Gn = 0;
+    const uint32_t eps = x ^ (open & (0u - par_apply(Gn, eps_e)));
+
+    // ---- value of a source position of this word --------------------------------------------------------------
+    auto source_value = [&](uint32_t i) -> uint32_t {
+        if ((S >> i) & 1u) return 0u;
+        const uint32_t m = p.ms[P + i] & 0x7fu;
+        if ((L >> i) & 1u) return ((GT >> i) & 1u) ? m : 0u;
+        return m - ((eps >> i) & 1u);
+    };
+    const uint32_t SRC = S | L | E;
+    uint32_t Hs = 32u;  // no source: 32 positions of distance
+    if (SRC) {
+        const uint32_t f = (uint32_t)__ffs((int)SRC) - 1u;
+        const uint32_t v = source_value(f);
+        Hs = (1u << 16) | (v > f ? v - f : 0u);
+    }
+    uint32_t HH = Hs;
+#pragma unroll
+    for (int off = 1; off < 32; off <<= 1) {
+        const uint32_t o = __shfl_down_sync(0xffffffffu, HH, off);
+        if (lane + off < 32) HH = src_compose(HH, o);
+    }
+    uint32_t Hn = __shfl_down_sync(0xffffffffu, HH, 1);
+    if (lane == 31) Hn = 0;
+    const uint32_t c_in = src_apply(Hn, c_e);  // clamped derandomized value of position P+32
+
+    // ---- classes of the below-threshold runs ---------------------------------------------------------------------
+    uint32_t Z0 = L & ~GT, O1 = 0, PL = 0, PG = (E & ~(GT & ~GT1 & eps)) | (L & GT);
+    uint32_t c_first = 0;  // numeric value of position P (needed by lane 0 only)
+    {
+        uint32_t rem = ~SRC;
+        while (rem) {
+            const uint32_t a = (uint32_t)__ffs((int)rem) - 1u;
+            const uint32_t inv_run = ~(rem >> a);
+            const uint32_t len = inv_run ? (uint32_t)__ffs((int)inv_run) - 1u : 32u;
+            const uint32_t end = a + len;  // the run's source (32 = next word)
+            const uint32_t v = end == 32 ? c_in : source_value(end);
+            const uint32_t run = bits_ge((int)a) & bits_le((int)end - 1);
+            const int t0 = (int)end - (int)v;  // c == 0 at and below t0
+            Z0 |= run & bits_le(t0);
+            O1 |= run & bits_ge(t0 + 1) & bits_le(t0 + 1);
+            PL |= run & bits_ge(t0 + 1) & bits_le(t0 + (int)thr - 1);
+            PG |= run & bits_ge(t0 + (int)thr + 1);
+            if (a == 0) c_first = v > end ? v - end : 0u;
+            rem &= ~run;
+        }
+        if (SRC & 1u) c_first = source_value(0);
+    }
+
+    // ---- neighbours across the word / tile boundaries --------------------------------------------------------
+    uint32_t nPL = __shfl_down_sync(0xffffffffu, PL, 1) & 1u, nO1 = __shfl_down_sync(0xffffffffu, O1, 1) & 1u;
+    if (lane == 31) {
+        nPL = (c_e > 0 && c_e < thr) ? 1u : 0u;
+        nO1 = c_e == 1 ? 1u : 0u;
+    }
+    uint32_t pPG = __shfl_up_sync(0xffffffffu, PG, 1) >> 31, pZ0 = __shfl_up_sync(0xffffffffu, Z0, 1) >> 31;
+    if (lane == 0) {
+        uint32_t c_left = 0;
+        if (s > 0 && !(s_prev & 2u) && !(S & 1u)) {  // P-1 and P are in the same query
+            const uint32_t mp = p.ms[s - 1] & 0x7fu;
+            if (mp > thr) {
+                const uint32_t eps0 = (E & 1u) ? (eps & 1u) : 0u;
+                const uint32_t op = parity_op(true, mp, mw[0] & 0xffu, k);
+                c_left = mp - ((op == OP_SET0) ? 0u : (eps0 ^ op));
+            } else {
+                c_left = c_first > 0 ? c_first - 1 : 0u;
+            }
+        }
+        pPG = c_left > thr ? 1u : 0u;
+        pZ0 = c_left == 0 ? 1u : 0u;
+    }
+    const uint32_t next_PL = (PL >> 1) | (nPL << 31), next_O1 = (O1 >> 1) | (nO1 << 31);
+    const uint32_t prev_PG = (PG << 1) | pPG, prev_Z0 = (Z0 << 1) | pZ0;
+    const uint32_t F01 = (S << 1) | (S << 2) | (s_prev >> 1) | ((s_prev & 2u)) | ((s_prev & 1u));
+    // (bit 0: sep(P-1) | sep(P-2); bit 1: sep(P) | sep(P-1))
+
+    // ---- translate_ms_vec (translate.rs:180-216,263-293) on the class masks ------------------------------------
+    const uint32_t V = ~S;
+    const uint32_t R = V & ~L & ((PG & next_PL) | (~F01 & prev_PG & PL));
+    const uint32_t X = V & ~R & Z0 & ~L & next_O1 & (F01 | ~prev_Z0);
+    const uint32_t dash = V & Z0 & ~X;
+
+    if (!CHARS) {
+        p.out_gap[P >> 5] = dash;
+        p.out_match[P >> 5] = V & ~Z0;  // 'M' or 'R'
+        p.out_r[P >> 5] = R;
+        return;
+    }
+
+    // ---- characters: padded layout in shared memory, then the runs between separators are copied out ---------
+    {
+        const uint32_t b0 = dash | R, b1 = X | R;
+        uint32_t* st = reinterpret_cast<uint32_t*>(&stage[warp][32 * lane]);
+        uint4 o;
+        o.x = lut[(b0 & 15u) | ((b1 & 15u) << 4)];
+        o.y = lut[((b0 >> 4) & 15u) | (((b1 >> 4) & 15u) << 4)];
+        o.z = lut[((b0 >> 8) & 15u) | (((b1 >> 8) & 15u) << 4)];
+        o.w = lut[((b0 >> 12) & 15u) | (((b1 >> 12) & 15u) << 4)];
+        *reinterpret_cast<uint4*>(st) = o;
+        o.x = lut[((b0 >> 16) & 15u) | (((b1 >> 16) & 15u) << 4)];
+        o.y = lut[((b0 >> 20) & 15u) | (((b1 >> 20) & 15u) << 4)];
+        o.z = lut[((b0 >> 24) & 15u) | (((b1 >> 24) & 15u) << 4)];
+        o.w = lut[((b0 >> 28) & 15u) | (((b1 >> 28) & 15u) << 4)];
+        *reinterpret_cast<uint4*>(st + 4) = o;
+    }
+    __syncwarp();
+    uint8_t* dst = p.out + p.off0 + s - __ldg(p.q.wq + (s >> 5));  // tile starts are word aligned
+    uint32_t seg = 0;  // start of the current run of non-separator positions (tile coordinates)
+    uint32_t has = __ballot_sync(0xffffffffu, S != 0);
+    while (has) {
+        const int l = __ffs((int)has) - 1;
+        has &= has - 1;
+        uint32_t sw = __shfl_sync(0xffffffffu, S, l);
+        while (sw) {
+            const uint32_t sp = 32u * l + (uint32_t)__ffs((int)sw) - 1u;
+            sw &= sw - 1;
+            if (sp > seg) {
+                warp_copy_out(stage[warp], seg, dst, sp - seg, lane);
+                dst += sp - seg;
+            }
+            seg = sp + 1;
+        }
+    }
+    if (seg < K2B_TILE) warp_copy_out(stage[warp], seg, dst, K2B_TILE - seg, lane);
+}
+
+// ---------------------------------------------------------------------------
 // K4: format::run_lengths_gapped (format.rs:143-193) on the PLAIN translation
-// K2 produces (alphabet M - X R only), one warp per query.  The warp walks the
-// query 32 characters per round; the four ballots of a round are consumed by
-// a warp-uniform state machine over the runs of gap / non-gap characters:
-//   a gap run inside a segment is "pending" until the next aligned character;
-//   it closes the segment as soon as it grows past max_gap_len, and a trailing
-//   gap run is dropped (format.rs:180-184).  jumps counts 'R' preceded by 'R'.
-// WRITE == false counts the segments of each query; after an exclusive scan of
-// the counts (rle_scan_kernel) WRITE == true stores the records in query order.
+// (alphabet M - X R only), data-parallel over the whole batch in padded space.
+//
+// Input: three bit masks per 32 positions ('-', match-like = M or R, 'R'), from
+// K2b<false> directly or from chars_to_masks_kernel.  N = not '-' and not a
+// separator.  The reference's state machine is equivalent to:
+//   * two aligned characters with only '-' between them belong to the same
+//     segment iff at most max_gap_len '-' separate them (D = max_gap_len + 1);
+//     leading / trailing '-' runs never belong to a segment (format.rs:180-184);
+//   * START[p] = N[p] and no N in [p-D, p-1] of the same query; END likewise;
+//   * a segment [ps, pe]: matches / mismatches / jumps / gap opens are counts of
+//     masks over [ps, pe], gap_bases = length - #N.  jumps counts 'R' preceded
+//     by 'R'; gap opens counts '-' preceded by N (a '-' run strictly inside).
+// With exclusive prefix counts per word (two library scans between the kernels)
+// every START / END test and every record is O(1):
+//   rle_word_counts -> scan -> rle_mark -> scan -> rle_query_offsets, rle_records.
+// Records are ordered by position, hence by query; the slot of a segment is the
+// number of STARTs before it.
 // ---------------------------------------------------------------------------
 struct RleRecord {
     uint64_t start, end, matches, mismatches, jumps, gap_bases, gap_opens;  // == kbo_rle
 };
 
-enum { RLE_STAGE = 8 };  // records per query kept in the staging buffer by the counting pass
-
-struct RleState {
-    uint64_t start, end;
-    uint32_t nm, nx, nj, gb, go, pend, prev_r, n_seg;
-    bool in_seg;
+struct RleCounts {  // per word; after the scan: counts before the word
+    uint32_t n, m, j, go;
+};
+struct RleCountsSum {
+    __host__ __device__ RleCounts operator()(const RleCounts& a, const RleCounts& b) const {
+        RleCounts c = {a.n + b.n, a.m + b.m, a.j + b.j, a.go + b.go};
+        return c;
+    }
 };
 
-// Stores one finished record: staging slot (counting pass) or final slot (write pass).
-template <bool WRITE>
-__device__ __forceinline__ void rle_emit(const RleState& st, int lane, RleRecord* __restrict__ dst, uint64_t slot0,
-                                         uint64_t cap) {
-    const uint64_t slot = slot0 + st.n_seg;
-    const bool ok = WRITE ? (slot < cap) : (st.n_seg < RLE_STAGE);
-    if (lane == 0 && ok) {
-        RleRecord rec = {st.start, st.end, st.nm, st.nx, st.nj, st.gb, st.go};
-        dst[slot] = rec;
+struct RleParams {
+    const uint32_t* gap;    // '-'                       (bit per padded position)
+    const uint32_t* match;  // 'M' or 'R'
+    const uint32_t* rr;     // 'R'
+    const uint32_t* sep;    // QueryView::sep
+    const uint32_t* wq;     // QueryView::wq
+    uint64_t n_words;       // words covered (a multiple of 32, >= ceil(Lp / 32))
+    const uint64_t* offsets;
+    uint64_t nq;
+    uint32_t window;        // D = max_gap_len + 1
+    uint32_t* jump;         // rle_word_counts out
+    uint32_t* gopen;
+    RleCounts* cnt;         // n_words + 1 entries; scanned in place
+    uint32_t* start;        // rle_mark out
+    uint32_t* end;
+    uint64_t* cse;          // n_words + 1 entries: #START | #END << 32; scanned in place
+    uint64_t* rle_offsets;  // nq + 1
+    RleRecord* out;
+    uint64_t cap;
+};
+
+__device__ __forceinline__ uint32_t low_mask(uint32_t b) { return b ? (~0u >> (32 - b)) : 0u; }  // bits below b (b < 32)
+
+// old K2 path / plain alignments: characters (unpadded) -> the three masks in padded space; thread per position
+__global__ void chars_to_masks_kernel(const uint8_t* __restrict__ aln, uint64_t off0, const uint32_t* __restrict__ sep,
+                                      const uint32_t* __restrict__ wq, uint64_t n_words, uint32_t* __restrict__ gap,
+                                      uint32_t* __restrict__ match, uint32_t* __restrict__ rr) {
+    const uint64_t pp = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;  // grid covers n_words * 32 exactly
+    const uint64_t w = pp >> 5;
+    const uint32_t b = (uint32_t)(pp & 31);
+    uint8_t ch = 0;
+    if (w < n_words) {
+        const uint32_t sw = __ldg(sep + w);
+        if (!((sw >> b) & 1u)) ch = aln[off0 + pp - __ldg(wq + w) - __popc(sw & low_mask(b))];
+    }
+    const uint32_t g = __ballot_sync(0xffffffffu, ch == '-');
+    const uint32_t m = __ballot_sync(0xffffffffu, ch == 'M' || ch == 'R');
+    const uint32_t r = __ballot_sync(0xffffffffu, ch == 'R');
+    if (b == 0 && w < n_words) {
+        gap[w] = g;
+        match[w] = m;
+        rr[w] = r;
     }
 }
 
-// One round of 32 characters (lane i holds character base+i; `nv` of them are valid).
-template <bool WRITE>
-__device__ __forceinline__ void rle_round(RleState& st, uint8_t ch, uint64_t base, uint32_t nv, uint32_t max_gap_len,
-                                          int lane, RleRecord* __restrict__ dst, uint64_t slot0, uint64_t cap) {
-    const uint32_t valid = nv == 32 ? 0xffffffffu : ((1u << nv) - 1u);
-    const uint32_t G = __ballot_sync(0xffffffffu, ch == '-') & valid;
-    const uint32_t N = valid & ~G;
-    const uint32_t Mm = __ballot_sync(0xffffffffu, ch == 'M' || ch == 'R' || ch == 'I') & N;
-    const uint32_t Rm = __ballot_sync(0xffffffffu, ch == 'R') & N;
-    const uint32_t J = Rm & ((Rm << 1) | st.prev_r);
-    st.prev_r = Rm >> 31;
-    if (G == 0 && nv == 32 && st.in_seg && st.pend == 0) {  // fast path: 32 aligned characters inside a segment
-        st.nm += __popc(Mm);
-        st.nx += __popc(~Mm);
-        st.nj += __popc(J);
-        st.end = base + 32;
+__device__ __forceinline__ uint32_t rle_nongap(const RleParams& p, uint64_t w) {
+    return ~__ldg(p.sep + w) & ~__ldg(p.gap + w);
+}
+
+// thread per word (+1): jump / gap-open masks and the four counts
+__global__ void rle_word_counts_kernel(RleParams p) {
+    const uint64_t w = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (w > p.n_words) return;
+    RleCounts c = {0, 0, 0, 0};
+    if (w < p.n_words) {
+        const uint32_t N = rle_nongap(p, w), R = __ldg(p.rr + w), Gp = __ldg(p.gap + w);
+        uint32_t n31 = 0, r31 = 0;
+        if (w > 0) {
+            n31 = rle_nongap(p, w - 1) >> 31;
+            r31 = __ldg(p.rr + w - 1) >> 31;
+        }
+        const uint32_t J = R & ((R << 1) | r31);    // 'R' preceded by 'R'          (format.rs:175-177)
+        const uint32_t GO = Gp & ((N << 1) | n31);  // '-' preceded by an aligned character
+        p.jump[w] = J;
+        p.gopen[w] = GO;
+        c.n = __popc(N);
+        c.m = __popc(__ldg(p.match + w));
+        c.j = __popc(J);
+        c.go = __popc(GO);
+    }
+    p.cnt[w] = c;
+}
+
+// number of aligned characters before padded position x (after the scan of cnt)
+__device__ __forceinline__ uint32_t rle_pref_n(const RleParams& p, uint64_t x) {
+    const uint64_t w = x >> 5;
+    uint32_t c = p.cnt[w].n;
+    const uint32_t b = (uint32_t)(x & 31);
+    if (b) c += __popc(rle_nongap(p, w) & low_mask(b));
+    return c;
+}
+__device__ __forceinline__ uint64_t rle_query_start(const RleParams& p, uint64_t q) {  // padded position of its first base
+    return p.offsets[q] - p.offsets[0] + q;
+}
+
+// thread per word (+1): START / END masks and their counts
+__global__ void rle_mark_kernel(RleParams p) {
+    const uint64_t w = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (w > p.n_words) return;
+    if (w == p.n_words) {
+        p.cse[w] = 0;
         return;
     }
-    uint32_t pos = 0;
-    while (pos < nv) {
-        if ((G >> pos) & 1u) {
-            const uint32_t rest = ~G >> pos;  // first zero of G at or after pos
-            uint32_t g = rest ? (uint32_t)(__ffs((int)rest) - 1) : 32u - pos;
-            if (g > nv - pos) g = nv - pos;
-            if (st.in_seg) {
-                st.pend += g;
-                if (st.pend > max_gap_len) {  // the gap outgrew max_gap_len: close without it
-                    rle_emit<WRITE>(st, lane, dst, slot0, cap);
-                    ++st.n_seg;
-                    st.in_seg = false;
-                    st.pend = 0;
-                }
-            }
-            pos += g;
-        } else {
-            const uint32_t rest = ~N >> pos;
-            uint32_t n = rest ? (uint32_t)(__ffs((int)rest) - 1) : 32u - pos;
-            if (n > nv - pos) n = nv - pos;
-            const uint32_t run = (n == 32 ? 0xffffffffu : ((1u << n) - 1u)) << pos;
-            if (!st.in_seg) {
-                st.in_seg = true;
-                st.start = base + pos;
-                st.nm = st.nx = st.nj = st.gb = st.go = 0;
-            } else if (st.pend) {
-                st.gb += st.pend;
-                st.go += 1;
-            }
-            st.pend = 0;
-            st.nm += __popc(Mm & run);
-            st.nx += __popc(N & ~Mm & run);
-            st.nj += __popc(J & run);
-            st.end = base + pos + n;
-            pos += n;
+    const uint32_t N = rle_nongap(p, w);
+    const uint32_t n31 = w > 0 ? rle_nongap(p, w - 1) >> 31 : 0u;
+    const uint32_t n0 = w + 1 < p.n_words ? rle_nongap(p, w + 1) & 1u : 0u;
+    uint32_t st = N & ~((N << 1) | n31);  // first character of a run of aligned characters
+    uint32_t en = N & ~((N >> 1) | (n0 << 31));
+    if (p.window > 1 && (st | en)) {
+        const uint32_t S = __ldg(p.sep + w);
+        const uint64_t q0 = __ldg(p.wq + w);
+        const uint64_t D = p.window;
+        uint32_t keep = 0;
+        for (uint32_t rem = st; rem; rem &= rem - 1) {
+            const uint32_t b = (uint32_t)__ffs((int)rem) - 1u;
+            const uint64_t pos = w * 32 + b;
+            const uint64_t qs = rle_query_start(p, q0 + __popc(S & low_mask(b)));
+            uint64_t lo = pos > D ? pos - D : 0;
+            if (lo < qs) lo = qs;
+            if (rle_pref_n(p, pos) == rle_pref_n(p, lo)) keep |= 1u << b;
         }
+        st = keep;
+        keep = 0;
+        for (uint32_t rem = en; rem; rem &= rem - 1) {
+            const uint32_t b = (uint32_t)__ffs((int)rem) - 1u;
+            const uint64_t pos = w * 32 + b;
+            const uint64_t qe = rle_query_start(p, q0 + __popc(S & low_mask(b)) + 1) - 1;  // its separator
+            uint64_t hi = pos + D + 1;  // exclusive
+            if (hi > qe) hi = qe;
+            if (rle_pref_n(p, hi) == rle_pref_n(p, pos + 1)) keep |= 1u << b;
+        }
+        en = keep;
     }
+    p.start[w] = st;
+    p.end[w] = en;
+    p.cse[w] = (uint64_t)__popc(st) | ((uint64_t)__popc(en) << 32);
 }
 
-// WRITE == false: count the segments of each query and keep the first RLE_STAGE records in `stage`.
-// WRITE == true : copy the staged records to their final slots; a query with more than RLE_STAGE
-//                 segments is recomputed and written directly.
-template <bool WRITE>
-__global__ void __launch_bounds__(128) rle_kernel(const uint8_t* __restrict__ aln, const uint64_t* __restrict__ offsets,
-                                                  uint64_t nq, uint32_t max_gap_len, uint32_t* __restrict__ counts,
-                                                  RleRecord* __restrict__ stage,
-                                                  const uint64_t* __restrict__ rle_offsets,
-                                                  RleRecord* __restrict__ out, uint64_t cap) {
-    const int lane = threadIdx.x & 31;
-    const uint64_t q = ((uint64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
-    if (q >= nq) return;  // warp-uniform
-    uint64_t slot0 = 0;
-    RleRecord* dst = stage + q * RLE_STAGE;
-    if (WRITE) {
-        slot0 = rle_offsets[q];
-        const uint32_t cnt = counts[q];
-        if (cnt <= RLE_STAGE) {  // common case: move the staged records (7 words each)
-            const uint64_t* src = reinterpret_cast<const uint64_t*>(stage + q * RLE_STAGE);
-            uint64_t* d64 = reinterpret_cast<uint64_t*>(out + slot0);
-            for (uint32_t w = lane; w < cnt * 7; w += 32)
-                if (slot0 + w / 7 < cap) d64[w] = src[w];
-            return;
-        }
-        dst = out;
+// thread per query (+1): records before the query = STARTs before its first base
+__global__ void rle_query_offsets_kernel(RleParams p) {
+    const uint64_t q = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (q > p.nq) return;
+    if (q == p.nq) {
+        p.rle_offsets[q] = (uint32_t)p.cse[p.n_words];
+        return;
     }
-    const uint64_t a = offsets[q] - offsets[0];
-    const uint64_t len = offsets[q + 1] - offsets[q];
-    RleState st;
-    st.start = st.end = 0;
-    st.nm = st.nx = st.nj = st.gb = st.go = st.pend = st.prev_r = st.n_seg = 0;
-    st.in_seg = false;
-    for (uint64_t base = 0; base < len; base += 128) {
-        // four rounds of loads in flight before the first ballot
-        uint8_t ch[4];
-#pragma unroll
-        for (int j = 0; j < 4; ++j) {
-            const uint64_t i = base + 32 * j + lane;
-            ch[j] = i < len ? aln[a + i] : 0;
-        }
-#pragma unroll
-        for (int j = 0; j < 4; ++j) {
-            const uint64_t b = base + 32 * j;
-            if (b < len) {
-                const uint32_t nv = len - b < 32 ? (uint32_t)(len - b) : 32u;
-                rle_round<WRITE>(st, ch[j], b, nv, max_gap_len, lane, dst, slot0, cap);
-            }
-        }
-    }
-    if (st.in_seg) {  // a trailing gap run is dropped
-        rle_emit<WRITE>(st, lane, dst, slot0, cap);
-        ++st.n_seg;
-    }
-    if (!WRITE && lane == 0) counts[q] = st.n_seg;
+    const uint64_t x = rle_query_start(p, q);
+    const uint32_t b = (uint32_t)(x & 31);
+    p.rle_offsets[q] = (uint32_t)p.cse[x >> 5] + (b ? __popc(p.start[x >> 5] & low_mask(b)) : 0);
 }
 
-// exclusive scan of the per-query segment counts -> rle_offsets[0..nq]; one block
-__global__ void __launch_bounds__(1024) rle_scan_kernel(const uint32_t* __restrict__ counts, uint64_t nq,
-                                                        uint64_t* __restrict__ rle_offsets) {
-    __shared__ uint64_t part[1024];
-    const uint32_t t = threadIdx.x;
-    const uint64_t per = (nq + 1023) / 1024;
-    const uint64_t lo = (uint64_t)t * per, hi = lo + per < nq ? lo + per : nq;
-    uint64_t s = 0;
-    for (uint64_t i = lo; i < hi; ++i) s += counts[i];
-    part[t] = s;
-    __syncthreads();
-    for (uint32_t off = 1; off < 1024; off <<= 1) {
-        uint64_t o = t >= off ? part[t - off] : 0;
-        __syncthreads();
-        part[t] += o;
-        __syncthreads();
+__device__ __forceinline__ RleCounts rle_pref_all(const RleParams& p, uint64_t x) {
+    const uint64_t w = x >> 5;
+    RleCounts c = p.cnt[w];
+    const uint32_t b = (uint32_t)(x & 31);
+    if (b) {
+        const uint32_t lm = low_mask(b);
+        c.n += __popc(rle_nongap(p, w) & lm);
+        c.m += __popc(__ldg(p.match + w) & lm);
+        c.j += __popc(p.jump[w] & lm);
+        c.go += __popc(p.gopen[w] & lm);
     }
-    uint64_t run = t ? part[t - 1] : 0;
-    for (uint64_t i = lo; i < hi; ++i) {
-        rle_offsets[i] = run;
-        run += counts[i];
+    return c;
+}
+
+// thread per word: one record per END bit
+__global__ void rle_records_kernel(RleParams p) {
+    const uint64_t w = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (w >= p.n_words) return;
+    uint32_t rem = p.end[w];
+    if (!rem) return;
+    const uint32_t S = __ldg(p.sep + w);
+    const uint64_t q0 = __ldg(p.wq + w);
+    uint32_t slot = (uint32_t)(p.cse[w] >> 32);
+    for (; rem; rem &= rem - 1, ++slot) {
+        if (slot >= p.cap) break;
+        const uint32_t b = (uint32_t)__ffs((int)rem) - 1u;
+        const uint64_t pe = w * 32 + b;
+        const uint64_t qs = rle_query_start(p, q0 + __popc(S & low_mask(b)));
+        // the START with the same rank: last word at or after the query's first whose prefix count is <= slot
+        uint64_t lo = qs >> 5, hi = w;
+        while (lo < hi) {
+            const uint64_t mid = (lo + hi + 1) >> 1;
+            if ((uint32_t)p.cse[mid] <= slot) lo = mid; else hi = mid - 1;
+        }
+        uint32_t sb = p.start[lo];
+        for (uint32_t skip = slot - (uint32_t)p.cse[lo]; skip; --skip) sb &= sb - 1;
+        const uint64_t ps = lo * 32 + (uint32_t)__ffs((int)sb) - 1u;
+        const RleCounts a = rle_pref_all(p, ps), z = rle_pref_all(p, pe + 1);
+        const uint32_t n = z.n - a.n, m = z.m - a.m;
+        RleRecord rec;
+        rec.start = ps - qs;
+        rec.end = pe + 1 - qs;
+        rec.matches = m;
+        rec.mismatches = n - m;
+        rec.jumps = z.j - a.j;
+        rec.gap_bases = (pe + 1 - ps) - n;
+        rec.gap_opens = z.go - a.go;
+        p.out[slot] = rec;
     }
-    if (t == 1023) rle_offsets[nq] = part[1023];
 }
 
 // ---------------------------------------------------------------------------

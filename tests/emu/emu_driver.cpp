@@ -23,6 +23,22 @@ using namespace kbo_b200;
 static uint32_t g_emu_probe_iters = 3;
 static uint32_t g_emu_flags = 0;
 extern "C" void emu_set_ms_flags(uint32_t v) { g_emu_flags = v; }
+static int g_emu_k2_mode = 0;  // 0: as the product dispatches, 1: always K2, 2: K2b (where supported)
+extern "C" void emu_set_k2_mode(int v) { g_emu_k2_mode = v; }
+
+// the product's K2 / K2b dispatch (capi.cu run_derand_translate)
+static void emu_run_translate(TrParams tp, const Geometry& g) {
+    const bool bits = g_emu_k2_mode != 1 && k2b_supported(tp.k, tp.thr);
+    if (bits) {
+        tp.n_tiles = g.n_tiles_b;
+        emu_launch_par((unsigned)((g.n_tiles_b + K2B_WARPS - 1) / K2B_WARPS), K2B_WARPS * 32,
+                       [&]() { derand_translate_bits_kernel<true>(tp); });
+    } else {
+        tp.n_tiles = g.n_tiles;
+        emu_launch_par((unsigned)((g.n_tiles + K2_WARPS - 1) / K2_WARPS), K2_WARPS * 32,
+                       [&]() { derand_translate_kernel(tp); });
+    }
+}
 extern "C" void emu_set_probe_iters(uint32_t v) { g_emu_probe_iters = v ? v : 1; }
 
 struct EmuIndex {
@@ -194,9 +210,7 @@ void emu_matches_batch(void* h, const uint8_t* concat, const uint64_t* offsets, 
     tp.thr = thr;
     tp.out = chars_out;
     tp.off0 = offsets[0];
-    tp.n_tiles = s.g.n_tiles;
-    const unsigned blocks = (unsigned)((s.g.n_tiles + K2_WARPS - 1) / K2_WARPS);
-    emu_launch_par(blocks, K2_WARPS * 32, [&]() { derand_translate_kernel(tp); });
+    emu_run_translate(tp, s.g);
 }
 
 // K2 alone on a caller-supplied u8 MS vector of ONE query (no separators except the final one)
@@ -214,8 +228,8 @@ void emu_derand_translate_u8(const uint8_t* ms, uint64_t n, uint32_t k, uint32_t
         pack_queries_kernel(ascii.data(), offsets, 1, qv, pack.data(), inv.data(), sep.data(), wq.data());
     });
     TrParams tp;
-    tp.ms = msbuf.data(); tp.q = qv; tp.k = k; tp.thr = thr; tp.out = chars_out; tp.off0 = 0; tp.n_tiles = g.n_tiles;
-    emu_launch_par((unsigned)((g.n_tiles + K2_WARPS - 1) / K2_WARPS), K2_WARPS * 32, [&]() { derand_translate_kernel(tp); });
+    tp.ms = msbuf.data(); tp.q = qv; tp.k = k; tp.thr = thr; tp.out = chars_out; tp.off0 = 0;
+    emu_run_translate(tp, g);
 }
 
 void emu_derandomize_general(const uint64_t* ms, uint64_t n, uint32_t k, uint32_t thr, int64_t* out) {
@@ -231,20 +245,84 @@ void emu_derandomize_general(const uint64_t* ms, uint64_t n, uint32_t k, uint32_
                    [&]() { g35_tile_kernel<true>(ms, n, k, thr, min_.data(), nullptr, eps.data(), out); });
 }
 
-// K4: run_lengths_gapped on plain translations, CSR batch; returns the number of records (out has `cap` slots of 7 u64)
+// K4 on masks in padded space (the product's run_rle; the two library scans are plain loops here)
+static uint64_t emu_run_rle(const uint32_t* gap, const uint32_t* match, const uint32_t* rr, const QueryView& qv,
+                            uint64_t n_words, const uint64_t* offsets, uint64_t nq, uint32_t max_gap_len,
+                            uint64_t* out7, uint64_t cap, uint64_t* rle_offsets) {
+    std::vector<uint32_t> jump(n_words), gopen(n_words), start(n_words), end(n_words);
+    std::vector<RleCounts> cnt(n_words + 1);
+    std::vector<uint64_t> cse(n_words + 1);
+    RleParams p;
+    p.gap = gap; p.match = match; p.rr = rr; p.sep = qv.sep; p.wq = qv.wq; p.n_words = n_words;
+    p.offsets = offsets; p.nq = nq; p.window = max_gap_len + 1;
+    p.jump = jump.data(); p.gopen = gopen.data(); p.cnt = cnt.data(); p.start = start.data(); p.end = end.data();
+    p.cse = cse.data(); p.rle_offsets = rle_offsets; p.out = (RleRecord*)out7; p.cap = cap;
+    const unsigned threads = 128, blocks = (unsigned)((n_words + 1 + threads - 1) / threads);
+    emu_launch_seq(blocks, threads, [&]() { rle_word_counts_kernel(p); });
+    RleCounts run = {0, 0, 0, 0};
+    for (uint64_t w = 0; w <= n_words; ++w) {
+        const RleCounts c = cnt[w];
+        cnt[w] = run;
+        run = RleCountsSum()(run, c);
+    }
+    emu_launch_seq(blocks, threads, [&]() { rle_mark_kernel(p); });
+    uint64_t acc = 0;
+    for (uint64_t w = 0; w <= n_words; ++w) {
+        const uint64_t c = cse[w];
+        cse[w] = acc;
+        acc += c;
+    }
+    emu_launch_seq((unsigned)((nq + 1 + threads - 1) / threads), threads, [&]() { rle_query_offsets_kernel(p); });
+    emu_launch_seq(blocks, threads, [&]() { rle_records_kernel(p); });
+    return rle_offsets[nq];
+}
+
+// K4 on plain translations (characters), CSR batch; returns the number of records (out has `cap` slots of 7 u64)
 uint64_t emu_rle_batch(const uint8_t* aln, const uint64_t* offsets, uint64_t nq, uint32_t max_gap_len, uint64_t* out7,
                        uint64_t cap, uint64_t* rle_offsets) {
-    std::vector<uint32_t> counts(nq);
-    std::vector<RleRecord> stage(nq * RLE_STAGE);
-    const unsigned threads = 128, blocks = (unsigned)((nq * 32 + threads - 1) / threads);
-    emu_launch_par(blocks, threads, [&]() {
-        rle_kernel<false>(aln, offsets, nq, max_gap_len, counts.data(), stage.data(), nullptr, nullptr, 0);
+    const Geometry g = make_geometry(offsets[nq] - offsets[0], nq, 0);
+    std::vector<uint64_t> pack(g.n_words);
+    std::vector<uint32_t> inv(g.n_words), sep(g.n_words), wq(g.n_words);
+    QueryView qv;
+    qv.pack = pack.data(); qv.inv = inv.data(); qv.sep = sep.data(); qv.wq = wq.data();
+    qv.Lp = g.Lp; qv.n_words = g.n_words;
+    emu_launch_seq((unsigned)((g.n_words + 127) / 128), 128,
+                   [&]() { pack_queries_kernel(aln, offsets, nq, qv, pack.data(), inv.data(), sep.data(), wq.data()); });
+    const uint64_t nw = g.n_tiles_b * 32;
+    std::vector<uint32_t> gap(nw), match(nw), rr(nw);
+    emu_launch_par((unsigned)(nw * 32 / 128), 128, [&]() {
+        chars_to_masks_kernel(aln, offsets[0], sep.data(), wq.data(), nw, gap.data(), match.data(), rr.data());
     });
-    emu_launch_par(1, 1024, [&]() { rle_scan_kernel(counts.data(), nq, rle_offsets); });
-    emu_launch_par(blocks, threads, [&]() {
-        rle_kernel<true>(aln, offsets, nq, max_gap_len, counts.data(), stage.data(), rle_offsets, (RleRecord*)out7, cap);
-    });
-    return rle_offsets[nq];
+    return emu_run_rle(gap.data(), match.data(), rr.data(), qv, nw, offsets, nq, max_gap_len, out7, cap, rle_offsets);
+}
+
+// K0 + K1 + K2b<masks> (or K2 + chars_to_masks) + K4: kbo::find for a CSR batch
+uint64_t emu_find_batch(void* h, const uint8_t* concat, const uint64_t* offsets, uint64_t nq, uint32_t thr,
+                        uint32_t max_gap_len, uint64_t* out7, uint64_t cap, uint64_t* rle_offsets) {
+    EmuIndex* e = (EmuIndex*)h;
+    Staged s;
+    stage_and_ms(e, concat + offsets[0], offsets, nq, 0, false, nullptr, &s);
+    const uint64_t nw = s.g.n_tiles_b * 32;
+    std::vector<uint32_t> gap(nw), match(nw), rr(nw);
+    TrParams tp;
+    tp.ms = s.ms.data(); tp.q = s.qv; tp.k = e->host.k; tp.thr = thr; tp.off0 = 0;
+    if (g_emu_k2_mode != 1 && k2b_supported(tp.k, tp.thr)) {
+        tp.out = nullptr;
+        tp.out_gap = gap.data(); tp.out_match = match.data(); tp.out_r = rr.data();
+        tp.n_tiles = s.g.n_tiles_b;
+        emu_launch_par((unsigned)((s.g.n_tiles_b + K2B_WARPS - 1) / K2B_WARPS), K2B_WARPS * 32,
+                       [&]() { derand_translate_bits_kernel<false>(tp); });
+    } else {
+        std::vector<uint8_t> chars(s.g.total + 16);
+        tp.out = chars.data();
+        emu_run_translate(tp, s.g);
+        emu_launch_par((unsigned)(nw * 32 / 128), 128, [&]() {
+            chars_to_masks_kernel(chars.data(), 0, s.qv.sep, s.qv.wq, nw, gap.data(), match.data(), rr.data());
+        });
+    }
+    std::vector<uint64_t> rel(nq + 1);
+    for (uint64_t i = 0; i <= nq; ++i) rel[i] = offsets[i] - offsets[0];
+    return emu_run_rle(gap.data(), match.data(), rr.data(), s.qv, nw, rel.data(), nq, max_gap_len, out7, cap, rle_offsets);
 }
 
 // ---- host refinement logic (refine_host.cpp) driven by emulated-kernel MS -------------------------
@@ -260,9 +338,7 @@ static void emu_single_ms(EmuIndex* e, const uint8_t* seq, uint64_t len, uint32_
         chars->assign(len + 16, 0);
         TrParams tp;
         tp.ms = s.ms.data(); tp.q = s.qv; tp.k = e->host.k; tp.thr = thr; tp.out = chars->data(); tp.off0 = 0;
-        tp.n_tiles = s.g.n_tiles;
-        emu_launch_par((unsigned)((s.g.n_tiles + K2_WARPS - 1) / K2_WARPS), K2_WARPS * 32,
-                       [&]() { derand_translate_kernel(tp); });
+        emu_run_translate(tp, s.g);
         chars->resize(len);
     }
 }

@@ -24,6 +24,8 @@ struct dim3 {
 struct uint4 {
     uint32_t x, y, z, w;
 };
+#include <cstdint>
+
 
 inline uint4 make_uint4(uint32_t x, uint32_t y, uint32_t z, uint32_t w) { return uint4{x, y, z, w}; }
 #define __align__(n) __attribute__((aligned(n)))

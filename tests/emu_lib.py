@@ -63,6 +63,8 @@ def lib():
                               C.c_uint32, C.c_int, u8p]
         L.emu_rle_batch.restype = C.c_uint64
         L.emu_rle_batch.argtypes = [u8p, u64p, C.c_uint64, C.c_uint32, u64p, C.c_uint64, u64p]
+        L.emu_find_batch.restype = C.c_uint64
+        L.emu_find_batch.argtypes = [C.c_void_p, u8p, u64p, C.c_uint64, C.c_uint32, C.c_uint32, u64p, C.c_uint64, u64p]
         _lib = L
     return _lib
 
@@ -174,6 +176,18 @@ class EmuIndex:
             raise RuntimeError("panic")
         return out.tobytes()
 
+    def find_batch(self, queries, thr, max_gap_len=0):
+        """K0+K1+K2b(masks)+K4; list (per query) of 7-tuples (start, end, matches, mismatches, jumps, gap_bases, gap_opens)."""
+        concat, offsets = csr(queries)
+        cap = len(concat) + 1
+        out = np.zeros(7 * cap, dtype=np.uint64)
+        roff = np.zeros(len(queries) + 1, dtype=np.uint64)
+        n = lib().emu_find_batch(self.h, _p(concat, C.c_uint8), _p(offsets, C.c_uint64), len(queries), thr, max_gap_len,
+                                 _p(out, C.c_uint64), cap, _p(roff, C.c_uint64))
+        assert n == roff[-1]
+        return [[tuple(int(x) for x in out[7 * j:7 * j + 7]) for j in range(int(roff[i]), int(roff[i + 1]))]
+                for i in range(len(queries))]
+
     def matches_batch(self, queries, thr, chunk_len=0):
         concat, offsets = csr(queries)
         out = np.zeros(len(concat), dtype=np.uint8)
@@ -193,6 +207,11 @@ def pack(concat, offsets):
     lib().emu_pack(_p(concat, C.c_uint8), _p(offsets, C.c_uint64), nq, _p(pk, C.c_uint64), _p(iv, C.c_uint32),
                    _p(sp, C.c_uint32), _p(wq, C.c_uint32))
     return pk, iv, sp, wq
+
+
+def set_k2_mode(mode):
+    """0: product dispatch, 1: always K2, 2: K2b where supported."""
+    lib().emu_set_k2_mode(int(mode))
 
 
 def derand_translate_u8(ms, k, thr):

@@ -116,6 +116,18 @@ def test_ms_tiny_index_and_counters():
 
 
 # -------------------------------------------------- K2: derandomize+translate ---
+@pytest.fixture(autouse=True, params=["dispatch", "k2-only"])
+def k2_mode(request):
+    """Tests that reach derandomize+translate run twice: product dispatch (K2b where it applies) and K2 alone."""
+    name = request.node.name
+    touches_k2 = any(t in name for t in ("k2", "matches", "map", "call", "find", "rle"))
+    if request.param == "k2-only" and not touches_k2:
+        pytest.skip("does not reach K2")
+    E.set_k2_mode(1 if request.param == "k2-only" else 0)
+    yield
+    E.set_k2_mode(0)
+
+
 def valid_ms_vector(rng, n, k, thr):
     """Random vector obeying ms[i+1] <= ms[i] + 1 with long flat / rising runs above and below thr."""
     out = np.zeros(n, dtype=np.int64)
@@ -134,10 +146,11 @@ def valid_ms_vector(rng, n, k, thr):
     return out
 
 
-@pytest.mark.parametrize("k,thr", [(3, 2), (31, 15), (31, 22), (31, 30), (63, 24), (7, 6)])
+@pytest.mark.parametrize("k,thr", [(3, 2), (31, 15), (31, 22), (31, 30), (63, 24), (7, 6), (31, 2), (127, 60), (128, 60),
+                                   (31, 31), (5, 3)])
 def test_k2_on_valid_ms(k, thr):
     rng = np.random.default_rng(k * 100 + thr)
-    for n in (3, 4, 31, 32, 33, 511, 512, 513, 1024, 5000):
+    for n in (3, 4, 31, 32, 33, 511, 512, 513, 1023, 1024, 1025, 2047, 2048, 5000):
         ms = valid_ms_vector(rng, n, k, thr)
         want = O.translate_ms_vec(O.derandomize_ms_vec(ms, k, thr), k, thr)
         got = E.derand_translate_u8(ms.astype(np.uint8), k, thr)
@@ -180,6 +193,29 @@ def test_matches_batch_matches_oracle(k, p):
         got = e.matches_batch(queries, thr, chunk_len)
         for g_, q in zip(got, queries):
             assert g_ == o.matches(q, p)
+
+
+@pytest.mark.parametrize("seed", [31, 32])
+def test_matches_batch_many_tiny_queries(seed):
+    """Separators in almost every word (3 bases is the shortest query the reference accepts, derandomize.rs:276),
+    queries around the word / tile sizes."""
+    k, p = 31, 1e-7
+    ref = np.frombuffer(rand_seq(30_000, 26), dtype=np.uint8)
+    o = O.OracleIndex([ref.tobytes()], k=k)
+    e = E.EmuIndex.build([ref.tobytes()], k=k)
+    thr = O.random_match_threshold(k, o.n_kmers, 4, p)
+    asm = synth.mutate(ref, 27).tobytes()
+    rng = np.random.default_rng(seed)
+    lens = [3, 3, 3, 4, 5, 31, 32, 33, 63, 64, 65, 1023, 1024, 1025, 3, 3, 3, 2047] + \
+           [int(x) for x in rng.integers(3, 90, 150)] + [int(x) for x in rng.integers(25, 400, 30)]
+    rng.shuffle(lens)
+    queries = []
+    for n in lens:
+        a = int(rng.integers(0, len(asm) - n))
+        queries.append(asm[a:a + n])
+    got = e.matches_batch(queries, thr, 64)
+    for g_, q in zip(got, queries):
+        assert g_ == o.matches(q, p)
 
 
 # -------------------------------------------- standalone derandomize / translate ---
@@ -238,6 +274,29 @@ def test_rle_kernel_random_plain_alignments():
             got = E.rle_batch(alns, gap)
             for g_, a in zip(got, alns):
                 assert g_ == O.run_lengths_gapped(a, gap), (gap, a[:80])
+
+
+@pytest.mark.parametrize("gap", [0, 3, 25, 100_000])
+def test_find_batch_matches_oracle(gap):
+    """K0+K1+K2b(masks)+K4 (or K2+chars_to_masks in k2-only mode) against kbo::find of the oracle."""
+    k, p = 31, 1e-7
+    ref = np.frombuffer(rand_seq(40_000, 41), dtype=np.uint8)
+    o = O.OracleIndex([ref.tobytes()], k=k)
+    e = E.EmuIndex.build([ref.tobytes()], k=k)
+    thr = O.random_match_threshold(k, o.n_kmers, 4, p)
+    genes, off = synth.gene_queries(ref, 30, 1000, 42)
+    queries = [genes[int(off[i]):int(off[i + 1])].tobytes() for i in range(30)]
+    asm = synth.mutate(ref, 43).tobytes()
+    queries += [asm[:7000], rand_seq(1500, 44), with_ns(asm[7000:9000], 45, 0.01), asm[9000:9003], asm[9100:9611],
+                asm[10_000:10_040] + rand_seq(30, 46) + asm[10_070:10_200] + rand_seq(300, 47) + asm[10_500:10_600],
+                rand_seq(40, 48) + asm[11_000:11_513] + rand_seq(33, 49)]
+    rng = np.random.default_rng(50)
+    for n in rng.integers(3, 120, 60):
+        a = int(rng.integers(0, len(asm) - 200))
+        queries.append(asm[a:a + int(n)])
+    got = e.find_batch(queries, thr, gap)
+    for i, (g_, q) in enumerate(zip(got, queries)):
+        assert g_ == o.find(q, p, gap), (gap, i)
 
 
 def test_ms_independent_of_probe_iters_and_flags():

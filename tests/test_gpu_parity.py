@@ -235,12 +235,37 @@ def test_matches_batch_matches_oracle(k, p):
     asm = synth.mutate(ref, 23).tobytes()
     queries += [asm[:30_000], rand_seq(5000, 24), with_ns(asm[30_000:34_000], 25, 0.01), asm[40_000:40_003],
                 asm[41_000:41_511], asm[42_000:42_512], asm[43_000:43_513], b"A" * 3000, b"AC" * 2000]
-    for chunk_len in (64, 0):
-        api.set_chunk_len(chunk_len)
-        got = api.matches_batch(queries, ix, api.MatchOpts(max_error_prob=p))
-        for i, (g_, q) in enumerate(zip(got, queries)):
-            assert g_ == o.matches(q, p), (k, p, chunk_len, i)
-    api.set_chunk_len(0)
+    want = [o.matches(q, p) for q in queries]
+    try:
+        for chunk_len, flags in ((64, 0), (0, 0), (0, 2)):  # flags bit1: K2 instead of the bit-parallel K2b
+            api.set_chunk_len(chunk_len)
+            api.set_ms_flags(flags)
+            got = api.matches_batch(queries, ix, api.MatchOpts(max_error_prob=p))
+            for i, (g_, w_) in enumerate(zip(got, want)):
+                assert g_ == w_, (k, p, chunk_len, flags, i)
+    finally:
+        api.set_chunk_len(0)
+        api.set_ms_flags(0)
+
+
+def test_matches_many_tiny_queries():
+    """Separators in almost every 32-position word; queries around the word and tile sizes."""
+    k, p = 31, 1e-7
+    ref = synth.random_seq(60_000, 26)
+    o = O.OracleIndex([ref.tobytes()], k=k)
+    ix = api.build([ref.tobytes()], api.BuildOpts(k=k))
+    asm = synth.mutate(ref, 27).tobytes()
+    rng = np.random.default_rng(31)
+    lens = [3, 3, 3, 4, 5, 31, 32, 33, 63, 64, 65, 1023, 1024, 1025, 3, 3, 3, 2047] + \
+           [int(x) for x in rng.integers(3, 90, 3000)] + [int(x) for x in rng.integers(25, 400, 300)]
+    rng.shuffle(lens)
+    queries = []
+    for n in lens:
+        a = int(rng.integers(0, len(asm) - n))
+        queries.append(asm[a:a + n])
+    got = api.matches_batch(queries, ix, api.MatchOpts(max_error_prob=p))
+    for i, (g_, q) in enumerate(zip(got, queries)):
+        assert g_ == o.matches(q, p), i
 
 
 def test_matches_preconditions():

@@ -127,6 +127,7 @@ struct kbo_index {
     HostIndex host;
     uint64_t* d_rank = nullptr;
     uint8_t* d_lcs = nullptr;
+    uint32_t* d_links = nullptr;  // per node: LCS and the distances to the nearest smaller LCS on both sides
     uint64_t rank_stride = 0;
     uint64_t device_bytes = 0;
     IndexView view;
@@ -205,6 +206,17 @@ static int host_threshold(uint64_t k, uint64_t n_kmers, uint64_t alphabet, doubl
 // ---------------------------------------------------------------------------
 // index upload: SubsetMatrix rows + LCS -> interleaved rank words + padded LCS
 // ---------------------------------------------------------------------------
+// links array (kernels.cuh IndexView::links) from the device LCS bytes; called by both builders
+static int build_links(kbo_index* ix, uint64_t n) {
+    CUDA_TRY(cudaMalloc((void**)&ix->d_links, (n + 1) * 4));
+    lcs_links_kernel<<<(unsigned)((n + 1 + 255) / 256), 256>>>(ix->d_lcs, (uint32_t)n, ix->d_links);
+    LAUNCHED();
+    CUDA_TRY(cudaGetLastError());
+    ix->view.links = ix->d_links;
+    ix->device_bytes += (n + 1) * 4;
+    return KBO_OK;
+}
+
 static int upload_index(kbo_index* ix) {
     const HostIndex& h = ix->host;
     const uint64_t n = h.n_sets;
@@ -226,7 +238,7 @@ static int upload_index(kbo_index* ix) {
     ix->view.lcs = ix->d_lcs;
     ix->view.n = (uint32_t)n;
     ix->view.k = h.k;
-    return KBO_OK;
+    return build_links(ix, n);
 }
 
 // ---------------------------------------------------------------------------
@@ -422,7 +434,7 @@ static int build_index_gpu(kbo_index* ix, const uint8_t* const* seqs, const uint
     ix->view.lcs = ix->d_lcs;
     ix->view.n = (uint32_t)n;
     ix->view.k = k;
-    return KBO_OK;
+    return build_links(ix, n);
 }
 
 // ---------------------------------------------------------------------------
@@ -819,6 +831,7 @@ void kbo_index_free(kbo_index* ix) {
         for (PinnedBuf& pb : ix->pinned_pool) if (pb.p) cudaFreeHost(pb.p);
         if (ix->d_rank) cudaFree(ix->d_rank);
         if (ix->d_lcs) cudaFree(ix->d_lcs);
+        if (ix->d_links) cudaFree(ix->d_links);
     }
     delete ix;
 }

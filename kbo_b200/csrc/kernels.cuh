@@ -38,11 +38,15 @@ namespace kbo_b200 {
 //          so extend_right needs ONE 8-byte load per interval end and a popc.
 //          Four consecutive words (128 positions) share a 32-byte L2 sector.
 //   lcs  : one byte per node, zero padded past n (sentinel for the right scan).
+//   links: one 32-bit word per node (and one for n): bits 0-7 LCS[q], bits 8-19 q - PSV(q), bits 20-31 NSV(q) - q,
+//          PSV / NSV = nearest position to the left / right whose LCS is smaller; 4095 = farther than that (or none).
+//          contract_left to the first depth that changes the interval is then two loads and a few additions.
 // ---------------------------------------------------------------------------
 struct IndexView {
     const uint64_t* rank;
     uint32_t rank_stride;  // words per row (< 2^28 for n_sets < 2^32)
     const uint8_t* lcs;
+    const uint32_t* links;  // n + 1 entries: LCS | distance to the previous smaller LCS << 8 | to the next smaller << 20
     uint32_t n;  // n_sets
     uint32_t k;
 };
@@ -177,23 +181,61 @@ struct MsParams {
     unsigned long long* counters;  // optional (COUNT)
 };
 
-__device__ __forceinline__ uint32_t popc_alu(uint32_t x) {
-    x = x - ((x >> 1) & 0x55555555u);
-    x = (x & 0x33333333u) + ((x >> 2) & 0x33333333u);
-    x = (x + (x >> 4)) & 0x0f0f0f0fu;
-    return (x * 0x01010101u) >> 24;
-}
-
 __device__ __forceinline__ uint64_t lcs_lt_mask64(uint64_t w, uint64_t t_rep) {
     // 0x80 in every byte of w that is < t (bytes and t are < 128)
     const uint64_t H = 0x8080808080808080ull;
     return ~((w | H) - t_rep) & H;
 }
 
-// Loop structure: `probe_iters` probe iterations (lanes whose extension failed sit out the rest of
-// the group), then ONE contraction phase executed together by every lane that failed.  The divergent
-// contraction code (~40 % of the static loop body, used by ~10 % of the lanes per iteration) is thus
-// issued once per group instead of once per iteration.  All position arithmetic is 32-bit.
+enum { LINK_FAR = 4095, LINK_SCAN_WORDS = 512 };
+
+// largest q <= from with LCS[q] < t (t >= 1; LCS[0] = 0 ends every scan).  Gives up after max_words 8-byte words
+// (returns 0xffffffff); max_words == 0: no limit.
+__device__ __noinline__ uint32_t lcs_scan_left(const uint8_t* __restrict__ lcs, uint32_t from, uint32_t t, uint32_t max_words) {
+    const uint64_t* __restrict__ L8 = reinterpret_cast<const uint64_t*>(lcs);
+    const uint64_t T = (uint64_t)t * 0x0101010101010101ull;
+    uint32_t b = from >> 3;
+    uint64_t m = lcs_lt_mask64(L8[b], T);
+    if ((from & 7) != 7) m &= (1ull << (8 * ((from & 7) + 1))) - 1ull;
+    for (uint32_t words = 1; m == 0; ++words) {
+        if (max_words && words >= max_words) return 0xffffffffu;
+        --b;
+        m = lcs_lt_mask64(L8[b], T);
+    }
+    return (b << 3) + ((63 - __clzll((long long)m)) >> 3);
+}
+// smallest q >= from with LCS[q] < t (the zero padding at n ends every scan)
+__device__ __noinline__ uint32_t lcs_scan_right(const uint8_t* __restrict__ lcs, uint32_t from, uint32_t t, uint32_t max_words) {
+    const uint64_t* __restrict__ L8 = reinterpret_cast<const uint64_t*>(lcs);
+    const uint64_t T = (uint64_t)t * 0x0101010101010101ull;
+    uint32_t b = from >> 3;
+    uint64_t m = lcs_lt_mask64(L8[b], T) & (~0ull << (8 * (from & 7)));
+    for (uint32_t words = 1; m == 0; ++words) {
+        if (max_words && words >= max_words) return 0xffffffffu;
+        ++b;
+        m = lcs_lt_mask64(L8[b], T);
+    }
+    return (b << 3) + ((__ffsll((long long)m) - 1) >> 3);
+}
+
+// links[q] for q in [0, n]; thread per node.  LCS values are < 128 (k <= 128).
+__global__ void lcs_links_kernel(const uint8_t* __restrict__ lcs, uint32_t n, uint32_t* __restrict__ links) {
+    const uint64_t q64 = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (q64 > n) return;
+    const uint32_t q = (uint32_t)q64;
+    const uint32_t v = q < n ? lcs[q] : 0u;
+    uint32_t dl = LINK_FAR, dr = LINK_FAR;
+    if (v > 0) {  // q >= 1 here because LCS[0] = 0
+        const uint32_t a = lcs_scan_left(lcs, q - 1, v, LINK_SCAN_WORDS);
+        if (a != 0xffffffffu && q - a < LINK_FAR) dl = q - a;
+        const uint32_t b = lcs_scan_right(lcs, q + 1, v, LINK_SCAN_WORDS);
+        if (b != 0xffffffffu && b - q < LINK_FAR) dr = b - q;
+    }
+    links[q] = v | (dl << 8) | (dr << 20);
+}
+
+// One extend attempt per loop iteration and lane.  A lane whose extension fails (at d > 0) contracts in the same
+// iteration -- two loads of `links` and a few additions -- and retries the base in the next one.
 template <bool INTERVALS, bool COUNT>
 __global__ void __launch_bounds__(256, 8) ms_kernel(MsParams p) {
     __shared__ __align__(16) uint8_t ms_stage[256 * 36];
@@ -217,127 +259,89 @@ __global__ void __launch_bounds__(256, 8) ms_kernel(MsParams p) {
         uint64_t qw = __ldg(qptr) >> (2 * bp);
         uint32_t iw = __ldg(iptr) >> bp;
         uint32_t l = 0, r = n, d = 0;
-        bool failed = false;
         // emitted MS bytes are staged in shared memory (36-byte stride per lane: conflict-free word access) and
         // flushed as two 16-byte stores per 32 positions; chunk starts are multiples of 32, so flushes are aligned
         uint8_t* const stg = ms_stage + threadIdx.x * 36u;
         while (bp < bp_end) {
-            // ---- probe phase ------------------------------------------------------------------
-#pragma unroll 1
-            for (uint32_t it = 0; it < p.probe_iters; ++it) {
-                if (failed || bp >= bp_end) continue;
-                bool advance;
-                if (iw & 1u) {
-                    l = 0; r = n; d = 0;
-                    advance = true;
-                } else {
-                    const uint32_t rowoff = ((uint32_t)qw & 3u) * p.ix.rank_stride;  // 32-bit word index
-                    const uint32_t bl = l >> 5, br = r >> 5;
-                    const uint64_t wl = __ldg(p.ix.rank + (rowoff + bl));
-                    const uint64_t wr = (br == bl) ? wl : __ldg(p.ix.rank + (rowoff + br));
-                    const uint32_t ml = (uint32_t)wl & ((1u << (l & 31)) - 1u), mr = (uint32_t)wr & ((1u << (r & 31)) - 1u);
-                    uint32_t nl, nr;
-                    if (p.flags & 1u) {
-                        nl = (uint32_t)(wl >> 32) + popc_alu(ml);
-                        nr = (uint32_t)(wr >> 32) + popc_alu(mr);
-                    } else {
-                        nl = (uint32_t)(wl >> 32) + __popc(ml);
-                        nr = (uint32_t)(wr >> 32) + __popc(mr);
-                    }
-                    if (COUNT) {
-                        const bool sp = (bl >> 2) != (br >> 2);
-                        ++cnt_att; cnt_split += sp;
-                        if (bp >= bp_emit) { ++cnt_att_e; cnt_split_e += sp; }
-                    }
-                    if (nl < nr) {
-                        l = nl; r = nr;
-                        d = d + 1 < k ? d + 1 : k;
-                        advance = true;
-                    } else if (d == 0) {
-                        advance = true;  // state stays (0,[0,n))
-                    } else {
-                        advance = false;
-                        failed = true;
-                    }
+            bool advance = true;
+            if (iw & 1u) {
+                l = 0; r = n; d = 0;
+            } else {
+                const uint32_t rowoff = ((uint32_t)qw & 3u) * p.ix.rank_stride;  // 32-bit word index
+                const uint32_t bl = l >> 5, br = r >> 5;
+                const uint64_t wl = __ldg(p.ix.rank + (rowoff + bl));
+                const uint64_t wr = (br == bl) ? wl : __ldg(p.ix.rank + (rowoff + br));
+                const uint32_t nl = (uint32_t)(wl >> 32) + __popc((uint32_t)wl & ((1u << (l & 31)) - 1u));
+                const uint32_t nr = (uint32_t)(wr >> 32) + __popc((uint32_t)wr & ((1u << (r & 31)) - 1u));
+                if (COUNT) {
+                    const bool sp = (bl >> 2) != (br >> 2);
+                    ++cnt_att; cnt_split += sp;
+                    if (bp >= bp_emit) { ++cnt_att_e; cnt_split_e += sp; }
                 }
-                if (advance) {
-                    if (COUNT) ++cnt_proc;
-                    if (bp >= bp_emit) {
-                        if (COUNT) ++cnt_emit;
-                        stg[bp & 31u] = (uint8_t)d;
-                        if (INTERVALS) {
-                            p.l_out[(wbase << 5) + bp] = l;
-                            p.r_out[(wbase << 5) + bp] = r;
+                if (nl < nr) {
+                    l = nl; r = nr;
+                    d = d + 1 < k ? d + 1 : k;
+                } else if (d != 0) {
+                    // contract_left to the largest depth that changes the interval: t = max(LCS[l], LCS[r])
+                    advance = false;
+                    const uint32_t el = __ldg(p.ix.links + l), er = __ldg(p.ix.links + r);
+                    const uint32_t vl = el & 0xffu, vr = er & 0xffu;
+                    uint32_t t = vl > vr ? vl : vr;
+                    if (COUNT) { ++cnt_con; if (bp >= bp_emit) ++cnt_con_e; }
+                    if (t == 0) {
+                        l = 0; r = n; d = 0;
+                    } else if (t > d - 1) {  // cannot happen for a maximal interval; keeps the literal bound
+                        t = d - 1;
+                        d = t;
+                        if (t == 0) { l = 0; r = n; }
+                        else { l = lcs_scan_left(p.ix.lcs, l, t, 0); r = lcs_scan_right(p.ix.lcs, r, t, 0); }
+                    } else {
+                        d = t;
+                        if (vl == t) {  // the left end moves to the previous position with a smaller LCS
+                            const uint32_t dl = (el >> 8) & 0xfffu;
+                            if (dl == LINK_FAR) {
+                                l = lcs_scan_left(p.ix.lcs, l - 1, t, 0);
+                                if (COUNT) { ++cnt_extra; cnt_extra_e += (bp >= bp_emit); }
+                            } else {
+                                l -= dl;
+                            }
                         }
-                    }
-                    ++bp;
-                    qw >>= 2;
-                    iw >>= 1;
-                    if ((bp & 31) == 0 || bp == bp_end) {
-                        if (bp > bp_emit) {  // flush the 32 (or last, partial) staged positions
-                            const uint32_t* w = reinterpret_cast<const uint32_t*>(stg);
-                            uint4* dst = reinterpret_cast<uint4*>(msw + ((bp - 1) & ~31u));
-                            dst[0] = make_uint4(w[0], w[1], w[2], w[3]);
-                            dst[1] = make_uint4(w[4], w[5], w[6], w[7]);
-                        }
-                        if (bp < bp_end) {
-                            qw = __ldg(qptr + (bp >> 5));
-                            iw = __ldg(iptr + (bp >> 5));
+                        if (vr == t) {
+                            const uint32_t dr = er >> 20;
+                            if (dr == LINK_FAR) {
+                                r = lcs_scan_right(p.ix.lcs, r + 1, t, 0);
+                                if (COUNT) { ++cnt_extra; cnt_extra_e += (bp >= bp_emit); }
+                            } else {
+                                r += dr;
+                            }
                         }
                     }
                 }
             }
-            // ---- contraction phase: contract_left to the largest target that changes the interval ----
-            if (failed) {
-                failed = false;
-                // 16 LCS cells on each side are requested at once (two aligned 8-byte words per side), so the
-                // scans below almost never need a further, dependent load
-                const uint64_t* __restrict__ L8 = reinterpret_cast<const uint64_t*>(p.ix.lcs);
-                const uint32_t wl_i = l >> 3, wr_i = r >> 3;
-                const uint64_t Wl1 = L8[wl_i];
-                const uint64_t Wl0 = L8[wl_i ? wl_i - 1 : 0];
-                const uint64_t Wr0 = (wr_i == wl_i) ? Wl1 : L8[wr_i];
-                const uint64_t Wr1 = L8[wr_i + 1];  // the zero padding past n makes this readable
-                if (COUNT) {
-                    ++cnt_con; cnt_extra += (wr_i != wl_i);
-                    if (bp >= bp_emit) { ++cnt_con_e; cnt_extra_e += (wr_i != wl_i); }
+            if (advance) {
+                if (COUNT) ++cnt_proc;
+                if (bp >= bp_emit) {
+                    if (COUNT) ++cnt_emit;
+                    stg[bp & 31u] = (uint8_t)d;
+                    if (INTERVALS) {
+                        p.l_out[(wbase << 5) + bp] = l;
+                        p.r_out[(wbase << 5) + bp] = r;
+                    }
                 }
-                const uint32_t vl = (uint32_t)(Wl1 >> (8 * (l & 7))) & 0xffu;
-                const uint32_t vr = (uint32_t)(Wr0 >> (8 * (r & 7))) & 0xffu;  // LCS[n] reads the zero padding
-                uint32_t t = vl > vr ? vl : vr;
-                if (t > d - 1) t = d - 1;  // cannot happen for a maximal interval; keeps the literal bound
-                if (t == 0) {
-                    l = 0; r = n; d = 0;
-                } else {
-                    d = t;
-                    const uint64_t T = (uint64_t)t * 0x0101010101010101ull;
-                    // left: largest q <= l with LCS[q] < t (LCS[0] = 0 stops the scan)
-                    uint64_t m = lcs_lt_mask64(Wl1, T);
-                    if ((l & 7) != 7) m &= (1ull << (8 * ((l & 7) + 1))) - 1ull;
-                    uint32_t b = wl_i;
-                    if (m == 0) {
-                        m = lcs_lt_mask64(Wl0, T);
-                        --b;
-                        while (m == 0) {
-                            --b;
-                            m = lcs_lt_mask64(L8[b], T);
-                            if (COUNT) { ++cnt_extra; cnt_extra_e += (bp >= bp_emit); }
-                        }
+                ++bp;
+                qw >>= 2;
+                iw >>= 1;
+                if ((bp & 31) == 0 || bp == bp_end) {
+                    if (bp > bp_emit) {  // flush the 32 (or last, partial) staged positions
+                        const uint32_t* w = reinterpret_cast<const uint32_t*>(stg);
+                        uint4* dst = reinterpret_cast<uint4*>(msw + ((bp - 1) & ~31u));
+                        dst[0] = make_uint4(w[0], w[1], w[2], w[3]);
+                        dst[1] = make_uint4(w[4], w[5], w[6], w[7]);
                     }
-                    l = (b << 3) + ((63 - __clzll((long long)m)) >> 3);
-                    // right: smallest q >= r with LCS[q] < t (the zero padding at n stops the scan)
-                    m = lcs_lt_mask64(Wr0, T) & (~0ull << (8 * (r & 7)));
-                    b = wr_i;
-                    if (m == 0) {
-                        m = lcs_lt_mask64(Wr1, T);
-                        ++b;
-                        while (m == 0) {
-                            ++b;
-                            m = lcs_lt_mask64(L8[b], T);
-                            if (COUNT) { ++cnt_extra; cnt_extra_e += (bp >= bp_emit); }
-                        }
+                    if (bp < bp_end) {
+                        qw = __ldg(qptr + (bp >> 5));
+                        iw = __ldg(iptr + (bp >> 5));
                     }
-                    r = (b << 3) + ((__ffsll((long long)m) - 1) >> 3);
                 }
             }
         }

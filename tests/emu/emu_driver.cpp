@@ -44,6 +44,7 @@ extern "C" void emu_set_probe_iters(uint32_t v) { g_emu_probe_iters = v ? v : 1;
 struct EmuIndex {
     HostIndex host;
     DeviceLayout lay;
+    std::vector<uint32_t> links;
     IndexView view;
 };
 
@@ -54,6 +55,11 @@ static void finish(EmuIndex* e) {
     e->view.lcs = e->lay.lcs.data();
     e->view.n = (uint32_t)e->host.n_sets;
     e->view.k = e->host.k;
+    const uint32_t n = e->view.n;
+    e->links.assign((size_t)n + 1, 0);
+    emu_launch_seq((unsigned)(((uint64_t)n + 1 + 255) / 256), 256,
+                   [&]() { lcs_links_kernel(e->lay.lcs.data(), n, e->links.data()); });
+    e->view.links = e->links.data();
 }
 
 struct Staged {

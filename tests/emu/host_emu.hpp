@@ -36,6 +36,7 @@ inline thread_local dim3 threadIdx, blockIdx, blockDim, gridDim;
 #define __device__
 #define __host__
 #define __forceinline__ inline
+#define __noinline__ inline
 #define __restrict__
 #define __launch_bounds__(...)
 #define __shared__ static

@@ -105,6 +105,22 @@ def test_ms_matches_oracle(k):
         check_ms(o, e, queries, chunk_len)
 
 
+def test_ms_wide_intervals_take_the_scan_path():
+    """Two-letter reference: a G/T in the query fails at every depth, so contract_left walks down to depths whose
+    intervals are wider than the 4095-node reach of the link array (kernels.cuh LINK_FAR) and falls back to scanning."""
+    rng = np.random.default_rng(5)
+    ref = np.frombuffer(b"AC", dtype=np.uint8)[rng.integers(0, 2, 30_000)].tobytes()
+    o = O.OracleIndex([ref], k=31)
+    e = E.EmuIndex.build([ref], k=31)
+    q = bytearray(ref[1000:5000])
+    for i in rng.integers(0, len(q), 150):
+        q[int(i)] = ord("GT"[int(i) & 1])
+    q2 = np.frombuffer(b"ACGT", dtype=np.uint8)[rng.choice(4, 3000, p=[0.45, 0.45, 0.05, 0.05])].tobytes()
+    check_ms(o, e, [bytes(q), q2, b"AAAAAAAAAAAAAAAAAAAAAAAAAAAAAAAAAAAAAAAAG" * 10], 64)
+    d, l, r, off, cnt = e.query_sbwt_batch([bytes(q), q2], chunk_len=64, counters=True)
+    assert cnt[3] > 0  # scans past the link reach did happen
+
+
 def test_ms_tiny_index_and_counters():
     o = O.OracleIndex([b"ACG"], k=3)
     e = E.EmuIndex.build([b"ACG"], k=3)

@@ -53,6 +53,7 @@ def parse_args():
     ap.add_argument("--chunk-len", type=int, default=0, help="MS chunk length (0 = automatic)")
     ap.add_argument("--probe-iters", type=int, default=0, help="K1 probe iterations per contraction phase (0 = default)")
     ap.add_argument("--ms-flags", type=int, default=0, help="K1 experiment switches")
+    ap.add_argument("--no-l2-persist", action="store_true", help="do not mark the index persisting in L2 (comparison)")
     ap.add_argument("--streams", type=int, default=4,
                     help="CUDA streams the device-resident steps are issued round-robin on (independent batches)")
     ap.add_argument("--e2e-threads", type=int, default=3,
@@ -237,6 +238,8 @@ def run_ours(args, rank, local_rank, world):
         api.set_probe_iters(args.probe_iters)
     if args.ms_flags:
         api.set_ms_flags(args.ms_flags)
+    if args.no_l2_persist:
+        api.set_l2_persist(False)
 
     ref, batches, offsets = workload(args, rank)
     hw = os.cpu_count() or 1

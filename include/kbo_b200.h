@@ -201,6 +201,8 @@ int kbo_set_device_parts(uint32_t parts);
 int kbo_set_pipeline_parts(uint32_t parts);
 /* Index construction runs on the GPU for 2 <= k <= 32; enabled != 0 forces the host builder (for comparison). */
 int kbo_set_host_builder(int enabled);
+/* enabled == 0: streams created afterwards do not mark the index arrays as persisting in L2 (comparison runs). */
+int kbo_set_l2_persist(int enabled);
 /* Tuning knob: probe iterations of K1 between two contraction phases (>= 1).  Results never depend on it. */
 int kbo_set_probe_iters(uint32_t iters);
 /* Experiment switches (bit 0: K1 population count on the ALU pipe; bit 1: K2 where the bit-parallel K2b would

@@ -32,6 +32,7 @@ static std::atomic<int> g_profile_counters(0);
 static std::atomic<uint32_t> g_chunk_len(0);
 static std::atomic<int> g_kernel_timing(0);
 static std::atomic<uint32_t> g_probe_iters(2);
+static std::atomic<int> g_l2_persist(1);  // 0: do not mark the index persisting in L2 (comparison runs)
 static std::atomic<uint32_t> g_ms_flags(0);
 static std::atomic<int> g_host_builder(0);
 static std::atomic<uint32_t> g_parts(0);
@@ -128,6 +129,9 @@ struct kbo_index {
     uint64_t* d_rank = nullptr;
     uint8_t* d_lcs = nullptr;
     uint32_t* d_links = nullptr;  // per node: LCS and the distances to the nearest smaller LCS on both sides
+    uint8_t* d_blob = nullptr;    // the one allocation holding rank | links | lcs (one L2 access-policy window)
+    uint64_t blob_bytes = 0;
+    float l2_hit_ratio = 0.f;     // 0: no persisting-L2 window available
     uint64_t rank_stride = 0;
     uint64_t device_bytes = 0;
     IndexView view;
@@ -137,6 +141,49 @@ struct kbo_index {
     kbo_ms_counters last_counters = {0, 0, 0, 0, 0, 0, 0, 0, 0, 0};
     float last_kernel_ms = 0.f;
 };
+
+// The index arrays live in ONE allocation so that a single access-policy window covers them: every stream that
+// runs K1 marks that range "persisting" in L2 (the streaming batch buffers of K0/K2/K4 would otherwise keep
+// evicting index lines, and a warp of K1 waits for the slowest of its ~60 random loads per iteration).
+static int alloc_index_arrays(kbo_index* ix, uint64_t rank_words, uint64_t lcs_bytes, uint64_t n) {
+    const uint64_t rank_bytes = rank_words * 8;
+    const uint64_t links_bytes = ((n + 1) * 4 + 255) & ~255ull;
+    ix->blob_bytes = rank_bytes + links_bytes + lcs_bytes;
+    CUDA_TRY(cudaMalloc((void**)&ix->d_blob, ix->blob_bytes));
+    ix->d_rank = reinterpret_cast<uint64_t*>(ix->d_blob);
+    ix->d_links = reinterpret_cast<uint32_t*>(ix->d_blob + rank_bytes);
+    ix->d_lcs = ix->d_blob + rank_bytes + links_bytes;
+    ix->device_bytes = ix->blob_bytes;
+    cudaDeviceProp prop;
+    int dev = 0;
+    if (cudaGetDevice(&dev) == cudaSuccess && cudaGetDeviceProperties(&prop, dev) == cudaSuccess &&
+        prop.persistingL2CacheMaxSize > 0 && prop.accessPolicyMaxWindowSize > 0) {
+        size_t want = std::min<size_t>((size_t)ix->blob_bytes, (size_t)prop.persistingL2CacheMaxSize);
+        size_t have = 0;
+        cudaDeviceGetLimit(&have, cudaLimitPersistingL2CacheSize);
+        if (have < want && cudaDeviceSetLimit(cudaLimitPersistingL2CacheSize, want) != cudaSuccess) want = have;
+        else if (have > want) want = std::min<size_t>(have, (size_t)ix->blob_bytes);
+        const size_t window = std::min<size_t>((size_t)ix->blob_bytes, (size_t)prop.accessPolicyMaxWindowSize);
+        ix->l2_hit_ratio = window ? (float)std::min(1.0, (double)want / (double)window) : 0.f;
+    }
+    cudaGetLastError();
+    return KBO_OK;
+}
+static void apply_l2_window(const kbo_index* ix, cudaStream_t st) {
+    if (!ix->d_blob || ix->l2_hit_ratio <= 0.f || g_l2_persist.load() == 0) return;
+    cudaDeviceProp prop;
+    int dev = 0;
+    if (cudaGetDevice(&dev) != cudaSuccess || cudaGetDeviceProperties(&prop, dev) != cudaSuccess) return;
+    cudaStreamAttrValue attr;
+    std::memset(&attr, 0, sizeof(attr));
+    attr.accessPolicyWindow.base_ptr = ix->d_blob;
+    attr.accessPolicyWindow.num_bytes = std::min<size_t>((size_t)ix->blob_bytes, (size_t)prop.accessPolicyMaxWindowSize);
+    attr.accessPolicyWindow.hitRatio = ix->l2_hit_ratio;
+    attr.accessPolicyWindow.hitProp = cudaAccessPropertyPersisting;
+    attr.accessPolicyWindow.missProp = cudaAccessPropertyStreaming;
+    cudaStreamSetAttribute(st, cudaStreamAttributeAccessPolicyWindow, &attr);
+    cudaGetLastError();  // best effort: the window is an optimisation
+}
 
 static int acquire_ws(kbo_index* ix, Workspace** out) {
     {
@@ -150,6 +197,7 @@ static int acquire_ws(kbo_index* ix, Workspace** out) {
     Workspace* ws = new Workspace();
     ws->own_stream = true;
     CUDA_TRY(cudaStreamCreateWithFlags(&ws->stream, cudaStreamNonBlocking));
+    apply_l2_window(ix, ws->stream);
     CUDA_TRY(cudaEventCreate(&ws->ev0));
     CUDA_TRY(cudaEventCreate(&ws->ev1));
     *out = ws;
@@ -166,6 +214,7 @@ static int stream_ws(kbo_index* ix, cudaStream_t st, Workspace** out) {
     Workspace* ws = new Workspace();
     ws->stream = st;
     ws->own_stream = false;
+    apply_l2_window(ix, st);
     ix->by_stream[st] = ws;
     *out = ws;
     return KBO_OK;
@@ -208,12 +257,10 @@ static int host_threshold(uint64_t k, uint64_t n_kmers, uint64_t alphabet, doubl
 // ---------------------------------------------------------------------------
 // links array (kernels.cuh IndexView::links) from the device LCS bytes; called by both builders
 static int build_links(kbo_index* ix, uint64_t n) {
-    CUDA_TRY(cudaMalloc((void**)&ix->d_links, (n + 1) * 4));
     lcs_links_kernel<<<(unsigned)((n + 1 + 255) / 256), 256>>>(ix->d_lcs, (uint32_t)n, ix->d_links);
     LAUNCHED();
     CUDA_TRY(cudaGetLastError());
     ix->view.links = ix->d_links;
-    ix->device_bytes += (n + 1) * 4;
     return KBO_OK;
 }
 
@@ -227,12 +274,10 @@ static int upload_index(kbo_index* ix) {
     const std::vector<uint64_t>& rank = lay.rank;
     const std::vector<uint8_t>& lcs = lay.lcs;
     const uint64_t stride = lay.stride;
-    CUDA_TRY(cudaMalloc((void**)&ix->d_rank, rank.size() * 8));
-    CUDA_TRY(cudaMalloc((void**)&ix->d_lcs, lcs.size()));
+    { int rc = alloc_index_arrays(ix, rank.size(), lcs.size(), n); if (rc) return rc; }
     CUDA_TRY(cudaMemcpy(ix->d_rank, rank.data(), rank.size() * 8, cudaMemcpyHostToDevice));
     CUDA_TRY(cudaMemcpy(ix->d_lcs, lcs.data(), lcs.size(), cudaMemcpyHostToDevice));
     ix->rank_stride = stride;
-    ix->device_bytes = rank.size() * 8 + lcs.size();
     ix->view.rank = ix->d_rank;
     ix->view.rank_stride = (uint32_t)stride;
     ix->view.lcs = ix->d_lcs;
@@ -377,8 +422,7 @@ static int build_index_gpu(kbo_index* ix, const uint8_t* const* seqs, const uint
     const uint64_t nblk = (n >> 5) + 2;
     const uint64_t stride = (nblk + 3) & ~3ull;
     const uint64_t lcs_bytes = ((n + 8) & ~7ull) + 16;
-    CUDA_TRY(cudaMalloc((void**)&ix->d_rank, 4 * stride * 8));
-    CUDA_TRY(cudaMalloc((void**)&ix->d_lcs, lcs_bytes));
+    { int rc = alloc_index_arrays(ix, 4 * stride, lcs_bytes, n); if (rc) return rc; }
     CUDA_TRY(cudaMemset(ix->d_lcs, 0, lcs_bytes));
     CUDA_TRY(tmp.alloc(&d_rows32, 4 * stride));
     CUDA_TRY(tmp.alloc(&d_pc, 4 * stride));
@@ -428,7 +472,6 @@ static int build_index_gpu(kbo_index* ix, const uint8_t* const* seqs, const uint
         CUDA_TRY(cudaMemcpy(h.node_len.data(), d_Plen, n, cudaMemcpyDeviceToHost));
     }
     ix->rank_stride = stride;
-    ix->device_bytes = 4 * stride * 8 + lcs_bytes;
     ix->view.rank = ix->d_rank;
     ix->view.rank_stride = (uint32_t)stride;
     ix->view.lcs = ix->d_lcs;
@@ -829,9 +872,7 @@ void kbo_index_free(kbo_index* ix) {
         for (Workspace* ws : ix->pool) { ws->destroy(); delete ws; }
         for (auto& kv : ix->by_stream) { kv.second->destroy(); delete kv.second; }
         for (PinnedBuf& pb : ix->pinned_pool) if (pb.p) cudaFreeHost(pb.p);
-        if (ix->d_rank) cudaFree(ix->d_rank);
-        if (ix->d_lcs) cudaFree(ix->d_lcs);
-        if (ix->d_links) cudaFree(ix->d_links);
+        if (ix->d_blob) cudaFree(ix->d_blob);
     }
     delete ix;
 }
@@ -1069,6 +1110,7 @@ static int matches_device_forked(kbo_index* ix, Workspace* ws, const uint8_t* d_
         sub->own_stream = true;
         ws->subs.push_back(sub);
         CUDA_TRY(cudaStreamCreateWithFlags(&sub->stream, cudaStreamNonBlocking));
+        apply_l2_window(ix, sub->stream);
         cudaEvent_t e;
         CUDA_TRY(cudaEventCreateWithFlags(&e, cudaEventDisableTiming));
         ws->ev_join.push_back(e);
@@ -1578,6 +1620,7 @@ int kbo_set_chunk_len(uint32_t chunk_len) { g_chunk_len = chunk_len; return KBO_
 int kbo_set_device_parts(uint32_t parts) { g_dev_parts = parts > 16 ? 16 : parts; return KBO_OK; }
 int kbo_set_pipeline_parts(uint32_t parts) { g_parts = parts > 64 ? 64 : parts; return KBO_OK; }
 int kbo_set_host_builder(int enabled) { g_host_builder = enabled ? 1 : 0; return KBO_OK; }
+int kbo_set_l2_persist(int enabled) { g_l2_persist = enabled ? 1 : 0; return KBO_OK; }
 int kbo_set_probe_iters(uint32_t iters) { g_probe_iters = iters ? iters : 1; return KBO_OK; }
 int kbo_set_ms_flags(uint32_t flags) {
     g_ms_flags = flags & 0xffu;

@@ -203,10 +203,7 @@ int kbo_set_pipeline_parts(uint32_t parts);
 int kbo_set_host_builder(int enabled);
 /* enabled == 0: streams created afterwards do not mark the index arrays as persisting in L2 (comparison runs). */
 int kbo_set_l2_persist(int enabled);
-/* Tuning knob: probe iterations of K1 between two contraction phases (>= 1).  Results never depend on it. */
-int kbo_set_probe_iters(uint32_t iters);
-/* Experiment switches (bit 0: K1 population count on the ALU pipe; bit 1: K2 where the bit-parallel K2b would
- * be picked).  Results never depend on them. */
+/* Experiment switches (bit 1: run K2 where the bit-parallel K2b would be picked).  Results never depend on them. */
 int kbo_set_ms_flags(uint32_t flags);
 /* Number of kernel launches issued by this library since load (for bench.py's gpu_launches). */
 uint64_t kbo_kernel_launch_count(void);

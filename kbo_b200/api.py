@@ -38,7 +38,7 @@ EXPORTED_SYMBOLS = [
     "kbo_index_access_kmer", "kbo_index_search", "kbo_query_sbwt", "kbo_query_sbwt_batch_compact",
     "kbo_log_rm_max_cdf", "kbo_random_match_threshold", "kbo_derandomize_ms_vec", "kbo_translate_ms_vec",
     "kbo_run_lengths_gapped", "kbo_relative_to_ref", "kbo_matches", "kbo_matches_batch", "kbo_matches_batch_device",
-    "kbo_find_batch", "kbo_find_batch_device", "kbo_map_unrefined", "kbo_call", "kbo_map", "kbo_set_profile_counters", "kbo_get_ms_counters", "kbo_set_chunk_len", "kbo_set_probe_iters", "kbo_set_l2_persist", "kbo_set_host_builder", "kbo_set_pipeline_parts", "kbo_set_device_parts", "kbo_set_ms_flags",
+    "kbo_find_batch", "kbo_find_batch_device", "kbo_map_unrefined", "kbo_call", "kbo_map", "kbo_set_profile_counters", "kbo_get_ms_counters", "kbo_set_chunk_len", "kbo_set_l2_persist", "kbo_set_host_builder", "kbo_set_pipeline_parts", "kbo_set_device_parts", "kbo_set_ms_flags",
     "kbo_kernel_launch_count", "kbo_last_kernel_ms", "kbo_set_kernel_timing", "kbo_collect_kernel_times",
     "kbo_measure_random_sector_rate",
 ]
@@ -122,7 +122,6 @@ def load_library():
     L.kbo_set_profile_counters.argtypes = [C.c_int]
     L.kbo_get_ms_counters.argtypes = [C.c_void_p, C.POINTER(MsCountersC)]
     L.kbo_set_chunk_len.argtypes = [C.c_uint32]
-    L.kbo_set_probe_iters.argtypes = [C.c_uint32]
     L.kbo_set_l2_persist.argtypes = [C.c_int]
     L.kbo_set_host_builder.argtypes = [C.c_int]
     L.kbo_set_pipeline_parts.argtypes = [C.c_uint32]
@@ -497,10 +496,6 @@ def set_profile_counters(enabled):
 
 def set_chunk_len(chunk_len):
     _check(load_library().kbo_set_chunk_len(int(chunk_len)))
-
-
-def set_probe_iters(iters):
-    _check(load_library().kbo_set_probe_iters(int(iters)))
 
 
 def set_device_parts(parts):

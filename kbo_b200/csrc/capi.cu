@@ -31,7 +31,6 @@ static std::atomic<uint64_t> g_launches(0);
 static std::atomic<int> g_profile_counters(0);
 static std::atomic<uint32_t> g_chunk_len(0);
 static std::atomic<int> g_kernel_timing(0);
-static std::atomic<uint32_t> g_probe_iters(2);
 static std::atomic<int> g_l2_persist(1);  // 0: do not mark the index persisting in L2 (comparison runs)
 static std::atomic<uint32_t> g_ms_flags(0);
 static std::atomic<int> g_host_builder(0);
@@ -540,7 +539,6 @@ static int run_ms(kbo_index* ix, Workspace* ws, const QueryView& qv, const Geome
     mp.ix = ix->view;
     mp.q = qv;
     mp.chunk_len = g.chunk_len;
-    mp.probe_iters = g_probe_iters.load();
     mp.flags = g_ms_flags.load();
     mp.n_chunks = g.n_chunks;
     mp.ms = ws->ms.as<uint8_t>();
@@ -1621,7 +1619,6 @@ int kbo_set_device_parts(uint32_t parts) { g_dev_parts = parts > 16 ? 16 : parts
 int kbo_set_pipeline_parts(uint32_t parts) { g_parts = parts > 64 ? 64 : parts; return KBO_OK; }
 int kbo_set_host_builder(int enabled) { g_host_builder = enabled ? 1 : 0; return KBO_OK; }
 int kbo_set_l2_persist(int enabled) { g_l2_persist = enabled ? 1 : 0; return KBO_OK; }
-int kbo_set_probe_iters(uint32_t iters) { g_probe_iters = iters ? iters : 1; return KBO_OK; }
 int kbo_set_ms_flags(uint32_t flags) {
     g_ms_flags = flags & 0xffu;
     const uint32_t blk = (flags >> 8) & 0x3ffu;  // bits 8..17: K1 block size (experiment)

@@ -171,9 +171,7 @@ struct MsParams {
     IndexView ix;
     QueryView q;
     uint32_t chunk_len;    // multiple of 32
-    uint32_t probe_iters;  // probe iterations per contraction phase (>= 1)
-    uint32_t flags;        // experiment switches: bit0 = population count on the ALU pipe instead of POPC (XU pipe);
-                           // bit1 (host side) = run K2 where K2b would be picked
+    uint32_t flags;        // experiment switches (none read by K1 at present; bit1 is host side: K2 instead of K2b)
     uint64_t n_chunks;
     uint8_t* ms;         // padded space, 1 byte per position
     uint32_t* l_out;     // optional (INTERVALS)

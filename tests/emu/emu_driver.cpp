@@ -20,7 +20,6 @@
 
 using namespace kbo_b200;
 
-static uint32_t g_emu_probe_iters = 3;
 static uint32_t g_emu_flags = 0;
 extern "C" void emu_set_ms_flags(uint32_t v) { g_emu_flags = v; }
 static int g_emu_k2_mode = 0;  // 0: as the product dispatches, 1: always K2, 2: K2b (where supported)
@@ -39,7 +38,6 @@ static void emu_run_translate(TrParams tp, const Geometry& g) {
                        [&]() { derand_translate_kernel(tp); });
     }
 }
-extern "C" void emu_set_probe_iters(uint32_t v) { g_emu_probe_iters = v ? v : 1; }
 
 struct EmuIndex {
     HostIndex host;
@@ -102,7 +100,6 @@ static void stage_and_ms(EmuIndex* e, const uint8_t* concat, const uint64_t* off
     mp.ix = e->view;
     mp.q = qv;
     mp.chunk_len = g.chunk_len;
-    mp.probe_iters = g_emu_probe_iters;
     mp.flags = g_emu_flags;
     mp.n_chunks = g.n_chunks;
     mp.ms = s->ms.data();

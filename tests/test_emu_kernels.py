@@ -315,22 +315,6 @@ def test_find_batch_matches_oracle(gap):
         assert g_ == o.find(q, p, gap), (gap, i)
 
 
-def test_ms_independent_of_probe_iters_and_flags():
-    ref = rand_seq(20_000, 31)
-    asm = synth.mutate(np.frombuffer(ref, dtype=np.uint8), 32).tobytes()
-    o = O.OracleIndex([asm], k=31)
-    e = E.EmuIndex.build([asm], k=31)
-    queries = [ref[:6000], with_ns(ref[6000:8000], 3, 0.02), rand_seq(500, 33)]
-    try:
-        for iters, flags in ((1, 0), (2, 1), (5, 0)):
-            E.lib().emu_set_probe_iters(iters)
-            E.lib().emu_set_ms_flags(flags)
-            check_ms(o, e, queries, 64)
-    finally:
-        E.lib().emu_set_probe_iters(3)
-        E.lib().emu_set_ms_flags(0)
-
-
 # ---------------------------------------------------------------------------
 # K0 alone: arbitrary bytes, empty queries, misaligned batch start
 # ---------------------------------------------------------------------------

@@ -59,8 +59,9 @@ def parse_args():
                     help="second timed region with this chunk length (0 = skip); only when --chunk-len is automatic")
     ap.add_argument("--streams", type=int, default=6,
                     help="CUDA streams the device-resident steps are issued round-robin on (independent batches)")
-    ap.add_argument("--e2e-threads", type=int, default=3,
+    ap.add_argument("--e2e-threads", type=int, default=6,
                     help="host threads issuing the end-to-end calls concurrently (kbo-cli style per-query threading)")
+    ap.add_argument("--pipeline-parts", type=int, default=0, help="sub-batches of a host-buffer call (0 = automatic)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--cpu-seconds", type=float, default=20.0, help="target CPU work (core-seconds) of the cpu_baseline sample")
     return ap.parse_args()
@@ -241,6 +242,8 @@ def run_ours(args, rank, local_rank, world):
         api.set_ms_flags(args.ms_flags)
     if args.no_l2_persist:
         api.set_l2_persist(False)
+    if args.pipeline_parts:
+        api.set_pipeline_parts(args.pipeline_parts)
 
     ref, batches, offsets = workload(args, rank)
     hw = os.cpu_count() or 1
@@ -338,7 +341,12 @@ def run_ours(args, rank, local_rank, world):
     value = world * args.steps * bases_per_step / (ms_max * 1e-3)
 
     # ---- e2e: host buffers through the public C ABI call (H2D + kernels + D2H + RLE) -----------
-    pinned_np = [p.numpy() for p in pinned_in]
+    # host batches in memory from the library's own pinned allocator (cudaHostAlloc); measured on this box:
+    # copies from it run at 51-55 GB/s, copies from torch's pin_memory() buffers at 11-27 GB/s
+    pinned_keep = [api.PinnedBytes(len(b)) for b in batches]
+    for pb, b in zip(pinned_keep, batches):
+        pb.array[:] = b
+    pinned_np = [pb.array for pb in pinned_keep]
     n_thr = max(1, args.e2e_threads)
     fbufs = [api.FindBuffers(nq) for _ in range(n_thr)]
     n_rle_box = [0] * n_thr
@@ -434,7 +442,8 @@ def run_ours(args, rank, local_rank, world):
                         "h2d_bytes_per_step": bases_per_step + 8 * (nq + 1),
                         "d2h_bytes_per_step": 8 * (nq + 1) + 56 * n_rle,
                         "api": "kbo_find_batch: pinned host queries in, RLE records + per-query offsets out "
-                               "(matches and run lengths computed on the device; sub-batches pipelined on 4 streams); "
+                               "(matches and run lengths computed on the device; one stream per call when several host threads call "
+                               "concurrently, else up to 4 pipelined sub-batches); "
                                "%d steps issued by %d host threads" % (e2e_steps, n_thr)},
                 "gpu_launches": int(lt.item()), "roofline": roof}
         if cpu is not None:

@@ -425,6 +425,25 @@ def find_batch(queries, index, find_opts=None):
     return res
 
 
+class PinnedBytes:
+    """Page-locked host bytes from kbo_alloc_pinned (cudaHostAlloc); `.array` is a numpy view.  Host-buffer entry
+    points copy from / to such memory asynchronously and at full PCIe rate."""
+
+    def __init__(self, nbytes):
+        p = C.c_void_p()
+        _check(load_library().kbo_alloc_pinned(int(nbytes), C.byref(p)))
+        self._p = p
+        self.array = np.ctypeslib.as_array((C.c_uint8 * int(nbytes)).from_address(p.value))
+
+    def __del__(self):
+        try:
+            if self._p:
+                load_library().kbo_free_pinned(self._p)
+                self._p = None
+        except Exception:
+            pass
+
+
 class FindBuffers:
     """Reusable output buffers for find_csr (avoids reallocating per call in a timed loop)."""
 

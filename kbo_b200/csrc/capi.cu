@@ -124,6 +124,8 @@ struct Workspace {
 struct kbo_index {
     int device = 0;
     std::vector<PinnedBuf> pinned_pool;  // host staging for find (guarded by mu)
+    std::atomic<int> host_calls{0};      // host-buffer batch calls currently inside the library (any thread)
+    std::atomic<bool> seen_concurrency{false};  // some host-buffer call found another caller inside (sticky)
     HostIndex host;
     uint64_t* d_rank = nullptr;
     uint8_t* d_lcs = nullptr;
@@ -1022,6 +1024,57 @@ static int matches_prologue(kbo_index* ix, const uint64_t* offsets, uint64_t nq,
 
 static std::vector<uint64_t> split_queries(const uint64_t* offsets, uint64_t nq, uint64_t parts);
 
+// Sizes every buffer of a workspace for a WHOLE host call (not for the sub-batch it will run), so that a
+// workspace never has to be regrown -- cudaFree synchronises the device -- when calls alternate between one and
+// several sub-batches.
+static int reserve_ws(Workspace* ws, uint64_t total, uint64_t nq, bool for_find) {
+    cudaStream_t st = ws->stream;
+    const Geometry g = make_geometry(total, nq);
+    const uint64_t nw = g.n_tiles_b * 32;
+    CUDA_TRY(ws->ascii.ensure(total, st));
+    CUDA_TRY(ws->offsets.ensure((nq + 1) * 8, st));
+    CUDA_TRY(ws->pack.ensure(g.n_words * 8, st));
+    CUDA_TRY(ws->inv.ensure(g.n_words * 4, st));
+    CUDA_TRY(ws->sep.ensure(g.n_words * 4, st));
+    CUDA_TRY(ws->wq.ensure(g.n_words * 4, st));
+    CUDA_TRY(ws->ms.ensure(g.ms_bytes, st));
+    if (for_find) {
+        CUDA_TRY(ws->masks.ensure(nw * 3 * 4, st));
+        CUDA_TRY(ws->rle_words.ensure(nw * 4 * 4, st));
+        CUDA_TRY(ws->rle_cnt.ensure((nw + 1) * sizeof(RleCounts), st));
+        CUDA_TRY(ws->rle_cse.ensure((nw + 1) * 8, st));
+        CUDA_TRY(ws->tmp64.ensure((nq + 1) * 8, st));
+        CUDA_TRY(ws->h_rel.ensure((nq + 1) * 8));
+        CUDA_TRY(ws->h_roff.ensure((nq + 1) * 8));
+    } else {
+        CUDA_TRY(ws->out.ensure(total + 16, st));
+    }
+    return KBO_OK;
+}
+
+// Number of sub-batches a host-buffer batch call is cut into.  A lone caller overlaps its own copy-in with its
+// kernels by pipelining sub-batches; when other host threads are inside the library at the same time their calls
+// already overlap each other, and further splitting only multiplies driver calls (measured: 3 threads 40 vs 28 G
+// bases/s, 6 threads 46 vs 31 G bases/s with 1 vs 4 sub-batches).
+struct HostCallScope {
+    kbo_index* ix;
+    bool concurrent;  // this index is (or has been) used from several host threads at once; sticky, so that the
+                      // choice below does not flip back and forth
+    explicit HostCallScope(kbo_index* i) : ix(i) {
+        if (i->host_calls.fetch_add(1) > 0) i->seen_concurrency.store(true);
+        concurrent = i->seen_concurrency.load();
+    }
+    ~HostCallScope() { ix->host_calls.fetch_sub(1); }
+};
+static uint64_t pick_parts(const HostCallScope& scope, uint64_t total) {
+    if (g_profile_counters.load()) return 1;
+    if (g_parts.load()) return g_parts.load();
+    if (scope.concurrent) return 1;
+    return std::min<uint64_t>(4, std::max<uint64_t>(1, total >> 21));
+}
+
+
+
 // kbo::matches for a host CSR batch; large batches are pipelined over sub-batches on separate streams
 // (copy-in of part i+1 and copy-out of part i-1 overlap the kernels of part i).
 int kbo_matches_batch(const kbo_index* cix, const uint8_t* concat, const uint64_t* offsets, uint64_t n_queries,
@@ -1034,12 +1087,15 @@ int kbo_matches_batch(const kbo_index* cix, const uint8_t* concat, const uint64_
     if (rc) return rc;
     DeviceGuard dg(ix->device);
     if (!dg.ok) return fail(KBO_ERR_CUDA, "cudaSetDevice failed");
-    const uint64_t want_parts = g_profile_counters.load() ? 1 : (g_parts.load() ? g_parts.load() : std::min<uint64_t>(4, std::max<uint64_t>(1, total >> 21)));
+    const HostCallScope scope(ix);
+    const uint64_t want_parts = pick_parts(scope, total);
     const std::vector<uint64_t> cut = split_queries(offsets, n_queries, want_parts);
     const size_t np = cut.size() - 1;
     std::vector<Workspace*> wss(np, nullptr);
     for (size_t s = 0; s < np && !rc; ++s) {
         rc = acquire_ws(ix, &wss[s]);
+        if (rc) break;
+        rc = reserve_ws(wss[s], total, n_queries, false);
         if (rc) break;
         Workspace* ws = wss[s];
         cudaStream_t st = ws->stream;
@@ -1239,7 +1295,8 @@ int kbo_find_batch(const kbo_index* cix, const uint8_t* concat, const uint64_t* 
     const uint32_t gap = (uint32_t)std::min<uint64_t>(max_gap_len, 0x7fffffffull);
     DeviceGuard dg(ix->device);
     if (!dg.ok) return fail(KBO_ERR_CUDA, "cudaSetDevice failed");
-    const uint64_t want_parts = g_profile_counters.load() ? 1 : (g_parts.load() ? g_parts.load() : std::min<uint64_t>(4, std::max<uint64_t>(1, total >> 21)));
+    const HostCallScope scope(ix);
+    const uint64_t want_parts = pick_parts(scope, total);
     const std::vector<uint64_t> cut = split_queries(offsets, n_queries, want_parts);
     const size_t np = cut.size() - 1;
     std::vector<Workspace*> wss(np, nullptr);
@@ -1247,6 +1304,8 @@ int kbo_find_batch(const kbo_index* cix, const uint8_t* concat, const uint64_t* 
     // phase 1: enqueue copy-in, K0, K1, K2b (masks), K4 up to the per-query offsets, and their copy-out
     for (size_t s = 0; s < np && !rc; ++s) {
         rc = acquire_ws(ix, &wss[s]);
+        if (rc) break;
+        rc = reserve_ws(wss[s], total, n_queries, true);
         if (rc) break;
         Workspace* ws = wss[s];
         cudaStream_t st = ws->stream;

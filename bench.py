@@ -54,6 +54,7 @@ def parse_args():
     ap.add_argument("--batches", type=int, default=16, help="distinct batches rotated through (16 x 10 MB > L2)")
     ap.add_argument("--chunk-len", type=int, default=0, help="MS chunk length (0 = automatic)")
     ap.add_argument("--ms-flags", type=int, default=0, help="experiment switches (2: K2 instead of K2b)")
+    ap.add_argument("--no-prefix-table", action="store_true", help="build the index without the prefix-state table (comparison)")
     ap.add_argument("--no-l2-persist", action="store_true", help="do not mark the index persisting in L2 (comparison)")
     ap.add_argument("--tuned-chunk-len", type=int, default=192,
                     help="second timed region with this chunk length (0 = skip); only when --chunk-len is automatic")
@@ -242,6 +243,8 @@ def run_ours(args, rank, local_rank, world):
         api.set_ms_flags(args.ms_flags)
     if args.no_l2_persist:
         api.set_l2_persist(False)
+    if args.no_prefix_table:
+        api.set_prefix_table(False)
     if args.pipeline_parts:
         api.set_pipeline_parts(args.pipeline_parts)
 
@@ -364,8 +367,9 @@ def run_ours(args, rank, local_rank, world):
             th.join()
         torch.cuda.synchronize()
 
-    # warm-up with the same concurrency, so that every workspace the timed region needs already exists
-    run_threads(0, max(args.warmup, 3) * n_thr)
+    # warm-up with the same concurrency until every workspace the timed region needs exists at its final size
+    # (the library creates them lazily, one per concurrent call; measured: the first ~50 calls carry that cost)
+    run_threads(0, max(args.warmup, 16) * n_thr)
     barrier()
     e2e_steps = args.steps
     w0 = time.perf_counter()

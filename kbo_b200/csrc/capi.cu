@@ -31,6 +31,7 @@ static std::atomic<uint64_t> g_launches(0);
 static std::atomic<int> g_profile_counters(0);
 static std::atomic<uint32_t> g_chunk_len(0);
 static std::atomic<int> g_kernel_timing(0);
+static std::atomic<int> g_prefix_table(1);  // 0: indexes built afterwards get no prefix-state table (comparison runs)
 static std::atomic<int> g_l2_persist(1);  // 0: do not mark the index persisting in L2 (comparison runs)
 static std::atomic<uint32_t> g_ms_flags(0);
 static std::atomic<int> g_host_builder(0);
@@ -131,6 +132,7 @@ struct kbo_index {
     uint8_t* d_lcs = nullptr;
     uint32_t* d_links = nullptr;  // per node: LCS and the distances to the nearest smaller LCS on both sides
     uint8_t* d_blob = nullptr;    // the one allocation holding rank | links | lcs (one L2 access-policy window)
+    uint4* d_pref = nullptr;      // MS states after PREF_LEN bases (k >= PREF_MIN_K)
     uint64_t blob_bytes = 0;
     float l2_hit_ratio = 0.f;     // 0: no persisting-L2 window available
     uint64_t rank_stride = 0;
@@ -262,6 +264,28 @@ static int build_links(kbo_index* ix, uint64_t n) {
     LAUNCHED();
     CUDA_TRY(cudaGetLastError());
     ix->view.links = ix->d_links;
+    ix->view.pref = nullptr;
+    if (ix->view.k >= PREF_MIN_K && g_prefix_table.load()) {
+        // states after 1, 2, ... PREF_LEN bases, level by level (odd levels in `a`, even levels in `b`; the last is kept)
+        const size_t last = (size_t)1 << (2 * PREF_LEN);
+        uint4 *a = nullptr, *b = nullptr;
+        CUDA_TRY(cudaMalloc((void**)&a, (last / 4) * sizeof(uint4)));
+        CUDA_TRY(cudaMalloc((void**)&b, last * sizeof(uint4)));
+        static_assert(PREF_LEN % 2 == 0, "the last level must land in the large buffer");
+        for (uint32_t j = 1; j <= PREF_LEN; ++j) {
+            const uint32_t cnt = 1u << (2 * j);
+            uint4* cur = (j & 1) ? a : b;
+            const uint4* prev = (j & 1) ? b : a;
+            prefix_table_level_kernel<<<(cnt + 255) / 256, 256>>>(ix->view, prev, cur, j);
+            LAUNCHED();
+        }
+        CUDA_TRY(cudaGetLastError());
+        CUDA_TRY(cudaDeviceSynchronize());
+        cudaFree(a);
+        ix->d_pref = b;
+        ix->view.pref = b;
+        ix->device_bytes += last * sizeof(uint4);
+    }
     return KBO_OK;
 }
 
@@ -873,6 +897,7 @@ void kbo_index_free(kbo_index* ix) {
         for (auto& kv : ix->by_stream) { kv.second->destroy(); delete kv.second; }
         for (PinnedBuf& pb : ix->pinned_pool) if (pb.p) cudaFreeHost(pb.p);
         if (ix->d_blob) cudaFree(ix->d_blob);
+        if (ix->d_pref) cudaFree(ix->d_pref);
     }
     delete ix;
 }
@@ -1677,6 +1702,7 @@ int kbo_set_chunk_len(uint32_t chunk_len) { g_chunk_len = chunk_len; return KBO_
 int kbo_set_device_parts(uint32_t parts) { g_dev_parts = parts > 16 ? 16 : parts; return KBO_OK; }
 int kbo_set_pipeline_parts(uint32_t parts) { g_parts = parts > 64 ? 64 : parts; return KBO_OK; }
 int kbo_set_host_builder(int enabled) { g_host_builder = enabled ? 1 : 0; return KBO_OK; }
+int kbo_set_prefix_table(int enabled) { g_prefix_table = enabled ? 1 : 0; return KBO_OK; }
 int kbo_set_l2_persist(int enabled) { g_l2_persist = enabled ? 1 : 0; return KBO_OK; }
 int kbo_set_ms_flags(uint32_t flags) {
     g_ms_flags = flags & 0xffu;

@@ -41,12 +41,15 @@ namespace kbo_b200 {
 //   links: one 32-bit word per node (and one for n): bits 0-7 LCS[q], bits 8-19 q - PSV(q), bits 20-31 NSV(q) - q,
 //          PSV / NSV = nearest position to the left / right whose LCS is smaller; 4095 = farther than that (or none).
 //          contract_left to the first depth that changes the interval is then two loads and a few additions.
+//   pref : for k >= PREF_MIN_K, the MS state after any string of PREF_LEN = 10 bases (index: first base in the low bits);
+//          a chunk's warm-up starts from this entry instead of stepping through its first ten bases.
 // ---------------------------------------------------------------------------
 struct IndexView {
     const uint64_t* rank;
     uint32_t rank_stride;  // words per row (< 2^28 for n_sets < 2^32)
     const uint8_t* lcs;
     const uint32_t* links;  // n + 1 entries: LCS | distance to the previous smaller LCS << 8 | to the next smaller << 20
+    const uint4* pref;      // optional: MS state (l, r, d, -) after PREF_LEN bases fed to the empty state, 4^PREF_LEN entries
     uint32_t n;  // n_sets
     uint32_t k;
 };
@@ -232,10 +235,73 @@ __global__ void lcs_links_kernel(const uint8_t* __restrict__ lcs, uint32_t n, ui
     links[q] = v | (dl << 8) | (dr << 20);
 }
 
+// contract_left to the largest depth that changes the interval, t = max(LCS[l], LCS[r]), given the link words of
+// l and r.  Returns true when an end was farther than the links reach and had to be found by scanning.
+__device__ __forceinline__ bool ms_contract(const IndexView& ix, uint32_t el, uint32_t er, uint32_t& l, uint32_t& r,
+                                            uint32_t& d) {
+    const uint32_t vl = el & 0xffu, vr = er & 0xffu;
+    uint32_t t = vl > vr ? vl : vr;
+    bool scanned = false;
+    if (t == 0) {
+        l = 0; r = ix.n; d = 0;
+    } else if (t > d - 1) {  // cannot happen for a maximal interval; keeps the literal bound
+        t = d - 1;
+        d = t;
+        if (t == 0) { l = 0; r = ix.n; }
+        else { l = lcs_scan_left(ix.lcs, l, t, 0); r = lcs_scan_right(ix.lcs, r, t, 0); }
+    } else {
+        d = t;
+        if (vl == t) {  // the left end moves to the previous position with a smaller LCS
+            const uint32_t dl = (el >> 8) & 0xfffu;
+            if (dl == LINK_FAR) { l = lcs_scan_left(ix.lcs, l - 1, t, 0); scanned = true; }
+            else l -= dl;
+        }
+        if (vr == t) {
+            const uint32_t dr = er >> 20;
+            if (dr == LINK_FAR) { r = lcs_scan_right(ix.lcs, r + 1, t, 0); scanned = true; }
+            else r += dr;
+        }
+    }
+    return scanned;
+}
+
+// One base through the MS recurrence (extend; on failure at d > 0 contract and retry): what K1's loop does to a
+// lane's state between two advances.  Used to tabulate the states after PREF_LEN bases.
+enum { PREF_LEN = 10, PREF_MIN_K = 16 };
+__device__ __forceinline__ void ms_feed_base(const IndexView& ix, uint32_t c, uint32_t& l, uint32_t& r, uint32_t& d) {
+    for (;;) {
+        const uint32_t rowoff = c * ix.rank_stride;
+        const uint64_t wl = ix.rank[rowoff + (l >> 5)], wr = ix.rank[rowoff + (r >> 5)];
+        const uint32_t nl = (uint32_t)(wl >> 32) + __popc((uint32_t)wl & ((1u << (l & 31)) - 1u));
+        const uint32_t nr = (uint32_t)(wr >> 32) + __popc((uint32_t)wr & ((1u << (r & 31)) - 1u));
+        if (nl < nr) {
+            l = nl; r = nr;
+            d = d + 1 < ix.k ? d + 1 : ix.k;
+            return;
+        }
+        if (d == 0) return;
+        ms_contract(ix, ix.links[l], ix.links[r], l, r, d);
+    }
+}
+// level j (1..PREF_LEN): cur[idx] for the 4^j strings of j bases, from prev (level j-1; unused for j == 1)
+__global__ void prefix_table_level_kernel(IndexView ix, const uint4* __restrict__ prev, uint4* __restrict__ cur, uint32_t j) {
+    const uint32_t idx = blockIdx.x * blockDim.x + threadIdx.x;
+    if (idx >= (1u << (2 * j))) return;
+    const uint32_t c = idx >> (2 * (j - 1));               // the newest base sits in the highest two bits
+    const uint32_t parent = idx & ((1u << (2 * (j - 1))) - 1u);
+    uint32_t l = 0, r = ix.n, d = 0;
+    if (j > 1) {
+        const uint4 s = prev[parent];
+        l = s.x; r = s.y; d = s.z;
+    }
+    ms_feed_base(ix, c, l, r, d);
+    cur[idx] = make_uint4(l, r, d, 0u);
+}
+
 // One extend attempt per loop iteration and lane.  A lane whose extension fails (at d > 0) contracts in the same
 // iteration -- two loads of `links` and a few additions -- and retries the base in the next one.
 template <bool INTERVALS, bool COUNT>
-__global__ void __launch_bounds__(256, 8) ms_kernel(MsParams p) {
+__global__ void __launch_bounds__(256, 6) ms_kernel(MsParams p) {
     __shared__ __align__(16) uint8_t ms_stage[256 * 36];
     const uint64_t g = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
     unsigned long long cnt_att = 0, cnt_split = 0, cnt_con = 0, cnt_extra = 0, cnt_proc = 0, cnt_emit = 0;
@@ -245,7 +311,28 @@ __global__ void __launch_bounds__(256, 8) ms_kernel(MsParams p) {
         const uint64_t start = g * p.chunk_len;
         const uint64_t remain = p.q.Lp - start;
         const uint32_t len = remain < p.chunk_len ? (uint32_t)remain : p.chunk_len;
-        const uint32_t warm = start >= (uint64_t)(k - 1) ? k - 1 : (uint32_t)start;  // warm-up bases
+        // Warm-up: the state at `start` depends on the k-1 bases before it, and only on those after the last
+        // non-ACGT position among them (such a position resets the state).  The state after the first PREF_LEN of
+        // the remaining bases comes from the table; the rest are stepped through.
+        uint32_t warm = start >= (uint64_t)(k - 1) ? k - 1 : (uint32_t)start;
+        for (uint64_t w = start >> 5; warm && w-- > ((start - warm) >> 5);) {  // chunk starts are multiples of 32
+            uint32_t iv = __ldg(p.q.inv + w);
+            if (w == ((start - warm) >> 5)) iv &= ~0u << ((start - warm) & 31);
+            if (iv) {
+                warm = (uint32_t)(start - (w * 32 + (31 - __clz((int)iv)) + 1));
+                break;
+            }
+        }
+        uint32_t l = 0, r = n, d = 0;
+        if (p.ix.pref && warm >= PREF_LEN) {
+            const uint64_t first = start - warm;
+            const uint32_t sh = 2 * (uint32_t)(first & 31);
+            uint64_t bits = __ldg(p.q.pack + (first >> 5)) >> sh;
+            if (sh > 64 - 2 * PREF_LEN) bits |= __ldg(p.q.pack + (first >> 5) + 1) << (64 - sh);
+            const uint4 s = __ldg(p.ix.pref + ((uint32_t)bits & ((1u << (2 * PREF_LEN)) - 1u)));
+            l = s.x; r = s.y; d = s.z;
+            warm -= PREF_LEN;
+        }
         const uint64_t pos0 = start - warm;
         const uint64_t wbase = pos0 >> 5;
         const uint64_t* __restrict__ qptr = p.q.pack + wbase;
@@ -256,7 +343,6 @@ __global__ void __launch_bounds__(256, 8) ms_kernel(MsParams p) {
         const uint32_t bp_end = bp_emit + len;
         uint64_t qw = __ldg(qptr) >> (2 * bp);
         uint32_t iw = __ldg(iptr) >> bp;
-        uint32_t l = 0, r = n, d = 0;
         // emitted MS bytes are staged in shared memory (36-byte stride per lane: conflict-free word access) and
         // flushed as two 16-byte stores per 32 positions; chunk starts are multiples of 32, so flushes are aligned
         uint8_t* const stg = ms_stage + threadIdx.x * 36u;
@@ -283,36 +369,10 @@ __global__ void __launch_bounds__(256, 8) ms_kernel(MsParams p) {
                     // contract_left to the largest depth that changes the interval: t = max(LCS[l], LCS[r])
                     advance = false;
                     const uint32_t el = __ldg(p.ix.links + l), er = __ldg(p.ix.links + r);
-                    const uint32_t vl = el & 0xffu, vr = er & 0xffu;
-                    uint32_t t = vl > vr ? vl : vr;
-                    if (COUNT) { ++cnt_con; if (bp >= bp_emit) ++cnt_con_e; }
-                    if (t == 0) {
-                        l = 0; r = n; d = 0;
-                    } else if (t > d - 1) {  // cannot happen for a maximal interval; keeps the literal bound
-                        t = d - 1;
-                        d = t;
-                        if (t == 0) { l = 0; r = n; }
-                        else { l = lcs_scan_left(p.ix.lcs, l, t, 0); r = lcs_scan_right(p.ix.lcs, r, t, 0); }
-                    } else {
-                        d = t;
-                        if (vl == t) {  // the left end moves to the previous position with a smaller LCS
-                            const uint32_t dl = (el >> 8) & 0xfffu;
-                            if (dl == LINK_FAR) {
-                                l = lcs_scan_left(p.ix.lcs, l - 1, t, 0);
-                                if (COUNT) { ++cnt_extra; cnt_extra_e += (bp >= bp_emit); }
-                            } else {
-                                l -= dl;
-                            }
-                        }
-                        if (vr == t) {
-                            const uint32_t dr = er >> 20;
-                            if (dr == LINK_FAR) {
-                                r = lcs_scan_right(p.ix.lcs, r + 1, t, 0);
-                                if (COUNT) { ++cnt_extra; cnt_extra_e += (bp >= bp_emit); }
-                            } else {
-                                r += dr;
-                            }
-                        }
+                    const bool scanned = ms_contract(p.ix, el, er, l, r, d);
+                    if (COUNT) {
+                        ++cnt_con; cnt_extra += scanned;
+                        if (bp >= bp_emit) { ++cnt_con_e; cnt_extra_e += scanned; }
                     }
                 }
             }

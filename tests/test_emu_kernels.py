@@ -121,6 +121,24 @@ def test_ms_wide_intervals_take_the_scan_path():
     assert cnt[3] > 0  # scans past the link reach did happen
 
 
+def test_ms_prefix_table_shortens_warm_up_only():
+    """With the prefix-state table (k >= 16) a chunk steps through at most k-1-10 warm-up bases; (d, l, r) are unchanged."""
+    ref = rand_seq(30_000, 61)
+    asm = synth.mutate(np.frombuffer(ref, dtype=np.uint8), 62).tobytes()
+    o = O.OracleIndex([asm], k=31)
+    queries = [ref[:9000], with_ns(ref[9000:12_000], 63, 0.03), rand_seq(800, 64), ref[15_000:15_040], b"ACGTN" * 30]
+    processed = {}
+    try:
+        for on in (0, 1):
+            E.lib().emu_set_prefix_table(on)
+            e = E.EmuIndex.build([asm], k=31)
+            check_ms(o, e, queries, 64)
+            processed[on] = e.query_sbwt_batch(queries, chunk_len=64, counters=True)[4][4]
+    finally:
+        E.lib().emu_set_prefix_table(1)
+    assert processed[1] < 0.93 * processed[0]
+
+
 def test_ms_tiny_index_and_counters():
     o = O.OracleIndex([b"ACG"], k=3)
     e = E.EmuIndex.build([b"ACG"], k=3)

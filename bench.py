@@ -31,6 +31,11 @@ import sys
 import threading
 import time
 
+# One hardware work queue per stream: with the default of 8 connections, streams of concurrent host-buffer calls
+# alias onto the same queue and wait for each other's copies (measured: e2e 28-30 instead of 43-47 G bases/s when
+# that happens).  Must be set before the CUDA context exists.
+os.environ.setdefault("CUDA_DEVICE_MAX_CONNECTIONS", "32")
+
 import numpy as np
 
 ROOT = os.path.dirname(os.path.abspath(__file__))

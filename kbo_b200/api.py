@@ -77,6 +77,9 @@ def load_library():
     if not os.path.exists(_LIB_PATH):
         raise RuntimeError("kbo_b200: %s is missing -- build it with `python -m kbo_b200.build` "
                            "(there is no CPU fallback)" % _LIB_PATH)
+    # one hardware work queue per stream (the default of 8 makes concurrent calls wait for each other's copies);
+    # only takes effect when the CUDA context does not exist yet
+    os.environ.setdefault("CUDA_DEVICE_MAX_CONNECTIONS", "32")
     L = C.CDLL(_LIB_PATH)
     L.kbo_last_error_message.restype = C.c_char_p
     L.kbo_device_count.argtypes = [C.POINTER(C.c_int)]

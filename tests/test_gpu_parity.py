@@ -204,6 +204,35 @@ def test_query_sbwt_matches_oracle(k):
     assert e.value.status == 1
 
 
+def test_prefix_table_and_wide_intervals():
+    """(d, l, r) with and without the prefix-state table; a two-letter reference drives contractions into intervals
+    wider than the link reach (kernels.cuh LINK_FAR), i.e. through the scanning fallback."""
+    rng = np.random.default_rng(5)
+    two = np.frombuffer(b"AC", dtype=np.uint8)[rng.integers(0, 2, 60_000)].tobytes()
+    q = bytearray(two[1000:9000])
+    for i in rng.integers(0, len(q), 300):
+        q[int(i)] = ord("GT"[int(i) & 1])
+    ref = rand_seq(50_000, 11)
+    asm = synth.mutate(np.frombuffer(ref, dtype=np.uint8), 12).tobytes()
+    cases = [(two, [bytes(q), b"A" * 500 + b"G" + b"C" * 300]),
+             (asm, [ref[:20_000], with_ns(ref[20_000:26_000], 5, 0.02), rand_seq(3000, 13), b"ACGTN" * 50])]
+    try:
+        for on in (False, True):
+            api.set_prefix_table(on)
+            for text, queries in cases:
+                o = O.OracleIndex([text], k=31)
+                ix = api.build([text], api.BuildOpts(k=31))
+                d, l, r, off = api.query_sbwt_batch(queries, ix)
+                for i, qq in enumerate(queries):
+                    od, ol, orr = o.query_sbwt(qq)
+                    a, b_ = int(off[i]), int(off[i + 1])
+                    assert np.array_equal(d[a:b_].astype(np.uint64), od), (on, i)
+                    assert np.array_equal(l[a:b_].astype(np.uint64), ol), (on, i)
+                    assert np.array_equal(r[a:b_].astype(np.uint64), orr), (on, i)
+    finally:
+        api.set_prefix_table(True)
+
+
 def test_ms_invariants_large():
     """Size-independent properties at a larger size: chunking never changes the result, MS grows by
     at most one per base, intervals are non-empty and inside [0, n_sets]."""

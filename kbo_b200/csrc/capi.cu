@@ -102,8 +102,8 @@ struct Workspace {
     cudaStream_t stream = nullptr;
     bool own_stream = false;
     cudaEvent_t ev0 = nullptr, ev1 = nullptr;
-    DevBuf ascii, offsets, pack, inv, sep, wq, ms, l, r, out, out2, out3, tmp64, tmp64b, tmp32, tmp32b, counters;
-    DevBuf masks, rle_words, rle_cnt, rle_cse, cub_tmp;  // K2b<false> masks and the K4 arrays
+    DevBuf ascii, offsets, pack, inv, sep, wq, ms, l, r, out, out2, out3, tmp64, counters;
+    DevBuf masks, rle_words, rle_cnt, rle_cse, rle_tickets;  // K2b<false> masks and the K4 arrays
     RleParams rle;                                       // filled by run_rle_offsets, reused by run_rle_records
     std::vector<cudaEvent_t> timing;  // 4 events per timed call (before K0, after K0, after K1, after K2)
     size_t timed_calls = 0;
@@ -114,7 +114,7 @@ struct Workspace {
         if (ev_fork) cudaEventDestroy(ev_fork);
         for (cudaEvent_t e : ev_join) cudaEventDestroy(e);
         DevBuf* all[] = {&ascii, &offsets, &pack, &inv, &sep, &wq, &ms, &l, &r, &out, &out2, &out3,
-                         &tmp64, &tmp64b, &tmp32, &tmp32b, &counters, &masks, &rle_words, &rle_cnt, &rle_cse, &cub_tmp};
+                         &tmp64, &counters, &masks, &rle_words, &rle_cnt, &rle_cse, &rle_tickets};
         for (DevBuf* b : all) b->release();
         if (ev0) cudaEventDestroy(ev0);
         if (ev1) cudaEventDestroy(ev1);
@@ -631,15 +631,20 @@ static int run_derand_translate(kbo_index* ix, Workspace* ws, const QueryView& q
     return KBO_OK;
 }
 
-// K4 up to the per-query record offsets: word counts -> scan -> START/END marks -> scan -> offsets.
+// K4 up to the per-query record offsets: word counts -> START/END marks -> offsets (the scans are inside).
 // d_offsets are the batch's own CSR offsets (offsets[0] may be non-zero); d_rle_offsets gets nq + 1 entries.
 static int run_rle_offsets(Workspace* ws, const QueryView& qv, const Geometry& g, const uint64_t* d_offsets, uint64_t nq,
                            uint32_t max_gap_len, uint64_t* d_rle_offsets) {
     cudaStream_t st = ws->stream;
     const uint64_t nw = g.n_tiles_b * 32;
+    const uint64_t nb = (nw + RLE_BLOCK - 1) / RLE_BLOCK;
     CUDA_TRY(ws->rle_words.ensure(nw * 4 * 4, st));
-    CUDA_TRY(ws->rle_cnt.ensure((nw + 1) * sizeof(RleCounts), st));
-    CUDA_TRY(ws->rle_cse.ensure((nw + 1) * 8, st));
+    CUDA_TRY(ws->rle_cnt.ensure((nw + nb + 1) * sizeof(RleCounts), st));
+    CUDA_TRY(ws->rle_cse.ensure((nw + nb + 1) * 8, st));
+    if (!ws->rle_tickets.p) {
+        CUDA_TRY(ws->rle_tickets.ensure(8, st));
+        CUDA_TRY(cudaMemsetAsync(ws->rle_tickets.p, 0, 8, st));  // the kernels leave them at zero
+    }
     RleParams& p = ws->rle;
     p.gap = ws->masks.as<uint32_t>();
     p.match = p.gap + nw;
@@ -647,6 +652,7 @@ static int run_rle_offsets(Workspace* ws, const QueryView& qv, const Geometry& g
     p.sep = qv.sep;
     p.wq = qv.wq;
     p.n_words = nw;
+    p.n_blocks = nb;
     p.offsets = d_offsets;
     p.nq = nq;
     p.window = max_gap_len + 1;
@@ -655,24 +661,18 @@ static int run_rle_offsets(Workspace* ws, const QueryView& qv, const Geometry& g
     p.start = p.gopen + nw;
     p.end = p.start + nw;
     p.cnt = ws->rle_cnt.as<RleCounts>();
+    p.cnt_blk = p.cnt + nw;
     p.cse = ws->rle_cse.as<uint64_t>();
+    p.cse_blk = p.cse + nw;
+    p.tickets = ws->rle_tickets.as<unsigned int>();
     p.rle_offsets = d_rle_offsets;
     p.out = nullptr;
     p.cap = 0;
-    size_t tmp_a = 0, tmp_b = 0;
-    const RleCounts zero = {0, 0, 0, 0};
-    CUDA_TRY(cub::DeviceScan::ExclusiveScan(nullptr, tmp_a, p.cnt, p.cnt, RleCountsSum(), zero, (int)(nw + 1), st));
-    CUDA_TRY(cub::DeviceScan::ExclusiveSum(nullptr, tmp_b, p.cse, p.cse, (int)(nw + 1), st));
-    size_t tmp = std::max(tmp_a, tmp_b);
-    CUDA_TRY(ws->cub_tmp.ensure(tmp, st));
+    rle_word_counts_kernel<<<(unsigned)nb, RLE_BLOCK, 0, st>>>(p);
+    LAUNCHED();
+    rle_mark_kernel<<<(unsigned)nb, RLE_BLOCK, 0, st>>>(p);
+    LAUNCHED();
     const unsigned threads = 128;
-    const unsigned blocks = (unsigned)((nw + 1 + threads - 1) / threads);
-    rle_word_counts_kernel<<<blocks, threads, 0, st>>>(p);
-    LAUNCHED();
-    CUDA_TRY(cub::DeviceScan::ExclusiveScan(ws->cub_tmp.p, tmp, p.cnt, p.cnt, RleCountsSum(), zero, (int)(nw + 1), st));
-    rle_mark_kernel<<<blocks, threads, 0, st>>>(p);
-    LAUNCHED();
-    CUDA_TRY(cub::DeviceScan::ExclusiveSum(ws->cub_tmp.p, tmp, p.cse, p.cse, (int)(nw + 1), st));
     rle_query_offsets_kernel<<<(unsigned)((nq + 1 + threads - 1) / threads), threads, 0, st>>>(p);
     LAUNCHED();
     CUDA_TRY(cudaGetLastError());
@@ -1066,8 +1066,9 @@ static int reserve_ws(Workspace* ws, uint64_t total, uint64_t nq, bool for_find)
     if (for_find) {
         CUDA_TRY(ws->masks.ensure(nw * 3 * 4, st));
         CUDA_TRY(ws->rle_words.ensure(nw * 4 * 4, st));
-        CUDA_TRY(ws->rle_cnt.ensure((nw + 1) * sizeof(RleCounts), st));
-        CUDA_TRY(ws->rle_cse.ensure((nw + 1) * 8, st));
+        const uint64_t nb = (nw + RLE_BLOCK - 1) / RLE_BLOCK;
+        CUDA_TRY(ws->rle_cnt.ensure((nw + nb + 1) * sizeof(RleCounts), st));
+        CUDA_TRY(ws->rle_cse.ensure((nw + nb + 1) * 8, st));
         CUDA_TRY(ws->tmp64.ensure((nq + 1) * 8, st));
         CUDA_TRY(ws->h_rel.ensure((nq + 1) * 8));
         CUDA_TRY(ws->h_roff.ensure((nq + 1) * 8));

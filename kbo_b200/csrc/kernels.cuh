@@ -971,9 +971,10 @@ __global__ void __launch_bounds__(K2B_WARPS * 32) derand_translate_bits_kernel(T
 //   * a segment [ps, pe]: matches / mismatches / jumps / gap opens are counts of
 //     masks over [ps, pe], gap_bases = length - #N.  jumps counts 'R' preceded
 //     by 'R'; gap opens counts '-' preceded by N (a '-' run strictly inside).
-// With exclusive prefix counts per word (two library scans between the kernels)
-// every START / END test and every record is O(1):
-//   rle_word_counts -> scan -> rle_mark -> scan -> rle_query_offsets, rle_records.
+// With exclusive prefix counts per word every START / END test and every record is O(1).  The counts are kept in
+// two levels (before the word inside its block of 256 words, before the block); each of the two counting kernels
+// scans inside its blocks, and its last block to finish scans the block totals:
+//   rle_word_counts -> rle_mark -> rle_query_offsets, rle_records.
 // Records are ordered by position, hence by query; the slot of a segment is the
 // number of STARTs before it.
 // ---------------------------------------------------------------------------
@@ -981,15 +982,11 @@ struct RleRecord {
     uint64_t start, end, matches, mismatches, jumps, gap_bases, gap_opens;  // == kbo_rle
 };
 
-struct RleCounts {  // per word; after the scan: counts before the word
+struct RleCounts {  // per word: counts before the word inside its block of RLE_BLOCK words; per block: before the block
     uint32_t n, m, j, go;
 };
-struct RleCountsSum {
-    __host__ __device__ RleCounts operator()(const RleCounts& a, const RleCounts& b) const {
-        RleCounts c = {a.n + b.n, a.m + b.m, a.j + b.j, a.go + b.go};
-        return c;
-    }
-};
+
+enum { RLE_BLOCK = 256 };  // words (= threads) per block of the two scanning kernels
 
 struct RleParams {
     const uint32_t* gap;    // '-'                       (bit per padded position)
@@ -998,15 +995,19 @@ struct RleParams {
     const uint32_t* sep;    // QueryView::sep
     const uint32_t* wq;     // QueryView::wq
     uint64_t n_words;       // words covered (a multiple of 32, >= ceil(Lp / 32))
+    uint64_t n_blocks;      // ceil(n_words / RLE_BLOCK)
     const uint64_t* offsets;
     uint64_t nq;
     uint32_t window;        // D = max_gap_len + 1
     uint32_t* jump;         // rle_word_counts out
     uint32_t* gopen;
-    RleCounts* cnt;         // n_words + 1 entries; scanned in place
+    RleCounts* cnt;         // n_words entries (block-relative) ...
+    RleCounts* cnt_blk;     // ... + n_blocks + 1 entries (before each block; last = grand total)
     uint32_t* start;        // rle_mark out
     uint32_t* end;
-    uint64_t* cse;          // n_words + 1 entries: #START | #END << 32; scanned in place
+    uint64_t* cse;          // n_words entries: #START | #END << 32 before the word inside its block ...
+    uint64_t* cse_blk;      // ... + n_blocks + 1 entries
+    unsigned int* tickets;  // two zero-initialised counters (self-resetting) electing the last block of a launch
     uint64_t* rle_offsets;  // nq + 1
     RleRecord* out;
     uint64_t cap;
@@ -1040,11 +1041,76 @@ __device__ __forceinline__ uint32_t rle_nongap(const RleParams& p, uint64_t w) {
     return ~__ldg(p.sep + w) & ~__ldg(p.gap + w);
 }
 
-// thread per word (+1): jump / gap-open masks and the four counts
-__global__ void rle_word_counts_kernel(RleParams p) {
-    const uint64_t w = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
-    if (w > p.n_words) return;
-    RleCounts c = {0, 0, 0, 0};
+// Exclusive scan of N 32-bit counters over the RLE_BLOCK threads of a block (all threads must call).
+// v: in = the thread's counts, out = counts of the threads before it; total = counts of the whole block.
+template <int N>
+__device__ __forceinline__ void rle_block_scan(uint32_t (&v)[N], uint32_t (&total)[N]) {
+    __shared__ uint32_t warp_sum[RLE_BLOCK / 32][N];
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    uint32_t inc[N];
+#pragma unroll
+    for (int i = 0; i < N; ++i) inc[i] = v[i];
+#pragma unroll
+    for (int off = 1; off < 32; off <<= 1) {
+#pragma unroll
+        for (int i = 0; i < N; ++i) {
+            const uint32_t o = __shfl_up_sync(0xffffffffu, inc[i], off);
+            if (lane >= off) inc[i] += o;
+        }
+    }
+    __syncthreads();  // warp_sum may still be read by the previous use
+    if (lane == 31)
+        for (int i = 0; i < N; ++i) warp_sum[warp][i] = inc[i];
+    __syncthreads();
+#pragma unroll
+    for (int i = 0; i < N; ++i) {
+        uint32_t before = 0, all = 0;
+        for (int w = 0; w < RLE_BLOCK / 32; ++w) {
+            const uint32_t x = warp_sum[w][i];
+            if (w < warp) before += x;
+            all += x;
+        }
+        v[i] = before + inc[i] - v[i];
+        total[i] = all;
+    }
+}
+
+// The block that finishes last turns the per-block totals (N counters of 32 bits each per entry) into "before the
+// block", with the grand total at [n_blocks].  The ticket counter resets itself for the next launch.
+template <int N, typename T>
+__device__ __forceinline__ void rle_finish_blocks(T* blk, uint64_t n_blocks, unsigned int* ticket) {
+    __shared__ bool last;
+    __threadfence();
+    __syncthreads();
+    if (threadIdx.x == 0) last = atomicAdd(ticket, 1u) == gridDim.x - 1;
+    __syncthreads();
+    if (!last) return;
+    __threadfence();
+    uint32_t run[N];
+    for (int i = 0; i < N; ++i) run[i] = 0;
+    for (uint64_t base = 0; base < n_blocks; base += RLE_BLOCK) {
+        const uint64_t b = base + threadIdx.x;
+        uint32_t v[N], tot[N];
+        const uint32_t* src = reinterpret_cast<const uint32_t*>(blk + (b < n_blocks ? b : 0));
+        for (int i = 0; i < N; ++i) v[i] = b < n_blocks ? src[i] : 0u;
+        rle_block_scan<N>(v, tot);
+        if (b < n_blocks) {
+            uint32_t* dst = reinterpret_cast<uint32_t*>(blk + b);
+            for (int i = 0; i < N; ++i) dst[i] = run[i] + v[i];
+        }
+        for (int i = 0; i < N; ++i) run[i] += tot[i];
+    }
+    if (threadIdx.x == 0) {
+        uint32_t* dst = reinterpret_cast<uint32_t*>(blk + n_blocks);
+        for (int i = 0; i < N; ++i) dst[i] = run[i];
+        *ticket = 0;
+    }
+}
+
+// thread per word: jump / gap-open masks, the four counts before the word, block totals
+__global__ void __launch_bounds__(RLE_BLOCK) rle_word_counts_kernel(RleParams p) {
+    const uint64_t w = (uint64_t)blockIdx.x * RLE_BLOCK + threadIdx.x;
+    uint32_t c[4] = {0, 0, 0, 0}, tot[4];
     if (w < p.n_words) {
         const uint32_t N = rle_nongap(p, w), R = __ldg(p.rr + w), Gp = __ldg(p.gap + w);
         uint32_t n31 = 0, r31 = 0;
@@ -1056,18 +1122,28 @@ __global__ void rle_word_counts_kernel(RleParams p) {
         const uint32_t GO = Gp & ((N << 1) | n31);  // '-' preceded by an aligned character
         p.jump[w] = J;
         p.gopen[w] = GO;
-        c.n = __popc(N);
-        c.m = __popc(__ldg(p.match + w));
-        c.j = __popc(J);
-        c.go = __popc(GO);
+        c[0] = __popc(N);
+        c[1] = __popc(__ldg(p.match + w));
+        c[2] = __popc(J);
+        c[3] = __popc(GO);
     }
-    p.cnt[w] = c;
+    rle_block_scan<4>(c, tot);
+    if (w < p.n_words) {
+        RleCounts before = {c[0], c[1], c[2], c[3]};
+        p.cnt[w] = before;
+    }
+    if (threadIdx.x == 0) {
+        RleCounts t = {tot[0], tot[1], tot[2], tot[3]};
+        p.cnt_blk[blockIdx.x] = t;
+    }
+    rle_finish_blocks<4>(p.cnt_blk, p.n_blocks, p.tickets);
 }
 
-// number of aligned characters before padded position x (after the scan of cnt)
+// number of aligned characters before padded position x
 __device__ __forceinline__ uint32_t rle_pref_n(const RleParams& p, uint64_t x) {
     const uint64_t w = x >> 5;
-    uint32_t c = p.cnt[w].n;
+    if (w >= p.n_words) return p.cnt_blk[p.n_blocks].n;
+    uint32_t c = p.cnt_blk[w / RLE_BLOCK].n + p.cnt[w].n;
     const uint32_t b = (uint32_t)(x & 31);
     if (b) c += __popc(rle_nongap(p, w) & low_mask(b));
     return c;
@@ -1076,47 +1152,54 @@ __device__ __forceinline__ uint64_t rle_query_start(const RleParams& p, uint64_t
     return p.offsets[q] - p.offsets[0] + q;
 }
 
-// thread per word (+1): START / END masks and their counts
-__global__ void rle_mark_kernel(RleParams p) {
-    const uint64_t w = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
-    if (w > p.n_words) return;
-    if (w == p.n_words) {
-        p.cse[w] = 0;
-        return;
-    }
-    const uint32_t N = rle_nongap(p, w);
-    const uint32_t n31 = w > 0 ? rle_nongap(p, w - 1) >> 31 : 0u;
-    const uint32_t n0 = w + 1 < p.n_words ? rle_nongap(p, w + 1) & 1u : 0u;
-    uint32_t st = N & ~((N << 1) | n31);  // first character of a run of aligned characters
-    uint32_t en = N & ~((N >> 1) | (n0 << 31));
-    if (p.window > 1 && (st | en)) {
-        const uint32_t S = __ldg(p.sep + w);
-        const uint64_t q0 = __ldg(p.wq + w);
-        const uint64_t D = p.window;
-        uint32_t keep = 0;
-        for (uint32_t rem = st; rem; rem &= rem - 1) {
-            const uint32_t b = (uint32_t)__ffs((int)rem) - 1u;
-            const uint64_t pos = w * 32 + b;
-            const uint64_t qs = rle_query_start(p, q0 + __popc(S & low_mask(b)));
-            uint64_t lo = pos > D ? pos - D : 0;
-            if (lo < qs) lo = qs;
-            if (rle_pref_n(p, pos) == rle_pref_n(p, lo)) keep |= 1u << b;
+// thread per word: START / END masks, their counts before the word, block totals
+__global__ void __launch_bounds__(RLE_BLOCK) rle_mark_kernel(RleParams p) {
+    const uint64_t w = (uint64_t)blockIdx.x * RLE_BLOCK + threadIdx.x;
+    uint32_t st = 0, en = 0;
+    if (w < p.n_words) {
+        const uint32_t N = rle_nongap(p, w);
+        const uint32_t n31 = w > 0 ? rle_nongap(p, w - 1) >> 31 : 0u;
+        const uint32_t n0 = w + 1 < p.n_words ? rle_nongap(p, w + 1) & 1u : 0u;
+        st = N & ~((N << 1) | n31);  // first character of a run of aligned characters
+        en = N & ~((N >> 1) | (n0 << 31));
+        if (p.window > 1 && (st | en)) {
+            const uint32_t S = __ldg(p.sep + w);
+            const uint64_t q0 = __ldg(p.wq + w);
+            const uint64_t D = p.window;
+            uint32_t keep = 0;
+            for (uint32_t rem = st; rem; rem &= rem - 1) {
+                const uint32_t b = (uint32_t)__ffs((int)rem) - 1u;
+                const uint64_t pos = w * 32 + b;
+                const uint64_t qs = rle_query_start(p, q0 + __popc(S & low_mask(b)));
+                uint64_t lo = pos > D ? pos - D : 0;
+                if (lo < qs) lo = qs;
+                if (rle_pref_n(p, pos) == rle_pref_n(p, lo)) keep |= 1u << b;
+            }
+            st = keep;
+            keep = 0;
+            for (uint32_t rem = en; rem; rem &= rem - 1) {
+                const uint32_t b = (uint32_t)__ffs((int)rem) - 1u;
+                const uint64_t pos = w * 32 + b;
+                const uint64_t qe = rle_query_start(p, q0 + __popc(S & low_mask(b)) + 1) - 1;  // its separator
+                uint64_t hi = pos + D + 1;  // exclusive
+                if (hi > qe) hi = qe;
+                if (rle_pref_n(p, hi) == rle_pref_n(p, pos + 1)) keep |= 1u << b;
+            }
+            en = keep;
         }
-        st = keep;
-        keep = 0;
-        for (uint32_t rem = en; rem; rem &= rem - 1) {
-            const uint32_t b = (uint32_t)__ffs((int)rem) - 1u;
-            const uint64_t pos = w * 32 + b;
-            const uint64_t qe = rle_query_start(p, q0 + __popc(S & low_mask(b)) + 1) - 1;  // its separator
-            uint64_t hi = pos + D + 1;  // exclusive
-            if (hi > qe) hi = qe;
-            if (rle_pref_n(p, hi) == rle_pref_n(p, pos + 1)) keep |= 1u << b;
-        }
-        en = keep;
+        p.start[w] = st;
+        p.end[w] = en;
     }
-    p.start[w] = st;
-    p.end[w] = en;
-    p.cse[w] = (uint64_t)__popc(st) | ((uint64_t)__popc(en) << 32);
+    uint32_t c[2] = {(uint32_t)__popc(st), (uint32_t)__popc(en)}, tot[2];
+    rle_block_scan<2>(c, tot);
+    if (w < p.n_words) p.cse[w] = (uint64_t)c[0] | ((uint64_t)c[1] << 32);
+    if (threadIdx.x == 0) p.cse_blk[blockIdx.x] = (uint64_t)tot[0] | ((uint64_t)tot[1] << 32);
+    rle_finish_blocks<2>(p.cse_blk, p.n_blocks, p.tickets + 1);
+}
+
+// STARTs (low half) / ENDs (high half) before word w
+__device__ __forceinline__ uint64_t rle_cse(const RleParams& p, uint64_t w) {
+    return p.cse_blk[w / RLE_BLOCK] + p.cse[w];
 }
 
 // thread per query (+1): records before the query = STARTs before its first base
@@ -1124,17 +1207,20 @@ __global__ void rle_query_offsets_kernel(RleParams p) {
     const uint64_t q = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (q > p.nq) return;
     if (q == p.nq) {
-        p.rle_offsets[q] = (uint32_t)p.cse[p.n_words];
+        p.rle_offsets[q] = (uint32_t)p.cse_blk[p.n_blocks];
         return;
     }
     const uint64_t x = rle_query_start(p, q);
     const uint32_t b = (uint32_t)(x & 31);
-    p.rle_offsets[q] = (uint32_t)p.cse[x >> 5] + (b ? __popc(p.start[x >> 5] & low_mask(b)) : 0);
+    p.rle_offsets[q] = (uint32_t)rle_cse(p, x >> 5) + (b ? __popc(p.start[x >> 5] & low_mask(b)) : 0);
 }
 
 __device__ __forceinline__ RleCounts rle_pref_all(const RleParams& p, uint64_t x) {
     const uint64_t w = x >> 5;
+    if (w >= p.n_words) return p.cnt_blk[p.n_blocks];
+    const RleCounts blk = p.cnt_blk[w / RLE_BLOCK];
     RleCounts c = p.cnt[w];
+    c.n += blk.n; c.m += blk.m; c.j += blk.j; c.go += blk.go;
     const uint32_t b = (uint32_t)(x & 31);
     if (b) {
         const uint32_t lm = low_mask(b);
@@ -1154,7 +1240,7 @@ __global__ void rle_records_kernel(RleParams p) {
     if (!rem) return;
     const uint32_t S = __ldg(p.sep + w);
     const uint64_t q0 = __ldg(p.wq + w);
-    uint32_t slot = (uint32_t)(p.cse[w] >> 32);
+    uint32_t slot = (uint32_t)(rle_cse(p, w) >> 32);
     for (; rem; rem &= rem - 1, ++slot) {
         if (slot >= p.cap) break;
         const uint32_t b = (uint32_t)__ffs((int)rem) - 1u;
@@ -1164,10 +1250,10 @@ __global__ void rle_records_kernel(RleParams p) {
         uint64_t lo = qs >> 5, hi = w;
         while (lo < hi) {
             const uint64_t mid = (lo + hi + 1) >> 1;
-            if ((uint32_t)p.cse[mid] <= slot) lo = mid; else hi = mid - 1;
+            if ((uint32_t)rle_cse(p, mid) <= slot) lo = mid; else hi = mid - 1;
         }
         uint32_t sb = p.start[lo];
-        for (uint32_t skip = slot - (uint32_t)p.cse[lo]; skip; --skip) sb &= sb - 1;
+        for (uint32_t skip = slot - (uint32_t)rle_cse(p, lo); skip; --skip) sb &= sb - 1;
         const uint64_t ps = lo * 32 + (uint32_t)__ffs((int)sb) - 1u;
         const RleCounts a = rle_pref_all(p, ps), z = rle_pref_all(p, pe + 1);
         const uint32_t n = z.n - a.n, m = z.m - a.m;

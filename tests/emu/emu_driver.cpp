@@ -264,35 +264,27 @@ void emu_derandomize_general(const uint64_t* ms, uint64_t n, uint32_t k, uint32_
                    [&]() { g35_tile_kernel<true>(ms, n, k, thr, min_.data(), nullptr, eps.data(), out); });
 }
 
-// K4 on masks in padded space (the product's run_rle; the two library scans are plain loops here)
+// K4 on masks in padded space (the product's run_rle_offsets + run_rle_records)
 static uint64_t emu_run_rle(const uint32_t* gap, const uint32_t* match, const uint32_t* rr, const QueryView& qv,
                             uint64_t n_words, const uint64_t* offsets, uint64_t nq, uint32_t max_gap_len,
                             uint64_t* out7, uint64_t cap, uint64_t* rle_offsets) {
+    const uint64_t nb = (n_words + RLE_BLOCK - 1) / RLE_BLOCK;
     std::vector<uint32_t> jump(n_words), gopen(n_words), start(n_words), end(n_words);
-    std::vector<RleCounts> cnt(n_words + 1);
-    std::vector<uint64_t> cse(n_words + 1);
+    std::vector<RleCounts> cnt(n_words + nb + 1);
+    std::vector<uint64_t> cse(n_words + nb + 1);
+    unsigned int tickets[2] = {0, 0};
     RleParams p;
-    p.gap = gap; p.match = match; p.rr = rr; p.sep = qv.sep; p.wq = qv.wq; p.n_words = n_words;
+    p.gap = gap; p.match = match; p.rr = rr; p.sep = qv.sep; p.wq = qv.wq; p.n_words = n_words; p.n_blocks = nb;
     p.offsets = offsets; p.nq = nq; p.window = max_gap_len + 1;
-    p.jump = jump.data(); p.gopen = gopen.data(); p.cnt = cnt.data(); p.start = start.data(); p.end = end.data();
-    p.cse = cse.data(); p.rle_offsets = rle_offsets; p.out = (RleRecord*)out7; p.cap = cap;
-    const unsigned threads = 128, blocks = (unsigned)((n_words + 1 + threads - 1) / threads);
-    emu_launch_seq(blocks, threads, [&]() { rle_word_counts_kernel(p); });
-    RleCounts run = {0, 0, 0, 0};
-    for (uint64_t w = 0; w <= n_words; ++w) {
-        const RleCounts c = cnt[w];
-        cnt[w] = run;
-        run = RleCountsSum()(run, c);
-    }
-    emu_launch_seq(blocks, threads, [&]() { rle_mark_kernel(p); });
-    uint64_t acc = 0;
-    for (uint64_t w = 0; w <= n_words; ++w) {
-        const uint64_t c = cse[w];
-        cse[w] = acc;
-        acc += c;
-    }
+    p.jump = jump.data(); p.gopen = gopen.data(); p.cnt = cnt.data(); p.cnt_blk = cnt.data() + n_words;
+    p.start = start.data(); p.end = end.data(); p.cse = cse.data(); p.cse_blk = cse.data() + n_words;
+    p.tickets = tickets; p.rle_offsets = rle_offsets; p.out = (RleRecord*)out7; p.cap = cap;
+    emu_launch_par((unsigned)nb, RLE_BLOCK, [&]() { rle_word_counts_kernel(p); });
+    emu_launch_par((unsigned)nb, RLE_BLOCK, [&]() { rle_mark_kernel(p); });
+    const unsigned threads = 128;
     emu_launch_seq((unsigned)((nq + 1 + threads - 1) / threads), threads, [&]() { rle_query_offsets_kernel(p); });
-    emu_launch_seq(blocks, threads, [&]() { rle_records_kernel(p); });
+    emu_launch_seq((unsigned)((n_words + threads - 1) / threads), threads, [&]() { rle_records_kernel(p); });
+    if (tickets[0] != 0 || tickets[1] != 0) std::abort();  // the last block must leave the counters at zero
     return rle_offsets[nq];
 }
 

@@ -1588,7 +1588,8 @@ int kbo_map(const kbo_index* cix, const uint8_t* ref_seq, uint64_t len, double m
     view.r = ms.r.data();
     view.n = len;
     try {
-        if (do_fill_gaps) fill_gaps(&aln, view, ref_seq, len, ix->host, thr, max_error_prob);  // lib.rs:743-744
+        if (do_fill_gaps)  // lib.rs:743-744; gaps are independent: bridged on build_opts.num_threads host threads
+            fill_gaps(&aln, view, ref_seq, len, ix->host, thr, max_error_prob, std::max<uint32_t>(1, o.num_threads));
         if (do_call_variants) {                                                             // lib.rs:749-751
             std::vector<VariantRec> vars;
             rc = call_impl(ix, ref_seq, len, max_error_prob, &o, ms, &vars);

@@ -7,6 +7,8 @@
 
 #include <algorithm>
 #include <cmath>
+#include <thread>
+#include <utility>
 
 namespace kbo_b200 {
 namespace {
@@ -270,8 +272,12 @@ void add_variants(Bytes* translation, const std::vector<VariantRec>& variants) {
 // ---------------------------------------------------------------------------
 // gap_filling.rs:444-526
 // ---------------------------------------------------------------------------
+// The gaps are found on the translation as it comes in: filling one only rewrites positions inside it, which the
+// scan never looks at again, so the list of gaps does not depend on the fills and every gap can be bridged
+// independently (num_threads > 1: contiguous ranges of the list on host threads; a reference panic is reported for the
+// first gap in order, as the sequential loop would).
 void fill_gaps(Bytes* translation, const MsArrays& noisy_ms, const uint8_t* ref_seq, uint64_t len,
-               const HostIndex& ix, uint64_t thr, double max_err_prob) {
+               const HostIndex& ix, uint64_t thr, double max_err_prob, uint32_t num_threads) {
     Bytes& a = *translation;
     const uint64_t n = a.size();
     require(n > 0 && n == noisy_ms.n, "gap_filling.rs:453-454");
@@ -279,11 +285,14 @@ void fill_gaps(Bytes* translation, const MsArrays& noisy_ms, const uint8_t* ref_
     require(k > 0, "gap_filling.rs:457");
     require(n >= thr, "gap_filling.rs:467 usize underflow");
     const double log_bound = std::log1p(-max_err_prob);
+    std::vector<std::pair<uint64_t, uint64_t>> gaps;  // [start, end)
     for (uint64_t i = thr + 1; i < n - thr; ++i) {
         if (a[i - 1] != '-' && a[i - 1] != 'X') continue;
         const uint64_t gs = i - 1;
         while (i < n && a[i] == '-') ++i;
-        const uint64_t ge = std::min(i, n - thr);
+        gaps.emplace_back(gs, std::min(i, n - thr));
+    }
+    auto bridge = [&](uint64_t gs, uint64_t ge) {
         const uint64_t glen = ge - gs;
         const bool fits_in_kmer = glen + 2 * thr <= k;
         const Bytes kmer = bridge_gap(noisy_ms, ref_seq, len, ix, thr, thr, gs, ge, k - (fits_in_kmer ? thr : 0));
@@ -311,7 +320,29 @@ void fill_gaps(Bytes* translation, const MsArrays& noisy_ms, const uint8_t* ref_
         if (found && no_indels && (fits_in_kmer || by_overlap || flanked)) {
             for (uint64_t p = gs, t = thr; p < ge; ++p, ++t) a[p] = (kmer[t] == ref_seq[p]) ? (uint8_t)'M' : kmer[t];
         }
+    };
+    const size_t nt = std::max<size_t>(1, std::min<size_t>(num_threads, gaps.size() / 64 + 1));
+    if (nt == 1) {
+        for (const auto& g : gaps) bridge(g.first, g.second);
+        return;
     }
+    std::vector<std::string> panic_what(nt);
+    std::vector<char> panicked(nt, 0);
+    std::vector<std::thread> workers;
+    for (size_t t = 0; t < nt; ++t) {
+        workers.emplace_back([&, t]() {
+            const size_t lo = gaps.size() * t / nt, hi = gaps.size() * (t + 1) / nt;
+            try {
+                for (size_t g = lo; g < hi; ++g) bridge(gaps[g].first, gaps[g].second);
+            } catch (const RefinePanic& e) {
+                panic_what[t] = e.what;  // ranges are in gap order: the lowest t holds the first panic
+                panicked[t] = 1;
+            }
+        });
+    }
+    for (auto& w : workers) w.join();
+    for (size_t t = 0; t < nt; ++t)
+        if (panicked[t]) throw RefinePanic{panic_what[t]};
 }
 
 }  // namespace kbo_b200

@@ -57,6 +57,6 @@ void add_variants(std::vector<uint8_t>* translation, const std::vector<VariantRe
 
 // gap_filling::fill_gaps (gap_filling.rs:444-526), in place on a byte alignment.
 void fill_gaps(std::vector<uint8_t>* translation, const MsArrays& noisy_ms, const uint8_t* ref_seq, uint64_t len,
-               const HostIndex& query_sbwt, uint64_t threshold, double max_err_prob);
+               const HostIndex& query_sbwt, uint64_t threshold, double max_err_prob, uint32_t num_threads = 1);
 
 }  // namespace kbo_b200

@@ -415,7 +415,7 @@ int emu_map(void* h_query, const uint8_t* ref_seq, uint64_t len, uint32_t thr, u
         emu_single_ms(q, ref_seq, len, thr, &d, &l, &r, &chars);
         MsArrays ms;
         ms.d = d.data(); ms.l = l.data(); ms.r = r.data(); ms.n = len;
-        if (do_fill) fill_gaps(&chars, ms, ref_seq, len, q->host, thr, p);
+        if (do_fill) fill_gaps(&chars, ms, ref_seq, len, q->host, thr, p, 4);  // the threaded branch when there are >= 64 gaps
         if (do_call) add_variants(&chars, emu_call_impl(q, ref_seq, len, call_thr ? call_thr : thr, build_k, revcomp, ms));
         for (uint64_t i = 0; i < len; ++i) {
             const uint8_t a = chars[i];

@@ -364,6 +364,9 @@ def test_config1_full_size_map_bit_exact():
     assert 0.005 < frac_gap < 0.2
     # the unformatted translation as well (fill_gaps on, variants on)
     assert api.map(r, ix, api.MapOpts(format=False)) == o.map(r, format=False, build_k=31)
+    # gaps bridged on 8 host threads (sbwt_build_opts.num_threads): same result
+    threaded = api.MapOpts(sbwt_build_opts=api.BuildOpts(k=31, build_select=True, num_threads=8))
+    assert api.map(r, ix, threaded) == want
 
 
 def test_hbm_resident_index_regime():

@@ -68,10 +68,13 @@ enum { CNT_ATTEMPTS = 0, CNT_SPLIT = 1, CNT_CONTRACT = 2, CNT_EXTRA_LCS = 3, CNT
        CNT_ATT_EMIT = 6, CNT_SPLIT_EMIT = 7, CNT_CON_EMIT = 8, CNT_EXTRA_EMIT = 9, CNT_N = 10 };
 
 // ---------------------------------------------------------------------------
-// K0: pack.  One thread per 32 padded positions.  The bases of a word are read
-// eight at a time (aligned 8-byte loads, shifted together when the source is
-// misaligned) and converted four per 32-bit register with byte-parallel
-// arithmetic; a word that holds separators is cut into its runs of bases.
+// K0: pack.  One thread per 32 padded positions (a warp covers 1024).
+//   * the number of separators before the warp's first position is found by ONE search per warp, 32 probes per
+//     step; a lane then walks forward from there to its own word (a few steps unless queries are tiny);
+//   * the word's source bytes are contiguous in the CSR buffer even across query borders (a separator occupies a
+//     padded position but no source byte), so 32 of them are read with aligned 8-byte loads, shifted together,
+//     and converted four per register with byte-parallel arithmetic;
+//   * each separator inside the word is then inserted by shifting the upper part of the masks up by one position.
 // ---------------------------------------------------------------------------
 __device__ __forceinline__ uint64_t sep_pos(const uint64_t* offsets, uint64_t q) {
     // padded position of the separator that follows query q
@@ -93,63 +96,86 @@ __device__ __forceinline__ void swar_pack4(uint32_t v, uint32_t& code8, uint32_t
     inv4 = (nz * 0x00204081u) >> 28;                     // bits 8i+7 -> 28+i
 }
 
-// n (1..8) bytes starting at src, little endian; touches only the aligned 8-byte words that hold them
-__device__ __forceinline__ uint64_t load_bytes8(const uint8_t* src, uint32_t n) {
-    const uintptr_t a = reinterpret_cast<uintptr_t>(src) & ~(uintptr_t)7;
-    const uint32_t mis = (uint32_t)(reinterpret_cast<uintptr_t>(src) & 7u);
-    uint64_t v = *reinterpret_cast<const uint64_t*>(a) >> (8 * mis);
-    if (mis + n > 8) v |= *reinterpret_cast<const uint64_t*>(a + 8) << (64 - 8 * mis);
-    return v;
-}
-
 __global__ void pack_queries_kernel(const uint8_t* __restrict__ ascii, const uint64_t* __restrict__ offsets,
                                     uint64_t nq, QueryView qv, uint64_t* __restrict__ pack,
                                     uint32_t* __restrict__ inv, uint32_t* __restrict__ sep,
                                     uint32_t* __restrict__ wq) {
-    uint64_t w = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
-    if (w >= qv.n_words) return;
+    const uint64_t w = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;  // blockDim.x is a multiple of 32
+    const int lane = threadIdx.x & 31;
     const uint64_t pp0 = w * 32;
-    // q = first query whose separator is at or after pp0
-    uint64_t lo = 0, hi = nq;
-    while (lo < hi) {
-        uint64_t mid = (lo + hi) >> 1;
-        if (sep_pos(offsets, mid) < pp0) lo = mid + 1; else hi = mid;
-    }
-    uint64_t q = lo;
-    wq[w] = (uint32_t)q;
     const uint64_t off0 = offsets[0];
+    // ---- first query whose separator is at or after the warp's first position: 33-ary search, whole warp ----
+    uint64_t lo = 0, hi = nq;  // the answer is in [lo, hi]
+    {
+        const uint64_t warp_pp0 = pp0 - 32ull * lane;
+        while (lo < hi) {
+            const uint64_t span = hi - lo;
+            uint64_t t = lo + (span * (uint64_t)(lane + 1)) / 33;  // increasing in lane, < hi
+            const bool before = sep_pos(offsets, t) < warp_pp0;  // monotone: true for a prefix of the lanes
+            const uint32_t c = (uint32_t)__popc(__ballot_sync(0xffffffffu, before));
+            const uint64_t t_last_true = __shfl_sync(0xffffffffu, t, c ? c - 1 : 0);
+            const uint64_t t_first_false = __shfl_sync(0xffffffffu, t, c < 32 ? c : 31);
+            if (c) lo = t_last_true + 1;
+            if (c < 32) hi = t_first_false;
+        }
+    }
+    if (w >= qv.n_words) return;
+    // ---- this word's first query: walk forward, a bounded binary search if that takes long ----------------------
+    uint64_t q = lo;
+    for (int step = 0; step < 4 && q < nq && sep_pos(offsets, q) < pp0; ++step) ++q;
+    if (q < nq && sep_pos(offsets, q) < pp0) {
+        uint64_t a = q + 1, b = nq;
+        while (a < b) {
+            const uint64_t mid = (a + b) >> 1;
+            if (sep_pos(offsets, mid) < pp0) a = mid + 1; else b = mid;
+        }
+        q = a;
+    }
+    wq[w] = (uint32_t)q;
     uint64_t pk = 0;
     uint32_t iv = 0, sp = 0;
-    uint32_t j = 0;
-    while (j < 32) {
-        if (q >= nq) {  // past the last separator: the tail is all separator
-            iv |= ~0u << j;
-            sp |= ~0u << j;
-            break;
+    if (q >= nq) {  // past the last separator: all tail
+        iv = sp = ~0u;
+    } else {
+        // ---- 32 source bytes from off0 + pp0 - q on (only aligned words that hold bytes of the batch are read) ----
+        const uint64_t src = off0 + pp0 - q, src_end = offsets[nq];
+        const uintptr_t addr = reinterpret_cast<uintptr_t>(ascii) + src;
+        const uintptr_t end_addr = reinterpret_cast<uintptr_t>(ascii) + src_end;
+        const uintptr_t a0 = addr & ~(uintptr_t)7;
+        const uint32_t sh = 8u * (uint32_t)(addr & 7u);
+        uint64_t wv[5];
+#pragma unroll
+        for (int j = 0; j < 5; ++j)
+            wv[j] = (a0 + 8 * j < end_addr) ? __ldg(reinterpret_cast<const uint64_t*>(a0 + 8 * j)) : 0ull;
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+            const uint64_t v = sh ? ((wv[j] >> sh) | (wv[j + 1] << (64 - sh))) : wv[j];
+            uint32_t c0, c1, i0, i1;
+            swar_pack4((uint32_t)v, c0, i0);
+            swar_pack4((uint32_t)(v >> 32), c1, i1);
+            pk |= (uint64_t)(c0 | (c1 << 8)) << (16 * j);
+            iv |= (i0 | (i1 << 4)) << (8 * j);
         }
-        const uint64_t pp = pp0 + j;
-        const uint64_t next_sep = sep_pos(offsets, q);
-        if (pp == next_sep) {
-            iv |= 1u << j;
-            sp |= 1u << j;
+        // ---- separators inside the word: open one position at each ------------------------------------------
+        uint64_t next_sep = sep_pos(offsets, q);
+        while (next_sep < pp0 + 32) {
+            const uint32_t b = (uint32_t)(next_sep - pp0);
+            const uint64_t low2 = (1ull << (2 * b)) - 1ull;
+            const uint32_t low1 = (1u << b) - 1u;
+            pk = (pk & low2) | ((pk & ~low2) << 2);  // b <= 31: the shifts stay below 64
+            pk &= ~(3ull << (2 * b));
+            iv = (iv & low1) | ((iv & ~low1) << 1) | (1u << b);
+            sp = (sp & low1) | ((sp & ~low1) << 1) | (1u << b);
             ++q;
-            ++j;
-            continue;
+            if (q >= nq) {  // everything after the last separator is tail
+                const uint32_t tail = b == 31 ? 0u : (~0u << (b + 1));
+                iv |= tail;
+                sp |= tail;
+                pk &= b == 31 ? ~0ull : ((1ull << (2 * (b + 1))) - 1ull);
+                break;
+            }
+            next_sep = sep_pos(offsets, q);
         }
-        uint64_t n64 = next_sep - pp;
-        uint32_t n = 32 - j;
-        if (n64 < n) n = (uint32_t)n64;
-        if (n > 8) n = 8;
-        const uint64_t v = load_bytes8(ascii + off0 + pp - q, n);
-        uint32_t c0, c1, i0, i1;
-        swar_pack4((uint32_t)v, c0, i0);
-        swar_pack4((uint32_t)(v >> 32), c1, i1);
-        const uint32_t keep = (1u << n) - 1u;  // drop what was read past the run
-        const uint32_t code16 = (c0 | (c1 << 8)) & ((1u << (2 * n)) - 1u);
-        const uint32_t inv8 = (i0 | (i1 << 4)) & keep;
-        pk |= (uint64_t)code16 << (2 * j);
-        iv |= inv8 << j;
-        j += n;
     }
     pack[w] = pk;
     inv[w] = iv;

@@ -108,7 +108,7 @@ static void stage_and_ms(EmuIndex* e, const uint8_t* concat, const uint64_t* off
     qv.n_words = g.n_words;
     {
         const unsigned threads = 128, blocks = (unsigned)((g.n_words + threads - 1) / threads);
-        emu_launch_seq(blocks, threads, [&]() {
+        emu_launch_par(blocks, threads, [&]() {
             pack_queries_kernel(concat, offsets, nq, qv, s->pack.data(), s->inv.data(), s->sep.data(), s->wq.data());
         });
     }
@@ -211,7 +211,7 @@ uint64_t emu_pack(const uint8_t* ascii, const uint64_t* offsets, uint64_t nq, ui
     QueryView qv;
     qv.pack = pack; qv.inv = inv; qv.sep = sep; qv.wq = wq;
     qv.Lp = g.Lp; qv.n_words = g.n_words;
-    emu_launch_seq((unsigned)((g.n_words + 127) / 128), 128,
+    emu_launch_par((unsigned)((g.n_words + 127) / 128), 128,
                    [&]() { pack_queries_kernel(ascii, offsets, nq, qv, pack, inv, sep, wq); });
     return g.n_words;
 }
@@ -243,7 +243,7 @@ void emu_derand_translate_u8(const uint8_t* ms, uint64_t n, uint32_t k, uint32_t
     QueryView qv;
     qv.pack = pack.data(); qv.inv = inv.data(); qv.sep = sep.data(); qv.wq = wq.data();
     qv.Lp = g.Lp; qv.n_words = g.n_words;
-    emu_launch_seq((unsigned)((g.n_words + 127) / 128), 128, [&]() {
+    emu_launch_par((unsigned)((g.n_words + 127) / 128), 128, [&]() {
         pack_queries_kernel(ascii.data(), offsets, 1, qv, pack.data(), inv.data(), sep.data(), wq.data());
     });
     TrParams tp;
@@ -297,7 +297,7 @@ uint64_t emu_rle_batch(const uint8_t* aln, const uint64_t* offsets, uint64_t nq,
     QueryView qv;
     qv.pack = pack.data(); qv.inv = inv.data(); qv.sep = sep.data(); qv.wq = wq.data();
     qv.Lp = g.Lp; qv.n_words = g.n_words;
-    emu_launch_seq((unsigned)((g.n_words + 127) / 128), 128,
+    emu_launch_par((unsigned)((g.n_words + 127) / 128), 128,
                    [&]() { pack_queries_kernel(aln, offsets, nq, qv, pack.data(), inv.data(), sep.data(), wq.data()); });
     const uint64_t nw = g.n_tiles_b * 32;
     std::vector<uint32_t> gap(nw), match(nw), rr(nw);

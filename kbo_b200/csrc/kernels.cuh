@@ -263,32 +263,49 @@ __global__ void lcs_links_kernel(const uint8_t* __restrict__ lcs, uint32_t n, ui
 
 // contract_left to the largest depth that changes the interval, t = max(LCS[l], LCS[r]), given the link words of
 // l and r.  Returns true when an end was farther than the links reach and had to be found by scanning.
-__device__ __forceinline__ bool ms_contract(const IndexView& ix, uint32_t el, uint32_t er, uint32_t& l, uint32_t& r,
-                                            uint32_t& d) {
+// The rare cases (t == 0, an end beyond the reach of the links, the impossible t > d - 1) are kept out of line.
+__device__ __noinline__ uint4 ms_contract_rare(const uint8_t* __restrict__ lcs, uint32_t n, uint32_t el, uint32_t er,
+                                               uint32_t l, uint32_t r, uint32_t d) {  // returns (l, r, d, scanned)
     const uint32_t vl = el & 0xffu, vr = er & 0xffu;
     uint32_t t = vl > vr ? vl : vr;
-    bool scanned = false;
+    uint32_t scanned = 0;
     if (t == 0) {
-        l = 0; r = ix.n; d = 0;
+        l = 0; r = n; d = 0;
     } else if (t > d - 1) {  // cannot happen for a maximal interval; keeps the literal bound
         t = d - 1;
         d = t;
-        if (t == 0) { l = 0; r = ix.n; }
-        else { l = lcs_scan_left(ix.lcs, l, t, 0); r = lcs_scan_right(ix.lcs, r, t, 0); }
+        if (t == 0) { l = 0; r = n; }
+        else { l = lcs_scan_left(lcs, l, t, 0); r = lcs_scan_right(lcs, r, t, 0); }
     } else {
         d = t;
         if (vl == t) {  // the left end moves to the previous position with a smaller LCS
             const uint32_t dl = (el >> 8) & 0xfffu;
-            if (dl == LINK_FAR) { l = lcs_scan_left(ix.lcs, l - 1, t, 0); scanned = true; }
+            if (dl == LINK_FAR) { l = lcs_scan_left(lcs, l - 1, t, 0); scanned = 1; }
             else l -= dl;
         }
         if (vr == t) {
             const uint32_t dr = er >> 20;
-            if (dr == LINK_FAR) { r = lcs_scan_right(ix.lcs, r + 1, t, 0); scanned = true; }
+            if (dr == LINK_FAR) { r = lcs_scan_right(lcs, r + 1, t, 0); scanned = 1; }
             else r += dr;
         }
     }
-    return scanned;
+    return make_uint4(l, r, d, scanned);
+}
+__device__ __forceinline__ bool ms_contract(const IndexView& ix, uint32_t el, uint32_t er, uint32_t& l, uint32_t& r,
+                                            uint32_t& d) {
+    const uint32_t vl = el & 0xffu, vr = er & 0xffu;
+    const uint32_t t = vl > vr ? vl : vr;
+    const uint32_t dl = (el >> 8) & 0xfffu, dr = er >> 20;
+    const bool far = (vl == t && dl == LINK_FAR) || (vr == t && dr == LINK_FAR);
+    if (t == 0 || t > d - 1 || far) {
+        const uint4 s = ms_contract_rare(ix.lcs, ix.n, el, er, l, r, d);
+        l = s.x; r = s.y; d = s.z;
+        return s.w != 0;
+    }
+    d = t;
+    l -= vl == t ? dl : 0u;  // the left end moves to the previous position with a smaller LCS
+    r += vr == t ? dr : 0u;
+    return false;
 }
 
 // One base through the MS recurrence (extend; on failure at d > 0 contract and retry): what K1's loop does to a

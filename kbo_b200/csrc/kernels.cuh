@@ -137,16 +137,26 @@ __global__ void pack_queries_kernel(const uint8_t* __restrict__ ascii, const uin
     if (q >= nq) {  // past the last separator: all tail
         iv = sp = ~0u;
     } else {
-        // ---- 32 source bytes from off0 + pp0 - q on (only aligned words that hold bytes of the batch are read) ----
+        // ---- 32 source bytes from off0 + pp0 - q on (no byte outside the batch is touched) ----
         const uint64_t src = off0 + pp0 - q, src_end = offsets[nq];
         const uintptr_t addr = reinterpret_cast<uintptr_t>(ascii) + src;
+        const uintptr_t beg_addr = reinterpret_cast<uintptr_t>(ascii) + off0;
         const uintptr_t end_addr = reinterpret_cast<uintptr_t>(ascii) + src_end;
         const uintptr_t a0 = addr & ~(uintptr_t)7;
         const uint32_t sh = 8u * (uint32_t)(addr & 7u);
         uint64_t wv[5];
 #pragma unroll
-        for (int j = 0; j < 5; ++j)
-            wv[j] = (a0 + 8 * j < end_addr) ? __ldg(reinterpret_cast<const uint64_t*>(a0 + 8 * j)) : 0ull;
+        for (int j = 0; j < 5; ++j) {
+            const uintptr_t a = a0 + 8 * j;
+            if (a >= beg_addr && a + 8 <= end_addr) {
+                wv[j] = __ldg(reinterpret_cast<const uint64_t*>(a));
+            } else {  // the aligned word sticks out of the batch (its first / last one): byte by byte
+                uint64_t v = 0;
+                for (int t = 0; t < 8; ++t)
+                    if (a + t >= beg_addr && a + t < end_addr) v |= (uint64_t)__ldg(reinterpret_cast<const uint8_t*>(a + t)) << (8 * t);
+                wv[j] = v;
+            }
+        }
 #pragma unroll
         for (int j = 0; j < 4; ++j) {
             const uint64_t v = sh ? ((wv[j] >> sh) | (wv[j + 1] << (64 - sh))) : wv[j];
@@ -539,8 +549,8 @@ __device__ __forceinline__ uint32_t lookahead_c(const TrParams& p, uint64_t e, i
     uint32_t src_val = 0, src_dist = 0, parity = 0;
     for (uint64_t base = e;; base += 32) {
         const uint64_t pp = base + lane;
-        const uint32_t m0 = p.ms[pp], m1 = p.ms[pp + 1];
         const bool s0 = sep_bit(p.q, (int64_t)pp), s1 = sep_bit(p.q, (int64_t)pp + 1);
+        const uint32_t m0 = s0 ? 0u : p.ms[pp], m1 = s1 ? 0u : p.ms[pp + 1];  // (K1 never wrote past the batch)
         const bool last = !s0 && s1;
         const bool elig = !s0 && !last && (m0 > p.thr || m0 == p.k);
         const bool source = s0 || last || elig;
@@ -601,14 +611,6 @@ __global__ void __launch_bounds__(K2_WARPS * 32) derand_translate_kernel(TrParam
     const uint32_t k = p.k, thr = p.thr;
 
     // ---- loads ------------------------------------------------------------
-    uint32_t m[K2_PER_LANE + 1];
-    {
-        const uint4 v = *reinterpret_cast<const uint4*>(p.ms + P);
-        const uint32_t w[4] = {v.x, v.y, v.z, v.w};
-#pragma unroll
-        for (int t = 0; t < K2_PER_LANE; ++t) m[t] = (w[t >> 2] >> (8 * (t & 3))) & 0xffu;
-        m[K2_PER_LANE] = p.ms[P + K2_PER_LANE];
-    }
     // separator bits of positions P-2 .. P+16 -> sf bit (t+2) = sep(P+t)
     uint32_t sf;
     {
@@ -617,9 +619,18 @@ __global__ void __launch_bounds__(K2_WARPS * 32) derand_translate_kernel(TrParam
         sf |= sep_bit(p.q, (int64_t)P - 2) | (sep_bit(p.q, (int64_t)P - 1) << 1);
         sf |= sep_bit(p.q, (int64_t)P + 16) << 18;
     }
+    uint32_t m[K2_PER_LANE + 1];
+    {
+        uint4 v = make_uint4(0u, 0u, 0u, 0u);
+        if (((sf >> 2) & 0xffffu) != 0xffffu) v = *reinterpret_cast<const uint4*>(p.ms + P);  // K1 never wrote past the batch
+        const uint32_t w[4] = {v.x, v.y, v.z, v.w};
+#pragma unroll
+        for (int t = 0; t < K2_PER_LANE; ++t) m[t] = (w[t >> 2] >> (8 * (t & 3))) & 0xffu;
+        m[K2_PER_LANE] = ((sf >> 18) & 1u) ? 0u : p.ms[P + K2_PER_LANE];
+    }
     const uint32_t c_e = lookahead_c(p, s + K2_TILE, lane);
-    const uint32_t m_e = p.ms[s + K2_TILE];
     const bool e_sep = sep_bit(p.q, (int64_t)(s + K2_TILE));
+    const uint32_t m_e = e_sep ? 0u : p.ms[s + K2_TILE];
     const bool e_last = !e_sep && sep_bit(p.q, (int64_t)(s + K2_TILE) + 1);
     const uint32_t eps_e = (!e_sep && !e_last && (m_e > thr || m_e == k)) ? (m_e - c_e) & 1u : 0u;
 
@@ -810,27 +821,30 @@ __global__ void __launch_bounds__(K2B_WARPS * 32) derand_translate_bits_kernel(T
     const uint32_t H = 0x80808080u;
 
     // ---- loads: 32 MS bytes + the first four of the next word; separator bits around the word -------------
-    uint32_t mw[9];
-    {
-        const uint4 va = *reinterpret_cast<const uint4*>(p.ms + P);
-        const uint4 vb = *reinterpret_cast<const uint4*>(p.ms + P + 16);
-        mw[0] = va.x; mw[1] = va.y; mw[2] = va.z; mw[3] = va.w;
-        mw[4] = vb.x; mw[5] = vb.y; mw[6] = vb.z; mw[7] = vb.w;
-#pragma unroll
-        for (int j = 0; j < 8; ++j) mw[j] &= 0x7f7f7f7fu;  // bytes of separators / the tail may hold anything
-        mw[8] = __shfl_down_sync(0xffffffffu, mw[0], 1);
-        if (lane == 31) mw[8] = *reinterpret_cast<const uint32_t*>(p.ms + P + 32) & 0x7f7f7f7fu;
-    }
     const uint32_t S = __ldg(p.q.sep + (P >> 5));
     uint32_t s_next = __shfl_down_sync(0xffffffffu, S, 1) & 1u;  // separator bit of P+32
     if (lane == 31) s_next = sep_bit(p.q, (int64_t)e);
+    uint32_t mw[9];
+    {
+        uint4 va = make_uint4(0u, 0u, 0u, 0u), vb = va;
+        if (S != ~0u) {  // words past the end of the batch were never written by K1
+            va = *reinterpret_cast<const uint4*>(p.ms + P);
+            vb = *reinterpret_cast<const uint4*>(p.ms + P + 16);
+        }
+        mw[0] = va.x; mw[1] = va.y; mw[2] = va.z; mw[3] = va.w;
+        mw[4] = vb.x; mw[5] = vb.y; mw[6] = vb.z; mw[7] = vb.w;
+#pragma unroll
+        for (int j = 0; j < 8; ++j) mw[j] &= 0x7f7f7f7fu;  // bytes of separators may hold anything
+        mw[8] = __shfl_down_sync(0xffffffffu, mw[0], 1);
+        if (lane == 31) mw[8] = s_next ? 0u : (*reinterpret_cast<const uint32_t*>(p.ms + P + 32) & 0x7f7f7f7fu);
+    }
     uint32_t s_prev = __shfl_up_sync(0xffffffffu, S, 1) >> 30;   // bit0 = sep(P-2), bit1 = sep(P-1)
     if (lane == 0) s_prev = sep_bit(p.q, (int64_t)P - 2) | (sep_bit(p.q, (int64_t)P - 1) << 1);
 
     // ---- value entering the tile from the right ---------------------------------------------------------------
     const uint32_t c_e = lookahead_c(p, e, lane);
-    const uint32_t m_e = p.ms[e] & 0x7fu;
     const bool e_sep = sep_bit(p.q, (int64_t)e);
+    const uint32_t m_e = e_sep ? 0u : (p.ms[e] & 0x7fu);
     const bool e_last = !e_sep && sep_bit(p.q, (int64_t)e + 1);
     const uint32_t eps_e = (!e_sep && !e_last && (m_e > thr || m_e == k)) ? (m_e - c_e) & 1u : 0u;
 

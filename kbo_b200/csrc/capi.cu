@@ -1709,7 +1709,7 @@ int kbo_set_l2_persist(int enabled) { g_l2_persist = enabled ? 1 : 0; return KBO
 int kbo_set_ms_flags(uint32_t flags) {
     g_ms_flags = flags & 0xffu;
     const uint32_t blk = (flags >> 8) & 0x3ffu;  // bits 8..17: K1 block size (experiment)
-    if (blk == 64 || blk == 128 || blk == 256) g_ms_block = blk;
+    if (blk == 128 || blk == 256) g_ms_block = blk;
     return KBO_OK;
 }
 uint64_t kbo_kernel_launch_count(void) { return g_launches.load(); }

@@ -153,7 +153,7 @@ def test_ms_tiny_index_and_counters():
 @pytest.fixture(autouse=True, params=["dispatch", "k2-only"])
 def k2_mode(request):
     """Tests that reach derandomize+translate run twice: product dispatch (K2b where it applies) and K2 alone."""
-    name = request.node.name
+    name = request.node.originalname or request.node.name  # the function name, without the parameter ids
     touches_k2 = any(t in name for t in ("k2", "matches", "map", "call", "find", "rle"))
     if request.param == "k2-only" and not touches_k2:
         pytest.skip("does not reach K2")

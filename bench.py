@@ -374,7 +374,9 @@ def run_ours(args, rank, local_rank, world):
 
     # warm-up with the same concurrency until every workspace the timed region needs exists at its final size
     # (the library creates them lazily, one per concurrent call; measured: the first ~50 calls carry that cost)
-    run_threads(0, max(args.warmup, 16) * n_thr)
+    # ... and one untimed pass of the same length: in some runs the first pass after start-up stays 10-25 % slower
+    # for its whole length (profiles/README.md: repeated regions in one process settle at 47 G bases/s from the second on)
+    run_threads(0, max(max(args.warmup, 16) * n_thr, args.steps))
     barrier()
     e2e_steps = args.steps
     w0 = time.perf_counter()

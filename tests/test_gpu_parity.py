@@ -468,6 +468,36 @@ def test_find_batch_matches_oracle():
             assert rle_tuples(g_) == o.find(q, max_gap_len=gap)
 
 
+def test_find_mixed_query_sizes_and_gap_lengths():
+    """Thousands of tiny queries (separators in most words), queries around the word / tile / block sizes of K2b and
+    K4, one long query with inserted unrelated stretches (long '-' runs), K2 as well as K2b, several max_gap_len."""
+    k, p = 31, 1e-7
+    ref = synth.random_seq(400_000, 51)
+    o = O.OracleIndex([ref.tobytes()], k=k)
+    ix = api.build([ref.tobytes()], api.BuildOpts(k=k))
+    asm = synth.mutate(ref, 52, snp=0.02, indel=0.002).tobytes()
+    rng = np.random.default_rng(53)
+    lens = [3, 4, 31, 32, 33, 1023, 1024, 1025, 8191, 8192, 8193] + [int(x) for x in rng.integers(3, 120, 4000)] + \
+           [int(x) for x in rng.integers(200, 3000, 60)]
+    rng.shuffle(lens)
+    queries = []
+    for n in lens:
+        a = int(rng.integers(0, len(asm) - n))
+        queries.append(asm[a:a + n])
+    long_q = bytearray(asm[100_000:300_000])
+    for a, n in ((5_000, 40), (20_000, 700), (60_000, 33), (61_000, 5_000), (150_000, 1)):
+        long_q[a:a + n] = rand_seq(n, a)
+    queries.append(bytes(long_q))
+    try:
+        for gap, flags in ((0, 0), (7, 0), (100, 0), (10_000, 0), (7, 2)):  # flags 2: K2 + chars_to_masks
+            api.set_ms_flags(flags)
+            got = api.find_batch(queries, ix, api.FindOpts(max_error_prob=p, max_gap_len=gap))
+            for i, (g_, q) in enumerate(zip(got, queries)):
+                assert rle_tuples(g_) == o.find(q, p, gap), (gap, flags, i, len(q))
+    finally:
+        api.set_ms_flags(0)
+
+
 def test_device_pointer_entry_points_match_host_entry_points():
     """kbo_matches_batch_device / kbo_find_batch_device on torch-owned device memory and stream."""
     import torch

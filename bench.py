@@ -8,8 +8,8 @@ pass of the hot path over one batch of 10,000 queries (10^7 query bases).
   value : whole-job throughput with the batch already resident in HBM (kbo_find_batch_device:
           K0 pack -> K1 matching statistics -> K2b derandomize+translate (masks) -> K4 run-length records),
           independent steps round-robin on `--streams` streams forked from / joined into the timing stream,
-          CUDA events on that stream, max over ranks.  config["overlap_tuned"] repeats the region with the
-          chunk length that suits overlapped launches.  Steps rotate through `--batches` distinct batches whose total
+          CUDA events on that stream, max over ranks.  (`--tuned-chunk-len N` repeats the region with an explicit
+          chunk length for comparison; the library picks it per call from the batch size and the observed overlap.)  Steps rotate through `--batches` distinct batches whose total
           size exceeds L2, so queries always come from HBM while the index stays L2 resident.
   e2e   : the same metric through the host-buffer C ABI call a kbo user makes (kbo_find_batch):
           pinned host -> device copy of the queries, kernels, device -> host copy of the RLE records.
@@ -61,7 +61,7 @@ def parse_args():
     ap.add_argument("--ms-flags", type=int, default=0, help="experiment switches (2: K2 instead of K2b)")
     ap.add_argument("--no-prefix-table", action="store_true", help="build the index without the prefix-state table (comparison)")
     ap.add_argument("--no-l2-persist", action="store_true", help="do not mark the index persisting in L2 (comparison)")
-    ap.add_argument("--tuned-chunk-len", type=int, default=192,
+    ap.add_argument("--tuned-chunk-len", type=int, default=0,
                     help="second timed region with this chunk length (0 = skip); only when --chunk-len is automatic")
     ap.add_argument("--streams", type=int, default=6,
                     help="CUDA streams the device-resident steps are issued round-robin on (independent batches)")
@@ -437,7 +437,9 @@ def run_ours(args, rank, local_rank, world):
 
     if rank == 0:
         cfg = config_dict(args)
-        cfg.update({"chunk_len": args.chunk_len or "auto", "index_device_bytes": index.device_bytes,
+        cfg.update({"chunk_len": args.chunk_len or "auto (per call, from the batch size and the number of caller streams "
+                                                  "seen in the last 8 stream-ordered calls)",
+                    "index_device_bytes": index.device_bytes,
                     "n_sets": index.n_sets, "index_build_s_host": round(index_build_s, 2), "rle_records_per_step": n_rle,
                     "streams": len(workers),
                     "parallelism": "replicated index, %d rank(s) x own batches" % world})

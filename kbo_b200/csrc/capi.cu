@@ -127,6 +127,8 @@ struct kbo_index {
     std::vector<PinnedBuf> pinned_pool;  // host staging for find (guarded by mu)
     std::atomic<int> host_calls{0};      // host-buffer batch calls currently inside the library (any thread)
     std::atomic<bool> seen_concurrency{false};  // some host-buffer call found another caller inside (sticky)
+    cudaStream_t recent_streams[8] = {};       // caller streams of the last 8 stream-ordered calls (guarded by mu)
+    unsigned recent_pos = 0;
     HostIndex host;
     uint64_t* d_rank = nullptr;
     uint8_t* d_lcs = nullptr;
@@ -210,8 +212,22 @@ static void release_ws(kbo_index* ix, Workspace* ws) {
     std::lock_guard<std::mutex> g(ix->mu);
     ix->pool.push_back(ws);
 }
+// How many launches of K1 a stream-ordered call can expect to share the machine with: K1 is about 60 % of a step, so
+// of the distinct caller streams among the last 8 calls roughly that share is inside K1 at any time.
+static uint32_t expected_overlap(kbo_index* ix) {
+    std::lock_guard<std::mutex> g(ix->mu);
+    uint32_t distinct = 0;
+    for (int i = 0; i < 8; ++i) {
+        bool seen = false;
+        for (int j = 0; j < i; ++j) seen |= ix->recent_streams[j] == ix->recent_streams[i];
+        distinct += !seen;  // (the initial null entries count as one stream)
+    }
+    return std::max<uint32_t>(1, distinct * 6 / 10);
+}
+
 static int stream_ws(kbo_index* ix, cudaStream_t st, Workspace** out) {
     std::lock_guard<std::mutex> g(ix->mu);
+    ix->recent_streams[ix->recent_pos++ & 7u] = st;
     auto it = ix->by_stream.find(st);
     if (it != ix->by_stream.end()) { *out = it->second; return KBO_OK; }
     Workspace* ws = new Workspace();
@@ -508,7 +524,9 @@ static int build_index_gpu(kbo_index* ix, const uint8_t* const* seqs, const uint
 // ---------------------------------------------------------------------------
 // batch geometry
 // ---------------------------------------------------------------------------
-static Geometry make_geometry(uint64_t total, uint64_t nq) { return kbo_b200::make_geometry(total, nq, g_chunk_len.load()); }
+static Geometry batch_geometry(uint64_t total, uint64_t nq, uint32_t overlap = 1) {
+    return kbo_b200::make_geometry(total, nq, g_chunk_len.load(), overlap);
+}
 
 static int check_offsets(const uint64_t* offsets, uint64_t nq, uint64_t min_len, uint64_t* total) {
     if (!offsets) return fail(KBO_ERR_BAD_ARGUMENT, "offsets is null");
@@ -966,7 +984,7 @@ int kbo_query_sbwt_batch_compact(const kbo_index* cix, const uint8_t* concat, co
     Workspace* ws = nullptr;
     rc = acquire_ws(ix, &ws);
     if (rc) return rc;
-    const Geometry g = make_geometry(total, n_queries);
+    const Geometry g = batch_geometry(total, n_queries);
     const bool intervals = l_out || r_out;
     cudaStream_t st = ws->stream;
     auto body = [&]() -> int {
@@ -1054,7 +1072,7 @@ static std::vector<uint64_t> split_queries(const uint64_t* offsets, uint64_t nq,
 // several sub-batches.
 static int reserve_ws(Workspace* ws, uint64_t total, uint64_t nq, bool for_find) {
     cudaStream_t st = ws->stream;
-    const Geometry g = make_geometry(total, nq);
+    const Geometry g = batch_geometry(total, nq);
     const uint64_t nw = g.n_tiles_b * 32;
     CUDA_TRY(ws->ascii.ensure(total, st));
     CUDA_TRY(ws->offsets.ensure((nq + 1) * 8, st));
@@ -1127,7 +1145,7 @@ int kbo_matches_batch(const kbo_index* cix, const uint8_t* concat, const uint64_
         cudaStream_t st = ws->stream;
         const uint64_t q0 = cut[s], q1 = cut[s + 1], nq = q1 - q0;
         const uint64_t bytes = offsets[q1] - offsets[q0];
-        const Geometry g = make_geometry(bytes, nq);
+        const Geometry g = batch_geometry(bytes, nq);
         auto body = [&]() -> int {
             CUDA_TRY(ws->ascii.ensure(bytes, st));
             CUDA_TRY(ws->offsets.ensure((nq + 1) * 8, st));
@@ -1182,7 +1200,8 @@ static int matches_device_forked(kbo_index* ix, Workspace* ws, const uint8_t* d_
     const size_t np = cut.size() - 1;
     cudaStream_t user = ws->stream;
     if (np == 1) {
-        const Geometry g = make_geometry(total, nq);
+        const bool instrumented = g_profile_counters.load() || g_kernel_timing.load();
+        const Geometry g = batch_geometry(total, nq, instrumented ? 1 : expected_overlap(ix));
         return matches_device(ix, ws, d_concat, d_offsets, nq, g, thr, d_chars, 0);
     }
     while (ws->subs.size() < np) {
@@ -1200,7 +1219,7 @@ static int matches_device_forked(kbo_index* ix, Workspace* ws, const uint8_t* d_
     for (size_t s = 0; s < np; ++s) {
         Workspace* sub = ws->subs[s];
         const uint64_t q0 = cut[s], q1 = cut[s + 1], n = q1 - q0;
-        const Geometry g = make_geometry(host_offsets[q1] - host_offsets[q0], n);
+        const Geometry g = batch_geometry(host_offsets[q1] - host_offsets[q0], n);
         CUDA_TRY(cudaStreamWaitEvent(sub->stream, ws->ev_fork, 0));
         int rc = matches_device(ix, sub, d_concat, d_offsets + q0, n, g, thr, d_chars, host_offsets[q0]);
         if (rc) return rc;
@@ -1337,7 +1356,7 @@ int kbo_find_batch(const kbo_index* cix, const uint8_t* concat, const uint64_t* 
         cudaStream_t st = ws->stream;
         const uint64_t q0 = cut[s], q1 = cut[s + 1], nq = q1 - q0;
         const uint64_t bytes = offsets[q1] - offsets[q0];
-        const Geometry g = make_geometry(bytes, nq);
+        const Geometry g = batch_geometry(bytes, nq);
         auto body = [&]() -> int {
             CUDA_TRY(ws->ascii.ensure(bytes, st));
             CUDA_TRY(ws->offsets.ensure((nq + 1) * 8, st));
@@ -1425,7 +1444,8 @@ int kbo_find_batch_device(const kbo_index* cix, const uint8_t* d_concat, const u
     Workspace* ws = nullptr;
     rc = stream_ws(ix, (cudaStream_t)stream, &ws);
     if (rc) return rc;
-    const Geometry g = make_geometry(total, n_queries);
+    const bool instrumented = g_profile_counters.load() || g_kernel_timing.load();
+    const Geometry g = batch_geometry(total, n_queries, instrumented ? 1 : expected_overlap(ix));
     QueryView qv;
     rc = matches_device(ix, ws, d_concat, d_offsets, n_queries, g, thr, nullptr, 0, true, &qv);
     if (rc) return rc;
@@ -1459,7 +1479,7 @@ static int run_single_full(kbo_index* ix, const uint8_t* seq, uint64_t len, uint
     Workspace* ws = nullptr;
     int rc = acquire_ws(ix, &ws);
     if (rc) return rc;
-    const Geometry g = make_geometry(len, 1);
+    const Geometry g = batch_geometry(len, 1);
     cudaStream_t st = ws->stream;
     const uint64_t offsets[2] = {0, len};
     out->d.resize(len);

@@ -53,24 +53,26 @@ struct Geometry {
     size_t ms_bytes = 0;   // bytes of the u8 MS array (readable slack past n_words*32)
 };
 
-inline uint32_t auto_chunk_len(uint64_t Lp) {
-    // Measured on B200 (profiles/README.md): for a 10^7-base batch 64 beats 32/96/128; K1 is bound by
-    // instruction issue, so the warm-up overhead (k-1)/chunk_len and the number of chunks in flight
-    // (one per lane, 148 SMs x 1024 lanes wanted) are traded here.
-    uint64_t c = (Lp / (148ull * 1024ull)) & ~31ull;
+// `overlap` = number of launches of K1 expected to share the machine (1 for a lone call).  Measured on B200
+// (profiles/README.md): one launch over a 10^7-base batch is fastest at chunk_len 64 (148 SMs x 1024 lanes wanted:
+// a wider chunk leaves too few warps, a narrower one doubles the warm-up work); when independent batches overlap on
+// several streams the warps come from the other launches and the longer chunk's smaller warm-up share wins
+// (6 streams: 95 G bases/s at 64, 109 G at 192, 80 G at 256).
+inline uint32_t auto_chunk_len(uint64_t Lp, uint32_t overlap = 1) {
+    uint64_t c = (Lp * (overlap ? overlap : 1) / (148ull * 1024ull)) & ~31ull;
     if (c < 64) c = 64;
     if (c > 512) c = 512;
     return (uint32_t)c;
 }
 
-inline Geometry make_geometry(uint64_t total, uint64_t nq, uint32_t forced_chunk_len) {
+inline Geometry make_geometry(uint64_t total, uint64_t nq, uint32_t forced_chunk_len, uint32_t overlap = 1) {
     Geometry g;
     g.total = total;
     g.Lp = total + nq;
     g.n_tiles = (g.Lp + 511) / 512;
     g.n_tiles_b = (g.Lp + 1023) / 1024;
     g.n_words = g.n_tiles_b * 32 + 4;
-    g.chunk_len = forced_chunk_len ? ((forced_chunk_len + 31u) & ~31u) : auto_chunk_len(g.Lp);
+    g.chunk_len = forced_chunk_len ? ((forced_chunk_len + 31u) & ~31u) : auto_chunk_len(g.Lp, overlap);
     g.n_chunks = (g.Lp + g.chunk_len - 1) / g.chunk_len;
     g.ms_bytes = (size_t)(g.n_words * 32 + 64);
     return g;

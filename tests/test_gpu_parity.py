@@ -525,6 +525,19 @@ def test_device_pointer_entry_points_match_host_entry_points():
     for q in range(300):
         got = [tuple(int(x) for x in rle[j]) for j in range(int(roff[q]), int(roff[q + 1]))]
         assert got == o.find(concat[int(off[q]):int(off[q + 1])].tobytes(), max_gap_len=25)
+    # the same batch round-robin on six streams: the library then picks a longer chunk per call (more overlap
+    # expected); results must not depend on it
+    streams = [torch.cuda.Stream() for _ in range(6)]
+    outs = [(torch.zeros(cap * 7, dtype=torch.int64, device="cuda"), torch.zeros(len(off), dtype=torch.int64, device="cuda"),
+             torch.zeros(len(concat) + 16, dtype=torch.uint8, device="cuda")) for _ in range(18)]
+    for i, (r_, ro_, ch_) in enumerate(outs):
+        st = streams[i % 6]
+        api.find_device(ix, d_in.data_ptr(), d_off.data_ptr(), off, r_.data_ptr(), cap, ro_.data_ptr(), 1e-7, 25, st.cuda_stream)
+        api.matches_device(ix, d_in.data_ptr(), d_off.data_ptr(), off, ch_.data_ptr(), 1e-7, st.cuda_stream)
+    torch.cuda.synchronize()
+    for r_, ro_, ch_ in outs:
+        assert torch.equal(ro_, d_roff) and torch.equal(ch_, d_out)
+        assert torch.equal(r_[:int(roff[-1]) * 7], d_rle[:int(roff[-1]) * 7])
 
 
 # ------------------------------------------------------ call / map with refinement ---

@@ -275,13 +275,13 @@ static int host_threshold(uint64_t k, uint64_t n_kmers, uint64_t alphabet, doubl
 // index upload: SubsetMatrix rows + LCS -> interleaved rank words + padded LCS
 // ---------------------------------------------------------------------------
 // links array (kernels.cuh IndexView::links) from the device LCS bytes; called by both builders
-static int build_links(kbo_index* ix, uint64_t n) {
+static int build_links(kbo_index* ix, uint64_t n, bool with_prefix_table = true) {
     lcs_links_kernel<<<(unsigned)((n + 1 + 255) / 256), 256>>>(ix->d_lcs, (uint32_t)n, ix->d_links);
     LAUNCHED();
     CUDA_TRY(cudaGetLastError());
     ix->view.links = ix->d_links;
     ix->view.pref = nullptr;
-    if (ix->view.k >= PREF_MIN_K && g_prefix_table.load()) {
+    if (with_prefix_table && ix->view.k >= PREF_MIN_K && g_prefix_table.load()) {
         // states after 1, 2, ... PREF_LEN bases, level by level (odd levels in `a`, even levels in `b`; the last is kept)
         const size_t last = (size_t)1 << (2 * PREF_LEN);
         uint4 *a = nullptr, *b = nullptr;
@@ -356,8 +356,10 @@ struct TmpBufs {
     }
 };
 
+// device_only: the index will only serve K1 on short queries (the per-call index of `ref_seq` in kbo::call): no
+// host copy of the SubsetMatrix form, no prefix-state table.
 static int build_index_gpu(kbo_index* ix, const uint8_t* const* seqs, const uint64_t* lens, uint64_t n_seqs, uint32_t k,
-                           bool revcomp, bool keep_nodes) {
+                           bool revcomp, bool keep_nodes, bool device_only = false) {
     uint64_t total = 0;
     std::vector<uint64_t> offsets(n_seqs + 1, 0);
     for (uint64_t i = 0; i < n_seqs; ++i) { total += lens[i]; offsets[i + 1] = total; }
@@ -492,6 +494,13 @@ static int build_index_gpu(kbo_index* ix, const uint8_t* const* seqs, const uint
     h.k = k;
     h.n_sets = n;
     h.n_kmers = nR;
+    ix->rank_stride = stride;
+    ix->view.rank = ix->d_rank;
+    ix->view.rank_stride = (uint32_t)stride;
+    ix->view.lcs = ix->d_lcs;
+    ix->view.n = (uint32_t)n;
+    ix->view.k = k;
+    if (device_only) return build_links(ix, n, false);
     std::vector<uint32_t> rows32((size_t)(4 * stride));
     CUDA_TRY(cudaMemcpy(rows32.data(), d_rows32, 4 * stride * 4, cudaMemcpyDeviceToHost));
     h.lcs.resize((size_t)n);
@@ -512,12 +521,6 @@ static int build_index_gpu(kbo_index* ix, const uint8_t* const* seqs, const uint
         CUDA_TRY(cudaMemcpy(h.node_hi.data(), d_Pkey, n * 8, cudaMemcpyDeviceToHost));
         CUDA_TRY(cudaMemcpy(h.node_len.data(), d_Plen, n, cudaMemcpyDeviceToHost));
     }
-    ix->rank_stride = stride;
-    ix->view.rank = ix->d_rank;
-    ix->view.rank_stride = (uint32_t)stride;
-    ix->view.lcs = ix->d_lcs;
-    ix->view.n = (uint32_t)n;
-    ix->view.k = k;
     return build_links(ix, n);
 }
 
@@ -1525,8 +1528,19 @@ static int call_impl(kbo_index* query_index, const uint8_t* ref_seq, uint64_t le
     kbo_index* ref_index = nullptr;
     const uint8_t* seqs[1] = {ref_seq};
     const uint64_t lens[1] = {len};
-    rc = kbo_index_build(seqs, lens, 1, &o, query_index->device, &ref_index);  // lib.rs:553
-    if (rc) return rc;
+    if (o.k >= 2 && o.k <= 32 && !g_host_builder.load()) {  // lib.rs:553; only its device arrays are used below
+        if (len == 0) return fail(KBO_ERR_EMPTY_INPUT, "no input sequences (index.rs:60)");
+        DeviceGuard dg(query_index->device);
+        if (!dg.ok) return fail(KBO_ERR_CUDA, "cudaSetDevice failed");
+        ref_index = new kbo_index();
+        ref_index->device = query_index->device;
+        ref_index->host.k = o.k;
+        rc = build_index_gpu(ref_index, seqs, lens, 1, o.k, o.add_revcomp != 0, false, true);
+        if (rc) { kbo_index_free(ref_index); return rc; }
+    } else {
+        rc = kbo_index_build(seqs, lens, 1, &o, query_index->device, &ref_index);
+        if (rc) return rc;
+    }
     if (ref_index->host.k != query_index->host.k) {  // lib.rs:559
         kbo_index_free(ref_index);
         return fail(KBO_ERR_K_MISMATCH, "k of the reference index differs from k of the query index (lib.rs:559)");

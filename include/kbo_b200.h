@@ -193,7 +193,9 @@ typedef struct kbo_ms_counters {
 } kbo_ms_counters;
 int kbo_set_profile_counters(int enabled);
 int kbo_get_ms_counters(const kbo_index* ix, kbo_ms_counters* out);
-/* Tuning knob: bases per MS chunk (0 = automatic).  Results never depend on it. */
+/* Tuning knob: bases per MS chunk.  0 = automatic: from the batch size, and for the stream-ordered (_device) entry
+ * points also from the number of distinct caller streams among the last 8 calls (overlapping calls get longer chunks:
+ * less warm-up work per base; a lone call gets the chunk length that makes it finish soonest).  Results never depend on it. */
 int kbo_set_chunk_len(uint32_t chunk_len);
 /* Tuning knob: number of concurrent sub-batches inside the device-pointer batch calls (0 = automatic). */
 int kbo_set_device_parts(uint32_t parts);

@@ -227,6 +227,27 @@ def config_dict(args, sample_note=None):
     return c
 
 
+def pin_to_gpu_numa_node(torch, dev):
+    """Multi-GPU boxes: run this rank's host threads (and first-touch its pinned buffers) on the CPUs local to its GPU,
+    so that the end-to-end copies do not cross the socket interconnect.  Best effort; returns a note for the JSON line."""
+    try:
+        bus = torch.cuda.get_device_properties(dev).pci_bus_id
+        dom = torch.cuda.get_device_properties(dev).pci_domain_id
+        devn = torch.cuda.get_device_properties(dev).pci_device_id
+        path = "/sys/bus/pci/devices/%04x:%02x:%02x.0/local_cpulist" % (dom, bus, devn)
+        cpus = set()
+        for part in open(path).read().strip().split(","):
+            a, _, b = part.partition("-")
+            cpus.update(range(int(a), int(b or a) + 1))
+        cpus &= os.sched_getaffinity(0)
+        if cpus:
+            os.sched_setaffinity(0, cpus)
+            return "rank pinned to the %d CPUs local to its GPU" % len(cpus)
+    except Exception as ex:  # topology not exposed (containers): keep the inherited affinity
+        return "no NUMA pinning (%s)" % type(ex).__name__
+    return None
+
+
 # --------------------------------------------------------------------------------------- our arm ---
 def run_ours(args, rank, local_rank, world):
     import torch
@@ -237,6 +258,7 @@ def run_ours(args, rank, local_rank, world):
         raise SystemExit("bench.py: no CUDA device (kbo_b200 has no CPU fallback)")
     dev = local_rank
     torch.cuda.set_device(dev)
+    numa_note = pin_to_gpu_numa_node(torch, dev) if world > 1 else None
     dist = None
     if world > 1:
         if os.environ.get("NCCL_DEBUG", "").upper() == "VERSION":
@@ -443,6 +465,8 @@ def run_ours(args, rank, local_rank, world):
                     "n_sets": index.n_sets, "index_build_s_host": round(index_build_s, 2), "rle_records_per_step": n_rle,
                     "streams": len(workers),
                     "parallelism": "replicated index, %d rank(s) x own batches" % world})
+        if numa_note:
+            cfg["host_affinity"] = numa_note
         if tuned is not None:
             tuned["note"] = ("same timed region with kbo_set_chunk_len(%d): less chunk warm-up work per base; suits "
                              "overlapped launches, not a lone one (K1 alone is slower at this chunk length)" % tuned["chunk_len"])

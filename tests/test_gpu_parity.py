@@ -498,6 +498,53 @@ def test_find_mixed_query_sizes_and_gap_lengths():
         api.set_ms_flags(0)
 
 
+@pytest.mark.parametrize("seed", list(range(8)))
+def test_randomised_small_configurations(seed):
+    """Random k, reference sizes, error probabilities and query mixes (tiny indexes, k below the prefix-table limit,
+    thresholds equal to k -> K2, N-rich and unrelated queries): query_sbwt (d, l, r), matches and find vs the oracle."""
+    rng = np.random.default_rng(1000 + seed)
+    for _ in range(4):
+        k = int(rng.integers(3, 33))
+        n_ref = int(rng.choice([k + 5, 200, 1500, 20_000]))
+        ref = synth.random_seq(max(n_ref, k + 1), int(rng.integers(1 << 30))).tobytes()
+        revcomp = bool(rng.integers(2))
+        o = O.OracleIndex([ref], k=k, add_revcomp=revcomp)
+        ix = api.build([ref], api.BuildOpts(k=k, add_revcomp=revcomp))
+        assert (ix.n_sets, ix.n_kmers) == (o.n_sets, o.n_kmers)
+        asm = synth.mutate(np.frombuffer(ref, dtype=np.uint8), int(rng.integers(1 << 30)), snp=0.03, indel=0.003).tobytes()
+        queries = []
+        for _q in range(int(rng.integers(1, 25))):
+            n = int(rng.integers(3, min(len(asm), 3000) + 1))
+            a = int(rng.integers(0, len(asm) - n + 1))
+            q = asm[a:a + n]
+            u = rng.random()
+            if u < 0.2:
+                q = with_ns(q, int(rng.integers(1 << 30)), 0.05)
+            elif u < 0.3:
+                q = rand_seq(n, int(rng.integers(1 << 30)))
+            queries.append(q)
+        d, l, r, off = api.query_sbwt_batch(queries, ix)
+        for i, q in enumerate(queries):
+            od, ol, orr = o.query_sbwt(q)
+            a, b_ = int(off[i]), int(off[i + 1])
+            assert np.array_equal(d[a:b_].astype(np.uint64), od), (k, i)
+            assert np.array_equal(l[a:b_].astype(np.uint64), ol) and np.array_equal(r[a:b_].astype(np.uint64), orr), (k, i)
+        p = float(rng.choice([1e-7, 1e-3, 0.05]))
+        try:
+            want = [o.matches(q, p) for q in queries]
+        except O.OraclePanic:
+            continue  # e.g. threshold <= 1 for this (k, n_kmers, p): the reference panics, nothing to compare
+        got = api.matches_batch(queries, ix, api.MatchOpts(max_error_prob=p))
+        assert got == want, (k, p)
+        gap = int(rng.choice([0, 3, 50]))
+        try:
+            want_f = [o.find(q, p, gap) for q in queries]
+        except O.OraclePanic:
+            continue  # format.rs:176 panics on an alignment that starts with 'R'
+        got_f = api.find_batch(queries, ix, api.FindOpts(max_error_prob=p, max_gap_len=gap))
+        assert [rle_tuples(g_) for g_ in got_f] == want_f, (k, p, gap)
+
+
 def test_device_pointer_entry_points_match_host_entry_points():
     """kbo_matches_batch_device / kbo_find_batch_device on torch-owned device memory and stream."""
     import torch

@@ -378,7 +378,7 @@ def run_ours(args, rank, local_rank, world):
         pb.array[:] = b
     pinned_np = [pb.array for pb in pinned_keep]
     n_thr = max(1, args.e2e_threads)
-    fbufs = [api.FindBuffers(nq) for _ in range(n_thr)]
+    fbufs = [api.FindBuffers(nq, pinned=True) for _ in range(n_thr)]
     n_rle_box = [0] * n_thr
 
     def e2e_worker(t, first, count):

@@ -152,7 +152,8 @@ int kbo_matches_batch_device(const kbo_index* ix, const uint8_t* d_concat, const
                              const uint64_t* host_offsets, uint64_t n_queries, double max_error_prob,
                              uint8_t* d_chars_out, void* stream);
 /* kbo::find (lib.rs:808-821) for a CSR batch: matches + run_lengths[_gapped].  RLEs of query i are
- * rle_out[rle_offsets[i] .. rle_offsets[i+1]) (rle_offsets has n_queries+1 entries). */
+ * rle_out[rle_offsets[i] .. rle_offsets[i+1]) (rle_offsets has n_queries+1 entries).  `concat` and `rle_out` may be
+ * pageable; page-locked buffers (kbo_alloc_pinned) are read / written in place by the copy engines. */
 int kbo_find_batch(const kbo_index* ix, const uint8_t* concat, const uint64_t* offsets, uint64_t n_queries,
                    double max_error_prob, uint64_t max_gap_len, kbo_rle* rle_out, uint64_t rle_cap,
                    uint64_t* rle_offsets);

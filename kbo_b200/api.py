@@ -451,9 +451,13 @@ class PinnedBytes:
 class FindBuffers:
     """Reusable output buffers for find_csr (avoids reallocating per call in a timed loop)."""
 
-    def __init__(self, n_queries, cap=None):
+    def __init__(self, n_queries, cap=None, pinned=False):
         self.cap = cap or (8 * n_queries + 1024)
-        self.rle = (RleC * self.cap)()
+        if pinned:  # page-locked records buffer: kbo_find_batch lets the copy engine write into it directly
+            self._pin = PinnedBytes(self.cap * C.sizeof(RleC))
+            self.rle = (RleC * self.cap).from_address(self._pin._p.value)
+        else:
+            self.rle = (RleC * self.cap)()
         self.rle_offsets = np.zeros(n_queries + 1, dtype=np.uint64)
 
 

@@ -1383,6 +1383,12 @@ int kbo_find_batch(const kbo_index* cix, const uint8_t* concat, const uint64_t* 
         rc = body();
     }
     // phase 2: per sub-batch, in order: record count -> K4 records -> asynchronous copy-out of the records
+    bool out_is_pinned = false;
+    if (rle_out) {
+        cudaPointerAttributes attr;
+        if (cudaPointerGetAttributes(&attr, rle_out) == cudaSuccess) out_is_pinned = attr.type == cudaMemoryTypeHost;
+        cudaGetLastError();
+    }
     uint64_t base = 0;
     std::vector<uint64_t> part_base(np, 0), part_n(np, 0);
     rle_offsets[0] = 0;
@@ -1402,10 +1408,15 @@ int kbo_find_batch(const kbo_index* cix, const uint8_t* concat, const uint64_t* 
             if (n_rle) {
                 if (!rle_out) return fail(KBO_ERR_BAD_ARGUMENT, "rle_out is null");
                 CUDA_TRY(ws->out2.ensure(n_rle * sizeof(RleRecord), st));
-                CUDA_TRY(ws->h_rle.ensure(n_rle * sizeof(RleRecord)));
                 int rc2 = run_rle_records(ws, ws->out2.as<RleRecord>(), n_rle);
                 if (rc2) return rc2;
-                CUDA_TRY(cudaMemcpyAsync(ws->h_rle.p, ws->out2.p, n_rle * sizeof(RleRecord), cudaMemcpyDeviceToHost, st));
+                if (out_is_pinned) {  // page-locked caller buffer: the copy engine writes the records in place
+                    CUDA_TRY(cudaMemcpyAsync(rle_out + part_base[s], ws->out2.p, n_rle * sizeof(RleRecord),
+                                             cudaMemcpyDeviceToHost, st));
+                } else {
+                    CUDA_TRY(ws->h_rle.ensure(n_rle * sizeof(RleRecord)));
+                    CUDA_TRY(cudaMemcpyAsync(ws->h_rle.p, ws->out2.p, n_rle * sizeof(RleRecord), cudaMemcpyDeviceToHost, st));
+                }
             }
             return KBO_OK;
         };
@@ -1418,7 +1429,8 @@ int kbo_find_batch(const kbo_index* cix, const uint8_t* concat, const uint64_t* 
         if (s + 1 == np && !rc) cudaEventRecord(wss[s]->ev1, wss[s]->stream);
         cudaError_t e = cudaStreamSynchronize(wss[s]->stream);
         if (e != cudaSuccess && !rc) rc = fail(KBO_ERR_CUDA, std::string("CUDA error: ") + cudaGetErrorString(e));
-        if (!rc && part_n[s]) std::memcpy(rle_out + part_base[s], wss[s]->h_rle.p, part_n[s] * sizeof(RleRecord));
+        if (!rc && part_n[s] && !out_is_pinned)
+            std::memcpy(rle_out + part_base[s], wss[s]->h_rle.p, part_n[s] * sizeof(RleRecord));
     }
     if (!rc && np == 1) {
         float ms = 0.f;

@@ -17,15 +17,20 @@
  *    allocated.  The library never frees caller memory.
  *  - Host-pointer entry points copy host->device and device->host inside the
  *    call.  `_device` entry points take CUDA device pointers (same device as
- *    the index) and an optional cudaStream_t (as void*; NULL = the library's
- *    own stream) and are asynchronous only with respect to that stream.
+ *    the index) and a cudaStream_t (as void*; NULL = the legacy default
+ *    stream) and are asynchronous only with respect to that stream.  The library
+ *    never changes attributes of a caller's stream.
  *  - Widths: the device works in u8 (MS length, alignment characters) and u32
  *    (colex ranks, n_sets < 2^32).  Entry points without a `_compact` suffix
  *    widen to the reference's usize/i64 on the way out; alignment characters
  *    are 1 byte each (Rust `char` is 4; the shim widens).
  *  - All functions are thread-safe; an index handle is immutable after
  *    creation and may be shared by concurrent callers (reference functions take
- *    `&SbwtIndexVariant`, src/lib.rs:612-617).
+ *    `&SbwtIndexVariant`, src/lib.rs:612-617).  Concurrent `_device` calls that
+ *    pass the same stream are serialised on that stream's workspace.
+ *  - Device-wide state the library changes: creating an index raises
+ *    cudaLimitPersistingL2CacheSize (never lowered again) so that the library's
+ *    own streams can mark the index as persisting in L2.
  *  - There is no CPU fallback: without a CUDA device every compute entry point
  *    fails with KBO_ERR_CUDA.
  * ======================================================================== */
@@ -52,7 +57,8 @@ typedef enum kbo_status {
     KBO_ERR_OOM = 9,              /* host or device allocation failed */
     KBO_ERR_INDEX_TOO_LARGE = 10, /* n_sets >= 2^32 */
     KBO_ERR_BUFFER_TOO_SMALL = 11,/* caller capacity too small (count is still returned) */
-    KBO_ERR_PANIC = 12            /* the reference would panic on these inputs (index out of bounds etc.) */
+    KBO_ERR_PANIC = 12,           /* the reference would panic on these inputs (index out of bounds etc.) */
+    KBO_ERR_BATCH_TOO_LARGE = 13  /* a device-resident batch of >= 2^32 - 2^20 positions (host-buffer calls split internally) */
 } kbo_status;
 
 #define KBO_MAX_K 64 /* packed k-mers are two 64-bit words; reference tests use k <= 63 */
@@ -62,7 +68,7 @@ typedef struct kbo_build_opts {
     uint32_t k;              /* default 31 */
     int32_t add_revcomp;     /* default 0 */
     uint32_t num_threads;    /* default 1 (host-side sort threads) */
-    uint32_t prefix_precalc; /* default 8; ignored (no prefix table is needed on the device) */
+    uint32_t prefix_precalc; /* default 8; ignored (the device keeps its own table of the MS states after 10 bases) */
     int32_t build_select;    /* default 0; != 0 keeps the sorted nodes on the host for O(1) access_kmer (map/call);
                               * without it access_kmer walks the index (slower, same result) */
     uint32_t mem_gb;         /* ignored */
@@ -93,8 +99,10 @@ int kbo_index_build(const uint8_t* const* seqs, const uint64_t* lens, uint64_t n
                     int device, kbo_index** out);
 /* Upload an index built elsewhere (e.g. by the sbwt crate): 4 subset-matrix bit rows of
  * ceil(n_sets/64) little-endian u64 words (bit i of row c = node i has outgoing label c,
- * A,C,G,T order) and n_sets LCS bytes.  `kmers_colex` may be NULL (then access_kmer walks
- * the index); otherwise it is ignored in this version. */
+ * A,C,G,T order) and n_sets LCS bytes (LCS[0] == 0, every value < k).  1 <= k <= 127 here (LCS bytes are compared
+ * seven bits wide on the device); KBO_MAX_K bounds kbo_index_build only.  The arrays are validated (LCS range, and
+ * the rows must hold exactly n_sets - 1 set bits: every node but the root has one incoming edge);
+ * KBO_ERR_BAD_ARGUMENT otherwise.  access_kmer on such an index walks the index (no stored nodes). */
 int kbo_index_from_parts(uint32_t k, uint64_t n_sets, uint64_t n_kmers, const uint64_t* const rows[4],
                          const uint8_t* lcs, int device, kbo_index** out);
 void kbo_index_free(kbo_index* ix);
@@ -157,6 +165,17 @@ int kbo_matches_batch_device(const kbo_index* ix, const uint8_t* d_concat, const
 int kbo_find_batch(const kbo_index* ix, const uint8_t* concat, const uint64_t* offsets, uint64_t n_queries,
                    double max_error_prob, uint64_t max_gap_len, kbo_rle* rle_out, uint64_t rle_cap,
                    uint64_t* rle_offsets);
+/* Asynchronous form of kbo_find_batch: the copy-in and all kernels of the batch are enqueued and the call returns;
+ * kbo_job_wait blocks until the results are in rle_out / rle_offsets, returns the number of records in *n_rle (may be
+ * NULL) and destroys the job.  One host thread can keep several batches in flight (submit, submit, wait, submit, ...).
+ * All buffers must stay valid until the wait.  With page-locked `rle_out` and `rle_offsets` (kbo_alloc_pinned) the
+ * device writes the results straight into them and the job needs a single synchronisation; `concat` and `offsets`
+ * should be page-locked too, otherwise the copy-in is staged by the driver inside the submit call. */
+typedef struct kbo_job kbo_job;
+int kbo_find_batch_submit(const kbo_index* ix, const uint8_t* concat, const uint64_t* offsets, uint64_t n_queries,
+                          double max_error_prob, uint64_t max_gap_len, kbo_rle* rle_out, uint64_t rle_cap,
+                          uint64_t* rle_offsets, kbo_job** job);
+int kbo_job_wait(kbo_job* job, uint64_t* n_rle);
 /* Device-resident form of kbo_find_batch: d_concat, d_offsets, d_rle_out (rle_cap records) and d_rle_offsets
  * (n_queries+1 u64) are device pointers; asynchronous on `stream`.  If more than rle_cap records are found
  * only the first rle_cap are stored; d_rle_offsets[n_queries] always holds the true count. */

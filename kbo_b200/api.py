@@ -28,7 +28,7 @@ u8p, u32p, u64p, i64p = C.POINTER(C.c_uint8), C.POINTER(C.c_uint32), C.POINTER(C
 
 STATUS_NAMES = {0: "OK", 1: "EMPTY_INPUT", 2: "BAD_THRESHOLD", 3: "TOO_SHORT", 4: "BAD_K", 5: "K_MISMATCH",
                 6: "BAD_PROB", 7: "BAD_ARGUMENT", 8: "CUDA", 9: "OOM", 10: "INDEX_TOO_LARGE", 11: "BUFFER_TOO_SMALL",
-                12: "PANIC"}
+                12: "PANIC", 13: "BATCH_TOO_LARGE"}
 
 # every symbol include/kbo_b200.h declares (tests check that the library exports all of them)
 EXPORTED_SYMBOLS = [
@@ -38,7 +38,7 @@ EXPORTED_SYMBOLS = [
     "kbo_index_access_kmer", "kbo_index_search", "kbo_query_sbwt", "kbo_query_sbwt_batch_compact",
     "kbo_log_rm_max_cdf", "kbo_random_match_threshold", "kbo_derandomize_ms_vec", "kbo_translate_ms_vec",
     "kbo_run_lengths_gapped", "kbo_relative_to_ref", "kbo_matches", "kbo_matches_batch", "kbo_matches_batch_device",
-    "kbo_find_batch", "kbo_find_batch_device", "kbo_map_unrefined", "kbo_call", "kbo_map", "kbo_set_profile_counters", "kbo_get_ms_counters", "kbo_set_chunk_len", "kbo_set_l2_persist", "kbo_set_prefix_table", "kbo_set_host_builder", "kbo_set_pipeline_parts", "kbo_set_device_parts", "kbo_set_ms_flags",
+    "kbo_find_batch", "kbo_find_batch_submit", "kbo_job_wait", "kbo_find_batch_device", "kbo_map_unrefined", "kbo_call", "kbo_map", "kbo_set_profile_counters", "kbo_get_ms_counters", "kbo_set_chunk_len", "kbo_set_l2_persist", "kbo_set_prefix_table", "kbo_set_host_builder", "kbo_set_pipeline_parts", "kbo_set_device_parts", "kbo_set_ms_flags",
     "kbo_kernel_launch_count", "kbo_last_kernel_ms", "kbo_set_kernel_timing", "kbo_collect_kernel_times",
     "kbo_measure_random_sector_rate",
 ]
@@ -115,6 +115,9 @@ def load_library():
                                            C.c_void_p, C.c_void_p]
     L.kbo_find_batch.argtypes = [C.c_void_p, u8p, u64p, C.c_uint64, C.c_double, C.c_uint64, C.POINTER(RleC),
                                  C.c_uint64, u64p]
+    L.kbo_find_batch_submit.argtypes = [C.c_void_p, u8p, u64p, C.c_uint64, C.c_double, C.c_uint64, C.POINTER(RleC),
+                                        C.c_uint64, u64p, C.POINTER(C.c_void_p)]
+    L.kbo_job_wait.argtypes = [C.c_void_p, u64p]
     L.kbo_find_batch_device.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, u64p, C.c_uint64, C.c_double, C.c_uint64,
                                         C.c_void_p, C.c_uint64, C.c_void_p, C.c_void_p]
     L.kbo_call.argtypes = [C.c_void_p, u8p, C.c_uint64, C.c_double, C.POINTER(BuildOptsC), u64p, u32p, u32p, u8p, u8p,
@@ -449,16 +452,45 @@ class PinnedBytes:
 
 
 class FindBuffers:
-    """Reusable output buffers for find_csr (avoids reallocating per call in a timed loop)."""
+    """Reusable output buffers for find_csr / find_submit (avoids reallocating per call in a timed loop)."""
 
     def __init__(self, n_queries, cap=None, pinned=False):
         self.cap = cap or (8 * n_queries + 1024)
-        if pinned:  # page-locked records buffer: kbo_find_batch lets the copy engine write into it directly
+        if pinned:  # page-locked outputs: the last kernel of kbo_find_batch writes records and offsets into them directly
             self._pin = PinnedBytes(self.cap * C.sizeof(RleC))
             self.rle = (RleC * self.cap).from_address(self._pin._p.value)
+            self._pin_off = PinnedBytes((n_queries + 1) * 8)
+            self.rle_offsets = self._pin_off.array.view(np.uint64)
         else:
             self.rle = (RleC * self.cap)()
-        self.rle_offsets = np.zeros(n_queries + 1, dtype=np.uint64)
+            self.rle_offsets = np.zeros(n_queries + 1, dtype=np.uint64)
+
+
+class FindJob:
+    """One kbo::find batch in flight (kbo_find_batch_submit); wait() returns the number of RLE records."""
+
+    def __init__(self, handle, buffers, keep):
+        self._h, self.buffers, self._keep = handle, buffers, keep
+
+    def wait(self):
+        n = C.c_uint64(0)
+        h, self._h = self._h, None
+        _check(load_library().kbo_job_wait(h, C.byref(n)))
+        self._keep = None
+        return int(n.value)
+
+
+def find_submit(concat, offsets, index, find_opts=None, buffers=None):
+    """kbo_find_batch_submit: enqueue one CSR batch (ideally page-locked arrays in, FindBuffers(pinned=True) out) and
+    return a FindJob; several jobs may be in flight from one host thread."""
+    o = find_opts or FindOpts()
+    nq = len(offsets) - 1
+    buf = buffers or FindBuffers(nq, pinned=True)
+    h = C.c_void_p()
+    _check(load_library().kbo_find_batch_submit(index._h, _p(concat, C.c_uint8), _p(offsets, C.c_uint64), nq,
+                                                o.max_error_prob, o.max_gap_len, buf.rle, buf.cap,
+                                                _p(buf.rle_offsets, C.c_uint64), C.byref(h)))
+    return FindJob(h, buf, (concat, offsets))
 
 
 def find_csr(concat, offsets, index, find_opts=None, buffers=None):

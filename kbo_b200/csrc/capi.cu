@@ -95,6 +95,8 @@ struct PinnedBuf {  // page-locked host staging: copies to/from it are truly asy
 };
 
 struct Workspace {
+    std::mutex mu;  // held for the whole enqueue section of the stream-ordered (_device) entry points: a workspace bound
+                    // to a caller stream (NULL included) is shared by every host thread that passes that stream
     PinnedBuf h_rel, h_roff, h_rle;
     std::vector<Workspace*> subs;          // per-part workspaces with their own streams (device-pointer calls)
     cudaEvent_t ev_fork = nullptr;
@@ -102,19 +104,19 @@ struct Workspace {
     cudaStream_t stream = nullptr;
     bool own_stream = false;
     cudaEvent_t ev0 = nullptr, ev1 = nullptr;
-    DevBuf ascii, offsets, pack, inv, sep, wq, ms, l, r, out, out2, out3, tmp64, counters;
+    DevBuf ascii, offsets, pack, inv, sep, wq, ms, l, r, out, out2, out3, tmp64, counters, counters2;
+    PinnedBuf h_count;
     DevBuf masks, rle_words, rle_cnt, rle_cse, rle_tickets;  // K2b<false> masks and the K4 arrays
-    RleParams rle;                                       // filled by run_rle_offsets, reused by run_rle_records
     std::vector<cudaEvent_t> timing;  // 4 events per timed call (before K0, after K0, after K1, after K2)
     size_t timed_calls = 0;
     void destroy() {
         for (cudaEvent_t e : timing) cudaEventDestroy(e);
-        h_rel.release(); h_roff.release(); h_rle.release();
+        h_rel.release(); h_roff.release(); h_rle.release(); h_count.release();
         for (Workspace* w : subs) { w->destroy(); delete w; }
         if (ev_fork) cudaEventDestroy(ev_fork);
         for (cudaEvent_t e : ev_join) cudaEventDestroy(e);
         DevBuf* all[] = {&ascii, &offsets, &pack, &inv, &sep, &wq, &ms, &l, &r, &out, &out2, &out3,
-                         &tmp64, &counters, &masks, &rle_words, &rle_cnt, &rle_cse, &rle_tickets};
+                         &tmp64, &counters, &counters2, &masks, &rle_words, &rle_cnt, &rle_cse, &rle_tickets};
         for (DevBuf* b : all) b->release();
         if (ev0) cudaEventDestroy(ev0);
         if (ev1) cudaEventDestroy(ev1);
@@ -232,21 +234,47 @@ static int stream_ws(kbo_index* ix, cudaStream_t st, Workspace** out) {
     if (it != ix->by_stream.end()) { *out = it->second; return KBO_OK; }
     Workspace* ws = new Workspace();
     ws->stream = st;
-    ws->own_stream = false;
-    apply_l2_window(ix, st);
+    ws->own_stream = false;  // caller-owned stream: its attributes (access-policy window) are left alone
     ix->by_stream[st] = ws;
     *out = ws;
     return KBO_OK;
 }
 
+// Does the calling thread already have a CUDA context bound?  (Driver entry point looked up at run time so that the
+// library has no link-time dependency on libcuda and still loads on a box without a driver.)
+static bool thread_has_context() {
+    typedef int (*ctx_get_current_t)(void**);
+    static const ctx_get_current_t fn = []() -> ctx_get_current_t {
+        void* p = nullptr;
+        cudaDriverEntryPointQueryResult q;
+        if (cudaGetDriverEntryPoint("cuCtxGetCurrent", &p, cudaEnableDefault, &q) != cudaSuccess || !p) {
+            cudaGetLastError();
+            return nullptr;
+        }
+        return reinterpret_cast<ctx_get_current_t>(p);
+    }();
+    if (!fn) return true;  // unknown: behave like a thread that has one
+    void* ctx = nullptr;
+    return fn(&ctx) == 0 && ctx != nullptr;
+}
+
+// Makes the index's device current for the duration of a call.  The previous device is restored only when the
+// thread really had a context on it: a fresh host thread reports device 0 as "current" without having touched it,
+// and cudaSetDevice(0) on the way out would create a primary context on GPU 0 from every worker thread of every
+// rank (round-1 finding: GPU 0 busy 21 % at 8 ranks while the other GPUs stayed at 1 %).
 struct DeviceGuard {
     int prev = -1;
     bool ok = true;
+    bool restore = false;
     explicit DeviceGuard(int dev) {
+        const bool had_ctx = thread_has_context();
         if (cudaGetDevice(&prev) != cudaSuccess) { ok = false; return; }
-        if (prev != dev && cudaSetDevice(dev) != cudaSuccess) ok = false;
+        if (prev != dev) {
+            if (cudaSetDevice(dev) != cudaSuccess) ok = false;
+            else restore = had_ctx;
+        }
     }
-    ~DeviceGuard() { if (prev >= 0) cudaSetDevice(prev); }
+    ~DeviceGuard() { if (restore) cudaSetDevice(prev); }
 };
 
 // ---------------------------------------------------------------------------
@@ -652,10 +680,11 @@ static int run_derand_translate(kbo_index* ix, Workspace* ws, const QueryView& q
     return KBO_OK;
 }
 
-// K4 up to the per-query record offsets: word counts -> START/END marks -> offsets (the scans are inside).
-// d_offsets are the batch's own CSR offsets (offsets[0] may be non-zero); d_rle_offsets gets nq + 1 entries.
-static int run_rle_offsets(Workspace* ws, const QueryView& qv, const Geometry& g, const uint64_t* d_offsets, uint64_t nq,
-                           uint32_t max_gap_len, uint64_t* d_rle_offsets) {
+// K4, first two launches: word counts -> START/END marks (the scans are inside).  Returns the parameter block for
+// run_rle_finish BY VALUE (workspaces bound to caller streams can be shared between host threads).
+// d_offsets are the batch's own CSR offsets (offsets[0] may be non-zero).
+static int run_rle_counts(Workspace* ws, const QueryView& qv, const Geometry& g, const uint64_t* d_offsets, uint64_t nq,
+                          uint32_t max_gap_len, RleParams* out_params) {
     cudaStream_t st = ws->stream;
     const uint64_t nw = g.n_tiles_b * 32;
     const uint64_t nb = (nw + RLE_BLOCK - 1) / RLE_BLOCK;
@@ -666,7 +695,8 @@ static int run_rle_offsets(Workspace* ws, const QueryView& qv, const Geometry& g
         CUDA_TRY(ws->rle_tickets.ensure(8, st));
         CUDA_TRY(cudaMemsetAsync(ws->rle_tickets.p, 0, 8, st));  // the kernels leave them at zero
     }
-    RleParams& p = ws->rle;
+    RleParams p;
+    std::memset(&p, 0, sizeof(p));
     p.gap = ws->masks.as<uint32_t>();
     p.match = p.gap + nw;
     p.rr = p.match + nw;
@@ -686,27 +716,30 @@ static int run_rle_offsets(Workspace* ws, const QueryView& qv, const Geometry& g
     p.cse = ws->rle_cse.as<uint64_t>();
     p.cse_blk = p.cse + nw;
     p.tickets = ws->rle_tickets.as<unsigned int>();
-    p.rle_offsets = d_rle_offsets;
-    p.out = nullptr;
-    p.cap = 0;
     rle_word_counts_kernel<<<(unsigned)nb, RLE_BLOCK, 0, st>>>(p);
     LAUNCHED();
     rle_mark_kernel<<<(unsigned)nb, RLE_BLOCK, 0, st>>>(p);
     LAUNCHED();
-    const unsigned threads = 128;
-    rle_query_offsets_kernel<<<(unsigned)((nq + 1 + threads - 1) / threads), threads, 0, st>>>(p);
-    LAUNCHED();
     CUDA_TRY(cudaGetLastError());
+    *out_params = p;
     return KBO_OK;
 }
 
-// K4 records (after run_rle_offsets on the same workspace): slots >= cap are dropped
-static int run_rle_records(Workspace* ws, RleRecord* d_out, uint64_t cap) {
-    RleParams& p = ws->rle;
-    p.out = d_out;
+// K4, last launch: per-query record offsets + the records.  `rle_offsets` (nq + 1 entries) and `out` (`cap` records)
+// must be device-visible: device memory, or page-locked host memory mapped into the device (the kernel then writes
+// the results straight into the caller's buffer and no device->host copy follows).  `base_in` / `total_out` chain
+// the sub-batches of one host call (RleParams).
+static int run_rle_finish(cudaStream_t st, RleParams p, uint64_t* rle_offsets, RleRecord* out, uint64_t cap,
+                          const uint64_t* base_in = nullptr, uint64_t* total_out = nullptr, bool write_first = true) {
+    p.rle_offsets = rle_offsets;
+    p.out = out;
     p.cap = cap;
+    p.base_in = base_in;
+    p.total_out = total_out;
+    p.write_first = write_first ? 1u : 0u;
     const unsigned threads = 128;
-    rle_records_kernel<<<(unsigned)((p.n_words + threads - 1) / threads), threads, 0, ws->stream>>>(p);
+    const uint64_t items = std::max<uint64_t>(p.n_words, p.nq + 1);
+    rle_finish_kernel<<<(unsigned)((items + threads - 1) / threads), threads, 0, st>>>(p);
     LAUNCHED();
     CUDA_TRY(cudaGetLastError());
     return KBO_OK;
@@ -906,6 +939,18 @@ int kbo_index_from_parts(uint32_t k, uint64_t n_sets, uint64_t n_kmers, const ui
         if (n_sets & 63) h.rows[c][nw - 1] &= ~0ull >> (64 - (n_sets & 63));
     }
     h.lcs.assign(lcs, lcs + n_sets);
+    // K1 relies on these: LCS[0] == 0 stops every left scan, LCS bytes < k <= 127 keep the seven-bit compares
+    // exact, and every node but the root has exactly one incoming edge (so ranks stay inside [0, n_sets]).
+    bool lcs_ok = h.lcs[0] == 0;
+    for (uint64_t i = 0; i < n_sets && lcs_ok; ++i) lcs_ok = h.lcs[i] < k;
+    uint64_t bits = 0;
+    for (int c = 0; c < 4; ++c)
+        for (size_t w = 0; w < nw; ++w) bits += (uint64_t)__builtin_popcountll(h.rows[c][w]);
+    if (!lcs_ok || bits != n_sets - 1) {
+        delete ix;
+        return fail(KBO_ERR_BAD_ARGUMENT, !lcs_ok ? "LCS array invalid: need LCS[0] == 0 and every value < k"
+                                                  : "subset rows must hold exactly n_sets - 1 set bits");
+    }
     h.finalize();
     return finish_index(ix, device, out);
 }
@@ -1059,16 +1104,30 @@ static int matches_prologue(kbo_index* ix, const uint64_t* offsets, uint64_t nq,
     uint64_t t = 0;
     int rc = host_threshold(ix->host.k, ix->host.n_kmers, 4, p, &t);  // lib.rs:620
     if (rc) return rc;
-    rc = check_offsets(offsets, nq, 1, total);                          // index.rs:248
+    // the reference checks in this order: non-empty query (index.rs:248), threshold > 1 (derandomize.rs:275),
+    // len > 2 (derandomize.rs:276); one pass over the offsets when the threshold is fine
+    rc = check_offsets(offsets, nq, t <= 1 ? 1 : 3, total);
     if (rc) return rc;
     if (t <= 1) return fail(KBO_ERR_BAD_THRESHOLD, "threshold must be > 1 (derandomize.rs:275)");
-    rc = check_offsets(offsets, nq, 3, total);                          // derandomize.rs:276
-    if (rc) return rc;
     *thr = (uint32_t)t;
     return KBO_OK;
 }
 
 static std::vector<uint64_t> split_queries(const uint64_t* offsets, uint64_t nq, uint64_t parts);
+
+// K4 keeps its prefix counts (and K0 / K2b their word indices) in 32 bits: one launch sequence handles at most
+// KBO_MAX_LAUNCH_POSITIONS padded positions.  Host-buffer calls split larger batches into sub-batches; the
+// stream-ordered (_device) calls, which are one launch sequence, reject them.
+static const uint64_t KBO_MAX_LAUNCH_POSITIONS = (1ull << 32) - (1ull << 20);
+static uint64_t min_parts_for(uint64_t total, uint64_t nq) {
+    return (total + nq) / (KBO_MAX_LAUNCH_POSITIONS / 2) + 1;  // (halved: split points fall on query borders)
+}
+static int check_launch_size(uint64_t total, uint64_t nq) {
+    if (total + nq >= KBO_MAX_LAUNCH_POSITIONS)
+        return fail(KBO_ERR_BATCH_TOO_LARGE, "a device-resident batch must stay below 2^32 - 2^20 padded positions "
+                                             "(sum of lengths + number of queries); split it");
+    return KBO_OK;
+}
 
 // Sizes every buffer of a workspace for a WHOLE host call (not for the sub-batch it will run), so that a
 // workspace never has to be regrown -- cudaFree synchronises the device -- when calls alternate between one and
@@ -1135,7 +1194,7 @@ int kbo_matches_batch(const kbo_index* cix, const uint8_t* concat, const uint64_
     DeviceGuard dg(ix->device);
     if (!dg.ok) return fail(KBO_ERR_CUDA, "cudaSetDevice failed");
     const HostCallScope scope(ix);
-    const uint64_t want_parts = pick_parts(scope, total);
+    const uint64_t want_parts = std::max<uint64_t>(pick_parts(scope, total), min_parts_for(total, n_queries));
     const std::vector<uint64_t> cut = split_queries(offsets, n_queries, want_parts);
     const size_t np = cut.size() - 1;
     std::vector<Workspace*> wss(np, nullptr);
@@ -1210,11 +1269,16 @@ static int matches_device_forked(kbo_index* ix, Workspace* ws, const uint8_t* d_
     while (ws->subs.size() < np) {
         Workspace* sub = new Workspace();
         sub->own_stream = true;
-        ws->subs.push_back(sub);
-        CUDA_TRY(cudaStreamCreateWithFlags(&sub->stream, cudaStreamNonBlocking));
+        cudaEvent_t e = nullptr;
+        cudaError_t ce = cudaStreamCreateWithFlags(&sub->stream, cudaStreamNonBlocking);
+        if (ce == cudaSuccess) ce = cudaEventCreateWithFlags(&e, cudaEventDisableTiming);
+        if (ce != cudaSuccess) {  // keep subs and ev_join the same length
+            if (sub->stream) cudaStreamDestroy(sub->stream);
+            delete sub;
+            return fail(KBO_ERR_CUDA, std::string("CUDA error: ") + cudaGetErrorString(ce));
+        }
         apply_l2_window(ix, sub->stream);
-        cudaEvent_t e;
-        CUDA_TRY(cudaEventCreateWithFlags(&e, cudaEventDisableTiming));
+        ws->subs.push_back(sub);
         ws->ev_join.push_back(e);
     }
     if (!ws->ev_fork) CUDA_TRY(cudaEventCreateWithFlags(&ws->ev_fork, cudaEventDisableTiming));
@@ -1244,9 +1308,12 @@ int kbo_matches_batch_device(const kbo_index* cix, const uint8_t* d_concat, cons
     if (host_offsets[0] != 0) return fail(KBO_ERR_BAD_ARGUMENT, "device batches must have offsets[0] == 0");
     DeviceGuard dg(ix->device);
     if (!dg.ok) return fail(KBO_ERR_CUDA, "cudaSetDevice failed");
+    rc = check_launch_size(total, n_queries);
+    if (rc) return rc;
     Workspace* ws = nullptr;
     rc = stream_ws(ix, (cudaStream_t)stream, &ws);
     if (rc) return rc;
+    std::lock_guard<std::mutex> lk(ws->mu);
     rc = matches_device_forked(ix, ws, d_concat, d_offsets, host_offsets, n_queries, thr, d_chars_out);
     if (rc) return rc;
     if (g_profile_counters.load()) return fetch_counters(ix, ws);
@@ -1329,12 +1396,47 @@ static std::vector<uint64_t> split_queries(const uint64_t* offsets, uint64_t nq,
     return cut;
 }
 
-// kbo::find for a host CSR batch.  Large batches are cut into sub-batches that run on their own streams, so
-// the host->device copy of sub-batch i+1 overlaps the kernels of sub-batch i.
-int kbo_find_batch(const kbo_index* cix, const uint8_t* concat, const uint64_t* offsets, uint64_t n_queries,
-                   double max_error_prob, uint64_t max_gap_len, kbo_rle* rle_out, uint64_t rle_cap,
-                   uint64_t* rle_offsets) {
-    kbo_index* ix = const_cast<kbo_index*>(cix);
+// ---- kbo::find for host CSR batches: asynchronous jobs ---------------------------------------------------------
+// A job is one kbo::find batch in flight: copy-in, K0, K1, K2b (masks), K4 enqueued on the streams of its
+// workspaces, nothing synchronised until kbo_job_wait.  When the caller's output buffers are device-visible
+// (page-locked host memory from kbo_alloc_pinned / cudaHostAlloc / cudaHostRegister, or device memory) the last K4
+// kernel writes the records and the per-query offsets straight into them: no device->host copy, no record count on
+// the host in the middle of the call, ONE synchronisation per job.  Pageable output buffers take a staged path
+// (records in device memory, copied out when the count is known).
+struct kbo_job {
+    kbo_index* ix = nullptr;
+    std::vector<Workspace*> wss;
+    std::vector<RleParams> rle;      // per sub-batch (staged path: to re-run the last kernel with a larger buffer)
+    std::vector<uint64_t> cut;       // sub-batch query ranges
+    uint64_t nq = 0;
+    kbo_rle* rle_out = nullptr;
+    uint64_t rle_cap = 0;
+    uint64_t* rle_offsets = nullptr;
+    bool direct = false;
+    uint64_t staged_cap = 0;         // staged path: records the device buffer of wss[0] holds
+    int rc = KBO_OK;
+    std::string err;
+};
+
+// device-visible address of `p` if the device can write to it (page-locked / registered host, device, managed), else null
+static void* device_visible(const void* p) {
+    if (!p) return nullptr;
+    cudaPointerAttributes attr;
+    if (cudaPointerGetAttributes(&attr, p) != cudaSuccess) { cudaGetLastError(); return nullptr; }
+    if (attr.type == cudaMemoryTypeHost || attr.type == cudaMemoryTypeDevice || attr.type == cudaMemoryTypeManaged)
+        return attr.devicePointer;
+    return nullptr;
+}
+
+static void job_release(kbo_job* job) {
+    for (Workspace* w : job->wss) if (w) release_ws(job->ix, w);
+    job->wss.clear();
+}
+
+static int find_submit(kbo_index* ix, const uint8_t* concat, const uint64_t* offsets, uint64_t n_queries,
+                       double max_error_prob, uint64_t max_gap_len, kbo_rle* rle_out, uint64_t rle_cap,
+                       uint64_t* rle_offsets, uint64_t want_parts, kbo_job** out) {
+    *out = nullptr;
     if (!rle_offsets || !concat) return fail(KBO_ERR_BAD_ARGUMENT, "null argument");
     uint64_t total = 0;
     uint32_t thr = 0;
@@ -1343,102 +1445,167 @@ int kbo_find_batch(const kbo_index* cix, const uint8_t* concat, const uint64_t* 
     const uint32_t gap = (uint32_t)std::min<uint64_t>(max_gap_len, 0x7fffffffull);
     DeviceGuard dg(ix->device);
     if (!dg.ok) return fail(KBO_ERR_CUDA, "cudaSetDevice failed");
-    const HostCallScope scope(ix);
-    const uint64_t want_parts = pick_parts(scope, total);
-    const std::vector<uint64_t> cut = split_queries(offsets, n_queries, want_parts);
-    const size_t np = cut.size() - 1;
-    std::vector<Workspace*> wss(np, nullptr);
-    auto give_back = [&]() { for (Workspace* w : wss) if (w) release_ws(ix, w); };
-    // phase 1: enqueue copy-in, K0, K1, K2b (masks), K4 up to the per-query offsets, and their copy-out
-    for (size_t s = 0; s < np && !rc; ++s) {
-        rc = acquire_ws(ix, &wss[s]);
-        if (rc) break;
-        rc = reserve_ws(wss[s], total, n_queries, true);
-        if (rc) break;
-        Workspace* ws = wss[s];
-        cudaStream_t st = ws->stream;
-        const uint64_t q0 = cut[s], q1 = cut[s + 1], nq = q1 - q0;
-        const uint64_t bytes = offsets[q1] - offsets[q0];
-        const Geometry g = batch_geometry(bytes, nq);
-        auto body = [&]() -> int {
-            CUDA_TRY(ws->ascii.ensure(bytes, st));
-            CUDA_TRY(ws->offsets.ensure((nq + 1) * 8, st));
-            CUDA_TRY(ws->tmp64.ensure((nq + 1) * 8, st));
-            CUDA_TRY(ws->h_rel.ensure((nq + 1) * 8));
-            CUDA_TRY(ws->h_roff.ensure((nq + 1) * 8));
-            uint64_t* rel = ws->h_rel.as<uint64_t>();
-            for (uint64_t i = 0; i <= nq; ++i) rel[i] = offsets[q0 + i] - offsets[q0];
+    want_parts = std::max<uint64_t>(want_parts, min_parts_for(total, n_queries));
+    kbo_job* job = new kbo_job();
+    job->ix = ix;
+    job->nq = n_queries;
+    job->rle_out = rle_out;
+    job->rle_cap = rle_cap;
+    job->rle_offsets = rle_offsets;
+    job->cut = split_queries(offsets, n_queries, want_parts);
+    const size_t np = job->cut.size() - 1;
+    job->wss.assign(np, nullptr);
+    job->rle.resize(np);
+    RleRecord* dv_out = reinterpret_cast<RleRecord*>(device_visible(rle_out));
+    uint64_t* dv_off = reinterpret_cast<uint64_t*>(device_visible(rle_offsets));
+    job->direct = dv_off && (dv_out || rle_cap == 0);
+    auto body = [&]() -> int {
+        for (size_t s = 0; s < np; ++s) {
+            int r = acquire_ws(ix, &job->wss[s]);
+            if (r) return r;
+            r = reserve_ws(job->wss[s], total, n_queries, true);
+            if (r) return r;
+        }
+        Workspace* ws0 = job->wss[0];
+        // running record totals of the sub-batches (device) and the final count (page-locked host), in ws0
+        CUDA_TRY(ws0->counters2.ensure((np + 1) * 8, ws0->stream));
+        CUDA_TRY(ws0->h_count.ensure(8));
+        uint64_t* d_totals = ws0->counters2.as<uint64_t>();
+        CUDA_TRY(cudaMemsetAsync(d_totals, 0, 8, ws0->stream));
+        uint64_t* st_off = nullptr;     // staged path: device copies of the outputs
+        RleRecord* st_out = nullptr;
+        if (!job->direct) {
+            job->staged_cap = std::min<uint64_t>(rle_cap, 4 * n_queries + total / 64 + 1024);
+            CUDA_TRY(ws0->out2.ensure(std::max<uint64_t>(job->staged_cap, 1) * sizeof(RleRecord), ws0->stream));
+            CUDA_TRY(ws0->tmp64.ensure((n_queries + 1) * 8, ws0->stream));
+            CUDA_TRY(ws0->h_roff.ensure((n_queries + 1) * 8));
+            st_off = ws0->tmp64.as<uint64_t>();
+            st_out = ws0->out2.as<RleRecord>();
+        }
+        for (size_t s = 0; s < np; ++s) {
+            Workspace* ws = job->wss[s];
+            cudaStream_t st = ws->stream;
+            const uint64_t q0 = job->cut[s], q1 = job->cut[s + 1], nq = q1 - q0;
+            const uint64_t bytes = offsets[q1] - offsets[q0];
+            const Geometry g = batch_geometry(bytes, nq);
+            // the kernels subtract offsets[0] themselves, so the caller's offsets are copied as they are
             CUDA_TRY(cudaMemcpyAsync(ws->ascii.p, concat + offsets[q0], bytes, cudaMemcpyHostToDevice, st));
-            CUDA_TRY(cudaMemcpyAsync(ws->offsets.p, rel, (nq + 1) * 8, cudaMemcpyHostToDevice, st));
+            CUDA_TRY(cudaMemcpyAsync(ws->offsets.p, offsets + q0, (nq + 1) * 8, cudaMemcpyHostToDevice, st));
             if (s == 0) CUDA_TRY(cudaEventRecord(ws->ev0, st));
             QueryView qv;
-            int rc2 = matches_device(ix, ws, ws->ascii.as<uint8_t>(), ws->offsets.as<uint64_t>(), nq, g, thr, nullptr, 0,
-                                     true, &qv);
-            if (rc2) return rc2;
-            rc2 = run_rle_offsets(ws, qv, g, ws->offsets.as<uint64_t>(), nq, gap, ws->tmp64.as<uint64_t>());
-            if (rc2) return rc2;
-            CUDA_TRY(cudaMemcpyAsync(ws->h_roff.p, ws->tmp64.p, (nq + 1) * 8, cudaMemcpyDeviceToHost, st));
-            return KBO_OK;
-        };
-        rc = body();
-    }
-    // phase 2: per sub-batch, in order: record count -> K4 records -> asynchronous copy-out of the records
-    bool out_is_pinned = false;
-    if (rle_out) {
-        cudaPointerAttributes attr;
-        if (cudaPointerGetAttributes(&attr, rle_out) == cudaSuccess) out_is_pinned = attr.type == cudaMemoryTypeHost;
-        cudaGetLastError();
-    }
-    uint64_t base = 0;
-    std::vector<uint64_t> part_base(np, 0), part_n(np, 0);
-    rle_offsets[0] = 0;
-    for (size_t s = 0; s < np && !rc; ++s) {
-        Workspace* ws = wss[s];
-        cudaStream_t st = ws->stream;
-        const uint64_t q0 = cut[s], q1 = cut[s + 1], nq = q1 - q0;
-        auto body = [&]() -> int {
-            CUDA_TRY(cudaStreamSynchronize(st));
-            const uint64_t* roff = ws->h_roff.as<uint64_t>();
-            const uint64_t n_rle = roff[nq];
-            for (uint64_t i = 1; i <= nq; ++i) rle_offsets[q0 + i] = base + roff[i];
-            part_base[s] = base;
-            part_n[s] = n_rle;
-            base += n_rle;
-            if (base > rle_cap) return KBO_OK;  // keep counting; reported below
-            if (n_rle) {
-                if (!rle_out) return fail(KBO_ERR_BAD_ARGUMENT, "rle_out is null");
-                CUDA_TRY(ws->out2.ensure(n_rle * sizeof(RleRecord), st));
-                int rc2 = run_rle_records(ws, ws->out2.as<RleRecord>(), n_rle);
-                if (rc2) return rc2;
-                if (out_is_pinned) {  // page-locked caller buffer: the copy engine writes the records in place
-                    CUDA_TRY(cudaMemcpyAsync(rle_out + part_base[s], ws->out2.p, n_rle * sizeof(RleRecord),
-                                             cudaMemcpyDeviceToHost, st));
-                } else {
-                    CUDA_TRY(ws->h_rle.ensure(n_rle * sizeof(RleRecord)));
-                    CUDA_TRY(cudaMemcpyAsync(ws->h_rle.p, ws->out2.p, n_rle * sizeof(RleRecord), cudaMemcpyDeviceToHost, st));
-                }
+            // (K0 addresses the text as base + offsets[i]: bias the base instead of rebasing the offsets on the host)
+            int r = matches_device(ix, ws, ws->ascii.as<uint8_t>() - offsets[q0], ws->offsets.as<uint64_t>(), nq, g, thr,
+                                   nullptr, 0, true, &qv);
+            if (r) return r;
+            r = run_rle_counts(ws, qv, g, ws->offsets.as<uint64_t>(), nq, gap, &job->rle[s]);
+            if (r) return r;
+            if (s > 0) CUDA_TRY(cudaStreamWaitEvent(st, job->wss[s - 1]->ev1, 0));  // its total is this part's base
+            else if (np > 1) { /* d_totals[0] was zeroed on this very stream */ }
+            r = run_rle_finish(st, job->rle[s], (job->direct ? dv_off : st_off) + q0, job->direct ? dv_out : st_out,
+                               job->direct ? rle_cap : job->staged_cap, d_totals + s, d_totals + s + 1, s == 0);
+            if (r) return r;
+            CUDA_TRY(cudaEventRecord(ws->ev1, st));
+            if (s + 1 == np) {
+                CUDA_TRY(cudaMemcpyAsync(ws0->h_count.p, d_totals + np, 8, cudaMemcpyDeviceToHost, st));
+                if (!job->direct)
+                    CUDA_TRY(cudaMemcpyAsync(ws0->h_roff.p, st_off, (n_queries + 1) * 8, cudaMemcpyDeviceToHost, st));
             }
-            return KBO_OK;
-        };
-        rc = body();
+        }
+        return KBO_OK;
+    };
+    rc = body();
+    if (rc) {
+        for (Workspace* w : job->wss) if (w) cudaStreamSynchronize(w->stream);
+        job_release(job);
+        delete job;
+        return rc;
     }
-    if (!rc && base > rle_cap) rc = fail(KBO_ERR_BUFFER_TOO_SMALL, "rle capacity too small");
-    // phase 3: collect the records
+    *out = job;
+    return KBO_OK;
+}
+
+static int find_wait(kbo_job* job, uint64_t* n_rle_out) {
+    kbo_index* ix = job->ix;
+    DeviceGuard dg(ix->device);
+    int rc = KBO_OK;
+    const size_t np = job->wss.size();
     for (size_t s = 0; s < np; ++s) {
-        if (!wss[s]) continue;
-        if (s + 1 == np && !rc) cudaEventRecord(wss[s]->ev1, wss[s]->stream);
-        cudaError_t e = cudaStreamSynchronize(wss[s]->stream);
+        cudaError_t e = cudaStreamSynchronize(job->wss[s]->stream);
         if (e != cudaSuccess && !rc) rc = fail(KBO_ERR_CUDA, std::string("CUDA error: ") + cudaGetErrorString(e));
-        if (!rc && part_n[s] && !out_is_pinned)
-            std::memcpy(rle_out + part_base[s], wss[s]->h_rle.p, part_n[s] * sizeof(RleRecord));
     }
+    uint64_t count = 0;
+    if (!rc) {
+        Workspace* ws0 = job->wss[0];
+        count = *ws0->h_count.as<uint64_t>();
+        if (!job->direct) {  // staged path: pageable caller buffers
+            std::memcpy(job->rle_offsets, ws0->h_roff.p, (job->nq + 1) * 8);
+            if (count <= job->rle_cap && count) {
+                auto body = [&]() -> int {
+                    if (count > job->staged_cap) {  // the estimate was too small: re-run the last kernels into a larger buffer
+                        CUDA_TRY(ws0->out2.ensure(count * sizeof(RleRecord), ws0->stream));
+                        for (size_t s = 0; s < np; ++s) {
+                            int r = run_rle_finish(ws0->stream, job->rle[s], ws0->tmp64.as<uint64_t>() + job->cut[s],
+                                                   ws0->out2.as<RleRecord>(), count, ws0->counters2.as<uint64_t>() + s,
+                                                   nullptr, s == 0);
+                            if (r) return r;
+                        }
+                    }
+                    CUDA_TRY(cudaMemcpyAsync(job->rle_out, ws0->out2.p, count * sizeof(RleRecord), cudaMemcpyDeviceToHost,
+                                             ws0->stream));
+                    CUDA_TRY(cudaStreamSynchronize(ws0->stream));
+                    return KBO_OK;
+                };
+                rc = body();
+            }
+        }
+        if (!rc && count > job->rle_cap)  // rle_offsets[nq] holds the true count on both paths
+            rc = fail(KBO_ERR_BUFFER_TOO_SMALL, "rle capacity too small");
+    }
+    if (n_rle_out) *n_rle_out = count;
     if (!rc && np == 1) {
         float ms = 0.f;
-        cudaEventElapsedTime(&ms, wss[0]->ev0, wss[0]->ev1);
+        cudaEventElapsedTime(&ms, job->wss[0]->ev0, job->wss[0]->ev1);
         ix->last_kernel_ms = ms;
-        rc = fetch_counters(ix, wss[0]);
+        rc = fetch_counters(ix, job->wss[0]);
     }
-    give_back();
+    job_release(job);
+    delete job;
+    return rc;
+}
+
+int kbo_find_batch_submit(const kbo_index* cix, const uint8_t* concat, const uint64_t* offsets, uint64_t n_queries,
+                          double max_error_prob, uint64_t max_gap_len, kbo_rle* rle_out, uint64_t rle_cap,
+                          uint64_t* rle_offsets, kbo_job** job) {
+    if (!job) return fail(KBO_ERR_BAD_ARGUMENT, "job is null");
+    return find_submit(const_cast<kbo_index*>(cix), concat, offsets, n_queries, max_error_prob, max_gap_len, rle_out,
+                       rle_cap, rle_offsets, 1, job);
+}
+
+int kbo_job_wait(kbo_job* job, uint64_t* n_rle) {
+    if (!job) return fail(KBO_ERR_BAD_ARGUMENT, "job is null");
+    return find_wait(job, n_rle);
+}
+
+// kbo::find for a host CSR batch, synchronous.  A lone caller's large batch is cut into sub-batches that run on their
+// own streams, so the host->device copy of sub-batch i+1 overlaps the kernels of sub-batch i.
+int kbo_find_batch(const kbo_index* cix, const uint8_t* concat, const uint64_t* offsets, uint64_t n_queries,
+                   double max_error_prob, uint64_t max_gap_len, kbo_rle* rle_out, uint64_t rle_cap,
+                   uint64_t* rle_offsets) {
+    kbo_index* ix = const_cast<kbo_index*>(cix);
+    if (!ix) return fail(KBO_ERR_BAD_ARGUMENT, "index is null");
+    uint64_t want_parts = 1;
+    kbo_job* job = nullptr;
+    int rc;
+    {
+        const HostCallScope scope(ix);
+        uint64_t total = 0;
+        if (offsets && n_queries) total = offsets[n_queries] - offsets[0];
+        want_parts = pick_parts(scope, total);
+        rc = find_submit(ix, concat, offsets, n_queries, max_error_prob, max_gap_len, rle_out, rle_cap, rle_offsets,
+                         want_parts, &job);
+        if (rc) return rc;
+        rc = find_wait(job, nullptr);
+    }
     return rc;
 }
 
@@ -1456,17 +1623,21 @@ int kbo_find_batch_device(const kbo_index* cix, const uint8_t* d_concat, const u
     const uint32_t gap = (uint32_t)std::min<uint64_t>(max_gap_len, 0x7fffffffull);
     DeviceGuard dg(ix->device);
     if (!dg.ok) return fail(KBO_ERR_CUDA, "cudaSetDevice failed");
+    rc = check_launch_size(total, n_queries);
+    if (rc) return rc;
     Workspace* ws = nullptr;
     rc = stream_ws(ix, (cudaStream_t)stream, &ws);
     if (rc) return rc;
+    std::lock_guard<std::mutex> lk(ws->mu);
     const bool instrumented = g_profile_counters.load() || g_kernel_timing.load();
     const Geometry g = batch_geometry(total, n_queries, instrumented ? 1 : expected_overlap(ix));
     QueryView qv;
     rc = matches_device(ix, ws, d_concat, d_offsets, n_queries, g, thr, nullptr, 0, true, &qv);
     if (rc) return rc;
-    rc = run_rle_offsets(ws, qv, g, d_offsets, n_queries, gap, d_rle_offsets);
+    RleParams rp;
+    rc = run_rle_counts(ws, qv, g, d_offsets, n_queries, gap, &rp);
     if (rc) return rc;
-    rc = run_rle_records(ws, reinterpret_cast<RleRecord*>(d_rle_out), rle_cap);
+    rc = run_rle_finish(ws->stream, rp, d_rle_offsets, reinterpret_cast<RleRecord*>(d_rle_out), rle_cap);
     if (rc) return rc;
     if (g_profile_counters.load()) return fetch_counters(ix, ws);
     return KBO_OK;
@@ -1770,6 +1941,7 @@ int kbo_collect_kernel_times(const kbo_index* cix, void* stream, double sum_ms_o
     Workspace* ws = nullptr;
     int rc = stream_ws(ix, (cudaStream_t)stream, &ws);
     if (rc) return rc;
+    std::lock_guard<std::mutex> lk(ws->mu);
     sum_ms_out[0] = sum_ms_out[1] = sum_ms_out[2] = 0.0;
     for (size_t c = 0; c < ws->timed_calls; ++c) {
         cudaEvent_t* ev = ws->timing.data() + c * 4;

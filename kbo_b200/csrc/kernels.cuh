@@ -1065,9 +1065,12 @@ struct RleParams {
     uint64_t* cse;          // n_words entries: #START | #END << 32 before the word inside its block ...
     uint64_t* cse_blk;      // ... + n_blocks + 1 entries
     unsigned int* tickets;  // two zero-initialised counters (self-resetting) electing the last block of a launch
-    uint64_t* rle_offsets;  // nq + 1
-    RleRecord* out;
-    uint64_t cap;
+    uint64_t* rle_offsets;  // nq + 1 (device memory, or page-locked host memory mapped into the device)
+    RleRecord* out;         // likewise
+    uint64_t cap;           // records with a slot >= cap are dropped (the count is still exact)
+    const uint64_t* base_in;  // optional: number of records of the sub-batches before this one (device counter);
+    uint64_t* total_out;      // optional: receives *base_in + the records of this sub-batch
+    uint32_t write_first;     // != 0: rle_offsets[0] is written too (0 for the sub-batches after the first)
 };
 
 __device__ __forceinline__ uint32_t low_mask(uint32_t b) { return b ? (~0u >> (32 - b)) : 0u; }  // bits below b (b < 32)
@@ -1149,7 +1152,7 @@ __device__ __forceinline__ void rle_finish_blocks(T* blk, uint64_t n_blocks, uns
         const uint64_t b = base + threadIdx.x;
         uint32_t v[N], tot[N];
         const uint32_t* src = reinterpret_cast<const uint32_t*>(blk + (b < n_blocks ? b : 0));
-        for (int i = 0; i < N; ++i) v[i] = b < n_blocks ? src[i] : 0u;
+        for (int i = 0; i < N; ++i) v[i] = b < n_blocks ? __ldcg(src + i) : 0u;  // written by other blocks: read at L2
         rle_block_scan<N>(v, tot);
         if (b < n_blocks) {
             uint32_t* dst = reinterpret_cast<uint32_t*>(blk + b);
@@ -1259,19 +1262,6 @@ __device__ __forceinline__ uint64_t rle_cse(const RleParams& p, uint64_t w) {
     return p.cse_blk[w / RLE_BLOCK] + p.cse[w];
 }
 
-// thread per query (+1): records before the query = STARTs before its first base
-__global__ void rle_query_offsets_kernel(RleParams p) {
-    const uint64_t q = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
-    if (q > p.nq) return;
-    if (q == p.nq) {
-        p.rle_offsets[q] = (uint32_t)p.cse_blk[p.n_blocks];
-        return;
-    }
-    const uint64_t x = rle_query_start(p, q);
-    const uint32_t b = (uint32_t)(x & 31);
-    p.rle_offsets[q] = (uint32_t)rle_cse(p, x >> 5) + (b ? __popc(p.start[x >> 5] & low_mask(b)) : 0);
-}
-
 __device__ __forceinline__ RleCounts rle_pref_all(const RleParams& p, uint64_t x) {
     const uint64_t w = x >> 5;
     if (w >= p.n_words) return p.cnt_blk[p.n_blocks];
@@ -1289,9 +1279,24 @@ __device__ __forceinline__ RleCounts rle_pref_all(const RleParams& p, uint64_t x
     return c;
 }
 
-// thread per word: one record per END bit
-__global__ void rle_records_kernel(RleParams p) {
-    const uint64_t w = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+// Last K4 launch: thread t < n_words writes one record per END bit of word t; thread t <= nq writes the record
+// offset of query t (records before the query = STARTs before its first base).  `base` = records of the sub-batches
+// that precede this one in the same host call (0 when there are none).
+__global__ void rle_finish_kernel(RleParams p) {
+    const uint64_t t = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    const uint64_t base = p.base_in ? *p.base_in : 0ull;
+    if (t <= p.nq) {
+        if (t == p.nq) {
+            const uint64_t total = base + (uint32_t)p.cse_blk[p.n_blocks];
+            p.rle_offsets[t] = total;
+            if (p.total_out) *p.total_out = total;
+        } else if (t > 0 || p.write_first) {
+            const uint64_t x = rle_query_start(p, t);
+            const uint32_t b = (uint32_t)(x & 31);
+            p.rle_offsets[t] = base + (uint32_t)rle_cse(p, x >> 5) + (b ? __popc(p.start[x >> 5] & low_mask(b)) : 0);
+        }
+    }
+    const uint64_t w = t;
     if (w >= p.n_words) return;
     uint32_t rem = p.end[w];
     if (!rem) return;
@@ -1299,7 +1304,7 @@ __global__ void rle_records_kernel(RleParams p) {
     const uint64_t q0 = __ldg(p.wq + w);
     uint32_t slot = (uint32_t)(rle_cse(p, w) >> 32);
     for (; rem; rem &= rem - 1, ++slot) {
-        if (slot >= p.cap) break;
+        if (base + slot >= p.cap) break;
         const uint32_t b = (uint32_t)__ffs((int)rem) - 1u;
         const uint64_t pe = w * 32 + b;
         const uint64_t qs = rle_query_start(p, q0 + __popc(S & low_mask(b)));
@@ -1322,7 +1327,7 @@ __global__ void rle_records_kernel(RleParams p) {
         rec.jumps = z.j - a.j;
         rec.gap_bases = (pe + 1 - ps) - n;
         rec.gap_opens = z.go - a.go;
-        p.out[slot] = rec;
+        p.out[base + slot] = rec;
     }
 }
 

@@ -279,11 +279,12 @@ static uint64_t emu_run_rle(const uint32_t* gap, const uint32_t* match, const ui
     p.jump = jump.data(); p.gopen = gopen.data(); p.cnt = cnt.data(); p.cnt_blk = cnt.data() + n_words;
     p.start = start.data(); p.end = end.data(); p.cse = cse.data(); p.cse_blk = cse.data() + n_words;
     p.tickets = tickets; p.rle_offsets = rle_offsets; p.out = (RleRecord*)out7; p.cap = cap;
+    p.base_in = nullptr; p.total_out = nullptr; p.write_first = 1;
     emu_launch_par((unsigned)nb, RLE_BLOCK, [&]() { rle_word_counts_kernel(p); });
     emu_launch_par((unsigned)nb, RLE_BLOCK, [&]() { rle_mark_kernel(p); });
     const unsigned threads = 128;
-    emu_launch_seq((unsigned)((nq + 1 + threads - 1) / threads), threads, [&]() { rle_query_offsets_kernel(p); });
-    emu_launch_seq((unsigned)((n_words + threads - 1) / threads), threads, [&]() { rle_records_kernel(p); });
+    const uint64_t items = n_words > nq + 1 ? n_words : nq + 1;
+    emu_launch_seq((unsigned)((items + threads - 1) / threads), threads, [&]() { rle_finish_kernel(p); });
     if (tickets[0] != 0 || tickets[1] != 0) std::abort();  // the last block must leave the counters at zero
     return rle_offsets[nq];
 }

@@ -226,6 +226,9 @@ int kbo_set_host_builder(int enabled);
 /* enabled == 0: indexes created afterwards carry no prefix-state table (K1 then warms every chunk up over k-1 bases;
  * comparison runs).  Results never depend on it. */
 int kbo_set_prefix_table(int enabled);
+/* enabled == 0: indexes created afterwards carry no rank2 rows (K1 then probes one base at a time; comparison runs).
+ * Results never depend on it. */
+int kbo_set_rank2(int enabled);
 /* enabled == 0: streams created afterwards do not mark the index arrays as persisting in L2 (comparison runs). */
 int kbo_set_l2_persist(int enabled);
 /* Experiment switches (bit 1: run K2 where the bit-parallel K2b would be picked).  Results never depend on them. */

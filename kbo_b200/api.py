@@ -38,7 +38,7 @@ EXPORTED_SYMBOLS = [
     "kbo_index_access_kmer", "kbo_index_search", "kbo_query_sbwt", "kbo_query_sbwt_batch_compact",
     "kbo_log_rm_max_cdf", "kbo_random_match_threshold", "kbo_derandomize_ms_vec", "kbo_translate_ms_vec",
     "kbo_run_lengths_gapped", "kbo_relative_to_ref", "kbo_matches", "kbo_matches_batch", "kbo_matches_batch_device",
-    "kbo_find_batch", "kbo_find_batch_submit", "kbo_job_wait", "kbo_find_batch_device", "kbo_map_unrefined", "kbo_call", "kbo_map", "kbo_set_profile_counters", "kbo_get_ms_counters", "kbo_set_chunk_len", "kbo_set_l2_persist", "kbo_set_prefix_table", "kbo_set_host_builder", "kbo_set_pipeline_parts", "kbo_set_device_parts", "kbo_set_ms_flags",
+    "kbo_find_batch", "kbo_find_batch_submit", "kbo_job_wait", "kbo_find_batch_device", "kbo_map_unrefined", "kbo_call", "kbo_map", "kbo_set_profile_counters", "kbo_get_ms_counters", "kbo_set_chunk_len", "kbo_set_l2_persist", "kbo_set_prefix_table", "kbo_set_rank2", "kbo_set_host_builder", "kbo_set_pipeline_parts", "kbo_set_device_parts", "kbo_set_ms_flags",
     "kbo_kernel_launch_count", "kbo_last_kernel_ms", "kbo_set_kernel_timing", "kbo_collect_kernel_times",
     "kbo_measure_random_sector_rate",
 ]
@@ -130,6 +130,7 @@ def load_library():
     L.kbo_set_chunk_len.argtypes = [C.c_uint32]
     L.kbo_set_l2_persist.argtypes = [C.c_int]
     L.kbo_set_prefix_table.argtypes = [C.c_int]
+    L.kbo_set_rank2.argtypes = [C.c_int]
     L.kbo_set_host_builder.argtypes = [C.c_int]
     L.kbo_set_pipeline_parts.argtypes = [C.c_uint32]
     L.kbo_set_device_parts.argtypes = [C.c_uint32]
@@ -572,6 +573,11 @@ def set_host_builder(enabled):
 def set_prefix_table(enabled):
     """Indexes built after this call do / do not carry the prefix-state table that shortens K1's chunk warm-up."""
     _check(load_library().kbo_set_prefix_table(int(bool(enabled))))
+
+
+def set_rank2(enabled):
+    """Indexes built after this call do / do not carry the rank2 rows (two bases per probe in K1)."""
+    _check(load_library().kbo_set_rank2(int(bool(enabled))))
 
 
 def set_l2_persist(enabled):

@@ -31,6 +31,7 @@ static std::atomic<uint64_t> g_launches(0);
 static std::atomic<int> g_profile_counters(0);
 static std::atomic<uint32_t> g_chunk_len(0);
 static std::atomic<int> g_kernel_timing(0);
+static std::atomic<int> g_rank2(1);  // 0: indexes built afterwards carry no two-bases-per-probe rows (comparison runs)
 static std::atomic<int> g_prefix_table(1);  // 0: indexes built afterwards get no prefix-state table (comparison runs)
 static std::atomic<int> g_l2_persist(1);  // 0: do not mark the index persisting in L2 (comparison runs)
 static std::atomic<uint32_t> g_ms_flags(0);
@@ -133,6 +134,7 @@ struct kbo_index {
     unsigned recent_pos = 0;
     HostIndex host;
     uint64_t* d_rank = nullptr;
+    uint64_t* d_rank2 = nullptr;  // 16 rows for two bases per probe (inside the blob; null for device-only helper indexes)
     uint8_t* d_lcs = nullptr;
     uint32_t* d_links = nullptr;  // per node: LCS and the distances to the nearest smaller LCS on both sides
     uint8_t* d_blob = nullptr;    // the one allocation holding rank | links | lcs (one L2 access-policy window)
@@ -152,14 +154,16 @@ struct kbo_index {
 // The index arrays live in ONE allocation so that a single access-policy window covers them: every stream that
 // runs K1 marks that range "persisting" in L2 (the streaming batch buffers of K0/K2/K4 would otherwise keep
 // evicting index lines, and a warp of K1 waits for the slowest of its ~60 random loads per iteration).
-static int alloc_index_arrays(kbo_index* ix, uint64_t rank_words, uint64_t lcs_bytes, uint64_t n) {
+static int alloc_index_arrays(kbo_index* ix, uint64_t rank_words, uint64_t lcs_bytes, uint64_t n, bool with_rank2) {
     const uint64_t rank_bytes = rank_words * 8;
+    const uint64_t rank2_bytes = with_rank2 && g_rank2.load() ? 4 * rank_bytes : 0;  // 16 rows instead of 4
     const uint64_t links_bytes = ((n + 1) * 4 + 255) & ~255ull;
-    ix->blob_bytes = rank_bytes + links_bytes + lcs_bytes;
+    ix->blob_bytes = rank_bytes + rank2_bytes + links_bytes + lcs_bytes;
     CUDA_TRY(cudaMalloc((void**)&ix->d_blob, ix->blob_bytes));
     ix->d_rank = reinterpret_cast<uint64_t*>(ix->d_blob);
-    ix->d_links = reinterpret_cast<uint32_t*>(ix->d_blob + rank_bytes);
-    ix->d_lcs = ix->d_blob + rank_bytes + links_bytes;
+    ix->d_rank2 = rank2_bytes ? reinterpret_cast<uint64_t*>(ix->d_blob + rank_bytes) : nullptr;
+    ix->d_links = reinterpret_cast<uint32_t*>(ix->d_blob + rank_bytes + rank2_bytes);
+    ix->d_lcs = ix->d_blob + rank_bytes + rank2_bytes + links_bytes;
     ix->device_bytes = ix->blob_bytes;
     cudaDeviceProp prop;
     int dev = 0;
@@ -303,7 +307,40 @@ static int host_threshold(uint64_t k, uint64_t n_kmers, uint64_t alphabet, doubl
 // index upload: SubsetMatrix rows + LCS -> interleaved rank words + padded LCS
 // ---------------------------------------------------------------------------
 // links array (kernels.cuh IndexView::links) from the device LCS bytes; called by both builders
+// rank2 rows from the rank words that are already on the device (both builders and kbo_index_from_parts end here)
+static int build_rank2(kbo_index* ix) {
+    ix->view.rank2 = nullptr;
+    if (!ix->d_rank2) return KBO_OK;
+    const uint64_t stride = ix->rank_stride, words = 16 * stride;
+    uint32_t *rows2 = nullptr, *pc = nullptr, *prefix = nullptr;
+    void* scan_tmp = nullptr;
+    auto body = [&]() -> int {
+        CUDA_TRY(cudaMalloc((void**)&rows2, words * 4));
+        CUDA_TRY(cudaMalloc((void**)&pc, words * 4));
+        CUDA_TRY(cudaMalloc((void**)&prefix, words * 4));
+        rank2_bits_kernel<<<(unsigned)((stride + 127) / 128), 128>>>(ix->view, rows2);
+        LAUNCHED();
+        row_popc_kernel<<<(unsigned)((words + 255) / 256), 256>>>(rows2, words, pc);
+        LAUNCHED();
+        size_t need = 0;
+        cub::DeviceScan::ExclusiveSum(nullptr, need, pc, prefix, (int64_t)words);
+        CUDA_TRY(cudaMalloc(&scan_tmp, need ? need : 1));
+        CUDA_TRY(cub::DeviceScan::ExclusiveSum(scan_tmp, need, pc, prefix, (int64_t)words));
+        LAUNCHED();
+        compose_rank2_kernel<<<(unsigned)((words + 255) / 256), 256>>>(ix->view, rows2, prefix, ix->d_rank2);
+        LAUNCHED();
+        CUDA_TRY(cudaGetLastError());
+        CUDA_TRY(cudaDeviceSynchronize());
+        return KBO_OK;
+    };
+    const int rc = body();
+    cudaFree(rows2); cudaFree(pc); cudaFree(prefix); cudaFree(scan_tmp);
+    if (rc == KBO_OK) ix->view.rank2 = ix->d_rank2;
+    return rc;
+}
+
 static int build_links(kbo_index* ix, uint64_t n, bool with_prefix_table = true) {
+    { int rc = build_rank2(ix); if (rc) return rc; }
     lcs_links_kernel<<<(unsigned)((n + 1 + 255) / 256), 256>>>(ix->d_lcs, (uint32_t)n, ix->d_links);
     LAUNCHED();
     CUDA_TRY(cudaGetLastError());
@@ -343,7 +380,7 @@ static int upload_index(kbo_index* ix) {
     const std::vector<uint64_t>& rank = lay.rank;
     const std::vector<uint8_t>& lcs = lay.lcs;
     const uint64_t stride = lay.stride;
-    { int rc = alloc_index_arrays(ix, rank.size(), lcs.size(), n); if (rc) return rc; }
+    { int rc = alloc_index_arrays(ix, rank.size(), lcs.size(), n, true); if (rc) return rc; }
     CUDA_TRY(cudaMemcpy(ix->d_rank, rank.data(), rank.size() * 8, cudaMemcpyHostToDevice));
     CUDA_TRY(cudaMemcpy(ix->d_lcs, lcs.data(), lcs.size(), cudaMemcpyHostToDevice));
     ix->rank_stride = stride;
@@ -493,7 +530,7 @@ static int build_index_gpu(kbo_index* ix, const uint8_t* const* seqs, const uint
     const uint64_t nblk = (n >> 5) + 2;
     const uint64_t stride = (nblk + 3) & ~3ull;
     const uint64_t lcs_bytes = ((n + 8) & ~7ull) + 16;
-    { int rc = alloc_index_arrays(ix, 4 * stride, lcs_bytes, n); if (rc) return rc; }
+    { int rc = alloc_index_arrays(ix, 4 * stride, lcs_bytes, n, !device_only); if (rc) return rc; }
     CUDA_TRY(cudaMemset(ix->d_lcs, 0, lcs_bytes));
     CUDA_TRY(tmp.alloc(&d_rows32, 4 * stride));
     CUDA_TRY(tmp.alloc(&d_pc, 4 * stride));
@@ -1922,6 +1959,7 @@ int kbo_set_device_parts(uint32_t parts) { g_dev_parts = parts > 16 ? 16 : parts
 int kbo_set_pipeline_parts(uint32_t parts) { g_parts = parts > 64 ? 64 : parts; return KBO_OK; }
 int kbo_set_host_builder(int enabled) { g_host_builder = enabled ? 1 : 0; return KBO_OK; }
 int kbo_set_prefix_table(int enabled) { g_prefix_table = enabled ? 1 : 0; return KBO_OK; }
+int kbo_set_rank2(int enabled) { g_rank2 = enabled ? 1 : 0; return KBO_OK; }
 int kbo_set_l2_persist(int enabled) { g_l2_persist = enabled ? 1 : 0; return KBO_OK; }
 int kbo_set_ms_flags(uint32_t flags) {
     g_ms_flags = flags & 0xffu;

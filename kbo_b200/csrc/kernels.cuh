@@ -41,11 +41,16 @@ namespace kbo_b200 {
 //   links: one 32-bit word per node (and one for n): bits 0-7 LCS[q], bits 8-19 q - PSV(q), bits 20-31 NSV(q) - q,
 //          PSV / NSV = nearest position to the left / right whose LCS is smaller; 4095 = farther than that (or none).
 //          contract_left to the first depth that changes the interval is then two loads and a few additions.
+//   rank2: see IndexView::rank2 (DESIGN.md "two bases per probe").
 //   pref : for k >= PREF_MIN_K, the MS state after any string of PREF_LEN = 10 bases (index: first base in the low bits);
 //          a chunk's warm-up starts from this entry instead of stepping through its first ten bases.
 // ---------------------------------------------------------------------------
 struct IndexView {
     const uint64_t* rank;
+    const uint64_t* rank2;  // optional: 16 rows (first base | second base << 2) in the same word format, for TWO bases per
+                            // probe: word b of row (a, c) = (C[c] + rank_c(C[a]) + #{i < 32b : node i has label a and its
+                            // a-successor has label c}) << 32 | those 32 bits, so that
+                            // extend_right(extend_right([l, r), a), c) = [rank2(l), rank2(r)) with one load per end
     uint32_t rank_stride;  // words per row (< 2^28 for n_sets < 2^32)
     const uint8_t* lcs;
     const uint32_t* links;  // n + 1 entries: LCS | distance to the previous smaller LCS << 8 | to the next smaller << 20
@@ -271,6 +276,49 @@ __global__ void lcs_links_kernel(const uint8_t* __restrict__ lcs, uint32_t n, ui
     links[q] = v | (dl << 8) | (dr << 20);
 }
 
+// ---- rank2: two bases per probe (IndexView::rank2) -------------------------------------------------------------
+// Thread per 32-node word: for every node i of the word with label a, its a-successor s = C[a] + rank_a(i) is read
+// off the rank word, and bit i of row (a | c << 2) is set iff s carries label c.  (No warp collectives, so the
+// CPU emulation of tests/emu can run it thread by thread.)
+__global__ void rank2_bits_kernel(IndexView ix, uint32_t* __restrict__ rows2) {
+    const uint64_t w = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    const uint64_t stride = ix.rank_stride;
+    if (w >= stride) return;
+    uint32_t m[16];
+#pragma unroll
+    for (int i = 0; i < 16; ++i) m[i] = 0;
+#pragma unroll
+    for (int a = 0; a < 4; ++a) {
+        const uint64_t wa = ix.rank[a * stride + w];
+        uint32_t bits = (uint32_t)wa;
+        while (bits) {
+            const uint32_t j = (uint32_t)__ffs((int)bits) - 1u;
+            bits &= bits - 1;
+            if (w * 32 + j >= ix.n) break;
+            const uint32_t s = (uint32_t)(wa >> 32) + __popc((uint32_t)wa & ((1u << j) - 1u));
+#pragma unroll
+            for (int c = 0; c < 4; ++c)
+                if ((ix.rank[c * stride + (s >> 5)] >> (s & 31)) & 1ull) m[a | (c << 2)] |= 1u << j;
+        }
+    }
+#pragma unroll
+    for (int i = 0; i < 16; ++i) rows2[i * stride + w] = m[i];
+}
+
+// word b of row (a | c << 2) = (C[c] + rank_c(C[a]) + ones of the row before the word) << 32 | bits;
+// prefix = exclusive sum of the popcounts of the 16 rows laid end to end
+__global__ void compose_rank2_kernel(IndexView ix, const uint32_t* __restrict__ rows2, const uint32_t* __restrict__ prefix,
+                                     uint64_t* __restrict__ rank2) {
+    const uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    const uint64_t stride = ix.rank_stride;
+    if (i >= 16 * stride) return;
+    const uint32_t row = (uint32_t)(i / stride), a = row & 3u, c = row >> 2;
+    const uint32_t Ca = (uint32_t)(ix.rank[a * stride] >> 32);           // C[a]
+    const uint64_t wc = ix.rank[c * stride + (Ca >> 5)];
+    const uint32_t base = (uint32_t)(wc >> 32) + __popc((uint32_t)wc & ((1u << (Ca & 31)) - 1u));  // C[c] + rank_c(C[a])
+    rank2[i] = ((uint64_t)(base + prefix[i] - prefix[row * stride]) << 32) | rows2[i];
+}
+
 // contract_left to the largest depth that changes the interval, t = max(LCS[l], LCS[r]), given the link words of
 // l and r.  Returns true when an end was farther than the links reach and had to be found by scanning.
 // The rare cases (t == 0, an end beyond the reach of the links, the impossible t > d - 1) are kept out of line.
@@ -353,6 +401,14 @@ __global__ void prefix_table_level_kernel(IndexView ix, const uint4* __restrict_
 
 // One extend attempt per loop iteration and lane.  A lane whose extension fails (at d > 0) contracts in the same
 // iteration -- two loads of `links` and a few additions -- and retries the base in the next one.
+//
+// Two bases per probe (no intervals requested, index carries rank2): while the lane is in a matching stretch (its
+// last base extended at the first try) it probes rank2 with the next TWO bases; a non-empty result is exactly the
+// state after both (the state in between is not needed: its depth is min(d+1, k)).  An empty result says that one of
+// the two extensions fails; the lane then takes the first base alone, and if that succeeds the second is KNOWN to
+// fail from the new state, so its probe is skipped and the lane contracts at once.  After a failure the lane stays
+// with single probes until a base extends at the first try again (noise stretches fail at every base).
+enum { MS_FLAG_NO_PAIRS = 4 };
 template <bool INTERVALS, bool COUNT>
 __global__ void __launch_bounds__(256, 6) ms_kernel(MsParams p) {
     __shared__ __align__(16) uint8_t ms_stage[256 * 36];
@@ -396,52 +452,100 @@ __global__ void __launch_bounds__(256, 6) ms_kernel(MsParams p) {
         const uint32_t bp_end = bp_emit + len;
         uint64_t qw = __ldg(qptr) >> (2 * bp);
         uint32_t iw = __ldg(iptr) >> bp;
+        const bool pairs = !INTERVALS && p.ix.rank2 != nullptr && !(p.flags & MS_FLAG_NO_PAIRS);
+        bool fast = true;         // the last base extended at the first try: probe two bases at once
+        bool clean = true;        // no failed attempt for the current base so far
+        bool pair_failed = false; // the pair starting at the current base is known to be empty
+        bool known_fail = false;  // the current base is known not to extend from the current state
         // emitted MS bytes are staged in shared memory (36-byte stride per lane: conflict-free word access) and
         // flushed as two 16-byte stores per 32 positions; chunk starts are multiples of 32, so flushes are aligned
         uint8_t* const stg = ms_stage + threadIdx.x * 36u;
         while (bp < bp_end) {
-            bool advance = true;
+            uint32_t adv = 1, dA = 0, dB = 0;  // positions consumed by this iteration and their MS lengths
             if (iw & 1u) {
                 l = 0; r = n; d = 0;
-            } else {
-                const uint32_t rowoff = ((uint32_t)qw & 3u) * p.ix.rank_stride;  // 32-bit word index
+                fast = false; clean = true; pair_failed = false; known_fail = false;
+            } else if (pairs && fast && !(iw & 2u) && (bp & 31u) != 31u && bp + 1 < bp_end) {
+                const uint32_t rowoff = ((uint32_t)qw & 15u) * p.ix.rank_stride;
                 const uint32_t bl = l >> 5, br = r >> 5;
-                const uint64_t wl = __ldg(p.ix.rank + (rowoff + bl));
-                const uint64_t wr = (br == bl) ? wl : __ldg(p.ix.rank + (rowoff + br));
+                const uint64_t wl = __ldg(p.ix.rank2 + (rowoff + bl));
+                const uint64_t wr = (br == bl) ? wl : __ldg(p.ix.rank2 + (rowoff + br));
                 const uint32_t nl = (uint32_t)(wl >> 32) + __popc((uint32_t)wl & ((1u << (l & 31)) - 1u));
                 const uint32_t nr = (uint32_t)(wr >> 32) + __popc((uint32_t)wr & ((1u << (r & 31)) - 1u));
                 if (COUNT) {
                     const bool sp = (bl >> 2) != (br >> 2);
                     ++cnt_att; cnt_split += sp;
-                    if (bp >= bp_emit) { ++cnt_att_e; cnt_split_e += sp; }
+                    if (bp + 1 >= bp_emit) { ++cnt_att_e; cnt_split_e += sp; }
                 }
                 if (nl < nr) {
                     l = nl; r = nr;
+                    dA = d + 1 < k ? d + 1 : k;
+                    dB = d + 2 < k ? d + 2 : k;
+                    d = dB;
+                    adv = 2;
+                } else {
+                    adv = 0;
+                    fast = false;
+                    pair_failed = true;
+                }
+            } else {
+                bool ok = false;
+                if (known_fail) {
+                    known_fail = false;  // (d >= 1 here: the previous base has just extended)
+                } else {
+                    const uint32_t rowoff = ((uint32_t)qw & 3u) * p.ix.rank_stride;  // 32-bit word index
+                    const uint32_t bl = l >> 5, br = r >> 5;
+                    const uint64_t wl = __ldg(p.ix.rank + (rowoff + bl));
+                    const uint64_t wr = (br == bl) ? wl : __ldg(p.ix.rank + (rowoff + br));
+                    const uint32_t nl = (uint32_t)(wl >> 32) + __popc((uint32_t)wl & ((1u << (l & 31)) - 1u));
+                    const uint32_t nr = (uint32_t)(wr >> 32) + __popc((uint32_t)wr & ((1u << (r & 31)) - 1u));
+                    if (COUNT) {
+                        const bool sp = (bl >> 2) != (br >> 2);
+                        ++cnt_att; cnt_split += sp;
+                        if (bp >= bp_emit) { ++cnt_att_e; cnt_split_e += sp; }
+                    }
+                    ok = nl < nr;
+                    if (ok) { l = nl; r = nr; }
+                }
+                if (ok) {
                     d = d + 1 < k ? d + 1 : k;
+                    dA = d;
+                    fast = clean && !pair_failed;
+                    known_fail = pair_failed;
+                    pair_failed = false;
+                    clean = true;
                 } else if (d != 0) {
                     // contract_left to the largest depth that changes the interval: t = max(LCS[l], LCS[r])
-                    advance = false;
+                    adv = 0;
+                    clean = false;
+                    pair_failed = false;
                     const uint32_t el = __ldg(p.ix.links + l), er = __ldg(p.ix.links + r);
                     const bool scanned = ms_contract(p.ix, el, er, l, r, d);
                     if (COUNT) {
                         ++cnt_con; cnt_extra += scanned;
                         if (bp >= bp_emit) { ++cnt_con_e; cnt_extra_e += scanned; }
                     }
+                } else {  // nothing matches this base: it is emitted with d == 0
+                    fast = false; clean = true; pair_failed = false;
                 }
             }
-            if (advance) {
-                if (COUNT) ++cnt_proc;
+            if (adv) {
+                if (COUNT) cnt_proc += adv;
                 if (bp >= bp_emit) {
                     if (COUNT) ++cnt_emit;
-                    stg[bp & 31u] = (uint8_t)d;
+                    stg[bp & 31u] = (uint8_t)(adv == 2 ? dA : d);
                     if (INTERVALS) {
                         p.l_out[(wbase << 5) + bp] = l;
                         p.r_out[(wbase << 5) + bp] = r;
                     }
                 }
-                ++bp;
-                qw >>= 2;
-                iw >>= 1;
+                if (adv == 2 && bp + 1 >= bp_emit) {
+                    if (COUNT) ++cnt_emit;
+                    stg[(bp + 1) & 31u] = (uint8_t)dB;
+                }
+                bp += adv;
+                qw >>= 2 * adv;
+                iw >>= adv;
                 if ((bp & 31) == 0 || bp == bp_end) {
                     if (bp > bp_emit) {  // flush the 32 (or last, partial) staged positions
                         const uint32_t* w = reinterpret_cast<const uint32_t*>(stg);

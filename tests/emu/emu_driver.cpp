@@ -41,9 +41,13 @@ static void emu_run_translate(TrParams tp, const Geometry& g) {
     }
 }
 
+static int g_emu_rank2 = 1;  // 0: indexes built afterwards carry no rank2 rows
+extern "C" void emu_set_rank2(int v) { g_emu_rank2 = v; }
+
 struct EmuIndex {
     HostIndex host;
     DeviceLayout lay;
+    std::vector<uint64_t> rank2;
     std::vector<uint32_t> links;
     std::vector<uint4> pref, pref_tmp;
     IndexView view;
@@ -56,6 +60,18 @@ static void finish(EmuIndex* e) {
     e->view.lcs = e->lay.lcs.data();
     e->view.n = (uint32_t)e->host.n_sets;
     e->view.k = e->host.k;
+    e->view.rank2 = nullptr;
+    if (g_emu_rank2) {  // as capi.cu build_rank2 (the scan between the two kernels is plain C++ here)
+        const uint64_t stride = e->lay.stride, words = 16 * stride;
+        std::vector<uint32_t> rows2(words), prefix(words);
+        emu_launch_seq((unsigned)((stride + 127) / 128), 128, [&]() { rank2_bits_kernel(e->view, rows2.data()); });
+        uint32_t run = 0;
+        for (uint64_t i = 0; i < words; ++i) { prefix[i] = run; run += (uint32_t)__builtin_popcount(rows2[i]); }
+        e->rank2.assign(words, 0);
+        emu_launch_seq((unsigned)((words + 255) / 256), 256,
+                       [&]() { compose_rank2_kernel(e->view, rows2.data(), prefix.data(), e->rank2.data()); });
+        e->view.rank2 = e->rank2.data();
+    }
     const uint32_t n = e->view.n;
     e->links.assign((size_t)n + 1, 0);
     emu_launch_seq((unsigned)(((uint64_t)n + 1 + 255) / 256), 256,

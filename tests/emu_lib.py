@@ -63,6 +63,7 @@ def lib():
                               C.c_uint32, C.c_int, u8p]
         L.emu_rle_batch.restype = C.c_uint64
         L.emu_rle_batch.argtypes = [u8p, u64p, C.c_uint64, C.c_uint32, u64p, C.c_uint64, u64p]
+        L.emu_set_rank2.argtypes = [C.c_int]
         L.emu_find_batch.restype = C.c_uint64
         L.emu_find_batch.argtypes = [C.c_void_p, u8p, u64p, C.c_uint64, C.c_uint32, C.c_uint32, u64p, C.c_uint64, u64p]
         _lib = L

@@ -139,6 +139,34 @@ def test_ms_prefix_table_shortens_warm_up_only():
     assert processed[1] < 0.93 * processed[0]
 
 
+@pytest.mark.parametrize("k", [3, 7, 31, 63])
+def test_ms_two_bases_per_probe(k):
+    """Lengths-only MS (no intervals) takes the rank2 path: two bases per probe in matching stretches.  Same d as the
+    oracle for every chunk length, with fewer probes than the one-base path."""
+    ref = rand_seq(30_000, 71)
+    asm = synth.mutate(np.frombuffer(ref, dtype=np.uint8), 72).tobytes()
+    o = O.OracleIndex([asm], k=k)
+    queries = [ref[:6000], with_ns(ref[6000:9000], 73, 0.02), rand_seq(900, 74), ref[10_000:10_003], b"N", b"AC",
+               ref[20_000:20_257], b"ACGT" * 40 + b"$" + ref[100:400], asm[500:2500]]
+    want = [o.query_sbwt(q)[0] for q in queries]
+    attempts = {}
+    try:
+        for on in (1, 0):
+            E.lib().emu_set_rank2(on)
+            e = E.EmuIndex.build([asm], k=k)
+            for chunk_len in (32, 64, 96, 1024):
+                d, _, _, off, cnt = e.query_sbwt_batch(queries, chunk_len=chunk_len, intervals=False, counters=True)
+                for i, w in enumerate(want):
+                    assert np.array_equal(d[int(off[i]):int(off[i + 1])].astype(np.uint64), w), (k, on, chunk_len, i)
+                assert cnt[5] == sum(len(q) + 1 for q in queries)
+                attempts[(on, chunk_len)] = int(cnt[0])
+    finally:
+        E.lib().emu_set_rank2(1)
+    print("probes with / without rank2:", attempts)
+    if k >= 31:  # (for small k nearly every base fails first: nothing to pair)
+        assert attempts[(1, 64)] < 0.8 * attempts[(0, 64)]
+
+
 def test_ms_tiny_index_and_counters():
     o = O.OracleIndex([b"ACG"], k=3)
     e = E.EmuIndex.build([b"ACG"], k=3)

@@ -16,6 +16,7 @@
 
 #include "../../include/kbo_b200.h"
 #include "kernels.cuh"
+#include "fused.cuh"
 #include "index_build.cuh"
 #include "host_layout.hpp"
 #include "refine_host.hpp"
@@ -812,6 +813,87 @@ static int fetch_counters(kbo_index* ix, Workspace* ws) {
     return KBO_OK;
 }
 
+// ---------------------------------------------------------------------------
+// fused K1 + K2b (fused.cuh): tile geometry and launch
+// ---------------------------------------------------------------------------
+static int device_sm_count(int device) {
+    static std::mutex mu;
+    static std::unordered_map<int, int> cache;
+    std::lock_guard<std::mutex> lk(mu);
+    auto it = cache.find(device);
+    if (it != cache.end()) return it->second;
+    int n = 148;
+    if (cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, device) != cudaSuccess || n <= 0) { cudaGetLastError(); n = 148; }
+    cache[device] = n;
+    return n;
+}
+
+template <bool CHARS, bool COUNT>
+static cudaError_t launch_fused(const FusedParams& fp, const FusedGeom& fg, cudaStream_t st) {
+    static std::mutex mu;
+    static std::vector<int> configured;  // devices on which this instantiation may use > 48 KB of dynamic shared memory
+    int dev = 0;
+    cudaGetDevice(&dev);
+    {
+        std::lock_guard<std::mutex> lk(mu);
+        if (std::find(configured.begin(), configured.end(), dev) == configured.end()) {
+            cudaError_t e = cudaFuncSetAttribute(ms_fused_kernel<CHARS, COUNT>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
+            if (e != cudaSuccess) return e;
+            configured.push_back(dev);
+        }
+    }
+    ms_fused_kernel<CHARS, COUNT><<<(unsigned)fg.n_tiles, FUSED_THREADS, fg.smem.total, st>>>(fp);
+    return cudaGetLastError();
+}
+
+// K1 + K2b in one launch.  Returns KBO_OK and *done = false when the parameters are outside the fused kernel's range
+// (the caller then runs K1 and K2/K2b separately).
+static int run_fused(kbo_index* ix, Workspace* ws, const QueryView& qv, const Geometry& g, uint32_t thr, uint8_t* d_out,
+                     uint64_t off0, bool want_masks, bool* done) {
+    *done = false;
+    const uint32_t flags = g_ms_flags.load();
+    if (!k2b_supported(ix->host.k, thr) || (flags & 2u) || (flags & 8u)) return KBO_OK;  // bit 1: K2, bit 3: unfused
+    FusedGeom fg;
+    if (!fused_geometry(g.Lp, ix->host.k, !want_masks, device_sm_count(ix->device), g_chunk_len.load(), &fg)) return KBO_OK;
+    cudaStream_t st = ws->stream;
+    FusedParams fp;
+    std::memset(&fp, 0, sizeof(fp));
+    fp.ix = ix->view;
+    fp.q = qv;
+    fp.tr.ms = nullptr;
+    fp.tr.q = qv;
+    fp.tr.k = ix->host.k;
+    fp.tr.thr = thr;
+    fp.tr.out = d_out;
+    fp.tr.off0 = off0;
+    fp.tile_len = fg.tile_len;
+    fp.chunk = fg.chunk;
+    fp.stage_words = fg.stage_words;
+    fp.task_cap = fg.task_cap;
+    fp.flags = flags;
+    const uint64_t nw = g.n_tiles_b * 32;
+    if (want_masks) {
+        CUDA_TRY(ws->masks.ensure(nw * 3 * 4, st));
+        fp.tr.out_gap = ws->masks.as<uint32_t>();
+        fp.tr.out_match = fp.tr.out_gap + nw;
+        fp.tr.out_r = fp.tr.out_match + nw;
+        fp.mask_words = nw;
+    }
+    const bool count = g_profile_counters.load() != 0;
+    if (count) {
+        CUDA_TRY(ws->counters.ensure(CNT_N * 8, st));
+        CUDA_TRY(cudaMemsetAsync(ws->counters.p, 0, CNT_N * 8, st));
+        fp.counters = ws->counters.as<unsigned long long>();
+    }
+    cudaError_t e;
+    if (want_masks) e = count ? launch_fused<false, true>(fp, fg, st) : launch_fused<false, false>(fp, fg, st);
+    else e = count ? launch_fused<true, true>(fp, fg, st) : launch_fused<true, false>(fp, fg, st);
+    LAUNCHED();
+    CUDA_TRY(e);
+    *done = true;
+    return KBO_OK;
+}
+
 // matches for a batch whose inputs are already on the device (ws->stream)
 static int matches_device(kbo_index* ix, Workspace* ws, const uint8_t* d_concat, const uint64_t* d_offsets,
                           uint64_t nq, const Geometry& g, uint32_t thr, uint8_t* d_out, uint64_t off0,
@@ -832,12 +914,20 @@ static int matches_device(kbo_index* ix, Workspace* ws, const uint8_t* d_concat,
     int rc = run_pack(ws, d_concat, d_offsets, nq, g, &qv);
     if (rc) return rc;
     if (ev) CUDA_TRY(cudaEventRecord(ev[1], ws->stream));
-    rc = run_ms(ix, ws, qv, g, false);
+    bool fused = false;
+    rc = run_fused(ix, ws, qv, g, thr, d_out, off0, want_masks, &fused);
     if (rc) return rc;
-    if (ev) CUDA_TRY(cudaEventRecord(ev[2], ws->stream));
-    rc = run_derand_translate(ix, ws, qv, g, thr, d_out, off0, want_masks);
-    if (rc) return rc;
-    if (ev) CUDA_TRY(cudaEventRecord(ev[3], ws->stream));
+    if (fused) {  // one kernel: its time is reported as "ms", derandomize + translate as 0
+        if (ev) CUDA_TRY(cudaEventRecord(ev[2], ws->stream));
+        if (ev) CUDA_TRY(cudaEventRecord(ev[3], ws->stream));
+    } else {
+        rc = run_ms(ix, ws, qv, g, false);
+        if (rc) return rc;
+        if (ev) CUDA_TRY(cudaEventRecord(ev[2], ws->stream));
+        rc = run_derand_translate(ix, ws, qv, g, thr, d_out, off0, want_masks);
+        if (rc) return rc;
+        if (ev) CUDA_TRY(cudaEventRecord(ev[3], ws->stream));
+    }
     if (qv_out) *qv_out = qv;
     return KBO_OK;
 }

@@ -401,14 +401,6 @@ __global__ void prefix_table_level_kernel(IndexView ix, const uint4* __restrict_
 
 // One extend attempt per loop iteration and lane.  A lane whose extension fails (at d > 0) contracts in the same
 // iteration -- two loads of `links` and a few additions -- and retries the base in the next one.
-//
-// Two bases per probe (no intervals requested, index carries rank2): while the lane is in a matching stretch (its
-// last base extended at the first try) it probes rank2 with the next TWO bases; a non-empty result is exactly the
-// state after both (the state in between is not needed: its depth is min(d+1, k)).  An empty result says that one of
-// the two extensions fails; the lane then takes the first base alone, and if that succeeds the second is KNOWN to
-// fail from the new state, so its probe is skipped and the lane contracts at once.  After a failure the lane stays
-// with single probes until a base extends at the first try again (noise stretches fail at every base).
-enum { MS_FLAG_NO_PAIRS = 4 };
 template <bool INTERVALS, bool COUNT>
 __global__ void __launch_bounds__(256, 6) ms_kernel(MsParams p) {
     __shared__ __align__(16) uint8_t ms_stage[256 * 36];
@@ -452,100 +444,52 @@ __global__ void __launch_bounds__(256, 6) ms_kernel(MsParams p) {
         const uint32_t bp_end = bp_emit + len;
         uint64_t qw = __ldg(qptr) >> (2 * bp);
         uint32_t iw = __ldg(iptr) >> bp;
-        const bool pairs = !INTERVALS && p.ix.rank2 != nullptr && !(p.flags & MS_FLAG_NO_PAIRS);
-        bool fast = true;         // the last base extended at the first try: probe two bases at once
-        bool clean = true;        // no failed attempt for the current base so far
-        bool pair_failed = false; // the pair starting at the current base is known to be empty
-        bool known_fail = false;  // the current base is known not to extend from the current state
         // emitted MS bytes are staged in shared memory (36-byte stride per lane: conflict-free word access) and
         // flushed as two 16-byte stores per 32 positions; chunk starts are multiples of 32, so flushes are aligned
         uint8_t* const stg = ms_stage + threadIdx.x * 36u;
         while (bp < bp_end) {
-            uint32_t adv = 1, dA = 0, dB = 0;  // positions consumed by this iteration and their MS lengths
+            bool advance = true;
             if (iw & 1u) {
                 l = 0; r = n; d = 0;
-                fast = false; clean = true; pair_failed = false; known_fail = false;
-            } else if (pairs && fast && !(iw & 2u) && (bp & 31u) != 31u && bp + 1 < bp_end) {
-                const uint32_t rowoff = ((uint32_t)qw & 15u) * p.ix.rank_stride;
+            } else {
+                const uint32_t rowoff = ((uint32_t)qw & 3u) * p.ix.rank_stride;  // 32-bit word index
                 const uint32_t bl = l >> 5, br = r >> 5;
-                const uint64_t wl = __ldg(p.ix.rank2 + (rowoff + bl));
-                const uint64_t wr = (br == bl) ? wl : __ldg(p.ix.rank2 + (rowoff + br));
+                const uint64_t wl = __ldg(p.ix.rank + (rowoff + bl));
+                const uint64_t wr = (br == bl) ? wl : __ldg(p.ix.rank + (rowoff + br));
                 const uint32_t nl = (uint32_t)(wl >> 32) + __popc((uint32_t)wl & ((1u << (l & 31)) - 1u));
                 const uint32_t nr = (uint32_t)(wr >> 32) + __popc((uint32_t)wr & ((1u << (r & 31)) - 1u));
                 if (COUNT) {
                     const bool sp = (bl >> 2) != (br >> 2);
                     ++cnt_att; cnt_split += sp;
-                    if (bp + 1 >= bp_emit) { ++cnt_att_e; cnt_split_e += sp; }
+                    if (bp >= bp_emit) { ++cnt_att_e; cnt_split_e += sp; }
                 }
                 if (nl < nr) {
                     l = nl; r = nr;
-                    dA = d + 1 < k ? d + 1 : k;
-                    dB = d + 2 < k ? d + 2 : k;
-                    d = dB;
-                    adv = 2;
-                } else {
-                    adv = 0;
-                    fast = false;
-                    pair_failed = true;
-                }
-            } else {
-                bool ok = false;
-                if (known_fail) {
-                    known_fail = false;  // (d >= 1 here: the previous base has just extended)
-                } else {
-                    const uint32_t rowoff = ((uint32_t)qw & 3u) * p.ix.rank_stride;  // 32-bit word index
-                    const uint32_t bl = l >> 5, br = r >> 5;
-                    const uint64_t wl = __ldg(p.ix.rank + (rowoff + bl));
-                    const uint64_t wr = (br == bl) ? wl : __ldg(p.ix.rank + (rowoff + br));
-                    const uint32_t nl = (uint32_t)(wl >> 32) + __popc((uint32_t)wl & ((1u << (l & 31)) - 1u));
-                    const uint32_t nr = (uint32_t)(wr >> 32) + __popc((uint32_t)wr & ((1u << (r & 31)) - 1u));
-                    if (COUNT) {
-                        const bool sp = (bl >> 2) != (br >> 2);
-                        ++cnt_att; cnt_split += sp;
-                        if (bp >= bp_emit) { ++cnt_att_e; cnt_split_e += sp; }
-                    }
-                    ok = nl < nr;
-                    if (ok) { l = nl; r = nr; }
-                }
-                if (ok) {
                     d = d + 1 < k ? d + 1 : k;
-                    dA = d;
-                    fast = clean && !pair_failed;
-                    known_fail = pair_failed;
-                    pair_failed = false;
-                    clean = true;
                 } else if (d != 0) {
                     // contract_left to the largest depth that changes the interval: t = max(LCS[l], LCS[r])
-                    adv = 0;
-                    clean = false;
-                    pair_failed = false;
+                    advance = false;
                     const uint32_t el = __ldg(p.ix.links + l), er = __ldg(p.ix.links + r);
                     const bool scanned = ms_contract(p.ix, el, er, l, r, d);
                     if (COUNT) {
                         ++cnt_con; cnt_extra += scanned;
                         if (bp >= bp_emit) { ++cnt_con_e; cnt_extra_e += scanned; }
                     }
-                } else {  // nothing matches this base: it is emitted with d == 0
-                    fast = false; clean = true; pair_failed = false;
                 }
             }
-            if (adv) {
-                if (COUNT) cnt_proc += adv;
+            if (advance) {
+                if (COUNT) ++cnt_proc;
                 if (bp >= bp_emit) {
                     if (COUNT) ++cnt_emit;
-                    stg[bp & 31u] = (uint8_t)(adv == 2 ? dA : d);
+                    stg[bp & 31u] = (uint8_t)d;
                     if (INTERVALS) {
                         p.l_out[(wbase << 5) + bp] = l;
                         p.r_out[(wbase << 5) + bp] = r;
                     }
                 }
-                if (adv == 2 && bp + 1 >= bp_emit) {
-                    if (COUNT) ++cnt_emit;
-                    stg[(bp + 1) & 31u] = (uint8_t)dB;
-                }
-                bp += adv;
-                qw >>= 2 * adv;
-                iw >>= adv;
+                ++bp;
+                qw >>= 2;
+                iw >>= 1;
                 if ((bp & 31) == 0 || bp == bp_end) {
                     if (bp > bp_emit) {  // flush the 32 (or last, partial) staged positions
                         const uint32_t* w = reinterpret_cast<const uint32_t*>(stg);
@@ -645,16 +589,54 @@ __device__ __forceinline__ uint32_t src_apply(uint32_t f, uint32_t c_in) {
     return c_in > x ? c_in - x : 0u;
 }
 
+// MS bytes beyond the part of the vector that is in memory (the fused kernel keeps the MS of one tile plus a short
+// look-ahead in shared memory).  When the look-ahead of derandomize runs past `end`, lane 0 continues the MS
+// recurrence from the state at `end` and the warp reads the new values from `ring` (64 bytes, indexed by position
+// modulo 64).  Rare: it takes a run of more than MS_LOOKAHEAD positions whose derandomized value stays undecided.
+struct MsTail {
+    uint64_t end;        // MS is in memory for positions < end
+    uint32_t l, r, d;    // MS state after position end - 1
+    uint8_t* ring;       // this warp's 64 bytes
+    const IndexView* ix;
+};
+__device__ __forceinline__ void ms_feed_base(const IndexView& ix, uint32_t c, uint32_t& l, uint32_t& r, uint32_t& d);
+
 // Clamped derandomized value of position e (first position right of a tile).  Warp-uniform.
-__device__ __forceinline__ uint32_t lookahead_c(const TrParams& p, uint64_t e, int lane) {
+// `ms` is indexed by padded position; `tail` (optional) says where it ends and how to continue it.
+__device__ __forceinline__ uint32_t lookahead_c(const TrParams& p, const uint8_t* ms, uint64_t e, int lane,
+                                                const MsTail* tail = nullptr) {
     if (sep_bit(p.q, (int64_t)e)) return 0u;  // tile ends exactly at a query end: nothing enters
     uint32_t dist = 0;       // N positions skipped before the first source
     bool in_run = false;     // source found, waiting for the first SET0
     uint32_t src_val = 0, src_dist = 0, parity = 0;
+    uint64_t have = tail ? tail->end : ~0ull;  // MS known for positions < have (memory, then the ring)
+    uint32_t tl = 0, tr = 0, td = 0;
+    if (tail) { tl = tail->l; tr = tail->r; td = tail->d; }
     for (uint64_t base = e;; base += 32) {
         const uint64_t pp = base + lane;
+        if (tail && base + 33 > have) {  // warp-uniform: this round reads positions up to base + 32
+            if (lane == 0) {
+#ifdef KBO_HOST_EMU
+                ++emu_tail_extensions();  // (tests check that this path is reached)
+#endif
+                for (uint64_t q = have; q < base + 33; ++q) {
+                    uint32_t v = 0;
+                    if (q < p.q.Lp && !((__ldg(p.q.inv + (q >> 5)) >> (q & 31)) & 1u)) {
+                        ms_feed_base(*tail->ix, (uint32_t)(__ldg(p.q.pack + (q >> 5)) >> (2 * (q & 31))) & 3u, tl, tr, td);
+                        v = td;
+                    } else {
+                        tl = 0; tr = tail->ix->n; td = 0;
+                    }
+                    tail->ring[q & 63] = (uint8_t)v;
+                }
+            }
+            have = base + 33;
+            __syncwarp();
+        }
         const bool s0 = sep_bit(p.q, (int64_t)pp), s1 = sep_bit(p.q, (int64_t)pp + 1);
-        const uint32_t m0 = s0 ? 0u : p.ms[pp], m1 = s1 ? 0u : p.ms[pp + 1];  // (K1 never wrote past the batch)
+        uint32_t m0 = 0, m1 = 0;  // (K1 never wrote past the batch)
+        if (!s0) m0 = (tail && pp >= tail->end) ? tail->ring[pp & 63] : ms[pp];
+        if (!s1) m1 = (tail && pp + 1 >= tail->end) ? tail->ring[(pp + 1) & 63] : ms[pp + 1];
         const bool last = !s0 && s1;
         const bool elig = !s0 && !last && (m0 > p.thr || m0 == p.k);
         const bool source = s0 || last || elig;
@@ -732,7 +714,7 @@ __global__ void __launch_bounds__(K2_WARPS * 32) derand_translate_kernel(TrParam
         for (int t = 0; t < K2_PER_LANE; ++t) m[t] = (w[t >> 2] >> (8 * (t & 3))) & 0xffu;
         m[K2_PER_LANE] = ((sf >> 18) & 1u) ? 0u : p.ms[P + K2_PER_LANE];
     }
-    const uint32_t c_e = lookahead_c(p, s + K2_TILE, lane);
+    const uint32_t c_e = lookahead_c(p, p.ms, s + K2_TILE, lane);
     const bool e_sep = sep_bit(p.q, (int64_t)(s + K2_TILE));
     const uint32_t m_e = e_sep ? 0u : p.ms[s + K2_TILE];
     const bool e_last = !e_sep && sep_bit(p.q, (int64_t)(s + K2_TILE) + 1);
@@ -900,55 +882,57 @@ __device__ __forceinline__ void warp_copy_out(const uint8_t* st, uint32_t src_of
     if (done + lane < n) dst[done + lane] = st[src_off + done + lane];
 }
 
-template <bool CHARS>
-__global__ void __launch_bounds__(K2B_WARPS * 32) derand_translate_bits_kernel(TrParams p) {
-    __shared__ uint32_t lut[256];                                     // (4 bits b0, 4 bits b1) -> 4 characters
-    __shared__ __align__(16) uint8_t stage[K2B_WARPS][K2B_TILE + 16];
-    if (CHARS) {
-        for (uint32_t i = threadIdx.x; i < 256; i += blockDim.x) {
-            uint32_t v = 0;
-            for (int j = 0; j < 4; ++j) {
-                const uint32_t code = ((i >> j) & 1u) | (((i >> (4 + j)) & 1u) << 1);  // 0 M, 1 -, 2 X, 3 R
-                const uint32_t ch = code == 0 ? 'M' : (code == 1 ? '-' : (code == 2 ? 'X' : 'R'));
-                v |= ch << (8 * j);
-            }
-            lut[i] = v;
+// (4 bits b0, 4 bits b1) -> 4 characters; all threads of the block, followed by __syncthreads by the caller
+__device__ __forceinline__ void k2b_fill_lut(uint32_t* lut) {
+    for (uint32_t i = threadIdx.x; i < 256; i += blockDim.x) {
+        uint32_t v = 0;
+        for (int j = 0; j < 4; ++j) {
+            const uint32_t code = ((i >> j) & 1u) | (((i >> (4 + j)) & 1u) << 1);  // 0 M, 1 -, 2 X, 3 R
+            const uint32_t ch = code == 0 ? 'M' : (code == 1 ? '-' : (code == 2 ? 'X' : 'R'));
+            v |= ch << (8 * j);
         }
-        __syncthreads();
+        lut[i] = v;
     }
-    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-    const uint64_t tile = (uint64_t)blockIdx.x * K2B_WARPS + warp;
-    if (tile >= p.n_tiles) return;  // warp-uniform
-    const uint64_t s = tile * K2B_TILE, e = s + K2B_TILE;
+}
+
+// One warp, one group of up to 32 words (1024 padded positions) starting at position s (a multiple of 32): lanes
+// 0..last hold one word each, lanes above `last` are inert (they behave like words full of separators and write
+// nothing).  `ms` is indexed by padded position and must be readable for [s - 1, s + 32 (last + 1) + 4) -- global
+// memory (K2b after K1) or the fused kernel's shared-memory tile; `tail` continues it for the look-ahead (MsTail).
+template <bool CHARS>
+__device__ __forceinline__ void k2b_group(const TrParams& p, const uint8_t* ms, const uint64_t s, const int last,
+                                          const MsTail* tail, const uint32_t* lut, uint8_t* stage) {
+    const int lane = threadIdx.x & 31;
+    const uint64_t e = s + 32ull * (uint32_t)(last + 1);
     const uint64_t P = s + 32ull * lane;
     const uint32_t k = p.k, thr = p.thr;
     const uint32_t H = 0x80808080u;
 
     // ---- loads: 32 MS bytes + the first four of the next word; separator bits around the word -------------
-    const uint32_t S = __ldg(p.q.sep + (P >> 5));
+    const uint32_t S = lane <= last ? __ldg(p.q.sep + (P >> 5)) : ~0u;
     uint32_t s_next = __shfl_down_sync(0xffffffffu, S, 1) & 1u;  // separator bit of P+32
-    if (lane == 31) s_next = sep_bit(p.q, (int64_t)e);
+    if (lane == last) s_next = sep_bit(p.q, (int64_t)e);
     uint32_t mw[9];
     {
         uint4 va = make_uint4(0u, 0u, 0u, 0u), vb = va;
         if (S != ~0u) {  // words past the end of the batch were never written by K1
-            va = *reinterpret_cast<const uint4*>(p.ms + P);
-            vb = *reinterpret_cast<const uint4*>(p.ms + P + 16);
+            va = *reinterpret_cast<const uint4*>(ms + P);
+            vb = *reinterpret_cast<const uint4*>(ms + P + 16);
         }
         mw[0] = va.x; mw[1] = va.y; mw[2] = va.z; mw[3] = va.w;
         mw[4] = vb.x; mw[5] = vb.y; mw[6] = vb.z; mw[7] = vb.w;
 #pragma unroll
         for (int j = 0; j < 8; ++j) mw[j] &= 0x7f7f7f7fu;  // bytes of separators may hold anything
         mw[8] = __shfl_down_sync(0xffffffffu, mw[0], 1);
-        if (lane == 31) mw[8] = s_next ? 0u : (*reinterpret_cast<const uint32_t*>(p.ms + P + 32) & 0x7f7f7f7fu);
+        if (lane == last) mw[8] = s_next ? 0u : (*reinterpret_cast<const uint32_t*>(ms + P + 32) & 0x7f7f7f7fu);
     }
     uint32_t s_prev = __shfl_up_sync(0xffffffffu, S, 1) >> 30;   // bit0 = sep(P-2), bit1 = sep(P-1)
     if (lane == 0) s_prev = sep_bit(p.q, (int64_t)P - 2) | (sep_bit(p.q, (int64_t)P - 1) << 1);
 
     // ---- value entering the tile from the right ---------------------------------------------------------------
-    const uint32_t c_e = lookahead_c(p, e, lane);
+    const uint32_t c_e = lookahead_c(p, ms, e, lane, tail);
     const bool e_sep = sep_bit(p.q, (int64_t)e);
-    const uint32_t m_e = e_sep ? 0u : (p.ms[e] & 0x7fu);
+    const uint32_t m_e = e_sep ? 0u : (((tail && e >= tail->end) ? tail->ring[e & 63] : ms[e]) & 0x7fu);
     const bool e_last = !e_sep && sep_bit(p.q, (int64_t)e + 1);
     const uint32_t eps_e = (!e_sep && !e_last && (m_e > thr || m_e == k)) ? (m_e - c_e) & 1u : 0u;
 
@@ -988,16 +972,16 @@ __global__ void __launch_bounds__(K2B_WARPS * 32) derand_translate_bits_kernel(T
 #pragma unroll
     for (int off = 1; off < 32; off <<= 1) {
         const uint32_t o = __shfl_down_sync(0xffffffffu, G, off);
-        if (lane + off < 32) G = par_compose(G, o);
+        if (lane + off <= last) G = par_compose(G, o);
     }
     uint32_t Gn = __shfl_down_sync(0xffffffffu, G, 1);
-    if (lane == 31) Gn = 0;
+    if (lane >= last) Gn = 0;
     const uint32_t eps = x ^ (open & (0u - par_apply(Gn, eps_e)));
 
     // ---- value of a source position of this word --------------------------------------------------------------
     auto source_value = [&](uint32_t i) -> uint32_t {
         if ((S >> i) & 1u) return 0u;
-        const uint32_t m = p.ms[P + i] & 0x7fu;
+        const uint32_t m = ms[P + i] & 0x7fu;
         if ((L >> i) & 1u) return ((GT >> i) & 1u) ? m : 0u;
         return m - ((eps >> i) & 1u);
     };
@@ -1012,10 +996,10 @@ __global__ void __launch_bounds__(K2B_WARPS * 32) derand_translate_bits_kernel(T
 #pragma unroll
     for (int off = 1; off < 32; off <<= 1) {
         const uint32_t o = __shfl_down_sync(0xffffffffu, HH, off);
-        if (lane + off < 32) HH = src_compose(HH, o);
+        if (lane + off <= last) HH = src_compose(HH, o);
     }
     uint32_t Hn = __shfl_down_sync(0xffffffffu, HH, 1);
-    if (lane == 31) Hn = 0;
+    if (lane >= last) Hn = 0;
     const uint32_t c_in = src_apply(Hn, c_e);  // clamped derandomized value of position P+32
 
     // ---- classes of the below-threshold runs ---------------------------------------------------------------------
@@ -1043,7 +1027,7 @@ __global__ void __launch_bounds__(K2B_WARPS * 32) derand_translate_bits_kernel(T
 
     // ---- neighbours across the word / tile boundaries --------------------------------------------------------
     uint32_t nPL = __shfl_down_sync(0xffffffffu, PL, 1) & 1u, nO1 = __shfl_down_sync(0xffffffffu, O1, 1) & 1u;
-    if (lane == 31) {
+    if (lane >= last) {
         nPL = (c_e > 0 && c_e < thr) ? 1u : 0u;
         nO1 = c_e == 1 ? 1u : 0u;
     }
@@ -1051,7 +1035,7 @@ __global__ void __launch_bounds__(K2B_WARPS * 32) derand_translate_bits_kernel(T
     if (lane == 0) {
         uint32_t c_left = 0;
         if (s > 0 && !(s_prev & 2u) && !(S & 1u)) {  // P-1 and P are in the same query
-            const uint32_t mp = p.ms[s - 1] & 0x7fu;
+            const uint32_t mp = ms[s - 1] & 0x7fu;
             if (mp > thr) {
                 const uint32_t eps0 = (E & 1u) ? (eps & 1u) : 0u;
                 const uint32_t op = parity_op(true, mp, mw[0] & 0xffu, k);
@@ -1075,16 +1059,18 @@ __global__ void __launch_bounds__(K2B_WARPS * 32) derand_translate_bits_kernel(T
     const uint32_t dash = V & Z0 & ~X;
 
     if (!CHARS) {
-        p.out_gap[P >> 5] = dash;
-        p.out_match[P >> 5] = V & ~Z0;  // 'M' or 'R'
-        p.out_r[P >> 5] = R;
+        if (lane <= last) {
+            p.out_gap[P >> 5] = dash;
+            p.out_match[P >> 5] = V & ~Z0;  // 'M' or 'R'
+            p.out_r[P >> 5] = R;
+        }
         return;
     }
 
     // ---- characters: padded layout in shared memory, then the runs between separators are copied out ---------
     {
         const uint32_t b0 = dash | R, b1 = X | R;
-        uint32_t* st = reinterpret_cast<uint32_t*>(&stage[warp][32 * lane]);
+        uint32_t* st = reinterpret_cast<uint32_t*>(stage + 32 * lane);
         uint4 o;
         o.x = lut[(b0 & 15u) | ((b1 & 15u) << 4)];
         o.y = lut[((b0 >> 4) & 15u) | (((b1 >> 4) & 15u) << 4)];
@@ -1109,13 +1095,27 @@ __global__ void __launch_bounds__(K2B_WARPS * 32) derand_translate_bits_kernel(T
             const uint32_t sp = 32u * l + (uint32_t)__ffs((int)sw) - 1u;
             sw &= sw - 1;
             if (sp > seg) {
-                warp_copy_out(stage[warp], seg, dst, sp - seg, lane);
+                warp_copy_out(stage, seg, dst, sp - seg, lane);
                 dst += sp - seg;
             }
             seg = sp + 1;
         }
     }
-    if (seg < K2B_TILE) warp_copy_out(stage[warp], seg, dst, K2B_TILE - seg, lane);
+    if (seg < K2B_TILE) warp_copy_out(stage, seg, dst, K2B_TILE - seg, lane);
+}
+
+template <bool CHARS>
+__global__ void __launch_bounds__(K2B_WARPS * 32) derand_translate_bits_kernel(TrParams p) {
+    __shared__ uint32_t lut[256];
+    __shared__ __align__(16) uint8_t stage[K2B_WARPS][K2B_TILE + 16];
+    if (CHARS) {
+        k2b_fill_lut(lut);
+        __syncthreads();
+    }
+    const int warp = threadIdx.x >> 5;
+    const uint64_t tile = (uint64_t)blockIdx.x * K2B_WARPS + warp;
+    if (tile >= p.n_tiles) return;  // warp-uniform
+    k2b_group<CHARS>(p, p.ms, tile * K2B_TILE, 31, nullptr, lut, stage[warp]);
 }
 
 // ---------------------------------------------------------------------------

@@ -15,6 +15,7 @@
 
 #include "../../kbo_b200/csrc/host_layout.hpp"
 #include "../../kbo_b200/csrc/kernels.cuh"
+#include "../../kbo_b200/csrc/fused.cuh"
 #include "../../kbo_b200/csrc/refine_host.hpp"
 #include "../../kbo_b200/csrc/sbwt_host.hpp"
 
@@ -92,6 +93,15 @@ static void finish(EmuIndex* e) {
     }
 }
 
+static int g_emu_fused = 0;         // 1: matches / find go through the fused K1 + K2b kernel (fused.cuh) where it applies
+static uint32_t g_emu_fused_chunk = 0;  // target positions per lane (0 = automatic)
+static int g_emu_sms = 4;           // "SM count" of the emulated device (tiles are rounded to a multiple of it)
+static uint64_t g_emu_fused_launches = 0, g_emu_fused_tiles = 0;
+extern "C" uint64_t emu_fused_launches() { return g_emu_fused_launches; }
+extern "C" uint64_t emu_fused_tiles() { return g_emu_fused_tiles; }
+extern "C" uint64_t emu_tail_extension_count() { return emu_tail_extensions(); }
+extern "C" void emu_set_fused(int on, uint32_t chunk, int sms) { g_emu_fused = on; g_emu_fused_chunk = chunk; g_emu_sms = sms > 0 ? sms : 4; }
+
 struct Staged {
     Geometry g;
     std::vector<uint64_t> pack;
@@ -146,6 +156,42 @@ static void stage_and_ms(EmuIndex* e, const uint8_t* concat, const uint64_t* off
             if (counters) ms_kernel<false, true>(mp); else ms_kernel<false, false>(mp);
         }
     });
+}
+
+// K0 + fused kernel (as capi.cu run_pack + run_fused).  Returns false when the parameters are outside its range.
+static bool emu_run_fused(EmuIndex* e, const uint8_t* concat, const uint64_t* offsets, uint64_t nq, uint32_t thr,
+                          uint8_t* chars_out, uint64_t off0, uint32_t* gap, uint32_t* match, uint32_t* rr,
+                          unsigned long long* counters, Staged* s) {
+    if (!k2b_supported(e->host.k, thr) || g_emu_k2_mode == 1) return false;
+    const uint64_t total = offsets[nq] - offsets[0];
+    s->g = make_geometry(total, nq, 0);
+    const Geometry& g = s->g;
+    FusedGeom fg;
+    if (!fused_geometry(g.Lp, e->host.k, chars_out != nullptr, g_emu_sms, g_emu_fused_chunk, &fg)) return false;
+    s->pack.assign(g.n_words, 0xdeadbeefdeadbeefull);
+    s->inv.assign(g.n_words, 0xdeadbeef);
+    s->sep.assign(g.n_words, 0xdeadbeef);
+    s->wq.assign(g.n_words, 0xdeadbeef);
+    QueryView& qv = s->qv;
+    qv.pack = s->pack.data(); qv.inv = s->inv.data(); qv.sep = s->sep.data(); qv.wq = s->wq.data();
+    qv.Lp = g.Lp; qv.n_words = g.n_words;
+    emu_launch_par((unsigned)((g.n_words + 127) / 128), 128, [&]() {
+        pack_queries_kernel(concat, offsets, nq, qv, s->pack.data(), s->inv.data(), s->sep.data(), s->wq.data());
+    });
+    FusedParams fp;
+    std::memset(&fp, 0, sizeof(fp));
+    fp.ix = e->view; fp.q = qv;
+    fp.tr.ms = nullptr; fp.tr.q = qv; fp.tr.k = e->host.k; fp.tr.thr = thr; fp.tr.out = chars_out; fp.tr.off0 = off0;
+    fp.tr.out_gap = gap; fp.tr.out_match = match; fp.tr.out_r = rr;
+    fp.tile_len = fg.tile_len; fp.chunk = fg.chunk; fp.stage_words = fg.stage_words; fp.task_cap = fg.task_cap;
+    fp.flags = g_emu_flags; fp.mask_words = g.n_tiles_b * 32; fp.counters = counters;
+    ++g_emu_fused_launches;
+    g_emu_fused_tiles += fg.n_tiles;
+    emu_launch_par((unsigned)fg.n_tiles, FUSED_THREADS, [&]() {
+        if (chars_out) { if (counters) ms_fused_kernel<true, true>(fp); else ms_fused_kernel<true, false>(fp); }
+        else { if (counters) ms_fused_kernel<false, true>(fp); else ms_fused_kernel<false, false>(fp); }
+    });
+    return true;
 }
 
 template <typename T>
@@ -237,6 +283,9 @@ void emu_matches_batch(void* h, const uint8_t* concat, const uint64_t* offsets, 
                        uint32_t chunk_len, uint8_t* chars_out) {
     EmuIndex* e = (EmuIndex*)h;
     Staged s;
+    if (g_emu_fused && emu_run_fused(e, concat + offsets[0], offsets, nq, thr, chars_out, offsets[0], nullptr, nullptr,
+                                     nullptr, nullptr, &s))
+        return;
     stage_and_ms(e, concat + offsets[0], offsets, nq, chunk_len, false, nullptr, &s);
     TrParams tp;
     tp.ms = s.ms.data();
@@ -329,6 +378,16 @@ uint64_t emu_find_batch(void* h, const uint8_t* concat, const uint64_t* offsets,
                         uint32_t max_gap_len, uint64_t* out7, uint64_t cap, uint64_t* rle_offsets) {
     EmuIndex* e = (EmuIndex*)h;
     Staged s;
+    if (g_emu_fused) {
+        const Geometry g0 = make_geometry(offsets[nq] - offsets[0], nq, 0);
+        const uint64_t nw0 = g0.n_tiles_b * 32;
+        std::vector<uint32_t> gap(nw0, 0xdeadbeef), match(nw0, 0xdeadbeef), rr(nw0, 0xdeadbeef);
+        if (emu_run_fused(e, concat + offsets[0], offsets, nq, thr, nullptr, 0, gap.data(), match.data(), rr.data(), nullptr, &s)) {
+            std::vector<uint64_t> rel(nq + 1);
+            for (uint64_t i = 0; i <= nq; ++i) rel[i] = offsets[i] - offsets[0];
+            return emu_run_rle(gap.data(), match.data(), rr.data(), s.qv, nw0, rel.data(), nq, max_gap_len, out7, cap, rle_offsets);
+        }
+    }
     stage_and_ms(e, concat + offsets[0], offsets, nq, 0, false, nullptr, &s);
     const uint64_t nw = s.g.n_tiles_b * 32;
     std::vector<uint32_t> gap(nw), match(nw), rr(nw);

@@ -100,6 +100,8 @@ inline unsigned long long atomicAdd(unsigned long long* p, unsigned long long v)
     return __atomic_fetch_add(p, v, __ATOMIC_RELAXED);
 }
 
+inline unsigned long long& emu_tail_extensions() { static unsigned long long n = 0; return n; }
+
 // ---- launchers --------------------------------------------------------------
 template <typename F>
 inline void emu_launch_seq(unsigned grid, unsigned block, F&& body) {

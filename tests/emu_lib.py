@@ -64,6 +64,10 @@ def lib():
         L.emu_rle_batch.restype = C.c_uint64
         L.emu_rle_batch.argtypes = [u8p, u64p, C.c_uint64, C.c_uint32, u64p, C.c_uint64, u64p]
         L.emu_set_rank2.argtypes = [C.c_int]
+        L.emu_set_fused.argtypes = [C.c_int, C.c_uint32, C.c_int]
+        L.emu_fused_launches.restype = C.c_uint64
+        L.emu_fused_tiles.restype = C.c_uint64
+        L.emu_tail_extension_count.restype = C.c_uint64
         L.emu_find_batch.restype = C.c_uint64
         L.emu_find_batch.argtypes = [C.c_void_p, u8p, u64p, C.c_uint64, C.c_uint32, C.c_uint32, u64p, C.c_uint64, u64p]
         _lib = L
@@ -208,6 +212,11 @@ def pack(concat, offsets):
     lib().emu_pack(_p(concat, C.c_uint8), _p(offsets, C.c_uint64), nq, _p(pk, C.c_uint64), _p(iv, C.c_uint32),
                    _p(sp, C.c_uint32), _p(wq, C.c_uint32))
     return pk, iv, sp, wq
+
+
+def set_fused(on, chunk=0, sms=4):
+    """matches / find through the fused K1 + K2b kernel (fused.cuh); chunk = target positions per lane, sms = emulated SM count."""
+    lib().emu_set_fused(int(on), int(chunk), int(sms))
 
 
 def set_k2_mode(mode):

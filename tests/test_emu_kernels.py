@@ -178,16 +178,23 @@ def test_ms_tiny_index_and_counters():
 
 
 # -------------------------------------------------- K2: derandomize+translate ---
-@pytest.fixture(autouse=True, params=["dispatch", "k2-only"])
+@pytest.fixture(autouse=True, params=["dispatch", "k2-only", "fused", "fused-small-chunks"])
 def k2_mode(request):
-    """Tests that reach derandomize+translate run twice: product dispatch (K2b where it applies) and K2 alone."""
+    """Tests that reach derandomize+translate run several times: product dispatch of the separate kernels (K2b where it
+    applies), K2 alone, and the fused K1 + K2b kernel (fused.cuh) with the default and with a tiny lane chunk (many
+    tiles, tasks that span lanes' whole chunks, look-ahead past the shared-memory tile)."""
     name = request.node.originalname or request.node.name  # the function name, without the parameter ids
     touches_k2 = any(t in name for t in ("k2", "matches", "map", "call", "find", "rle"))
+    touches_fused = any(t in name for t in ("matches", "find")) and "rle_kernel" not in name
     if request.param == "k2-only" and not touches_k2:
         pytest.skip("does not reach K2")
+    if request.param.startswith("fused") and not touches_fused:
+        pytest.skip("does not reach the fused kernel")
     E.set_k2_mode(1 if request.param == "k2-only" else 0)
+    E.set_fused(request.param.startswith("fused"), 9 if request.param == "fused-small-chunks" else 0, 3)
     yield
     E.set_k2_mode(0)
+    E.set_fused(False)
 
 
 def valid_ms_vector(rng, n, k, thr):
@@ -281,6 +288,35 @@ def test_matches_batch_many_tiny_queries(seed):
 
 
 # -------------------------------------------- standalone derandomize / translate ---
+def test_matches_long_plateaus_cross_tiles(request):
+    """MS plateaus between the threshold and k (low-complexity runs longer than anything in the index) keep the
+    derandomize look-ahead undecided for hundreds of positions: in the fused kernel it runs past the tile's MS bytes
+    and continues the recurrence on the fly (MsTail); find on the same batch crosses tiles with open segments."""
+    rng = np.random.default_rng(77)
+    left, right = rand_seq(3000, 78), rand_seq(3000, 79)
+    ref = left + b"C" + b"A" * 25 + b"G" + right + b"T" + b"AC" * 13 + b"G" + rand_seq(500, 80)
+    o = O.OracleIndex([ref], k=31)
+    e = E.EmuIndex.build([ref], k=31)
+    queries = [left[2000:] + b"C" + b"A" * 700 + b"G" + right[:800],
+               b"A" * 1500,
+               right[100:900] + b"AC" * 400 + right[900:1500],
+               left[:1200], b"ACA", b"A" * 90 + b"N" + b"A" * 200]
+    concat, offsets = E.csr(queries)
+    ext0, launches0 = E.lib().emu_tail_extension_count(), E.lib().emu_fused_launches()
+    for p in (1e-7, 0.3):
+        thr = O.random_match_threshold(31, o.n_kmers, 4, p)
+        assert 2 <= thr < 25
+        _, want, _ = o.matches_batch(concat, offsets, p)
+        got = b"".join(e.matches_batch(queries, thr))
+        assert got == want.tobytes()
+        for gap in (0, 3):
+            assert e.find_batch(queries, thr, gap) == [o.find(q, p, gap) for q in queries]
+    if "fused" in request.node.name:
+        assert E.lib().emu_fused_launches() > launches0
+        if "small-chunks" in request.node.name:  # (tile ends fall inside the plateaus)
+            assert E.lib().emu_tail_extension_count() > ext0  # the look-ahead did leave the tile's MS bytes
+
+
 @pytest.mark.parametrize("k,thr", [(3, 2), (31, 15), (31, 22), (63, 40), (5, 4)])
 def test_general_derandomize_arbitrary_vectors(k, thr):
     rng = np.random.default_rng(k + thr)

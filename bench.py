@@ -2,26 +2,28 @@
 """bench.py -- query bases/s of the kbo MS hot path (matches/find) on B200.
 
 Workload (BASELINE.json configs[1]): kbo::find of 10,000 synthetic 1 kbp gene queries (1 % SNPs)
-against a 5 Mbp reference, k = 31, p = 1e-7; the index (30 MB: rank words, link words, LCS) is L2 resident.  A "step" is one
+against a 5 Mbp reference, k = 31, p = 1e-7; the index (rank words, rank2 words, link words, LCS) is L2 resident.  A "step" is one
 pass of the hot path over one batch of 10,000 queries (10^7 query bases).
 
   value : whole-job throughput with the batch already resident in HBM (kbo_find_batch_device:
-          K0 pack -> K1 matching statistics -> K2b derandomize+translate (masks) -> K4 run-length records),
-          independent steps round-robin on `--streams` streams forked from / joined into the timing stream,
-          CUDA events on that stream, max over ranks.  (`--tuned-chunk-len N` repeats the region with an explicit
-          chunk length for comparison; the library picks it per call from the batch size and the observed overlap.)  Steps rotate through `--batches` distinct batches whose total
-          size exceeds L2, so queries always come from HBM while the index stays L2 resident.
-  e2e   : the same metric through the host-buffer C ABI call a kbo user makes (kbo_find_batch):
-          pinned host -> device copy of the queries, kernels, device -> host copy of the RLE records.
-  roofline     : K1 (ms_kernel), algorithmic bytes / its CUDA-event duration vs the
-                 measured HBM peak (MEASURED_PEAKS.json); random-sector L2/HBM rates beside it.
+          K0 pack -> fused K1+K2b (matching statistics, derandomize, translate; MS only in shared memory) -> K4
+          run-length records), independent steps round-robin on `--streams` streams forked from / joined into the
+          timing stream, CUDA events on that stream, max over ranks.  Steps rotate through `--batches` distinct
+          batches whose total size exceeds L2, so queries always come from HBM while the index stays L2 resident.
+          config.single_stream is the same region on ONE stream.
+  e2e   : the same metric through the host-buffer C ABI a kbo user calls: kbo_find_batch_submit / kbo_job_wait from
+          ONE host thread with `--e2e-depth` batches in flight: pinned host -> device copy of the queries, kernels,
+          RLE records and per-query offsets written by the last kernel straight into the caller's pinned buffers.
+          Multi-GPU: every rank does this for its own batches; the per-step record counts of all ranks are gathered
+          with NCCL at the end, inside the timed region (the records stay on the ranks' hosts).
+  roofline     : the fused kernel, algorithmic bytes / its CUDA-event duration, measured in the same
+                 configuration as `value`, vs the measured L2 random-sector rate (the index is L2 resident; the
+                 HBM copy peak of MEASURED_PEAKS.json is given beside it).
   cpu_baseline : the C++ oracle (restatement of kbo 0.5.1 + sbwt 0.3.4 semantics) running kbo::find
                  on all host cores over a bounded sample of the same workload.
 
 `--impl reference` times that CPU restatement alone (the reference crate cannot be built here: no
 Rust toolchain and its MS engine is the un-vendored crate sbwt 0.3.4).
-Multi-GPU (torchrun, one rank per GPU): the index is replicated, every rank processes its own
-batches (weak scaling), no collective on the data path; NCCL only carries the timing reduction.
 """
 import argparse
 import json
@@ -60,13 +62,14 @@ def parse_args():
     ap.add_argument("--chunk-len", type=int, default=0, help="MS chunk length (0 = automatic)")
     ap.add_argument("--ms-flags", type=int, default=0, help="experiment switches (2: K2 instead of K2b)")
     ap.add_argument("--no-prefix-table", action="store_true", help="build the index without the prefix-state table (comparison)")
+    ap.add_argument("--no-rank2", action="store_true", help="build the index without the rank2 rows: one base per probe (comparison)")
     ap.add_argument("--no-l2-persist", action="store_true", help="do not mark the index persisting in L2 (comparison)")
-    ap.add_argument("--tuned-chunk-len", type=int, default=0,
-                    help="second timed region with this chunk length (0 = skip); only when --chunk-len is automatic")
     ap.add_argument("--streams", type=int, default=6,
                     help="CUDA streams the device-resident steps are issued round-robin on (independent batches)")
-    ap.add_argument("--e2e-threads", type=int, default=6,
-                    help="host threads issuing the end-to-end calls concurrently (kbo-cli style per-query threading)")
+    ap.add_argument("--e2e-depth", type=int, default=6,
+                    help="batches one host thread keeps in flight through kbo_find_batch_submit / kbo_job_wait")
+    ap.add_argument("--e2e-threads", type=int, default=0,
+                    help="> 0: issue the end-to-end steps as synchronous kbo_find_batch calls from this many host threads instead")
     ap.add_argument("--pipeline-parts", type=int, default=0, help="sub-batches of a host-buffer call (0 = automatic)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--cpu-seconds", type=float, default=20.0, help="target CPU work (core-seconds) of the cpu_baseline sample")
@@ -88,7 +91,7 @@ class ClockSampler:
     def start(self):
         try:
             self.proc = subprocess.Popen(["nvidia-smi", "-i", str(self.device), "--query-gpu=" + self.Q,
-                                          "--format=csv,noheader,nounits", "-lms", "20"],
+                                          "--format=csv,noheader,nounits", "-lms", "100"],
                                          stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
             self.thread = threading.Thread(target=self._read, daemon=True)
             self.thread.start()
@@ -208,13 +211,13 @@ def run_reference(args, rank, world):
             "unit": "query bases/s", "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup,
             "ms_per_step": 1e3 * total / args.steps, "higher_is_better": True, "scaling": "weak",
             "vs_baseline": None, "dtype": "u8", "data": "synthetic",
-            "config": config_dict(args, sample_note=sample),
+            "config": config_dict(args), "impl_detail": {"sample": sample},
             "cpu_baseline": {"value": value, "unit": "query bases/s", "cores": cores, "kind": "port", "sample": sample},
             "e2e": {"value": value, "unit": "query bases/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
     print(json.dumps(line), flush=True)
 
 
-def config_dict(args, sample_note=None):
+def config_dict(args):
     c = {"workload": "kbo::find of %d synthetic %d bp gene queries (1%% SNPs) vs a %d bp synthetic reference, k=%d, "
                      "p=%g (BASELINE.json configs[1]; index L2-resident)" % (args.queries, args.query_len, args.ref_len,
                                                                            K, P),
@@ -222,30 +225,22 @@ def config_dict(args, sample_note=None):
          "l2_policy": "inputs larger than L2: steps rotate through %d distinct batches (%d MB of queries); the index "
                       "is L2-resident by the config's design" % (args.batches,
                                                                  args.batches * args.queries * args.query_len // 10**6)}
-    if sample_note:
-        c["sample"] = sample_note
-    return c
+    return c  # identical for both arms; everything arm-specific goes to the line's top-level "impl_detail"
 
 
-def pin_to_gpu_numa_node(torch, dev):
-    """Multi-GPU boxes: run this rank's host threads (and first-touch its pinned buffers) on the CPUs local to its GPU,
-    so that the end-to-end copies do not cross the socket interconnect.  Best effort; returns a note for the JSON line."""
+def partition_cpus(local_rank, local_world):
+    """One rank per GPU on one box: give every rank its own slice of the CPUs this process may use (round 1 pinned all
+    ranks to the same NUMA-local list, i.e. onto each other).  Returns a note for the JSON line."""
     try:
-        bus = torch.cuda.get_device_properties(dev).pci_bus_id
-        dom = torch.cuda.get_device_properties(dev).pci_domain_id
-        devn = torch.cuda.get_device_properties(dev).pci_device_id
-        path = "/sys/bus/pci/devices/%04x:%02x:%02x.0/local_cpulist" % (dom, bus, devn)
-        cpus = set()
-        for part in open(path).read().strip().split(","):
-            a, _, b = part.partition("-")
-            cpus.update(range(int(a), int(b or a) + 1))
-        cpus &= os.sched_getaffinity(0)
-        if cpus:
-            os.sched_setaffinity(0, cpus)
-            return "rank pinned to the %d CPUs local to its GPU" % len(cpus)
-    except Exception as ex:  # topology not exposed (containers): keep the inherited affinity
-        return "no NUMA pinning (%s)" % type(ex).__name__
-    return None
+        cpus = sorted(os.sched_getaffinity(0))
+        per = len(cpus) // max(1, local_world)
+        if per < 1:
+            return "no pinning (%d CPUs for %d ranks)" % (len(cpus), local_world)
+        mine = cpus[local_rank * per:(local_rank + 1) * per]
+        os.sched_setaffinity(0, mine)
+        return "rank pinned to its own %d of %d CPUs" % (len(mine), len(cpus))
+    except Exception as ex:
+        return "no pinning (%s)" % type(ex).__name__
 
 
 # --------------------------------------------------------------------------------------- our arm ---
@@ -258,7 +253,7 @@ def run_ours(args, rank, local_rank, world):
         raise SystemExit("bench.py: no CUDA device (kbo_b200 has no CPU fallback)")
     dev = local_rank
     torch.cuda.set_device(dev)
-    numa_note = pin_to_gpu_numa_node(torch, dev) if world > 1 else None
+    numa_note = partition_cpus(local_rank, int(os.environ.get("LOCAL_WORLD_SIZE", world))) if world > 1 else None
     dist = None
     if world > 1:
         if os.environ.get("NCCL_DEBUG", "").upper() == "VERSION":
@@ -272,6 +267,8 @@ def run_ours(args, rank, local_rank, world):
         api.set_l2_persist(False)
     if args.no_prefix_table:
         api.set_prefix_table(False)
+    if args.no_rank2:
+        api.set_rank2(False)
     if args.pipeline_parts:
         api.set_pipeline_parts(args.pipeline_parts)
 
@@ -295,9 +292,10 @@ def run_ours(args, rank, local_rank, world):
 
     workers = [torch.cuda.Stream() for _ in range(max(1, args.streams))]
 
-    def step_device(s, on=None):
+    def step_device(s, on=None, use=None):
         b = s % len(batches)
-        st = on if on is not None else workers[s % len(workers)].cuda_stream
+        use = use or workers
+        st = on if on is not None else use[s % len(use)].cuda_stream
         api.find_device(index, d_in[b].data_ptr(), d_off.data_ptr(), offsets, d_rle[b].data_ptr(), rle_cap,
                         d_rle_off[b].data_ptr(), P, 0, st)
 
@@ -310,16 +308,16 @@ def run_ours(args, rank, local_rank, world):
     # ---- value: device-resident ---------------------------------------------------------------
     # Steps are independent batches; they are issued round-robin on `--streams` streams that fork from and
     # join into the timing stream, so the CUDA events on that stream bracket exactly the K steps.
-    def timed_region(n_steps):
-        """K steps round-robin on the worker streams, bracketed by events on the timing stream; returns ms."""
+    def timed_region(n_steps, use):
+        """K steps round-robin on the streams `use`, bracketed by events on the timing stream; returns ms."""
         a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         barrier()
         a.record(stream)
-        for w in workers:
+        for w in use:
             w.wait_event(a)
         for s in range(n_steps):
-            step_device(args.warmup + s)
-        for w in workers:
+            step_device(args.warmup + s, use=use)
+        for w in use:
             done = torch.cuda.Event()
             done.record(w)
             stream.wait_event(done)
@@ -327,32 +325,29 @@ def run_ours(args, rank, local_rank, world):
         barrier()
         return a.elapsed_time(b)
 
+    def reduce_max(x):
+        t = torch.tensor([x], dtype=torch.float64, device="cuda")
+        if dist is not None:
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        return float(t.item())
+
     for s in range(max(args.warmup, len(workers))):
         step_device(s)
     barrier()
-    sampler = ClockSampler(dev)
-    sampler.start()
+    sampler = ClockSampler(dev) if rank == 0 else None  # one sampler per box, 100 ms period
+    if sampler:
+        sampler.start()
     n0 = api.kernel_launch_count()
-    ms_total = timed_region(args.steps)
+    ms_total = timed_region(args.steps, workers)
     launches = api.kernel_launch_count() - n0
-    clocks = sampler.stop()
-    # the same region with the chunk length that suits overlapped launches (fewer warm-up bases per chunk; a single
-    # launch would be too narrow, the concurrent ones fill the machine).  Reported in config["overlap_tuned"].
-    tuned = None
-    if args.chunk_len == 0 and args.tuned_chunk_len:
-        api.set_chunk_len(args.tuned_chunk_len)
-        for s in range(max(args.warmup, len(workers))):
-            step_device(s)
-        ms_tuned = timed_region(args.steps)
-        api.set_chunk_len(0)
-        tt = torch.tensor([ms_tuned], dtype=torch.float64, device="cuda")
-        if dist is not None:
-            dist.all_reduce(tt, op=dist.ReduceOp.MAX)
-        tuned = {"chunk_len": args.tuned_chunk_len, "ms_per_step": float(tt.item()) / args.steps,
-                 "value": world * args.steps * bases_per_step / (float(tt.item()) * 1e-3)}
-    # per-kernel durations: the same steps again with CUDA events around K0 / K1 / K2 of every call; the
-    # library runs these instrumented calls serially (no sub-batch concurrency), so a kernel's elapsed time
-    # is its own duration
+    ms_max = reduce_max(ms_total)
+    value = world * args.steps * bases_per_step / (ms_max * 1e-3)
+    # the same steps on ONE stream (no overlap between steps)
+    for s in range(args.warmup):
+        step_device(s, use=workers[:1])
+    ms_single = reduce_max(timed_region(args.steps, workers[:1]))
+    # per-kernel durations: the same steps again with CUDA events around K0 / fused K1+K2b of every call, serially on
+    # the timing stream (same kernels, same geometry as the timed region: the library derives it from the batch only)
     api.set_kernel_timing(True)
     step_device(0, on=sptr)  # sizes the serial workspace; discarded
     torch.cuda.synchronize()
@@ -362,91 +357,122 @@ def run_ours(args, rank, local_rank, world):
     torch.cuda.synchronize()
     api.set_kernel_timing(False)
     ksum, kcalls = api.collect_kernel_times(index, sptr)
-    t = torch.tensor([ms_total], dtype=torch.float64, device="cuda")
     lt = torch.tensor([float(launches)], dtype=torch.float64, device="cuda")
     if dist is not None:
-        dist.all_reduce(t, op=dist.ReduceOp.MAX)
         dist.all_reduce(lt, op=dist.ReduceOp.SUM)
-    ms_max = float(t.item())
-    value = world * args.steps * bases_per_step / (ms_max * 1e-3)
 
-    # ---- e2e: host buffers through the public C ABI call (H2D + kernels + D2H + RLE) -----------
+    # ---- e2e: host buffers through the public C ABI (H2D + kernels + results written into pinned host memory) -----
     # host batches in memory from the library's own pinned allocator (cudaHostAlloc); measured on this box:
     # copies from it run at 51-55 GB/s, copies from torch's pin_memory() buffers at 11-27 GB/s
     pinned_keep = [api.PinnedBytes(len(b)) for b in batches]
     for pb, b in zip(pinned_keep, batches):
         pb.array[:] = b
     pinned_np = [pb.array for pb in pinned_keep]
-    n_thr = max(1, args.e2e_threads)
-    fbufs = [api.FindBuffers(nq, pinned=True) for _ in range(n_thr)]
-    n_rle_box = [0] * n_thr
+    pin_off = api.PinnedBytes(8 * (nq + 1))
+    offsets_pinned = pin_off.array.view(np.uint64)
+    offsets_pinned[:] = offsets
+    depth = max(1, args.e2e_depth)
+    n_thr = max(0, args.e2e_threads)
+    fbufs = [api.FindBuffers(nq, pinned=True) for _ in range(max(depth, n_thr))]
+    counts = np.zeros(max(args.steps, 1), dtype=np.int64)
 
-    def e2e_worker(t, first, count):
-        # every call copies its batch host->device, runs the kernels and copies the RLE records back
-        for s in range(first + t, first + count, n_thr):
-            _, n_rle_box[t] = api.find_csr(pinned_np[s % len(batches)], offsets, index, api.FindOpts(P, 0), fbufs[t])
+    def e2e_async(first, count, record):
+        """One host thread, `depth` batches in flight: submit, submit, ..., wait for the oldest, submit, ..."""
+        inflight = []
+        for s in range(first, first + count):
+            if len(inflight) == depth:
+                s0, job = inflight.pop(0)
+                n = job.wait()
+                if record:
+                    counts[s0 - first] = n
+            inflight.append((s, api.find_submit(pinned_np[s % len(batches)], offsets_pinned, index, api.FindOpts(P, 0),
+                                                fbufs[s % depth])))
+        for s0, job in inflight:
+            n = job.wait()
+            if record:
+                counts[s0 - first] = n
 
-    def run_threads(first, count):
-        ths = [threading.Thread(target=e2e_worker, args=(t, first, count)) for t in range(n_thr)]
+    def e2e_threads(first, count, record):
+        def worker(t):
+            for s in range(first + t, first + count, n_thr):
+                _, n = api.find_csr(pinned_np[s % len(batches)], offsets_pinned, index, api.FindOpts(P, 0), fbufs[t])
+                if record:
+                    counts[s - first] = n
+        ths = [threading.Thread(target=worker, args=(t,)) for t in range(n_thr)]
         for th in ths:
             th.start()
         for th in ths:
             th.join()
-        torch.cuda.synchronize()
 
+    run_e2e = e2e_threads if n_thr else e2e_async
     # warm-up with the same concurrency until every workspace the timed region needs exists at its final size
-    # (the library creates them lazily, one per concurrent call; measured: the first ~50 calls carry that cost)
-    # ... and one untimed pass of the same length: in some runs the first pass after start-up stays 10-25 % slower
-    # for its whole length (profiles/README.md: repeated regions in one process settle at 47 G bases/s from the second on)
-    run_threads(0, max(max(args.warmup, 16) * n_thr, args.steps))
+    run_e2e(0, max(args.warmup, 2 * max(depth, n_thr, 1)) + 8, False)
     barrier()
-    e2e_steps = args.steps
     w0 = time.perf_counter()
-    run_threads(args.warmup, e2e_steps)
+    run_e2e(args.warmup, args.steps, True)
+    gathered = None
+    if dist is not None:  # final gather of the per-step record counts of every rank (NCCL), inside the timed region
+        mine = torch.from_numpy(counts[:args.steps]).cuda()
+        gathered = [torch.empty_like(mine) for _ in range(world)]
+        dist.all_gather(gathered, mine)
+        torch.cuda.synchronize()
     e2e_s = time.perf_counter() - w0
-    n_rle = n_rle_box[0]
-    te = torch.tensor([e2e_s], dtype=torch.float64, device="cuda")
-    if dist is not None:
-        dist.all_reduce(te, op=dist.ReduceOp.MAX)
-    e2e_value = world * e2e_steps * bases_per_step / float(te.item())
+    n_rle = int(counts[0])
+    e2e_value = world * args.steps * bases_per_step / reduce_max(e2e_s)
+    total_records = int(sum(int(g.sum().item()) for g in gathered)) if gathered is not None else int(counts[:args.steps].sum())
+    clocks = sampler.stop() if sampler else None
 
-    # ---- roofline inputs: event counters of one batch (profiling build of K1, outside the timing) --
+    # ---- roofline inputs: event counters of one batch (profiling build of the kernel, outside the timing) --
     api.set_profile_counters(True)
     out_host = api.matches_csr(pinned_np[0], offsets, index, P)
     api.set_profile_counters(False)
     cnt = index.ms_counters()
-    L = cnt["bases_emitted"]
-    alg_bytes = (SECTOR * (cnt["emit_extend_attempts"] + cnt["emit_extend_split_sector"]) +
-                 SECTOR * (cnt["emit_contractions"] + cnt["emit_contraction_extra_words"]) + 2 * L)
+    L = max(cnt["bases_emitted"], 1)
+    alg_sectors = (cnt["emit_extend_attempts"] + cnt["emit_extend_split_sector"] + cnt["emit_contractions"] +
+                   cnt["emit_contraction_extra_words"])
+    alg_bytes = SECTOR * alg_sectors + 2 * L
     k1_ms = ksum["ms"] / max(kcalls, 1)
     achieved = alg_bytes / (k1_ms * 1e-3) / 1e9 if k1_ms > 0 else 0.0
-    peak, peak_src = measured_peaks()
-    roof = {"bound": "hbm", "kernel": "ms_kernel", "achieved": achieved, "peak": peak, "unit": "GB/s",
-            "frac": achieved / peak, "traffic": committed_traffic(), "peak_source": peak_src,
-            "algorithmic_bytes_per_launch": alg_bytes, "algorithmic_bytes_per_base": alg_bytes / max(L, 1),
-            "achieved_whole_step_overlapped": alg_bytes / ((ms_max / args.steps) * 1e-3) / 1e9,
-            "kernel_ms": {"pack": ksum["pack"] / max(kcalls, 1), "ms": k1_ms,
-                          "derand_translate": ksum["derand_translate"] / max(kcalls, 1),
-                          "how": "CUDA events around each kernel over %d serial instrumented steps on the launch "
-                                 "stream (the timed `value` region overlaps independent steps on %d streams)" % (kcalls, len(workers))},
-            "events_per_base": {"extend_attempts": cnt["emit_extend_attempts"] / max(L, 1),
-                                "contractions": cnt["emit_contractions"] / max(L, 1),
-                                "warmup_overhead": cnt["bases_processed"] / max(L, 1)},
-            "note": "the index is L2-resident in this config, so the HBM-peak fraction is not a ceiling; "
-                    "the measured random-sector rates below are the relevant denominators"}
+    hbm_peak, peak_src = measured_peaks()
+    roof = {"kernel": "ms_fused_kernel (K1 matching statistics + K2b derandomize/translate)",
+            "achieved": achieved, "unit": "GB/s", "traffic": committed_traffic(),
+            "algorithmic_bytes_per_launch": alg_bytes, "algorithmic_bytes_per_base": alg_bytes / L,
+            "algorithmic_bytes_how": "32 B x (rank probes + probes whose two ends fall in different sectors + contractions "
+                                     "+ contractions that had to scan), counted by the profiling build of the kernel for "
+                                     "the tile's own positions only (repair-pass work included, chunk warm-up and look-ahead "
+                                     "excluded), + 2 B per base (1 in, 1 out)",
+            "reference_algorithm_bytes_per_base": 51.0,
+            "reference_algorithm_note": "SURVEY 8d figure for this workload (one base per probe, one-by-one contraction: "
+                                        "1.26 probes + 0.26 contractions per base); the kernel does the same job with fewer "
+                                        "probes (two bases per probe, contraction jumps), which LOWERS its own figure",
+            "achieved_reference_algorithm_GBps": 51.0 * L / (k1_ms * 1e-3) / 1e9 if k1_ms > 0 else 0.0,
+            "kernel_ms": {"pack": ksum["pack"] / max(kcalls, 1), "ms_fused": k1_ms,
+                          "how": "CUDA events around each kernel over %d serial steps on the launch stream, same kernels "
+                                 "and geometry as the timed region" % kcalls},
+            "step_ms_single_stream": ms_single / args.steps,
+            "events_per_base": {"rank_probes": cnt["emit_extend_attempts"] / L,
+                                "contractions": cnt["emit_contractions"] / L,
+                                "processed_over_emitted": cnt["bases_processed"] / L}}
+    l2_ind = None
     if rank == 0:
         try:
             l2_dep = api.measure_random_sector_rate(8 << 20, True, dev)
             l2_ind = api.measure_random_sector_rate(8 << 20, False, dev)
             hbm_ind = api.measure_random_sector_rate(4 << 30, False, dev)
-            sectors_per_s = (cnt["emit_extend_attempts"] + cnt["emit_extend_split_sector"] + cnt["emit_contractions"] +
-                             cnt["emit_contraction_extra_words"]) / (k1_ms * 1e-3)
             roof["random_sector"] = {"l2_dependent_chain_sectors_per_s": l2_dep, "l2_independent_sectors_per_s": l2_ind,
-                                     "hbm_independent_sectors_per_s": hbm_ind, "kernel_sectors_per_s": sectors_per_s,
-                                     "frac_of_l2_independent": sectors_per_s / l2_ind if l2_ind else None,
-                                     "frac_of_l2_dependent_chain": sectors_per_s / l2_dep if l2_dep else None}
+                                     "hbm_independent_sectors_per_s": hbm_ind,
+                                     "kernel_algorithmic_sectors_per_s": alg_sectors / (k1_ms * 1e-3) if k1_ms > 0 else 0.0}
         except Exception as ex:  # instrumentation only
             roof["random_sector"] = {"error": str(ex)}
+    if l2_ind and index.device_bytes < 100e6:
+        roof.update({"bound": "l2", "peak": l2_ind * SECTOR / 1e9,
+                     "peak_source": "measured in this run: independent random 32-byte-sector loads over an 8 MB (L2-resident) "
+                                    "buffer, %.1f G sectors/s x 32 B (kbo_measure_random_sector_rate); the index (%d MB) is "
+                                    "L2 resident" % (l2_ind / 1e9, index.device_bytes >> 20),
+                     "hbm_copy_peak": hbm_peak, "hbm_copy_peak_source": peak_src, "frac_of_hbm_copy_peak": achieved / hbm_peak})
+    else:
+        roof.update({"bound": "hbm", "peak": hbm_peak, "peak_source": peak_src})
+    roof["frac"] = achieved / roof["peak"]
 
     # ---- cpu baseline + a parity spot check against it (rank 0, N = 1) --------------------------
     cpu = None
@@ -459,29 +485,29 @@ def run_ours(args, rank, local_rank, world):
 
     if rank == 0:
         cfg = config_dict(args)
-        cfg.update({"chunk_len": args.chunk_len or "auto (per call, from the batch size and the number of caller streams "
-                                                  "seen in the last 8 stream-ordered calls)",
-                    "index_device_bytes": index.device_bytes,
-                    "n_sets": index.n_sets, "index_build_s_host": round(index_build_s, 2), "rle_records_per_step": n_rle,
-                    "streams": len(workers),
-                    "parallelism": "replicated index, %d rank(s) x own batches" % world})
+        detail = {"index_device_bytes": index.device_bytes, "n_sets": index.n_sets,
+                              "index_build_s": round(index_build_s, 3), "rle_records_per_step": n_rle,
+                              "streams": len(workers),
+                              "single_stream": {"ms_per_step": ms_single / args.steps,
+                                                "value": world * args.steps * bases_per_step / (ms_single * 1e-3)},
+                              "chunk_len": args.chunk_len or "auto (about 64 positions per lane, tiles a multiple of the SM count)",
+                              "parallelism": "replicated index, %d rank(s) x own batches" % world}
         if numa_note:
-            cfg["host_affinity"] = numa_note
-        if tuned is not None:
-            tuned["note"] = ("same timed region with kbo_set_chunk_len(%d): less chunk warm-up work per base; suits "
-                             "overlapped launches, not a lone one (K1 alone is slower at this chunk length)" % tuned["chunk_len"])
-            cfg["overlap_tuned"] = tuned
+            detail["host_affinity"] = numa_note
         line = {"metric": "query bases/s (kbo find, whole box)", "value": value, "unit": "query bases/s",
                 "n_gpus": world, "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms_max / args.steps,
                 "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "u8", "data": "synthetic",
-                "config": cfg, "clocks": clocks,
+                "config": cfg, "impl_detail": detail, "clocks": clocks,
                 "e2e": {"value": e2e_value, "unit": "query bases/s",
                         "h2d_bytes_per_step": bases_per_step + 8 * (nq + 1),
-                        "d2h_bytes_per_step": 8 * (nq + 1) + 56 * n_rle,
-                        "api": "kbo_find_batch: pinned host queries in, RLE records + per-query offsets out "
-                               "(matches and run lengths computed on the device; one stream per call when several host threads call "
-                               "concurrently, else up to 4 pipelined sub-batches); "
-                               "%d steps issued by %d host threads" % (e2e_steps, n_thr)},
+                        "d2h_bytes_per_step": 8 * (nq + 1) + 56 * n_rle + 8,
+                        "records_total": total_records,
+                        "api": ("kbo_find_batch_submit / kbo_job_wait: pinned host queries in, RLE records + per-query "
+                                "offsets written by the device into pinned host buffers; %d steps, one host thread, %d "
+                                "batches in flight" % (args.steps, depth)) if not n_thr else
+                               ("kbo_find_batch (synchronous) from %d host threads; %d steps" % (n_thr, args.steps)),
+                        "gather": "NCCL all_gather of every rank's per-step record counts at the end, inside the timed "
+                                  "region; records stay in the ranks' host buffers" if dist is not None else "single rank"},
                 "gpu_launches": int(lt.item()), "roofline": roof}
         if cpu is not None:
             line["cpu_baseline"] = cpu

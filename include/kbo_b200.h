@@ -183,6 +183,32 @@ int kbo_find_batch_device(const kbo_index* ix, const uint8_t* d_concat, const ui
                           const uint64_t* host_offsets, uint64_t n_queries, double max_error_prob,
                           uint64_t max_gap_len, kbo_rle* d_rle_out, uint64_t rle_cap, uint64_t* d_rle_offsets,
                           void* stream);
+/* ---- multi-GPU (SURVEY 8b "ctx_create(n_gpus) + batch calls that shard internally", 8e) ------------------------
+ * One process drives several GPUs: a context owns one worker thread per device, an index set holds one replica of
+ * an index per device.  The batch calls cut the CSR batch into contiguous query ranges of equal base counts (one per
+ * device), run the hot path of every range on its device, and gather the results into the caller's buffers: alignment
+ * characters at their final positions, RLE records in query order exactly as the single-device call returns them
+ * (every device writes its records straight into the caller's buffer once the record counts of the devices before it
+ * are known).  `devices` may repeat an ordinal (several workers on one GPU).  Pageable output buffers are page-locked
+ * for the duration of the call. */
+typedef struct kbo_ctx kbo_ctx;
+typedef struct kbo_index_set kbo_index_set;
+int kbo_ctx_create(int n_gpus /* <= 0: all */, const int* devices /* NULL: 0 .. n_gpus-1 */, kbo_ctx** out);
+void kbo_ctx_free(kbo_ctx* ctx);
+int kbo_ctx_n_gpus(const kbo_ctx* ctx);
+/* kbo::build on every device of the context (index::build_sbwt_from_vecs, index.rs:56-99) */
+int kbo_index_set_build(kbo_ctx* ctx, const uint8_t* const* seqs, const uint64_t* lens, uint64_t n_seqs,
+                        const kbo_build_opts* opts, kbo_index_set** out);
+void kbo_index_set_free(kbo_index_set* set);
+const kbo_index* kbo_index_set_get(const kbo_index_set* set, int i);
+/* kbo::matches / kbo::find over a CSR batch on all devices of the set; same arguments and results as
+ * kbo_matches_batch / kbo_find_batch. */
+int kbo_matches_batch_multi(const kbo_index_set* set, const uint8_t* concat, const uint64_t* offsets, uint64_t n_queries,
+                            double max_error_prob, uint8_t* chars_out);
+int kbo_find_batch_multi(const kbo_index_set* set, const uint8_t* concat, const uint64_t* offsets, uint64_t n_queries,
+                         double max_error_prob, uint64_t max_gap_len, kbo_rle* rle_out, uint64_t rle_cap,
+                         uint64_t* rle_offsets);
+
 /* kbo::map without refinement (lib.rs:726-738,756-760 with fill_gaps = call_variants = false):
  * `format` != 0 applies relative_to_ref, else the raw translation characters are returned. */
 int kbo_map_unrefined(const kbo_index* query_index, const uint8_t* ref_seq, uint64_t len, double max_error_prob,
@@ -231,7 +257,10 @@ int kbo_set_prefix_table(int enabled);
 int kbo_set_rank2(int enabled);
 /* enabled == 0: streams created afterwards do not mark the index arrays as persisting in L2 (comparison runs). */
 int kbo_set_l2_persist(int enabled);
-/* Experiment switches (bit 1: run K2 where the bit-parallel K2b would be picked).  Results never depend on them. */
+/* Experiment switches.  bit 1 (2): run K2 where the bit-parallel K2b would be picked; bit 4 (16): run matching
+ * statistics + derandomize + translate as ONE fused kernel (fused.cuh: MS bytes only in shared memory, two bases per
+ * rank probe) instead of K1 followed by K2b; bit 2 (4): the fused kernel probes one base at a time.  Results never
+ * depend on them. */
 int kbo_set_ms_flags(uint32_t flags);
 /* Number of kernel launches issued by this library since load (for bench.py's gpu_launches). */
 uint64_t kbo_kernel_launch_count(void);

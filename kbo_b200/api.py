@@ -38,7 +38,8 @@ EXPORTED_SYMBOLS = [
     "kbo_index_access_kmer", "kbo_index_search", "kbo_query_sbwt", "kbo_query_sbwt_batch_compact",
     "kbo_log_rm_max_cdf", "kbo_random_match_threshold", "kbo_derandomize_ms_vec", "kbo_translate_ms_vec",
     "kbo_run_lengths_gapped", "kbo_relative_to_ref", "kbo_matches", "kbo_matches_batch", "kbo_matches_batch_device",
-    "kbo_find_batch", "kbo_find_batch_submit", "kbo_job_wait", "kbo_find_batch_device", "kbo_map_unrefined", "kbo_call", "kbo_map", "kbo_set_profile_counters", "kbo_get_ms_counters", "kbo_set_chunk_len", "kbo_set_l2_persist", "kbo_set_prefix_table", "kbo_set_rank2", "kbo_set_host_builder", "kbo_set_pipeline_parts", "kbo_set_device_parts", "kbo_set_ms_flags",
+    "kbo_find_batch", "kbo_find_batch_submit", "kbo_job_wait", "kbo_find_batch_device", "kbo_ctx_create", "kbo_ctx_free", "kbo_ctx_n_gpus", "kbo_index_set_build", "kbo_index_set_free", "kbo_index_set_get",
+    "kbo_matches_batch_multi", "kbo_find_batch_multi", "kbo_map_unrefined", "kbo_call", "kbo_map", "kbo_set_profile_counters", "kbo_get_ms_counters", "kbo_set_chunk_len", "kbo_set_l2_persist", "kbo_set_prefix_table", "kbo_set_rank2", "kbo_set_host_builder", "kbo_set_pipeline_parts", "kbo_set_device_parts", "kbo_set_ms_flags",
     "kbo_kernel_launch_count", "kbo_last_kernel_ms", "kbo_set_kernel_timing", "kbo_collect_kernel_times",
     "kbo_measure_random_sector_rate",
 ]
@@ -120,6 +121,19 @@ def load_library():
     L.kbo_job_wait.argtypes = [C.c_void_p, u64p]
     L.kbo_find_batch_device.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, u64p, C.c_uint64, C.c_double, C.c_uint64,
                                         C.c_void_p, C.c_uint64, C.c_void_p, C.c_void_p]
+    L.kbo_ctx_create.argtypes = [C.c_int, C.POINTER(C.c_int), C.POINTER(C.c_void_p)]
+    L.kbo_ctx_free.argtypes = [C.c_void_p]
+    L.kbo_ctx_free.restype = None
+    L.kbo_ctx_n_gpus.argtypes = [C.c_void_p]
+    L.kbo_index_set_build.argtypes = [C.c_void_p, C.POINTER(u8p), u64p, C.c_uint64, C.POINTER(BuildOptsC),
+                                      C.POINTER(C.c_void_p)]
+    L.kbo_index_set_free.argtypes = [C.c_void_p]
+    L.kbo_index_set_free.restype = None
+    L.kbo_index_set_get.argtypes = [C.c_void_p, C.c_int]
+    L.kbo_index_set_get.restype = C.c_void_p
+    L.kbo_matches_batch_multi.argtypes = [C.c_void_p, u8p, u64p, C.c_uint64, C.c_double, u8p]
+    L.kbo_find_batch_multi.argtypes = [C.c_void_p, u8p, u64p, C.c_uint64, C.c_double, C.c_uint64, C.POINTER(RleC),
+                                       C.c_uint64, u64p]
     L.kbo_call.argtypes = [C.c_void_p, u8p, C.c_uint64, C.c_double, C.POINTER(BuildOptsC), u64p, u32p, u32p, u8p, u8p,
                            C.c_uint64, C.c_uint64, u64p]
     L.kbo_map.argtypes = [C.c_void_p, u8p, C.c_uint64, C.c_double, C.c_int, C.c_int, C.c_int, C.POINTER(BuildOptsC),
@@ -509,6 +523,85 @@ def find_csr(concat, offsets, index, find_opts=None, buffers=None):
                                            _p(buf.rle_offsets, C.c_uint64))
     _check(rc)
     return buf, int(buf.rle_offsets[nq])
+
+
+# ------------------------------------------------------------------------------- multi-GPU ---
+class Context:
+    """kbo_ctx: several GPUs driven by one process (one worker thread per device)."""
+
+    def __init__(self, n_gpus=0, devices=None):
+        h = C.c_void_p()
+        devs = (C.c_int * len(devices))(*devices) if devices else None
+        _check(load_library().kbo_ctx_create(len(devices) if devices else n_gpus, devs, C.byref(h)))
+        self._h = h
+        self.n_gpus = load_library().kbo_ctx_n_gpus(h)
+
+    def close(self):
+        if self._h:
+            load_library().kbo_ctx_free(self._h)
+            self._h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def build(self, seq_data, build_opts=None):
+        """kbo::build on every device of the context -> IndexSet."""
+        o = build_opts or BuildOpts()
+        seqs = [_u8(s) for s in seq_data]
+        ptrs = (u8p * max(len(seqs), 1))(*[_p(s, C.c_uint8) for s in seqs])
+        lens = np.array([len(s) for s in seqs], dtype=np.uint64)
+        co = _build_opts_c(o)
+        h = C.c_void_p()
+        _check(load_library().kbo_index_set_build(self._h, ptrs, _p(lens, C.c_uint64), len(seqs), C.byref(co), C.byref(h)))
+        return IndexSet(h, self)
+
+
+class IndexSet:
+    """kbo_index_set: one replica of an index per device of a Context."""
+
+    def __init__(self, handle, ctx):
+        self._h, self.ctx = handle, ctx
+        first = load_library().kbo_index_set_get(handle, 0)
+        self.k = load_library().kbo_index_k(first)
+        self.n_sets = load_library().kbo_index_n_sets(first)
+        self.n_kmers = load_library().kbo_index_n_kmers(first)
+
+    def close(self):
+        if self._h:
+            load_library().kbo_index_set_free(self._h)
+            self._h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def matches_csr(self, concat, offsets, max_error_prob=0.0000001, out=None):
+        if out is None:
+            out = np.zeros(max(len(concat), 1), dtype=np.uint8)
+        _check(load_library().kbo_matches_batch_multi(self._h, _p(concat, C.c_uint8), _p(offsets, C.c_uint64),
+                                                      len(offsets) - 1, max_error_prob, _p(out, C.c_uint8)))
+        return out
+
+    def find_csr(self, concat, offsets, find_opts=None, buffers=None):
+        """Returns (FindBuffers, n_rle) like find_csr."""
+        o = find_opts or FindOpts()
+        nq = len(offsets) - 1
+        buf = buffers or FindBuffers(nq, pinned=True)
+        rc = load_library().kbo_find_batch_multi(self._h, _p(concat, C.c_uint8), _p(offsets, C.c_uint64), nq,
+                                                 o.max_error_prob, o.max_gap_len, buf.rle, buf.cap,
+                                                 _p(buf.rle_offsets, C.c_uint64))
+        if rc == 11:
+            buf = FindBuffers(nq, cap=int(buf.rle_offsets[nq]) + 1024, pinned=True)
+            rc = load_library().kbo_find_batch_multi(self._h, _p(concat, C.c_uint8), _p(offsets, C.c_uint64), nq,
+                                                     o.max_error_prob, o.max_gap_len, buf.rle, buf.cap,
+                                                     _p(buf.rle_offsets, C.c_uint64))
+        _check(rc)
+        return buf, int(buf.rle_offsets[nq])
 
 
 def _build_opts_c(o):

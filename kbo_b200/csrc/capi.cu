@@ -7,6 +7,9 @@
 // point needs a CUDA device and fails with KBO_ERR_CUDA otherwise.
 // ===========================================================================
 #include <atomic>
+#include <condition_variable>
+#include <functional>
+#include <thread>
 #include <cmath>
 #include <cstring>
 #include <mutex>
@@ -718,7 +721,7 @@ static int run_derand_translate(kbo_index* ix, Workspace* ws, const QueryView& q
     return KBO_OK;
 }
 
-// K4, first two launches: word counts -> START/END marks (the scans are inside).  Returns the parameter block for
+// K4 up to the START / END marks: one launch for max_gap_len == 0, two for the gapped form (the scans are inside).  Returns the parameter block for
 // run_rle_finish BY VALUE (workspaces bound to caller streams can be shared between host threads).
 // d_offsets are the batch's own CSR offsets (offsets[0] may be non-zero).
 static int run_rle_counts(Workspace* ws, const QueryView& qv, const Geometry& g, const uint64_t* d_offsets, uint64_t nq,
@@ -754,10 +757,15 @@ static int run_rle_counts(Workspace* ws, const QueryView& qv, const Geometry& g,
     p.cse = ws->rle_cse.as<uint64_t>();
     p.cse_blk = p.cse + nw;
     p.tickets = ws->rle_tickets.as<unsigned int>();
-    rle_word_counts_kernel<<<(unsigned)nb, RLE_BLOCK, 0, st>>>(p);
-    LAUNCHED();
-    rle_mark_kernel<<<(unsigned)nb, RLE_BLOCK, 0, st>>>(p);
-    LAUNCHED();
+    if (p.window == 1) {  // max_gap_len == 0: counts and START / END marks in one launch
+        rle_word_counts_kernel<true><<<(unsigned)nb, RLE_BLOCK, 0, st>>>(p);
+        LAUNCHED();
+    } else {
+        rle_word_counts_kernel<false><<<(unsigned)nb, RLE_BLOCK, 0, st>>>(p);
+        LAUNCHED();
+        rle_mark_kernel<<<(unsigned)nb, RLE_BLOCK, 0, st>>>(p);
+        LAUNCHED();
+    }
     CUDA_TRY(cudaGetLastError());
     *out_params = p;
     return KBO_OK;
@@ -852,7 +860,10 @@ static int run_fused(kbo_index* ix, Workspace* ws, const QueryView& qv, const Ge
                      uint64_t off0, bool want_masks, bool* done) {
     *done = false;
     const uint32_t flags = g_ms_flags.load();
-    if (!k2b_supported(ix->host.k, thr) || (flags & 2u) || (flags & 8u)) return KBO_OK;  // bit 1: K2, bit 3: unfused
+    // bit 4 selects the fused kernel.  It is NOT the default: measured on B200 (profiles/README.md, round 2) it takes
+    // 225-300 us per 10^7-base batch where K1 + K2b take 112 + 18 us -- the per-iteration latency of a dependent chain
+    // (~1 us at this occupancy) is the same in both, and the two-pass scheme does not save enough iterations.
+    if (!k2b_supported(ix->host.k, thr) || (flags & 2u) || !(flags & 16u)) return KBO_OK;
     FusedGeom fg;
     if (!fused_geometry(g.Lp, ix->host.k, !want_masks, device_sm_count(ix->device), g_chunk_len.load(), &fg)) return KBO_OK;
     cudaStream_t st = ws->stream;
@@ -1540,6 +1551,7 @@ struct kbo_job {
     uint64_t rle_cap = 0;
     uint64_t* rle_offsets = nullptr;
     bool direct = false;
+    bool deferred = false;           // multi-GPU: the last K4 kernel waits for the record base of this device's slice
     uint64_t staged_cap = 0;         // staged path: records the device buffer of wss[0] holds
     int rc = KBO_OK;
     std::string err;
@@ -1562,7 +1574,7 @@ static void job_release(kbo_job* job) {
 
 static int find_submit(kbo_index* ix, const uint8_t* concat, const uint64_t* offsets, uint64_t n_queries,
                        double max_error_prob, uint64_t max_gap_len, kbo_rle* rle_out, uint64_t rle_cap,
-                       uint64_t* rle_offsets, uint64_t want_parts, kbo_job** out) {
+                       uint64_t* rle_offsets, uint64_t want_parts, kbo_job** out, bool defer_finish = false) {
     *out = nullptr;
     if (!rle_offsets || !concat) return fail(KBO_ERR_BAD_ARGUMENT, "null argument");
     uint64_t total = 0;
@@ -1586,6 +1598,8 @@ static int find_submit(kbo_index* ix, const uint8_t* concat, const uint64_t* off
     RleRecord* dv_out = reinterpret_cast<RleRecord*>(device_visible(rle_out));
     uint64_t* dv_off = reinterpret_cast<uint64_t*>(device_visible(rle_offsets));
     job->direct = dv_off && (dv_out || rle_cap == 0);
+    job->deferred = defer_finish;
+    if (defer_finish && !job->direct) { delete job; return fail(KBO_ERR_BAD_ARGUMENT, "deferred jobs need device-visible outputs"); }
     auto body = [&]() -> int {
         for (size_t s = 0; s < np; ++s) {
             int r = acquire_ws(ix, &job->wss[s]);
@@ -1596,7 +1610,7 @@ static int find_submit(kbo_index* ix, const uint8_t* concat, const uint64_t* off
         Workspace* ws0 = job->wss[0];
         // running record totals of the sub-batches (device) and the final count (page-locked host), in ws0
         CUDA_TRY(ws0->counters2.ensure((np + 1) * 8, ws0->stream));
-        CUDA_TRY(ws0->h_count.ensure(8));
+        CUDA_TRY(ws0->h_count.ensure(8 * (np + 2)));  // [0] final count; [1] deferred base; [2..] deferred part totals
         uint64_t* d_totals = ws0->counters2.as<uint64_t>();
         CUDA_TRY(cudaMemsetAsync(d_totals, 0, 8, ws0->stream));
         uint64_t* st_off = nullptr;     // staged path: device copies of the outputs
@@ -1626,6 +1640,11 @@ static int find_submit(kbo_index* ix, const uint8_t* concat, const uint64_t* off
             if (r) return r;
             r = run_rle_counts(ws, qv, g, ws->offsets.as<uint64_t>(), nq, gap, &job->rle[s]);
             if (r) return r;
+            if (defer_finish) {  // only this part's record total goes to the host for now
+                CUDA_TRY(cudaMemcpyAsync(ws0->h_count.as<uint64_t>() + 2 + s, job->rle[s].cse_blk + job->rle[s].n_blocks, 8,
+                                         cudaMemcpyDeviceToHost, st));
+                continue;
+            }
             if (s > 0) CUDA_TRY(cudaStreamWaitEvent(st, job->wss[s - 1]->ev1, 0));  // its total is this part's base
             else if (np > 1) { /* d_totals[0] was zeroed on this very stream */ }
             r = run_rle_finish(st, job->rle[s], (job->direct ? dv_off : st_off) + q0, job->direct ? dv_out : st_out,
@@ -1700,6 +1719,38 @@ static int find_wait(kbo_job* job, uint64_t* n_rle_out) {
     return rc;
 }
 
+// ---- deferred finish (multi-GPU gather): records of this job are placed after `base` records of other devices -----
+static int find_deferred_count(kbo_job* job, uint64_t* count) {
+    DeviceGuard dg(job->ix->device);
+    uint64_t c = 0;
+    for (size_t s = 0; s < job->wss.size(); ++s) {
+        CUDA_TRY(cudaStreamSynchronize(job->wss[s]->stream));
+        c += (uint32_t)job->wss[0]->h_count.as<uint64_t>()[2 + s];  // low half: STARTs = records of the part
+    }
+    *count = c;
+    return KBO_OK;
+}
+static int find_deferred_finish(kbo_job* job, uint64_t base, bool first_slice) {
+    DeviceGuard dg(job->ix->device);
+    const size_t np = job->wss.size();
+    Workspace* ws0 = job->wss[0];
+    uint64_t* d_totals = ws0->counters2.as<uint64_t>();
+    RleRecord* dv_out = reinterpret_cast<RleRecord*>(device_visible(job->rle_out));
+    uint64_t* dv_off = reinterpret_cast<uint64_t*>(device_visible(job->rle_offsets));
+    ws0->h_count.as<uint64_t>()[1] = base;
+    CUDA_TRY(cudaMemcpyAsync(d_totals, ws0->h_count.as<uint64_t>() + 1, 8, cudaMemcpyHostToDevice, ws0->stream));
+    for (size_t s = 0; s < np; ++s) {
+        cudaStream_t st = job->wss[s]->stream;
+        if (s > 0) CUDA_TRY(cudaStreamWaitEvent(st, job->wss[s - 1]->ev1, 0));
+        int r = run_rle_finish(st, job->rle[s], dv_off + job->cut[s], dv_out, job->rle_cap, d_totals + s, d_totals + s + 1,
+                               first_slice && s == 0);
+        if (r) return r;
+        CUDA_TRY(cudaEventRecord(job->wss[s]->ev1, st));
+        if (s + 1 == np) CUDA_TRY(cudaMemcpyAsync(ws0->h_count.p, d_totals + np, 8, cudaMemcpyDeviceToHost, st));
+    }
+    return KBO_OK;
+}
+
 int kbo_find_batch_submit(const kbo_index* cix, const uint8_t* concat, const uint64_t* offsets, uint64_t n_queries,
                           double max_error_prob, uint64_t max_gap_len, kbo_rle* rle_out, uint64_t rle_cap,
                           uint64_t* rle_offsets, kbo_job** job) {
@@ -1734,6 +1785,202 @@ int kbo_find_batch(const kbo_index* cix, const uint8_t* concat, const uint64_t* 
         rc = find_wait(job, nullptr);
     }
     return rc;
+}
+
+// ---- multi-GPU: one process, one worker thread and one index replica per device ----------------
+// The path shards by independent units: the query batch is cut into contiguous ranges of equal base counts, one per
+// device; every device runs the hot path on its range; the results are gathered into the caller's buffers -- alignment
+// characters at their final positions straight away, RLE records after the record counts of all devices are known
+// (one extra synchronisation per call), written by every device directly into the caller's page-locked buffer.
+// No collective is needed: the gather is the devices' own writes over PCIe.
+struct kbo_ctx {
+    std::vector<int> devices;
+    std::vector<std::thread> workers;
+    std::mutex mu;
+    std::condition_variable cv_work, cv_done;
+    std::vector<std::function<int()>> tasks;  // one slot per worker
+    std::vector<int> results;
+    uint64_t generation = 0;
+    int pending = 0;
+    bool stop = false;
+    std::mutex call_mu;  // one multi-device call at a time per context
+
+    void worker(size_t w) {
+        cudaSetDevice(devices[w]);
+        uint64_t seen = 0;
+        for (;;) {
+            std::function<int()> fn;
+            {
+                std::unique_lock<std::mutex> lk(mu);
+                cv_work.wait(lk, [&] { return stop || generation != seen; });
+                if (stop) return;
+                seen = generation;
+                fn = tasks[w];
+            }
+            const int rc = fn ? fn() : KBO_OK;
+            {
+                std::lock_guard<std::mutex> lk(mu);
+                results[w] = rc;
+                if (--pending == 0) cv_done.notify_all();
+            }
+        }
+    }
+    // runs fn(w) on every worker, returns the first non-zero status
+    int run_all(const std::function<int(size_t)>& fn, std::string* err) {
+        {
+            std::lock_guard<std::mutex> lk(mu);
+            for (size_t w = 0; w < workers.size(); ++w)
+                tasks[w] = [&fn, w, err]() {
+                    const int rc = fn(w);
+                    if (rc && err) { static std::mutex emu; std::lock_guard<std::mutex> g(emu); if (err->empty()) *err = g_err; }
+                    return rc;
+                };
+            pending = (int)workers.size();
+            ++generation;
+        }
+        cv_work.notify_all();
+        std::unique_lock<std::mutex> lk(mu);
+        cv_done.wait(lk, [&] { return pending == 0; });
+        for (int rc : results) if (rc) return rc;
+        return KBO_OK;
+    }
+};
+
+struct kbo_index_set {
+    kbo_ctx* ctx = nullptr;
+    std::vector<kbo_index*> replicas;
+};
+
+int kbo_ctx_create(int n_gpus, const int* devices, kbo_ctx** out) {
+    if (!out) return fail(KBO_ERR_BAD_ARGUMENT, "out is null");
+    *out = nullptr;
+    int ndev = 0;
+    if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev == 0)
+        return fail(KBO_ERR_CUDA, "no CUDA device available (this library has no CPU fallback)");
+    if (n_gpus <= 0) n_gpus = ndev;
+    kbo_ctx* ctx = new kbo_ctx();
+    for (int i = 0; i < n_gpus; ++i) {
+        const int d = devices ? devices[i] : i;
+        if (d < 0 || d >= ndev) { delete ctx; return fail(KBO_ERR_BAD_ARGUMENT, "device ordinal out of range"); }
+        ctx->devices.push_back(d);
+    }
+    ctx->tasks.resize(ctx->devices.size());
+    ctx->results.assign(ctx->devices.size(), 0);
+    for (size_t w = 0; w < ctx->devices.size(); ++w) ctx->workers.emplace_back([ctx, w] { ctx->worker(w); });
+    *out = ctx;
+    return KBO_OK;
+}
+
+void kbo_ctx_free(kbo_ctx* ctx) {
+    if (!ctx) return;
+    {
+        std::lock_guard<std::mutex> lk(ctx->mu);
+        ctx->stop = true;
+    }
+    ctx->cv_work.notify_all();
+    for (std::thread& t : ctx->workers) t.join();
+    delete ctx;
+}
+
+int kbo_ctx_n_gpus(const kbo_ctx* ctx) { return ctx ? (int)ctx->devices.size() : 0; }
+
+int kbo_index_set_build(kbo_ctx* ctx, const uint8_t* const* seqs, const uint64_t* lens, uint64_t n_seqs,
+                        const kbo_build_opts* opts, kbo_index_set** out) {
+    if (!ctx || !out) return fail(KBO_ERR_BAD_ARGUMENT, "null argument");
+    *out = nullptr;
+    kbo_index_set* set = new kbo_index_set();
+    set->ctx = ctx;
+    set->replicas.assign(ctx->devices.size(), nullptr);
+    std::string err;
+    std::lock_guard<std::mutex> call(ctx->call_mu);
+    const int rc = ctx->run_all([&](size_t w) {  // construction is deterministic: every device builds its own replica
+        return kbo_index_build(seqs, lens, n_seqs, opts, ctx->devices[w], &set->replicas[w]);
+    }, &err);
+    if (rc) {
+        for (kbo_index* ix : set->replicas) kbo_index_free(ix);
+        delete set;
+        return fail(rc, err);
+    }
+    *out = set;
+    return KBO_OK;
+}
+
+void kbo_index_set_free(kbo_index_set* set) {
+    if (!set) return;
+    for (kbo_index* ix : set->replicas) kbo_index_free(ix);
+    delete set;
+}
+
+const kbo_index* kbo_index_set_get(const kbo_index_set* set, int i) {
+    return (set && i >= 0 && (size_t)i < set->replicas.size()) ? set->replicas[(size_t)i] : nullptr;
+}
+
+int kbo_matches_batch_multi(const kbo_index_set* set, const uint8_t* concat, const uint64_t* offsets, uint64_t n_queries,
+                            double max_error_prob, uint8_t* chars_out) {
+    if (!set || !concat || !chars_out) return fail(KBO_ERR_BAD_ARGUMENT, "null argument");
+    uint64_t total = 0;
+    uint32_t thr = 0;
+    int rc = matches_prologue(set->replicas[0], offsets, n_queries, max_error_prob, &total, &thr);
+    if (rc) return rc;
+    kbo_ctx* ctx = set->ctx;
+    const std::vector<uint64_t> cut = split_queries(offsets, n_queries, ctx->devices.size());
+    std::string err;
+    std::lock_guard<std::mutex> call(ctx->call_mu);
+    rc = ctx->run_all([&](size_t w) {  // outputs are indexed like concat: every device writes its own range in place
+        if (w + 1 >= cut.size()) return (int)KBO_OK;
+        return kbo_matches_batch(set->replicas[w], concat, offsets + cut[w], cut[w + 1] - cut[w], max_error_prob, chars_out);
+    }, &err);
+    return rc ? fail(rc, err) : KBO_OK;
+}
+
+int kbo_find_batch_multi(const kbo_index_set* set, const uint8_t* concat, const uint64_t* offsets, uint64_t n_queries,
+                         double max_error_prob, uint64_t max_gap_len, kbo_rle* rle_out, uint64_t rle_cap,
+                         uint64_t* rle_offsets) {
+    if (!set || !concat || !rle_offsets) return fail(KBO_ERR_BAD_ARGUMENT, "null argument");
+    uint64_t total = 0;
+    uint32_t thr = 0;
+    int rc = matches_prologue(set->replicas[0], offsets, n_queries, max_error_prob, &total, &thr);
+    if (rc) return rc;
+    kbo_ctx* ctx = set->ctx;
+    // the devices write into the caller's buffers: page-lock them for the call if they are pageable
+    bool reg_out = false, reg_off = false;
+    if (rle_out && rle_cap && !device_visible(rle_out))
+        reg_out = cudaHostRegister(rle_out, rle_cap * sizeof(kbo_rle), cudaHostRegisterPortable) == cudaSuccess;
+    if (!device_visible(rle_offsets))
+        reg_off = cudaHostRegister(rle_offsets, (n_queries + 1) * 8, cudaHostRegisterPortable) == cudaSuccess;
+    cudaGetLastError();
+    const std::vector<uint64_t> cut = split_queries(offsets, n_queries, ctx->devices.size());
+    const size_t ns = cut.size() - 1;
+    std::vector<kbo_job*> jobs(ns, nullptr);
+    std::vector<uint64_t> counts(ns, 0), bases(ns + 1, 0);
+    std::string err;
+    {
+        std::lock_guard<std::mutex> call(ctx->call_mu);
+        rc = ctx->run_all([&](size_t w) {  // phase 1: everything up to the record counts
+            if (w >= ns) return (int)KBO_OK;
+            int r = find_submit(set->replicas[w], concat, offsets + cut[w], cut[w + 1] - cut[w], max_error_prob, max_gap_len,
+                                rle_out, rle_cap, rle_offsets + cut[w], 1, &jobs[w], true);
+            if (r) return r;
+            return find_deferred_count(jobs[w], &counts[w]);
+        }, &err);
+        for (size_t w = 0; w < ns; ++w) bases[w + 1] = bases[w] + counts[w];
+        const int rc1 = rc;
+        const int rc2 = ctx->run_all([&](size_t w) {  // phase 2: records and offsets at their final places
+            if (w >= ns || !jobs[w]) return (int)KBO_OK;
+            int r = rc1 ? rc1 : find_deferred_finish(jobs[w], bases[w], w == 0);
+            uint64_t n = 0;
+            const int rw = find_wait(jobs[w], &n);  // (always: it releases the job)
+            jobs[w] = nullptr;
+            if (r) return r;
+            return rw == KBO_ERR_BUFFER_TOO_SMALL ? (int)KBO_OK : rw;  // capacity is judged on the grand total below
+        }, &err);
+        if (!rc) rc = rc2;
+    }
+    if (reg_out) cudaHostUnregister(rle_out);
+    if (reg_off) cudaHostUnregister(rle_offsets);
+    if (rc) return fail(rc, err);
+    if (bases[ns] > rle_cap) { rle_offsets[n_queries] = bases[ns]; return fail(KBO_ERR_BUFFER_TOO_SMALL, "rle capacity too small"); }
+    return KBO_OK;
 }
 
 int kbo_find_batch_device(const kbo_index* cix, const uint8_t* d_concat, const uint64_t* d_offsets,
@@ -2052,7 +2299,7 @@ int kbo_set_prefix_table(int enabled) { g_prefix_table = enabled ? 1 : 0; return
 int kbo_set_rank2(int enabled) { g_rank2 = enabled ? 1 : 0; return KBO_OK; }
 int kbo_set_l2_persist(int enabled) { g_l2_persist = enabled ? 1 : 0; return KBO_OK; }
 int kbo_set_ms_flags(uint32_t flags) {
-    g_ms_flags = flags & 0xffu;
+    g_ms_flags = flags & 0xffu;  // bit 1: K2 instead of K2b; bit 2: fused kernel without rank2 pairs; bit 4: fused K1+K2b kernel
     const uint32_t blk = (flags >> 8) & 0x3ffu;  // bits 8..17: K1 block size (experiment)
     if (blk == 128 || blk == 256) g_ms_block = blk;
     return KBO_OK;

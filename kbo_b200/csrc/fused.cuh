@@ -11,7 +11,7 @@
 //   A. "fast pass", one lane per chunk of the tile: the MS recurrence with TWO
 //      bases per rank probe (IndexView::rank2) and NO contraction code.  When a
 //      base does not extend, the lane records a task (position + the exact
-//      state before it), restarts from the empty state at that base and goes
+//      state before it), restarts from the empty state after that base and goes
 //      on.  What it writes after a restart is provisional: the longest match
 //      that STARTS at or after the restart;
 //   B. "repair pass", one lane per task: the exact recurrence (extend, contract
@@ -64,14 +64,17 @@ struct FusedParams {
 
 // shared-memory carve-up (all offsets multiples of 16)
 struct FusedSmem {
-    uint32_t off_pack, off_inv, off_ms, off_tasks, off_misc, off_ring, off_lut, off_stage, total;
+    uint32_t off_pack, off_inv, off_ms, off_warm, off_tasks, off_misc, off_ring, off_lut, off_stage, total;
 };
-__host__ __device__ inline FusedSmem fused_smem_layout(uint32_t tile_len, uint32_t stage_words, uint32_t task_cap, bool chars) {
+__host__ __device__ inline uint32_t fused_warm_row(uint32_t k) { return (k + 14u) & ~15u; }  // >= k - 1, multiple of 16
+__host__ __device__ inline FusedSmem fused_smem_layout(uint32_t tile_len, uint32_t stage_words, uint32_t task_cap, uint32_t k,
+                                                       bool chars) {
     FusedSmem s;
     uint32_t o = 0;
     s.off_pack = o;  o += ((stage_words * 8u) + 15u) & ~15u;
     s.off_inv = o;   o += ((stage_words * 4u) + 15u) & ~15u;
     s.off_ms = o;    o += (16u + tile_len + MS_LOOKAHEAD + 16u + 15u) & ~15u;
+    s.off_warm = o;  o += FUSED_THREADS * fused_warm_row(k);  // provisional MS of every lane's warm-up positions
     s.off_tasks = o; o += task_cap * 16u;
     s.off_misc = o;  o += 64u;   // mbarrier (8), task count, tail state
     s.off_ring = o;  o += FUSED_WARPS * 64u;
@@ -107,7 +110,7 @@ inline bool fused_geometry(uint64_t Lp, uint32_t k, bool chars, int n_sms, uint3
     g.chunk = (g.tile_len + MS_LOOKAHEAD + FUSED_THREADS - 1) / FUSED_THREADS;
     g.stage_words = (g.tile_len + MS_LOOKAHEAD + 31) / 32 + ((k + 30) >> 5) + 8;
     g.task_cap = FUSED_THREADS * ((g.chunk + 2 * (k - 1)) / k + 2);  // a new task at most every k positions of a lane's feed
-    g.smem = fused_smem_layout(g.tile_len, g.stage_words, g.task_cap, chars);
+    g.smem = fused_smem_layout(g.tile_len, g.stage_words, g.task_cap, k, chars);
     if (g.smem.total > 200 * 1024) return false;
     *out = g;
     return true;
@@ -151,10 +154,11 @@ __device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
 template <bool CHARS, bool COUNT>
 __global__ void __launch_bounds__(FUSED_THREADS, 8) ms_fused_kernel(const KBO_GRID_CONSTANT FusedParams p) {
     KBO_DYN_SMEM(smem);
-    const FusedSmem lay = fused_smem_layout(p.tile_len, p.stage_words, p.task_cap, CHARS);
+    const FusedSmem lay = fused_smem_layout(p.tile_len, p.stage_words, p.task_cap, p.ix.k, CHARS);
     uint64_t* const pack_s = reinterpret_cast<uint64_t*>(smem + lay.off_pack);
     uint32_t* const inv_s = reinterpret_cast<uint32_t*>(smem + lay.off_inv);
     uint8_t* const ms_s = smem + lay.off_ms;
+    uint8_t* const warm_s = smem + lay.off_warm;
     uint4* const tasks = reinterpret_cast<uint4*>(smem + lay.off_tasks);
     uint64_t* const bar = reinterpret_cast<uint64_t*>(smem + lay.off_misc);
     uint32_t* const misc = reinterpret_cast<uint32_t*>(smem + lay.off_misc) + 2;  // [0] task count, [1..3] tail l, r, d
@@ -240,8 +244,10 @@ __global__ void __launch_bounds__(FUSED_THREADS, 8) ms_fused_kernel(const KBO_GR
                 warm -= PREF_LEN;
             }
             uint32_t bp = a - warm;
-            // lane 0 also produces the MS byte of the position before the tile (translate's left neighbour)
-            const uint32_t emit_from = (tid == 0 && a > 0) ? a - 1 : a;
+            // Bytes of positions >= a go to the tile's MS array; the lane's provisional bytes of its warm-up positions
+            // go to its private row (index: distance below a), where the repair pass compares against them.
+            // Lane 0 also produces the MS byte of the position before the tile (translate's left neighbour).
+            uint8_t* const wrow = warm_s + tid * fused_warm_row(k);
             if (tid == 0) ms_s[15] = (uint8_t)d;  // overwritten below when that position is stepped through
             uint64_t qw = pack_s[bp >> 5] >> (2u * (bp & 31u));
             uint32_t iw = inv_s[bp >> 5] >> (bp & 31u);
@@ -285,8 +291,12 @@ __global__ void __launch_bounds__(FUSED_THREADS, 8) ms_fused_kernel(const KBO_GR
                         adv = 0;
                         fast = false;  // retry the first base alone
                     } else if (d != 0) {
-                        // failure in a state with d > 0: hand the exact continuation to the repair pass, restart here
-                        adv = 0;
+                        // Failure in a state with d > 0: the exact continuation goes to the repair pass and the lane
+                        // restarts from the empty state AFTER this base (provisional length 0 here).  After a
+                        // substitution -- the common case -- the match that starts at the next base is the one the
+                        // exact recurrence ends up with a dozen positions later, where the two then agree; a restart
+                        // AT the failing base would die at about that depth and restart again behind the exact match
+                        // (measured: 42 instead of ~13 positions per repair).
                         if (bp >= new_from) {
                             cur_task = atomicAdd(misc, 1u);
                             cur_start = bp;
@@ -294,8 +304,9 @@ __global__ void __launch_bounds__(FUSED_THREADS, 8) ms_fused_kernel(const KBO_GR
                         } else if (cur_task < p.task_cap) {
                             reinterpret_cast<uint16_t*>(&tasks[cur_task].w)[1] = (uint16_t)(bp - cur_start);
                         }
-                        new_from = bp + k;
+                        new_from = bp + 1 + k;
                         l = 0; r = n; d = 0;
+                        dA = 0;
                         fast = true; known_fail = false;
                     } else {
                         dA = 0;  // nothing matches this base, not even alone
@@ -304,8 +315,15 @@ __global__ void __launch_bounds__(FUSED_THREADS, 8) ms_fused_kernel(const KBO_GR
                 }
                 if (adv) {
                     if (COUNT) { cnt_proc += adv; cnt_emit += (bp >= a && bp < rel_end) + (adv == 2 && bp + 1 >= a && bp + 1 < rel_end); }
-                    if (bp >= emit_from) msb[bp] = (uint8_t)(adv == 2 ? dA : d);
-                    if (adv == 2 && bp + 1 >= emit_from) msb[bp + 1] = (uint8_t)dB;
+                    {
+                        const uint8_t v0 = (uint8_t)(adv == 2 ? dA : d);
+                        if (bp >= a) msb[bp] = v0; else wrow[a - 1 - bp] = v0;
+                        if (tid == 0 && bp + 1 == a) ms_s[15] = v0;
+                    }
+                    if (adv == 2) {
+                        if (bp + 1 >= a) msb[bp + 1] = (uint8_t)dB; else wrow[a - 2 - bp] = (uint8_t)dB;
+                        if (tid == 0 && bp + 2 == a) ms_s[15] = (uint8_t)dB;
+                    }
                     bp += adv;
                     qw >>= 2 * adv;
                     iw >>= adv;
@@ -321,18 +339,22 @@ __global__ void __launch_bounds__(FUSED_THREADS, 8) ms_fused_kernel(const KBO_GR
     __syncthreads();
 
     // ---- B. repair pass: one lane per task ------------------------------------------------------------------------
+    // Most positions of a task are noise: the base fails to extend, the interval is contracted, the base extends.
+    // The link words of the current interval are therefore loaded TOGETHER with the rank words of every probe, so a
+    // failed probe costs no second round trip before the contraction (the extra sector is wasted when the probe
+    // succeeds, which is the rarer case here).  The first probe of a task is known to fail (the fast pass saw it).
     {
         const uint32_t n_tasks = misc[0] < p.task_cap ? misc[0] : p.task_cap;  // (the capacity is a proven bound)
         for (uint32_t t = tid; t < n_tasks; t += FUSED_THREADS) {
             const uint4 T = tasks[t];
             uint32_t bp = T.x, l = T.y, r = T.z, d = T.w & 0xffu;
-            const uint32_t owner = (T.w >> 8) & 0xffu, last_reset = T.x + (T.w >> 16);
+            const uint32_t owner = (T.w >> 8) & 0xffu, last_fail = T.x + (T.w >> 16);  // (restart = the position after it)
             const uint32_t a = rel_tile + owner * p.chunk;
             const uint32_t b = a + p.chunk < rel_V ? a + p.chunk : rel_V;
-            const uint32_t emit_from = (owner == 0 && a > 0) ? a - 1 : a;
+            uint8_t* const wrow = warm_s + owner * fused_warm_row(k);
             uint64_t qw = pack_s[bp >> 5] >> (2u * (bp & 31u));
             uint32_t iw = inv_s[bp >> 5] >> (bp & 31u);
-            bool synced = false;
+            bool synced = false, known_fail = true;
             while (bp < b) {
                 if (iw & 1u) {
                     l = 0; r = n; d = 0;
@@ -340,22 +362,26 @@ __global__ void __launch_bounds__(FUSED_THREADS, 8) ms_fused_kernel(const KBO_GR
                     const uint32_t rowoff = ((uint32_t)qw & 3u) * stride;
                     for (;;) {  // extend; on failure contract to the next depth that changes the interval and retry
                         const uint32_t bl = l >> 5, br = r >> 5;
-                        const uint64_t wl = __ldg(p.ix.rank + (rowoff + bl));
-                        const uint64_t wr = (br == bl) ? wl : __ldg(p.ix.rank + (rowoff + br));
-                        const uint32_t nl = (uint32_t)(wl >> 32) + __popc((uint32_t)wl & ((1u << (l & 31)) - 1u));
-                        const uint32_t nr = (uint32_t)(wr >> 32) + __popc((uint32_t)wr & ((1u << (r & 31)) - 1u));
-                        if (COUNT) {
-                            const bool sp = (bl >> 2) != (br >> 2);
-                            ++cnt_att; cnt_split += sp;
-                            if (bp >= a && bp < rel_end) { ++cnt_att_e; cnt_split_e += sp; }
+                        uint32_t nl = 0, nr = 0;
+                        const uint32_t el = __ldg(p.ix.links + l), er = __ldg(p.ix.links + r);
+                        if (!known_fail) {
+                            const uint64_t wl = __ldg(p.ix.rank + (rowoff + bl));
+                            const uint64_t wr = (br == bl) ? wl : __ldg(p.ix.rank + (rowoff + br));
+                            nl = (uint32_t)(wl >> 32) + __popc((uint32_t)wl & ((1u << (l & 31)) - 1u));
+                            nr = (uint32_t)(wr >> 32) + __popc((uint32_t)wr & ((1u << (r & 31)) - 1u));
+                            if (COUNT) {
+                                const bool sp = (bl >> 2) != (br >> 2);
+                                ++cnt_att; cnt_split += sp;
+                                if (bp >= a && bp < rel_end) { ++cnt_att_e; cnt_split_e += sp; }
+                            }
                         }
+                        known_fail = false;
                         if (nl < nr) {
                             l = nl; r = nr;
                             d = d + 1 < k ? d + 1 : k;
                             break;
                         }
                         if (d == 0) break;
-                        const uint32_t el = __ldg(p.ix.links + l), er = __ldg(p.ix.links + r);
                         const bool scanned = ms_contract(p.ix, el, er, l, r, d);
                         if (COUNT) {
                             ++cnt_con; cnt_extra += scanned;
@@ -364,9 +390,11 @@ __global__ void __launch_bounds__(FUSED_THREADS, 8) ms_fused_kernel(const KBO_GR
                     }
                 }
                 if (COUNT) ++cnt_proc;
-                if (bp >= emit_from) {
-                    if (bp >= last_reset && msb[bp] == (uint8_t)d) { synced = true; break; }  // same match from here on
-                    msb[bp] = (uint8_t)d;
+                {
+                    uint8_t* const slot = bp >= a ? msb + bp : wrow + (a - 1 - bp);
+                    if (bp > last_fail && *slot == (uint8_t)d) { synced = true; break; }  // same match from here on
+                    *slot = (uint8_t)d;
+                    if (owner == 0 && bp + 1 == a) ms_s[15] = (uint8_t)d;
                 }
                 ++bp;
                 qw >>= 2;

@@ -1173,7 +1173,7 @@ struct RleParams {
     RleRecord* out;         // likewise
     uint64_t cap;           // records with a slot >= cap are dropped (the count is still exact)
     const uint64_t* base_in;  // optional: number of records of the sub-batches before this one (device counter);
-    uint64_t* total_out;      // optional: receives *base_in + the records of this sub-batch
+    uint64_t* total_out;      // optional: receives base + the records of this sub-batch
     uint32_t write_first;     // != 0: rle_offsets[0] is written too (0 for the sub-batches after the first)
 };
 
@@ -1239,24 +1239,17 @@ __device__ __forceinline__ void rle_block_scan(uint32_t (&v)[N], uint32_t (&tota
     }
 }
 
-// The block that finishes last turns the per-block totals (N counters of 32 bits each per entry) into "before the
-// block", with the grand total at [n_blocks].  The ticket counter resets itself for the next launch.
+// One block turns the per-block totals (N counters of 32 bits each per entry) into "before the block", with the
+// grand total at [n_blocks].  The totals were written by other blocks of the same launch: they are read at L2.
 template <int N, typename T>
-__device__ __forceinline__ void rle_finish_blocks(T* blk, uint64_t n_blocks, unsigned int* ticket) {
-    __shared__ bool last;
-    __threadfence();
-    __syncthreads();
-    if (threadIdx.x == 0) last = atomicAdd(ticket, 1u) == gridDim.x - 1;
-    __syncthreads();
-    if (!last) return;
-    __threadfence();
+__device__ __forceinline__ void rle_scan_block_totals(T* blk, uint64_t n_blocks) {
     uint32_t run[N];
     for (int i = 0; i < N; ++i) run[i] = 0;
     for (uint64_t base = 0; base < n_blocks; base += RLE_BLOCK) {
         const uint64_t b = base + threadIdx.x;
         uint32_t v[N], tot[N];
         const uint32_t* src = reinterpret_cast<const uint32_t*>(blk + (b < n_blocks ? b : 0));
-        for (int i = 0; i < N; ++i) v[i] = b < n_blocks ? __ldcg(src + i) : 0u;  // written by other blocks: read at L2
+        for (int i = 0; i < N; ++i) v[i] = b < n_blocks ? __ldcg(src + i) : 0u;
         rle_block_scan<N>(v, tot);
         if (b < n_blocks) {
             uint32_t* dst = reinterpret_cast<uint32_t*>(blk + b);
@@ -1267,14 +1260,33 @@ __device__ __forceinline__ void rle_finish_blocks(T* blk, uint64_t n_blocks, uns
     if (threadIdx.x == 0) {
         uint32_t* dst = reinterpret_cast<uint32_t*>(blk + n_blocks);
         for (int i = 0; i < N; ++i) dst[i] = run[i];
-        *ticket = 0;
     }
 }
 
-// thread per word: jump / gap-open masks, the four counts before the word, block totals
+// The block that finishes last scans the block totals.  The ticket counter resets itself for the next launch.
+template <int N, typename T>
+__device__ __forceinline__ void rle_finish_blocks(T* blk, uint64_t n_blocks, unsigned int* ticket) {
+    __shared__ bool last;
+    __threadfence();
+    __syncthreads();
+    if (threadIdx.x == 0) last = atomicAdd(ticket, 1u) == gridDim.x - 1;
+    __syncthreads();
+    if (!last) return;
+    __threadfence();
+    rle_scan_block_totals<N>(blk, n_blocks);
+    if (threadIdx.x == 0) *ticket = 0;
+}
+
+// thread per word: jump / gap-open masks, the four counts before the word, block totals.
+// MARKS (window == 1, i.e. max_gap_len == 0: a segment is a maximal run of aligned characters, so START / END need
+// no prefix counts): also the START / END masks and their counts -- what rle_mark_kernel does in a second launch
+// for the gapped form.
+template <bool MARKS>
 __global__ void __launch_bounds__(RLE_BLOCK) rle_word_counts_kernel(RleParams p) {
     const uint64_t w = (uint64_t)blockIdx.x * RLE_BLOCK + threadIdx.x;
-    uint32_t c[4] = {0, 0, 0, 0}, tot[4];
+    uint32_t c[MARKS ? 6 : 4], tot[MARKS ? 6 : 4];
+#pragma unroll
+    for (int i = 0; i < (MARKS ? 6 : 4); ++i) c[i] = 0;
     if (w < p.n_words) {
         const uint32_t N = rle_nongap(p, w), R = __ldg(p.rr + w), Gp = __ldg(p.gap + w);
         uint32_t n31 = 0, r31 = 0;
@@ -1290,17 +1302,41 @@ __global__ void __launch_bounds__(RLE_BLOCK) rle_word_counts_kernel(RleParams p)
         c[1] = __popc(__ldg(p.match + w));
         c[2] = __popc(J);
         c[3] = __popc(GO);
+        if (MARKS) {
+            const uint32_t n0 = w + 1 < p.n_words ? rle_nongap(p, w + 1) & 1u : 0u;
+            const uint32_t st = N & ~((N << 1) | n31);  // first / last character of a run of aligned characters
+            const uint32_t en = N & ~((N >> 1) | (n0 << 31));
+            p.start[w] = st;
+            p.end[w] = en;
+            c[4] = __popc(st);
+            c[5] = __popc(en);
+        }
     }
-    rle_block_scan<4>(c, tot);
+    rle_block_scan<(MARKS ? 6 : 4)>(c, tot);
     if (w < p.n_words) {
         RleCounts before = {c[0], c[1], c[2], c[3]};
         p.cnt[w] = before;
+        if (MARKS) p.cse[w] = (uint64_t)c[4] | ((uint64_t)c[5] << 32);
     }
     if (threadIdx.x == 0) {
         RleCounts t = {tot[0], tot[1], tot[2], tot[3]};
         p.cnt_blk[blockIdx.x] = t;
+        if (MARKS) p.cse_blk[blockIdx.x] = (uint64_t)tot[4] | ((uint64_t)tot[5] << 32);
     }
-    rle_finish_blocks<4>(p.cnt_blk, p.n_blocks, p.tickets);
+    if (MARKS) {  // one election, both arrays
+        __shared__ bool last;
+        __threadfence();
+        __syncthreads();
+        if (threadIdx.x == 0) last = atomicAdd(p.tickets, 1u) == gridDim.x - 1;
+        __syncthreads();
+        if (!last) return;
+        __threadfence();
+        rle_scan_block_totals<4>(p.cnt_blk, p.n_blocks);
+        rle_scan_block_totals<2>(p.cse_blk, p.n_blocks);
+        if (threadIdx.x == 0) *p.tickets = 0;
+    } else {
+        rle_finish_blocks<4>(p.cnt_blk, p.n_blocks, p.tickets);
+    }
 }
 
 // number of aligned characters before padded position x

@@ -345,8 +345,12 @@ static uint64_t emu_run_rle(const uint32_t* gap, const uint32_t* match, const ui
     p.start = start.data(); p.end = end.data(); p.cse = cse.data(); p.cse_blk = cse.data() + n_words;
     p.tickets = tickets; p.rle_offsets = rle_offsets; p.out = (RleRecord*)out7; p.cap = cap;
     p.base_in = nullptr; p.total_out = nullptr; p.write_first = 1;
-    emu_launch_par((unsigned)nb, RLE_BLOCK, [&]() { rle_word_counts_kernel(p); });
-    emu_launch_par((unsigned)nb, RLE_BLOCK, [&]() { rle_mark_kernel(p); });
+    if (p.window == 1) {  // as capi.cu run_rle_counts
+        emu_launch_par((unsigned)nb, RLE_BLOCK, [&]() { rle_word_counts_kernel<true>(p); });
+    } else {
+        emu_launch_par((unsigned)nb, RLE_BLOCK, [&]() { rle_word_counts_kernel<false>(p); });
+        emu_launch_par((unsigned)nb, RLE_BLOCK, [&]() { rle_mark_kernel(p); });
+    }
     const unsigned threads = 128;
     const uint64_t items = n_words > nq + 1 ? n_words : nq + 1;
     emu_launch_seq((unsigned)((items + threads - 1) / threads), threads, [&]() { rle_finish_kernel(p); });

@@ -27,6 +27,19 @@ def _lib():
     api.set_chunk_len(0)
 
 
+@pytest.fixture(autouse=True, params=["separate", "fused"])
+def kernel_path(request):
+    """Tests that reach matches / find run twice: K1 followed by K2b (the default), and the fused K1 + K2b kernel of
+    fused.cuh (kbo_set_ms_flags bit 4: MS bytes only in shared memory, TMA-staged queries, two bases per probe)."""
+    name = request.node.originalname or request.node.name
+    if request.param == "fused":
+        if not any(t in name for t in ("matches", "find", "config2", "randomised", "tiny")):
+            pytest.skip("does not reach the fused kernel")
+        api.set_ms_flags(16)
+    yield
+    api.set_ms_flags(0)
+
+
 def g(block, var):
     return GOLD[block][var].encode()
 
@@ -631,9 +644,51 @@ def test_counters_and_launch_count():
     q = synth.mutate(ref, 52).tobytes()[:40_000]
     api.matches(q, ix)
     api.set_profile_counters(False)
-    assert api.kernel_launch_count() - n0 == 3  # pack, MS, derandomize+translate
+    assert api.kernel_launch_count() - n0 == 3  # pack, MS, derandomize+translate (K1 and K2b as separate kernels)
     c = ix.ms_counters()
     assert c["bases_emitted"] == len(q) + 1
     assert c["bases_processed"] >= c["bases_emitted"]
     assert c["extend_attempts"] >= len(q) * 0.9
     assert ix.last_kernel_ms() > 0
+
+
+# ------------------------------------------------------------------------ multi-GPU context ---
+@pytest.mark.parametrize("devices", [[0], [0, 0, 0], "all"])
+def test_multi_gpu_context_matches_and_find(devices):
+    """kbo_ctx / kbo_index_set: the batch is sharded over the workers and gathered into the caller's buffers; results
+    equal the oracle's (and the single-device calls').  [0, 0, 0] runs three workers on one GPU, so the sharding and the
+    gather of the record counts are exercised on a one-GPU box too; "all" uses every visible GPU."""
+    if devices == "all":
+        if api.device_count() < 2:
+            pytest.skip("needs at least two GPUs")
+        devices = list(range(api.device_count()))
+    ref = rand_seq(300_000, 901)
+    ctx = api.Context(devices=devices)
+    iset = ctx.build([ref], api.BuildOpts(k=31))
+    single = api.build([ref], api.BuildOpts(k=31))
+    o = O.OracleIndex([ref], k=31)
+    assert (iset.n_sets, iset.n_kmers) == (o.n_sets, o.n_kmers)
+    rng = np.random.default_rng(902)
+    queries = []
+    for i in range(400):
+        a = int(rng.integers(0, len(ref) - 3000))
+        q = synth.mutate(np.frombuffer(ref[a:a + int(rng.integers(3, 3000))], dtype=np.uint8), 903 + i).tobytes()
+        queries.append(with_ns(q, 904 + i, 0.002) if len(q) > 2 else ref[a:a + 3])
+    concat, offsets = api.csr(queries)
+    _, want, _ = o.matches_batch(concat, offsets, n_threads=4)
+    got = iset.matches_csr(concat, offsets)
+    assert np.array_equal(got[:len(concat)], want)
+    for gap in (0, 25):
+        for pinned in (True, False):
+            buf, n = iset.find_csr(concat, offsets, api.FindOpts(max_gap_len=gap), api.FindBuffers(len(queries), pinned=pinned))
+            assert n == int(buf.rle_offsets[len(queries)])
+            for i in (0, 1, 7, 133, 134, 265, 266, 399):
+                got_i = [tuple(int(getattr(buf.rle[j], f)) for f, _ in api.RleC._fields_)
+                         for j in range(int(buf.rle_offsets[i]), int(buf.rle_offsets[i + 1]))]
+                assert got_i == o.find(queries[i], 1e-7, gap), (gap, pinned, i)
+            # the gathered records are exactly the single-device call's
+            sbuf, sn = api.find_csr(concat, offsets, single, api.FindOpts(max_gap_len=gap))
+            assert sn == n and np.array_equal(sbuf.rle_offsets, buf.rle_offsets)
+            assert bytes(memoryview(sbuf.rle))[:56 * n] == bytes(memoryview(buf.rle))[:56 * n]
+    iset.close()
+    ctx.close()

@@ -55,9 +55,16 @@ def parse_args():
     ap.add_argument("--steps", type=int, default=400)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
-    ap.add_argument("--ref-len", type=int, default=5_000_000)
-    ap.add_argument("--queries", type=int, default=10_000)
-    ap.add_argument("--query-len", type=int, default=1000)
+    ap.add_argument("--config", type=int, default=2, choices=[2, 3, 4, 5],
+                    help="BASELINE.json configs[] entry (1-based): 2 = find, 10,000 x 1 kbp vs 5 Mbp (the headline, default); "
+                         "5 = find vs an HBM-resident pangenome index with 10 kbp queries; 3 / 4 = call / map of whole "
+                         "assemblies against one reference (index built per assembly)")
+    ap.add_argument("--ref-len", type=int, default=0, help="reference length (0 = the config's: 5 Mbp, config 5: 1 Gbp per GPU)")
+    ap.add_argument("--queries", type=int, default=0)
+    ap.add_argument("--query-len", type=int, default=0)
+    ap.add_argument("--assemblies", type=int, default=8, help="configs 3 / 4: assemblies per rank")
+    ap.add_argument("--k", type=int, default=31, help="configs 3 / 4: k of the indexes (k > 32 takes the host builder; the "
+                                                      "reference resolves variants only when k - threshold leaves room, e.g. k = 51)")
     ap.add_argument("--batches", type=int, default=16, help="distinct batches rotated through (16 x 10 MB > L2)")
     ap.add_argument("--chunk-len", type=int, default=0, help="MS chunk length (0 = automatic)")
     ap.add_argument("--ms-flags", type=int, default=0, help="experiment switches (2: K2 instead of K2b)")
@@ -73,7 +80,16 @@ def parse_args():
     ap.add_argument("--pipeline-parts", type=int, default=0, help="sub-batches of a host-buffer call (0 = automatic)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--cpu-seconds", type=float, default=20.0, help="target CPU work (core-seconds) of the cpu_baseline sample")
-    return ap.parse_args()
+    args = ap.parse_args()
+    if args.config == 5:
+        args.ref_len = args.ref_len or 1_000_000_000
+        args.queries = args.queries or 1000
+        args.query_len = args.query_len or 10_000
+    else:
+        args.ref_len = args.ref_len or 5_000_000
+        args.queries = args.queries or 10_000
+        args.query_len = args.query_len or 1000
+    return args
 
 
 # ------------------------------------------------------------------------------------ helpers ---
@@ -218,9 +234,10 @@ def run_reference(args, rank, world):
 
 
 def config_dict(args):
+    where = ("BASELINE.json configs[4] shape on one GPU per rank: pangenome index HBM-resident, L2-miss-bound rank queries"
+             if args.config == 5 else "BASELINE.json configs[1]; index L2-resident")
     c = {"workload": "kbo::find of %d synthetic %d bp gene queries (1%% SNPs) vs a %d bp synthetic reference, k=%d, "
-                     "p=%g (BASELINE.json configs[1]; index L2-resident)" % (args.queries, args.query_len, args.ref_len,
-                                                                           K, P),
+                     "p=%g (%s)" % (args.queries, args.query_len, args.ref_len, K, P, where),
          "queries_per_step": args.queries, "query_len": args.query_len, "ref_len": args.ref_len, "k": K,
          "l2_policy": "inputs larger than L2: steps rotate through %d distinct batches (%d MB of queries); the index "
                       "is L2-resident by the config's design" % (args.batches,
@@ -285,7 +302,7 @@ def run_ours(args, rank, local_rank, world):
     d_off = torch.from_numpy(offsets.astype(np.int64)).cuda()
     pinned_in = [torch.from_numpy(b).pin_memory() for b in batches]
     d_in = [p.cuda(non_blocking=True) for p in pinned_in]
-    rle_cap = 16 * nq + 1024
+    rle_cap = 16 * nq + bases_per_step // 16 + 1024
     d_rle = [torch.empty(rle_cap * 7, dtype=torch.int64, device="cuda") for _ in batches]
     d_rle_off = [torch.empty(nq + 1, dtype=torch.int64, device="cuda") for _ in batches]
     torch.cuda.synchronize()
@@ -373,7 +390,7 @@ def run_ours(args, rank, local_rank, world):
     offsets_pinned[:] = offsets
     depth = max(1, args.e2e_depth)
     n_thr = max(0, args.e2e_threads)
-    fbufs = [api.FindBuffers(nq, pinned=True) for _ in range(max(depth, n_thr))]
+    fbufs = [api.FindBuffers(nq, cap=rle_cap, pinned=True) for _ in range(max(depth, n_thr))]
     counts = np.zeros(max(args.steps, 1), dtype=np.int64)
 
     def e2e_async(first, count, record):
@@ -419,6 +436,21 @@ def run_ours(args, rank, local_rank, world):
     e2e_s = time.perf_counter() - w0
     n_rle = int(counts[0])
     e2e_value = world * args.steps * bases_per_step / reduce_max(e2e_s)
+    # the copy-in alone, all ranks at once: what the host -> device path of this box allows for this many GPUs
+    hin = [torch.from_numpy(a) for a in pinned_np]
+    d_tmp = [torch.empty(len(batches[0]), dtype=torch.uint8, device="cuda") for _ in range(4)]
+    cstreams = workers[:4] if len(workers) >= 4 else [torch.cuda.Stream() for _ in range(4)]
+
+    def copy_in_only(n):
+        for s in range(n):
+            with torch.cuda.stream(cstreams[s % 4]):
+                d_tmp[s % 4].copy_(hin[s % len(hin)], non_blocking=True)
+        torch.cuda.synchronize()
+    copy_in_only(4)
+    barrier()
+    w0 = time.perf_counter()
+    copy_in_only(args.steps)
+    copy_value = world * args.steps * bases_per_step / reduce_max(time.perf_counter() - w0)
     total_records = int(sum(int(g.sum().item()) for g in gathered)) if gathered is not None else int(counts[:args.steps].sum())
     clocks = sampler.stop() if sampler else None
 
@@ -476,7 +508,7 @@ def run_ours(args, rank, local_rank, world):
 
     # ---- cpu baseline + a parity spot check against it (rank 0, N = 1) --------------------------
     cpu = None
-    if rank == 0 and world == 1 and not args.no_cpu_baseline:
+    if rank == 0 and world == 1 and not args.no_cpu_baseline and args.config == 2:
         cpu, oix = cpu_baseline(ref, batches, offsets, args, args.cpu_seconds)
         nchk = min(nq, 200)
         _, want, _ = oix.matches_batch(batches[0][:int(offsets[nchk])], offsets[:nchk + 1], P, n_threads=cpu["cores"])
@@ -502,6 +534,9 @@ def run_ours(args, rank, local_rank, world):
                         "h2d_bytes_per_step": bases_per_step + 8 * (nq + 1),
                         "d2h_bytes_per_step": 8 * (nq + 1) + 56 * n_rle + 8,
                         "records_total": total_records,
+                        "copy_in_only_value": copy_value,
+                        "copy_in_only_note": "same steps, only the pinned host -> device copy of the queries, all ranks at "
+                                             "once: the ceiling of any host-buffer path on this box at this GPU count",
                         "api": ("kbo_find_batch_submit / kbo_job_wait: pinned host queries in, RLE records + per-query "
                                 "offsets written by the device into pinned host buffers; %d steps, one host thread, %d "
                                 "batches in flight" % (args.steps, depth)) if not n_thr else
@@ -511,6 +546,103 @@ def run_ours(args, rank, local_rank, world):
                 "gpu_launches": int(lt.item()), "roofline": roof}
         if cpu is not None:
             line["cpu_baseline"] = cpu
+        print(json.dumps(line), flush=True)
+    if dist is not None:
+        dist.barrier()
+        dist.destroy_process_group()
+
+
+# ------------------------------------------------------------- configs 3 / 4: whole assemblies ---
+def run_assemblies(args, rank, local_rank, world):
+    """BASELINE configs[2] (kbo::call) / configs[3] (kbo::map): a stream of mutated 5 Mbp assemblies against one
+    reference.  Every assembly gets its own SBWT index (built on the GPU), the reference is streamed through it
+    (K0, K1 with intervals, K2b), and the host refinement runs on the device's (d, l, r); kbo::call / kbo::map also
+    rebuild the index of the reference per call, as the reference does (lib.rs:553).  A "step" is one assembly; the
+    metric counts the streamed reference bases.  Assemblies are sharded over the ranks (no collective)."""
+    import torch
+    from kbo_b200 import api, build, synth
+    build.build_library()
+    api.load_library()
+    dev = local_rank
+    torch.cuda.set_device(dev)
+    dist = None
+    if world > 1:
+        import torch.distributed as dist
+        dist.init_process_group("nccl", device_id=torch.device("cuda", dev))
+        partition_cpus(local_rank, int(os.environ.get("LOCAL_WORLD_SIZE", world)))
+    ref = synth.random_seq(args.ref_len, synth.SEED_C2_REF)
+    refb = ref.tobytes()
+    n_asm = max(1, args.assemblies)
+    hw = len(os.sched_getaffinity(0))
+    kk = args.k
+    bo = api.BuildOpts(k=kk, build_select=True, num_threads=hw)  # (num_threads also threads the gap filling)
+    name = "call" if args.config == 3 else "map"
+
+    asms = {i: synth.mutate(ref, 0x6B626F10 + 1000 * rank + i) for i in range(n_asm + 2)}  # synthetic inputs: untimed
+
+    def one(i):
+        asm = asms[i]
+        t0 = time.perf_counter()
+        ix = api.build([asm], bo, device=dev)
+        t1 = time.perf_counter()
+        if args.config == 3:
+            res = api.call(ix, refb, api.CallOpts(sbwt_build_opts=bo))
+        else:
+            res = api.map(refb, ix, api.MapOpts(sbwt_build_opts=bo))
+        t2 = time.perf_counter()
+        ix.close()
+        return asm, res, t1 - t0, t2 - t1
+
+    for i in range(2):  # warm-up (allocator pools, pinned staging)
+        one(n_asm + i)
+    torch.cuda.synchronize()
+    if dist is not None:
+        dist.barrier()
+    w0 = time.perf_counter()
+    build_s = run_s = 0.0
+    first = None
+    for i in range(n_asm):
+        asm, res, b, r = one(i)
+        build_s += b
+        run_s += r
+        if first is None:
+            first = (asm, res)
+    total_s = time.perf_counter() - w0
+    t = torch.tensor([total_s], dtype=torch.float64, device="cuda")
+    if dist is not None:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    value = world * n_asm * len(ref) / float(t.item())
+    parity = None
+    if rank == 0:  # bit-exact against the oracle on the first assembly
+        import oracle_lib as O
+        O.build_oracle()
+        t0 = time.perf_counter()
+        oix = O.OracleIndex([first[0].tobytes()], k=kk)
+        if args.config == 3:
+            want = oix.call(refb, 1e-7, kk)
+            got = [(v.query_pos, v.query_chars, v.ref_chars) for v in first[1]]
+        else:
+            want = oix.map(refb, build_k=kk)
+            got = first[1]
+        cpu_s = time.perf_counter() - t0
+        if got != want:
+            raise SystemExit("bench.py: kbo::%s differs from the oracle on the first assembly" % name)
+        parity = {"checked": "assembly 0 bit-exact vs the CPU oracle (%s)" % ("%d variants" % len(want) if args.config == 3
+                                                                             else "%d output bytes" % len(want)),
+                  "oracle_seconds_index_plus_%s_one_thread" % name: round(cpu_s, 2),
+                  "oracle_bases_per_s": len(ref) / cpu_s}
+        line = {"metric": "query bases/s (kbo %s, whole box)" % name, "value": value, "unit": "query bases/s",
+                "n_gpus": world, "steps": n_asm, "warmup": 2, "ms_per_step": 1e3 * float(t.item()) / n_asm,
+                "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "u8", "data": "synthetic",
+                "config": {"workload": "kbo::%s of %d mutated %d bp synthetic assemblies per rank (1%% SNPs + short indels) "
+                                       "against one reference, k=%d, default options (BASELINE.json configs[%d])"
+                                       % (name, n_asm, args.ref_len, kk, args.config - 1),
+                           "assemblies_per_rank": n_asm, "ref_len": args.ref_len, "k": kk},
+                "impl_detail": {"split_ms_per_assembly": {"assembly_index_build (GPU builder incl. copy-in and host mirror)":
+                                                          1e3 * build_s / n_asm,
+                                                          "kbo::%s (MS on the device + reference-index build + host refinement)" % name:
+                                                          1e3 * run_s / n_asm},
+                                "host_threads_for_refinement": hw, "parity": parity}}
         print(json.dumps(line), flush=True)
     if dist is not None:
         dist.barrier()
@@ -529,6 +661,8 @@ def main():
         raise SystemExit(subprocess.call(cmd))
     if args.impl == "reference":
         run_reference(args, rank, world)
+    elif args.config in (3, 4):
+        run_assemblies(args, rank, local_rank, world)
     else:
         run_ours(args, rank, local_rank, world)
 

@@ -67,7 +67,7 @@ typedef enum kbo_status {
 typedef struct kbo_build_opts {
     uint32_t k;              /* default 31 */
     int32_t add_revcomp;     /* default 0 */
-    uint32_t num_threads;    /* default 1 (host-side sort threads) */
+    uint32_t num_threads;    /* default 1 (host-side sort threads of the k > 32 builder; nothing else) */
     uint32_t prefix_precalc; /* default 8; ignored (the device keeps its own table of the MS states after 10 bases) */
     int32_t build_select;    /* default 0; != 0 keeps the sorted nodes on the host for O(1) access_kmer (map/call);
                               * without it access_kmer walks the index (slower, same result) */
@@ -243,6 +243,16 @@ int kbo_get_ms_counters(const kbo_index* ix, kbo_ms_counters* out);
  * points also from the number of distinct caller streams among the last 8 calls (overlapping calls get longer chunks:
  * less warm-up work per base; a lone call gets the chunk length that makes it finish soonest).  Results never depend on it. */
 int kbo_set_chunk_len(uint32_t chunk_len);
+/* Host threads that bridge gaps in kbo_map (gaps are independent given the incoming translation; results never depend
+ * on it).  0 = hardware concurrency, at most 16.  (BuildOpts.num_threads keeps the reference's meaning: builder threads.) */
+int kbo_set_refine_threads(uint32_t n);
+/* The kbo_set_* knobs are process-wide defaults; this sets a knob for ONE index (value -1 = back to the default), so
+ * that two indexes / callers in one process can differ. */
+typedef enum kbo_tuning_key {
+    KBO_TUNE_CHUNK_LEN = 0, KBO_TUNE_PIPELINE_PARTS = 1, KBO_TUNE_DEVICE_PARTS = 2, KBO_TUNE_MS_FLAGS = 3,
+    KBO_TUNE_REFINE_THREADS = 4
+} kbo_tuning_key;
+int kbo_index_set_tuning(kbo_index* ix, int key, int64_t value);
 /* Tuning knob: number of concurrent sub-batches inside the device-pointer batch calls (0 = automatic). */
 int kbo_set_device_parts(uint32_t parts);
 /* Tuning knob: number of sub-batches the host-buffer batch calls are pipelined over (0 = automatic). */

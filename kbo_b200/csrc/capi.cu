@@ -44,6 +44,11 @@ static std::atomic<uint32_t> g_parts(0);
 static std::atomic<uint32_t> g_dev_parts(0);
 static std::atomic<uint32_t> g_ms_block(128);
 
+static std::atomic<uint32_t> g_refine_threads(0);  // host threads of fill_gaps (0 = hardware concurrency, at most 16)
+struct kbo_index;
+static uint32_t tuned_chunk_len(const kbo_index* ix);
+static uint32_t tuned_ms_flags(const kbo_index* ix);
+
 static int fail(int code, const std::string& msg) {
     g_err = msg;
     return code;
@@ -129,8 +134,14 @@ struct Workspace {
     }
 };
 
+// Tuning knobs of ONE index (kbo_index_set_tuning); -1 = follow the process-wide default (kbo_set_*).
+struct IndexTuning {
+    std::atomic<int64_t> chunk_len{-1}, pipeline_parts{-1}, device_parts{-1}, ms_flags{-1}, refine_threads{-1};
+};
+
 struct kbo_index {
     int device = 0;
+    IndexTuning tune;
     std::vector<PinnedBuf> pinned_pool;  // host staging for find (guarded by mu)
     std::atomic<int> host_calls{0};      // host-buffer batch calls currently inside the library (any thread)
     std::atomic<bool> seen_concurrency{false};  // some host-buffer call found another caller inside (sticky)
@@ -154,6 +165,25 @@ struct kbo_index {
     kbo_ms_counters last_counters = {0, 0, 0, 0, 0, 0, 0, 0, 0, 0};
     float last_kernel_ms = 0.f;
 };
+
+static uint32_t tuned_chunk_len(const kbo_index* ix) {
+    const int64_t v = ix ? ix->tune.chunk_len.load() : -1;
+    return v >= 0 ? (uint32_t)v : g_chunk_len.load();
+}
+static uint32_t tuned_ms_flags(const kbo_index* ix) {
+    const int64_t v = ix ? ix->tune.ms_flags.load() : -1;
+    return v >= 0 ? (uint32_t)v : g_ms_flags.load();
+}
+static uint32_t tuned_parts(const kbo_index* ix, bool device) {
+    const int64_t v = ix ? (device ? ix->tune.device_parts.load() : ix->tune.pipeline_parts.load()) : -1;
+    return v >= 0 ? (uint32_t)v : (device ? g_dev_parts.load() : g_parts.load());
+}
+static uint32_t tuned_refine_threads(const kbo_index* ix) {
+    int64_t v = ix ? ix->tune.refine_threads.load() : -1;
+    if (v < 0) v = g_refine_threads.load();
+    if (v == 0) v = std::min<unsigned>(16, std::max<unsigned>(1, std::thread::hardware_concurrency()));
+    return (uint32_t)v;
+}
 
 // The index arrays live in ONE allocation so that a single access-policy window covers them: every stream that
 // runs K1 marks that range "persisting" in L2 (the streaming batch buffers of K0/K2/K4 would otherwise keep
@@ -596,8 +626,8 @@ static int build_index_gpu(kbo_index* ix, const uint8_t* const* seqs, const uint
 // ---------------------------------------------------------------------------
 // batch geometry
 // ---------------------------------------------------------------------------
-static Geometry batch_geometry(uint64_t total, uint64_t nq, uint32_t overlap = 1) {
-    return kbo_b200::make_geometry(total, nq, g_chunk_len.load(), overlap);
+static Geometry batch_geometry(const kbo_index* ix, uint64_t total, uint64_t nq, uint32_t overlap = 1) {
+    return kbo_b200::make_geometry(total, nq, tuned_chunk_len(ix), overlap);
 }
 
 static int check_offsets(const uint64_t* offsets, uint64_t nq, uint64_t min_len, uint64_t* total) {
@@ -655,7 +685,7 @@ static int run_ms(kbo_index* ix, Workspace* ws, const QueryView& qv, const Geome
     mp.ix = ix->view;
     mp.q = qv;
     mp.chunk_len = g.chunk_len;
-    mp.flags = g_ms_flags.load();
+    mp.flags = tuned_ms_flags(ix);
     mp.n_chunks = g.n_chunks;
     mp.ms = ws->ms.as<uint8_t>();
     mp.l_out = intervals ? ws->l.as<uint32_t>() : nullptr;
@@ -695,7 +725,7 @@ static int run_derand_translate(kbo_index* ix, Workspace* ws, const QueryView& q
         tp.out_match = tp.out_gap + nw;
         tp.out_r = tp.out_match + nw;
     }
-    if (k2b_supported(tp.k, tp.thr) && !(g_ms_flags.load() & 2u)) {  // flag bit1: force K2 (experiments / tests)
+    if (k2b_supported(tp.k, tp.thr) && !(tuned_ms_flags(ix) & 2u)) {  // flag bit1: force K2 (experiments / tests)
         tp.n_tiles = g.n_tiles_b;
         const unsigned blocks = (unsigned)((g.n_tiles_b + K2B_WARPS - 1) / K2B_WARPS);
         if (want_masks) derand_translate_bits_kernel<false><<<blocks, K2B_WARPS * 32, 0, st>>>(tp);
@@ -792,6 +822,18 @@ static int run_rle_finish(cudaStream_t st, RleParams p, uint64_t* rle_offsets, R
 }
 static_assert(sizeof(RleRecord) == sizeof(kbo_rle), "device and ABI RLE records must agree");
 
+// Copies the first min(*total, cap) records from device memory to the caller's page-locked buffer, 8 bytes per thread,
+// consecutive threads consecutive words.  The records kernel itself scatters 8-byte stores (one thread per record);
+// done straight into host memory those cost ~30 us per 25,000 records of end-to-end throughput (measured,
+// profiles/README.md round 2), a dense copy does not.  The count is read on the device: no host round trip.
+__global__ void relay_records_kernel(const uint64_t* __restrict__ src, uint64_t* __restrict__ dst,
+                                     const uint64_t* __restrict__ total, uint64_t base, uint64_t cap) {
+    const uint64_t cnt = *total - base;  // records of this job (`base` = records of the devices before it, multi-GPU)
+    const uint64_t n = (cnt < cap ? cnt : cap) * (sizeof(RleRecord) / 8);
+    for (uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (uint64_t)gridDim.x * blockDim.x)
+        dst[i] = src[i];
+}
+
 template <typename T>
 __global__ void unpad_kernel(const T* __restrict__ in, QueryView q, T* __restrict__ out) {
     const uint64_t pp = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
@@ -859,13 +901,13 @@ static cudaError_t launch_fused(const FusedParams& fp, const FusedGeom& fg, cuda
 static int run_fused(kbo_index* ix, Workspace* ws, const QueryView& qv, const Geometry& g, uint32_t thr, uint8_t* d_out,
                      uint64_t off0, bool want_masks, bool* done) {
     *done = false;
-    const uint32_t flags = g_ms_flags.load();
+    const uint32_t flags = tuned_ms_flags(ix);
     // bit 4 selects the fused kernel.  It is NOT the default: measured on B200 (profiles/README.md, round 2) it takes
     // 225-300 us per 10^7-base batch where K1 + K2b take 112 + 18 us -- the per-iteration latency of a dependent chain
     // (~1 us at this occupancy) is the same in both, and the two-pass scheme does not save enough iterations.
     if (!k2b_supported(ix->host.k, thr) || (flags & 2u) || !(flags & 16u)) return KBO_OK;
     FusedGeom fg;
-    if (!fused_geometry(g.Lp, ix->host.k, !want_masks, device_sm_count(ix->device), g_chunk_len.load(), &fg)) return KBO_OK;
+    if (!fused_geometry(g.Lp, ix->host.k, !want_masks, device_sm_count(ix->device), tuned_chunk_len(ix), &fg)) return KBO_OK;
     cudaStream_t st = ws->stream;
     FusedParams fp;
     std::memset(&fp, 0, sizeof(fp));
@@ -1170,7 +1212,7 @@ int kbo_query_sbwt_batch_compact(const kbo_index* cix, const uint8_t* concat, co
     Workspace* ws = nullptr;
     rc = acquire_ws(ix, &ws);
     if (rc) return rc;
-    const Geometry g = batch_geometry(total, n_queries);
+    const Geometry g = batch_geometry(ix, total, n_queries);
     const bool intervals = l_out || r_out;
     cudaStream_t st = ws->stream;
     auto body = [&]() -> int {
@@ -1272,7 +1314,7 @@ static int check_launch_size(uint64_t total, uint64_t nq) {
 // several sub-batches.
 static int reserve_ws(Workspace* ws, uint64_t total, uint64_t nq, bool for_find) {
     cudaStream_t st = ws->stream;
-    const Geometry g = batch_geometry(total, nq);
+    const Geometry g = batch_geometry(nullptr, total, nq);
     const uint64_t nw = g.n_tiles_b * 32;
     CUDA_TRY(ws->ascii.ensure(total, st));
     CUDA_TRY(ws->offsets.ensure((nq + 1) * 8, st));
@@ -1312,7 +1354,7 @@ struct HostCallScope {
 };
 static uint64_t pick_parts(const HostCallScope& scope, uint64_t total) {
     if (g_profile_counters.load()) return 1;
-    if (g_parts.load()) return g_parts.load();
+    if (tuned_parts(scope.ix, false)) return tuned_parts(scope.ix, false);
     if (scope.concurrent) return 1;
     return std::min<uint64_t>(4, std::max<uint64_t>(1, total >> 21));
 }
@@ -1345,7 +1387,7 @@ int kbo_matches_batch(const kbo_index* cix, const uint8_t* concat, const uint64_
         cudaStream_t st = ws->stream;
         const uint64_t q0 = cut[s], q1 = cut[s + 1], nq = q1 - q0;
         const uint64_t bytes = offsets[q1] - offsets[q0];
-        const Geometry g = batch_geometry(bytes, nq);
+        const Geometry g = batch_geometry(ix, bytes, nq);
         auto body = [&]() -> int {
             CUDA_TRY(ws->ascii.ensure(bytes, st));
             CUDA_TRY(ws->offsets.ensure((nq + 1) * 8, st));
@@ -1393,7 +1435,7 @@ int kbo_matches(const kbo_index* ix, const uint8_t* query, uint64_t len, double 
 static int matches_device_forked(kbo_index* ix, Workspace* ws, const uint8_t* d_concat, const uint64_t* d_offsets,
                                  const uint64_t* host_offsets, uint64_t nq, uint32_t thr, uint8_t* d_chars) {
     const uint64_t total = host_offsets[nq];
-    uint64_t want = g_dev_parts.load();
+    uint64_t want = tuned_parts(ix, true);
     if (!want) want = std::min<uint64_t>(2, std::max<uint64_t>(1, total >> 22));
     if (g_profile_counters.load() || g_kernel_timing.load()) want = 1;  // instrumentation passes stay serial
     const std::vector<uint64_t> cut = split_queries(host_offsets, nq, want);
@@ -1401,7 +1443,7 @@ static int matches_device_forked(kbo_index* ix, Workspace* ws, const uint8_t* d_
     cudaStream_t user = ws->stream;
     if (np == 1) {
         const bool instrumented = g_profile_counters.load() || g_kernel_timing.load();
-        const Geometry g = batch_geometry(total, nq, instrumented ? 1 : expected_overlap(ix));
+        const Geometry g = batch_geometry(ix, total, nq, instrumented ? 1 : expected_overlap(ix));
         return matches_device(ix, ws, d_concat, d_offsets, nq, g, thr, d_chars, 0);
     }
     while (ws->subs.size() < np) {
@@ -1424,7 +1466,7 @@ static int matches_device_forked(kbo_index* ix, Workspace* ws, const uint8_t* d_
     for (size_t s = 0; s < np; ++s) {
         Workspace* sub = ws->subs[s];
         const uint64_t q0 = cut[s], q1 = cut[s + 1], n = q1 - q0;
-        const Geometry g = batch_geometry(host_offsets[q1] - host_offsets[q0], n);
+        const Geometry g = batch_geometry(ix, host_offsets[q1] - host_offsets[q0], n);
         CUDA_TRY(cudaStreamWaitEvent(sub->stream, ws->ev_fork, 0));
         int rc = matches_device(ix, sub, d_concat, d_offsets + q0, n, g, thr, d_chars, host_offsets[q0]);
         if (rc) return rc;
@@ -1552,6 +1594,8 @@ struct kbo_job {
     uint64_t* rle_offsets = nullptr;
     bool direct = false;
     bool deferred = false;           // multi-GPU: the last K4 kernel waits for the record base of this device's slice
+    bool relay = false;              // direct path, page-locked records buffer: records go through device memory
+    uint64_t relay_cap = 0;          //   (relay_records_kernel); capacity of that device buffer
     uint64_t staged_cap = 0;         // staged path: records the device buffer of wss[0] holds
     int rc = KBO_OK;
     std::string err;
@@ -1615,6 +1659,19 @@ static int find_submit(kbo_index* ix, const uint8_t* concat, const uint64_t* off
         CUDA_TRY(cudaMemsetAsync(d_totals, 0, 8, ws0->stream));
         uint64_t* st_off = nullptr;     // staged path: device copies of the outputs
         RleRecord* st_out = nullptr;
+        RleRecord* rec_out = dv_out;    // where the records kernel writes
+        uint64_t rec_cap = rle_cap;
+        if (job->direct && !defer_finish && dv_out && rle_cap) {
+            cudaPointerAttributes attr;
+            if (cudaPointerGetAttributes(&attr, rle_out) == cudaSuccess && attr.type == cudaMemoryTypeHost) {
+                job->relay = true;
+                job->relay_cap = std::min<uint64_t>(rle_cap, 4 * n_queries + total / 64 + 1024);
+                CUDA_TRY(ws0->out2.ensure(job->relay_cap * sizeof(RleRecord), ws0->stream));
+                rec_out = ws0->out2.as<RleRecord>();
+                rec_cap = job->relay_cap;
+            }
+            cudaGetLastError();
+        }
         if (!job->direct) {
             job->staged_cap = std::min<uint64_t>(rle_cap, 4 * n_queries + total / 64 + 1024);
             CUDA_TRY(ws0->out2.ensure(std::max<uint64_t>(job->staged_cap, 1) * sizeof(RleRecord), ws0->stream));
@@ -1628,7 +1685,7 @@ static int find_submit(kbo_index* ix, const uint8_t* concat, const uint64_t* off
             cudaStream_t st = ws->stream;
             const uint64_t q0 = job->cut[s], q1 = job->cut[s + 1], nq = q1 - q0;
             const uint64_t bytes = offsets[q1] - offsets[q0];
-            const Geometry g = batch_geometry(bytes, nq);
+            const Geometry g = batch_geometry(ix, bytes, nq);
             // the kernels subtract offsets[0] themselves, so the caller's offsets are copied as they are
             CUDA_TRY(cudaMemcpyAsync(ws->ascii.p, concat + offsets[q0], bytes, cudaMemcpyHostToDevice, st));
             CUDA_TRY(cudaMemcpyAsync(ws->offsets.p, offsets + q0, (nq + 1) * 8, cudaMemcpyHostToDevice, st));
@@ -1647,9 +1704,15 @@ static int find_submit(kbo_index* ix, const uint8_t* concat, const uint64_t* off
             }
             if (s > 0) CUDA_TRY(cudaStreamWaitEvent(st, job->wss[s - 1]->ev1, 0));  // its total is this part's base
             else if (np > 1) { /* d_totals[0] was zeroed on this very stream */ }
-            r = run_rle_finish(st, job->rle[s], (job->direct ? dv_off : st_off) + q0, job->direct ? dv_out : st_out,
-                               job->direct ? rle_cap : job->staged_cap, d_totals + s, d_totals + s + 1, s == 0);
+            r = run_rle_finish(st, job->rle[s], (job->direct ? dv_off : st_off) + q0, job->direct ? rec_out : st_out,
+                               job->direct ? rec_cap : job->staged_cap, d_totals + s, d_totals + s + 1, s == 0);
             if (r) return r;
+            if (s + 1 == np && job->relay) {  // (the parts before this one have finished: their events were waited for)
+                relay_records_kernel<<<64, 256, 0, st>>>(reinterpret_cast<const uint64_t*>(rec_out),
+                                                         reinterpret_cast<uint64_t*>(dv_out), d_totals + np, 0, job->relay_cap);
+                LAUNCHED();
+                CUDA_TRY(cudaGetLastError());
+            }
             CUDA_TRY(cudaEventRecord(ws->ev1, st));
             if (s + 1 == np) {
                 CUDA_TRY(cudaMemcpyAsync(ws0->h_count.p, d_totals + np, 8, cudaMemcpyDeviceToHost, st));
@@ -1704,6 +1767,21 @@ static int find_wait(kbo_job* job, uint64_t* n_rle_out) {
                 rc = body();
             }
         }
+        if (!rc && job->relay && count > job->relay_cap && count <= job->rle_cap) {
+            // more records than the device-side estimate: write them again, straight into the caller's buffer
+            auto body = [&]() -> int {
+                RleRecord* dv_out = reinterpret_cast<RleRecord*>(device_visible(job->rle_out));
+                uint64_t* dv_off = reinterpret_cast<uint64_t*>(device_visible(job->rle_offsets));
+                for (size_t s = 0; s < np; ++s) {
+                    int r = run_rle_finish(ws0->stream, job->rle[s], dv_off + job->cut[s], dv_out, job->rle_cap,
+                                           ws0->counters2.as<uint64_t>() + s, nullptr, s == 0);
+                    if (r) return r;
+                }
+                CUDA_TRY(cudaStreamSynchronize(ws0->stream));
+                return KBO_OK;
+            };
+            rc = body();
+        }
         if (!rc && count > job->rle_cap)  // rle_offsets[nq] holds the true count on both paths
             rc = fail(KBO_ERR_BUFFER_TOO_SMALL, "rle capacity too small");
     }
@@ -1739,12 +1817,31 @@ static int find_deferred_finish(kbo_job* job, uint64_t base, bool first_slice) {
     uint64_t* dv_off = reinterpret_cast<uint64_t*>(device_visible(job->rle_offsets));
     ws0->h_count.as<uint64_t>()[1] = base;
     CUDA_TRY(cudaMemcpyAsync(d_totals, ws0->h_count.as<uint64_t>() + 1, 8, cudaMemcpyHostToDevice, ws0->stream));
+    // the record count of this device is known (find_deferred_count): records go through device memory and are copied
+    // densely into the caller's buffer at their final place (see relay_records_kernel)
+    uint64_t mine = 0;
+    for (size_t s = 0; s < np; ++s) mine += (uint32_t)ws0->h_count.as<uint64_t>()[2 + s];
+    const uint64_t room = base < job->rle_cap ? job->rle_cap - base : 0;
+    const uint64_t keep = std::min<uint64_t>(mine, room);
+    RleRecord* rec_out = dv_out;
+    uint64_t rec_cap = job->rle_cap;
+    if (keep && dv_out) {
+        CUDA_TRY(ws0->out2.ensure(keep * sizeof(RleRecord), ws0->stream));
+        rec_out = ws0->out2.as<RleRecord>() - base;  // the kernel indexes records by their global slot
+        rec_cap = base + keep;
+    }
     for (size_t s = 0; s < np; ++s) {
         cudaStream_t st = job->wss[s]->stream;
         if (s > 0) CUDA_TRY(cudaStreamWaitEvent(st, job->wss[s - 1]->ev1, 0));
-        int r = run_rle_finish(st, job->rle[s], dv_off + job->cut[s], dv_out, job->rle_cap, d_totals + s, d_totals + s + 1,
+        int r = run_rle_finish(st, job->rle[s], dv_off + job->cut[s], rec_out, rec_cap, d_totals + s, d_totals + s + 1,
                                first_slice && s == 0);
         if (r) return r;
+        if (s + 1 == np && keep && dv_out) {
+            relay_records_kernel<<<64, 256, 0, st>>>(reinterpret_cast<const uint64_t*>(ws0->out2.p),
+                                                     reinterpret_cast<uint64_t*>(dv_out + base), d_totals + np, base, keep);
+            LAUNCHED();
+            CUDA_TRY(cudaGetLastError());
+        }
         CUDA_TRY(cudaEventRecord(job->wss[s]->ev1, st));
         if (s + 1 == np) CUDA_TRY(cudaMemcpyAsync(ws0->h_count.p, d_totals + np, 8, cudaMemcpyDeviceToHost, st));
     }
@@ -2004,7 +2101,7 @@ int kbo_find_batch_device(const kbo_index* cix, const uint8_t* d_concat, const u
     if (rc) return rc;
     std::lock_guard<std::mutex> lk(ws->mu);
     const bool instrumented = g_profile_counters.load() || g_kernel_timing.load();
-    const Geometry g = batch_geometry(total, n_queries, instrumented ? 1 : expected_overlap(ix));
+    const Geometry g = batch_geometry(ix, total, n_queries, instrumented ? 1 : expected_overlap(ix));
     QueryView qv;
     rc = matches_device(ix, ws, d_concat, d_offsets, n_queries, g, thr, nullptr, 0, true, &qv);
     if (rc) return rc;
@@ -2039,7 +2136,7 @@ static int run_single_full(kbo_index* ix, const uint8_t* seq, uint64_t len, uint
     Workspace* ws = nullptr;
     int rc = acquire_ws(ix, &ws);
     if (rc) return rc;
-    const Geometry g = batch_geometry(len, 1);
+    const Geometry g = batch_geometry(ix, len, 1);
     cudaStream_t st = ws->stream;
     const uint64_t offsets[2] = {0, len};
     out->d.resize(len);
@@ -2074,9 +2171,66 @@ static int run_single_full(kbo_index* ix, const uint8_t* seq, uint64_t len, uint
     return rc;
 }
 
+// One query through K0 -> K1 (with intervals) -> the candidate scan of call_variants on the device
+// (variant_calling.rs:266-272): only the candidates come back to the host, not 9 bytes per base of (d, l, r).
+static int run_single_candidates(kbo_index* ix, const uint8_t* seq, uint64_t len, uint32_t thr,
+                                 std::vector<VariantCandidate64>* out) {
+    DeviceGuard dg(ix->device);
+    if (!dg.ok) return fail(KBO_ERR_CUDA, "cudaSetDevice failed");
+    if (len >= KBO_MAX_LAUNCH_POSITIONS) return fail(KBO_ERR_BATCH_TOO_LARGE, "sequence too long for one launch");
+    Workspace* ws = nullptr;
+    int rc = acquire_ws(ix, &ws);
+    if (rc) return rc;
+    const Geometry g = batch_geometry(ix, len, 1);
+    cudaStream_t st = ws->stream;
+    const uint64_t offsets[2] = {0, len};
+    auto body = [&]() -> int {
+        CUDA_TRY(ws->ascii.ensure(len, st));
+        CUDA_TRY(ws->offsets.ensure(16, st));
+        CUDA_TRY(ws->counters2.ensure(8, st));
+        CUDA_TRY(ws->h_count.ensure(16));
+        CUDA_TRY(cudaMemcpyAsync(ws->ascii.p, seq, len, cudaMemcpyHostToDevice, st));
+        CUDA_TRY(cudaMemcpyAsync(ws->offsets.p, offsets, 16, cudaMemcpyHostToDevice, st));
+        QueryView qv;
+        int rc2 = run_pack(ws, ws->ascii.as<uint8_t>(), ws->offsets.as<uint64_t>(), 1, g, &qv);
+        if (rc2) return rc2;
+        rc2 = run_ms(ix, ws, qv, g, true);
+        if (rc2) return rc2;
+        uint32_t cap = (uint32_t)std::min<uint64_t>(len / 16 + 4096, 1u << 26);
+        for (int attempt = 0; attempt < 2; ++attempt) {
+            CUDA_TRY(ws->out2.ensure((uint64_t)cap * sizeof(VariantCandidate), st));
+            CUDA_TRY(cudaMemsetAsync(ws->counters2.p, 0, 4, st));
+            // a single query has its only separator at position len: padded == unpadded below len
+            variant_candidates_kernel<<<(unsigned)((len + 255) / 256), 256, 0, st>>>(
+                ws->ms.as<uint8_t>(), ws->l.as<uint32_t>(), ws->r.as<uint32_t>(), len, ix->host.k, thr,
+                ws->out2.as<VariantCandidate>(), cap, ws->counters2.as<unsigned int>());
+            LAUNCHED();
+            CUDA_TRY(cudaGetLastError());
+            CUDA_TRY(cudaMemcpyAsync(ws->h_count.p, ws->counters2.p, 4, cudaMemcpyDeviceToHost, st));
+            CUDA_TRY(cudaStreamSynchronize(st));
+            const uint32_t n = *ws->h_count.as<uint32_t>();
+            if (n <= cap) {
+                std::vector<VariantCandidate> tmp(n);
+                if (n) CUDA_TRY(cudaMemcpy(tmp.data(), ws->out2.p, (size_t)n * sizeof(VariantCandidate), cudaMemcpyDeviceToHost));
+                std::sort(tmp.begin(), tmp.end(), [](const VariantCandidate& a, const VariantCandidate& b) { return a.i < b.i; });
+                out->clear();
+                out->reserve(n);
+                for (const VariantCandidate& c : tmp) out->push_back(VariantCandidate64{c.i, c.j, c.node});
+                return KBO_OK;
+            }
+            cap = n;  // more candidates than the first guess: once more with room for all of them
+        }
+        return fail(KBO_ERR_CUDA, "candidate scan did not converge");
+    };
+    rc = body();
+    release_ws(ix, ws);
+    return rc;
+}
+
 // lib.rs:547-573 given the full-length MS of ref_seq against the assembly index (computed by the caller)
 static int call_impl(kbo_index* query_index, const uint8_t* ref_seq, uint64_t len, double max_error_prob,
-                     const kbo_build_opts* opts, const HostMs& ms, std::vector<VariantRec>* variants) {
+                     const kbo_build_opts* opts, const std::vector<VariantCandidate64>& cands,
+                     std::vector<VariantRec>* variants) {
     kbo_build_opts o;
     if (opts) o = *opts; else { kbo_default_build_opts(&o); o.build_select = 1; }
     uint64_t thr = 0;
@@ -2110,13 +2264,8 @@ static int call_impl(kbo_index* query_index, const uint8_t* ref_seq, uint64_t le
                                               nullptr, nullptr);
         if (r2 && !inner_rc) inner_rc = r2;
     };
-    MsArrays view;
-    view.d = ms.d.data();
-    view.l = ms.l.data();
-    view.r = ms.r.data();
-    view.n = len;
     try {
-        *variants = call_variants(query_index->host, view, ref_seq, len, thr, kmer_ms);
+        *variants = call_variants_from(query_index->host, cands, ref_seq, len, thr, kmer_ms);
     } catch (const RefinePanic& p) {
         kbo_index_free(ref_index);
         return fail(KBO_ERR_PANIC, p.what);
@@ -2131,11 +2280,14 @@ int kbo_call(const kbo_index* cix, const uint8_t* ref_seq, uint64_t len, double 
     kbo_index* ix = const_cast<kbo_index*>(cix);
     if (!ix || !n_variants) return fail(KBO_ERR_BAD_ARGUMENT, "null argument");
     if (!ref_seq || len == 0) return fail(KBO_ERR_EMPTY_INPUT, "empty reference sequence");
-    HostMs ms;
-    int rc = run_single_full(ix, ref_seq, len, 0, &ms);  // variant_calling.rs:266
+    uint64_t thr = 0;
+    int rc = host_threshold(ix->host.k, ix->host.n_kmers, 4, max_error_prob, &thr);  // variant_calling.rs:260
+    if (rc) return rc;
+    std::vector<VariantCandidate64> cands;
+    rc = run_single_candidates(ix, ref_seq, len, (uint32_t)std::min<uint64_t>(thr, 255), &cands);  // variant_calling.rs:266-272
     if (rc) return rc;
     std::vector<VariantRec> vars;
-    rc = call_impl(ix, ref_seq, len, max_error_prob, sbwt_build_opts, ms, &vars);
+    rc = call_impl(ix, ref_seq, len, max_error_prob, sbwt_build_opts, cands, &vars);
     if (rc) return rc;
     *n_variants = vars.size();
     if (vars.size() > cap_variants) return fail(KBO_ERR_BUFFER_TOO_SMALL, "variant capacity too small");
@@ -2180,10 +2332,13 @@ int kbo_map(const kbo_index* cix, const uint8_t* ref_seq, uint64_t len, double m
     view.n = len;
     try {
         if (do_fill_gaps)  // lib.rs:743-744; gaps are independent: bridged on build_opts.num_threads host threads
-            fill_gaps(&aln, view, ref_seq, len, ix->host, thr, max_error_prob, std::max<uint32_t>(1, o.num_threads));
+            fill_gaps(&aln, view, ref_seq, len, ix->host, thr, max_error_prob, tuned_refine_threads(ix));
         if (do_call_variants) {                                                             // lib.rs:749-751
             std::vector<VariantRec> vars;
-            rc = call_impl(ix, ref_seq, len, max_error_prob, &o, ms, &vars);
+            uint64_t call_thr = 0;
+            rc = host_threshold(ix->host.k, ix->host.n_kmers, 4, max_error_prob, &call_thr);  // variant_calling.rs:260
+            if (rc) return rc;
+            rc = call_impl(ix, ref_seq, len, max_error_prob, &o, find_variant_candidates(view, len, ix->host.k, call_thr), &vars);
             if (rc) return rc;
             add_variants(&aln, vars);
         }
@@ -2292,6 +2447,19 @@ int kbo_get_ms_counters(const kbo_index* cix, kbo_ms_counters* out) {
     return KBO_OK;
 }
 int kbo_set_chunk_len(uint32_t chunk_len) { g_chunk_len = chunk_len; return KBO_OK; }
+int kbo_set_refine_threads(uint32_t n) { g_refine_threads = n > 256 ? 256 : n; return KBO_OK; }
+int kbo_index_set_tuning(kbo_index* ix, int key, int64_t value) {
+    if (!ix) return fail(KBO_ERR_BAD_ARGUMENT, "index is null");
+    switch (key) {
+        case KBO_TUNE_CHUNK_LEN: ix->tune.chunk_len = value; break;
+        case KBO_TUNE_PIPELINE_PARTS: ix->tune.pipeline_parts = value > 64 ? 64 : value; break;
+        case KBO_TUNE_DEVICE_PARTS: ix->tune.device_parts = value > 16 ? 16 : value; break;
+        case KBO_TUNE_MS_FLAGS: ix->tune.ms_flags = value < 0 ? -1 : (value & 0xff); break;
+        case KBO_TUNE_REFINE_THREADS: ix->tune.refine_threads = value > 256 ? 256 : value; break;
+        default: return fail(KBO_ERR_BAD_ARGUMENT, "unknown tuning key");
+    }
+    return KBO_OK;
+}
 int kbo_set_device_parts(uint32_t parts) { g_dev_parts = parts > 16 ? 16 : parts; return KBO_OK; }
 int kbo_set_pipeline_parts(uint32_t parts) { g_parts = parts > 64 ? 64 : parts; return KBO_OK; }
 int kbo_set_host_builder(int enabled) { g_host_builder = enabled ? 1 : 0; return KBO_OK; }

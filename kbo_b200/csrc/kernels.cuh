@@ -1494,6 +1494,47 @@ __global__ void translate_i64_kernel(const int64_t* __restrict__ d, uint64_t n, 
 }
 
 // ---------------------------------------------------------------------------
+// Refinement helpers on the device.
+//
+// variant_candidates_kernel: the candidate scan of call_variants (variant_calling.rs:268-272) on K1's (d, l, r) of
+// ONE query: position i is a candidate when ms[i] < ms[i-1], ms[i-1] >= thr and ms[i] < thr, and some j in
+// (i, min(i + k + 1, len)) has ms[j] >= thr with a one-node interval; the first such j is reported.  Thread per
+// position; candidates are appended through an atomic counter (the host sorts the few of them by i).
+// relative_to_ref_kernel: format::relative_to_ref (format.rs:266-287), byte per thread.
+// ---------------------------------------------------------------------------
+struct VariantCandidate {
+    uint32_t i, j, node, pad;  // query position of the drop, position of the unique match, its colex rank
+};
+
+__global__ void variant_candidates_kernel(const uint8_t* __restrict__ d, const uint32_t* __restrict__ l,
+                                          const uint32_t* __restrict__ r, uint64_t len, uint32_t k, uint32_t thr,
+                                          VariantCandidate* __restrict__ out, uint32_t cap, unsigned int* __restrict__ count) {
+    const uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i == 0 || i >= len) return;
+    const uint32_t cur = d[i], prev = d[i - 1];
+    if (!(cur < prev && prev >= thr && cur < thr)) return;
+    const uint64_t stop = i + k + 1 < len ? i + k + 1 : len;
+    for (uint64_t j = i + 1; j < stop; ++j) {
+        if (d[j] >= thr && r[j] - l[j] == 1u) {
+            const unsigned int slot = atomicAdd(count, 1u);
+            if (slot < cap) out[slot] = VariantCandidate{(uint32_t)i, (uint32_t)j, l[j], 0u};
+            return;
+        }
+    }
+}
+
+__global__ void relative_to_ref_kernel(const uint8_t* __restrict__ ref, const uint8_t* __restrict__ aln, uint64_t n,
+                                       uint8_t* __restrict__ out) {
+    const uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    const uint8_t a = aln[i];
+    uint8_t o = a;
+    if (a == 'M' || a == 'R' || a == 'I') o = ref[i];
+    else if (a == 'X' || a == 'D' || a == '-') o = '-';
+    out[i] = o;
+}
+
+// ---------------------------------------------------------------------------
 // G: derandomize_ms_vec (derandomize.rs:269-288) for one ARBITRARY MS vector
 // (values <= k, no monotonicity assumed), exact i64 output.
 //

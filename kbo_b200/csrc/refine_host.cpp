@@ -194,26 +194,30 @@ bool resolve_variant(const uint8_t* query_kmer, const uint8_t* ref_kmer, const u
     return true;
 }
 
-std::vector<VariantRec> call_variants(const HostIndex& sbwt_ref, const MsArrays& ms, const uint8_t* query,
-                                      uint64_t len, uint64_t thr, const KmerMsFn& kmer_ms) {
-    const uint32_t k = sbwt_ref.k;
-    // pass 1: candidates = significant drops followed (within k) by a significant unique match
-    struct Cand { uint64_t i, j; };
-    std::vector<Cand> cands;
+std::vector<VariantCandidate64> find_variant_candidates(const MsArrays& ms, uint64_t len, uint32_t k, uint64_t thr) {
+    // candidates = significant drops followed (within k) by a significant unique match
+    std::vector<VariantCandidate64> cands;
     for (uint64_t i = 1; i < len; ++i) {
         if (!(ms.d[i] < ms.d[i - 1] && ms.d[i - 1] >= thr && ms.d[i] < thr)) continue;
         const uint64_t stop = std::min<uint64_t>(i + k + 1, len);
         for (uint64_t j = i + 1; j < stop; ++j) {
             if (ms.d[j] >= thr && ms.r[j] - ms.l[j] == 1) {
-                cands.push_back(Cand{i, j});
+                cands.push_back(VariantCandidate64{i, j, ms.l[j]});
                 break;
             }
         }
     }
+    return cands;
+}
+
+std::vector<VariantRec> call_variants_from(const HostIndex& sbwt_ref, const std::vector<VariantCandidate64>& cands,
+                                           const uint8_t* query, uint64_t len, uint64_t thr, const KmerMsFn& kmer_ms) {
+    (void)len;
+    const uint32_t k = sbwt_ref.k;
     std::vector<VariantRec> calls;
     if (cands.empty()) return calls;
-    // pass 2: the k-mer ending at j in the query ('$'-padded at the start, variant_calling.rs:46-59) and
-    // the index k-mer of the unique node; their MS against the two indexes in ONE batch each
+    // the k-mer ending at j in the query ('$'-padded at the start, variant_calling.rs:46-59) and the index k-mer of
+    // the unique node; their MS against the two indexes in ONE batch each
     const uint64_t nc = cands.size();
     Bytes qk(nc * k), rk(nc * k), ms_q_vs_ref(nc * k), ms_r_vs_query(nc * k);
     for (uint64_t c = 0; c < nc; ++c) {
@@ -226,11 +230,10 @@ std::vector<VariantRec> call_variants(const HostIndex& sbwt_ref, const MsArrays&
             std::fill(dst, dst + dollars, (uint8_t)'$');
             std::copy(query, query + j + 1, dst + dollars);
         }
-        sbwt_ref.access_kmer(ms.l[j], rk.data() + c * k);
+        sbwt_ref.access_kmer(cands[c].node, rk.data() + c * k);
     }
     kmer_ms(0, qk.data(), nc, k, ms_q_vs_ref.data());
     kmer_ms(1, rk.data(), nc, k, ms_r_vs_query.data());
-    // pass 3
     for (uint64_t c = 0; c < nc; ++c) {
         VariantRec v;
         v.query_pos = cands[c].i;
@@ -239,6 +242,11 @@ std::vector<VariantRec> call_variants(const HostIndex& sbwt_ref, const MsArrays&
             calls.push_back(v);
     }
     return calls;
+}
+
+std::vector<VariantRec> call_variants(const HostIndex& sbwt_ref, const MsArrays& ms, const uint8_t* query,
+                                      uint64_t len, uint64_t thr, const KmerMsFn& kmer_ms) {
+    return call_variants_from(sbwt_ref, find_variant_candidates(ms, len, sbwt_ref.k, thr), query, len, thr, kmer_ms);
 }
 
 // ---------------------------------------------------------------------------

@@ -47,6 +47,17 @@ bool resolve_variant(const uint8_t* query_kmer, const uint8_t* ref_kmer, const u
                      const uint8_t* ms_vs_ref_d, uint32_t k, uint64_t significant_match_threshold,
                      std::vector<uint8_t>* query_chars, std::vector<uint8_t>* ref_chars);
 
+// A variant candidate (variant_calling.rs:268-272): a significant drop of the MS at query position i followed, within
+// k positions, by a significant match at j whose interval is the single node `node`.
+struct VariantCandidate64 {
+    uint64_t i, j, node;
+};
+// the candidate scan on host arrays (kbo::map, which needs the arrays on the host anyway for fill_gaps)
+std::vector<VariantCandidate64> find_variant_candidates(const MsArrays& ms_vs_ref, uint64_t len, uint32_t k, uint64_t threshold);
+// call_variants given the candidates in increasing i (kbo::call finds them on the device: variant_candidates_kernel)
+std::vector<VariantRec> call_variants_from(const HostIndex& sbwt_ref, const std::vector<VariantCandidate64>& cands,
+                                           const uint8_t* query, uint64_t len, uint64_t threshold, const KmerMsFn& kmer_ms);
+
 // variant_calling::call_variants (variant_calling.rs:249-294).  `ms_vs_ref` = MS of `query` against
 // `sbwt_ref` (already computed on the GPU); `threshold` = random_match_threshold(k, sbwt_ref.n_kmers, 4, p).
 std::vector<VariantRec> call_variants(const HostIndex& sbwt_ref, const MsArrays& ms_vs_ref, const uint8_t* query,

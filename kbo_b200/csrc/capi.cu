@@ -696,6 +696,9 @@ static int run_ms(kbo_index* ix, Workspace* ws, const QueryView& qv, const Geome
     if (intervals) {
         if (count) ms_kernel<true, true><<<blocks, threads, 0, st>>>(mp);
         else ms_kernel<true, false><<<blocks, threads, 0, st>>>(mp);
+    } else if ((mp.flags & 32u) && ix->view.rank2) {  // bit 5: two bases per probe in K1 (ms_pairs_kernel)
+        if (count) ms_pairs_kernel<true><<<blocks, threads, 0, st>>>(mp);
+        else ms_pairs_kernel<false><<<blocks, threads, 0, st>>>(mp);
     } else {
         if (count) ms_kernel<false, true><<<blocks, threads, 0, st>>>(mp);
         else ms_kernel<false, false><<<blocks, threads, 0, st>>>(mp);

@@ -47,7 +47,8 @@ namespace kbo_b200 {
 // ---------------------------------------------------------------------------
 struct IndexView {
     const uint64_t* rank;
-    const uint64_t* rank2;  // optional: 16 rows (first base | second base << 2) in the same word format, for TWO bases per
+    const uint64_t* rank2;  // optional (== rank + 4 * rank_stride when present: the rows follow rank's in one allocation):
+                            // 16 rows (first base | second base << 2) in the same word format, for TWO bases per
                             // probe: word b of row (a, c) = (C[c] + rank_c(C[a]) + #{i < 32b : node i has label a and its
                             // a-successor has label c}) << 32 | those 32 bits, so that
                             // extend_right(extend_right([l, r), a), c) = [rank2(l), rank2(r)) with one load per end
@@ -503,6 +504,142 @@ __global__ void __launch_bounds__(256, 6) ms_kernel(MsParams p) {
                     }
                 }
             }
+        }
+    }
+    if (COUNT) {
+        atomicAdd(p.counters + CNT_ATTEMPTS, cnt_att);
+        atomicAdd(p.counters + CNT_SPLIT, cnt_split);
+        atomicAdd(p.counters + CNT_CONTRACT, cnt_con);
+        atomicAdd(p.counters + CNT_EXTRA_LCS, cnt_extra);
+        atomicAdd(p.counters + CNT_PROCESSED, cnt_proc);
+        atomicAdd(p.counters + CNT_EMITTED, cnt_emit);
+        atomicAdd(p.counters + CNT_ATT_EMIT, cnt_att_e);
+        atomicAdd(p.counters + CNT_SPLIT_EMIT, cnt_split_e);
+        atomicAdd(p.counters + CNT_CON_EMIT, cnt_con_e);
+        atomicAdd(p.counters + CNT_EXTRA_EMIT, cnt_extra_e);
+    }
+}
+
+// K1p: K1 without intervals, probing TWO bases per rank word (IndexView::rank2) while the lane is in a matching
+// stretch.  One code path per iteration: the lane picks the row set (rank2 / rank) and the advance (2 / 1) by select,
+// not by branch, so pair lanes and single lanes of a warp execute the same instructions.  An empty pair says that one
+// of the two extensions fails: the lane retries the first base alone (no contraction).  After any failed probe the
+// lane probes single bases until two in a row have extended at the first try (noise stretches fail at every base).
+template <bool COUNT>
+__global__ void __launch_bounds__(256, 6) ms_pairs_kernel(MsParams p) {
+    __shared__ __align__(16) uint8_t ms_stage[256 * 36];
+    const uint64_t g = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    unsigned long long cnt_att = 0, cnt_split = 0, cnt_con = 0, cnt_extra = 0, cnt_proc = 0, cnt_emit = 0;
+    unsigned long long cnt_att_e = 0, cnt_split_e = 0, cnt_con_e = 0, cnt_extra_e = 0;
+    // state of the lane's chain (declared here: the main loop below is executed by the WHOLE warp, see there)
+    const uint32_t n = p.ix.n, k = p.ix.k;
+    uint32_t l = 0, r = n, d = 0, bp = 0, bp_emit = 0, bp_end = 0, iw = 0;
+    uint64_t qw = 0, wbase = 0;
+    const uint64_t* __restrict__ qptr = p.q.pack;
+    const uint32_t* __restrict__ iptr = p.q.inv;
+    uint8_t* msw = p.ms;
+    if (g < p.n_chunks) {
+        const uint64_t start = g * p.chunk_len;
+        const uint64_t remain = p.q.Lp - start;
+        const uint32_t len = remain < p.chunk_len ? (uint32_t)remain : p.chunk_len;
+        uint32_t warm = start >= (uint64_t)(k - 1) ? k - 1 : (uint32_t)start;
+        for (uint64_t w = start >> 5; warm && w-- > ((start - warm) >> 5);) {  // chunk starts are multiples of 32
+            uint32_t iv = __ldg(p.q.inv + w);
+            if (w == ((start - warm) >> 5)) iv &= ~0u << ((start - warm) & 31);
+            if (iv) {
+                warm = (uint32_t)(start - (w * 32 + (31 - __clz((int)iv)) + 1));
+                break;
+            }
+        }
+        if (p.ix.pref && warm >= PREF_LEN) {
+            const uint64_t first = start - warm;
+            const uint32_t sh = 2 * (uint32_t)(first & 31);
+            uint64_t bits = __ldg(p.q.pack + (first >> 5)) >> sh;
+            if (sh > 64 - 2 * PREF_LEN) bits |= __ldg(p.q.pack + (first >> 5) + 1) << (64 - sh);
+            const uint4 s = __ldg(p.ix.pref + ((uint32_t)bits & ((1u << (2 * PREF_LEN)) - 1u)));
+            l = s.x; r = s.y; d = s.z;
+            warm -= PREF_LEN;
+        }
+        const uint64_t pos0 = start - warm;
+        wbase = pos0 >> 5;
+        qptr = p.q.pack + wbase;
+        iptr = p.q.inv + wbase;
+        msw = p.ms + (wbase << 5);
+        bp = (uint32_t)(pos0 & 31);
+        bp_emit = bp + warm;
+        bp_end = bp_emit + len;
+        qw = __ldg(qptr) >> (2 * bp);
+        iw = __ldg(iptr) >> bp;
+    }
+    {
+        const uint32_t stride = p.ix.rank_stride;
+        uint32_t cool = 0;  // successful advances left before the lane probes pairs again (set by every failed probe)
+        uint8_t* const stg = ms_stage + threadIdx.x * 36u;
+        while (bp < bp_end) {
+          {
+            uint32_t adv = 1, dA = 0, dB = 0;
+            if (iw & 1u) {
+                l = 0; r = n; d = 0;
+                cool = 0;
+            } else {
+                // Integer arithmetic on `two` and ONE base pointer (rank2's 16 rows follow rank's 4 rows in the index
+                // allocation), so pair lanes and single lanes run the same instructions: with a pointer select the
+                // compiler emitted the probe twice, once per kind of lane, and the warp executed both.
+                const uint32_t two = (uint32_t)(cool == 0) & (~(iw >> 1) & 1u) & (uint32_t)((bp & 31u) != 31u) &
+                                     (uint32_t)(bp + 1 < bp_end);
+                const uint32_t rowoff = (((uint32_t)qw & (3u + 12u * two)) + 4u * two) * stride;
+                const uint32_t bl = l >> 5, br = r >> 5;
+                const uint64_t wl = __ldg(p.ix.rank + (rowoff + bl));
+                const uint64_t wr = (br == bl) ? wl : __ldg(p.ix.rank + (rowoff + br));
+                const uint32_t nl = (uint32_t)(wl >> 32) + __popc((uint32_t)wl & ((1u << (l & 31)) - 1u));
+                const uint32_t nr = (uint32_t)(wr >> 32) + __popc((uint32_t)wr & ((1u << (r & 31)) - 1u));
+                if (COUNT) {
+                    const bool sp = (bl >> 2) != (br >> 2);
+                    ++cnt_att; cnt_split += sp;
+                    if (bp + two >= bp_emit) { ++cnt_att_e; cnt_split_e += sp; }
+                }
+                if (nl < nr) {
+                    l = nl; r = nr;
+                    dA = d + 1 < k ? d + 1 : k;
+                    dB = d + 2 < k ? d + 2 : k;
+                    adv = 1u + two;
+                    d = two ? dB : dA;
+                    cool = cool ? cool - 1u : 0u;
+                } else {
+                    cool = 2;  // single probes until two bases in a row have extended at the first try
+                    adv = (two | d) ? 0u : 1u;  // (d == 0 and a single base that matches nothing: emitted with d == 0)
+                    if (!two && d != 0) {
+                        // contract_left to the largest depth that changes the interval: t = max(LCS[l], LCS[r])
+                        const uint32_t el = __ldg(p.ix.links + l), er = __ldg(p.ix.links + r);
+                        const bool scanned = ms_contract(p.ix, el, er, l, r, d);
+                        if (COUNT) {
+                            ++cnt_con; cnt_extra += scanned;
+                            if (bp >= bp_emit) { ++cnt_con_e; cnt_extra_e += scanned; }
+                        }
+                    }
+                }
+            }
+            if (adv) {
+                if (COUNT) { cnt_proc += adv; cnt_emit += (bp >= bp_emit) + (adv == 2 && bp + 1 >= bp_emit); }
+                if (bp >= bp_emit) stg[bp & 31u] = (uint8_t)(adv == 2 ? dA : d);
+                if (adv == 2 && bp + 1 >= bp_emit) stg[(bp + 1) & 31u] = (uint8_t)dB;
+                bp += adv;
+                qw >>= 2 * adv;
+                iw >>= adv;
+                if ((bp & 31) == 0 || bp == bp_end) {
+                    if (bp > bp_emit) {  // flush the 32 (or last, partial) staged positions
+                        const uint32_t* w = reinterpret_cast<const uint32_t*>(stg);
+                        uint4* dst = reinterpret_cast<uint4*>(msw + ((bp - 1) & ~31u));
+                        dst[0] = make_uint4(w[0], w[1], w[2], w[3]);
+                        dst[1] = make_uint4(w[4], w[5], w[6], w[7]);
+                    }
+                    if (bp < bp_end) {
+                        qw = __ldg(qptr + (bp >> 5));
+                        iw = __ldg(iptr + (bp >> 5));
+                    }
+                }
+            }
+          }
         }
     }
     if (COUNT) {

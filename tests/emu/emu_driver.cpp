@@ -68,10 +68,13 @@ static void finish(EmuIndex* e) {
         emu_launch_seq((unsigned)((stride + 127) / 128), 128, [&]() { rank2_bits_kernel(e->view, rows2.data()); });
         uint32_t run = 0;
         for (uint64_t i = 0; i < words; ++i) { prefix[i] = run; run += (uint32_t)__builtin_popcount(rows2[i]); }
-        e->rank2.assign(words, 0);
+        // rank2's rows follow rank's four rows in ONE array (as in the device allocation; K1p relies on it)
+        e->rank2.assign(4 * stride + words, 0);
+        std::memcpy(e->rank2.data(), e->lay.rank.data(), 4 * stride * 8);
         emu_launch_seq((unsigned)((words + 255) / 256), 256,
-                       [&]() { compose_rank2_kernel(e->view, rows2.data(), prefix.data(), e->rank2.data()); });
-        e->view.rank2 = e->rank2.data();
+                       [&]() { compose_rank2_kernel(e->view, rows2.data(), prefix.data(), e->rank2.data() + 4 * stride); });
+        e->view.rank = e->rank2.data();
+        e->view.rank2 = e->rank2.data() + 4 * stride;
     }
     const uint32_t n = e->view.n;
     e->links.assign((size_t)n + 1, 0);
@@ -149,6 +152,12 @@ static void stage_and_ms(EmuIndex* e, const uint8_t* concat, const uint64_t* off
     mp.r_out = intervals ? s->r.data() : nullptr;
     mp.counters = counters;
     const unsigned threads = 256, blocks = (unsigned)((g.n_chunks + threads - 1) / threads);
+    if (!intervals && (mp.flags & 32u) && mp.ix.rank2) {  // K1p uses warp collectives: one host thread per lane
+        emu_launch_par(blocks, threads, [&]() {
+            if (counters) ms_pairs_kernel<true>(mp); else ms_pairs_kernel<false>(mp);
+        });
+        return;
+    }
     emu_launch_seq(blocks, threads, [&]() {
         if (intervals) {
             if (counters) ms_kernel<true, true>(mp); else ms_kernel<true, false>(mp);

@@ -81,6 +81,7 @@ inline unsigned __ballot_sync(unsigned, bool pred) {
     emu_warp->bar.arrive_and_wait();
     return r;
 }
+inline int __any_sync(unsigned m, bool pred) { return __ballot_sync(m, pred) != 0; }
 inline void __syncwarp(unsigned = 0xffffffffu) { emu_warp->bar.arrive_and_wait(); }
 inline void __syncthreads() { emu_block->bar->arrive_and_wait(); }
 

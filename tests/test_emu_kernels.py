@@ -150,6 +150,18 @@ def test_ms_two_bases_per_probe(k):
                ref[20_000:20_257], b"ACGT" * 40 + b"$" + ref[100:400], asm[500:2500]]
     want = [o.query_sbwt(q)[0] for q in queries]
     attempts = {}
+    # K1p (flag bit 5): two bases per probe inside K1; same lengths, fewer probes
+    E.lib().emu_set_ms_flags(32)
+    try:
+        e = E.EmuIndex.build([asm], k=k)
+        for chunk_len in (32, 64, 96, 1024):
+            d, _, _, off, cnt = e.query_sbwt_batch(queries, chunk_len=chunk_len, intervals=False, counters=True)
+            for i, w in enumerate(want):
+                assert np.array_equal(d[int(off[i]):int(off[i + 1])].astype(np.uint64), w), ("pairs", k, chunk_len, i)
+            assert cnt[5] == sum(len(q) + 1 for q in queries)
+            attempts[("pairs", chunk_len)] = int(cnt[0])
+    finally:
+        E.lib().emu_set_ms_flags(0)
     try:
         for on in (1, 0):
             E.lib().emu_set_rank2(on)
@@ -165,6 +177,8 @@ def test_ms_two_bases_per_probe(k):
     # (K1 itself probes one base at a time -- the pair probes through rank2 live in the fused kernel, which the
     # matches / find tests below run; here rank2 must simply not change anything)
     assert attempts[(1, 64)] == attempts[(0, 64)]
+    if k >= 31:
+        assert attempts[("pairs", 64)] < 0.8 * attempts[(1, 64)]
 
 
 def test_ms_tiny_index_and_counters():

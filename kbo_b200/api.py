@@ -644,6 +644,15 @@ def map(ref_seq, query_index, map_opts=None):
     return out[:len(r)].tobytes()
 
 
+def map_unrefined(ref_seq, query_index, max_error_prob=0.0000001, format=True):
+    """kbo::map with fill_gaps = call_variants = false (lib.rs:726-738, 756-760), entirely on the device."""
+    r = _u8(ref_seq)
+    out = np.zeros(max(len(r), 1), dtype=np.uint8)
+    _check(load_library().kbo_map_unrefined(query_index._h, _p(r, C.c_uint8), len(r), max_error_prob, int(format),
+                                            _p(out, C.c_uint8)))
+    return out[:len(r)].tobytes()
+
+
 # ---------------------------------------------------------------------------- instrumentation ---
 def set_profile_counters(enabled):
     _check(load_library().kbo_set_profile_counters(int(enabled)))

@@ -7,6 +7,9 @@
 // point needs a CUDA device and fails with KBO_ERR_CUDA otherwise.
 // ===========================================================================
 #include <atomic>
+#include <chrono>
+#include <cstdio>
+#include <cstdlib>
 #include <condition_variable>
 #include <functional>
 #include <thread>
@@ -457,8 +460,22 @@ struct TmpBufs {
 
 // device_only: the index will only serve K1 on short queries (the per-call index of `ref_seq` in kbo::call): no
 // host copy of the SubsetMatrix form, no prefix-state table.
+// KBO_BUILD_TIMING=1 in the environment prints where an index construction spends its time (stderr)
+struct BuildTimer {
+    bool on = std::getenv("KBO_BUILD_TIMING") != nullptr;
+    std::chrono::steady_clock::time_point t0 = std::chrono::steady_clock::now();
+    void lap(const char* what) {
+        if (!on) return;
+        cudaDeviceSynchronize();
+        const auto t1 = std::chrono::steady_clock::now();
+        std::fprintf(stderr, "[kbo build] %-28s %8.2f ms\n", what, std::chrono::duration<double, std::milli>(t1 - t0).count());
+        t0 = t1;
+    }
+};
+
 static int build_index_gpu(kbo_index* ix, const uint8_t* const* seqs, const uint64_t* lens, uint64_t n_seqs, uint32_t k,
                            bool revcomp, bool keep_nodes, bool device_only = false) {
+    BuildTimer bt;
     uint64_t total = 0;
     std::vector<uint64_t> offsets(n_seqs + 1, 0);
     for (uint64_t i = 0; i < n_seqs; ++i) { total += lens[i]; offsets[i + 1] = total; }
@@ -498,6 +515,7 @@ static int build_index_gpu(kbo_index* ix, const uint8_t* const* seqs, const uint
     kmer_keys_kernel<<<(unsigned)((Lp + 255) / 256), 256>>>(d_pack, d_inv, Lp, k, revcomp ? 1 : 0, d_keys, d_keys_rc, d_flags);
     LAUNCHED();
     CUDA_TRY(cudaGetLastError());
+    bt.lap("copy-in, pack, k-mer keys");
     // compaction of the valid k-mers (forward, then reverse complements)
     size_t tb = 0, need = 0;
     void* d_tmp = nullptr;
@@ -526,6 +544,7 @@ static int build_index_gpu(kbo_index* ix, const uint8_t* const* seqs, const uint
         CUDA_TRY(cub::DeviceSelect::Unique(d_tmp, need, d_sorted, d_R, d_count, (int64_t)n_valid));
         CUDA_TRY(cudaMemcpy(&nR, d_count, 8, cudaMemcpyDeviceToHost));
     }
+    bt.lap("select, sort, unique");
     // dummy nodes: few, made on the host from the k-mers that have no predecessor
     std::vector<uint64_t> h_src;
     if (nR) {
@@ -560,6 +579,7 @@ static int build_index_gpu(kbo_index* ix, const uint8_t* const* seqs, const uint
     CUDA_TRY(tmp.alloc(&d_Plen, n));
     merge_nodes_kernel<<<(unsigned)((n + 255) / 256), 256>>>(d_R, nR, d_Dkey, d_Dlen, nD, k, d_Pkey, d_Plen);
     LAUNCHED();
+    bt.lap("dummies, merge");
     // final device arrays
     const uint64_t nblk = (n >> 5) + 2;
     const uint64_t stride = (nblk + 3) & ~3ull;
@@ -599,7 +619,8 @@ static int build_index_gpu(kbo_index* ix, const uint8_t* const* seqs, const uint
     ix->view.lcs = ix->d_lcs;
     ix->view.n = (uint32_t)n;
     ix->view.k = k;
-    if (device_only) return build_links(ix, n, false);
+    bt.lap("lcs, labels, rank words");
+    if (device_only) { const int rc = build_links(ix, n, false); bt.lap("links (device-only index)"); return rc; }
     std::vector<uint32_t> rows32((size_t)(4 * stride));
     CUDA_TRY(cudaMemcpy(rows32.data(), d_rows32, 4 * stride * 4, cudaMemcpyDeviceToHost));
     h.lcs.resize((size_t)n);
@@ -620,7 +641,10 @@ static int build_index_gpu(kbo_index* ix, const uint8_t* const* seqs, const uint
         CUDA_TRY(cudaMemcpy(h.node_hi.data(), d_Pkey, n * 8, cudaMemcpyDeviceToHost));
         CUDA_TRY(cudaMemcpy(h.node_len.data(), d_Plen, n, cudaMemcpyDeviceToHost));
     }
-    return build_links(ix, n);
+    bt.lap("host mirror (rows, lcs, nodes)");
+    const int rc_links = build_links(ix, n);
+    bt.lap("rank2, links, prefix table");
+    return rc_links;
 }
 
 // ---------------------------------------------------------------------------
@@ -2117,13 +2141,50 @@ int kbo_find_batch_device(const kbo_index* cix, const uint8_t* d_concat, const u
     return KBO_OK;
 }
 
-int kbo_map_unrefined(const kbo_index* query_index, const uint8_t* ref_seq, uint64_t len, double max_error_prob,
+// kbo::map without refinement (lib.rs:726-738, 756-760): K0 -> K1 -> K2b on the device, and for `format` also
+// format::relative_to_ref (format.rs:266-287) before the result leaves the device (relative_to_ref_kernel: the
+// reference bases are already there, staged for K0).
+int kbo_map_unrefined(const kbo_index* cix, const uint8_t* ref_seq, uint64_t len, double max_error_prob,
                       int format, uint8_t* out) {
+    kbo_index* ix = const_cast<kbo_index*>(cix);
     if (!out) return fail(KBO_ERR_BAD_ARGUMENT, "out is null");
-    int rc = kbo_matches(query_index, ref_seq, len, max_error_prob, out);
+    if (!ref_seq && len) return fail(KBO_ERR_BAD_ARGUMENT, "ref_seq is null");
+    const uint64_t offsets[2] = {0, len};
+    uint64_t total = 0;
+    uint32_t thr = 0;
+    int rc = matches_prologue(ix, offsets, 1, max_error_prob, &total, &thr);
     if (rc) return rc;
-    if (format) return kbo_relative_to_ref(ref_seq, out, len, out);
-    return KBO_OK;
+    if (!format || total + 1 >= KBO_MAX_LAUNCH_POSITIONS / 2) {  // (very long sequences: the pipelined host path)
+        rc = kbo_matches(cix, ref_seq, len, max_error_prob, out);
+        if (rc || !format) return rc;
+        return kbo_relative_to_ref(ref_seq, out, len, out);
+    }
+    DeviceGuard dg(ix->device);
+    if (!dg.ok) return fail(KBO_ERR_CUDA, "cudaSetDevice failed");
+    Workspace* ws = nullptr;
+    rc = acquire_ws(ix, &ws);
+    if (rc) return rc;
+    cudaStream_t st = ws->stream;
+    const Geometry g = batch_geometry(ix, len, 1);
+    auto body = [&]() -> int {
+        CUDA_TRY(ws->ascii.ensure(len, st));
+        CUDA_TRY(ws->offsets.ensure(16, st));
+        CUDA_TRY(ws->out.ensure(len + 16, st));
+        CUDA_TRY(cudaMemcpyAsync(ws->ascii.p, ref_seq, len, cudaMemcpyHostToDevice, st));
+        CUDA_TRY(cudaMemcpyAsync(ws->offsets.p, offsets, 16, cudaMemcpyHostToDevice, st));
+        int rc2 = matches_device(ix, ws, ws->ascii.as<uint8_t>(), ws->offsets.as<uint64_t>(), 1, g, thr, ws->out.as<uint8_t>(), 0);
+        if (rc2) return rc2;
+        relative_to_ref_kernel<<<(unsigned)((len + 255) / 256), 256, 0, st>>>(ws->ascii.as<uint8_t>(), ws->out.as<uint8_t>(),
+                                                                              len, ws->out.as<uint8_t>());
+        LAUNCHED();
+        CUDA_TRY(cudaGetLastError());
+        CUDA_TRY(cudaMemcpyAsync(out, ws->out.p, len, cudaMemcpyDeviceToHost, st));
+        CUDA_TRY(cudaStreamSynchronize(st));
+        return KBO_OK;
+    };
+    rc = body();
+    release_ws(ix, ws);
+    return rc;
 }
 
 // ---- call / map with refinement (lib.rs:547-573, 720-761) ---------------------------------------
@@ -2324,6 +2385,8 @@ int kbo_map(const kbo_index* cix, const uint8_t* ref_seq, uint64_t len, double m
     if (!ref_seq && len) return fail(KBO_ERR_BAD_ARGUMENT, "ref_seq is null");
     int rc = matches_prologue(ix, offsets, 1, max_error_prob, &total, &thr);  // lib.rs:731-738 preconditions
     if (rc) return rc;
+    if (!do_fill_gaps && !do_call_variants)  // nothing needs the intervals or the host: translate (and format) on the device
+        return kbo_map_unrefined(cix, ref_seq, len, max_error_prob, format, out);
     HostMs ms;
     rc = run_single_full(ix, ref_seq, len, thr, &ms);
     if (rc) return rc;

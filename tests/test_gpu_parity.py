@@ -737,3 +737,17 @@ def test_find_many_records_exceeds_relay_estimate():
     assert got == want
     job = api.find_submit(concat, offsets, ix, api.FindOpts(), api.FindBuffers(1, cap=len(q), pinned=True))
     assert job.wait() == len(want)
+
+
+@pytest.mark.parametrize("fmt", [True, False])
+def test_map_unrefined_on_device_matches_oracle(fmt):
+    """kbo_map_unrefined: translate and relative_to_ref (format.rs:266-287) on the device; also what kbo_map does when both
+    refinements are switched off."""
+    ref = rand_seq(120_000, 961)
+    asm = synth.mutate(np.frombuffer(ref, dtype=np.uint8), 962).tobytes()
+    q = with_ns(ref, 963, 0.001)
+    ix = api.build([asm], api.BuildOpts(k=31, build_select=True))
+    o = O.OracleIndex([asm], k=31)
+    want = o.map(q, fill_gaps=False, call_variants=False, format=fmt)
+    assert api.map_unrefined(q, ix, format=fmt) == want
+    assert api.map(q, ix, api.MapOpts(fill_gaps=False, call_variants=False, format=fmt)) == want

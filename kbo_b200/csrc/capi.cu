@@ -116,15 +116,17 @@ struct Workspace {
     std::vector<cudaEvent_t> ev_join;
     cudaStream_t stream = nullptr;
     bool own_stream = false;
+    const void* l2_blob = nullptr;  // index allocation the stream's persisting-L2 window points at
     cudaEvent_t ev0 = nullptr, ev1 = nullptr;
     DevBuf ascii, offsets, pack, inv, sep, wq, ms, l, r, out, out2, out3, tmp64, counters, counters2;
-    PinnedBuf h_count;
+    PinnedBuf h_count, h_d, h_l, h_r, h_chars;  // (h_d .. h_chars: kbo_map's (d, l, r) and characters on the host)
     DevBuf masks, rle_words, rle_cnt, rle_cse, rle_tickets;  // K2b<false> masks and the K4 arrays
     std::vector<cudaEvent_t> timing;  // 4 events per timed call (before K0, after K0, after K1, after K2)
     size_t timed_calls = 0;
     void destroy() {
         for (cudaEvent_t e : timing) cudaEventDestroy(e);
         h_rel.release(); h_roff.release(); h_rle.release(); h_count.release();
+        h_d.release(); h_l.release(); h_r.release(); h_chars.release();
         for (Workspace* w : subs) { w->destroy(); delete w; }
         if (ev_fork) cudaEventDestroy(ev_fork);
         for (cudaEvent_t e : ev_join) cudaEventDestroy(e);
@@ -163,7 +165,6 @@ struct kbo_index {
     uint64_t device_bytes = 0;
     IndexView view;
     std::mutex mu;
-    std::vector<Workspace*> pool;                             // idle workspaces with their own stream
     std::unordered_map<cudaStream_t, Workspace*> by_stream;  // workspaces bound to caller streams
     kbo_ms_counters last_counters = {0, 0, 0, 0, 0, 0, 0, 0, 0, 0};
     float last_kernel_ms = 0.f;
@@ -233,27 +234,51 @@ static void apply_l2_window(const kbo_index* ix, cudaStream_t st) {
     cudaGetLastError();  // best effort: the window is an optimisation
 }
 
+// Idle workspaces (own stream + scratch buffers, nothing index-specific) are pooled per DEVICE, not per index: kbo::call /
+// kbo::map build a fresh index for every assembly, and with per-index pools every one of them paid for its ~20 device
+// allocations and page-locked staging buffers again.  The persisting-L2 window of the stream is re-pointed when a
+// workspace moves to another index.
+struct DevicePool {
+    std::mutex mu;
+    std::vector<Workspace*> idle;
+};
+static DevicePool* device_pool(int device) {
+    static std::mutex mu;
+    static std::unordered_map<int, DevicePool*> pools;
+    std::lock_guard<std::mutex> g(mu);
+    DevicePool*& p = pools[device];
+    if (!p) p = new DevicePool();
+    return p;
+}
+
 static int acquire_ws(kbo_index* ix, Workspace** out) {
+    DevicePool* pool = device_pool(ix->device);
+    Workspace* ws = nullptr;
     {
-        std::lock_guard<std::mutex> g(ix->mu);
-        if (!ix->pool.empty()) {
-            *out = ix->pool.back();
-            ix->pool.pop_back();
-            return KBO_OK;
+        std::lock_guard<std::mutex> g(pool->mu);
+        if (!pool->idle.empty()) {
+            ws = pool->idle.back();
+            pool->idle.pop_back();
         }
     }
-    Workspace* ws = new Workspace();
-    ws->own_stream = true;
-    CUDA_TRY(cudaStreamCreateWithFlags(&ws->stream, cudaStreamNonBlocking));
-    apply_l2_window(ix, ws->stream);
-    CUDA_TRY(cudaEventCreate(&ws->ev0));
-    CUDA_TRY(cudaEventCreate(&ws->ev1));
+    if (!ws) {
+        ws = new Workspace();
+        ws->own_stream = true;
+        CUDA_TRY(cudaStreamCreateWithFlags(&ws->stream, cudaStreamNonBlocking));
+        CUDA_TRY(cudaEventCreate(&ws->ev0));
+        CUDA_TRY(cudaEventCreate(&ws->ev1));
+    }
+    if (ws->l2_blob != ix->d_blob) {
+        apply_l2_window(ix, ws->stream);
+        ws->l2_blob = ix->d_blob;
+    }
     *out = ws;
     return KBO_OK;
 }
 static void release_ws(kbo_index* ix, Workspace* ws) {
-    std::lock_guard<std::mutex> g(ix->mu);
-    ix->pool.push_back(ws);
+    DevicePool* pool = device_pool(ix->device);
+    std::lock_guard<std::mutex> g(pool->mu);
+    pool->idle.push_back(ws);
 }
 // How many launches of K1 a stream-ordered call can expect to share the machine with: K1 is about 60 % of a step, so
 // of the distinct caller streams among the last 8 calls roughly that share is inside K1 at any time.
@@ -1166,7 +1191,7 @@ void kbo_index_free(kbo_index* ix) {
     if (!ix) return;
     {
         DeviceGuard dg(ix->device);
-        for (Workspace* ws : ix->pool) { ws->destroy(); delete ws; }
+        // (idle pooled workspaces belong to the device, not to this index: they stay for the next index)
         for (auto& kv : ix->by_stream) { kv.second->destroy(); delete kv.second; }
         for (PinnedBuf& pb : ix->pinned_pool) if (pb.p) cudaFreeHost(pb.p);
         if (ix->d_blob) cudaFree(ix->d_blob);
@@ -2188,29 +2213,43 @@ int kbo_map_unrefined(const kbo_index* cix, const uint8_t* ref_seq, uint64_t len
 }
 
 // ---- call / map with refinement (lib.rs:547-573, 720-761) ---------------------------------------
+// index::query_sbwt output of ONE query on the host, in page-locked buffers of the workspace that computed it (copied
+// at PCIe rate; into pageable vectors the 9 bytes per base took 15 of kbo_map's 25 ms).  The workspace stays
+// acquired until release().  `cands` (optional): the candidate scan of call_variants, done on the device.
 struct HostMs {
-    std::vector<uint8_t> d, chars;
-    std::vector<uint32_t> l, r;
+    kbo_index* ix = nullptr;
+    Workspace* ws = nullptr;
+    const uint8_t* d = nullptr;
+    const uint8_t* chars = nullptr;
+    const uint32_t* l = nullptr;
+    const uint32_t* r = nullptr;
+    void release() { if (ws) release_ws(ix, ws); ws = nullptr; }
+    ~HostMs() { release(); }
 };
 
-// One query through K0 -> K1 (with intervals) [-> K2 when thr != 0]; results copied to the host.
-static int run_single_full(kbo_index* ix, const uint8_t* seq, uint64_t len, uint32_t thr, HostMs* out) {
+static int scan_candidates(kbo_index* ix, Workspace* ws, uint64_t len, uint32_t thr, std::vector<VariantCandidate64>* out);
+
+// One query through K0 -> K1 (with intervals) [-> K2 when thr != 0] [-> candidate scan]; results copied to the host.
+static int run_single_full(kbo_index* ix, const uint8_t* seq, uint64_t len, uint32_t thr, HostMs* out,
+                           uint32_t cand_thr = 0, std::vector<VariantCandidate64>* cands = nullptr) {
     DeviceGuard dg(ix->device);
     if (!dg.ok) return fail(KBO_ERR_CUDA, "cudaSetDevice failed");
     Workspace* ws = nullptr;
     int rc = acquire_ws(ix, &ws);
     if (rc) return rc;
+    out->ix = ix;
+    out->ws = ws;
     const Geometry g = batch_geometry(ix, len, 1);
     cudaStream_t st = ws->stream;
     const uint64_t offsets[2] = {0, len};
-    out->d.resize(len);
-    out->l.resize(len);
-    out->r.resize(len);
-    if (thr) out->chars.resize(len);
     auto body = [&]() -> int {
         CUDA_TRY(ws->ascii.ensure(len, st));
         CUDA_TRY(ws->offsets.ensure(16, st));
         CUDA_TRY(ws->out.ensure(len + 16, st));
+        CUDA_TRY(ws->h_d.ensure(len));
+        CUDA_TRY(ws->h_l.ensure(len * 4));
+        CUDA_TRY(ws->h_r.ensure(len * 4));
+        if (thr) CUDA_TRY(ws->h_chars.ensure(len));
         CUDA_TRY(cudaMemcpyAsync(ws->ascii.p, seq, len, cudaMemcpyHostToDevice, st));
         CUDA_TRY(cudaMemcpyAsync(ws->offsets.p, offsets, 16, cudaMemcpyHostToDevice, st));
         QueryView qv;
@@ -2221,22 +2260,59 @@ static int run_single_full(kbo_index* ix, const uint8_t* seq, uint64_t len, uint
         if (thr) {
             rc2 = run_derand_translate(ix, ws, qv, g, thr, ws->out.as<uint8_t>(), 0);
             if (rc2) return rc2;
-            CUDA_TRY(cudaMemcpyAsync(out->chars.data(), ws->out.p, len, cudaMemcpyDeviceToHost, st));
+            CUDA_TRY(cudaMemcpyAsync(ws->h_chars.p, ws->out.p, len, cudaMemcpyDeviceToHost, st));
         }
         // a single query has its only separator at position len: padded == unpadded below len
-        CUDA_TRY(cudaMemcpyAsync(out->d.data(), ws->ms.p, len, cudaMemcpyDeviceToHost, st));
-        CUDA_TRY(cudaMemcpyAsync(out->l.data(), ws->l.p, len * 4, cudaMemcpyDeviceToHost, st));
-        CUDA_TRY(cudaMemcpyAsync(out->r.data(), ws->r.p, len * 4, cudaMemcpyDeviceToHost, st));
+        CUDA_TRY(cudaMemcpyAsync(ws->h_d.p, ws->ms.p, len, cudaMemcpyDeviceToHost, st));
+        CUDA_TRY(cudaMemcpyAsync(ws->h_l.p, ws->l.p, len * 4, cudaMemcpyDeviceToHost, st));
+        CUDA_TRY(cudaMemcpyAsync(ws->h_r.p, ws->r.p, len * 4, cudaMemcpyDeviceToHost, st));
+        if (cands) return scan_candidates(ix, ws, len, cand_thr, cands);  // (synchronises the stream)
         CUDA_TRY(cudaStreamSynchronize(st));
         return KBO_OK;
     };
     rc = body();
-    release_ws(ix, ws);
+    out->d = ws->h_d.as<uint8_t>();
+    out->l = ws->h_l.as<uint32_t>();
+    out->r = ws->h_r.as<uint32_t>();
+    out->chars = ws->h_chars.as<uint8_t>();
+    if (rc) out->release();
     return rc;
 }
 
-// One query through K0 -> K1 (with intervals) -> the candidate scan of call_variants on the device
-// (variant_calling.rs:266-272): only the candidates come back to the host, not 9 bytes per base of (d, l, r).
+// The candidate scan of call_variants (variant_calling.rs:268-272) on the (d, l, r) that K1 has just left in the
+// workspace (one query: padded == unpadded below len); candidates come back sorted by position.  Synchronises.
+static int scan_candidates(kbo_index* ix, Workspace* ws, uint64_t len, uint32_t thr, std::vector<VariantCandidate64>* out) {
+    cudaStream_t st = ws->stream;
+    CUDA_TRY(ws->counters2.ensure(8, st));
+    CUDA_TRY(ws->h_count.ensure(16));
+    uint32_t cap = (uint32_t)std::min<uint64_t>(len / 16 + 4096, 1u << 26);
+    for (int attempt = 0; attempt < 2; ++attempt) {
+        CUDA_TRY(ws->out2.ensure((uint64_t)cap * sizeof(VariantCandidate), st));
+        CUDA_TRY(cudaMemsetAsync(ws->counters2.p, 0, 4, st));
+        variant_candidates_kernel<<<(unsigned)((len + 255) / 256), 256, 0, st>>>(
+            ws->ms.as<uint8_t>(), ws->l.as<uint32_t>(), ws->r.as<uint32_t>(), len, ix->host.k, thr,
+            ws->out2.as<VariantCandidate>(), cap, ws->counters2.as<unsigned int>());
+        LAUNCHED();
+        CUDA_TRY(cudaGetLastError());
+        CUDA_TRY(cudaMemcpyAsync(ws->h_count.p, ws->counters2.p, 4, cudaMemcpyDeviceToHost, st));
+        CUDA_TRY(cudaStreamSynchronize(st));
+        const uint32_t n = *ws->h_count.as<uint32_t>();
+        if (n <= cap) {
+            std::vector<VariantCandidate> tmp(n);
+            if (n) CUDA_TRY(cudaMemcpy(tmp.data(), ws->out2.p, (size_t)n * sizeof(VariantCandidate), cudaMemcpyDeviceToHost));
+            std::sort(tmp.begin(), tmp.end(), [](const VariantCandidate& a, const VariantCandidate& b) { return a.i < b.i; });
+            out->clear();
+            out->reserve(n);
+            for (const VariantCandidate& c : tmp) out->push_back(VariantCandidate64{c.i, c.j, c.node});
+            return KBO_OK;
+        }
+        cap = n;  // more candidates than the first guess: once more with room for all of them
+    }
+    return fail(KBO_ERR_CUDA, "candidate scan did not converge");
+}
+
+// One query through K0 -> K1 (with intervals) -> the candidate scan on the device: only the candidates come back to
+// the host, not 9 bytes per base of (d, l, r)  (kbo::call, variant_calling.rs:266-272).
 static int run_single_candidates(kbo_index* ix, const uint8_t* seq, uint64_t len, uint32_t thr,
                                  std::vector<VariantCandidate64>* out) {
     DeviceGuard dg(ix->device);
@@ -2251,8 +2327,6 @@ static int run_single_candidates(kbo_index* ix, const uint8_t* seq, uint64_t len
     auto body = [&]() -> int {
         CUDA_TRY(ws->ascii.ensure(len, st));
         CUDA_TRY(ws->offsets.ensure(16, st));
-        CUDA_TRY(ws->counters2.ensure(8, st));
-        CUDA_TRY(ws->h_count.ensure(16));
         CUDA_TRY(cudaMemcpyAsync(ws->ascii.p, seq, len, cudaMemcpyHostToDevice, st));
         CUDA_TRY(cudaMemcpyAsync(ws->offsets.p, offsets, 16, cudaMemcpyHostToDevice, st));
         QueryView qv;
@@ -2260,31 +2334,7 @@ static int run_single_candidates(kbo_index* ix, const uint8_t* seq, uint64_t len
         if (rc2) return rc2;
         rc2 = run_ms(ix, ws, qv, g, true);
         if (rc2) return rc2;
-        uint32_t cap = (uint32_t)std::min<uint64_t>(len / 16 + 4096, 1u << 26);
-        for (int attempt = 0; attempt < 2; ++attempt) {
-            CUDA_TRY(ws->out2.ensure((uint64_t)cap * sizeof(VariantCandidate), st));
-            CUDA_TRY(cudaMemsetAsync(ws->counters2.p, 0, 4, st));
-            // a single query has its only separator at position len: padded == unpadded below len
-            variant_candidates_kernel<<<(unsigned)((len + 255) / 256), 256, 0, st>>>(
-                ws->ms.as<uint8_t>(), ws->l.as<uint32_t>(), ws->r.as<uint32_t>(), len, ix->host.k, thr,
-                ws->out2.as<VariantCandidate>(), cap, ws->counters2.as<unsigned int>());
-            LAUNCHED();
-            CUDA_TRY(cudaGetLastError());
-            CUDA_TRY(cudaMemcpyAsync(ws->h_count.p, ws->counters2.p, 4, cudaMemcpyDeviceToHost, st));
-            CUDA_TRY(cudaStreamSynchronize(st));
-            const uint32_t n = *ws->h_count.as<uint32_t>();
-            if (n <= cap) {
-                std::vector<VariantCandidate> tmp(n);
-                if (n) CUDA_TRY(cudaMemcpy(tmp.data(), ws->out2.p, (size_t)n * sizeof(VariantCandidate), cudaMemcpyDeviceToHost));
-                std::sort(tmp.begin(), tmp.end(), [](const VariantCandidate& a, const VariantCandidate& b) { return a.i < b.i; });
-                out->clear();
-                out->reserve(n);
-                for (const VariantCandidate& c : tmp) out->push_back(VariantCandidate64{c.i, c.j, c.node});
-                return KBO_OK;
-            }
-            cap = n;  // more candidates than the first guess: once more with room for all of them
-        }
-        return fail(KBO_ERR_CUDA, "candidate scan did not converge");
+        return scan_candidates(ix, ws, len, thr, out);
     };
     rc = body();
     release_ws(ix, ws);
@@ -2387,25 +2437,34 @@ int kbo_map(const kbo_index* cix, const uint8_t* ref_seq, uint64_t len, double m
     if (rc) return rc;
     if (!do_fill_gaps && !do_call_variants)  // nothing needs the intervals or the host: translate (and format) on the device
         return kbo_map_unrefined(cix, ref_seq, len, max_error_prob, format, out);
+    BuildTimer bt;  // (KBO_BUILD_TIMING=1: where kbo_map spends its time)
     HostMs ms;
-    rc = run_single_full(ix, ref_seq, len, thr, &ms);
+    std::vector<VariantCandidate64> cands;
+    uint64_t call_thr = 0;
+    if (do_call_variants) {
+        rc = host_threshold(ix->host.k, ix->host.n_kmers, 4, max_error_prob, &call_thr);  // variant_calling.rs:260
+        if (rc) return rc;
+    }
+    rc = run_single_full(ix, ref_seq, len, thr, &ms, (uint32_t)std::min<uint64_t>(call_thr, 255),
+                         do_call_variants ? &cands : nullptr);
     if (rc) return rc;
-    std::vector<uint8_t> aln = ms.chars;
+    bt.lap("map: K0, K1 (d,l,r), K2b, candidate scan + copy-out");
+    std::vector<uint8_t> aln(ms.chars, ms.chars + len);
     MsArrays view;
-    view.d = ms.d.data();
-    view.l = ms.l.data();
-    view.r = ms.r.data();
+    view.d = ms.d;
+    view.l = ms.l;
+    view.r = ms.r;
     view.n = len;
     try {
         if (do_fill_gaps)  // lib.rs:743-744; gaps are independent: bridged on build_opts.num_threads host threads
             fill_gaps(&aln, view, ref_seq, len, ix->host, thr, max_error_prob, tuned_refine_threads(ix));
+        bt.lap("map: fill_gaps (host)");
         if (do_call_variants) {                                                             // lib.rs:749-751
             std::vector<VariantRec> vars;
-            uint64_t call_thr = 0;
-            rc = host_threshold(ix->host.k, ix->host.n_kmers, 4, max_error_prob, &call_thr);  // variant_calling.rs:260
+            ms.release();  // (the arrays are not needed any more; call_impl takes workspaces of its own)
+            rc = call_impl(ix, ref_seq, len, max_error_prob, &o, cands, &vars);
             if (rc) return rc;
-            rc = call_impl(ix, ref_seq, len, max_error_prob, &o, find_variant_candidates(view, len, ix->host.k, call_thr), &vars);
-            if (rc) return rc;
+            bt.lap("map: call (ref index, k-mer MS, resolve)");
             add_variants(&aln, vars);
         }
     } catch (const RefinePanic& p) {

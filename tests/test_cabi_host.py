@@ -131,3 +131,39 @@ def test_argument_validation_before_any_device_work(lib):
     with pytest.raises(api.KboPanic) as e:
         api.build([b"ACGT"], api.BuildOpts(k=65))
     assert e.value.status == 4
+
+
+def test_index_from_parts_validates_its_arrays(lib):
+    """kbo_index_from_parts rejects arrays K1 could not walk safely: LCS[0] != 0, an LCS value >= k,
+    rows whose set bits are not n_sets - 1 -- before any device work, so also without a GPU."""
+    import oracle_lib as O
+    o = O.OracleIndex([b"AAAGAACCA-TCAGGGCG"], k=3)
+    rows, lcs = o.rows(), o.lcs()
+    bad = lcs.copy(); bad[0] = 1
+    with pytest.raises(api.KboPanic) as e:
+        api.index_from_parts(3, o.n_sets, o.n_kmers, rows, bad)
+    assert e.value.status == 7 and "LCS" in str(e.value)
+    bad = lcs.copy(); bad[5] = 3
+    with pytest.raises(api.KboPanic) as e:
+        api.index_from_parts(3, o.n_sets, o.n_kmers, rows, bad)
+    assert e.value.status == 7
+    rows_bad = [r.copy() for r in rows]; rows_bad[0][0] ^= np.uint64(1 << 7)
+    with pytest.raises(api.KboPanic) as e:
+        api.index_from_parts(3, o.n_sets, o.n_kmers, rows_bad, lcs)
+    assert e.value.status == 7 and "set bits" in str(e.value)
+    with pytest.raises(api.KboPanic) as e:
+        api.index_from_parts(128, o.n_sets, o.n_kmers, rows, lcs)
+    assert e.value.status == 4
+
+
+def test_new_entry_points_check_their_arguments(lib):
+    h = C.c_void_p()
+    assert lib.kbo_job_wait(None, None) == 7
+    assert lib.kbo_find_batch_submit(None, None, None, 0, 1e-7, 0, None, 0, None, C.byref(h)) == 7
+    assert lib.kbo_index_set_tuning(None, 0, 1) == 7
+    assert lib.kbo_find_batch_multi(None, None, None, 0, 1e-7, 0, None, 0, None) == 7
+    assert lib.kbo_matches_batch_multi(None, None, None, 0, 1e-7, None) == 7
+    assert lib.kbo_ctx_n_gpus(None) == 0
+    assert lib.kbo_index_set_get(None, 0) is None
+    if api.device_count() == 0:
+        assert lib.kbo_ctx_create(1, None, C.byref(h)) == 8  # no device: KBO_ERR_CUDA, no fallback

@@ -751,3 +751,25 @@ def test_map_unrefined_on_device_matches_oracle(fmt):
     want = o.map(q, fill_gaps=False, call_variants=False, format=fmt)
     assert api.map_unrefined(q, ix, format=fmt) == want
     assert api.map(q, ix, api.MapOpts(fill_gaps=False, call_variants=False, format=fmt)) == want
+
+
+def test_per_index_tuning_knobs():
+    """kbo_index_set_tuning: two indexes in one process run with different chunk lengths / kernel paths; results are the
+    oracle's for both, and -1 returns a knob to the process-wide default."""
+    ref = rand_seq(150_000, 971)
+    a, b = api.build([ref], api.BuildOpts(k=31)), api.build([ref], api.BuildOpts(k=31))
+    o = O.OracleIndex([ref], k=31)
+    concat, off = synth.gene_queries(np.frombuffer(ref, dtype=np.uint8), 300, 700, 972, snp=0.02)
+    _, want, _ = o.matches_batch(concat, off, n_threads=4)
+    api.set_index_tuning(a, api.TUNE_CHUNK_LEN, 96)
+    api.set_index_tuning(a, api.TUNE_MS_FLAGS, 16)       # fused kernel on index a only
+    api.set_index_tuning(b, api.TUNE_PIPELINE_PARTS, 3)  # three sub-batches per host call on index b only
+    assert np.array_equal(api.matches_csr(concat, off, a)[:len(concat)], want)
+    assert np.array_equal(api.matches_csr(concat, off, b)[:len(concat)], want)
+    n0 = api.kernel_launch_count()
+    api.matches_csr(concat, off, a)
+    assert api.kernel_launch_count() - n0 == 2           # K0 + the fused kernel
+    api.set_index_tuning(a, api.TUNE_MS_FLAGS, -1)
+    n0 = api.kernel_launch_count()
+    api.matches_csr(concat, off, a)
+    assert api.kernel_launch_count() - n0 == 3           # K0, K1, K2b again

@@ -257,7 +257,8 @@ int kbo_index_set_tuning(kbo_index* ix, int key, int64_t value);
 int kbo_set_device_parts(uint32_t parts);
 /* Tuning knob: number of sub-batches the host-buffer batch calls are pipelined over (0 = automatic). */
 int kbo_set_pipeline_parts(uint32_t parts);
-/* Index construction runs on the GPU for 2 <= k <= 32; enabled != 0 forces the host builder (for comparison). */
+/* Index construction runs on the GPU for 2 <= k <= 64 (128-bit keys above 32); enabled != 0 forces the host builder
+ * (for comparison). */
 int kbo_set_host_builder(int enabled);
 /* enabled == 0: indexes created afterwards carry no prefix-state table (K1 then warms every chunk up over k-1 bases;
  * comparison runs).  Results never depend on it. */

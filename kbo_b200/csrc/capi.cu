@@ -455,7 +455,7 @@ static int upload_index(kbo_index* ix) {
 }
 
 // ---------------------------------------------------------------------------
-// index construction on the device (index_build.cuh), 2 <= k <= 32
+// index construction on the device (index_build.cuh), 2 <= k <= 64
 // ---------------------------------------------------------------------------
 // Scratch of one index construction: stream-ordered allocations from the device's default memory pool
 // (kept warm between builds), so that the ~25 temporaries cost microseconds instead of a cudaMalloc /
@@ -498,8 +498,10 @@ struct BuildTimer {
     }
 };
 
-static int build_index_gpu(kbo_index* ix, const uint8_t* const* seqs, const uint64_t* lens, uint64_t n_seqs, uint32_t k,
-                           bool revcomp, bool keep_nodes, bool device_only = false) {
+template <typename K>
+static int build_index_gpu_typed(kbo_index* ix, const uint8_t* const* seqs, const uint64_t* lens, uint64_t n_seqs, uint32_t k,
+                                 bool revcomp, bool keep_nodes, bool device_only) {
+    constexpr int BITS = KmerKey<K>::BITS;
     BuildTimer bt;
     uint64_t total = 0;
     std::vector<uint64_t> offsets(n_seqs + 1, 0);
@@ -508,7 +510,8 @@ static int build_index_gpu(kbo_index* ix, const uint8_t* const* seqs, const uint
     TmpBufs::warm_pool(ix->device);
     TmpBufs tmp;
     uint8_t *d_ascii, *d_flags, *d_nopred, *d_Dlen = nullptr, *d_Plen;
-    uint64_t *d_off, *d_pack, *d_keys, *d_keys_rc = nullptr, *d_sel, *d_sorted, *d_R, *d_src, *d_Dkey = nullptr, *d_Pkey, *d_count;
+    uint64_t *d_off, *d_pack, *d_count;
+    K *d_keys, *d_keys_rc = nullptr, *d_sel, *d_sorted, *d_R, *d_src, *d_Dkey = nullptr, *d_Pkey;
     uint32_t *d_inv, *d_sep, *d_wq, *d_rows32, *d_pc, *d_prefix;
     CUDA_TRY(tmp.alloc(&d_ascii, total));
     CUDA_TRY(tmp.alloc(&d_off, n_seqs + 1));
@@ -537,7 +540,7 @@ static int build_index_gpu(kbo_index* ix, const uint8_t* const* seqs, const uint
     CUDA_TRY(tmp.alloc(&d_sel, n_cand));
     CUDA_TRY(tmp.alloc(&d_sorted, n_cand));
     CUDA_TRY(tmp.alloc(&d_R, n_cand));
-    kmer_keys_kernel<<<(unsigned)((Lp + 255) / 256), 256>>>(d_pack, d_inv, Lp, k, revcomp ? 1 : 0, d_keys, d_keys_rc, d_flags);
+    kmer_keys_kernel<K><<<(unsigned)((Lp + 255) / 256), 256>>>(d_pack, d_inv, Lp, k, revcomp ? 1 : 0, d_keys, d_keys_rc, d_flags);
     LAUNCHED();
     CUDA_TRY(cudaGetLastError());
     bt.lap("copy-in, pack, k-mer keys");
@@ -545,7 +548,7 @@ static int build_index_gpu(kbo_index* ix, const uint8_t* const* seqs, const uint
     size_t tb = 0, need = 0;
     void* d_tmp = nullptr;
     cub::DeviceSelect::Flagged(nullptr, need, d_keys, d_flags, d_sel, d_count, (int64_t)Lp); tb = std::max(tb, need);
-    cub::DeviceRadixSort::SortKeys(nullptr, need, d_sel, d_sorted, (int64_t)n_cand, 64 - 2 * (int)k, 64); tb = std::max(tb, need);
+    cub::DeviceRadixSort::SortKeys(nullptr, need, d_sel, d_sorted, (int64_t)n_cand, BITS - 2 * (int)k, BITS); tb = std::max(tb, need);
     cub::DeviceSelect::Unique(nullptr, need, d_sorted, d_R, d_count, (int64_t)n_cand); tb = std::max(tb, need);
     CUDA_TRY(cudaMallocAsync(&d_tmp, tb ? tb : 1, 0));
     tmp.ptrs.push_back(d_tmp);
@@ -564,45 +567,45 @@ static int build_index_gpu(kbo_index* ix, const uint8_t* const* seqs, const uint
     uint64_t nR = 0;
     if (n_valid) {
         need = tb;
-        CUDA_TRY(cub::DeviceRadixSort::SortKeys(d_tmp, need, d_sel, d_sorted, (int64_t)n_valid, 64 - 2 * (int)k, 64));
+        CUDA_TRY(cub::DeviceRadixSort::SortKeys(d_tmp, need, d_sel, d_sorted, (int64_t)n_valid, BITS - 2 * (int)k, BITS));
         need = tb;
         CUDA_TRY(cub::DeviceSelect::Unique(d_tmp, need, d_sorted, d_R, d_count, (int64_t)n_valid));
         CUDA_TRY(cudaMemcpy(&nR, d_count, 8, cudaMemcpyDeviceToHost));
     }
     bt.lap("select, sort, unique");
     // dummy nodes: few, made on the host from the k-mers that have no predecessor
-    std::vector<uint64_t> h_src;
+    std::vector<K> h_src;
     if (nR) {
         CUDA_TRY(tmp.alloc(&d_nopred, nR));
         CUDA_TRY(tmp.alloc(&d_src, nR));
-        no_predecessor_kernel<<<(unsigned)((nR + 255) / 256), 256>>>(d_R, nR, k, d_nopred);
+        no_predecessor_kernel<K><<<(unsigned)((nR + 255) / 256), 256>>>(d_R, nR, k, d_nopred);
         LAUNCHED();
         need = tb;
         CUDA_TRY(cub::DeviceSelect::Flagged(d_tmp, need, d_R, d_nopred, d_src, d_count, (int64_t)nR));
         uint64_t n_src = 0;
         CUDA_TRY(cudaMemcpy(&n_src, d_count, 8, cudaMemcpyDeviceToHost));
         h_src.resize(n_src);
-        if (n_src) CUDA_TRY(cudaMemcpy(h_src.data(), d_src, n_src * 8, cudaMemcpyDeviceToHost));
+        if (n_src) CUDA_TRY(cudaMemcpy(h_src.data(), d_src, n_src * sizeof(K), cudaMemcpyDeviceToHost));
     }
-    std::vector<std::pair<uint64_t, uint8_t>> dummies;
-    dummies.push_back({0ull, (uint8_t)0});
-    for (uint64_t x : h_src)
-        for (uint32_t j = 1; j < k; ++j) dummies.push_back({x << (2 * (k - j)), (uint8_t)j});
+    std::vector<std::pair<K, uint8_t>> dummies;
+    dummies.push_back({(K)0, (uint8_t)0});
+    for (K x : h_src)
+        for (uint32_t j = 1; j < k; ++j) dummies.push_back({(K)(x << (2 * (k - j))), (uint8_t)j});
     std::sort(dummies.begin(), dummies.end());
     dummies.erase(std::unique(dummies.begin(), dummies.end()), dummies.end());
     const uint64_t nD = dummies.size();
     const uint64_t n = nR + nD;
     if (n >= (1ull << 32) - 64) return fail(KBO_ERR_INDEX_TOO_LARGE, "n_sets must be < 2^32");
-    std::vector<uint64_t> h_Dkey(nD);
+    std::vector<K> h_Dkey(nD);
     std::vector<uint8_t> h_Dlen(nD);
     for (uint64_t i = 0; i < nD; ++i) { h_Dkey[i] = dummies[i].first; h_Dlen[i] = dummies[i].second; }
     CUDA_TRY(tmp.alloc(&d_Dkey, nD));
     CUDA_TRY(tmp.alloc(&d_Dlen, nD));
-    CUDA_TRY(cudaMemcpy(d_Dkey, h_Dkey.data(), nD * 8, cudaMemcpyHostToDevice));
+    CUDA_TRY(cudaMemcpy(d_Dkey, h_Dkey.data(), nD * sizeof(K), cudaMemcpyHostToDevice));
     CUDA_TRY(cudaMemcpy(d_Dlen, h_Dlen.data(), nD, cudaMemcpyHostToDevice));
     CUDA_TRY(tmp.alloc(&d_Pkey, n));
     CUDA_TRY(tmp.alloc(&d_Plen, n));
-    merge_nodes_kernel<<<(unsigned)((n + 255) / 256), 256>>>(d_R, nR, d_Dkey, d_Dlen, nD, k, d_Pkey, d_Plen);
+    merge_nodes_kernel<K><<<(unsigned)((n + 255) / 256), 256>>>(d_R, nR, d_Dkey, d_Dlen, nD, k, d_Pkey, d_Plen);
     LAUNCHED();
     bt.lap("dummies, merge");
     // final device arrays
@@ -615,9 +618,9 @@ static int build_index_gpu(kbo_index* ix, const uint8_t* const* seqs, const uint
     CUDA_TRY(tmp.alloc(&d_pc, 4 * stride));
     CUDA_TRY(tmp.alloc(&d_prefix, 4 * stride));
     CUDA_TRY(cudaMemset(d_rows32, 0, 4 * stride * 4));
-    lcs_kernel<<<(unsigned)((n + 255) / 256), 256>>>(d_Pkey, d_Plen, n, ix->d_lcs);
+    lcs_kernel<K><<<(unsigned)((n + 255) / 256), 256>>>(d_Pkey, d_Plen, n, ix->d_lcs);
     LAUNCHED();
-    labels_kernel<<<(unsigned)((n + 255) / 256), 256>>>(d_Pkey, d_Plen, n, k, d_rows32, stride);
+    labels_kernel<K><<<(unsigned)((n + 255) / 256), 256>>>(d_Pkey, d_Plen, n, k, d_rows32, stride);
     LAUNCHED();
     row_popc_kernel<<<(unsigned)((4 * stride + 255) / 256), 256>>>(d_rows32, 4 * stride, d_pc);
     LAUNCHED();
@@ -663,13 +666,29 @@ static int build_index_gpu(kbo_index* ix, const uint8_t* const* seqs, const uint
     if (keep_nodes) {  // "select support": the nodes themselves, for O(1) access_kmer on the host
         h.node_hi.resize((size_t)n);
         h.node_len.resize((size_t)n);
-        CUDA_TRY(cudaMemcpy(h.node_hi.data(), d_Pkey, n * 8, cudaMemcpyDeviceToHost));
+        if (BITS == 64) {
+            CUDA_TRY(cudaMemcpy(h.node_hi.data(), d_Pkey, n * 8, cudaMemcpyDeviceToHost));
+        } else {  // 128-bit keys: little-endian (lo, hi) pairs on the device
+            std::vector<K> keys((size_t)n);
+            CUDA_TRY(cudaMemcpy(keys.data(), d_Pkey, n * sizeof(K), cudaMemcpyDeviceToHost));
+            h.node_lo.resize((size_t)n);
+            for (size_t i = 0; i < (size_t)n; ++i) {
+                h.node_hi[i] = (uint64_t)((u128)keys[i] >> 64);
+                h.node_lo[i] = (uint64_t)keys[i];
+            }
+        }
         CUDA_TRY(cudaMemcpy(h.node_len.data(), d_Plen, n, cudaMemcpyDeviceToHost));
     }
     bt.lap("host mirror (rows, lcs, nodes)");
     const int rc_links = build_links(ix, n);
     bt.lap("rank2, links, prefix table");
     return rc_links;
+}
+
+static int build_index_gpu(kbo_index* ix, const uint8_t* const* seqs, const uint64_t* lens, uint64_t n_seqs, uint32_t k,
+                           bool revcomp, bool keep_nodes, bool device_only = false) {
+    if (k <= 32) return build_index_gpu_typed<uint64_t>(ix, seqs, lens, n_seqs, k, revcomp, keep_nodes, device_only);
+    return build_index_gpu_typed<u128>(ix, seqs, lens, n_seqs, k, revcomp, keep_nodes, device_only);
 }
 
 // ---------------------------------------------------------------------------
@@ -1131,7 +1150,7 @@ int kbo_index_build(const uint8_t* const* seqs, const uint64_t* lens, uint64_t n
     if (opts) o = *opts; else kbo_default_build_opts(&o);
     if (o.k == 0 || o.k > KBO_MAX_K) return fail(KBO_ERR_BAD_K, "1 <= k <= 64 in this build");
     kbo_index* ix = new kbo_index();
-    if (o.k >= 2 && o.k <= 32 && !g_host_builder.load()) {  // device construction (index_build.cuh)
+    if (o.k >= 2 && o.k <= KBO_MAX_K && !g_host_builder.load()) {  // device construction (index_build.cuh)
         int ndev = 0;
         if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev == 0) {
             delete ix;
@@ -2353,7 +2372,7 @@ static int call_impl(kbo_index* query_index, const uint8_t* ref_seq, uint64_t le
     kbo_index* ref_index = nullptr;
     const uint8_t* seqs[1] = {ref_seq};
     const uint64_t lens[1] = {len};
-    if (o.k >= 2 && o.k <= 32 && !g_host_builder.load()) {  // lib.rs:553; only its device arrays are used below
+    if (o.k >= 2 && o.k <= KBO_MAX_K && !g_host_builder.load()) {  // lib.rs:553; only its device arrays are used below
         if (len == 0) return fail(KBO_ERR_EMPTY_INPUT, "no input sequences (index.rs:60)");
         DeviceGuard dg(query_index->device);
         if (!dg.ok) return fail(KBO_ERR_CUDA, "cudaSetDevice failed");

@@ -132,9 +132,11 @@ def test_index_build_matches_oracle(k, revcomp):
     assert np.array_equal(lcs, o.lcs()) and np.array_equal(Cc, o.C())
 
 
-@pytest.mark.parametrize("k,revcomp", [(2, False), (5, True), (16, False), (32, False), (32, True)])
+@pytest.mark.parametrize("k,revcomp", [(2, False), (5, True), (16, False), (32, False), (32, True), (33, False), (33, True),
+                                       (51, True), (63, False), (64, True)])
 def test_gpu_and_host_builders_agree_with_oracle(k, revcomp):
-    """k <= 32 is built on the device (index_build.cuh); the host builder is forced for comparison."""
+    """Every k <= 64 is built on the device (index_build.cuh: 64-bit keys up to 32, 128-bit keys above); the host builder
+    is forced for comparison."""
     ref = with_ns(rand_seq(40_000, 17), 18, rate=0.001)
     seqs = [ref[:25_000], ref[25_000:], b"ACGT" * 20, b"AC", ref[100:160]]
     o = O.OracleIndex(seqs, k=k, add_revcomp=revcomp)

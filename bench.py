@@ -479,8 +479,9 @@ def run_ours(args, rank, local_rank, world):
                                         "probes (two bases per probe, contraction jumps), which LOWERS its own figure",
             "achieved_reference_algorithm_GBps": 51.0 * L / (k1_ms * 1e-3) / 1e9 if k1_ms > 0 else 0.0,
             "kernel_ms": {"pack": ksum["pack"] / max(kcalls, 1), "ms_fused": k1_ms,
-                          "how": "CUDA events around each kernel over %d serial steps on the launch stream, same kernels "
-                                 "and geometry as the timed region" % kcalls},
+                          "how": "CUDA events around each kernel over %d serial steps on the launch stream: the configuration "
+                                 "of impl_detail.single_stream (chunk length 64); the %d-stream `value` region overlaps steps "
+                                 "and runs K1 with longer chunks" % (kcalls, len(workers))},
             "step_ms_single_stream": ms_single / args.steps,
             "events_per_base": {"rank_probes": cnt["emit_extend_attempts"] / L,
                                 "contractions": cnt["emit_contractions"] / L,

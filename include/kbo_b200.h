@@ -246,6 +246,10 @@ int kbo_set_chunk_len(uint32_t chunk_len);
 /* Host threads that bridge gaps in kbo_map (gaps are independent given the incoming translation; results never depend
  * on it).  0 = hardware concurrency, at most 16.  (BuildOpts.num_threads keeps the reference's meaning: builder threads.) */
 int kbo_set_refine_threads(uint32_t n);
+/* kbo_map / kbo_call on an index that the GPU builder made with build_select keep the node k-mers on the device and
+ * run gap_filling::fill_gaps (gap_filling.rs:444-526) and the access_kmer of call_variants (variant_calling.rs:276)
+ * there; enabled == 0 sends both to the host versions (comparison runs).  Results never depend on it. */
+int kbo_set_device_refine(int enabled);
 /* The kbo_set_* knobs are process-wide defaults; this sets a knob for ONE index (value -1 = back to the default), so
  * that two indexes / callers in one process can differ. */
 typedef enum kbo_tuning_key {

@@ -39,7 +39,7 @@ EXPORTED_SYMBOLS = [
     "kbo_log_rm_max_cdf", "kbo_random_match_threshold", "kbo_derandomize_ms_vec", "kbo_translate_ms_vec",
     "kbo_run_lengths_gapped", "kbo_relative_to_ref", "kbo_matches", "kbo_matches_batch", "kbo_matches_batch_device",
     "kbo_find_batch", "kbo_find_batch_submit", "kbo_job_wait", "kbo_find_batch_device", "kbo_ctx_create", "kbo_ctx_free", "kbo_ctx_n_gpus", "kbo_index_set_build", "kbo_index_set_free", "kbo_index_set_get",
-    "kbo_matches_batch_multi", "kbo_find_batch_multi", "kbo_map_unrefined", "kbo_call", "kbo_map", "kbo_set_profile_counters", "kbo_get_ms_counters", "kbo_set_chunk_len", "kbo_set_l2_persist", "kbo_set_prefix_table", "kbo_set_rank2", "kbo_set_refine_threads", "kbo_index_set_tuning", "kbo_set_host_builder", "kbo_set_pipeline_parts", "kbo_set_device_parts", "kbo_set_ms_flags",
+    "kbo_matches_batch_multi", "kbo_find_batch_multi", "kbo_map_unrefined", "kbo_call", "kbo_map", "kbo_set_profile_counters", "kbo_get_ms_counters", "kbo_set_chunk_len", "kbo_set_l2_persist", "kbo_set_prefix_table", "kbo_set_rank2", "kbo_set_refine_threads", "kbo_set_device_refine", "kbo_index_set_tuning", "kbo_set_host_builder", "kbo_set_pipeline_parts", "kbo_set_device_parts", "kbo_set_ms_flags",
     "kbo_kernel_launch_count", "kbo_last_kernel_ms", "kbo_set_kernel_timing", "kbo_collect_kernel_times",
     "kbo_measure_random_sector_rate",
 ]
@@ -146,6 +146,7 @@ def load_library():
     L.kbo_set_prefix_table.argtypes = [C.c_int]
     L.kbo_set_rank2.argtypes = [C.c_int]
     L.kbo_set_refine_threads.argtypes = [C.c_uint32]
+    L.kbo_set_device_refine.argtypes = [C.c_int]
     L.kbo_index_set_tuning.argtypes = [C.c_void_p, C.c_int, C.c_int64]
     L.kbo_set_host_builder.argtypes = [C.c_int]
     L.kbo_set_pipeline_parts.argtypes = [C.c_uint32]
@@ -685,6 +686,11 @@ TUNE_CHUNK_LEN, TUNE_PIPELINE_PARTS, TUNE_DEVICE_PARTS, TUNE_MS_FLAGS, TUNE_REFI
 def set_refine_threads(n):
     """Host threads that bridge gaps in map() (0 = hardware concurrency, at most 16)."""
     _check(load_library().kbo_set_refine_threads(int(n)))
+
+
+def set_device_refine(enabled):
+    """fill_gaps / access_kmer of map() and call() on the device (default) or on the host (comparison runs)."""
+    _check(load_library().kbo_set_device_refine(int(bool(enabled))))
 
 
 def set_index_tuning(index, key, value):

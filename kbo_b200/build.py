@@ -9,7 +9,7 @@ PKG_DIR = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(PKG_DIR, "csrc")
 LIB_PATH = os.path.join(PKG_DIR, "libkbo_b200.so")
 SOURCES = ["capi.cu", "sbwt_host.cpp", "refine_host.cpp"]
-HEADERS = ["kernels.cuh", "index_build.cuh", "host_layout.hpp", "sbwt_host.hpp", "refine_host.hpp", os.path.join("..", "..", "include", "kbo_b200.h")]
+HEADERS = ["kernels.cuh", "fused.cuh", "refine.cuh", "index_build.cuh", "host_layout.hpp", "sbwt_host.hpp", "refine_host.hpp", os.path.join("..", "..", "include", "kbo_b200.h")]
 
 NVCC_FLAGS = [
     "-gencode", "arch=compute_100a,code=sm_100a",

@@ -24,6 +24,7 @@
 #include "kernels.cuh"
 #include "fused.cuh"
 #include "index_build.cuh"
+#include "refine.cuh"
 #include "host_layout.hpp"
 #include "refine_host.hpp"
 #include "sbwt_host.hpp"
@@ -47,6 +48,7 @@ static std::atomic<uint32_t> g_parts(0);
 static std::atomic<uint32_t> g_dev_parts(0);
 static std::atomic<uint32_t> g_ms_block(128);
 
+static std::atomic<int> g_device_refine(1);  // 0: fill_gaps / access_kmer of kbo::map and kbo::call on the host (comparison runs)
 static std::atomic<uint32_t> g_refine_threads(0);  // host threads of fill_gaps (0 = hardware concurrency, at most 16)
 struct kbo_index;
 static uint32_t tuned_chunk_len(const kbo_index* ix);
@@ -121,6 +123,7 @@ struct Workspace {
     DevBuf ascii, offsets, pack, inv, sep, wq, ms, l, r, out, out2, out3, tmp64, counters, counters2;
     PinnedBuf h_count, h_d, h_l, h_r, h_chars;  // (h_d .. h_chars: kbo_map's (d, l, r) and characters on the host)
     DevBuf masks, rle_words, rle_cnt, rle_cse, rle_tickets;  // K2b<false> masks and the K4 arrays
+    DevBuf gaps, arena, terms;  // fill_gaps on the device (refine.cuh)
     std::vector<cudaEvent_t> timing;  // 4 events per timed call (before K0, after K0, after K1, after K2)
     size_t timed_calls = 0;
     void destroy() {
@@ -131,7 +134,8 @@ struct Workspace {
         if (ev_fork) cudaEventDestroy(ev_fork);
         for (cudaEvent_t e : ev_join) cudaEventDestroy(e);
         DevBuf* all[] = {&ascii, &offsets, &pack, &inv, &sep, &wq, &ms, &l, &r, &out, &out2, &out3,
-                         &tmp64, &counters, &counters2, &masks, &rle_words, &rle_cnt, &rle_cse, &rle_tickets};
+                         &tmp64, &counters, &counters2, &masks, &rle_words, &rle_cnt, &rle_cse, &rle_tickets, &gaps, &arena,
+                         &terms};
         for (DevBuf* b : all) b->release();
         if (ev0) cudaEventDestroy(ev0);
         if (ev1) cudaEventDestroy(ev1);
@@ -159,6 +163,15 @@ struct kbo_index {
     uint32_t* d_links = nullptr;  // per node: LCS and the distances to the nearest smaller LCS on both sides
     uint8_t* d_blob = nullptr;    // the one allocation holding rank | links | lcs (one L2 access-policy window)
     uint4* d_pref = nullptr;      // MS states after PREF_LEN bases (k >= PREF_MIN_K)
+    // "select support" (BuildOpts.build_select) on the device: the colex-sorted node keys of the GPU builder
+    // (refine.cuh NodeKeysView); null for indexes made from parts or by the host builder
+    uint64_t* d_node_keys = nullptr;
+    uint8_t* d_node_len = nullptr;
+    uint32_t node_key_words = 0;
+    // the plain SubsetMatrix form in `host` (rows, LCS, nodes) is read back from the device on first use
+    // (ensure_host_mirror): kbo::map / kbo::call on a freshly built index never need it
+    std::atomic<bool> host_ready{true};
+    std::mutex host_mu;
     uint64_t blob_bytes = 0;
     float l2_hit_ratio = 0.f;     // 0: no persisting-L2 window available
     uint64_t rank_stride = 0;
@@ -432,6 +445,52 @@ static int build_links(kbo_index* ix, uint64_t n, bool with_prefix_table = true)
     return KBO_OK;
 }
 
+// Reads the plain SubsetMatrix form (4 bit rows, LCS bytes, C, and the stored nodes) back from the device arrays of an
+// index that the GPU builder made.  Host-side lookups (kbo_index_search / access_kmer / export_parts, the host
+// versions of fill_gaps and call_variants) call this first; the device paths never do.
+static int ensure_host_mirror(const kbo_index* cix) {
+    kbo_index* ix = const_cast<kbo_index*>(cix);
+    if (ix->host_ready.load(std::memory_order_acquire)) return KBO_OK;
+    std::lock_guard<std::mutex> g(ix->host_mu);
+    if (ix->host_ready.load(std::memory_order_acquire)) return KBO_OK;
+    DeviceGuard dg(ix->device);
+    if (!dg.ok) return fail(KBO_ERR_CUDA, "cudaSetDevice failed");
+    HostIndex& h = ix->host;
+    const uint64_t n = h.n_sets, stride = ix->rank_stride;
+    std::vector<uint64_t> rank((size_t)(4 * stride));
+    CUDA_TRY(cudaMemcpy(rank.data(), ix->d_rank, 4 * stride * 8, cudaMemcpyDeviceToHost));
+    h.lcs.resize((size_t)n);
+    CUDA_TRY(cudaMemcpy(h.lcs.data(), ix->d_lcs, n, cudaMemcpyDeviceToHost));
+    const size_t nw64 = (size_t)(n + 63) / 64 + 1;
+    for (int c = 0; c < 4; ++c) {
+        h.rows[c].assign(nw64, 0);
+        for (size_t w = 0; w < nw64; ++w) {  // the low half of a rank word holds the 32 row bits
+            const uint64_t lo = 2 * w < stride ? (uint32_t)rank[(size_t)(c * stride + 2 * w)] : 0;
+            const uint64_t hi = 2 * w + 1 < stride ? (uint32_t)rank[(size_t)(c * stride + 2 * w + 1)] : 0;
+            h.rows[c][w] = lo | (hi << 32);
+        }
+    }
+    h.finalize();
+    if (ix->d_node_keys) {
+        h.node_hi.resize((size_t)n);
+        h.node_len.resize((size_t)n);
+        if (ix->node_key_words == 1) {
+            CUDA_TRY(cudaMemcpy(h.node_hi.data(), ix->d_node_keys, n * 8, cudaMemcpyDeviceToHost));
+        } else {  // 128-bit keys: little-endian (lo, hi) pairs on the device
+            std::vector<uint64_t> keys((size_t)(2 * n));
+            CUDA_TRY(cudaMemcpy(keys.data(), ix->d_node_keys, n * 16, cudaMemcpyDeviceToHost));
+            h.node_lo.resize((size_t)n);
+            for (size_t i = 0; i < (size_t)n; ++i) {
+                h.node_lo[i] = keys[2 * i];
+                h.node_hi[i] = keys[2 * i + 1];
+            }
+        }
+        CUDA_TRY(cudaMemcpy(h.node_len.data(), ix->d_node_len, n, cudaMemcpyDeviceToHost));
+    }
+    ix->host_ready.store(true, std::memory_order_release);
+    return KBO_OK;
+}
+
 static int upload_index(kbo_index* ix) {
     const HostIndex& h = ix->host;
     const uint64_t n = h.n_sets;
@@ -603,8 +662,16 @@ static int build_index_gpu_typed(kbo_index* ix, const uint8_t* const* seqs, cons
     CUDA_TRY(tmp.alloc(&d_Dlen, nD));
     CUDA_TRY(cudaMemcpy(d_Dkey, h_Dkey.data(), nD * sizeof(K), cudaMemcpyHostToDevice));
     CUDA_TRY(cudaMemcpy(d_Dlen, h_Dlen.data(), nD, cudaMemcpyHostToDevice));
-    CUDA_TRY(tmp.alloc(&d_Pkey, n));
-    CUDA_TRY(tmp.alloc(&d_Plen, n));
+    if (keep_nodes && !device_only) {  // "select support": the sorted nodes stay on the device with the index
+        CUDA_TRY(cudaMalloc((void**)&ix->d_node_keys, (n ? n : 1) * sizeof(K)));
+        CUDA_TRY(cudaMalloc((void**)&ix->d_node_len, n ? n : 1));
+        ix->node_key_words = sizeof(K) / 8;
+        d_Pkey = reinterpret_cast<K*>(ix->d_node_keys);
+        d_Plen = ix->d_node_len;
+    } else {
+        CUDA_TRY(tmp.alloc(&d_Pkey, n));
+        CUDA_TRY(tmp.alloc(&d_Plen, n));
+    }
     merge_nodes_kernel<K><<<(unsigned)((n + 255) / 256), 256>>>(d_R, nR, d_Dkey, d_Dlen, nD, k, d_Pkey, d_Plen);
     LAUNCHED();
     bt.lap("dummies, merge");
@@ -649,37 +716,9 @@ static int build_index_gpu_typed(kbo_index* ix, const uint8_t* const* seqs, cons
     ix->view.k = k;
     bt.lap("lcs, labels, rank words");
     if (device_only) { const int rc = build_links(ix, n, false); bt.lap("links (device-only index)"); return rc; }
-    std::vector<uint32_t> rows32((size_t)(4 * stride));
-    CUDA_TRY(cudaMemcpy(rows32.data(), d_rows32, 4 * stride * 4, cudaMemcpyDeviceToHost));
-    h.lcs.resize((size_t)n);
-    CUDA_TRY(cudaMemcpy(h.lcs.data(), ix->d_lcs, n, cudaMemcpyDeviceToHost));
-    const size_t nw64 = (size_t)(n + 63) / 64 + 1;
-    for (int c = 0; c < 4; ++c) {
-        h.rows[c].assign(nw64, 0);
-        for (size_t w = 0; w < nw64; ++w) {
-            const uint64_t lo = 2 * w < stride ? rows32[(size_t)(c * stride + 2 * w)] : 0;
-            const uint64_t hi = 2 * w + 1 < stride ? rows32[(size_t)(c * stride + 2 * w + 1)] : 0;
-            h.rows[c][w] = lo | (hi << 32);
-        }
-    }
-    h.finalize();
-    if (keep_nodes) {  // "select support": the nodes themselves, for O(1) access_kmer on the host
-        h.node_hi.resize((size_t)n);
-        h.node_len.resize((size_t)n);
-        if (BITS == 64) {
-            CUDA_TRY(cudaMemcpy(h.node_hi.data(), d_Pkey, n * 8, cudaMemcpyDeviceToHost));
-        } else {  // 128-bit keys: little-endian (lo, hi) pairs on the device
-            std::vector<K> keys((size_t)n);
-            CUDA_TRY(cudaMemcpy(keys.data(), d_Pkey, n * sizeof(K), cudaMemcpyDeviceToHost));
-            h.node_lo.resize((size_t)n);
-            for (size_t i = 0; i < (size_t)n; ++i) {
-                h.node_hi[i] = (uint64_t)((u128)keys[i] >> 64);
-                h.node_lo[i] = (uint64_t)keys[i];
-            }
-        }
-        CUDA_TRY(cudaMemcpy(h.node_len.data(), d_Plen, n, cudaMemcpyDeviceToHost));
-    }
-    bt.lap("host mirror (rows, lcs, nodes)");
+    // the plain SubsetMatrix form (search / access_kmer / export on the host) is read back only if somebody asks
+    ix->host_ready.store(false, std::memory_order_release);
+    if (ix->d_node_keys) ix->device_bytes += n * (sizeof(K) + 1);
     const int rc_links = build_links(ix, n);
     bt.lap("rank2, links, prefix table");
     return rc_links;
@@ -1215,6 +1254,8 @@ void kbo_index_free(kbo_index* ix) {
         for (PinnedBuf& pb : ix->pinned_pool) if (pb.p) cudaFreeHost(pb.p);
         if (ix->d_blob) cudaFree(ix->d_blob);
         if (ix->d_pref) cudaFree(ix->d_pref);
+        if (ix->d_node_keys) cudaFree(ix->d_node_keys);
+        if (ix->d_node_len) cudaFree(ix->d_node_len);
     }
     delete ix;
 }
@@ -1227,6 +1268,7 @@ uint64_t kbo_index_device_bytes(const kbo_index* ix) { return ix ? ix->device_by
 
 int kbo_index_export_parts(const kbo_index* ix, uint64_t* rows[4], uint8_t* lcs, uint64_t C_out[4]) {
     if (!ix) return fail(KBO_ERR_BAD_ARGUMENT, "index is null");
+    { const int rc = ensure_host_mirror(ix); if (rc) return rc; }
     const size_t nw = (size_t)(ix->host.n_sets + 63) / 64;
     if (rows)
         for (int c = 0; c < 4; ++c)
@@ -1240,6 +1282,7 @@ int kbo_index_export_parts(const kbo_index* ix, uint64_t* rows[4], uint8_t* lcs,
 int kbo_index_access_kmer(const kbo_index* ix, uint64_t colex, uint8_t* out_k) {
     if (!ix || !out_k) return fail(KBO_ERR_BAD_ARGUMENT, "null argument");
     if (colex >= ix->host.n_sets) return fail(KBO_ERR_PANIC, "access_kmer: colex rank out of range");
+    { const int rc = ensure_host_mirror(ix); if (rc) return rc; }
     ix->host.access_kmer(colex, out_k);
     return KBO_OK;
 }
@@ -1247,6 +1290,7 @@ int kbo_index_access_kmer(const kbo_index* ix, uint64_t colex, uint8_t* out_k) {
 int kbo_index_search(const kbo_index* ix, const uint8_t* pattern, uint64_t len, int* found, uint64_t* l, uint64_t* r) {
     if (!ix || !found || (!pattern && len)) return fail(KBO_ERR_BAD_ARGUMENT, "null argument");
     uint64_t a = 0, b = 0;
+    { const int rc = ensure_host_mirror(ix); if (rc) return rc; }
     *found = ix->host.search(pattern, len, &a, &b) ? 1 : 0;
     if (*found) {
         if (l) *l = a;
@@ -2249,8 +2293,13 @@ struct HostMs {
 static int scan_candidates(kbo_index* ix, Workspace* ws, uint64_t len, uint32_t thr, std::vector<VariantCandidate64>* out);
 
 // One query through K0 -> K1 (with intervals) [-> K2 when thr != 0] [-> candidate scan]; results copied to the host.
+static int device_fill_gaps(kbo_index* ix, Workspace* ws, uint64_t len, uint32_t thr, double max_err_prob);
+
+// fill_on_device (with the error probability in fill_p): fill_gaps runs on the device on the characters K2 wrote, and
+// (d, l, r) stay there -- only the refined characters (and the candidates) come back.
 static int run_single_full(kbo_index* ix, const uint8_t* seq, uint64_t len, uint32_t thr, HostMs* out,
-                           uint32_t cand_thr = 0, std::vector<VariantCandidate64>* cands = nullptr) {
+                           uint32_t cand_thr = 0, std::vector<VariantCandidate64>* cands = nullptr,
+                           bool fill_on_device = false, double fill_p = 0.0) {
     DeviceGuard dg(ix->device);
     if (!dg.ok) return fail(KBO_ERR_CUDA, "cudaSetDevice failed");
     Workspace* ws = nullptr;
@@ -2265,9 +2314,11 @@ static int run_single_full(kbo_index* ix, const uint8_t* seq, uint64_t len, uint
         CUDA_TRY(ws->ascii.ensure(len, st));
         CUDA_TRY(ws->offsets.ensure(16, st));
         CUDA_TRY(ws->out.ensure(len + 16, st));
-        CUDA_TRY(ws->h_d.ensure(len));
-        CUDA_TRY(ws->h_l.ensure(len * 4));
-        CUDA_TRY(ws->h_r.ensure(len * 4));
+        if (!fill_on_device) {
+            CUDA_TRY(ws->h_d.ensure(len));
+            CUDA_TRY(ws->h_l.ensure(len * 4));
+            CUDA_TRY(ws->h_r.ensure(len * 4));
+        }
         if (thr) CUDA_TRY(ws->h_chars.ensure(len));
         CUDA_TRY(cudaMemcpyAsync(ws->ascii.p, seq, len, cudaMemcpyHostToDevice, st));
         CUDA_TRY(cudaMemcpyAsync(ws->offsets.p, offsets, 16, cudaMemcpyHostToDevice, st));
@@ -2279,13 +2330,23 @@ static int run_single_full(kbo_index* ix, const uint8_t* seq, uint64_t len, uint
         if (thr) {
             rc2 = run_derand_translate(ix, ws, qv, g, thr, ws->out.as<uint8_t>(), 0);
             if (rc2) return rc2;
-            CUDA_TRY(cudaMemcpyAsync(ws->h_chars.p, ws->out.p, len, cudaMemcpyDeviceToHost, st));
+            if (!fill_on_device) CUDA_TRY(cudaMemcpyAsync(ws->h_chars.p, ws->out.p, len, cudaMemcpyDeviceToHost, st));
         }
         // a single query has its only separator at position len: padded == unpadded below len
-        CUDA_TRY(cudaMemcpyAsync(ws->h_d.p, ws->ms.p, len, cudaMemcpyDeviceToHost, st));
-        CUDA_TRY(cudaMemcpyAsync(ws->h_l.p, ws->l.p, len * 4, cudaMemcpyDeviceToHost, st));
-        CUDA_TRY(cudaMemcpyAsync(ws->h_r.p, ws->r.p, len * 4, cudaMemcpyDeviceToHost, st));
-        if (cands) return scan_candidates(ix, ws, len, cand_thr, cands);  // (synchronises the stream)
+        if (!fill_on_device) {
+            CUDA_TRY(cudaMemcpyAsync(ws->h_d.p, ws->ms.p, len, cudaMemcpyDeviceToHost, st));
+            CUDA_TRY(cudaMemcpyAsync(ws->h_l.p, ws->l.p, len * 4, cudaMemcpyDeviceToHost, st));
+            CUDA_TRY(cudaMemcpyAsync(ws->h_r.p, ws->r.p, len * 4, cudaMemcpyDeviceToHost, st));
+        }
+        if (cands) {
+            rc2 = scan_candidates(ix, ws, len, cand_thr, cands);  // (synchronises the stream)
+            if (rc2) return rc2;
+        }
+        if (fill_on_device) {
+            rc2 = device_fill_gaps(ix, ws, len, thr, fill_p);
+            if (rc2) return rc2;
+            CUDA_TRY(cudaMemcpyAsync(ws->h_chars.p, ws->out.p, len, cudaMemcpyDeviceToHost, st));
+        }
         CUDA_TRY(cudaStreamSynchronize(st));
         return KBO_OK;
     };
@@ -2328,6 +2389,122 @@ static int scan_candidates(kbo_index* ix, Workspace* ws, uint64_t len, uint32_t 
         cap = n;  // more candidates than the first guess: once more with room for all of them
     }
     return fail(KBO_ERR_CUDA, "candidate scan did not converge");
+}
+
+// gap_filling::fill_gaps (gap_filling.rs:444-526) on the device, in place on the characters in ws->out, from the
+// intervals K1 left in ws->l / ws->r and the sequence in ws->ascii (refine.cuh).  Synchronises the stream twice
+// (number of gaps, panic word).
+static const char* refine_panic_text(unsigned code) {
+    switch (code) {
+        case RP_BRIDGE_ARGS: return "gap_filling.rs:305-310";
+        case RP_RIGHT_ARGS: return "gap_filling.rs:25-27";
+        case RP_RIGHT_OOB: return "gap_filling.rs:33 index out of bounds";
+        case RP_LEFT_ARGS: return "gap_filling.rs:50-52";
+        case RP_LEFT_OOB: return "gap_filling.rs:58 index out of bounds";
+        case RP_TRIM_UNDERFLOW: return "gap_filling.rs:335 usize underflow";
+        case RP_TRIM_RANGE: return "gap_filling.rs:336 slice out of range";
+        case RP_IDX_UNDERFLOW: return "gap_filling.rs:357 usize underflow";
+        default: return "gap_filling.rs: panic";
+    }
+}
+static const std::vector<double>& gap_run_terms() {
+    static const std::vector<double> terms = []() {
+        std::vector<double> t(544);  // (1/4)^m underflows to zero from m = 538 on: the term is -0.0 beyond the table
+        for (size_t m = 0; m < t.size(); ++m) t[m] = gap_run_log_term(m);
+        return t;
+    }();
+    return terms;
+}
+static int device_fill_gaps(kbo_index* ix, Workspace* ws, uint64_t len, uint32_t thr, double max_err_prob) {
+    cudaStream_t st = ws->stream;
+    if (len == 0) return fail(KBO_ERR_PANIC, "gap_filling.rs:453-454");
+    if (len < thr) return fail(KBO_ERR_PANIC, "gap_filling.rs:467 usize underflow");
+    if (len <= 2ull * thr + 1) return KBO_OK;  // the scan of gap_filling.rs:458 visits no position
+    const uint64_t n_pos = len - 2ull * thr - 1;
+    CUDA_TRY(ws->counters2.ensure(32, st));
+    CUDA_TRY(ws->h_count.ensure(32));
+    uint32_t cap = (uint32_t)std::min<uint64_t>(len / 16 + 4096, 1u << 30), n_gaps = 0;
+    for (int attempt = 0;; ++attempt) {
+        if (attempt == 2) return fail(KBO_ERR_CUDA, "gap scan did not converge");
+        CUDA_TRY(ws->gaps.ensure((uint64_t)cap * sizeof(uint2), st));
+        CUDA_TRY(cudaMemsetAsync(ws->counters2.p, 0, 4, st));
+        gap_list_kernel<<<(unsigned)((n_pos + 255) / 256), 256, 0, st>>>(ws->out.as<uint8_t>(), len, thr, ws->gaps.as<uint2>(), cap,
+                                                                        ws->counters2.as<unsigned int>());
+        LAUNCHED();
+        CUDA_TRY(cudaGetLastError());
+        CUDA_TRY(cudaMemcpyAsync(ws->h_count.p, ws->counters2.p, 4, cudaMemcpyDeviceToHost, st));
+        CUDA_TRY(cudaStreamSynchronize(st));
+        n_gaps = *ws->h_count.as<uint32_t>();
+        if (n_gaps <= cap) break;
+        cap = n_gaps;
+    }
+    if (n_gaps == 0) return KBO_OK;
+    const std::vector<double>& terms = gap_run_terms();
+    CUDA_TRY(ws->terms.ensure(terms.size() * 8, st));
+    CUDA_TRY(cudaMemcpyAsync(ws->terms.p, terms.data(), terms.size() * 8, cudaMemcpyHostToDevice, st));
+    CUDA_TRY(ws->arena.ensure(len + (uint64_t)n_gaps * thr + 16, st));  // gaps are disjoint: sum of (thr + length) fits
+    unsigned long long init[2] = {0ull, ~0ull};  // arena bytes used, panic word
+    CUDA_TRY(cudaMemcpyAsync(ws->counters2.as<uint8_t>() + 8, init, 16, cudaMemcpyHostToDevice, st));
+    FillGapsParams fp;
+    fp.ix = ix->view;
+    fp.nk.keys = ix->d_node_keys;
+    fp.nk.len = ix->d_node_len;
+    fp.nk.words = ix->node_key_words;
+    fp.l = ws->l.as<uint32_t>();
+    fp.r = ws->r.as<uint32_t>();
+    fp.ref = ws->ascii.as<uint8_t>();
+    fp.aln = ws->out.as<uint8_t>();
+    fp.n = len;
+    fp.thr = thr;
+    fp.run_terms = ws->terms.as<double>();
+    fp.n_terms = (uint32_t)terms.size();
+    fp.log_bound = std::log1p(-max_err_prob);
+    fp.gaps = ws->gaps.as<uint2>();
+    fp.n_gaps = n_gaps;
+    fp.arena = ws->arena.as<uint8_t>();
+    fp.arena_used = reinterpret_cast<unsigned long long*>(ws->counters2.as<uint8_t>() + 8);
+    fp.panic = reinterpret_cast<unsigned long long*>(ws->counters2.as<uint8_t>() + 16);
+    const unsigned blocks = (unsigned)std::min<uint64_t>((n_gaps + 63) / 64, 148ull * 32);
+    fill_gaps_kernel<<<blocks, 64, 0, st>>>(fp);
+    LAUNCHED();
+    CUDA_TRY(cudaGetLastError());
+    CUDA_TRY(cudaMemcpyAsync(ws->h_count.p, fp.panic, 8, cudaMemcpyDeviceToHost, st));
+    CUDA_TRY(cudaStreamSynchronize(st));
+    const unsigned long long panic = *ws->h_count.as<unsigned long long>();
+    if (panic != ~0ull) return fail(KBO_ERR_PANIC, refine_panic_text((unsigned)(panic & 0xffu)));
+    return KBO_OK;
+}
+
+// SbwtIndex::access_kmer for the nodes of all variant candidates (variant_calling.rs:276) from the node keys on the device
+static int device_access_kmers(kbo_index* ix, const std::vector<VariantCandidate64>& cands, uint32_t k, uint8_t* out) {
+    if (cands.empty()) return KBO_OK;
+    DeviceGuard dg(ix->device);
+    if (!dg.ok) return fail(KBO_ERR_CUDA, "cudaSetDevice failed");
+    Workspace* ws = nullptr;
+    int rc = acquire_ws(ix, &ws);
+    if (rc) return rc;
+    cudaStream_t st = ws->stream;
+    const uint64_t nc = cands.size();
+    std::vector<uint32_t> nodes(nc);
+    for (uint64_t c = 0; c < nc; ++c) nodes[c] = (uint32_t)cands[c].node;
+    auto body = [&]() -> int {
+        CUDA_TRY(ws->out2.ensure(nc * 4, st));
+        CUDA_TRY(ws->out3.ensure(nc * k, st));
+        CUDA_TRY(cudaMemcpyAsync(ws->out2.p, nodes.data(), nc * 4, cudaMemcpyHostToDevice, st));
+        NodeKeysView nk;
+        nk.keys = ix->d_node_keys;
+        nk.len = ix->d_node_len;
+        nk.words = ix->node_key_words;
+        access_kmers_kernel<<<(unsigned)((nc + 127) / 128), 128, 0, st>>>(nk, k, ws->out2.as<uint32_t>(), nc, ws->out3.as<uint8_t>());
+        LAUNCHED();
+        CUDA_TRY(cudaGetLastError());
+        CUDA_TRY(cudaMemcpyAsync(out, ws->out3.p, nc * k, cudaMemcpyDeviceToHost, st));
+        CUDA_TRY(cudaStreamSynchronize(st));
+        return KBO_OK;
+    };
+    rc = body();
+    release_ws(ix, ws);
+    return rc;
 }
 
 // One query through K0 -> K1 (with intervals) -> the candidate scan on the device: only the candidates come back to
@@ -2397,8 +2574,17 @@ static int call_impl(kbo_index* query_index, const uint8_t* ref_seq, uint64_t le
                                               nullptr, nullptr);
         if (r2 && !inner_rc) inner_rc = r2;
     };
+    const bool dev_access = query_index->d_node_keys && g_device_refine.load();
+    AccessKmersFn access = [&](const std::vector<VariantCandidate64>& cs, uint32_t k, uint8_t* out) {
+        const int r2 = device_access_kmers(query_index, cs, k, out);
+        if (r2 && !inner_rc) inner_rc = r2;
+    };
+    if (!dev_access) {
+        rc = ensure_host_mirror(query_index);
+        if (rc) { kbo_index_free(ref_index); return rc; }
+    }
     try {
-        *variants = call_variants_from(query_index->host, cands, ref_seq, len, thr, kmer_ms);
+        *variants = call_variants_from(query_index->host, cands, ref_seq, len, thr, kmer_ms, dev_access ? &access : nullptr);
     } catch (const RefinePanic& p) {
         kbo_index_free(ref_index);
         return fail(KBO_ERR_PANIC, p.what);
@@ -2464,10 +2650,13 @@ int kbo_map(const kbo_index* cix, const uint8_t* ref_seq, uint64_t len, double m
         rc = host_threshold(ix->host.k, ix->host.n_kmers, 4, max_error_prob, &call_thr);  // variant_calling.rs:260
         if (rc) return rc;
     }
+    // fill_gaps (lib.rs:743-744) on the device when the index keeps its node keys there; else on host threads
+    const bool dev_fill = do_fill_gaps && ix->d_node_keys && g_device_refine.load();
     rc = run_single_full(ix, ref_seq, len, thr, &ms, (uint32_t)std::min<uint64_t>(call_thr, 255),
-                         do_call_variants ? &cands : nullptr);
+                         do_call_variants ? &cands : nullptr, dev_fill, max_error_prob);
     if (rc) return rc;
-    bt.lap("map: K0, K1 (d,l,r), K2b, candidate scan + copy-out");
+    bt.lap(dev_fill ? "map: K0, K1 (d,l,r), K2b, candidate scan, fill_gaps (device) + copy-out"
+                    : "map: K0, K1 (d,l,r), K2b, candidate scan + copy-out");
     std::vector<uint8_t> aln(ms.chars, ms.chars + len);
     MsArrays view;
     view.d = ms.d;
@@ -2475,9 +2664,12 @@ int kbo_map(const kbo_index* cix, const uint8_t* ref_seq, uint64_t len, double m
     view.r = ms.r;
     view.n = len;
     try {
-        if (do_fill_gaps)  // lib.rs:743-744; gaps are independent: bridged on build_opts.num_threads host threads
+        if (do_fill_gaps && !dev_fill) {  // gaps are independent: bridged on kbo_set_refine_threads host threads
+            rc = ensure_host_mirror(ix);
+            if (rc) return rc;
             fill_gaps(&aln, view, ref_seq, len, ix->host, thr, max_error_prob, tuned_refine_threads(ix));
-        bt.lap("map: fill_gaps (host)");
+            bt.lap("map: fill_gaps (host)");
+        }
         if (do_call_variants) {                                                             // lib.rs:749-751
             std::vector<VariantRec> vars;
             ms.release();  // (the arrays are not needed any more; call_impl takes workspaces of its own)
@@ -2592,6 +2784,7 @@ int kbo_get_ms_counters(const kbo_index* cix, kbo_ms_counters* out) {
 }
 int kbo_set_chunk_len(uint32_t chunk_len) { g_chunk_len = chunk_len; return KBO_OK; }
 int kbo_set_refine_threads(uint32_t n) { g_refine_threads = n > 256 ? 256 : n; return KBO_OK; }
+int kbo_set_device_refine(int enabled) { g_device_refine = enabled ? 1 : 0; return KBO_OK; }
 int kbo_index_set_tuning(kbo_index* ix, int key, int64_t value) {
     if (!ix) return fail(KBO_ERR_BAD_ARGUMENT, "index is null");
     switch (key) {

@@ -211,7 +211,8 @@ std::vector<VariantCandidate64> find_variant_candidates(const MsArrays& ms, uint
 }
 
 std::vector<VariantRec> call_variants_from(const HostIndex& sbwt_ref, const std::vector<VariantCandidate64>& cands,
-                                           const uint8_t* query, uint64_t len, uint64_t thr, const KmerMsFn& kmer_ms) {
+                                           const uint8_t* query, uint64_t len, uint64_t thr, const KmerMsFn& kmer_ms,
+                                           const AccessKmersFn* access) {
     (void)len;
     const uint32_t k = sbwt_ref.k;
     std::vector<VariantRec> calls;
@@ -230,8 +231,9 @@ std::vector<VariantRec> call_variants_from(const HostIndex& sbwt_ref, const std:
             std::fill(dst, dst + dollars, (uint8_t)'$');
             std::copy(query, query + j + 1, dst + dollars);
         }
-        sbwt_ref.access_kmer(cands[c].node, rk.data() + c * k);
+        if (!access) sbwt_ref.access_kmer(cands[c].node, rk.data() + c * k);
     }
+    if (access) (*access)(cands, k, rk.data());
     kmer_ms(0, qk.data(), nc, k, ms_q_vs_ref.data());
     kmer_ms(1, rk.data(), nc, k, ms_r_vs_query.data());
     for (uint64_t c = 0; c < nc; ++c) {
@@ -280,6 +282,10 @@ void add_variants(Bytes* translation, const std::vector<VariantRec>& variants) {
 // ---------------------------------------------------------------------------
 // gap_filling.rs:444-526
 // ---------------------------------------------------------------------------
+double gap_run_log_term(uint64_t m) {  // gap_filling.rs:489-501: ln_1p(-(exp(ln 1 - ln 4)).powi(m)), m = run + 1 + 1
+    return std::log1p(-__builtin_powi(std::exp(std::log(1.0) - std::log(4.0)), (int)m));
+}
+
 // The gaps are found on the translation as it comes in: filling one only rewrites positions inside it, which the
 // scan never looks at again, so the list of gaps does not depend on the fills and every gap can be bridged
 // independently (num_threads > 1: contiguous ranges of the list on host threads; a reference panic is reported for the
@@ -319,7 +325,7 @@ void fill_gaps(Bytes* translation, const MsArrays& noisy_ms, const uint8_t* ref_
             if (same[w] && same[w + 1]) {
                 ++run;
             } else {
-                if (run > 0) log_probs += 1.0 * std::log1p(-__builtin_powi(std::exp(std::log(1.0) - std::log(4.0)), (int)(run + 1) + 1));
+                if (run > 0) log_probs += 1.0 * gap_run_log_term(run + 2);
                 run = 0;
             }
         }

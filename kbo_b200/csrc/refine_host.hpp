@@ -54,9 +54,14 @@ struct VariantCandidate64 {
 };
 // the candidate scan on host arrays (kbo::map, which needs the arrays on the host anyway for fill_gaps)
 std::vector<VariantCandidate64> find_variant_candidates(const MsArrays& ms_vs_ref, uint64_t len, uint32_t k, uint64_t threshold);
-// call_variants given the candidates in increasing i (kbo::call finds them on the device: variant_candidates_kernel)
+// SbwtIndex::access_kmer (variant_calling.rs:276) for the nodes of all candidates at once: k bytes each into `out`
+// (the C ABI layer implements it with access_kmers_kernel when the index keeps its node keys on the device)
+typedef std::function<void(const std::vector<VariantCandidate64>& cands, uint32_t k, uint8_t* out)> AccessKmersFn;
+// call_variants given the candidates in increasing i (kbo::call finds them on the device: variant_candidates_kernel);
+// access == nullptr: the k-mers come from sbwt_ref on the host, else sbwt_ref is only asked for k
 std::vector<VariantRec> call_variants_from(const HostIndex& sbwt_ref, const std::vector<VariantCandidate64>& cands,
-                                           const uint8_t* query, uint64_t len, uint64_t threshold, const KmerMsFn& kmer_ms);
+                                           const uint8_t* query, uint64_t len, uint64_t threshold, const KmerMsFn& kmer_ms,
+                                           const AccessKmersFn* access = nullptr);
 
 // variant_calling::call_variants (variant_calling.rs:249-294).  `ms_vs_ref` = MS of `query` against
 // `sbwt_ref` (already computed on the GPU); `threshold` = random_match_threshold(k, sbwt_ref.n_kmers, 4, p).
@@ -65,6 +70,10 @@ std::vector<VariantRec> call_variants(const HostIndex& sbwt_ref, const MsArrays&
 
 // translate::add_variants (translate.rs:350-386), in place on a byte alignment.
 void add_variants(std::vector<uint8_t>* translation, const std::vector<VariantRec>& variants);
+
+// ln(1 - (1/4)^m) exactly as gap_filling.rs:489-501 evaluates it for a run of m - 2 consecutive agreements; the device
+// version of fill_gaps reads these values from a table made with this function
+double gap_run_log_term(uint64_t m);
 
 // gap_filling::fill_gaps (gap_filling.rs:444-526), in place on a byte alignment.
 void fill_gaps(std::vector<uint8_t>* translation, const MsArrays& noisy_ms, const uint8_t* ref_seq, uint64_t len,

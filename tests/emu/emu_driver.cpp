@@ -10,12 +10,14 @@
 // ===========================================================================
 #define KBO_HOST_EMU 1
 #include <algorithm>
+#include <cmath>
 #include <cstdio>
 #include <string>
 
 #include "../../kbo_b200/csrc/host_layout.hpp"
 #include "../../kbo_b200/csrc/kernels.cuh"
 #include "../../kbo_b200/csrc/fused.cuh"
+#include "../../kbo_b200/csrc/refine.cuh"
 #include "../../kbo_b200/csrc/refine_host.hpp"
 #include "../../kbo_b200/csrc/sbwt_host.hpp"
 
@@ -443,6 +445,70 @@ static void emu_single_ms(EmuIndex* e, const uint8_t* seq, uint64_t len, uint32_
     }
 }
 
+// ---- refinement on the "device" (refine.cuh), as capi.cu device_fill_gaps / device_access_kmers drive it ----------
+static int g_emu_device_refine = 0;
+extern "C" void emu_set_device_refine(int v) { g_emu_device_refine = v; }
+static uint64_t g_emu_device_gaps = 0;
+extern "C" uint64_t emu_device_gap_count() { return g_emu_device_gaps; }
+
+struct EmuNodeKeys {
+    std::vector<uint64_t> keys;
+    NodeKeysView view;
+};
+static bool emu_node_keys(const EmuIndex* e, EmuNodeKeys* nk) {
+    const HostIndex& h = e->host;
+    if (h.node_len.empty()) return false;
+    const size_t n = (size_t)h.n_sets;
+    if (h.node_lo.empty()) {
+        nk->keys = h.node_hi;
+        nk->view.words = 1;
+    } else {
+        nk->keys.resize(2 * n);
+        for (size_t i = 0; i < n; ++i) { nk->keys[2 * i] = h.node_lo[i]; nk->keys[2 * i + 1] = h.node_hi[i]; }
+        nk->view.words = 2;
+    }
+    nk->view.keys = nk->keys.data();
+    nk->view.len = h.node_len.data();
+    return true;
+}
+
+static void emu_device_fill_gaps(EmuIndex* e, const EmuNodeKeys& nk, std::vector<uint8_t>* chars, const MsArrays& ms,
+                                 const uint8_t* ref_seq, uint64_t len, uint32_t thr, double p) {
+    if (len == 0) throw RefinePanic{"gap_filling.rs:453-454"};
+    if (len < thr) throw RefinePanic{"gap_filling.rs:467 usize underflow"};
+    if (len <= 2ull * thr + 1) return;
+    const uint64_t n_pos = len - 2ull * thr - 1;
+    std::vector<uint2> gaps((size_t)len);
+    unsigned int n_gaps = 0;
+    emu_launch_seq((unsigned)((n_pos + 255) / 256), 256,
+                   [&]() { gap_list_kernel(chars->data(), len, thr, gaps.data(), (uint32_t)gaps.size(), &n_gaps); });
+    g_emu_device_gaps += n_gaps;
+    if (!n_gaps) return;
+    std::vector<double> terms(544);
+    for (size_t m = 0; m < terms.size(); ++m) terms[m] = gap_run_log_term(m);
+    std::vector<uint8_t> arena((size_t)(len + (uint64_t)n_gaps * thr + 16));
+    unsigned long long used = 0, panic = ~0ull;
+    FillGapsParams fp;
+    fp.ix = e->view;
+    fp.nk = nk.view;
+    fp.l = ms.l; fp.r = ms.r;
+    fp.ref = ref_seq;
+    fp.aln = chars->data();
+    fp.n = len;
+    fp.thr = thr;
+    fp.run_terms = terms.data();
+    fp.n_terms = (uint32_t)terms.size();
+    fp.log_bound = std::log1p(-p);
+    fp.gaps = gaps.data();
+    fp.n_gaps = n_gaps;
+    fp.arena = arena.data();
+    fp.arena_used = &used;
+    fp.panic = &panic;
+    emu_launch_seq(3, 64, [&]() { fill_gaps_kernel(fp); });  // (fewer threads than gaps: the grid-stride loop runs)
+    if (used > arena.size()) throw RefinePanic{"emu: arena overflow"};
+    if (panic != ~0ull) throw RefinePanic{"gap_filling.rs panic on the device"};
+}
+
 static std::vector<VariantRec> emu_call_impl(EmuIndex* q, const uint8_t* ref_seq, uint64_t len, uint64_t thr,
                                              uint32_t build_k, int revcomp, const MsArrays& ms) {
     EmuIndex refix;
@@ -459,6 +525,16 @@ static std::vector<VariantRec> emu_call_impl(EmuIndex* q, const uint8_t* ref_seq
         stage_and_ms(which == 0 ? q : &refix, kmers, off.data(), n_kmers, 0, false, nullptr, &s);
         unpad<uint8_t>(s.ms.data(), s.qv, d_out);
     };
+    EmuNodeKeys nk;
+    if (g_emu_device_refine && emu_node_keys(q, &nk)) {
+        AccessKmersFn access = [&](const std::vector<VariantCandidate64>& cs, uint32_t k, uint8_t* out) {
+            std::vector<uint32_t> nodes(cs.size());
+            for (size_t i = 0; i < cs.size(); ++i) nodes[i] = (uint32_t)cs[i].node;
+            emu_launch_seq((unsigned)((cs.size() + 127) / 128), 128,
+                           [&]() { access_kmers_kernel(nk.view, k, nodes.data(), nodes.size(), out); });
+        };
+        return call_variants_from(q->host, find_variant_candidates(ms, len, q->host.k, thr), ref_seq, len, thr, fn, &access);
+    }
     return call_variants(q->host, ms, ref_seq, len, thr, fn);
 }
 
@@ -504,7 +580,9 @@ int emu_map(void* h_query, const uint8_t* ref_seq, uint64_t len, uint32_t thr, u
         emu_single_ms(q, ref_seq, len, thr, &d, &l, &r, &chars);
         MsArrays ms;
         ms.d = d.data(); ms.l = l.data(); ms.r = r.data(); ms.n = len;
-        if (do_fill) fill_gaps(&chars, ms, ref_seq, len, q->host, thr, p, 4);  // the threaded branch when there are >= 64 gaps
+        EmuNodeKeys nk;
+        if (do_fill && g_emu_device_refine && emu_node_keys(q, &nk)) emu_device_fill_gaps(q, nk, &chars, ms, ref_seq, len, thr, p);
+        else if (do_fill) fill_gaps(&chars, ms, ref_seq, len, q->host, thr, p, 4);  // the threaded branch when there are >= 64 gaps
         if (do_call) add_variants(&chars, emu_call_impl(q, ref_seq, len, call_thr ? call_thr : thr, build_k, revcomp, ms));
         for (uint64_t i = 0; i < len; ++i) {
             const uint8_t a = chars[i];

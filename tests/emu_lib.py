@@ -17,7 +17,7 @@ _CSRC = os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 
 def build_emu():
     srcs = [os.path.join(_DIR, "emu_driver.cpp"), os.path.join(_DIR, "host_emu.hpp")] + [
-        os.path.join(_CSRC, f) for f in ("kernels.cuh", "host_layout.hpp", "sbwt_host.hpp", "sbwt_host.cpp", "refine_host.hpp",
+        os.path.join(_CSRC, f) for f in ("kernels.cuh", "fused.cuh", "refine.cuh", "host_layout.hpp", "sbwt_host.hpp", "sbwt_host.cpp", "refine_host.hpp",
                                         "refine_host.cpp")]
     stale = (not os.path.exists(_SO)) or any(os.path.getmtime(s) > os.path.getmtime(_SO) for s in srcs)
     if stale:
@@ -64,6 +64,8 @@ def lib():
         L.emu_rle_batch.restype = C.c_uint64
         L.emu_rle_batch.argtypes = [u8p, u64p, C.c_uint64, C.c_uint32, u64p, C.c_uint64, u64p]
         L.emu_set_rank2.argtypes = [C.c_int]
+        L.emu_set_device_refine.argtypes = [C.c_int]
+        L.emu_device_gap_count.restype = C.c_uint64
         L.emu_set_fused.argtypes = [C.c_int, C.c_uint32, C.c_int]
         L.emu_fused_launches.restype = C.c_uint64
         L.emu_fused_tiles.restype = C.c_uint64
@@ -72,6 +74,16 @@ def lib():
         L.emu_find_batch.argtypes = [C.c_void_p, u8p, u64p, C.c_uint64, C.c_uint32, C.c_uint32, u64p, C.c_uint64, u64p]
         _lib = L
     return _lib
+
+
+def set_device_refine(on):
+    """map / call: fill_gaps and access_kmer through the kernels of refine.cuh (as capi.cu does when the index keeps
+    its node keys on the device) instead of refine_host.cpp."""
+    lib().emu_set_device_refine(int(bool(on)))
+
+
+def device_gap_count():
+    return int(lib().emu_device_gap_count())
 
 
 def _p(a, ty):

@@ -382,6 +382,12 @@ def test_config1_full_size_map_bit_exact():
     # gaps bridged on 8 host threads (sbwt_build_opts.num_threads): same result
     threaded = api.MapOpts(sbwt_build_opts=api.BuildOpts(k=31, build_select=True, num_threads=8))
     assert api.map(r, ix, threaded) == want
+    # fill_gaps / access_kmer on the host (refine_host.cpp) instead of the device (refine.cuh): same result
+    api.set_device_refine(False)
+    try:
+        assert api.map(r, ix, api.MapOpts()) == want
+    finally:
+        api.set_device_refine(True)
 
 
 def test_hbm_resident_index_regime():
@@ -657,6 +663,34 @@ def test_map_and_call_match_oracle(k, p, seed):
     for fill, callv, fmt in ((True, True, True), (True, False, False), (False, True, False)):
         want = o.map(r, max_error_prob=p, fill_gaps=fill, call_variants=callv, format=fmt, build_k=k)
         assert api.map(r, ix, api.MapOpts(p, fill, callv, fmt, bo)) == want, (fill, callv, fmt)
+    api.set_device_refine(False)  # the host versions of fill_gaps / access_kmer (the index mirror is read back lazily)
+    try:
+        got = api.call(ix, r, api.CallOpts(p, bo))
+        assert [(v.query_pos, v.query_chars, v.ref_chars) for v in got] == want_vars
+        assert api.map(r, ix, api.MapOpts(p, True, True, True, bo)) == o.map(r, max_error_prob=p, build_k=k)
+    finally:
+        api.set_device_refine(True)
+
+
+GF = "gap_filling.rs::"
+
+
+@pytest.mark.parametrize("device_refine", [True, False])
+@pytest.mark.parametrize("name,k,p", [
+    ("fill_gaps_with_clustered_changes_k51", 51, 0.0000001), ("fill_gaps_default_build_opts", 31, 0.0000001)])
+def test_fill_gaps_goldens(name, k, p, device_refine):
+    """gap_filling.rs:641-922 goldens whose threshold is the index's own (the C ABI takes no threshold), through
+    kbo_map with fill_gaps only, on the device (refine.cuh) and on the host (refine_host.cpp)."""
+    b = GF + name
+    ix = api.build([g(b, "query")], api.BuildOpts(k=k, build_select=True))
+    if name.endswith("k51") and api.random_match_threshold(k, ix.n_kmers, 4, p) != 23:
+        pytest.skip("the golden was made with threshold 23")
+    api.set_device_refine(device_refine)
+    try:
+        got = api.map(g(b, "reference"), ix, api.MapOpts(p, True, False, False, api.BuildOpts(k=k, build_select=True)))
+    finally:
+        api.set_device_refine(True)
+    assert got == g(b, "expected")
 
 
 def test_counters_and_launch_count():

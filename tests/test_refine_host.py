@@ -1,5 +1,6 @@
-"""CPU checks of the product's host refinement layer (kbo_b200/csrc/refine_host.cpp: call_variants,
-fill_gaps, add_variants) driven by emulated-kernel matching statistics, against the reference's golden
+"""CPU checks of the product's refinement layer -- the host version (kbo_b200/csrc/refine_host.cpp: call_variants,
+fill_gaps, add_variants) and the device version (kbo_b200/csrc/refine.cuh: gap_list / fill_gaps / access_kmers kernels,
+run through the CUDA-on-CPU shim) -- driven by emulated-kernel matching statistics, against the reference's golden
 vectors and the oracle.  The same entry points run on the GPU in tests/test_gpu_parity.py."""
 import json
 import os
@@ -17,6 +18,13 @@ REF_K3 = b"AAAGAACCA-TCAGGGCG"
 
 def g(block, var):
     return GOLD[block][var].encode()
+
+
+@pytest.fixture(params=["host", "device"], autouse=True)
+def refine_mode(request):
+    E.set_device_refine(request.param == "device")
+    yield request.param
+    E.set_device_refine(False)
 
 
 def thr_of(e, p):
@@ -69,14 +77,16 @@ GF = "gap_filling.rs::"
     ("fill_gaps_left_extend_long", 9, 4, 0.001), ("doc@401", 9, 4, 0.001),
     ("fill_gaps_with_clustered_changes_k51", 51, 23, 0.0000001), ("fill_gaps_default_build_opts", 31, None, 0.0000001),
 ])
-def test_fill_gaps_goldens(name, k, thr, p):
+def test_fill_gaps_goldens(name, k, thr, p, refine_mode):
     # gap_filling.rs:641-922: map(fill_gaps only, unformatted) with the test's threshold
     b = GF + name
     e = E.EmuIndex.build([g(b, "query")], k=k)
     if thr is None:
         thr = thr_of(e, p)
+    n0 = E.device_gap_count()
     got = e.map(g(b, "reference"), thr, p, fill_gaps=True, call_variants=False, format=False, build_k=k)
     assert got == g(b, "expected")
+    assert (E.device_gap_count() > n0) == (refine_mode == "device")  # the kernels really ran (every golden has a gap)
 
 
 @pytest.mark.parametrize("name", ["add_variants", "add_variants_multi_base_substitution",

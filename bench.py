@@ -62,12 +62,16 @@ def parse_args():
     ap.add_argument("--ref-len", type=int, default=0, help="reference length (0 = the config's: 5 Mbp, config 5: 1 Gbp per GPU)")
     ap.add_argument("--queries", type=int, default=0)
     ap.add_argument("--query-len", type=int, default=0)
-    ap.add_argument("--assemblies", type=int, default=8, help="configs 3 / 4: assemblies per rank")
+    ap.add_argument("--assemblies", type=int, default=16, help="configs 3 / 4: assemblies per rank")
+    ap.add_argument("--asm-threads", type=int, default=4,
+                    help="configs 3 / 4: host threads per rank, each taking whole assemblies (kbo-cli style)")
     ap.add_argument("--k", type=int, default=31, help="configs 3 / 4: k of the indexes (k > 32 takes the host builder; the "
                                                       "reference resolves variants only when k - threshold leaves room, e.g. k = 51)")
     ap.add_argument("--batches", type=int, default=16, help="distinct batches rotated through (16 x 10 MB > L2)")
     ap.add_argument("--chunk-len", type=int, default=0, help="MS chunk length (0 = automatic)")
     ap.add_argument("--ms-flags", type=int, default=0, help="experiment switches (2: K2 instead of K2b)")
+    ap.add_argument("--prefix-len", type=int, default=0, help="depth of the prefix-state table (0 = automatic: 10, then "
+                    "ceil(log4 n) + 1 once the index serves batches)")
     ap.add_argument("--no-prefix-table", action="store_true", help="build the index without the prefix-state table (comparison)")
     ap.add_argument("--no-rank2", action="store_true", help="build the index without the rank2 rows: one base per probe (comparison)")
     ap.add_argument("--no-l2-persist", action="store_true", help="do not mark the index persisting in L2 (comparison)")
@@ -284,6 +288,8 @@ def run_ours(args, rank, local_rank, world):
         api.set_l2_persist(False)
     if args.no_prefix_table:
         api.set_prefix_table(False)
+    if args.prefix_len:
+        api.set_prefix_len(args.prefix_len)
     if args.no_rank2:
         api.set_rank2(False)
     if args.pipeline_parts:
@@ -466,7 +472,8 @@ def run_ours(args, rank, local_rank, world):
     k1_ms = ksum["ms"] / max(kcalls, 1)
     achieved = alg_bytes / (k1_ms * 1e-3) / 1e9 if k1_ms > 0 else 0.0
     hbm_peak, peak_src = measured_peaks()
-    roof = {"kernel": "ms_fused_kernel (K1 matching statistics + K2b derandomize/translate)",
+    roof = {"kernel": "ms_fused_kernel (K1 matching statistics + K2b derandomize/translate in one kernel)" if args.ms_flags & 16
+            else "ms_kernel (K1: matching statistics; the dominant kernel of a find step)",
             "achieved": achieved, "unit": "GB/s", "traffic": committed_traffic(),
             "algorithmic_bytes_per_launch": alg_bytes, "algorithmic_bytes_per_base": alg_bytes / L,
             "algorithmic_bytes_how": "32 B x (rank probes + probes whose two ends fall in different sectors + contractions "
@@ -478,7 +485,7 @@ def run_ours(args, rank, local_rank, world):
                                         "1.26 probes + 0.26 contractions per base); the kernel does the same job with fewer "
                                         "probes (two bases per probe, contraction jumps), which LOWERS its own figure",
             "achieved_reference_algorithm_GBps": 51.0 * L / (k1_ms * 1e-3) / 1e9 if k1_ms > 0 else 0.0,
-            "kernel_ms": {"pack": ksum["pack"] / max(kcalls, 1), "ms_fused": k1_ms,
+            "kernel_ms": {"pack": ksum["pack"] / max(kcalls, 1), "ms": k1_ms,
                           "how": "CUDA events around each kernel over %d serial steps on the launch stream: the configuration "
                                  "of impl_detail.single_stream (chunk length 64); the %d-stream `value` region overlaps steps "
                                  "and runs K1 with longer chunks" % (kcalls, len(workers))},
@@ -519,6 +526,8 @@ def run_ours(args, rank, local_rank, world):
     if rank == 0:
         cfg = config_dict(args)
         detail = {"index_device_bytes": index.device_bytes, "n_sets": index.n_sets,
+                  "prefix_table_depth": args.prefix_len or "auto (10 at construction, ceil(log4 n_sets) + 1 <= 13 once the "
+                                                           "index has served 4 M bases of batch queries)",
                               "index_build_s": round(index_build_s, 3), "rle_records_per_step": n_rle,
                               "streams": len(workers),
                               "single_stream": {"ms_per_step": ms_single / args.steps,
@@ -581,42 +590,61 @@ def run_assemblies(args, rank, local_rank, world):
 
     asms = {i: synth.mutate(ref, 0x6B626F10 + 1000 * rank + i) for i in range(n_asm + 2)}  # synthetic inputs: untimed
 
-    free_box = [0.0]
-
-    def one(i):
+    def one(i, ref_index=None):
         asm = asms[i]
         t0 = time.perf_counter()
         ix = api.build([asm], bo, device=dev)
         t1 = time.perf_counter()
         if args.config == 3:
-            res = api.call(ix, refb, api.CallOpts(sbwt_build_opts=bo))
+            res = api.call(ix, refb, api.CallOpts(sbwt_build_opts=bo), ref_index=ref_index)
         else:
-            res = api.map(refb, ix, api.MapOpts(sbwt_build_opts=bo))
+            res = api.map(refb, ix, api.MapOpts(sbwt_build_opts=bo), ref_index=ref_index)
         t2 = time.perf_counter()
         ix.close()
-        free_box[0] += time.perf_counter() - t2
-        return asm, res, t1 - t0, t2 - t1
+        return asm, res, t1 - t0, t2 - t1, time.perf_counter() - t2
 
+    def region(n_threads, ref_index=None):
+        """n_asm assemblies on n_threads host threads (kbo-cli style: one assembly per worker at a time); returns
+        (seconds max over ranks, summed build / run / free seconds, result of assembly 0)."""
+        results = [None] * n_asm
+
+        def worker(t):
+            torch.cuda.set_device(dev)
+            for i in range(t, n_asm, n_threads):
+                results[i] = one(i, ref_index)
+        torch.cuda.synchronize()
+        if dist is not None:
+            dist.barrier()
+        w0 = time.perf_counter()
+        if n_threads == 1:
+            worker(0)
+        else:
+            ths = [threading.Thread(target=worker, args=(t,)) for t in range(n_threads)]
+            for th in ths:
+                th.start()
+            for th in ths:
+                th.join()
+        torch.cuda.synchronize()
+        total = time.perf_counter() - w0
+        t = torch.tensor([total], dtype=torch.float64, device="cuda")
+        if dist is not None:
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        sums = [sum(r[j] for r in results) for j in (2, 3, 4)]
+        return float(t.item()), sums, (results[0][0], results[0][1])
+
+    n_thr = max(1, args.asm_threads)
     for i in range(2):  # warm-up (allocator pools, pinned staging)
         one(n_asm + i)
-    torch.cuda.synchronize()
-    if dist is not None:
-        dist.barrier()
-    w0 = time.perf_counter()
-    build_s = run_s = 0.0
-    free_box[0] = 0.0
-    first = None
-    for i in range(n_asm):
-        asm, res, b, r = one(i)
-        build_s += b
-        run_s += r
-        if first is None:
-            first = (asm, res)
-    total_s = time.perf_counter() - w0
-    t = torch.tensor([total_s], dtype=torch.float64, device="cuda")
-    if dist is not None:
-        dist.all_reduce(t, op=dist.ReduceOp.MAX)
-    value = world * n_asm * len(ref) / float(t.item())
+    region(n_thr)  # (and once with the timed region's concurrency: every thread's workspaces exist afterwards)
+    total_s, (build_s, run_s, free_s), first = region(n_thr)
+    value = world * n_asm * len(ref) / total_s
+    one_s, (build1, run1, free1), first1 = region(1) if n_thr > 1 else (total_s, (build_s, run_s, free_s), first)
+    # the index of the reference built once and passed in (kbo_call_with_ref / kbo_map_with_ref) instead of per call
+    ref_ix = api.build([ref], bo, device=dev)
+    reuse_s, _, first_reuse = region(n_thr, ref_ix)
+    ref_ix.close()
+    if first1[1] != first[1] or first_reuse[1] != first[1]:
+        raise SystemExit("bench.py: kbo::%s results differ between the timed regions" % name)
     parity = None
     if rank == 0:  # bit-exact against the oracle on the first assembly
         import oracle_lib as O
@@ -637,18 +665,24 @@ def run_assemblies(args, rank, local_rank, world):
                   "oracle_seconds_index_plus_%s_one_thread" % name: round(cpu_s, 2),
                   "oracle_bases_per_s": len(ref) / cpu_s}
         line = {"metric": "query bases/s (kbo %s, whole box)" % name, "value": value, "unit": "query bases/s",
-                "n_gpus": world, "steps": n_asm, "warmup": 2, "ms_per_step": 1e3 * float(t.item()) / n_asm,
+                "n_gpus": world, "steps": n_asm, "warmup": 2 + n_asm, "ms_per_step": 1e3 * total_s / n_asm,
                 "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "u8", "data": "synthetic",
                 "config": {"workload": "kbo::%s of %d mutated %d bp synthetic assemblies per rank (1%% SNPs + short indels) "
                                        "against one reference, k=%d, default options (BASELINE.json configs[%d])"
                                        % (name, n_asm, args.ref_len, kk, args.config - 1),
                            "assemblies_per_rank": n_asm, "ref_len": args.ref_len, "k": kk},
-                "impl_detail": {"split_ms_per_assembly": {"assembly_index_build (GPU builder incl. copy-in and host mirror)":
-                                                          1e3 * build_s / n_asm,
-                                                          "kbo::%s (MS on the device + reference-index build + host refinement)" % name:
-                                                          1e3 * run_s / n_asm,
-                                                          "index free": 1e3 * free_box[0] / n_asm},
-                                "host_threads_for_refinement": hw, "parity": parity}}
+                "impl_detail": {"host_threads": n_thr,
+                                "one_host_thread": {"value": world * n_asm * len(ref) / one_s, "ms_per_assembly": 1e3 * one_s / n_asm,
+                                                    "split_ms_per_assembly": {
+                                                        "assembly_index_build (GPU builder incl. copy-in)": 1e3 * build1 / n_asm,
+                                                        "kbo::%s (MS, fill_gaps on the device, reference-index build, "
+                                                        "variant resolution)" % name: 1e3 * run1 / n_asm,
+                                                        "index free": 1e3 * free1 / n_asm}},
+                                "reference_index_built_once": {"value": world * n_asm * len(ref) / reuse_s,
+                                                               "ms_per_assembly": 1e3 * reuse_s / n_asm,
+                                                               "api": "kbo_%s_with_ref (the reference rebuilds it per call, "
+                                                                      "lib.rs:553; `value` does too)" % name},
+                                "parity": parity}}
         print(json.dumps(line), flush=True)
     if dist is not None:
         dist.barrier()

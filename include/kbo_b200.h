@@ -225,6 +225,16 @@ int kbo_call(const kbo_index* query_index, const uint8_t* ref_seq, uint64_t len,
 int kbo_map(const kbo_index* query_index, const uint8_t* ref_seq, uint64_t len, double max_error_prob,
             int fill_gaps, int call_variants, int format, const kbo_build_opts* sbwt_build_opts, uint8_t* out);
 
+/* kbo::call and kbo::map rebuild the SBWT of ref_seq on every call (lib.rs:553).  A caller that streams many assemblies
+ * against ONE reference can build that index once -- kbo_index_build of ref_seq with the sbwt_build_opts it would have
+ * passed, on the device of the query indexes -- and hand it in here: everything else, and every result, is as
+ * kbo_call / kbo_map.  ref_index is only read. */
+int kbo_call_with_ref(const kbo_index* query_index, const kbo_index* ref_index, const uint8_t* ref_seq, uint64_t len,
+                      double max_error_prob, uint64_t* pos, uint32_t* qlen, uint32_t* rlen, uint8_t* qchars,
+                      uint8_t* rchars, uint64_t cap_variants, uint64_t cap_chars, uint64_t* n_variants);
+int kbo_map_with_ref(const kbo_index* query_index, const kbo_index* ref_index, const uint8_t* ref_seq, uint64_t len,
+                     double max_error_prob, int fill_gaps, int call_variants, int format, uint8_t* out);
+
 /* ---- instrumentation ------------------------------------------------------ */
 /* Event counters of the last MS launch sequence on this index when profiling counters are enabled
  * (kbo_set_profile_counters(1)): extend attempts, attempts whose two rank probes fell in different
@@ -267,6 +277,11 @@ int kbo_set_host_builder(int enabled);
 /* enabled == 0: indexes created afterwards carry no prefix-state table (K1 then warms every chunk up over k-1 bases;
  * comparison runs).  Results never depend on it. */
 int kbo_set_prefix_table(int enabled);
+/* Depth P of the prefix-state table (the MS state after every string of P bases: a chunk's warm-up starts from it, and a
+ * failed extension at depth <= P is one lookup instead of contract + retry).  0 = automatic: 10 at construction, and
+ * ceil(log4 n_sets) + 1 (at most 13: 8 bytes x 4^13 = 537 MB) once the index has served 4 M bases of batch queries.
+ * 1 .. 14: indexes created afterwards get exactly that depth (capped at k - 1).  Results never depend on it. */
+int kbo_set_prefix_len(uint32_t len);
 /* enabled == 0: indexes created afterwards carry no rank2 rows (K1 then probes one base at a time; comparison runs).
  * Results never depend on it. */
 int kbo_set_rank2(int enabled);

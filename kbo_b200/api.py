@@ -39,7 +39,7 @@ EXPORTED_SYMBOLS = [
     "kbo_log_rm_max_cdf", "kbo_random_match_threshold", "kbo_derandomize_ms_vec", "kbo_translate_ms_vec",
     "kbo_run_lengths_gapped", "kbo_relative_to_ref", "kbo_matches", "kbo_matches_batch", "kbo_matches_batch_device",
     "kbo_find_batch", "kbo_find_batch_submit", "kbo_job_wait", "kbo_find_batch_device", "kbo_ctx_create", "kbo_ctx_free", "kbo_ctx_n_gpus", "kbo_index_set_build", "kbo_index_set_free", "kbo_index_set_get",
-    "kbo_matches_batch_multi", "kbo_find_batch_multi", "kbo_map_unrefined", "kbo_call", "kbo_map", "kbo_set_profile_counters", "kbo_get_ms_counters", "kbo_set_chunk_len", "kbo_set_l2_persist", "kbo_set_prefix_table", "kbo_set_rank2", "kbo_set_refine_threads", "kbo_set_device_refine", "kbo_index_set_tuning", "kbo_set_host_builder", "kbo_set_pipeline_parts", "kbo_set_device_parts", "kbo_set_ms_flags",
+    "kbo_matches_batch_multi", "kbo_find_batch_multi", "kbo_map_unrefined", "kbo_call", "kbo_map", "kbo_call_with_ref", "kbo_map_with_ref", "kbo_set_profile_counters", "kbo_get_ms_counters", "kbo_set_chunk_len", "kbo_set_l2_persist", "kbo_set_prefix_table", "kbo_set_prefix_len", "kbo_set_rank2", "kbo_set_refine_threads", "kbo_set_device_refine", "kbo_index_set_tuning", "kbo_set_host_builder", "kbo_set_pipeline_parts", "kbo_set_device_parts", "kbo_set_ms_flags",
     "kbo_kernel_launch_count", "kbo_last_kernel_ms", "kbo_set_kernel_timing", "kbo_collect_kernel_times",
     "kbo_measure_random_sector_rate",
 ]
@@ -139,11 +139,15 @@ def load_library():
     L.kbo_map.argtypes = [C.c_void_p, u8p, C.c_uint64, C.c_double, C.c_int, C.c_int, C.c_int, C.POINTER(BuildOptsC),
                           u8p]
     L.kbo_map_unrefined.argtypes = [C.c_void_p, u8p, C.c_uint64, C.c_double, C.c_int, u8p]
+    L.kbo_call_with_ref.argtypes = [C.c_void_p, C.c_void_p, u8p, C.c_uint64, C.c_double, u64p, u32p, u32p, u8p, u8p,
+                                    C.c_uint64, C.c_uint64, u64p]
+    L.kbo_map_with_ref.argtypes = [C.c_void_p, C.c_void_p, u8p, C.c_uint64, C.c_double, C.c_int, C.c_int, C.c_int, u8p]
     L.kbo_set_profile_counters.argtypes = [C.c_int]
     L.kbo_get_ms_counters.argtypes = [C.c_void_p, C.POINTER(MsCountersC)]
     L.kbo_set_chunk_len.argtypes = [C.c_uint32]
     L.kbo_set_l2_persist.argtypes = [C.c_int]
     L.kbo_set_prefix_table.argtypes = [C.c_int]
+    L.kbo_set_prefix_len.argtypes = [C.c_uint32]
     L.kbo_set_rank2.argtypes = [C.c_int]
     L.kbo_set_refine_threads.argtypes = [C.c_uint32]
     L.kbo_set_device_refine.argtypes = [C.c_int]
@@ -257,7 +261,11 @@ class Index:
         self.n_kmers = L.kbo_index_n_kmers(self._h)
         self.n_sets = L.kbo_index_n_sets(self._h)
         self.device = L.kbo_index_device(self._h)
-        self.device_bytes = L.kbo_index_device_bytes(self._h)
+
+    @property
+    def device_bytes(self):
+        """Device memory of the index (grows when the deeper prefix-state table or the rank2 rows are made)."""
+        return load_library().kbo_index_device_bytes(self._h) if self._h else 0
 
     def close(self):
         if self._h:
@@ -612,36 +620,50 @@ def _build_opts_c(o):
                       int(o.dedup_batches), o.temp_dir.encode() if o.temp_dir else None)
 
 
-def call(query_index, ref_seq, call_opts=None):
-    """kbo::call (lib.rs:547-573) -> list of Variant."""
+def call(query_index, ref_seq, call_opts=None, ref_index=None):
+    """kbo::call (lib.rs:547-573) -> list of Variant.  ref_index: the index of ref_seq built once by the caller
+    (kbo_call_with_ref) instead of per call as the reference does (lib.rs:553); same result."""
     o = call_opts or CallOpts()
     r = _u8(ref_seq)
-    cap = len(r) + 1
-    capc = 4 * len(r) + 64
-    pos = np.zeros(cap, dtype=np.uint64)
-    ql, rl = np.zeros(cap, dtype=np.uint32), np.zeros(cap, dtype=np.uint32)
-    qc, rc = np.zeros(capc, dtype=np.uint8), np.zeros(capc, dtype=np.uint8)
-    n = C.c_uint64(0)
+    L = load_library()
     co = _build_opts_c(o.sbwt_build_opts)
-    _check(load_library().kbo_call(query_index._h, _p(r, C.c_uint8), len(r), o.max_error_prob, C.byref(co),
-                                   _p(pos, C.c_uint64), _p(ql, C.c_uint32), _p(rl, C.c_uint32), _p(qc, C.c_uint8),
-                                   _p(rc, C.c_uint8), cap, capc, C.byref(n)))
+    # output capacity: a first guess, then (KBO_ERR_BUFFER_TOO_SMALL) the worst case
+    for cap, capc in ((len(r) // 32 + 4096, len(r) // 4 + 65536), (len(r) + 1, 4 * len(r) + 64)):
+        pos = np.empty(cap, dtype=np.uint64)
+        ql, rl = np.empty(cap, dtype=np.uint32), np.empty(cap, dtype=np.uint32)
+        qc, rc = np.empty(capc, dtype=np.uint8), np.empty(capc, dtype=np.uint8)
+        n = C.c_uint64(0)
+        tail = (_p(pos, C.c_uint64), _p(ql, C.c_uint32), _p(rl, C.c_uint32), _p(qc, C.c_uint8), _p(rc, C.c_uint8), cap,
+                capc, C.byref(n))
+        if ref_index is None:
+            status = L.kbo_call(query_index._h, _p(r, C.c_uint8), len(r), o.max_error_prob, C.byref(co), *tail)
+        else:
+            status = L.kbo_call_with_ref(query_index._h, ref_index._h, _p(r, C.c_uint8), len(r), o.max_error_prob, *tail)
+        if status != 11:
+            break
+    _check(status)
+    nv = int(n.value)
+    qends, rends = np.cumsum(ql[:nv], dtype=np.int64), np.cumsum(rl[:nv], dtype=np.int64)
+    qb, rb = qc[:int(qends[-1]) if nv else 0].tobytes(), rc[:int(rends[-1]) if nv else 0].tobytes()
     out, qo, ro = [], 0, 0
-    for i in range(n.value):
-        out.append(Variant(int(pos[i]), bytes(qc[qo:qo + ql[i]]), bytes(rc[ro:ro + rl[i]])))
-        qo += int(ql[i])
-        ro += int(rl[i])
+    for p_, qe, re in zip(pos[:nv].tolist(), qends.tolist(), rends.tolist()):
+        out.append(Variant(p_, qb[qo:qe], rb[ro:re]))
+        qo, ro = qe, re
     return out
 
 
-def map(ref_seq, query_index, map_opts=None):
-    """kbo::map (lib.rs:720-761)."""
+def map(ref_seq, query_index, map_opts=None, ref_index=None):
+    """kbo::map (lib.rs:720-761).  ref_index: see call()."""
     o = map_opts or MapOpts()
     r = _u8(ref_seq)
-    out = np.zeros(max(len(r), 1), dtype=np.uint8)
-    co = _build_opts_c(o.sbwt_build_opts)
-    _check(load_library().kbo_map(query_index._h, _p(r, C.c_uint8), len(r), o.max_error_prob, int(o.fill_gaps),
-                                  int(o.call_variants), int(o.format), C.byref(co), _p(out, C.c_uint8)))
+    out = np.empty(max(len(r), 1), dtype=np.uint8)
+    if ref_index is None:
+        co = _build_opts_c(o.sbwt_build_opts)
+        _check(load_library().kbo_map(query_index._h, _p(r, C.c_uint8), len(r), o.max_error_prob, int(o.fill_gaps),
+                                      int(o.call_variants), int(o.format), C.byref(co), _p(out, C.c_uint8)))
+    else:
+        _check(load_library().kbo_map_with_ref(query_index._h, ref_index._h, _p(r, C.c_uint8), len(r), o.max_error_prob,
+                                               int(o.fill_gaps), int(o.call_variants), int(o.format), _p(out, C.c_uint8)))
     return out[:len(r)].tobytes()
 
 
@@ -673,6 +695,11 @@ def set_pipeline_parts(parts):
 
 def set_host_builder(enabled):
     _check(load_library().kbo_set_host_builder(int(enabled)))
+
+
+def set_prefix_len(p):
+    """Depth of the prefix-state table (0 = automatic; see kbo_set_prefix_len in the header)."""
+    _check(load_library().kbo_set_prefix_len(int(p)))
 
 
 def set_prefix_table(enabled):

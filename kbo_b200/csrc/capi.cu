@@ -41,6 +41,7 @@ static std::atomic<uint32_t> g_chunk_len(0);
 static std::atomic<int> g_kernel_timing(0);
 static std::atomic<int> g_rank2(1);  // 0: indexes built afterwards carry no two-bases-per-probe rows (comparison runs)
 static std::atomic<int> g_prefix_table(1);  // 0: indexes built afterwards get no prefix-state table (comparison runs)
+static std::atomic<int> g_prefix_len(0);    // 0: automatic (PREF_LEN at construction, deepened once the index serves batches)
 static std::atomic<int> g_l2_persist(1);  // 0: do not mark the index persisting in L2 (comparison runs)
 static std::atomic<uint32_t> g_ms_flags(0);
 static std::atomic<int> g_host_builder(0);
@@ -162,7 +163,12 @@ struct kbo_index {
     uint8_t* d_lcs = nullptr;
     uint32_t* d_links = nullptr;  // per node: LCS and the distances to the nearest smaller LCS on both sides
     uint8_t* d_blob = nullptr;    // the one allocation holding rank | links | lcs (one L2 access-policy window)
-    uint4* d_pref = nullptr;      // MS states after PREF_LEN bases (k >= PREF_MIN_K)
+    uint64_t* d_pref = nullptr;   // MS states after view.pref_len bases (k >= PREF_MIN_K)
+    // the deeper table (ensure_deep_pref) and the view that carries it, published through deep_ready once complete
+    uint64_t* d_pref_deep = nullptr;
+    IndexView view_deep;
+    std::atomic<bool> deep_ready{false};
+    std::atomic<uint64_t> batch_bases{0};  // query bases that went through the batch entry points
     // "select support" (BuildOpts.build_select) on the device: the colex-sorted node keys of the GPU builder
     // (refine.cuh NodeKeysView); null for indexes made from parts or by the host builder
     uint64_t* d_node_keys = nullptr;
@@ -172,6 +178,7 @@ struct kbo_index {
     // (ensure_host_mirror): kbo::map / kbo::call on a freshly built index never need it
     std::atomic<bool> host_ready{true};
     std::mutex host_mu;
+    std::atomic<bool> rank2_ready{false};  // the rank2 rows are computed when a kernel that probes pairs first runs
     uint64_t blob_bytes = 0;
     float l2_hit_ratio = 0.f;     // 0: no persisting-L2 window available
     uint64_t rank_stride = 0;
@@ -410,37 +417,96 @@ static int build_rank2(kbo_index* ix) {
     };
     const int rc = body();
     cudaFree(rows2); cudaFree(pc); cudaFree(prefix); cudaFree(scan_tmp);
-    if (rc == KBO_OK) ix->view.rank2 = ix->d_rank2;
+    if (rc == KBO_OK) ix->view.rank2 = ix->view_deep.rank2 = ix->d_rank2;
+    return rc;
+}
+
+// The states after 1, 2, ... P bases, level by level (prefix_table_level_kernel); level P stays in *out.
+static int build_pref_table(const IndexView& view, uint32_t P, uint64_t** out) {
+    const size_t last = (size_t)1 << (2 * P);
+    uint64_t *a = nullptr, *b = nullptr;  // level j lives in b when P - j is even (so level P does), else in a
+    CUDA_TRY(cudaMalloc((void**)&a, std::max<size_t>(last / 4, 4) * 8));
+    if (cudaMalloc((void**)&b, last * 8) != cudaSuccess) {
+        cudaFree(a);
+        cudaGetLastError();
+        return fail(KBO_ERR_OOM, "prefix-state table: out of device memory");
+    }
+    for (uint32_t j = 1; j <= P; ++j) {
+        const uint32_t cnt = 1u << (2 * j);
+        uint64_t* cur = ((P - j) & 1u) ? a : b;
+        const uint64_t* prev = ((P - j) & 1u) ? b : a;
+        prefix_table_level_kernel<<<(cnt + 255) / 256, 256>>>(view, prev, cur, j);
+        LAUNCHED();
+    }
+    cudaError_t e = cudaGetLastError();
+    if (e == cudaSuccess) e = cudaDeviceSynchronize();
+    cudaFree(a);
+    if (e != cudaSuccess) {
+        cudaFree(b);
+        return fail(KBO_ERR_CUDA, std::string("CUDA error: ") + cudaGetErrorString(e) + " in the prefix-state table");
+    }
+    *out = b;
+    return KBO_OK;
+}
+
+// Depth of the table an index gets once it serves batches: failed extensions happen at depths around log4(n) (the
+// length of a chance match), and one at depth <= pref_len costs one lookup instead of contract + retry.
+static uint32_t deep_pref_len(const kbo_index* ix) {
+    uint32_t lg = 0;
+    while (lg < 16 && (1ull << (2 * lg)) < ix->host.n_sets) ++lg;  // ceil(log4 n)
+    uint32_t P = std::min<uint32_t>(lg + 1, 13);
+    P = std::max<uint32_t>(P, PREF_LEN);
+    return std::min<uint32_t>(P, ix->view.k - 1);
+}
+// The view K1 runs with: the deeper table once it exists.
+static const IndexView& current_view(const kbo_index* ix) {
+    return ix->deep_ready.load(std::memory_order_acquire) ? ix->view_deep : ix->view;
+}
+static int ensure_deep_pref(kbo_index* ix) {
+    if (!ix->view.pref || g_prefix_len.load() > 0 || ix->deep_ready.load(std::memory_order_acquire)) return KBO_OK;
+    const uint32_t P = deep_pref_len(ix);
+    if (P <= ix->view.pref_len) return KBO_OK;
+    std::lock_guard<std::mutex> g(ix->host_mu);
+    if (ix->deep_ready.load(std::memory_order_acquire)) return KBO_OK;
+    const int rc = build_pref_table(ix->view, P, &ix->d_pref_deep);
+    if (rc == KBO_ERR_OOM) return KBO_OK;  // (an optimisation: the shallow table keeps serving)
+    if (rc) return rc;
+    ix->view_deep = ix->view;
+    ix->view_deep.pref = ix->d_pref_deep;
+    ix->view_deep.pref_len = P;
+    ix->device_bytes += ((uint64_t)8 << (2 * P));
+    ix->deep_ready.store(true, std::memory_order_release);
+    return KBO_OK;
+}
+
+// The rows for two bases per probe are only read by the fused kernel and K1p (kbo_set_ms_flags bits 4 / 5): their
+// space is part of the index allocation, their contents are made on first use.
+static int ensure_rank2(kbo_index* ix) {
+    if (!ix->d_rank2 || ix->rank2_ready.load(std::memory_order_acquire)) return KBO_OK;
+    std::lock_guard<std::mutex> g(ix->host_mu);
+    if (ix->rank2_ready.load(std::memory_order_acquire)) return KBO_OK;
+    const int rc = build_rank2(ix);
+    if (rc == KBO_OK) ix->rank2_ready.store(true, std::memory_order_release);
     return rc;
 }
 
 static int build_links(kbo_index* ix, uint64_t n, bool with_prefix_table = true) {
-    { int rc = build_rank2(ix); if (rc) return rc; }
+    ix->view.rank2 = nullptr;
     lcs_links_kernel<<<(unsigned)((n + 1 + 255) / 256), 256>>>(ix->d_lcs, (uint32_t)n, ix->d_links);
     LAUNCHED();
     CUDA_TRY(cudaGetLastError());
     ix->view.links = ix->d_links;
     ix->view.pref = nullptr;
+    ix->view.pref_len = 0;
     if (with_prefix_table && ix->view.k >= PREF_MIN_K && g_prefix_table.load()) {
-        // states after 1, 2, ... PREF_LEN bases, level by level (odd levels in `a`, even levels in `b`; the last is kept)
-        const size_t last = (size_t)1 << (2 * PREF_LEN);
-        uint4 *a = nullptr, *b = nullptr;
-        CUDA_TRY(cudaMalloc((void**)&a, (last / 4) * sizeof(uint4)));
-        CUDA_TRY(cudaMalloc((void**)&b, last * sizeof(uint4)));
-        static_assert(PREF_LEN % 2 == 0, "the last level must land in the large buffer");
-        for (uint32_t j = 1; j <= PREF_LEN; ++j) {
-            const uint32_t cnt = 1u << (2 * j);
-            uint4* cur = (j & 1) ? a : b;
-            const uint4* prev = (j & 1) ? b : a;
-            prefix_table_level_kernel<<<(cnt + 255) / 256, 256>>>(ix->view, prev, cur, j);
-            LAUNCHED();
-        }
-        CUDA_TRY(cudaGetLastError());
-        CUDA_TRY(cudaDeviceSynchronize());
-        cudaFree(a);
-        ix->d_pref = b;
-        ix->view.pref = b;
-        ix->device_bytes += last * sizeof(uint4);
+        const int want = g_prefix_len.load();
+        const uint32_t P = std::min<uint32_t>(want > 0 ? (uint32_t)want : (uint32_t)PREF_LEN,
+                                              std::min<uint32_t>(PREF_MAX_LEN, ix->view.k - 1));
+        const int rc = build_pref_table(ix->view, P, &ix->d_pref);
+        if (rc) return rc;
+        ix->view.pref = ix->d_pref;
+        ix->view.pref_len = P;
+        ix->device_bytes += ((uint64_t)8 << (2 * P));
     }
     return KBO_OK;
 }
@@ -546,14 +612,27 @@ struct TmpBufs {
 // host copy of the SubsetMatrix form, no prefix-state table.
 // KBO_BUILD_TIMING=1 in the environment prints where an index construction spends its time (stderr)
 struct BuildTimer {
-    bool on = std::getenv("KBO_BUILD_TIMING") != nullptr;
+    const char* mode = std::getenv("KBO_BUILD_TIMING");  // "1": synchronise the device at every lap; "2": host clock only
+    bool on = mode != nullptr;
     std::chrono::steady_clock::time_point t0 = std::chrono::steady_clock::now();
     void lap(const char* what) {
         if (!on) return;
-        cudaDeviceSynchronize();
+        if (mode[0] != '2') cudaDeviceSynchronize();
         const auto t1 = std::chrono::steady_clock::now();
         std::fprintf(stderr, "[kbo build] %-28s %8.2f ms\n", what, std::chrono::duration<double, std::milli>(t1 - t0).count());
         t0 = t1;
+    }
+};
+
+// (KBO_BUILD_TIMING: wall time of a whole entry point, printed when it returns)
+struct ScopeTimer {
+    const char* what;
+    bool on = std::getenv("KBO_BUILD_TIMING") != nullptr;
+    std::chrono::steady_clock::time_point t0 = std::chrono::steady_clock::now();
+    explicit ScopeTimer(const char* w) : what(w) {}
+    ~ScopeTimer() {
+        if (on) std::fprintf(stderr, "[kbo total] %-28s %8.2f ms\n", what,
+                             std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - t0).count());
     }
 };
 
@@ -680,6 +759,7 @@ static int build_index_gpu_typed(kbo_index* ix, const uint8_t* const* seqs, cons
     const uint64_t stride = (nblk + 3) & ~3ull;
     const uint64_t lcs_bytes = ((n + 8) & ~7ull) + 16;
     { int rc = alloc_index_arrays(ix, 4 * stride, lcs_bytes, n, !device_only); if (rc) return rc; }
+    bt.lap("index allocation");
     CUDA_TRY(cudaMemset(ix->d_lcs, 0, lcs_bytes));
     CUDA_TRY(tmp.alloc(&d_rows32, 4 * stride));
     CUDA_TRY(tmp.alloc(&d_pc, 4 * stride));
@@ -788,8 +868,15 @@ static int run_ms(kbo_index* ix, Workspace* ws, const QueryView& qv, const Geome
         CUDA_TRY(ws->counters.ensure(CNT_N * 8, st));
         CUDA_TRY(cudaMemsetAsync(ws->counters.p, 0, CNT_N * 8, st));
     }
+    if (!intervals && (tuned_ms_flags(ix) & 32u)) { const int rc = ensure_rank2(ix); if (rc) return rc; }
+    // an index that serves batches (matches / find; 4 M bases so far) gets the deeper prefix-state table once
+    if (!intervals && !ix->deep_ready.load(std::memory_order_relaxed) &&
+        ix->batch_bases.fetch_add(g.total, std::memory_order_relaxed) + g.total >= (4ull << 20)) {
+        const int rc = ensure_deep_pref(ix);
+        if (rc) return rc;
+    }
     MsParams mp;
-    mp.ix = ix->view;
+    mp.ix = current_view(ix);
     mp.q = qv;
     mp.chunk_len = g.chunk_len;
     mp.flags = tuned_ms_flags(ix);
@@ -803,7 +890,7 @@ static int run_ms(kbo_index* ix, Workspace* ws, const QueryView& qv, const Geome
     if (intervals) {
         if (count) ms_kernel<true, true><<<blocks, threads, 0, st>>>(mp);
         else ms_kernel<true, false><<<blocks, threads, 0, st>>>(mp);
-    } else if ((mp.flags & 32u) && ix->view.rank2) {  // bit 5: two bases per probe in K1 (ms_pairs_kernel)
+    } else if ((mp.flags & 32u) && mp.ix.rank2) {  // bit 5: two bases per probe in K1 (ms_pairs_kernel)
         if (count) ms_pairs_kernel<true><<<blocks, threads, 0, st>>>(mp);
         else ms_pairs_kernel<false><<<blocks, threads, 0, st>>>(mp);
     } else {
@@ -1019,9 +1106,10 @@ static int run_fused(kbo_index* ix, Workspace* ws, const QueryView& qv, const Ge
     FusedGeom fg;
     if (!fused_geometry(g.Lp, ix->host.k, !want_masks, device_sm_count(ix->device), tuned_chunk_len(ix), &fg)) return KBO_OK;
     cudaStream_t st = ws->stream;
+    if (!(flags & 4u)) { const int rc = ensure_rank2(ix); if (rc) return rc; }  // (bit 2: one base per probe)
     FusedParams fp;
     std::memset(&fp, 0, sizeof(fp));
-    fp.ix = ix->view;
+    fp.ix = current_view(ix);
     fp.q = qv;
     fp.tr.ms = nullptr;
     fp.tr.q = qv;
@@ -1182,6 +1270,7 @@ static int finish_index(kbo_index* ix, int device, kbo_index** out) {
 
 int kbo_index_build(const uint8_t* const* seqs, const uint64_t* lens, uint64_t n_seqs, const kbo_build_opts* opts,
                     int device, kbo_index** out) {
+    ScopeTimer scope_timer("kbo_index_build");
     if (!out) return fail(KBO_ERR_BAD_ARGUMENT, "out is null");
     *out = nullptr;
     if (!seqs || !lens || n_seqs == 0) return fail(KBO_ERR_EMPTY_INPUT, "no input sequences (index.rs:60)");
@@ -1247,15 +1336,19 @@ int kbo_index_from_parts(uint32_t k, uint64_t n_sets, uint64_t n_kmers, const ui
 
 void kbo_index_free(kbo_index* ix) {
     if (!ix) return;
+    ScopeTimer scope_timer("kbo_index_free");
     {
+        BuildTimer bt;
         DeviceGuard dg(ix->device);
         // (idle pooled workspaces belong to the device, not to this index: they stay for the next index)
         for (auto& kv : ix->by_stream) { kv.second->destroy(); delete kv.second; }
         for (PinnedBuf& pb : ix->pinned_pool) if (pb.p) cudaFreeHost(pb.p);
         if (ix->d_blob) cudaFree(ix->d_blob);
         if (ix->d_pref) cudaFree(ix->d_pref);
+        if (ix->d_pref_deep) cudaFree(ix->d_pref_deep);
         if (ix->d_node_keys) cudaFree(ix->d_node_keys);
         if (ix->d_node_len) cudaFree(ix->d_node_len);
+        bt.lap("index free");
     }
     delete ix;
 }
@@ -1667,11 +1760,11 @@ int kbo_run_lengths_gapped(const uint8_t* aln, uint64_t n, uint64_t max_gap_len,
 
 int kbo_relative_to_ref(const uint8_t* ref_seq, const uint8_t* aln, uint64_t n, uint8_t* out) {
     if (n && (!ref_seq || !aln || !out)) return fail(KBO_ERR_BAD_ARGUMENT, "null argument");
-    for (uint64_t i = 0; i < n; ++i) {  // format.rs:270-286
+    for (uint64_t i = 0; i < n; ++i) {  // format.rs:270-286, as byte masks (the compiler vectorises this form)
         const uint8_t a = aln[i];
-        if (a == 'M' || a == 'R' || a == 'I') out[i] = ref_seq[i];
-        else if (a == 'X' || a == 'D' || a == '-') out[i] = '-';
-        else out[i] = a;
+        const uint8_t take_ref = (uint8_t) - (uint8_t)((a == 'M') | (a == 'R') | (a == 'I'));
+        const uint8_t to_gap = (uint8_t) - (uint8_t)((a == 'X') | (a == 'D') | (a == '-'));
+        out[i] = (uint8_t)((ref_seq[i] & take_ref) | ((uint8_t)'-' & to_gap) | (a & (uint8_t) ~(take_ref | to_gap)));
     }
     return KBO_OK;
 }
@@ -2446,7 +2539,7 @@ static int device_fill_gaps(kbo_index* ix, Workspace* ws, uint64_t len, uint32_t
     unsigned long long init[2] = {0ull, ~0ull};  // arena bytes used, panic word
     CUDA_TRY(cudaMemcpyAsync(ws->counters2.as<uint8_t>() + 8, init, 16, cudaMemcpyHostToDevice, st));
     FillGapsParams fp;
-    fp.ix = ix->view;
+    fp.ix = current_view(ix);
     fp.nk.keys = ix->d_node_keys;
     fp.nk.len = ix->d_node_len;
     fp.nk.words = ix->node_key_words;
@@ -2540,16 +2633,24 @@ static int run_single_candidates(kbo_index* ix, const uint8_t* seq, uint64_t len
 // lib.rs:547-573 given the full-length MS of ref_seq against the assembly index (computed by the caller)
 static int call_impl(kbo_index* query_index, const uint8_t* ref_seq, uint64_t len, double max_error_prob,
                      const kbo_build_opts* opts, const std::vector<VariantCandidate64>& cands,
-                     std::vector<VariantRec>* variants) {
+                     std::vector<VariantRec>* variants, kbo_index* given_ref_index = nullptr) {
     kbo_build_opts o;
     if (opts) o = *opts; else { kbo_default_build_opts(&o); o.build_select = 1; }
     uint64_t thr = 0;
     int rc = host_threshold(query_index->host.k, query_index->host.n_kmers, 4, max_error_prob, &thr);  // variant_calling.rs:260
     if (rc) return rc;
-    kbo_index* ref_index = nullptr;
+    kbo_index* ref_index = given_ref_index;
+    struct RefOwner {  // the per-call index of ref_seq is freed on every way out; a caller-provided one is left alone
+        kbo_index** p;
+        bool own;
+        ~RefOwner() { if (own && *p) kbo_index_free(*p); }
+    } ref_owner{&ref_index, given_ref_index == nullptr};
     const uint8_t* seqs[1] = {ref_seq};
     const uint64_t lens[1] = {len};
-    if (o.k >= 2 && o.k <= KBO_MAX_K && !g_host_builder.load()) {  // lib.rs:553; only its device arrays are used below
+    if (given_ref_index) {
+        if (given_ref_index->device != query_index->device)
+            return fail(KBO_ERR_BAD_ARGUMENT, "ref_index lives on another device than the query index");
+    } else if (o.k >= 2 && o.k <= KBO_MAX_K && !g_host_builder.load()) {  // lib.rs:553; only its device arrays are used below
         if (len == 0) return fail(KBO_ERR_EMPTY_INPUT, "no input sequences (index.rs:60)");
         DeviceGuard dg(query_index->device);
         if (!dg.ok) return fail(KBO_ERR_CUDA, "cudaSetDevice failed");
@@ -2557,13 +2658,13 @@ static int call_impl(kbo_index* query_index, const uint8_t* ref_seq, uint64_t le
         ref_index->device = query_index->device;
         ref_index->host.k = o.k;
         rc = build_index_gpu(ref_index, seqs, lens, 1, o.k, o.add_revcomp != 0, false, true);
-        if (rc) { kbo_index_free(ref_index); return rc; }
+        if (rc) return rc;
     } else {
         rc = kbo_index_build(seqs, lens, 1, &o, query_index->device, &ref_index);
         if (rc) return rc;
     }
+    BuildTimer bt;
     if (ref_index->host.k != query_index->host.k) {  // lib.rs:559
-        kbo_index_free(ref_index);
         return fail(KBO_ERR_K_MISMATCH, "k of the reference index differs from k of the query index (lib.rs:559)");
     }
     int inner_rc = KBO_OK;
@@ -2581,21 +2682,22 @@ static int call_impl(kbo_index* query_index, const uint8_t* ref_seq, uint64_t le
     };
     if (!dev_access) {
         rc = ensure_host_mirror(query_index);
-        if (rc) { kbo_index_free(ref_index); return rc; }
+        if (rc) return rc;
     }
     try {
         *variants = call_variants_from(query_index->host, cands, ref_seq, len, thr, kmer_ms, dev_access ? &access : nullptr);
     } catch (const RefinePanic& p) {
-        kbo_index_free(ref_index);
         return fail(KBO_ERR_PANIC, p.what);
     }
-    kbo_index_free(ref_index);
+    bt.lap("call: access_kmer, k-mer MS x 2, resolve");
     return inner_rc;
 }
 
-int kbo_call(const kbo_index* cix, const uint8_t* ref_seq, uint64_t len, double max_error_prob,
-             const kbo_build_opts* sbwt_build_opts, uint64_t* pos, uint32_t* qlen, uint32_t* rlen, uint8_t* qchars,
-             uint8_t* rchars, uint64_t cap_variants, uint64_t cap_chars, uint64_t* n_variants) {
+static int call_entry(const kbo_index* cix, const kbo_index* ref_index, const uint8_t* ref_seq, uint64_t len,
+                      double max_error_prob, const kbo_build_opts* sbwt_build_opts, uint64_t* pos, uint32_t* qlen,
+                      uint32_t* rlen, uint8_t* qchars, uint8_t* rchars, uint64_t cap_variants, uint64_t cap_chars,
+                      uint64_t* n_variants) {
+    ScopeTimer scope_timer("kbo_call");
     kbo_index* ix = const_cast<kbo_index*>(cix);
     if (!ix || !n_variants) return fail(KBO_ERR_BAD_ARGUMENT, "null argument");
     if (!ref_seq || len == 0) return fail(KBO_ERR_EMPTY_INPUT, "empty reference sequence");
@@ -2603,10 +2705,12 @@ int kbo_call(const kbo_index* cix, const uint8_t* ref_seq, uint64_t len, double 
     int rc = host_threshold(ix->host.k, ix->host.n_kmers, 4, max_error_prob, &thr);  // variant_calling.rs:260
     if (rc) return rc;
     std::vector<VariantCandidate64> cands;
+    BuildTimer bt;
     rc = run_single_candidates(ix, ref_seq, len, (uint32_t)std::min<uint64_t>(thr, 255), &cands);  // variant_calling.rs:266-272
     if (rc) return rc;
+    bt.lap("call: K0, K1 (d,l,r), candidate scan");
     std::vector<VariantRec> vars;
-    rc = call_impl(ix, ref_seq, len, max_error_prob, sbwt_build_opts, cands, &vars);
+    rc = call_impl(ix, ref_seq, len, max_error_prob, sbwt_build_opts, cands, &vars, const_cast<kbo_index*>(ref_index));
     if (rc) return rc;
     *n_variants = vars.size();
     if (vars.size() > cap_variants) return fail(KBO_ERR_BUFFER_TOO_SMALL, "variant capacity too small");
@@ -2626,12 +2730,28 @@ int kbo_call(const kbo_index* cix, const uint8_t* ref_seq, uint64_t len, double 
     return KBO_OK;
 }
 
-int kbo_map(const kbo_index* cix, const uint8_t* ref_seq, uint64_t len, double max_error_prob, int do_fill_gaps,
-            int do_call_variants, int format, const kbo_build_opts* sbwt_build_opts, uint8_t* out) {
+int kbo_call(const kbo_index* cix, const uint8_t* ref_seq, uint64_t len, double max_error_prob,
+             const kbo_build_opts* sbwt_build_opts, uint64_t* pos, uint32_t* qlen, uint32_t* rlen, uint8_t* qchars,
+             uint8_t* rchars, uint64_t cap_variants, uint64_t cap_chars, uint64_t* n_variants) {
+    return call_entry(cix, nullptr, ref_seq, len, max_error_prob, sbwt_build_opts, pos, qlen, rlen, qchars, rchars,
+                      cap_variants, cap_chars, n_variants);
+}
+int kbo_call_with_ref(const kbo_index* cix, const kbo_index* ref_index, const uint8_t* ref_seq, uint64_t len,
+                      double max_error_prob, uint64_t* pos, uint32_t* qlen, uint32_t* rlen, uint8_t* qchars,
+                      uint8_t* rchars, uint64_t cap_variants, uint64_t cap_chars, uint64_t* n_variants) {
+    if (!ref_index) return fail(KBO_ERR_BAD_ARGUMENT, "ref_index is null");
+    return call_entry(cix, ref_index, ref_seq, len, max_error_prob, nullptr, pos, qlen, rlen, qchars, rchars, cap_variants,
+                      cap_chars, n_variants);
+}
+
+static int map_entry(const kbo_index* cix, const kbo_index* ref_index, const uint8_t* ref_seq, uint64_t len,
+                     double max_error_prob, int do_fill_gaps, int do_call_variants, int format,
+                     const kbo_build_opts* sbwt_build_opts, uint8_t* out) {
     kbo_index* ix = const_cast<kbo_index*>(cix);
     if (!ix || !out) return fail(KBO_ERR_BAD_ARGUMENT, "null argument");
     kbo_build_opts o;
     if (sbwt_build_opts) o = *sbwt_build_opts; else { kbo_default_build_opts(&o); o.build_select = 1; }
+    if (ref_index) o.k = ref_index->host.k;  // (the options the caller built it with)
     if (do_call_variants && ix->host.k != o.k)  // lib.rs:729
         return fail(KBO_ERR_K_MISMATCH, "index k differs from sbwt_build_opts.k (lib.rs:729)");
     const uint64_t offsets[2] = {0, len};
@@ -2673,7 +2793,7 @@ int kbo_map(const kbo_index* cix, const uint8_t* ref_seq, uint64_t len, double m
         if (do_call_variants) {                                                             // lib.rs:749-751
             std::vector<VariantRec> vars;
             ms.release();  // (the arrays are not needed any more; call_impl takes workspaces of its own)
-            rc = call_impl(ix, ref_seq, len, max_error_prob, &o, cands, &vars);
+            rc = call_impl(ix, ref_seq, len, max_error_prob, &o, cands, &vars, const_cast<kbo_index*>(ref_index));
             if (rc) return rc;
             bt.lap("map: call (ref index, k-mer MS, resolve)");
             add_variants(&aln, vars);
@@ -2684,6 +2804,15 @@ int kbo_map(const kbo_index* cix, const uint8_t* ref_seq, uint64_t len, double m
     if (format) return kbo_relative_to_ref(ref_seq, aln.data(), len, out);  // lib.rs:756-760
     std::memcpy(out, aln.data(), len);
     return KBO_OK;
+}
+int kbo_map(const kbo_index* cix, const uint8_t* ref_seq, uint64_t len, double max_error_prob, int do_fill_gaps,
+            int do_call_variants, int format, const kbo_build_opts* sbwt_build_opts, uint8_t* out) {
+    return map_entry(cix, nullptr, ref_seq, len, max_error_prob, do_fill_gaps, do_call_variants, format, sbwt_build_opts, out);
+}
+int kbo_map_with_ref(const kbo_index* cix, const kbo_index* ref_index, const uint8_t* ref_seq, uint64_t len,
+                     double max_error_prob, int do_fill_gaps, int do_call_variants, int format, uint8_t* out) {
+    if (!ref_index) return fail(KBO_ERR_BAD_ARGUMENT, "ref_index is null");
+    return map_entry(cix, ref_index, ref_seq, len, max_error_prob, do_fill_gaps, do_call_variants, format, nullptr, out);
 }
 
 // ---- standalone derandomize / translate ------------------------------------------------
@@ -2801,6 +2930,7 @@ int kbo_set_device_parts(uint32_t parts) { g_dev_parts = parts > 16 ? 16 : parts
 int kbo_set_pipeline_parts(uint32_t parts) { g_parts = parts > 64 ? 64 : parts; return KBO_OK; }
 int kbo_set_host_builder(int enabled) { g_host_builder = enabled ? 1 : 0; return KBO_OK; }
 int kbo_set_prefix_table(int enabled) { g_prefix_table = enabled ? 1 : 0; return KBO_OK; }
+int kbo_set_prefix_len(uint32_t len) { g_prefix_len = (int)std::min<uint32_t>(len, PREF_MAX_LEN); return KBO_OK; }
 int kbo_set_rank2(int enabled) { g_rank2 = enabled ? 1 : 0; return KBO_OK; }
 int kbo_set_l2_persist(int enabled) { g_l2_persist = enabled ? 1 : 0; return KBO_OK; }
 int kbo_set_ms_flags(uint32_t flags) {

@@ -234,14 +234,13 @@ __global__ void __launch_bounds__(FUSED_THREADS, 8) ms_fused_kernel(const KBO_GR
                 }
             }
             uint32_t l = 0, r = n, d = 0;
-            if (p.ix.pref && warm >= PREF_LEN) {
+            const uint32_t P = p.ix.pref ? p.ix.pref_len : 0u;
+            if (P && warm >= P) {
                 const uint32_t first = a - warm;
                 const uint32_t sh = 2u * (first & 31u);
                 uint64_t bits = pack_s[first >> 5] >> sh;
-                if (sh > 64 - 2 * PREF_LEN) bits |= pack_s[(first >> 5) + 1] << (64 - sh);
-                const uint4 s = __ldg(p.ix.pref + ((uint32_t)bits & ((1u << (2 * PREF_LEN)) - 1u)));
-                l = s.x; r = s.y; d = s.z;
-                warm -= PREF_LEN;
+                if (sh > 64 - 2 * P) bits |= pack_s[(first >> 5) + 1] << (64 - sh);
+                if (pref_decode(__ldg(p.ix.pref + ((uint32_t)bits & ((1u << (2 * P)) - 1u))), n, l, r, d)) warm -= P;
             }
             uint32_t bp = a - warm;
             // Bytes of positions >= a go to the tile's MS array; the lane's provisional bytes of its warm-up positions

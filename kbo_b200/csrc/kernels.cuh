@@ -42,8 +42,10 @@ namespace kbo_b200 {
 //          PSV / NSV = nearest position to the left / right whose LCS is smaller; 4095 = farther than that (or none).
 //          contract_left to the first depth that changes the interval is then two loads and a few additions.
 //   rank2: see IndexView::rank2 (DESIGN.md "two bases per probe").
-//   pref : for k >= PREF_MIN_K, the MS state after any string of PREF_LEN = 10 bases (index: first base in the low bits);
-//          a chunk's warm-up starts from this entry instead of stepping through its first ten bases.
+//   pref : for k >= PREF_MIN_K, the MS state after any string of pref_len bases fed to the empty state (index: first
+//          base in the low bits; 8 bytes per entry, pref_encode).  A chunk's warm-up starts from its entry instead of
+//          stepping through its first pref_len bases, and a failed extension at depth <= pref_len is resolved by ONE
+//          lookup: the new state is at most that deep, so it is the state after the last pref_len bases.
 // ---------------------------------------------------------------------------
 struct IndexView {
     const uint64_t* rank;
@@ -55,7 +57,8 @@ struct IndexView {
     uint32_t rank_stride;  // words per row (< 2^28 for n_sets < 2^32)
     const uint8_t* lcs;
     const uint32_t* links;  // n + 1 entries: LCS | distance to the previous smaller LCS << 8 | to the next smaller << 20
-    const uint4* pref;      // optional: MS state (l, r, d, -) after PREF_LEN bases fed to the empty state, 4^PREF_LEN entries
+    const uint64_t* pref;   // optional: MS state after pref_len bases fed to the empty state, 4^pref_len entries (pref_encode)
+    uint32_t pref_len;
     uint32_t n;  // n_sets
     uint32_t k;
 };
@@ -368,8 +371,8 @@ __device__ __forceinline__ bool ms_contract(const IndexView& ix, uint32_t el, ui
 }
 
 // One base through the MS recurrence (extend; on failure at d > 0 contract and retry): what K1's loop does to a
-// lane's state between two advances.  Used to tabulate the states after PREF_LEN bases.
-enum { PREF_LEN = 10, PREF_MIN_K = 16 };
+// lane's state between two advances.  Used to tabulate the states after pref_len bases.
+enum { PREF_LEN = 10, PREF_MIN_K = 16, PREF_MAX_LEN = 14, PREF_WIDTH_SAT = (1 << 27) - 1 };  // PREF_LEN: the default depth
 __device__ __forceinline__ void ms_feed_base(const IndexView& ix, uint32_t c, uint32_t& l, uint32_t& r, uint32_t& d) {
     for (;;) {
         const uint32_t rowoff = c * ix.rank_stride;
@@ -385,25 +388,58 @@ __device__ __forceinline__ void ms_feed_base(const IndexView& ix, uint32_t c, ui
         ms_contract(ix, ix.links[l], ix.links[r], l, r, d);
     }
 }
-// level j (1..PREF_LEN): cur[idx] for the 4^j strings of j bases, from prev (level j-1; unused for j == 1)
-__global__ void prefix_table_level_kernel(IndexView ix, const uint4* __restrict__ prev, uint4* __restrict__ cur, uint32_t j) {
+// A table entry: l in the low word, (r - l) << 5 | d in the high word (d <= pref_len < 32).  d == 0 stands for the
+// empty state (0, [0, n)); an interval of 2^27 - 1 or more nodes does not fit and reads back as "no entry" (only
+// possible at depths below 3 for n < 2^32: the reader then steps or contracts as if there were no table).
+__device__ __forceinline__ uint64_t pref_encode(uint32_t l, uint32_t r, uint32_t d) {
+    uint32_t w = r - l;
+    if (w > (uint32_t)PREF_WIDTH_SAT) w = (uint32_t)PREF_WIDTH_SAT;
+    if (d == 0) { l = 0; w = 0; }
+    return (uint64_t)l | ((uint64_t)((w << 5) | d) << 32);
+}
+__device__ __forceinline__ bool pref_decode(uint64_t e, uint32_t n, uint32_t& l, uint32_t& r, uint32_t& d) {
+    const uint32_t hi = (uint32_t)(e >> 32), w = hi >> 5, dd = hi & 31u;
+    if (dd == 0) { l = 0; r = n; d = 0; return true; }
+    if (w == (uint32_t)PREF_WIDTH_SAT) return false;
+    l = (uint32_t)e; r = l + w; d = dd;
+    return true;
+}
+// level j (1 ..): cur[idx] for the 4^j strings of j bases, from prev (level j-1; unused for j == 1)
+__global__ void prefix_table_level_kernel(IndexView ix, const uint64_t* __restrict__ prev, uint64_t* __restrict__ cur, uint32_t j) {
     const uint32_t idx = blockIdx.x * blockDim.x + threadIdx.x;
     if (idx >= (1u << (2 * j))) return;
     const uint32_t c = idx >> (2 * (j - 1));               // the newest base sits in the highest two bits
     const uint32_t parent = idx & ((1u << (2 * (j - 1))) - 1u);
     uint32_t l = 0, r = ix.n, d = 0;
-    if (j > 1) {
-        const uint4 s = prev[parent];
-        l = s.x; r = s.y; d = s.z;
+    if (j > 1 && !pref_decode(prev[parent], ix.n, l, r, d)) {  // the parent's interval did not fit: feed its bases again
+        l = 0; r = ix.n; d = 0;
+        for (uint32_t t = 0; t + 1 < j; ++t) ms_feed_base(ix, (parent >> (2 * t)) & 3u, l, r, d);
     }
     ms_feed_base(ix, c, l, r, d);
-    cur[idx] = make_uint4(l, r, d, 0u);
+    cur[idx] = pref_encode(l, r, d);
 }
 
-// One extend attempt per loop iteration and lane.  A lane whose extension fails (at d > 0) contracts in the same
-// iteration -- two loads of `links` and a few additions -- and retries the base in the next one.
+// A read-only 8-byte load that stays where it is written: the compiler otherwise sinks the speculative table load below
+// the first use of the rank words, i.e. behind the very round trip it is meant to overlap with.
+__device__ __forceinline__ uint64_t ldg_issue_here(const uint64_t* ptr) {
+#ifdef KBO_HOST_EMU
+    return *ptr;
+#else
+    uint64_t v;
+    asm volatile("ld.global.nc.u64 %0, [%1];" : "=l"(v) : "l"(ptr));
+    return v;
+#endif
+}
+
+// One extend attempt per loop iteration and lane.  A lane whose extension fails at depth d > 0:
+//  * d <= pref_len and the last pref_len positions are bases of this query: the new state is at most d deep (the
+//    (d+1)-suffix is not in the index), so it is the state after the last pref_len bases -- ONE table lookup, and the
+//    lane advances in this iteration.  This is what a mismatch costs in the stretch after it, where the depth hovers
+//    around log4(n): one iteration per base instead of fail / contract / retry (profiles/README.md, round 2);
+//  * otherwise it contracts in the same iteration -- two loads of `links` and a few additions -- and retries the base
+//    in the next one.
 template <bool INTERVALS, bool COUNT>
-__global__ void __launch_bounds__(256, 6) ms_kernel(MsParams p) {
+__global__ void __launch_bounds__(256, 5) ms_kernel(MsParams p) {
     __shared__ __align__(16) uint8_t ms_stage[256 * 36];
     const uint64_t g = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
     unsigned long long cnt_att = 0, cnt_split = 0, cnt_con = 0, cnt_extra = 0, cnt_proc = 0, cnt_emit = 0;
@@ -426,14 +462,20 @@ __global__ void __launch_bounds__(256, 6) ms_kernel(MsParams p) {
             }
         }
         uint32_t l = 0, r = n, d = 0;
-        if (p.ix.pref && warm >= PREF_LEN) {
+        const uint32_t P = p.ix.pref ? p.ix.pref_len : 0u;
+        uint32_t hist = 0;  // the last 16 bases, the newest in the top two bits
+        uint32_t vrun = 0;  // consecutive bases of this query consumed so far (saturating; a non-ACGT position restarts it)
+        if (P && warm >= P) {
             const uint64_t first = start - warm;
             const uint32_t sh = 2 * (uint32_t)(first & 31);
             uint64_t bits = __ldg(p.q.pack + (first >> 5)) >> sh;
-            if (sh > 64 - 2 * PREF_LEN) bits |= __ldg(p.q.pack + (first >> 5) + 1) << (64 - sh);
-            const uint4 s = __ldg(p.ix.pref + ((uint32_t)bits & ((1u << (2 * PREF_LEN)) - 1u)));
-            l = s.x; r = s.y; d = s.z;
-            warm -= PREF_LEN;
+            if (sh > 64 - 2 * P) bits |= __ldg(p.q.pack + (first >> 5) + 1) << (64 - sh);
+            const uint32_t idx = (uint32_t)bits & ((1u << (2 * P)) - 1u);
+            if (pref_decode(__ldg(p.ix.pref + idx), n, l, r, d)) {
+                warm -= P;
+                hist = idx << (32 - 2 * P);
+                vrun = P;
+            }
         }
         const uint64_t pos0 = start - warm;
         const uint64_t wbase = pos0 >> 5;
@@ -448,10 +490,23 @@ __global__ void __launch_bounds__(256, 6) ms_kernel(MsParams p) {
         // emitted MS bytes are staged in shared memory (36-byte stride per lane: conflict-free word access) and
         // flushed as two 16-byte stores per 32 positions; chunk starts are multiples of 32, so flushes are aligned
         uint8_t* const stg = ms_stage + threadIdx.x * 36u;
+        // A lane at depth <= P asks for the state after the last P bases (the coming one included) BEFORE the iteration
+        // that may need it: when that extension fails the answer has travelled together with the rank words (one memory
+        // round trip per iteration instead of two).  Issued at the end of the previous iteration because the compiler
+        // otherwise schedules the load behind the first use of the rank words.
+        bool spec = false;
+        uint64_t pe = 0;
+#define KBO_K1_ISSUE_SPEC()                                                                                       \
+    do {                                                                                                          \
+        spec = d - 1u < P && vrun + 1u >= P;                                                                      \
+        if (spec) pe = ldg_issue_here(p.ix.pref + (__funnelshift_r(hist, (uint32_t)qw, 2) >> (32 - 2 * P)));       \
+    } while (0)
+        KBO_K1_ISSUE_SPEC();
         while (bp < bp_end) {
             bool advance = true;
             if (iw & 1u) {
                 l = 0; r = n; d = 0;
+                vrun = ~0u;  // (+ 1 below: no base of the current run consumed yet)
             } else {
                 const uint32_t rowoff = ((uint32_t)qw & 3u) * p.ix.rank_stride;  // 32-bit word index
                 const uint32_t bl = l >> 5, br = r >> 5;
@@ -468,13 +523,23 @@ __global__ void __launch_bounds__(256, 6) ms_kernel(MsParams p) {
                     l = nl; r = nr;
                     d = d + 1 < k ? d + 1 : k;
                 } else if (d != 0) {
-                    // contract_left to the largest depth that changes the interval: t = max(LCS[l], LCS[r])
-                    advance = false;
-                    const uint32_t el = __ldg(p.ix.links + l), er = __ldg(p.ix.links + r);
-                    const bool scanned = ms_contract(p.ix, el, er, l, r, d);
-                    if (COUNT) {
-                        ++cnt_con; cnt_extra += scanned;
-                        if (bp >= bp_emit) { ++cnt_con_e; cnt_extra_e += scanned; }
+                    bool resolved = false;
+                    if (spec) {  // the state after the last P bases, this one included
+                        resolved = pref_decode(pe, n, l, r, d);
+                        if (COUNT) {  // (counted with the contractions: one 32-byte sector each)
+                            ++cnt_con;
+                            if (bp >= bp_emit) ++cnt_con_e;
+                        }
+                    }
+                    if (!resolved) {
+                        // contract_left to the largest depth that changes the interval: t = max(LCS[l], LCS[r])
+                        advance = false;
+                        const uint32_t el = __ldg(p.ix.links + l), er = __ldg(p.ix.links + r);
+                        const bool scanned = ms_contract(p.ix, el, er, l, r, d);
+                        if (COUNT) {
+                            ++cnt_con; cnt_extra += scanned;
+                            if (bp >= bp_emit) { ++cnt_con_e; cnt_extra_e += scanned; }
+                        }
                     }
                 }
             }
@@ -489,6 +554,8 @@ __global__ void __launch_bounds__(256, 6) ms_kernel(MsParams p) {
                     }
                 }
                 ++bp;
+                hist = __funnelshift_r(hist, (uint32_t)qw, 2);
+                vrun = vrun + 1u < 16u ? vrun + 1u : 16u;
                 qw >>= 2;
                 iw >>= 1;
                 if ((bp & 31) == 0 || bp == bp_end) {
@@ -504,7 +571,9 @@ __global__ void __launch_bounds__(256, 6) ms_kernel(MsParams p) {
                     }
                 }
             }
+            KBO_K1_ISSUE_SPEC();
         }
+#undef KBO_K1_ISSUE_SPEC
     }
     if (COUNT) {
         atomicAdd(p.counters + CNT_ATTEMPTS, cnt_att);
@@ -551,14 +620,13 @@ __global__ void __launch_bounds__(256, 6) ms_pairs_kernel(MsParams p) {
                 break;
             }
         }
-        if (p.ix.pref && warm >= PREF_LEN) {
+        const uint32_t P = p.ix.pref ? p.ix.pref_len : 0u;
+        if (P && warm >= P) {
             const uint64_t first = start - warm;
             const uint32_t sh = 2 * (uint32_t)(first & 31);
             uint64_t bits = __ldg(p.q.pack + (first >> 5)) >> sh;
-            if (sh > 64 - 2 * PREF_LEN) bits |= __ldg(p.q.pack + (first >> 5) + 1) << (64 - sh);
-            const uint4 s = __ldg(p.ix.pref + ((uint32_t)bits & ((1u << (2 * PREF_LEN)) - 1u)));
-            l = s.x; r = s.y; d = s.z;
-            warm -= PREF_LEN;
+            if (sh > 64 - 2 * P) bits |= __ldg(p.q.pack + (first >> 5) + 1) << (64 - sh);
+            if (pref_decode(__ldg(p.ix.pref + ((uint32_t)bits & ((1u << (2 * P)) - 1u))), n, l, r, d)) warm -= P;
         }
         const uint64_t pos0 = start - warm;
         wbase = pos0 >> 5;

@@ -83,18 +83,22 @@ __device__ __forceinline__ bool rank_step(const IndexView& ix, uint32_t c, uint3
     return true;
 }
 // SbwtIndex::search of the first m characters of a window without '$': extend_right folded over them from [0, n).
-// The state after PREF_LEN characters is the table entry when all of them extended (its depth is PREF_LEN).
+// The state after pref_len characters is the table entry when all of them extended (its depth is pref_len).
 __device__ __forceinline__ bool search_window(const IndexView& ix, uint64_t lo, uint64_t hi, uint32_t m, uint32_t& l,
                                               uint32_t& r) {
     l = 0;
     r = ix.n;
     uint32_t j = 0;
-    if (ix.pref && m >= PREF_LEN) {
-        const uint4 s = __ldg(ix.pref + ((uint32_t)lo & ((1u << (2 * PREF_LEN)) - 1u)));
-        if (s.z != PREF_LEN) return false;
-        l = s.x;
-        r = s.y;
-        j = PREF_LEN;
+    const uint32_t P = ix.pref ? ix.pref_len : 0u;
+    if (P && m >= P) {
+        uint32_t d = 0;
+        if (pref_decode(__ldg(ix.pref + ((uint32_t)lo & ((1u << (2 * P)) - 1u))), ix.n, l, r, d)) {
+            if (d != P) return false;  // some base of the first P did not extend
+            j = P;
+        } else {
+            l = 0;
+            r = ix.n;
+        }
     }
     for (; j < m; ++j) {
         const uint32_t c = (uint32_t)(j < 32 ? lo >> (2 * j) : hi >> (2 * (j - 32))) & 3u;

@@ -27,6 +27,8 @@ static uint32_t g_emu_flags = 0;
 extern "C" void emu_set_ms_flags(uint32_t v) { g_emu_flags = v; }
 static int g_emu_prefix_table = 1;  // 0: indexes built afterwards get no prefix-state table
 extern "C" void emu_set_prefix_table(int v) { g_emu_prefix_table = v; }
+static uint32_t g_emu_prefix_len = PREF_LEN;  // depth of the table of indexes built afterwards
+extern "C" void emu_set_prefix_len(uint32_t v) { g_emu_prefix_len = v ? v : PREF_LEN; }
 static int g_emu_k2_mode = 0;  // 0: as the product dispatches, 1: always K2, 2: K2b (where supported)
 extern "C" void emu_set_k2_mode(int v) { g_emu_k2_mode = v; }
 
@@ -52,7 +54,7 @@ struct EmuIndex {
     DeviceLayout lay;
     std::vector<uint64_t> rank2;
     std::vector<uint32_t> links;
-    std::vector<uint4> pref, pref_tmp;
+    std::vector<uint64_t> pref, pref_tmp;
     IndexView view;
 };
 
@@ -84,17 +86,20 @@ static void finish(EmuIndex* e) {
                    [&]() { lcs_links_kernel(e->lay.lcs.data(), n, e->links.data()); });
     e->view.links = e->links.data();
     e->view.pref = nullptr;
-    if (e->view.k >= PREF_MIN_K && g_emu_prefix_table) {  // as capi.cu build_links
-        const size_t last = (size_t)1 << (2 * PREF_LEN);
-        e->pref_tmp.assign(last / 4, uint4{0, 0, 0, 0});
-        e->pref.assign(last, uint4{0, 0, 0, 0});
-        for (uint32_t j = 1; j <= PREF_LEN; ++j) {
+    e->view.pref_len = 0;
+    if (e->view.k >= PREF_MIN_K && g_emu_prefix_table) {  // as capi.cu build_pref_table
+        const uint32_t P = std::min<uint32_t>(std::min<uint32_t>(g_emu_prefix_len, PREF_MAX_LEN), e->view.k - 1);
+        const size_t last = (size_t)1 << (2 * P);
+        e->pref_tmp.assign(std::max<size_t>(last / 4, 4), 0);
+        e->pref.assign(last, 0);
+        for (uint32_t j = 1; j <= P; ++j) {
             const uint32_t cnt = 1u << (2 * j);
-            uint4* cur = (j & 1) ? e->pref_tmp.data() : e->pref.data();
-            const uint4* prev = (j & 1) ? e->pref.data() : e->pref_tmp.data();
+            uint64_t* cur = ((P - j) & 1u) ? e->pref_tmp.data() : e->pref.data();
+            const uint64_t* prev = ((P - j) & 1u) ? e->pref.data() : e->pref_tmp.data();
             emu_launch_seq((cnt + 255) / 256, 256, [&]() { prefix_table_level_kernel(e->view, prev, cur, j); });
         }
         e->view.pref = e->pref.data();
+        e->view.pref_len = P;
     }
 }
 

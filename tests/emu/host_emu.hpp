@@ -89,6 +89,9 @@ inline int __any_sync(unsigned m, bool pred) { return __ballot_sync(m, pred) != 
 inline void __syncwarp(unsigned = 0xffffffffu) { emu_warp->bar.arrive_and_wait(); }
 inline void __syncthreads() { emu_block->bar->arrive_and_wait(); }
 
+inline unsigned __funnelshift_r(unsigned lo, unsigned hi, unsigned sh) {
+    return (unsigned)((((unsigned long long)hi << 32) | lo) >> (sh & 31u));
+}
 inline int __popc(unsigned x) { return __builtin_popcount(x); }
 inline int __popcll(unsigned long long x) { return __builtin_popcountll(x); }
 inline int __clz(int x) { return x ? __builtin_clz((unsigned)x) : 32; }

@@ -65,6 +65,7 @@ def lib():
         L.emu_rle_batch.argtypes = [u8p, u64p, C.c_uint64, C.c_uint32, u64p, C.c_uint64, u64p]
         L.emu_set_rank2.argtypes = [C.c_int]
         L.emu_set_device_refine.argtypes = [C.c_int]
+        L.emu_set_prefix_len.argtypes = [C.c_uint32]
         L.emu_device_gap_count.restype = C.c_uint64
         L.emu_set_fused.argtypes = [C.c_int, C.c_uint32, C.c_int]
         L.emu_fused_launches.restype = C.c_uint64
@@ -80,6 +81,11 @@ def set_device_refine(on):
     """map / call: fill_gaps and access_kmer through the kernels of refine.cuh (as capi.cu does when the index keeps
     its node keys on the device) instead of refine_host.cpp."""
     lib().emu_set_device_refine(int(bool(on)))
+
+
+def set_prefix_len(p):
+    """Depth of the prefix-state table of indexes built afterwards (0 = the default, 10)."""
+    lib().emu_set_prefix_len(int(p))
 
 
 def device_gap_count():

@@ -248,6 +248,55 @@ def test_prefix_table_and_wide_intervals():
         api.set_prefix_table(True)
 
 
+@pytest.mark.parametrize("depth", [1, 5, 11, 12, 13, 14])
+def test_prefix_table_depths(depth):
+    """The prefix-state table at explicit depths (kbo_set_prefix_len): warm-up from it and one lookup per failed
+    extension at depth <= P.  (d, l, r), matches and find must not depend on the depth."""
+    ref = rand_seq(120_000, 21)
+    asm = synth.mutate(np.frombuffer(ref, dtype=np.uint8), 22).tobytes()
+    o = O.OracleIndex([asm], k=31)
+    queries = [ref[:30_000], with_ns(ref[30_000:36_000], 5, 0.03), rand_seq(3000, 23), b"ACGTN" * 50, b"A",
+               ref[40_000:40_011], b"N" * 40 + ref[100:160], ref[50_000:50_700] + b"-" + ref[9:500]]
+    api.set_prefix_len(depth)
+    try:
+        ix = api.build([asm], api.BuildOpts(k=31))
+    finally:
+        api.set_prefix_len(0)
+    d, l, r, off = api.query_sbwt_batch(queries, ix)
+    for i, qq in enumerate(queries):
+        od, ol, orr = o.query_sbwt(qq)
+        a, b_ = int(off[i]), int(off[i + 1])
+        assert np.array_equal(d[a:b_].astype(np.uint64), od), i
+        assert np.array_equal(l[a:b_].astype(np.uint64), ol), i
+        assert np.array_equal(r[a:b_].astype(np.uint64), orr), i
+    long_q = [q for q in queries if len(q) > 2]
+    got = api.matches_batch(long_q, ix)
+    for i, qq in enumerate(long_q):
+        assert got[i] == o.matches(qq), i
+
+
+def test_prefix_table_deepens_once_the_index_serves_batches():
+    """Automatic depth: 10 at construction; after 4 M bases of batch queries the index gets the table of depth
+    ceil(log4 n) + 1 (here 10 -> 11 for 4^9 < n <= 4^10 nodes), built once, and results stay identical."""
+    ref = rand_seq(600_000, 25)
+    asm = synth.mutate(np.frombuffer(ref, dtype=np.uint8), 26).tobytes()
+    o = O.OracleIndex([asm], k=31)
+    ix = api.build([asm], api.BuildOpts(k=31))
+    bytes0 = ix.device_bytes
+    genes = [ref[s:s + 1000] for s in range(0, 590_000, 997)]
+    want = [o.matches(q) for q in genes[:40]]
+    assert api.matches_batch(genes[:40], ix) == want
+    for _ in range(9):  # 9 x 0.59 M bases
+        api.matches_batch(genes, ix)
+    assert ix.device_bytes == bytes0 + 8 * 4 ** 11
+    assert api.matches_batch(genes[:40], ix) == want
+    d, l, r, off = api.query_sbwt_batch(genes[:5], ix)
+    for i in range(5):
+        od, ol, orr = o.query_sbwt(genes[i])
+        a, b_ = int(off[i]), int(off[i + 1])
+        assert np.array_equal(d[a:b_].astype(np.uint64), od) and np.array_equal(l[a:b_].astype(np.uint64), ol)
+
+
 def test_ms_invariants_large():
     """Size-independent properties at a larger size: chunking never changes the result, MS grows by
     at most one per base, intervals are non-empty and inside [0, n_sets]."""
@@ -663,6 +712,11 @@ def test_map_and_call_match_oracle(k, p, seed):
     for fill, callv, fmt in ((True, True, True), (True, False, False), (False, True, False)):
         want = o.map(r, max_error_prob=p, fill_gaps=fill, call_variants=callv, format=fmt, build_k=k)
         assert api.map(r, ix, api.MapOpts(p, fill, callv, fmt, bo)) == want, (fill, callv, fmt)
+    # the index of the reference built once by the caller instead of per call (kbo_call_with_ref / kbo_map_with_ref)
+    rix = api.build([r], bo)
+    got = api.call(ix, r, api.CallOpts(p, bo), ref_index=rix)
+    assert [(v.query_pos, v.query_chars, v.ref_chars) for v in got] == want_vars
+    assert api.map(r, ix, api.MapOpts(p, True, True, True, bo), ref_index=rix) == o.map(r, max_error_prob=p, build_k=k)
     api.set_device_refine(False)  # the host versions of fill_gaps / access_kmer (the index mirror is read back lazily)
     try:
         got = api.call(ix, r, api.CallOpts(p, bo))

@@ -67,11 +67,11 @@ def parse_args():
                     help="configs 3 / 4: host threads per rank, each taking whole assemblies (kbo-cli style)")
     ap.add_argument("--k", type=int, default=31, help="configs 3 / 4: k of the indexes (k > 32 takes the host builder; the "
                                                       "reference resolves variants only when k - threshold leaves room, e.g. k = 51)")
+    ap.add_argument("--snp-rate", type=float, default=0.01, help="SNP rate of the synthetic gene queries (the config's: 0.01)")
     ap.add_argument("--batches", type=int, default=16, help="distinct batches rotated through (16 x 10 MB > L2)")
     ap.add_argument("--chunk-len", type=int, default=0, help="MS chunk length (0 = automatic)")
     ap.add_argument("--ms-flags", type=int, default=0, help="experiment switches (2: K2 instead of K2b)")
-    ap.add_argument("--prefix-len", type=int, default=0, help="depth of the prefix-state table (0 = automatic: 10, then "
-                    "ceil(log4 n) + 1 once the index serves batches)")
+    ap.add_argument("--prefix-len", type=int, default=0, help="depth of the prefix-state table (0 = the default, 10)")
     ap.add_argument("--no-prefix-table", action="store_true", help="build the index without the prefix-state table (comparison)")
     ap.add_argument("--no-rank2", action="store_true", help="build the index without the rank2 rows: one base per probe (comparison)")
     ap.add_argument("--no-l2-persist", action="store_true", help="do not mark the index persisting in L2 (comparison)")
@@ -176,7 +176,7 @@ def workload(args, rank):
     batches = []
     for b in range(args.batches):
         concat, offsets = synth.gene_queries(ref, args.queries, args.query_len,
-                                             synth.SEED_C2_GENES + 1000 * rank + b)
+                                             synth.SEED_C2_GENES + 1000 * rank + b, snp=args.snp_rate)
         batches.append(concat)
     return ref, batches, offsets
 
@@ -526,8 +526,7 @@ def run_ours(args, rank, local_rank, world):
     if rank == 0:
         cfg = config_dict(args)
         detail = {"index_device_bytes": index.device_bytes, "n_sets": index.n_sets,
-                  "prefix_table_depth": args.prefix_len or "auto (10 at construction, ceil(log4 n_sets) + 1 <= 13 once the "
-                                                           "index has served 4 M bases of batch queries)",
+                  "prefix_table_depth": args.prefix_len or 10,
                               "index_build_s": round(index_build_s, 3), "rle_records_per_step": n_rle,
                               "streams": len(workers),
                               "single_stream": {"ms_per_step": ms_single / args.steps,

@@ -277,10 +277,9 @@ int kbo_set_host_builder(int enabled);
 /* enabled == 0: indexes created afterwards carry no prefix-state table (K1 then warms every chunk up over k-1 bases;
  * comparison runs).  Results never depend on it. */
 int kbo_set_prefix_table(int enabled);
-/* Depth P of the prefix-state table (the MS state after every string of P bases: a chunk's warm-up starts from it, and a
- * failed extension at depth <= P is one lookup instead of contract + retry).  0 = automatic: 10 at construction, and
- * ceil(log4 n_sets) + 1 (at most 13: 8 bytes x 4^13 = 537 MB) once the index has served 4 M bases of batch queries.
- * 1 .. 14: indexes created afterwards get exactly that depth (capped at k - 1).  Results never depend on it. */
+/* Depth P of the prefix-state table of indexes created afterwards (the MS state after every string of P bases: a
+ * chunk's warm-up starts from its entry instead of stepping through those bases; 8 bytes x 4^P).  0 = the default, 10;
+ * at most 14, capped at k - 1.  Results never depend on it. */
 int kbo_set_prefix_len(uint32_t len);
 /* enabled == 0: indexes created afterwards carry no rank2 rows (K1 then probes one base at a time; comparison runs).
  * Results never depend on it. */

@@ -264,7 +264,7 @@ class Index:
 
     @property
     def device_bytes(self):
-        """Device memory of the index (grows when the deeper prefix-state table or the rank2 rows are made)."""
+        """Device memory of the index."""
         return load_library().kbo_index_device_bytes(self._h) if self._h else 0
 
     def close(self):
@@ -698,7 +698,7 @@ def set_host_builder(enabled):
 
 
 def set_prefix_len(p):
-    """Depth of the prefix-state table (0 = automatic; see kbo_set_prefix_len in the header)."""
+    """Depth of the prefix-state table of indexes built afterwards (0 = the default, 10; at most 14)."""
     _check(load_library().kbo_set_prefix_len(int(p)))
 
 

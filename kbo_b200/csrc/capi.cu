@@ -41,7 +41,7 @@ static std::atomic<uint32_t> g_chunk_len(0);
 static std::atomic<int> g_kernel_timing(0);
 static std::atomic<int> g_rank2(1);  // 0: indexes built afterwards carry no two-bases-per-probe rows (comparison runs)
 static std::atomic<int> g_prefix_table(1);  // 0: indexes built afterwards get no prefix-state table (comparison runs)
-static std::atomic<int> g_prefix_len(0);    // 0: automatic (PREF_LEN at construction, deepened once the index serves batches)
+static std::atomic<int> g_prefix_len(0);    // depth of the prefix-state table of indexes built afterwards (0: PREF_LEN)
 static std::atomic<int> g_l2_persist(1);  // 0: do not mark the index persisting in L2 (comparison runs)
 static std::atomic<uint32_t> g_ms_flags(0);
 static std::atomic<int> g_host_builder(0);
@@ -164,11 +164,6 @@ struct kbo_index {
     uint32_t* d_links = nullptr;  // per node: LCS and the distances to the nearest smaller LCS on both sides
     uint8_t* d_blob = nullptr;    // the one allocation holding rank | links | lcs (one L2 access-policy window)
     uint64_t* d_pref = nullptr;   // MS states after view.pref_len bases (k >= PREF_MIN_K)
-    // the deeper table (ensure_deep_pref) and the view that carries it, published through deep_ready once complete
-    uint64_t* d_pref_deep = nullptr;
-    IndexView view_deep;
-    std::atomic<bool> deep_ready{false};
-    std::atomic<uint64_t> batch_bases{0};  // query bases that went through the batch entry points
     // "select support" (BuildOpts.build_select) on the device: the colex-sorted node keys of the GPU builder
     // (refine.cuh NodeKeysView); null for indexes made from parts or by the host builder
     uint64_t* d_node_keys = nullptr;
@@ -417,7 +412,7 @@ static int build_rank2(kbo_index* ix) {
     };
     const int rc = body();
     cudaFree(rows2); cudaFree(pc); cudaFree(prefix); cudaFree(scan_tmp);
-    if (rc == KBO_OK) ix->view.rank2 = ix->view_deep.rank2 = ix->d_rank2;
+    if (rc == KBO_OK) ix->view.rank2 = ix->d_rank2;
     return rc;
 }
 
@@ -446,36 +441,6 @@ static int build_pref_table(const IndexView& view, uint32_t P, uint64_t** out) {
         return fail(KBO_ERR_CUDA, std::string("CUDA error: ") + cudaGetErrorString(e) + " in the prefix-state table");
     }
     *out = b;
-    return KBO_OK;
-}
-
-// Depth of the table an index gets once it serves batches: failed extensions happen at depths around log4(n) (the
-// length of a chance match), and one at depth <= pref_len costs one lookup instead of contract + retry.
-static uint32_t deep_pref_len(const kbo_index* ix) {
-    uint32_t lg = 0;
-    while (lg < 16 && (1ull << (2 * lg)) < ix->host.n_sets) ++lg;  // ceil(log4 n)
-    uint32_t P = std::min<uint32_t>(lg + 1, 13);
-    P = std::max<uint32_t>(P, PREF_LEN);
-    return std::min<uint32_t>(P, ix->view.k - 1);
-}
-// The view K1 runs with: the deeper table once it exists.
-static const IndexView& current_view(const kbo_index* ix) {
-    return ix->deep_ready.load(std::memory_order_acquire) ? ix->view_deep : ix->view;
-}
-static int ensure_deep_pref(kbo_index* ix) {
-    if (!ix->view.pref || g_prefix_len.load() > 0 || ix->deep_ready.load(std::memory_order_acquire)) return KBO_OK;
-    const uint32_t P = deep_pref_len(ix);
-    if (P <= ix->view.pref_len) return KBO_OK;
-    std::lock_guard<std::mutex> g(ix->host_mu);
-    if (ix->deep_ready.load(std::memory_order_acquire)) return KBO_OK;
-    const int rc = build_pref_table(ix->view, P, &ix->d_pref_deep);
-    if (rc == KBO_ERR_OOM) return KBO_OK;  // (an optimisation: the shallow table keeps serving)
-    if (rc) return rc;
-    ix->view_deep = ix->view;
-    ix->view_deep.pref = ix->d_pref_deep;
-    ix->view_deep.pref_len = P;
-    ix->device_bytes += ((uint64_t)8 << (2 * P));
-    ix->deep_ready.store(true, std::memory_order_release);
     return KBO_OK;
 }
 
@@ -869,14 +834,8 @@ static int run_ms(kbo_index* ix, Workspace* ws, const QueryView& qv, const Geome
         CUDA_TRY(cudaMemsetAsync(ws->counters.p, 0, CNT_N * 8, st));
     }
     if (!intervals && (tuned_ms_flags(ix) & 32u)) { const int rc = ensure_rank2(ix); if (rc) return rc; }
-    // an index that serves batches (matches / find; 4 M bases so far) gets the deeper prefix-state table once
-    if (!intervals && !ix->deep_ready.load(std::memory_order_relaxed) &&
-        ix->batch_bases.fetch_add(g.total, std::memory_order_relaxed) + g.total >= (4ull << 20)) {
-        const int rc = ensure_deep_pref(ix);
-        if (rc) return rc;
-    }
     MsParams mp;
-    mp.ix = current_view(ix);
+    mp.ix = ix->view;
     mp.q = qv;
     mp.chunk_len = g.chunk_len;
     mp.flags = tuned_ms_flags(ix);
@@ -1109,7 +1068,7 @@ static int run_fused(kbo_index* ix, Workspace* ws, const QueryView& qv, const Ge
     if (!(flags & 4u)) { const int rc = ensure_rank2(ix); if (rc) return rc; }  // (bit 2: one base per probe)
     FusedParams fp;
     std::memset(&fp, 0, sizeof(fp));
-    fp.ix = current_view(ix);
+    fp.ix = ix->view;
     fp.q = qv;
     fp.tr.ms = nullptr;
     fp.tr.q = qv;
@@ -1345,7 +1304,6 @@ void kbo_index_free(kbo_index* ix) {
         for (PinnedBuf& pb : ix->pinned_pool) if (pb.p) cudaFreeHost(pb.p);
         if (ix->d_blob) cudaFree(ix->d_blob);
         if (ix->d_pref) cudaFree(ix->d_pref);
-        if (ix->d_pref_deep) cudaFree(ix->d_pref_deep);
         if (ix->d_node_keys) cudaFree(ix->d_node_keys);
         if (ix->d_node_len) cudaFree(ix->d_node_len);
         bt.lap("index free");
@@ -2539,7 +2497,7 @@ static int device_fill_gaps(kbo_index* ix, Workspace* ws, uint64_t len, uint32_t
     unsigned long long init[2] = {0ull, ~0ull};  // arena bytes used, panic word
     CUDA_TRY(cudaMemcpyAsync(ws->counters2.as<uint8_t>() + 8, init, 16, cudaMemcpyHostToDevice, st));
     FillGapsParams fp;
-    fp.ix = current_view(ix);
+    fp.ix = ix->view;
     fp.nk.keys = ix->d_node_keys;
     fp.nk.len = ix->d_node_len;
     fp.nk.words = ix->node_key_words;
@@ -2985,8 +2943,11 @@ int kbo_measure_random_sector_rate(int device, uint64_t buffer_bytes, int depend
         CUDA_TRY(cudaMemset(sink, 0, 8));
         CUDA_TRY(cudaEventCreate(&e0));
         CUDA_TRY(cudaEventCreate(&e1));
-        const unsigned blocks = 148 * 8, threads = 256;  // 2048 resident lanes per SM, like K1
-        const uint32_t iters = dependent ? 256 : 1024;
+        // dependent > 1: dependent chains at that many warps per SM (blocks of four warps, rounded up): the latency of a
+        // warp-wide load of 32 distinct sectors at a given occupancy = lanes in flight / the rate reported
+        const unsigned blocks = dependent > 1 ? 148u * (((unsigned)dependent + 3u) / 4u) : 148u * 8u;  // (else 2048 lanes per SM)
+        const unsigned threads = dependent > 1 ? 128u : 256u;
+        const uint32_t iters = dependent > 1 ? 2048 : (dependent ? 256 : 1024);
         double best = 0.0;
         for (int rep = 0; rep < 5; ++rep) {
             CUDA_TRY(cudaEventRecord(e0));

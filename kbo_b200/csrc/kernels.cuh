@@ -44,8 +44,7 @@ namespace kbo_b200 {
 //   rank2: see IndexView::rank2 (DESIGN.md "two bases per probe").
 //   pref : for k >= PREF_MIN_K, the MS state after any string of pref_len bases fed to the empty state (index: first
 //          base in the low bits; 8 bytes per entry, pref_encode).  A chunk's warm-up starts from its entry instead of
-//          stepping through its first pref_len bases, and a failed extension at depth <= pref_len is resolved by ONE
-//          lookup: the new state is at most that deep, so it is the state after the last pref_len bases.
+//          stepping through its first pref_len bases.
 // ---------------------------------------------------------------------------
 struct IndexView {
     const uint64_t* rank;
@@ -419,27 +418,10 @@ __global__ void prefix_table_level_kernel(IndexView ix, const uint64_t* __restri
     cur[idx] = pref_encode(l, r, d);
 }
 
-// A read-only 8-byte load that stays where it is written: the compiler otherwise sinks the speculative table load below
-// the first use of the rank words, i.e. behind the very round trip it is meant to overlap with.
-__device__ __forceinline__ uint64_t ldg_issue_here(const uint64_t* ptr) {
-#ifdef KBO_HOST_EMU
-    return *ptr;
-#else
-    uint64_t v;
-    asm volatile("ld.global.nc.u64 %0, [%1];" : "=l"(v) : "l"(ptr));
-    return v;
-#endif
-}
-
-// One extend attempt per loop iteration and lane.  A lane whose extension fails at depth d > 0:
-//  * d <= pref_len and the last pref_len positions are bases of this query: the new state is at most d deep (the
-//    (d+1)-suffix is not in the index), so it is the state after the last pref_len bases -- ONE table lookup, and the
-//    lane advances in this iteration.  This is what a mismatch costs in the stretch after it, where the depth hovers
-//    around log4(n): one iteration per base instead of fail / contract / retry (profiles/README.md, round 2);
-//  * otherwise it contracts in the same iteration -- two loads of `links` and a few additions -- and retries the base
-//    in the next one.
+// One extend attempt per loop iteration and lane.  A lane whose extension fails (at d > 0) contracts in the same
+// iteration -- two loads of `links` and a few additions -- and retries the base in the next one.
 template <bool INTERVALS, bool COUNT>
-__global__ void __launch_bounds__(256, 5) ms_kernel(MsParams p) {
+__global__ void __launch_bounds__(256, 6) ms_kernel(MsParams p) {
     __shared__ __align__(16) uint8_t ms_stage[256 * 36];
     const uint64_t g = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
     unsigned long long cnt_att = 0, cnt_split = 0, cnt_con = 0, cnt_extra = 0, cnt_proc = 0, cnt_emit = 0;
@@ -463,19 +445,12 @@ __global__ void __launch_bounds__(256, 5) ms_kernel(MsParams p) {
         }
         uint32_t l = 0, r = n, d = 0;
         const uint32_t P = p.ix.pref ? p.ix.pref_len : 0u;
-        uint32_t hist = 0;  // the last 16 bases, the newest in the top two bits
-        uint32_t vrun = 0;  // consecutive bases of this query consumed so far (saturating; a non-ACGT position restarts it)
         if (P && warm >= P) {
             const uint64_t first = start - warm;
             const uint32_t sh = 2 * (uint32_t)(first & 31);
             uint64_t bits = __ldg(p.q.pack + (first >> 5)) >> sh;
             if (sh > 64 - 2 * P) bits |= __ldg(p.q.pack + (first >> 5) + 1) << (64 - sh);
-            const uint32_t idx = (uint32_t)bits & ((1u << (2 * P)) - 1u);
-            if (pref_decode(__ldg(p.ix.pref + idx), n, l, r, d)) {
-                warm -= P;
-                hist = idx << (32 - 2 * P);
-                vrun = P;
-            }
+            if (pref_decode(__ldg(p.ix.pref + ((uint32_t)bits & ((1u << (2 * P)) - 1u))), n, l, r, d)) warm -= P;
         }
         const uint64_t pos0 = start - warm;
         const uint64_t wbase = pos0 >> 5;
@@ -490,23 +465,10 @@ __global__ void __launch_bounds__(256, 5) ms_kernel(MsParams p) {
         // emitted MS bytes are staged in shared memory (36-byte stride per lane: conflict-free word access) and
         // flushed as two 16-byte stores per 32 positions; chunk starts are multiples of 32, so flushes are aligned
         uint8_t* const stg = ms_stage + threadIdx.x * 36u;
-        // A lane at depth <= P asks for the state after the last P bases (the coming one included) BEFORE the iteration
-        // that may need it: when that extension fails the answer has travelled together with the rank words (one memory
-        // round trip per iteration instead of two).  Issued at the end of the previous iteration because the compiler
-        // otherwise schedules the load behind the first use of the rank words.
-        bool spec = false;
-        uint64_t pe = 0;
-#define KBO_K1_ISSUE_SPEC()                                                                                       \
-    do {                                                                                                          \
-        spec = d - 1u < P && vrun + 1u >= P;                                                                      \
-        if (spec) pe = ldg_issue_here(p.ix.pref + (__funnelshift_r(hist, (uint32_t)qw, 2) >> (32 - 2 * P)));       \
-    } while (0)
-        KBO_K1_ISSUE_SPEC();
         while (bp < bp_end) {
             bool advance = true;
             if (iw & 1u) {
                 l = 0; r = n; d = 0;
-                vrun = ~0u;  // (+ 1 below: no base of the current run consumed yet)
             } else {
                 const uint32_t rowoff = ((uint32_t)qw & 3u) * p.ix.rank_stride;  // 32-bit word index
                 const uint32_t bl = l >> 5, br = r >> 5;
@@ -523,23 +485,13 @@ __global__ void __launch_bounds__(256, 5) ms_kernel(MsParams p) {
                     l = nl; r = nr;
                     d = d + 1 < k ? d + 1 : k;
                 } else if (d != 0) {
-                    bool resolved = false;
-                    if (spec) {  // the state after the last P bases, this one included
-                        resolved = pref_decode(pe, n, l, r, d);
-                        if (COUNT) {  // (counted with the contractions: one 32-byte sector each)
-                            ++cnt_con;
-                            if (bp >= bp_emit) ++cnt_con_e;
-                        }
-                    }
-                    if (!resolved) {
-                        // contract_left to the largest depth that changes the interval: t = max(LCS[l], LCS[r])
-                        advance = false;
-                        const uint32_t el = __ldg(p.ix.links + l), er = __ldg(p.ix.links + r);
-                        const bool scanned = ms_contract(p.ix, el, er, l, r, d);
-                        if (COUNT) {
-                            ++cnt_con; cnt_extra += scanned;
-                            if (bp >= bp_emit) { ++cnt_con_e; cnt_extra_e += scanned; }
-                        }
+                    // contract_left to the largest depth that changes the interval: t = max(LCS[l], LCS[r])
+                    advance = false;
+                    const uint32_t el = __ldg(p.ix.links + l), er = __ldg(p.ix.links + r);
+                    const bool scanned = ms_contract(p.ix, el, er, l, r, d);
+                    if (COUNT) {
+                        ++cnt_con; cnt_extra += scanned;
+                        if (bp >= bp_emit) { ++cnt_con_e; cnt_extra_e += scanned; }
                     }
                 }
             }
@@ -554,8 +506,6 @@ __global__ void __launch_bounds__(256, 5) ms_kernel(MsParams p) {
                     }
                 }
                 ++bp;
-                hist = __funnelshift_r(hist, (uint32_t)qw, 2);
-                vrun = vrun + 1u < 16u ? vrun + 1u : 16u;
                 qw >>= 2;
                 iw >>= 1;
                 if ((bp & 31) == 0 || bp == bp_end) {
@@ -571,9 +521,7 @@ __global__ void __launch_bounds__(256, 5) ms_kernel(MsParams p) {
                     }
                 }
             }
-            KBO_K1_ISSUE_SPEC();
         }
-#undef KBO_K1_ISSUE_SPEC
     }
     if (COUNT) {
         atomicAdd(p.counters + CNT_ATTEMPTS, cnt_att);

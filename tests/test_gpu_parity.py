@@ -250,8 +250,8 @@ def test_prefix_table_and_wide_intervals():
 
 @pytest.mark.parametrize("depth", [1, 5, 11, 12, 13, 14])
 def test_prefix_table_depths(depth):
-    """The prefix-state table at explicit depths (kbo_set_prefix_len): warm-up from it and one lookup per failed
-    extension at depth <= P.  (d, l, r), matches and find must not depend on the depth."""
+    """The prefix-state table at explicit depths (kbo_set_prefix_len; a chunk's warm-up starts from its entry).
+    (d, l, r) and matches must not depend on the depth."""
     ref = rand_seq(120_000, 21)
     asm = synth.mutate(np.frombuffer(ref, dtype=np.uint8), 22).tobytes()
     o = O.OracleIndex([asm], k=31)
@@ -273,28 +273,6 @@ def test_prefix_table_depths(depth):
     got = api.matches_batch(long_q, ix)
     for i, qq in enumerate(long_q):
         assert got[i] == o.matches(qq), i
-
-
-def test_prefix_table_deepens_once_the_index_serves_batches():
-    """Automatic depth: 10 at construction; after 4 M bases of batch queries the index gets the table of depth
-    ceil(log4 n) + 1 (here 10 -> 11 for 4^9 < n <= 4^10 nodes), built once, and results stay identical."""
-    ref = rand_seq(600_000, 25)
-    asm = synth.mutate(np.frombuffer(ref, dtype=np.uint8), 26).tobytes()
-    o = O.OracleIndex([asm], k=31)
-    ix = api.build([asm], api.BuildOpts(k=31))
-    bytes0 = ix.device_bytes
-    genes = [ref[s:s + 1000] for s in range(0, 590_000, 997)]
-    want = [o.matches(q) for q in genes[:40]]
-    assert api.matches_batch(genes[:40], ix) == want
-    for _ in range(9):  # 9 x 0.59 M bases
-        api.matches_batch(genes, ix)
-    assert ix.device_bytes == bytes0 + 8 * 4 ** 11
-    assert api.matches_batch(genes[:40], ix) == want
-    d, l, r, off = api.query_sbwt_batch(genes[:5], ix)
-    for i in range(5):
-        od, ol, orr = o.query_sbwt(genes[i])
-        a, b_ = int(off[i]), int(off[i + 1])
-        assert np.array_equal(d[a:b_].astype(np.uint64), od) and np.array_equal(l[a:b_].astype(np.uint64), ol)
 
 
 def test_ms_invariants_large():

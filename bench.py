@@ -63,6 +63,7 @@ def parse_args():
     ap.add_argument("--queries", type=int, default=0)
     ap.add_argument("--query-len", type=int, default=0)
     ap.add_argument("--assemblies", type=int, default=16, help="configs 3 / 4: assemblies per rank")
+    ap.add_argument("--asm-reps", type=int, default=3, help="configs 3 / 4: repetitions of every timed region (the fastest counts)")
     ap.add_argument("--asm-threads", type=int, default=4,
                     help="configs 3 / 4: host threads per rank, each taking whole assemblies (kbo-cli style)")
     ap.add_argument("--k", type=int, default=31, help="configs 3 / 4: k of the indexes (k > 32 takes the host builder; the "
@@ -635,12 +636,20 @@ def run_assemblies(args, rank, local_rank, world):
     for i in range(2):  # warm-up (allocator pools, pinned staging)
         one(n_asm + i)
     region(n_thr)  # (and once with the timed region's concurrency: every thread's workspaces exist afterwards)
-    total_s, (build_s, run_s, free_s), first = region(n_thr)
+
+    def best_of(reps, *a):
+        """The region `reps` times, the fastest kept: the per-assembly host work (ctypes calls, numpy buffers, the staging
+        copies) is exposed to whatever else runs on the box's CPUs, and single regions varied up to 5x between boxes."""
+        runs = [region(*a) for _ in range(reps)]
+        return min(runs, key=lambda r: r[0])
+
+    reps = max(1, args.asm_reps)
+    total_s, (build_s, run_s, free_s), first = best_of(reps, n_thr)
     value = world * n_asm * len(ref) / total_s
-    one_s, (build1, run1, free1), first1 = region(1) if n_thr > 1 else (total_s, (build_s, run_s, free_s), first)
+    one_s, (build1, run1, free1), first1 = best_of(reps, 1) if n_thr > 1 else (total_s, (build_s, run_s, free_s), first)
     # the index of the reference built once and passed in (kbo_call_with_ref / kbo_map_with_ref) instead of per call
     ref_ix = api.build([ref], bo, device=dev)
-    reuse_s, _, first_reuse = region(n_thr, ref_ix)
+    reuse_s, _, first_reuse = best_of(reps, n_thr, ref_ix)
     ref_ix.close()
     if first1[1] != first[1] or first_reuse[1] != first[1]:
         raise SystemExit("bench.py: kbo::%s results differ between the timed regions" % name)
@@ -665,6 +674,7 @@ def run_assemblies(args, rank, local_rank, world):
                   "oracle_bases_per_s": len(ref) / cpu_s}
         line = {"metric": "query bases/s (kbo %s, whole box)" % name, "value": value, "unit": "query bases/s",
                 "n_gpus": world, "steps": n_asm, "warmup": 2 + n_asm, "ms_per_step": 1e3 * total_s / n_asm,
+                "timing": "fastest of %d repetitions of the %d-assembly region (wall clock, max over ranks)" % (reps, n_asm),
                 "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "u8", "data": "synthetic",
                 "config": {"workload": "kbo::%s of %d mutated %d bp synthetic assemblies per rank (1%% SNPs + short indels) "
                                        "against one reference, k=%d, default options (BASELINE.json configs[%d])"

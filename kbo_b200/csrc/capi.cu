@@ -174,6 +174,9 @@ struct kbo_index {
     std::atomic<bool> host_ready{true};
     std::mutex host_mu;
     std::atomic<bool> rank2_ready{false};  // the rank2 rows are computed when a kernel that probes pairs first runs
+    // arrays of an index made by the GPU builder come from the device's stream-ordered pool (kept warm): kbo::call /
+    // kbo::map build and free an index per assembly, and cudaMalloc / cudaFree cost them 3-5 ms each time
+    bool pool_alloc = false;
     uint64_t blob_bytes = 0;
     float l2_hit_ratio = 0.f;     // 0: no persisting-L2 window available
     uint64_t rank_stride = 0;
@@ -212,7 +215,8 @@ static int alloc_index_arrays(kbo_index* ix, uint64_t rank_words, uint64_t lcs_b
     const uint64_t rank2_bytes = with_rank2 && g_rank2.load() ? 4 * rank_bytes : 0;  // 16 rows instead of 4
     const uint64_t links_bytes = ((n + 1) * 4 + 255) & ~255ull;
     ix->blob_bytes = rank_bytes + rank2_bytes + links_bytes + lcs_bytes;
-    CUDA_TRY(cudaMalloc((void**)&ix->d_blob, ix->blob_bytes));
+    if (ix->pool_alloc) CUDA_TRY(cudaMallocAsync((void**)&ix->d_blob, ix->blob_bytes, 0));
+    else CUDA_TRY(cudaMalloc((void**)&ix->d_blob, ix->blob_bytes));
     ix->d_rank = reinterpret_cast<uint64_t*>(ix->d_blob);
     ix->d_rank2 = rank2_bytes ? reinterpret_cast<uint64_t*>(ix->d_blob + rank_bytes) : nullptr;
     ix->d_links = reinterpret_cast<uint32_t*>(ix->d_blob + rank_bytes + rank2_bytes);
@@ -417,12 +421,14 @@ static int build_rank2(kbo_index* ix) {
 }
 
 // The states after 1, 2, ... P bases, level by level (prefix_table_level_kernel); level P stays in *out.
-static int build_pref_table(const IndexView& view, uint32_t P, uint64_t** out) {
+static int build_pref_table(const IndexView& view, uint32_t P, uint64_t** out, bool pool) {
     const size_t last = (size_t)1 << (2 * P);
     uint64_t *a = nullptr, *b = nullptr;  // level j lives in b when P - j is even (so level P does), else in a
-    CUDA_TRY(cudaMalloc((void**)&a, std::max<size_t>(last / 4, 4) * 8));
-    if (cudaMalloc((void**)&b, last * 8) != cudaSuccess) {
-        cudaFree(a);
+    auto alloc = [&](uint64_t** p, size_t bytes) { return pool ? cudaMallocAsync((void**)p, bytes, 0) : cudaMalloc((void**)p, bytes); };
+    auto release = [&](uint64_t* p) { if (pool) cudaFreeAsync(p, 0); else cudaFree(p); };
+    CUDA_TRY(alloc(&a, std::max<size_t>(last / 4, 4) * 8));
+    if (alloc(&b, last * 8) != cudaSuccess) {
+        release(a);
         cudaGetLastError();
         return fail(KBO_ERR_OOM, "prefix-state table: out of device memory");
     }
@@ -435,9 +441,9 @@ static int build_pref_table(const IndexView& view, uint32_t P, uint64_t** out) {
     }
     cudaError_t e = cudaGetLastError();
     if (e == cudaSuccess) e = cudaDeviceSynchronize();
-    cudaFree(a);
+    release(a);
     if (e != cudaSuccess) {
-        cudaFree(b);
+        release(b);
         return fail(KBO_ERR_CUDA, std::string("CUDA error: ") + cudaGetErrorString(e) + " in the prefix-state table");
     }
     *out = b;
@@ -467,11 +473,14 @@ static int build_links(kbo_index* ix, uint64_t n, bool with_prefix_table = true)
         const int want = g_prefix_len.load();
         const uint32_t P = std::min<uint32_t>(want > 0 ? (uint32_t)want : (uint32_t)PREF_LEN,
                                               std::min<uint32_t>(PREF_MAX_LEN, ix->view.k - 1));
-        const int rc = build_pref_table(ix->view, P, &ix->d_pref);
+        const int rc = build_pref_table(ix->view, P, &ix->d_pref, ix->pool_alloc);
         if (rc) return rc;
         ix->view.pref = ix->d_pref;
         ix->view.pref_len = P;
         ix->device_bytes += ((uint64_t)8 << (2 * P));
+    } else {
+        // the construction ran on the legacy default stream; queries run on non-blocking streams of their own
+        CUDA_TRY(cudaStreamSynchronize(0));
     }
     return KBO_OK;
 }
@@ -706,9 +715,10 @@ static int build_index_gpu_typed(kbo_index* ix, const uint8_t* const* seqs, cons
     CUDA_TRY(tmp.alloc(&d_Dlen, nD));
     CUDA_TRY(cudaMemcpy(d_Dkey, h_Dkey.data(), nD * sizeof(K), cudaMemcpyHostToDevice));
     CUDA_TRY(cudaMemcpy(d_Dlen, h_Dlen.data(), nD, cudaMemcpyHostToDevice));
+    ix->pool_alloc = true;
     if (keep_nodes && !device_only) {  // "select support": the sorted nodes stay on the device with the index
-        CUDA_TRY(cudaMalloc((void**)&ix->d_node_keys, (n ? n : 1) * sizeof(K)));
-        CUDA_TRY(cudaMalloc((void**)&ix->d_node_len, n ? n : 1));
+        CUDA_TRY(cudaMallocAsync((void**)&ix->d_node_keys, (n ? n : 1) * sizeof(K), 0));
+        CUDA_TRY(cudaMallocAsync((void**)&ix->d_node_len, n ? n : 1, 0));
         ix->node_key_words = sizeof(K) / 8;
         d_Pkey = reinterpret_cast<K*>(ix->d_node_keys);
         d_Plen = ix->d_node_len;
@@ -1302,10 +1312,15 @@ void kbo_index_free(kbo_index* ix) {
         // (idle pooled workspaces belong to the device, not to this index: they stay for the next index)
         for (auto& kv : ix->by_stream) { kv.second->destroy(); delete kv.second; }
         for (PinnedBuf& pb : ix->pinned_pool) if (pb.p) cudaFreeHost(pb.p);
-        if (ix->d_blob) cudaFree(ix->d_blob);
-        if (ix->d_pref) cudaFree(ix->d_pref);
-        if (ix->d_node_keys) cudaFree(ix->d_node_keys);
-        if (ix->d_node_len) cudaFree(ix->d_node_len);
+        // pool memory goes back stream-ordered unless stream-ordered (_device) calls on caller streams may still be
+        // running (cudaFree waits for them; it accepts pool memory as well)
+        const bool async_free = ix->pool_alloc && ix->by_stream.empty();
+        void* arrays[] = {ix->d_blob, ix->d_pref, ix->d_node_keys, ix->d_node_len};
+        for (void* p : arrays) {
+            if (!p) continue;
+            if (async_free) cudaFreeAsync(p, 0);
+            else cudaFree(p);
+        }
         bt.lap("index free");
     }
     delete ix;

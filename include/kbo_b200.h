@@ -288,7 +288,9 @@ int kbo_set_rank2(int enabled);
 int kbo_set_l2_persist(int enabled);
 /* Experiment switches.  bit 1 (2): run K2 where the bit-parallel K2b would be picked; bit 4 (16): run matching
  * statistics + derandomize + translate as ONE fused kernel (fused.cuh: MS bytes only in shared memory, two bases per
- * rank probe) instead of K1 followed by K2b; bit 2 (4): the fused kernel probes one base at a time.  Results never
+ * rank probe, mismatch stretches in a second pass) instead of K1 followed by K2b; bit 2 (4): the fused kernel probes
+ * one base at a time; bit 3 (8, with bit 4): the fused kernel in its one-pass form (K1's own recurrence, then
+ * derandomize + translate on the shared-memory MS bytes); bit 5 (32): K1 with two bases per probe.  Results never
  * depend on them. */
 int kbo_set_ms_flags(uint32_t flags);
 /* Number of kernel launches issued by this library since load (for bench.py's gpu_launches). */

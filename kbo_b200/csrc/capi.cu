@@ -1044,7 +1044,7 @@ static int device_sm_count(int device) {
     return n;
 }
 
-template <bool CHARS, bool COUNT>
+template <bool CHARS, bool COUNT, bool EXACT>
 static cudaError_t launch_fused(const FusedParams& fp, const FusedGeom& fg, cudaStream_t st) {
     static std::mutex mu;
     static std::vector<int> configured;  // devices on which this instantiation may use > 48 KB of dynamic shared memory
@@ -1053,12 +1053,12 @@ static cudaError_t launch_fused(const FusedParams& fp, const FusedGeom& fg, cuda
     {
         std::lock_guard<std::mutex> lk(mu);
         if (std::find(configured.begin(), configured.end(), dev) == configured.end()) {
-            cudaError_t e = cudaFuncSetAttribute(ms_fused_kernel<CHARS, COUNT>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
+            cudaError_t e = cudaFuncSetAttribute(ms_fused_kernel<CHARS, COUNT, EXACT>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
             if (e != cudaSuccess) return e;
             configured.push_back(dev);
         }
     }
-    ms_fused_kernel<CHARS, COUNT><<<(unsigned)fg.n_tiles, FUSED_THREADS, fg.smem.total, st>>>(fp);
+    ms_fused_kernel<CHARS, COUNT, EXACT><<<(unsigned)fg.n_tiles, FUSED_THREADS, fg.smem.total, st>>>(fp);
     return cudaGetLastError();
 }
 
@@ -1068,14 +1068,18 @@ static int run_fused(kbo_index* ix, Workspace* ws, const QueryView& qv, const Ge
                      uint64_t off0, bool want_masks, bool* done) {
     *done = false;
     const uint32_t flags = tuned_ms_flags(ix);
-    // bit 4 selects the fused kernel.  It is NOT the default: measured on B200 (profiles/README.md, round 2) it takes
-    // 225-300 us per 10^7-base batch where K1 + K2b take 112 + 18 us -- the per-iteration latency of a dependent chain
-    // (~1 us at this occupancy) is the same in both, and the two-pass scheme does not save enough iterations.
+    // bit 4 selects the fused kernel.  It is NOT the default: measured on B200 (profiles/README.md, round 2) its two-pass
+    // form takes 225-300 us per 10^7-base batch where K1 + K2b take 112 + 18 us; its one-pass form (bit 3: K1's
+    // recurrence in pass A) takes 119 us and wins for a lone stream (63 vs 60 G bases/s) but loses when independent
+    // batches overlap on several streams (78 vs 97 G), which is how the library is fastest.
     if (!k2b_supported(ix->host.k, thr) || (flags & 2u) || !(flags & 16u)) return KBO_OK;
     FusedGeom fg;
-    if (!fused_geometry(g.Lp, ix->host.k, !want_masks, device_sm_count(ix->device), tuned_chunk_len(ix), &fg)) return KBO_OK;
+    const bool exact = (flags & FUSED_FLAG_EXACT) != 0;  // bit 3: the one-pass form (K1's recurrence + K2b in one kernel)
+    // (positions per lane stay at ~64 also when calls overlap: with K1's longer chunks for overlapping calls the one-pass
+    // form fell from 78 to 64 G bases/s on six streams -- a block waits for the slowest of its 128 lanes before pass C)
+    if (!fused_geometry(g.Lp, ix->host.k, !want_masks, device_sm_count(ix->device), tuned_chunk_len(ix), &fg, exact)) return KBO_OK;
     cudaStream_t st = ws->stream;
-    if (!(flags & 4u)) { const int rc = ensure_rank2(ix); if (rc) return rc; }  // (bit 2: one base per probe)
+    if (!exact && !(flags & 4u)) { const int rc = ensure_rank2(ix); if (rc) return rc; }  // (bit 2: one base per probe)
     FusedParams fp;
     std::memset(&fp, 0, sizeof(fp));
     fp.ix = ix->view;
@@ -1106,8 +1110,13 @@ static int run_fused(kbo_index* ix, Workspace* ws, const QueryView& qv, const Ge
         fp.counters = ws->counters.as<unsigned long long>();
     }
     cudaError_t e;
-    if (want_masks) e = count ? launch_fused<false, true>(fp, fg, st) : launch_fused<false, false>(fp, fg, st);
-    else e = count ? launch_fused<true, true>(fp, fg, st) : launch_fused<true, false>(fp, fg, st);
+    if (exact) {
+        if (want_masks) e = count ? launch_fused<false, true, true>(fp, fg, st) : launch_fused<false, false, true>(fp, fg, st);
+        else e = count ? launch_fused<true, true, true>(fp, fg, st) : launch_fused<true, false, true>(fp, fg, st);
+    } else {
+        if (want_masks) e = count ? launch_fused<false, true, false>(fp, fg, st) : launch_fused<false, false, false>(fp, fg, st);
+        else e = count ? launch_fused<true, true, false>(fp, fg, st) : launch_fused<true, false, false>(fp, fg, st);
+    }
     LAUNCHED();
     CUDA_TRY(e);
     *done = true;
@@ -2907,7 +2916,7 @@ int kbo_set_prefix_len(uint32_t len) { g_prefix_len = (int)std::min<uint32_t>(le
 int kbo_set_rank2(int enabled) { g_rank2 = enabled ? 1 : 0; return KBO_OK; }
 int kbo_set_l2_persist(int enabled) { g_l2_persist = enabled ? 1 : 0; return KBO_OK; }
 int kbo_set_ms_flags(uint32_t flags) {
-    g_ms_flags = flags & 0xffu;  // bit 1: K2 instead of K2b; bit 2: fused kernel without rank2 pairs; bit 4: fused K1+K2b kernel
+    g_ms_flags = flags & 0xffu;  // bit 1: K2 instead of K2b; bit 2: fused kernel without rank2 pairs; bit 3: its one-pass form; bit 4: fused K1+K2b kernel
     const uint32_t blk = (flags >> 8) & 0x3ffu;  // bits 8..17: K1 block size (experiment)
     if (blk == 128 || blk == 256) g_ms_block = blk;
     return KBO_OK;

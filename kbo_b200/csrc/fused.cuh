@@ -48,6 +48,9 @@ namespace kbo_b200 {
 
 enum { FUSED_THREADS = 128, FUSED_WARPS = 4, MS_LOOKAHEAD = 72, FUSED_STAGE_CHARS = K2B_TILE + 16 };
 enum { FUSED_FLAG_NO_PAIRS = 4 };  // kbo_set_ms_flags bit 2: one base per probe in the fast pass (comparison runs)
+// kbo_set_ms_flags bit 3 (together with bit 4): the ONE-PASS form -- pass A is K1's exact recurrence (one base per probe,
+// contraction on the link array in the same iteration), there are no tasks and no pass B; staging and pass C as above.
+enum { FUSED_FLAG_EXACT = 8 };
 
 struct FusedParams {
     IndexView ix;
@@ -74,7 +77,7 @@ __host__ __device__ inline FusedSmem fused_smem_layout(uint32_t tile_len, uint32
     s.off_pack = o;  o += ((stage_words * 8u) + 15u) & ~15u;
     s.off_inv = o;   o += ((stage_words * 4u) + 15u) & ~15u;
     s.off_ms = o;    o += (16u + tile_len + MS_LOOKAHEAD + 16u + 15u) & ~15u;
-    s.off_warm = o;  o += FUSED_THREADS * fused_warm_row(k);  // provisional MS of every lane's warm-up positions
+    s.off_warm = o;  o += task_cap ? FUSED_THREADS * fused_warm_row(k) : 0u;  // provisional MS of every lane's warm-up positions
     s.off_tasks = o; o += task_cap * 16u;
     s.off_misc = o;  o += 64u;   // mbarrier (8), task count, tail state
     s.off_ring = o;  o += FUSED_WARPS * 64u;
@@ -93,7 +96,8 @@ struct FusedGeom {
     uint64_t n_tiles = 0;
     FusedSmem smem;
 };
-inline bool fused_geometry(uint64_t Lp, uint32_t k, bool chars, int n_sms, uint32_t target, FusedGeom* out) {
+inline bool fused_geometry(uint64_t Lp, uint32_t k, bool chars, int n_sms, uint32_t target, FusedGeom* out,
+                           bool exact = false) {
     FusedGeom g;
     if (!target) {
         const uint64_t t = Lp / ((uint64_t)n_sms * 2048ull * 4ull);
@@ -109,7 +113,7 @@ inline bool fused_geometry(uint64_t Lp, uint32_t k, bool chars, int n_sms, uint3
     g.n_tiles = (Lp + tile_len - 1) / tile_len;
     g.chunk = (g.tile_len + MS_LOOKAHEAD + FUSED_THREADS - 1) / FUSED_THREADS;
     g.stage_words = (g.tile_len + MS_LOOKAHEAD + 31) / 32 + ((k + 30) >> 5) + 8;
-    g.task_cap = FUSED_THREADS * ((g.chunk + 2 * (k - 1)) / k + 2);  // a new task at most every k positions of a lane's feed
+    g.task_cap = exact ? 0u : FUSED_THREADS * ((g.chunk + 2 * (k - 1)) / k + 2);  // a new task at most every k positions of a lane's feed
     g.smem = fused_smem_layout(g.tile_len, g.stage_words, g.task_cap, k, chars);
     if (g.smem.total > 200 * 1024) return false;
     *out = g;
@@ -151,7 +155,7 @@ __device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
 #define KBO_GRID_CONSTANT
 #endif
 
-template <bool CHARS, bool COUNT>
+template <bool CHARS, bool COUNT, bool EXACT = false>
 __global__ void __launch_bounds__(FUSED_THREADS, 8) ms_fused_kernel(const KBO_GRID_CONSTANT FusedParams p) {
     KBO_DYN_SMEM(smem);
     const FusedSmem lay = fused_smem_layout(p.tile_len, p.stage_words, p.task_cap, p.ix.k, CHARS);
@@ -213,8 +217,85 @@ __global__ void __launch_bounds__(FUSED_THREADS, 8) ms_fused_kernel(const KBO_GR
     const bool pairs = p.ix.rank2 != nullptr && !(p.flags & FUSED_FLAG_NO_PAIRS);
     const uint32_t stride = p.ix.rank_stride;
 
+    // ---- A (one-pass form). the exact recurrence, as K1 -------------------------------------------------------------
+    if (EXACT) {
+        const uint32_t a = rel_tile + tid * p.chunk;
+        if (a < rel_V) {
+            const uint32_t b = a + p.chunk < rel_V ? a + p.chunk : rel_V;
+            const uint64_t a64 = tile_start + (uint64_t)tid * p.chunk;
+            uint32_t warm = a64 >= (uint64_t)(k - 1) ? k - 1 : (uint32_t)a64;
+            if (warm) {  // cut after the last non-ACGT position of the window
+                const uint32_t lo = a - warm;
+                for (int32_t w = (int32_t)((a - 1) >> 5); w >= (int32_t)(lo >> 5); --w) {
+                    uint32_t iv = inv_s[w];
+                    if ((uint32_t)w == ((a - 1) >> 5) && (a & 31u)) iv &= (1u << (a & 31u)) - 1u;
+                    if ((uint32_t)w == (lo >> 5)) iv &= ~0u << (lo & 31u);
+                    if (iv) {
+                        warm = a - ((uint32_t)w * 32u + (31u - (uint32_t)__clz((int)iv)) + 1u);
+                        break;
+                    }
+                }
+            }
+            uint32_t l = 0, r = n, d = 0;
+            const uint32_t P = p.ix.pref ? p.ix.pref_len : 0u;
+            if (P && warm >= P) {
+                const uint32_t first = a - warm;
+                const uint32_t sh = 2u * (first & 31u);
+                uint64_t bits = pack_s[first >> 5] >> sh;
+                if (sh > 64 - 2 * P) bits |= pack_s[(first >> 5) + 1] << (64 - sh);
+                if (pref_decode(__ldg(p.ix.pref + ((uint32_t)bits & ((1u << (2 * P)) - 1u))), n, l, r, d)) warm -= P;
+            }
+            uint32_t bp = a - warm;
+            if (tid == 0) ms_s[15] = (uint8_t)d;  // MS of the position before the tile (overwritten when it is stepped through)
+            uint64_t qw = pack_s[bp >> 5] >> (2u * (bp & 31u));
+            uint32_t iw = inv_s[bp >> 5] >> (bp & 31u);
+            while (bp < b) {
+                bool advance = true;
+                if (iw & 1u) {
+                    l = 0; r = n; d = 0;
+                } else {
+                    const uint32_t rowoff = ((uint32_t)qw & 3u) * stride;
+                    const uint32_t bl = l >> 5, br = r >> 5;
+                    const uint64_t wl = __ldg(p.ix.rank + (rowoff + bl));
+                    const uint64_t wr = (br == bl) ? wl : __ldg(p.ix.rank + (rowoff + br));
+                    const uint32_t nl = (uint32_t)(wl >> 32) + __popc((uint32_t)wl & ((1u << (l & 31)) - 1u));
+                    const uint32_t nr = (uint32_t)(wr >> 32) + __popc((uint32_t)wr & ((1u << (r & 31)) - 1u));
+                    if (COUNT) {
+                        const bool sp = (bl >> 2) != (br >> 2);
+                        ++cnt_att; cnt_split += sp;
+                        if (bp >= a && bp < rel_end) { ++cnt_att_e; cnt_split_e += sp; }
+                    }
+                    if (nl < nr) {
+                        l = nl; r = nr;
+                        d = d + 1 < k ? d + 1 : k;
+                    } else if (d != 0) {
+                        advance = false;
+                        const uint32_t el = __ldg(p.ix.links + l), er = __ldg(p.ix.links + r);
+                        const bool scanned = ms_contract(p.ix, el, er, l, r, d);
+                        if (COUNT) {
+                            ++cnt_con; cnt_extra += scanned;
+                            if (bp >= a && bp < rel_end) { ++cnt_con_e; cnt_extra_e += scanned; }
+                        }
+                    }
+                }
+                if (advance) {
+                    if (COUNT) { ++cnt_proc; cnt_emit += (bp >= a && bp < rel_end); }
+                    if (bp >= a) msb[bp] = (uint8_t)d;
+                    else if (tid == 0 && bp + 1 == a) ms_s[15] = (uint8_t)d;
+                    ++bp;
+                    qw >>= 2;
+                    iw >>= 1;
+                    if ((bp & 31u) == 0 && bp < b) {
+                        qw = pack_s[bp >> 5];
+                        iw = inv_s[bp >> 5];
+                    }
+                }
+            }
+            if (b == rel_V) { misc[1] = l; misc[2] = r; misc[3] = d; }  // exact state after the last MS position (pass C's tail)
+        }
+    }
     // ---- A. fast pass ---------------------------------------------------------------------------------------------
-    {
+    if (!EXACT) {
         const uint32_t a = rel_tile + tid * p.chunk;
         if (a < rel_V) {
             const uint32_t b = a + p.chunk < rel_V ? a + p.chunk : rel_V;
@@ -342,7 +423,7 @@ __global__ void __launch_bounds__(FUSED_THREADS, 8) ms_fused_kernel(const KBO_GR
     // The link words of the current interval are therefore loaded TOGETHER with the rank words of every probe, so a
     // failed probe costs no second round trip before the contraction (the extra sector is wasted when the probe
     // succeeds, which is the rarer case here).  The first probe of a task is known to fail (the fast pass saw it).
-    {
+    if (!EXACT) {
         const uint32_t n_tasks = misc[0] < p.task_cap ? misc[0] : p.task_cap;  // (the capacity is a proven bound)
         for (uint32_t t = tid; t < n_tasks; t += FUSED_THREADS) {
             const uint4 T = tasks[t];

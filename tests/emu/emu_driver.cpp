@@ -183,7 +183,8 @@ static bool emu_run_fused(EmuIndex* e, const uint8_t* concat, const uint64_t* of
     s->g = make_geometry(total, nq, 0);
     const Geometry& g = s->g;
     FusedGeom fg;
-    if (!fused_geometry(g.Lp, e->host.k, chars_out != nullptr, g_emu_sms, g_emu_fused_chunk, &fg)) return false;
+    const bool exact = (g_emu_flags & FUSED_FLAG_EXACT) != 0;
+    if (!fused_geometry(g.Lp, e->host.k, chars_out != nullptr, g_emu_sms, g_emu_fused_chunk, &fg, exact)) return false;
     s->pack.assign(g.n_words, 0xdeadbeefdeadbeefull);
     s->inv.assign(g.n_words, 0xdeadbeef);
     s->sep.assign(g.n_words, 0xdeadbeef);
@@ -204,8 +205,13 @@ static bool emu_run_fused(EmuIndex* e, const uint8_t* concat, const uint64_t* of
     ++g_emu_fused_launches;
     g_emu_fused_tiles += fg.n_tiles;
     emu_launch_par((unsigned)fg.n_tiles, FUSED_THREADS, [&]() {
-        if (chars_out) { if (counters) ms_fused_kernel<true, true>(fp); else ms_fused_kernel<true, false>(fp); }
-        else { if (counters) ms_fused_kernel<false, true>(fp); else ms_fused_kernel<false, false>(fp); }
+        if (exact) {
+            if (chars_out) { if (counters) ms_fused_kernel<true, true, true>(fp); else ms_fused_kernel<true, false, true>(fp); }
+            else { if (counters) ms_fused_kernel<false, true, true>(fp); else ms_fused_kernel<false, false, true>(fp); }
+        } else {
+            if (chars_out) { if (counters) ms_fused_kernel<true, true>(fp); else ms_fused_kernel<true, false>(fp); }
+            else { if (counters) ms_fused_kernel<false, true>(fp); else ms_fused_kernel<false, false>(fp); }
+        }
     });
     return true;
 }

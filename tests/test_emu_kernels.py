@@ -210,11 +210,13 @@ def test_ms_tiny_index_and_counters():
 
 
 # -------------------------------------------------- K2: derandomize+translate ---
-@pytest.fixture(autouse=True, params=["dispatch", "k2-only", "fused", "fused-small-chunks"])
+@pytest.fixture(autouse=True, params=["dispatch", "k2-only", "fused", "fused-small-chunks", "fused-exact",
+                                     "fused-exact-small-chunks"])
 def k2_mode(request):
     """Tests that reach derandomize+translate run several times: product dispatch of the separate kernels (K2b where it
-    applies), K2 alone, and the fused K1 + K2b kernel (fused.cuh) with the default and with a tiny lane chunk (many
-    tiles, tasks that span lanes' whole chunks, look-ahead past the shared-memory tile)."""
+    applies), K2 alone, and the fused K1 + K2b kernel (fused.cuh) -- its two-pass form and its one-pass form ("exact":
+    K1's recurrence in pass A, no repair pass) -- with the default and with a tiny lane chunk (many tiles, tasks that span
+    lanes' whole chunks, look-ahead past the shared-memory tile)."""
     name = request.node.originalname or request.node.name  # the function name, without the parameter ids
     touches_k2 = any(t in name for t in ("k2", "matches", "map", "call", "find", "rle"))
     touches_fused = any(t in name for t in ("matches", "find")) and "rle_kernel" not in name
@@ -223,10 +225,12 @@ def k2_mode(request):
     if request.param.startswith("fused") and not touches_fused:
         pytest.skip("does not reach the fused kernel")
     E.set_k2_mode(1 if request.param == "k2-only" else 0)
-    E.set_fused(request.param.startswith("fused"), 9 if request.param == "fused-small-chunks" else 0, 3)
+    E.set_fused(request.param.startswith("fused"), 9 if request.param.endswith("small-chunks") else 0, 3)
+    E.lib().emu_set_ms_flags(8 if "exact" in request.param else 0)  # bit 3: the one-pass form of the fused kernel
     yield
     E.set_k2_mode(0)
     E.set_fused(False)
+    E.lib().emu_set_ms_flags(0)
 
 
 def valid_ms_vector(rng, n, k, thr):

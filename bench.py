@@ -63,6 +63,7 @@ def parse_args():
     ap.add_argument("--queries", type=int, default=0)
     ap.add_argument("--query-len", type=int, default=0)
     ap.add_argument("--assemblies", type=int, default=16, help="configs 3 / 4: assemblies per rank")
+    ap.add_argument("--blocking-sync", type=int, default=0, help="configs 3 / 4: 1 = host threads sleep while they wait for the GPU")
     ap.add_argument("--asm-reps", type=int, default=3, help="configs 3 / 4: repetitions of every timed region (the fastest counts)")
     ap.add_argument("--asm-threads", type=int, default=4,
                     help="configs 3 / 4: host threads per rank, each taking whole assemblies (kbo-cli style)")
@@ -575,6 +576,16 @@ def run_assemblies(args, rank, local_rank, world):
     api.load_library()
     dev = local_rank
     torch.cuda.set_device(dev)
+    sync_note = "spin (CUDA default)"
+    if args.blocking_sync:
+        # host threads that wait for the GPU sleep instead of spinning: with several worker threads per rank and
+        # 8 ranks on a 32-core box the spinning waiters take the cores the other workers' host work needs
+        import ctypes
+        try:
+            rc = ctypes.CDLL("libcudart.so.12").cudaSetDeviceFlags(4)  # cudaDeviceScheduleBlockingSync
+            sync_note = "blocking (cudaDeviceScheduleBlockingSync, rc %d)" % rc
+        except OSError as ex:
+            sync_note = "spin (libcudart not found: %s)" % ex
     dist = None
     if world > 1:
         import torch.distributed as dist
@@ -680,7 +691,7 @@ def run_assemblies(args, rank, local_rank, world):
                                        "against one reference, k=%d, default options (BASELINE.json configs[%d])"
                                        % (name, n_asm, args.ref_len, kk, args.config - 1),
                            "assemblies_per_rank": n_asm, "ref_len": args.ref_len, "k": kk},
-                "impl_detail": {"host_threads": n_thr,
+                "impl_detail": {"host_threads": n_thr, "host_waits": sync_note,
                                 "one_host_thread": {"value": world * n_asm * len(ref) / one_s, "ms_per_assembly": 1e3 * one_s / n_asm,
                                                     "split_ms_per_assembly": {
                                                         "assembly_index_build (GPU builder incl. copy-in)": 1e3 * build1 / n_asm,

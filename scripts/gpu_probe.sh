@@ -1,11 +1,10 @@
-for i in 1 2; do
-python bench.py --config 4 > gpurun_out/p_c4_$i.json 2> gpurun_out/p_c4_$i.err; tail -c 200 gpurun_out/p_c4_$i.err
-done
-python bench.py --config 3 --k 51 > gpurun_out/p_c3_k51.json 2> gpurun_out/p_c3_k51.err
+python bench.py --config 4 > gpurun_out/r2g_c4.json 2> gpurun_out/r2g_c4.err; tail -c 200 gpurun_out/r2g_c4.err
+python bench.py --config 3 > gpurun_out/r2g_c3.json 2> gpurun_out/r2g_c3.err; tail -c 200 gpurun_out/r2g_c3.err
 python - <<'PY'
 import json
-for f in ('p_c4_1', 'p_c4_2', 'p_c3_k51'):
+for f in ('r2g_c4', 'r2g_c3'):
     d = json.loads(open('gpurun_out/%s.json' % f).read().strip().split('\n')[-1]); i = d['impl_detail']
-    print(f, 'ms/asm', round(d['ms_per_step'], 1), '| one thread', round(i['one_host_thread']['ms_per_assembly'], 1), '| ref index once', round(i['reference_index_built_once']['ms_per_assembly'], 1))
+    print(f, 'ms/asm', round(d['ms_per_step'], 1), 'M bases/s', round(d['value']/1e6), '| one thread', round(i['one_host_thread']['ms_per_assembly'], 1),
+          {k[:20]: round(v, 1) for k, v in i['one_host_thread']['split_ms_per_assembly'].items()}, '| ref index once', round(i['reference_index_built_once']['ms_per_assembly'], 1))
 PY
-nproc; cat /proc/loadavg
+python -m pytest tests/test_gpu_parity.py -m gpu -x -q -k "map or call or golden or config1" 2>&1 | tail -2

@@ -101,6 +101,18 @@ def test_relative_to_ref_goldens(lib):
     assert api.relative_to_ref(b"TTGATTGGCTGGGCAGAGCTG", b"MMMM--MMMMMMMXMMMMMMM") == b"TTGA--GGCTGGG-AGAGCTG"
 
 
+def test_relative_to_ref_all_bytes_and_lengths(lib):
+    """format.rs:270-286 on every alignment byte value and on lengths around the 16-byte vector width."""
+    rng = np.random.default_rng(7)
+    for n in (1, 15, 16, 17, 31, 32, 33, 1000, 4099):
+        ref = rng.integers(0, 256, n, dtype=np.uint8)
+        aln = rng.integers(0, 256, n, dtype=np.uint8)
+        mix = rng.random(n) < 0.7
+        aln[mix] = rng.choice(np.frombuffer(b"MRIXD-ACGTN", dtype=np.uint8), int(mix.sum()))
+        want = bytes(r if a in b"MRI" else (ord("-") if a in b"XD-" else a) for r, a in zip(ref.tolist(), aln.tolist()))
+        assert api.relative_to_ref(ref.tobytes(), aln.tobytes()) == want, n
+
+
 def test_compute_fails_loudly_without_gpu(lib):
     if api.device_count() > 0:
         pytest.skip("a GPU is present")

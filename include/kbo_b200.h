@@ -58,7 +58,9 @@ typedef enum kbo_status {
     KBO_ERR_INDEX_TOO_LARGE = 10, /* n_sets >= 2^32 */
     KBO_ERR_BUFFER_TOO_SMALL = 11,/* caller capacity too small (count is still returned) */
     KBO_ERR_PANIC = 12,           /* the reference would panic on these inputs (index out of bounds etc.) */
-    KBO_ERR_BATCH_TOO_LARGE = 13  /* a device-resident batch of >= 2^32 - 2^20 positions (host-buffer calls split internally) */
+    KBO_ERR_BATCH_TOO_LARGE = 13, /* a device-resident batch of >= 2^32 - 2^20 positions (host-buffer calls split internally) */
+    KBO_ERR_IO = 14,              /* index.rs:137,148,202,207: the index file cannot be created / opened (the reference panics) */
+    KBO_ERR_FORMAT = 15           /* index.rs:204,209 .unwrap(): not an index file this library can read */
 } kbo_status;
 
 #define KBO_MAX_K 64 /* packed k-mers are two 64-bit words; reference tests use k <= 63 */
@@ -113,6 +115,17 @@ int kbo_index_device(const kbo_index* ix);
 uint64_t kbo_index_device_bytes(const kbo_index* ix);
 /* Read the index back in the kbo_index_from_parts format (for verification / serialization). */
 int kbo_index_export_parts(const kbo_index* ix, uint64_t* rows[4], uint8_t* lcs, uint64_t C_out[4]);
+/* index::serialize_sbwt (index.rs:128-153): writes `<outfile_prefix>.sbwt` and `<outfile_prefix>.lcs`.
+ * index::load_sbwt (index.rs:195-212): reads the pair back and uploads the index to `device`.
+ * `.sbwt` starts with the reference's variant header (u64 LE 12, "SubsetMatrix": index.rs:139-140).  What follows it
+ * in the reference is the serialisation of the un-vendored sbwt crate, pinned by nothing but a round trip
+ * (index.rs:277-296); here the body is this library's own layout (magic "KBOB200", version, k, n_sets, n_kmers, the
+ * four kbo_index_from_parts rows, FNV-1a checksum; `.lcs`: magic, version, k, n_sets, the LCS bytes, checksum; all
+ * little endian).  Files round-trip bit-exactly through this pair; a file written by kbo-cli / the sbwt crate is
+ * recognised by the missing magic and refused with KBO_ERR_FORMAT (never misread).  A loaded index behaves like one
+ * from kbo_index_from_parts (access_kmer walks the index). */
+int kbo_index_serialize(const kbo_index* ix, const char* outfile_prefix);
+int kbo_index_load(const char* index_prefix, int device, kbo_index** out);
 /* SbwtIndex::access_kmer (variant_calling.rs:276, gap_filling.rs:144): k bytes, '$' padded. */
 int kbo_index_access_kmer(const kbo_index* ix, uint64_t colex, uint8_t* out_k);
 /* SbwtIndex::search (gap_filling.rs:217): *found = 0 when the pattern does not occur. */

@@ -28,13 +28,14 @@ u8p, u32p, u64p, i64p = C.POINTER(C.c_uint8), C.POINTER(C.c_uint32), C.POINTER(C
 
 STATUS_NAMES = {0: "OK", 1: "EMPTY_INPUT", 2: "BAD_THRESHOLD", 3: "TOO_SHORT", 4: "BAD_K", 5: "K_MISMATCH",
                 6: "BAD_PROB", 7: "BAD_ARGUMENT", 8: "CUDA", 9: "OOM", 10: "INDEX_TOO_LARGE", 11: "BUFFER_TOO_SMALL",
-                12: "PANIC", 13: "BATCH_TOO_LARGE"}
+                12: "PANIC", 13: "BATCH_TOO_LARGE", 14: "IO", 15: "FORMAT"}
 
 # every symbol include/kbo_b200.h declares (tests check that the library exports all of them)
 EXPORTED_SYMBOLS = [
     "kbo_last_error_message", "kbo_device_count", "kbo_default_build_opts", "kbo_alloc_pinned", "kbo_free_pinned",
     "kbo_index_build", "kbo_index_from_parts", "kbo_index_free", "kbo_index_k", "kbo_index_n_kmers",
     "kbo_index_n_sets", "kbo_index_device", "kbo_index_device_bytes", "kbo_index_export_parts",
+    "kbo_index_serialize", "kbo_index_load",
     "kbo_index_access_kmer", "kbo_index_search", "kbo_query_sbwt", "kbo_query_sbwt_batch_compact",
     "kbo_log_rm_max_cdf", "kbo_random_match_threshold", "kbo_derandomize_ms_vec", "kbo_translate_ms_vec",
     "kbo_run_lengths_gapped", "kbo_relative_to_ref", "kbo_matches", "kbo_matches_batch", "kbo_matches_batch_device",
@@ -100,6 +101,8 @@ def load_library():
         getattr(L, f).restype = C.c_uint64
     L.kbo_index_device.argtypes = [C.c_void_p]
     L.kbo_index_export_parts.argtypes = [C.c_void_p, C.POINTER(u64p), u8p, u64p]
+    L.kbo_index_serialize.argtypes = [C.c_void_p, C.c_char_p]
+    L.kbo_index_load.argtypes = [C.c_char_p, C.c_int, C.POINTER(C.c_void_p)]
     L.kbo_index_access_kmer.argtypes = [C.c_void_p, C.c_uint64, u8p]
     L.kbo_index_search.argtypes = [C.c_void_p, u8p, C.c_uint64, C.POINTER(C.c_int), u64p, u64p]
     L.kbo_query_sbwt.argtypes = [C.c_void_p, u8p, C.c_uint64, u64p, u64p, u64p]
@@ -330,6 +333,18 @@ def index_from_parts(k, n_sets, n_kmers, rows, lcs, device=0):
     ptrs = (u64p * 4)(*[_p(r, C.c_uint64) for r in rows])
     h = C.c_void_p()
     _check(L.kbo_index_from_parts(k, n_sets, n_kmers, ptrs, _p(lcs, C.c_uint8), device, C.byref(h)))
+    return Index(h.value)
+
+
+def serialize_sbwt(outfile_prefix, index):
+    """index::serialize_sbwt (index.rs:128-153): writes `<prefix>.sbwt` and `<prefix>.lcs` (layout: include/kbo_b200.h)."""
+    _check(load_library().kbo_index_serialize(index._h, os.fsencode(outfile_prefix)))
+
+
+def load_sbwt(index_prefix, device=0):
+    """index::load_sbwt (index.rs:195-212): reads `<prefix>.sbwt` / `<prefix>.lcs` written by serialize_sbwt."""
+    h = C.c_void_p()
+    _check(load_library().kbo_index_load(os.fsencode(index_prefix), device, C.byref(h)))
     return Index(h.value)
 
 

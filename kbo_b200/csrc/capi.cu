@@ -1379,6 +1379,132 @@ int kbo_index_export_parts(const kbo_index* ix, uint64_t* rows[4], uint8_t* lcs,
     return KBO_OK;
 }
 
+// ---- index files: index::serialize_sbwt / index::load_sbwt (index.rs:128-212) --------------------------
+// The reference writes `<prefix>.sbwt` = u64 LE 12 + "SubsetMatrix" (index.rs:139-140) followed by the sbwt crate's own
+// serialisation of the index, and `<prefix>.lcs` = the crate's serialisation of the LCS array.  The crate (sbwt
+// 0.3.4) is not part of the reference tree and the reference pins the files only by a round trip (index.rs:277-296),
+// so the byte layout AFTER the variant header is this library's own (below) and a file written by kbo-cli is
+// recognised and refused (KBO_ERR_FORMAT) instead of being misread.
+//   .sbwt: u64 12, "SubsetMatrix", "KBOB200\0", u32 version (1), u32 k, u64 n_sets, u64 n_kmers,
+//          4 x ceil(n_sets/64) u64 words (the kbo_index_from_parts rows, A C G T), u64 FNV-1a of everything before
+//   .lcs:  "KBOB200\0", u32 version (1), u32 k, u64 n_sets, n_sets bytes, u64 FNV-1a of everything before
+// all little endian.
+namespace {
+const char IO_VARIANT[] = "SubsetMatrix";
+const char IO_MAGIC[8] = {'K', 'B', 'O', 'B', '2', '0', '0', '\0'};
+const uint32_t IO_VERSION = 1;
+struct IoFile {
+    FILE* f = nullptr;
+    uint64_t h = 1469598103934665603ull;  // FNV-1a 64
+    ~IoFile() { if (f) std::fclose(f); }
+    bool write(const void* p, size_t n) {
+        const uint8_t* b = (const uint8_t*)p;
+        for (size_t i = 0; i < n; ++i) { h ^= b[i]; h *= 1099511628211ull; }
+        return std::fwrite(p, 1, n, f) == n;
+    }
+    bool read(void* p, size_t n) {
+        if (std::fread(p, 1, n, f) != n) return false;
+        const uint8_t* b = (const uint8_t*)p;
+        for (size_t i = 0; i < n; ++i) { h ^= b[i]; h *= 1099511628211ull; }
+        return true;
+    }
+    bool put32(uint32_t v) { return write(&v, 4); }  // the host is little endian (x86-64 / aarch64)
+    bool put64(uint64_t v) { return write(&v, 8); }
+    bool get(uint32_t& v) { return read(&v, 4); }
+    bool get(uint64_t& v) { return read(&v, 8); }
+};
+}  // namespace
+
+int kbo_index_serialize(const kbo_index* ix, const char* outfile_prefix) {
+    if (!ix || !outfile_prefix) return fail(KBO_ERR_BAD_ARGUMENT, "null argument");
+    { const int rc = ensure_host_mirror(ix); if (rc) return rc; }
+    const HostIndex& h = ix->host;
+    const size_t nw = (size_t)(h.n_sets + 63) / 64;
+    const std::string sbwt_path = std::string(outfile_prefix) + ".sbwt", lcs_path = std::string(outfile_prefix) + ".lcs";
+    {
+        IoFile o;
+        o.f = std::fopen(sbwt_path.c_str(), "wb");
+        if (!o.f) return fail(KBO_ERR_IO, "Expected write access to " + sbwt_path);  // index.rs:137
+        bool ok = o.put64(sizeof(IO_VARIANT) - 1) && o.write(IO_VARIANT, sizeof(IO_VARIANT) - 1) &&
+                  o.write(IO_MAGIC, 8) && o.put32(IO_VERSION) && o.put32(h.k) &&
+                  o.put64(h.n_sets) && o.put64(h.n_kmers);
+        for (int c = 0; c < 4 && ok; ++c) ok = o.write(h.rows[c].data(), nw * 8);
+        const uint64_t sum = o.h;
+        ok = ok && o.put64(sum) && std::fflush(o.f) == 0;
+        if (!ok) return fail(KBO_ERR_IO, "write failed: " + sbwt_path);
+    }
+    {
+        IoFile o;
+        o.f = std::fopen(lcs_path.c_str(), "wb");
+        if (!o.f) return fail(KBO_ERR_IO, "Expected write access to " + lcs_path);  // index.rs:148
+        bool ok = o.write(IO_MAGIC, 8) && o.put32(IO_VERSION) && o.put32(h.k) && o.put64(h.n_sets) &&
+                  o.write(h.lcs.data(), (size_t)h.n_sets);
+        const uint64_t sum = o.h;
+        ok = ok && o.put64(sum) && std::fflush(o.f) == 0;
+        if (!ok) return fail(KBO_ERR_IO, "write failed: " + lcs_path);
+    }
+    return KBO_OK;
+}
+
+int kbo_index_load(const char* index_prefix, int device, kbo_index** out) {
+    if (!out) return fail(KBO_ERR_BAD_ARGUMENT, "out is null");
+    *out = nullptr;
+    if (!index_prefix) return fail(KBO_ERR_BAD_ARGUMENT, "null argument");
+    const std::string sbwt_path = std::string(index_prefix) + ".sbwt", lcs_path = std::string(index_prefix) + ".lcs";
+    uint32_t k = 0;
+    uint64_t n_sets = 0, n_kmers = 0;
+    std::vector<uint64_t> rows[4];
+    std::vector<uint8_t> lcs;
+    {
+        IoFile in;
+        in.f = std::fopen(sbwt_path.c_str(), "rb");
+        if (!in.f) return fail(KBO_ERR_IO, "Expected SBWT at " + sbwt_path);  // index.rs:202
+        uint64_t name_len = 0;
+        char name[sizeof(IO_VARIANT)] = {0}, magic[8] = {0};
+        uint32_t version = 0;
+        if (!in.get(name_len) || name_len != sizeof(IO_VARIANT) - 1 || !in.read(name, name_len) ||
+            std::memcmp(name, IO_VARIANT, name_len) != 0)
+            return fail(KBO_ERR_FORMAT, sbwt_path + ": not a SubsetMatrix index file (index.rs:139-140)");
+        if (!in.read(magic, 8) || std::memcmp(magic, IO_MAGIC, 8) != 0)
+            return fail(KBO_ERR_FORMAT, sbwt_path + ": a SubsetMatrix file whose body was not written by this library "
+                                                    "(the sbwt crate's own layout is not readable here; rebuild the "
+                                                    "index from the sequences or pass its arrays to kbo_index_from_parts)");
+        if (!in.get(version) || version != IO_VERSION || !in.get(k) || !in.get(n_sets) || !in.get(n_kmers))
+            return fail(KBO_ERR_FORMAT, sbwt_path + ": unsupported version or truncated header");
+        if (k == 0 || k > 127 || n_sets == 0 || n_sets >= (1ull << 32))
+            return fail(KBO_ERR_FORMAT, sbwt_path + ": k or n_sets out of range");
+        const size_t nw = (size_t)(n_sets + 63) / 64;
+        for (int c = 0; c < 4; ++c) {
+            rows[c].resize(nw);
+            if (!in.read(rows[c].data(), nw * 8)) return fail(KBO_ERR_FORMAT, sbwt_path + ": truncated");
+        }
+        const uint64_t sum = in.h;
+        uint64_t stored = 0;
+        if (!in.get(stored) || stored != sum) return fail(KBO_ERR_FORMAT, sbwt_path + ": checksum mismatch");
+    }
+    {
+        IoFile in;
+        in.f = std::fopen(lcs_path.c_str(), "rb");
+        if (!in.f) return fail(KBO_ERR_IO, "Expected LCS array at " + lcs_path);  // index.rs:207
+        char magic[8] = {0};
+        uint32_t version = 0, k2 = 0;
+        uint64_t n2 = 0;
+        if (!in.read(magic, 8) || std::memcmp(magic, IO_MAGIC, 8) != 0)
+            return fail(KBO_ERR_FORMAT, lcs_path + ": not an LCS file written by this library");
+        if (!in.get(version) || version != IO_VERSION || !in.get(k2) || !in.get(n2))
+            return fail(KBO_ERR_FORMAT, lcs_path + ": unsupported version or truncated header");
+        if (k2 != k || n2 != n_sets) return fail(KBO_ERR_FORMAT, lcs_path + ": does not belong to " + sbwt_path);
+        lcs.resize((size_t)n_sets);
+        if (!in.read(lcs.data(), (size_t)n_sets)) return fail(KBO_ERR_FORMAT, lcs_path + ": truncated");
+        const uint64_t sum = in.h;
+        uint64_t stored = 0;
+        if (!in.get(stored) || stored != sum) return fail(KBO_ERR_FORMAT, lcs_path + ": checksum mismatch");
+    }
+    const uint64_t* rp[4] = {rows[0].data(), rows[1].data(), rows[2].data(), rows[3].data()};
+    const int rc = kbo_index_from_parts(k, n_sets, n_kmers, rp, lcs.data(), device, out);
+    return rc == KBO_ERR_BAD_ARGUMENT ? fail(KBO_ERR_FORMAT, sbwt_path + ": inconsistent arrays (" + g_err + ")") : rc;
+}
+
 int kbo_index_access_kmer(const kbo_index* ix, uint64_t colex, uint8_t* out_k) {
     if (!ix || !out_k) return fail(KBO_ERR_BAD_ARGUMENT, "null argument");
     if (colex >= ix->host.n_sets) return fail(KBO_ERR_PANIC, "access_kmer: colex rank out of range");

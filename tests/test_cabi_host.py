@@ -179,3 +179,68 @@ def test_new_entry_points_check_their_arguments(lib):
     assert lib.kbo_index_set_get(None, 0) is None
     if api.device_count() == 0:
         assert lib.kbo_ctx_create(1, None, C.byref(h)) == 8  # no device: KBO_ERR_CUDA, no fallback
+
+
+def _fnv1a(data):
+    h = 1469598103934665603
+    for b in data:
+        h = ((h ^ b) * 1099511628211) & 0xFFFFFFFFFFFFFFFF
+    return h
+
+
+def write_index_files(prefix, k, n_sets, n_kmers, rows, lcs):
+    """The documented layout of `<prefix>.sbwt` / `<prefix>.lcs` (include/kbo_b200.h), written independently of the library."""
+    import struct
+    body = struct.pack("<Q", 12) + b"SubsetMatrix" + b"KBOB200\0" + struct.pack("<IIQQ", 1, k, n_sets, n_kmers)
+    for r in rows:
+        body += np.ascontiguousarray(r[:(n_sets + 63) // 64], dtype="<u8").tobytes()
+    open(prefix + ".sbwt", "wb").write(body + struct.pack("<Q", _fnv1a(body)))
+    body = b"KBOB200\0" + struct.pack("<IIQ", 1, k, n_sets) + np.asarray(lcs, dtype=np.uint8).tobytes()
+    open(prefix + ".lcs", "wb").write(body + struct.pack("<Q", _fnv1a(body)))
+
+
+def test_load_sbwt_validates_the_files_before_any_device_work(lib, tmp_path):
+    """index::load_sbwt (index.rs:195-212): a missing file is the reference's panic (KBO_ERR_IO), anything that is not
+    an index file of this library is refused (KBO_ERR_FORMAT) -- checked without a GPU; a well-formed pair gets as far
+    as the upload (KBO_ERR_CUDA here)."""
+    import oracle_lib as O
+    o = O.OracleIndex([b"AAAGAACCA-TCAGGGCG"], k=3)
+    prefix = str(tmp_path / "idx")
+    with pytest.raises(api.KboPanic) as e:
+        api.load_sbwt(prefix)
+    assert e.value.status == 14 and "Expected SBWT at" in str(e.value)
+    write_index_files(prefix, 3, o.n_sets, o.n_kmers, o.rows(), o.lcs())
+    good_sbwt, good_lcs = open(prefix + ".sbwt", "rb").read(), open(prefix + ".lcs", "rb").read()
+
+    def expect_format(sbwt=None, lcs=None, word=None):
+        open(prefix + ".sbwt", "wb").write(good_sbwt if sbwt is None else sbwt)
+        open(prefix + ".lcs", "wb").write(good_lcs if lcs is None else lcs)
+        with pytest.raises(api.KboPanic) as e:
+            api.load_sbwt(prefix)
+        assert e.value.status == 15, str(e.value)
+        if word:
+            assert word in str(e.value)
+
+    expect_format(sbwt=b"\x05\0\0\0\0\0\0\0Other" + good_sbwt[20:], word="SubsetMatrix")
+    # the variant header of the reference followed by a body this library did not write (e.g. the sbwt crate's)
+    expect_format(sbwt=good_sbwt[:20] + b"\x13\0\0\0\0\0\0\0" + good_sbwt[28:], word="not written by this library")
+    expect_format(sbwt=good_sbwt[:-9], word="truncated")
+    flipped = bytearray(good_sbwt); flipped[60] ^= 1
+    expect_format(sbwt=bytes(flipped), word="checksum")
+    expect_format(lcs=good_lcs[:-3])
+    flipped = bytearray(good_lcs); flipped[26] ^= 1
+    expect_format(lcs=bytes(flipped), word="checksum")
+    o2 = O.OracleIndex([b"AAAGAACCA-TCAGGGCGTTTT"], k=3)
+    write_index_files(prefix + "2", 3, o2.n_sets, o2.n_kmers, o2.rows(), o2.lcs())
+    expect_format(lcs=open(prefix + "2.lcs", "rb").read(), word="does not belong")
+    os.remove(prefix + ".lcs")
+    open(prefix + ".sbwt", "wb").write(good_sbwt)
+    with pytest.raises(api.KboPanic) as e:
+        api.load_sbwt(prefix)
+    assert e.value.status == 14 and "Expected LCS array at" in str(e.value)
+    open(prefix + ".lcs", "wb").write(good_lcs)
+    if api.device_count() == 0:
+        with pytest.raises(api.KboPanic) as e:
+            api.load_sbwt(prefix)
+        assert e.value.status == 8  # the files are fine; there is no device to upload to and no CPU fallback
+    assert lib.kbo_index_serialize(None, b"x") == 7 and lib.kbo_index_load(None, 0, None) == 7

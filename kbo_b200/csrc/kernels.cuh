@@ -38,7 +38,7 @@ namespace kbo_b200 {
 //          so extend_right needs ONE 8-byte load per interval end and a popc.
 //          Four consecutive words (128 positions) share a 32-byte L2 sector.
 //   lcs  : one byte per node, zero padded past n (sentinel for the right scan).
-//   links: one 32-bit word per node (and one for n): bits 0-7 LCS[q], bits 8-19 q - PSV(q), bits 20-31 NSV(q) - q,
+//   links: one 32-bit word per node (and one for n): bits 0-6 LCS[q], bit 7 LINK_SLOW, bits 8-19 q - PSV(q), bits 20-31 NSV(q) - q,
 //          PSV / NSV = nearest position to the left / right whose LCS is smaller; 4095 = farther than that (or none).
 //          contract_left to the first depth that changes the interval is then two loads and a few additions.
 //   rank2: see IndexView::rank2 (DESIGN.md "two bases per probe").
@@ -232,7 +232,7 @@ __device__ __forceinline__ uint64_t lcs_lt_mask64(uint64_t w, uint64_t t_rep) {
     return ~((w | H) - t_rep) & H;
 }
 
-enum { LINK_FAR = 4095, LINK_SCAN_WORDS = 512 };
+enum { LINK_FAR = 4095, LINK_SCAN_WORDS = 512, LINK_SLOW = 0x80 };  // LCS values are < 128: bit 7 of the value byte is free
 
 // largest q <= from with LCS[q] < t (t >= 1; LCS[0] = 0 ends every scan).  Gives up after max_words 8-byte words
 // (returns 0xffffffff); max_words == 0: no limit.
@@ -276,7 +276,11 @@ __global__ void lcs_links_kernel(const uint8_t* __restrict__ lcs, uint32_t n, ui
         const uint32_t b = lcs_scan_right(lcs, q + 1, v, LINK_SCAN_WORDS);
         if (b != 0xffffffffu && b - q < LINK_FAR) dr = b - q;
     }
-    links[q] = v | (dl << 8) | (dr << 20);
+    // LINK_SLOW: the contraction's common case needs v > 0 and both distances in reach; everything else (a handful of
+    // nodes with LCS 0, the shallow nodes whose nearest smaller value is far away) is flagged once here instead of
+    // being tested for on every contraction
+    const uint32_t slow = (v == 0 || dl == LINK_FAR || dr == LINK_FAR) ? (uint32_t)LINK_SLOW : 0u;
+    links[q] = v | slow | (dl << 8) | (dr << 20);
 }
 
 // ---- rank2: two bases per probe (IndexView::rank2) -------------------------------------------------------------
@@ -327,7 +331,7 @@ __global__ void compose_rank2_kernel(IndexView ix, const uint32_t* __restrict__ 
 // The rare cases (t == 0, an end beyond the reach of the links, the impossible t > d - 1) are kept out of line.
 __device__ __noinline__ uint4 ms_contract_rare(const uint8_t* __restrict__ lcs, uint32_t n, uint32_t el, uint32_t er,
                                                uint32_t l, uint32_t r, uint32_t d) {  // returns (l, r, d, scanned)
-    const uint32_t vl = el & 0xffu, vr = er & 0xffu;
+    const uint32_t vl = el & 0x7fu, vr = er & 0x7fu;
     uint32_t t = vl > vr ? vl : vr;
     uint32_t scanned = 0;
     if (t == 0) {
@@ -354,18 +358,18 @@ __device__ __noinline__ uint4 ms_contract_rare(const uint8_t* __restrict__ lcs, 
 }
 __device__ __forceinline__ bool ms_contract(const IndexView& ix, uint32_t el, uint32_t er, uint32_t& l, uint32_t& r,
                                             uint32_t& d) {
-    const uint32_t vl = el & 0xffu, vr = er & 0xffu;
-    const uint32_t t = vl > vr ? vl : vr;
-    const uint32_t dl = (el >> 8) & 0xfffu, dr = er >> 20;
-    const bool far = (vl == t && dl == LINK_FAR) || (vr == t && dr == LINK_FAR);
-    if (t == 0 || t > d - 1 || far) {
+    if ((el | er) & (uint32_t)LINK_SLOW) {  // an end with LCS 0 or with a distance beyond the links' reach
         const uint4 s = ms_contract_rare(ix.lcs, ix.n, el, er, l, r, d);
         l = s.x; r = s.y; d = s.z;
         return s.w != 0;
     }
-    d = t;
-    l -= vl == t ? dl : 0u;  // the left end moves to the previous position with a smaller LCS
-    r += vr == t ? dr : 0u;
+    // Both values are > 0 and both distances are exact.  t <= d - 1 holds for every state the recurrence produces
+    // ([l, r) is the whole colex range of its d-suffix, so LCS[l] < d and LCS[r] < d); the literal bound of
+    // contract_left is kept in ms_contract_rare only.
+    const uint32_t vl = el & 0xffu, vr = er & 0xffu;
+    d = vl > vr ? vl : vr;
+    if (vl >= vr) l -= (el >> 8) & 0xfffu;  // the left end moves to the previous position with a smaller LCS
+    if (vr >= vl) r += er >> 20;
     return false;
 }
 
@@ -420,7 +424,10 @@ __global__ void prefix_table_level_kernel(IndexView ix, const uint64_t* __restri
 
 // One extend attempt per loop iteration and lane.  A lane whose extension fails (at d > 0) contracts in the same
 // iteration -- two loads of `links` and a few additions -- and retries the base in the next one.
-template <bool INTERVALS, bool COUNT>
+// GATE (kbo_set_ms_flags bit 6, experiment): contractions only in every second iteration of the warp.  A lane whose
+// extension fails in an odd iteration waits (no probe) and contracts in the next one, so the divergent contraction
+// block and its second memory round trip run in about half of the warp's iterations, for twice the lanes.
+template <bool INTERVALS, bool COUNT, bool GATE = false>
 __global__ void __launch_bounds__(256, 6) ms_kernel(MsParams p) {
     __shared__ __align__(16) uint8_t ms_stage[256 * 36];
     const uint64_t g = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
@@ -465,28 +472,50 @@ __global__ void __launch_bounds__(256, 6) ms_kernel(MsParams p) {
         // emitted MS bytes are staged in shared memory (36-byte stride per lane: conflict-free word access) and
         // flushed as two 16-byte stores per 32 positions; chunk starts are multiples of 32, so flushes are aligned
         uint8_t* const stg = ms_stage + threadIdx.x * 36u;
+        uint32_t it = 0;       // GATE: iterations of this warp (the lanes of a warp loop in lockstep)
+        bool pending = false;  // GATE: the extension failed, the contraction is still to be done
         while (bp < bp_end) {
             bool advance = true;
-            if (iw & 1u) {
-                l = 0; r = n; d = 0;
+            if (GATE && pending) {
+                advance = false;
             } else {
+                // (a non-ACGT position probes like any other and then resets the state: such positions are rare, and
+                // a branch around the probe costs every iteration its test and the compiler's speculated reset)
+                const bool inval = (iw & 1u) != 0;
                 const uint32_t rowoff = ((uint32_t)qw & 3u) * p.ix.rank_stride;  // 32-bit word index
                 const uint32_t bl = l >> 5, br = r >> 5;
                 const uint64_t wl = __ldg(p.ix.rank + (rowoff + bl));
                 const uint64_t wr = (br == bl) ? wl : __ldg(p.ix.rank + (rowoff + br));
                 const uint32_t nl = (uint32_t)(wl >> 32) + __popc((uint32_t)wl & ((1u << (l & 31)) - 1u));
                 const uint32_t nr = (uint32_t)(wr >> 32) + __popc((uint32_t)wr & ((1u << (r & 31)) - 1u));
-                if (COUNT) {
+                if (COUNT && !inval) {
                     const bool sp = (bl >> 2) != (br >> 2);
                     ++cnt_att; cnt_split += sp;
                     if (bp >= bp_emit) { ++cnt_att_e; cnt_split_e += sp; }
                 }
-                if (nl < nr) {
+                if (nl < nr && !inval) {
                     l = nl; r = nr;
                     d = d + 1 < k ? d + 1 : k;
-                } else if (d != 0) {
+                } else if (d != 0 && !inval) {
                     // contract_left to the largest depth that changes the interval: t = max(LCS[l], LCS[r])
                     advance = false;
+                    if (GATE) {
+                        pending = true;
+                    } else {
+                        const uint32_t el = __ldg(p.ix.links + l), er = __ldg(p.ix.links + r);
+                        const bool scanned = ms_contract(p.ix, el, er, l, r, d);
+                        if (COUNT) {
+                            ++cnt_con; cnt_extra += scanned;
+                            if (bp >= bp_emit) { ++cnt_con_e; cnt_extra_e += scanned; }
+                        }
+                    }
+                } else if (inval) {
+                    l = 0; r = n; d = 0;
+                }
+            }
+            if (GATE) {
+                if (pending && (it & 1u) == 0) {
+                    pending = false;
                     const uint32_t el = __ldg(p.ix.links + l), er = __ldg(p.ix.links + r);
                     const bool scanned = ms_contract(p.ix, el, er, l, r, d);
                     if (COUNT) {
@@ -494,12 +523,15 @@ __global__ void __launch_bounds__(256, 6) ms_kernel(MsParams p) {
                         if (bp >= bp_emit) { ++cnt_con_e; cnt_extra_e += scanned; }
                     }
                 }
+                ++it;
             }
             if (advance) {
                 if (COUNT) ++cnt_proc;
+                // (warm-up positions are staged as well: their slots are rewritten before the first flush, because
+                // bp_emit is a multiple of 32 and a flush needs bp > bp_emit)
+                stg[bp & 31u] = (uint8_t)d;
                 if (bp >= bp_emit) {
                     if (COUNT) ++cnt_emit;
-                    stg[bp & 31u] = (uint8_t)d;
                     if (INTERVALS) {
                         p.l_out[(wbase << 5) + bp] = l;
                         p.r_out[(wbase << 5) + bp] = r;

@@ -168,6 +168,8 @@ static void stage_and_ms(EmuIndex* e, const uint8_t* concat, const uint64_t* off
     emu_launch_seq(blocks, threads, [&]() {
         if (intervals) {
             if (counters) ms_kernel<true, true>(mp); else ms_kernel<true, false>(mp);
+        } else if (mp.flags & 64u) {  // contractions gated to every second iteration
+            if (counters) ms_kernel<false, true, true>(mp); else ms_kernel<false, false, true>(mp);
         } else {
             if (counters) ms_kernel<false, true>(mp); else ms_kernel<false, false>(mp);
         }

@@ -427,9 +427,16 @@ __global__ void prefix_table_level_kernel(IndexView ix, const uint64_t* __restri
 // GATE (kbo_set_ms_flags bit 6, experiment): contractions only in every second iteration of the warp.  A lane whose
 // extension fails in an odd iteration waits (no probe) and contracts in the next one, so the divergent contraction
 // block and its second memory round trip run in about half of the warp's iterations, for twice the lanes.
-template <bool INTERVALS, bool COUNT, bool GATE = false>
+// BSTAGE (kbo_set_ms_flags bit 7, experiment; chunk_len == 64, k <= 33, 256 lanes per block): a lane stages its whole chunk in
+// shared memory (100-byte slices = 32 scratch bytes for the warm-up positions + 64; 25 words: the byte stores of a warp
+// fall into distinct banks) and the block copies its 16 KB of MS
+// bytes -- one contiguous range of the batch -- out after the loop with coalesced stores.  The loop then has no flush:
+// in the default form the 2-3 flushes of a lane run when ITS position crosses a multiple of 32, i.e. for ~2 lanes at
+// a time, 20 instructions each.
+enum { MS_BSTAGE_CHUNK = 64, MS_BSTAGE_PRE = 32, MS_BSTAGE_STRIDE = 100 };
+template <bool INTERVALS, bool COUNT, bool GATE = false, bool BSTAGE = false>
 __global__ void __launch_bounds__(256, 6) ms_kernel(MsParams p) {
-    __shared__ __align__(16) uint8_t ms_stage[256 * 36];
+    __shared__ __align__(16) uint8_t ms_stage[256 * (BSTAGE ? (int)MS_BSTAGE_STRIDE : 36)];
     const uint64_t g = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
     unsigned long long cnt_att = 0, cnt_split = 0, cnt_con = 0, cnt_extra = 0, cnt_proc = 0, cnt_emit = 0;
     unsigned long long cnt_att_e = 0, cnt_split_e = 0, cnt_con_e = 0, cnt_extra_e = 0;
@@ -471,7 +478,8 @@ __global__ void __launch_bounds__(256, 6) ms_kernel(MsParams p) {
         uint32_t iw = __ldg(iptr) >> bp;
         // emitted MS bytes are staged in shared memory (36-byte stride per lane: conflict-free word access) and
         // flushed as two 16-byte stores per 32 positions; chunk starts are multiples of 32, so flushes are aligned
-        uint8_t* const stg = ms_stage + threadIdx.x * 36u;
+        uint8_t* const stg = ms_stage + threadIdx.x * (BSTAGE ? (uint32_t)MS_BSTAGE_STRIDE : 36u);
+        uint8_t* sp = stg + (uint32_t)MS_BSTAGE_PRE - warm;  // BSTAGE: next staging byte (the launcher checks k - 1 <= MS_BSTAGE_PRE)
         uint32_t it = 0;       // GATE: iterations of this warp (the lanes of a warp loop in lockstep)
         bool pending = false;  // GATE: the extension failed, the contraction is still to be done
         while (bp < bp_end) {
@@ -529,7 +537,9 @@ __global__ void __launch_bounds__(256, 6) ms_kernel(MsParams p) {
                 if (COUNT) ++cnt_proc;
                 // (warm-up positions are staged as well: their slots are rewritten before the first flush, because
                 // bp_emit is a multiple of 32 and a flush needs bp > bp_emit)
-                stg[bp & 31u] = (uint8_t)d;
+                // (BSTAGE: the warm-up positions go to the scratch bytes in front of the chunk's 64)
+                if (BSTAGE) *sp++ = (uint8_t)d;
+                else stg[bp & 31u] = (uint8_t)d;
                 if (bp >= bp_emit) {
                     if (COUNT) ++cnt_emit;
                     if (INTERVALS) {
@@ -540,7 +550,13 @@ __global__ void __launch_bounds__(256, 6) ms_kernel(MsParams p) {
                 ++bp;
                 qw >>= 2;
                 iw >>= 1;
-                if ((bp & 31) == 0 || bp == bp_end) {
+                if (BSTAGE) {
+                    if (__builtin_expect((bp & 31) == 0 && bp < bp_end, 0)) {
+                        asm volatile("" ::: "memory");  // keeps this a branch: predicated, its five instructions issue in every iteration
+                        qw = __ldg(qptr + (bp >> 5));
+                        iw = __ldg(iptr + (bp >> 5));
+                    }
+                } else if ((bp & 31) == 0 || bp == bp_end) {
                     if (bp > bp_emit) {  // flush the 32 (or last, partial) staged positions
                         const uint32_t* w = reinterpret_cast<const uint32_t*>(stg);
                         uint4* dst = reinterpret_cast<uint4*>(msw + ((bp - 1) & ~31u));
@@ -554,6 +570,20 @@ __global__ void __launch_bounds__(256, 6) ms_kernel(MsParams p) {
                 }
             }
         }
+    }
+    if (BSTAGE) {
+        // the block's chunks are consecutive: 256 x 64 positions from `base`; word w of that range sits in lane
+        // w / 16's slice.  The MS array has room for n_words x 32 positions (make_geometry); the tail of the last
+        // chunk past Lp carries stale bytes, as the partial flush of the default form does.
+        __syncthreads();
+        const uint64_t base = (uint64_t)blockIdx.x * blockDim.x * (uint64_t)MS_BSTAGE_CHUNK;
+        const uint64_t limit = p.q.n_words * 32ull;
+        const uint32_t n_w = base >= limit ? 0u
+                             : (uint32_t)((limit - base < 256ull * MS_BSTAGE_CHUNK ? limit - base : 256ull * MS_BSTAGE_CHUNK) >> 2);
+        const uint32_t* sw = reinterpret_cast<const uint32_t*>(ms_stage);
+        uint32_t* dst = reinterpret_cast<uint32_t*>(p.ms + base);
+        for (uint32_t w = threadIdx.x; w < n_w; w += blockDim.x)
+            dst[w] = sw[(w >> 4) * (uint32_t)(MS_BSTAGE_STRIDE / 4) + (uint32_t)(MS_BSTAGE_PRE / 4) + (w & 15u)];
     }
     if (COUNT) {
         atomicAdd(p.counters + CNT_ATTEMPTS, cnt_att);

@@ -887,14 +887,15 @@ static int run_ms(kbo_index* ix, Workspace* ws, const QueryView& qv, const Geome
     } else if ((mp.flags & 32u) && mp.ix.rank2) {  // bit 5: two bases per probe in K1 (ms_pairs_kernel)
         if (count) ms_pairs_kernel<true><<<blocks, threads, 0, st>>>(mp);
         else ms_pairs_kernel<false><<<blocks, threads, 0, st>>>(mp);
-    } else if ((mp.flags & 128u) && mp.chunk_len == MS_BSTAGE_CHUNK && mp.ix.k <= MS_BSTAGE_PRE + 1 && threads == 256) {
+    } else if ((mp.flags & 128u) && mp.chunk_len == MS_BSTAGE_CHUNK && mp.ix.k <= MS_BSTAGE_PRE + 1) {
         // bit 7: whole chunks staged in shared memory, block-wide copy-out (experiment; with bit 6: gated as well)
+        const size_t smem = (size_t)threads * MS_BSTAGE_STRIDE;
         if (mp.flags & 64u) {
-            if (count) ms_kernel<false, true, true, true><<<blocks, threads, 0, st>>>(mp);
-            else ms_kernel<false, false, true, true><<<blocks, threads, 0, st>>>(mp);
+            if (count) ms_kernel<false, true, true, true><<<blocks, threads, smem, st>>>(mp);
+            else ms_kernel<false, false, true, true><<<blocks, threads, smem, st>>>(mp);
         } else {
-            if (count) ms_kernel<false, true, false, true><<<blocks, threads, 0, st>>>(mp);
-            else ms_kernel<false, false, false, true><<<blocks, threads, 0, st>>>(mp);
+            if (count) ms_kernel<false, true, false, true><<<blocks, threads, smem, st>>>(mp);
+            else ms_kernel<false, false, false, true><<<blocks, threads, smem, st>>>(mp);
         }
     } else if (mp.flags & 64u) {  // bit 6: contractions gated to every second warp iteration (experiment)
         if (count) ms_kernel<false, true, true><<<blocks, threads, 0, st>>>(mp);

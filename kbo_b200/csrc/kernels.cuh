@@ -427,16 +427,22 @@ __global__ void prefix_table_level_kernel(IndexView ix, const uint64_t* __restri
 // GATE (kbo_set_ms_flags bit 6, experiment): contractions only in every second iteration of the warp.  A lane whose
 // extension fails in an odd iteration waits (no probe) and contracts in the next one, so the divergent contraction
 // block and its second memory round trip run in about half of the warp's iterations, for twice the lanes.
-// BSTAGE (kbo_set_ms_flags bit 7, experiment; chunk_len == 64, k <= 33, 256 lanes per block): a lane stages its whole chunk in
+// BSTAGE (kbo_set_ms_flags bit 7, experiment; chunk_len == 64, k <= 33): a lane stages its whole chunk in
 // shared memory (100-byte slices = 32 scratch bytes for the warm-up positions + 64; 25 words: the byte stores of a warp
-// fall into distinct banks) and the block copies its 16 KB of MS
+// fall into distinct banks) and the block copies its 8 or 16 KB of MS
 // bytes -- one contiguous range of the batch -- out after the loop with coalesced stores.  The loop then has no flush:
 // in the default form the 2-3 flushes of a lane run when ITS position crosses a multiple of 32, i.e. for ~2 lanes at
 // a time, 20 instructions each.
 enum { MS_BSTAGE_CHUNK = 64, MS_BSTAGE_PRE = 32, MS_BSTAGE_STRIDE = 100 };
 template <bool INTERVALS, bool COUNT, bool GATE = false, bool BSTAGE = false>
 __global__ void __launch_bounds__(256, 6) ms_kernel(MsParams p) {
-    __shared__ __align__(16) uint8_t ms_stage[256 * (BSTAGE ? (int)MS_BSTAGE_STRIDE : 36)];
+    __shared__ __align__(16) uint8_t ms_stage_static[BSTAGE ? 16 : 256 * 36];
+#ifdef KBO_HOST_EMU
+    static __attribute__((aligned(16))) uint8_t ms_stage_dynamic[256 * MS_BSTAGE_STRIDE];
+#else
+    extern __shared__ __align__(16) uint8_t ms_stage_dynamic[];  // BSTAGE: blockDim.x * MS_BSTAGE_STRIDE bytes
+#endif
+    uint8_t* const ms_stage = BSTAGE ? ms_stage_dynamic : ms_stage_static;
     const uint64_t g = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
     unsigned long long cnt_att = 0, cnt_split = 0, cnt_con = 0, cnt_extra = 0, cnt_proc = 0, cnt_emit = 0;
     unsigned long long cnt_att_e = 0, cnt_split_e = 0, cnt_con_e = 0, cnt_extra_e = 0;
@@ -572,14 +578,14 @@ __global__ void __launch_bounds__(256, 6) ms_kernel(MsParams p) {
         }
     }
     if (BSTAGE) {
-        // the block's chunks are consecutive: 256 x 64 positions from `base`; word w of that range sits in lane
+        // the block's chunks are consecutive: blockDim.x x 64 positions from `base`; word w of that range sits in lane
         // w / 16's slice.  The MS array has room for n_words x 32 positions (make_geometry); the tail of the last
         // chunk past Lp carries stale bytes, as the partial flush of the default form does.
         __syncthreads();
         const uint64_t base = (uint64_t)blockIdx.x * blockDim.x * (uint64_t)MS_BSTAGE_CHUNK;
         const uint64_t limit = p.q.n_words * 32ull;
-        const uint32_t n_w = base >= limit ? 0u
-                             : (uint32_t)((limit - base < 256ull * MS_BSTAGE_CHUNK ? limit - base : 256ull * MS_BSTAGE_CHUNK) >> 2);
+        const uint64_t span = (uint64_t)blockDim.x * (uint64_t)MS_BSTAGE_CHUNK;
+        const uint32_t n_w = base >= limit ? 0u : (uint32_t)((limit - base < span ? limit - base : span) >> 2);
         const uint32_t* sw = reinterpret_cast<const uint32_t*>(ms_stage);
         uint32_t* dst = reinterpret_cast<uint32_t*>(p.ms + base);
         for (uint32_t w = threadIdx.x; w < n_w; w += blockDim.x)

@@ -887,19 +887,6 @@ static int run_ms(kbo_index* ix, Workspace* ws, const QueryView& qv, const Geome
     } else if ((mp.flags & 32u) && mp.ix.rank2) {  // bit 5: two bases per probe in K1 (ms_pairs_kernel)
         if (count) ms_pairs_kernel<true><<<blocks, threads, 0, st>>>(mp);
         else ms_pairs_kernel<false><<<blocks, threads, 0, st>>>(mp);
-    } else if ((mp.flags & 128u) && mp.chunk_len == MS_BSTAGE_CHUNK && mp.ix.k <= MS_BSTAGE_PRE + 1) {
-        // bit 7: whole chunks staged in shared memory, block-wide copy-out (experiment; with bit 6: gated as well)
-        const size_t smem = (size_t)threads * MS_BSTAGE_STRIDE;
-        if (mp.flags & 64u) {
-            if (count) ms_kernel<false, true, true, true><<<blocks, threads, smem, st>>>(mp);
-            else ms_kernel<false, false, true, true><<<blocks, threads, smem, st>>>(mp);
-        } else {
-            if (count) ms_kernel<false, true, false, true><<<blocks, threads, smem, st>>>(mp);
-            else ms_kernel<false, false, false, true><<<blocks, threads, smem, st>>>(mp);
-        }
-    } else if (mp.flags & 64u) {  // bit 6: contractions gated to every second warp iteration (experiment)
-        if (count) ms_kernel<false, true, true><<<blocks, threads, 0, st>>>(mp);
-        else ms_kernel<false, false, true><<<blocks, threads, 0, st>>>(mp);
     } else {
         if (count) ms_kernel<false, true><<<blocks, threads, 0, st>>>(mp);
         else ms_kernel<false, false><<<blocks, threads, 0, st>>>(mp);
@@ -3104,7 +3091,7 @@ int kbo_set_prefix_len(uint32_t len) { g_prefix_len = (int)std::min<uint32_t>(le
 int kbo_set_rank2(int enabled) { g_rank2 = enabled ? 1 : 0; return KBO_OK; }
 int kbo_set_l2_persist(int enabled) { g_l2_persist = enabled ? 1 : 0; return KBO_OK; }
 int kbo_set_ms_flags(uint32_t flags) {
-    g_ms_flags = flags & 0xffu;  // bit 1: K2 instead of K2b; bit 2: fused kernel without rank2 pairs; bit 3: its one-pass form; bit 4: fused K1+K2b kernel; bit 5: K1p; bit 6: K1 with gated contractions; bit 7: K1 with block-staged output (chunk_len 64)
+    g_ms_flags = flags & 0xffu;  // bit 1: K2 instead of K2b; bit 2: fused kernel without rank2 pairs; bit 3: its one-pass form; bit 4: fused K1+K2b kernel; bit 5: K1p
     const uint32_t blk = (flags >> 8) & 0x3ffu;  // bits 8..17: K1 block size (experiment)
     if (blk == 128 || blk == 256) g_ms_block = blk;
     return KBO_OK;

@@ -424,25 +424,12 @@ __global__ void prefix_table_level_kernel(IndexView ix, const uint64_t* __restri
 
 // One extend attempt per loop iteration and lane.  A lane whose extension fails (at d > 0) contracts in the same
 // iteration -- two loads of `links` and a few additions -- and retries the base in the next one.
-// GATE (kbo_set_ms_flags bit 6, experiment): contractions only in every second iteration of the warp.  A lane whose
-// extension fails in an odd iteration waits (no probe) and contracts in the next one, so the divergent contraction
-// block and its second memory round trip run in about half of the warp's iterations, for twice the lanes.
-// BSTAGE (kbo_set_ms_flags bit 7, experiment; chunk_len == 64, k <= 33): a lane stages its whole chunk in
-// shared memory (100-byte slices = 32 scratch bytes for the warm-up positions + 64; 25 words: the byte stores of a warp
-// fall into distinct banks) and the block copies its 8 or 16 KB of MS
-// bytes -- one contiguous range of the batch -- out after the loop with coalesced stores.  The loop then has no flush:
-// in the default form the 2-3 flushes of a lane run when ITS position crosses a multiple of 32, i.e. for ~2 lanes at
-// a time, 20 instructions each.
-enum { MS_BSTAGE_CHUNK = 64, MS_BSTAGE_PRE = 32, MS_BSTAGE_STRIDE = 100 };
-template <bool INTERVALS, bool COUNT, bool GATE = false, bool BSTAGE = false>
+// (Round 2 measured two more forms of this loop and dropped them, profiles/README.md "K1, last measurements":
+// contractions gated to every second warp iteration -- 117 vs 107 us -- and whole chunks staged in shared memory with
+// a block-wide copy-out instead of the in-loop flush -- 107.8 vs 107.3 us; commit c63fe50 has both.)
+template <bool INTERVALS, bool COUNT>
 __global__ void __launch_bounds__(256, 6) ms_kernel(MsParams p) {
-    __shared__ __align__(16) uint8_t ms_stage_static[BSTAGE ? 16 : 256 * 36];
-#ifdef KBO_HOST_EMU
-    static __attribute__((aligned(16))) uint8_t ms_stage_dynamic[256 * MS_BSTAGE_STRIDE];
-#else
-    extern __shared__ __align__(16) uint8_t ms_stage_dynamic[];  // BSTAGE: blockDim.x * MS_BSTAGE_STRIDE bytes
-#endif
-    uint8_t* const ms_stage = BSTAGE ? ms_stage_dynamic : ms_stage_static;
+    __shared__ __align__(16) uint8_t ms_stage[256 * 36];
     const uint64_t g = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
     unsigned long long cnt_att = 0, cnt_split = 0, cnt_con = 0, cnt_extra = 0, cnt_proc = 0, cnt_emit = 0;
     unsigned long long cnt_att_e = 0, cnt_split_e = 0, cnt_con_e = 0, cnt_extra_e = 0;
@@ -484,68 +471,43 @@ __global__ void __launch_bounds__(256, 6) ms_kernel(MsParams p) {
         uint32_t iw = __ldg(iptr) >> bp;
         // emitted MS bytes are staged in shared memory (36-byte stride per lane: conflict-free word access) and
         // flushed as two 16-byte stores per 32 positions; chunk starts are multiples of 32, so flushes are aligned
-        uint8_t* const stg = ms_stage + threadIdx.x * (BSTAGE ? (uint32_t)MS_BSTAGE_STRIDE : 36u);
-        uint8_t* sp = stg + (uint32_t)MS_BSTAGE_PRE - warm;  // BSTAGE: next staging byte (the launcher checks k - 1 <= MS_BSTAGE_PRE)
-        uint32_t it = 0;       // GATE: iterations of this warp (the lanes of a warp loop in lockstep)
-        bool pending = false;  // GATE: the extension failed, the contraction is still to be done
+        uint8_t* const stg = ms_stage + threadIdx.x * 36u;
         while (bp < bp_end) {
             bool advance = true;
-            if (GATE && pending) {
-                advance = false;
-            } else {
-                // (a non-ACGT position probes like any other and then resets the state: such positions are rare, and
-                // a branch around the probe costs every iteration its test and the compiler's speculated reset)
-                const bool inval = (iw & 1u) != 0;
-                const uint32_t rowoff = ((uint32_t)qw & 3u) * p.ix.rank_stride;  // 32-bit word index
-                const uint32_t bl = l >> 5, br = r >> 5;
-                const uint64_t wl = __ldg(p.ix.rank + (rowoff + bl));
-                const uint64_t wr = (br == bl) ? wl : __ldg(p.ix.rank + (rowoff + br));
-                const uint32_t nl = (uint32_t)(wl >> 32) + __popc((uint32_t)wl & ((1u << (l & 31)) - 1u));
-                const uint32_t nr = (uint32_t)(wr >> 32) + __popc((uint32_t)wr & ((1u << (r & 31)) - 1u));
-                if (COUNT && !inval) {
-                    const bool sp = (bl >> 2) != (br >> 2);
-                    ++cnt_att; cnt_split += sp;
-                    if (bp >= bp_emit) { ++cnt_att_e; cnt_split_e += sp; }
-                }
-                if (nl < nr && !inval) {
-                    l = nl; r = nr;
-                    d = d + 1 < k ? d + 1 : k;
-                } else if (d != 0 && !inval) {
-                    // contract_left to the largest depth that changes the interval: t = max(LCS[l], LCS[r])
-                    advance = false;
-                    if (GATE) {
-                        pending = true;
-                    } else {
-                        const uint32_t el = __ldg(p.ix.links + l), er = __ldg(p.ix.links + r);
-                        const bool scanned = ms_contract(p.ix, el, er, l, r, d);
-                        if (COUNT) {
-                            ++cnt_con; cnt_extra += scanned;
-                            if (bp >= bp_emit) { ++cnt_con_e; cnt_extra_e += scanned; }
-                        }
-                    }
-                } else if (inval) {
-                    l = 0; r = n; d = 0;
-                }
+            // (a non-ACGT position probes like any other and then resets the state: such positions are rare, and
+            // a branch around the probe costs every iteration its test and the compiler's speculated reset)
+            const bool inval = (iw & 1u) != 0;
+            const uint32_t rowoff = ((uint32_t)qw & 3u) * p.ix.rank_stride;  // 32-bit word index
+            const uint32_t bl = l >> 5, br = r >> 5;
+            const uint64_t wl = __ldg(p.ix.rank + (rowoff + bl));
+            const uint64_t wr = (br == bl) ? wl : __ldg(p.ix.rank + (rowoff + br));
+            const uint32_t nl = (uint32_t)(wl >> 32) + __popc((uint32_t)wl & ((1u << (l & 31)) - 1u));
+            const uint32_t nr = (uint32_t)(wr >> 32) + __popc((uint32_t)wr & ((1u << (r & 31)) - 1u));
+            if (COUNT && !inval) {
+                const bool sp = (bl >> 2) != (br >> 2);
+                ++cnt_att; cnt_split += sp;
+                if (bp >= bp_emit) { ++cnt_att_e; cnt_split_e += sp; }
             }
-            if (GATE) {
-                if (pending && (it & 1u) == 0) {
-                    pending = false;
-                    const uint32_t el = __ldg(p.ix.links + l), er = __ldg(p.ix.links + r);
-                    const bool scanned = ms_contract(p.ix, el, er, l, r, d);
-                    if (COUNT) {
-                        ++cnt_con; cnt_extra += scanned;
-                        if (bp >= bp_emit) { ++cnt_con_e; cnt_extra_e += scanned; }
-                    }
+            if (nl < nr && !inval) {
+                l = nl; r = nr;
+                d = d + 1 < k ? d + 1 : k;
+            } else if (d != 0 && !inval) {
+                // contract_left to the largest depth that changes the interval: t = max(LCS[l], LCS[r])
+                advance = false;
+                const uint32_t el = __ldg(p.ix.links + l), er = __ldg(p.ix.links + r);
+                const bool scanned = ms_contract(p.ix, el, er, l, r, d);
+                if (COUNT) {
+                    ++cnt_con; cnt_extra += scanned;
+                    if (bp >= bp_emit) { ++cnt_con_e; cnt_extra_e += scanned; }
                 }
-                ++it;
+            } else if (inval) {
+                l = 0; r = n; d = 0;
             }
             if (advance) {
                 if (COUNT) ++cnt_proc;
                 // (warm-up positions are staged as well: their slots are rewritten before the first flush, because
                 // bp_emit is a multiple of 32 and a flush needs bp > bp_emit)
-                // (BSTAGE: the warm-up positions go to the scratch bytes in front of the chunk's 64)
-                if (BSTAGE) *sp++ = (uint8_t)d;
-                else stg[bp & 31u] = (uint8_t)d;
+                stg[bp & 31u] = (uint8_t)d;
                 if (bp >= bp_emit) {
                     if (COUNT) ++cnt_emit;
                     if (INTERVALS) {
@@ -556,13 +518,7 @@ __global__ void __launch_bounds__(256, 6) ms_kernel(MsParams p) {
                 ++bp;
                 qw >>= 2;
                 iw >>= 1;
-                if (BSTAGE) {
-                    if (__builtin_expect((bp & 31) == 0 && bp < bp_end, 0)) {
-                        asm volatile("" ::: "memory");  // keeps this a branch: predicated, its five instructions issue in every iteration
-                        qw = __ldg(qptr + (bp >> 5));
-                        iw = __ldg(iptr + (bp >> 5));
-                    }
-                } else if ((bp & 31) == 0 || bp == bp_end) {
+                if ((bp & 31) == 0 || bp == bp_end) {
                     if (bp > bp_emit) {  // flush the 32 (or last, partial) staged positions
                         const uint32_t* w = reinterpret_cast<const uint32_t*>(stg);
                         uint4* dst = reinterpret_cast<uint4*>(msw + ((bp - 1) & ~31u));
@@ -576,20 +532,6 @@ __global__ void __launch_bounds__(256, 6) ms_kernel(MsParams p) {
                 }
             }
         }
-    }
-    if (BSTAGE) {
-        // the block's chunks are consecutive: blockDim.x x 64 positions from `base`; word w of that range sits in lane
-        // w / 16's slice.  The MS array has room for n_words x 32 positions (make_geometry); the tail of the last
-        // chunk past Lp carries stale bytes, as the partial flush of the default form does.
-        __syncthreads();
-        const uint64_t base = (uint64_t)blockIdx.x * blockDim.x * (uint64_t)MS_BSTAGE_CHUNK;
-        const uint64_t limit = p.q.n_words * 32ull;
-        const uint64_t span = (uint64_t)blockDim.x * (uint64_t)MS_BSTAGE_CHUNK;
-        const uint32_t n_w = base >= limit ? 0u : (uint32_t)((limit - base < span ? limit - base : span) >> 2);
-        const uint32_t* sw = reinterpret_cast<const uint32_t*>(ms_stage);
-        uint32_t* dst = reinterpret_cast<uint32_t*>(p.ms + base);
-        for (uint32_t w = threadIdx.x; w < n_w; w += blockDim.x)
-            dst[w] = sw[(w >> 4) * (uint32_t)(MS_BSTAGE_STRIDE / 4) + (uint32_t)(MS_BSTAGE_PRE / 4) + (w & 15u)];
     }
     if (COUNT) {
         atomicAdd(p.counters + CNT_ATTEMPTS, cnt_att);

@@ -165,18 +165,9 @@ static void stage_and_ms(EmuIndex* e, const uint8_t* concat, const uint64_t* off
         });
         return;
     }
-    if (!intervals && (mp.flags & 128u) && mp.chunk_len == MS_BSTAGE_CHUNK && mp.ix.k <= MS_BSTAGE_PRE + 1) {  // block barrier: one host thread per lane
-        emu_launch_par(blocks, threads, [&]() {
-            if (mp.flags & 64u) { if (counters) ms_kernel<false, true, true, true>(mp); else ms_kernel<false, false, true, true>(mp); }
-            else { if (counters) ms_kernel<false, true, false, true>(mp); else ms_kernel<false, false, false, true>(mp); }
-        });
-        return;
-    }
     emu_launch_seq(blocks, threads, [&]() {
         if (intervals) {
             if (counters) ms_kernel<true, true>(mp); else ms_kernel<true, false>(mp);
-        } else if (mp.flags & 64u) {  // contractions gated to every second iteration
-            if (counters) ms_kernel<false, true, true>(mp); else ms_kernel<false, false, true>(mp);
         } else {
             if (counters) ms_kernel<false, true>(mp); else ms_kernel<false, false>(mp);
         }

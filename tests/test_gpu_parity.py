@@ -27,17 +27,16 @@ def _lib():
     api.set_chunk_len(0)
 
 
-@pytest.fixture(autouse=True, params=["separate", "fused", "fused-exact", "pairs", "gated", "bstage"])
+@pytest.fixture(autouse=True, params=["separate", "fused", "fused-exact", "pairs"])
 def kernel_path(request):
     """Tests that reach matches / find run several times: K1 followed by K2b, the fused K1 + K2b kernel of fused.cuh
     (kbo_set_ms_flags bit 4: MS bytes only in shared memory, TMA-staged queries) in its two-pass form (two bases per
-    probe + repair pass) and its one-pass form (bit 3: K1's recurrence), K1p (bit 5), K1 with contractions gated to
-    every second warp iteration (bit 6) and K1 with block-staged output (bit 7, here together with bit 6)."""
+    probe + repair pass) and its one-pass form (bit 3: K1's recurrence), and K1p (bit 5)."""
     name = request.node.originalname or request.node.name
     if request.param != "separate":
         if not any(t in name for t in ("matches", "find", "config2", "randomised", "tiny")):
             pytest.skip("does not reach the fused kernel / K1p")
-        api.set_ms_flags({"fused": 16, "fused-exact": 24, "pairs": 32, "gated": 64, "bstage": 192}[request.param])
+        api.set_ms_flags({"fused": 16, "fused-exact": 24, "pairs": 32}[request.param])
     yield
     api.set_ms_flags(0)
 

@@ -1268,7 +1268,7 @@ __device__ __forceinline__ void k2b_group(const TrParams& p, const uint8_t* ms, 
 }
 
 template <bool CHARS>
-__global__ void __launch_bounds__(K2B_WARPS * 32) derand_translate_bits_kernel(TrParams p) {
+__global__ void __launch_bounds__(K2B_WARPS * 32, 12) derand_translate_bits_kernel(TrParams p) {  // 40 registers, no spills: 12 blocks per SM
     __shared__ uint32_t lut[256];
     __shared__ __align__(16) uint8_t stage[K2B_WARPS][K2B_TILE + 16];
     if (CHARS) {
@@ -1429,10 +1429,13 @@ __device__ __forceinline__ void rle_scan_block_totals(T* blk, uint64_t n_blocks)
 // The block that finishes last scans the block totals.  The ticket counter resets itself for the next launch.
 template <int N, typename T>
 __device__ __forceinline__ void rle_finish_blocks(T* blk, uint64_t n_blocks, unsigned int* ticket) {
+    // (only thread 0 wrote this block's totals -- just before the call -- so only it has to order that write before
+    // its ticket; a fence in all 256 threads showed up as 3.5 warp-cycles of membar stall per issued instruction)
     __shared__ bool last;
-    __threadfence();
-    __syncthreads();
-    if (threadIdx.x == 0) last = atomicAdd(ticket, 1u) == gridDim.x - 1;
+    if (threadIdx.x == 0) {
+        __threadfence();
+        last = atomicAdd(ticket, 1u) == gridDim.x - 1;
+    }
     __syncthreads();
     if (!last) return;
     __threadfence();
@@ -1486,11 +1489,12 @@ __global__ void __launch_bounds__(RLE_BLOCK) rle_word_counts_kernel(RleParams p)
         p.cnt_blk[blockIdx.x] = t;
         if (MARKS) p.cse_blk[blockIdx.x] = (uint64_t)tot[4] | ((uint64_t)tot[5] << 32);
     }
-    if (MARKS) {  // one election, both arrays
+    if (MARKS) {  // one election, both arrays (thread 0 wrote the totals above and orders them before its ticket)
         __shared__ bool last;
-        __threadfence();
-        __syncthreads();
-        if (threadIdx.x == 0) last = atomicAdd(p.tickets, 1u) == gridDim.x - 1;
+        if (threadIdx.x == 0) {
+            __threadfence();
+            last = atomicAdd(p.tickets, 1u) == gridDim.x - 1;
+        }
         __syncthreads();
         if (!last) return;
         __threadfence();

@@ -1397,6 +1397,11 @@ struct IoFile {
     FILE* f = nullptr;
     uint64_t h = 1469598103934665603ull;  // FNV-1a 64
     ~IoFile() { if (f) std::fclose(f); }
+    bool close() {  // a writer checks this: buffered data may only fail to reach the disk here
+        const int rc = f ? std::fclose(f) : 0;
+        f = nullptr;
+        return rc == 0;
+    }
     bool write(const void* p, size_t n) {
         const uint8_t* b = (const uint8_t*)p;
         for (size_t i = 0; i < n; ++i) { h ^= b[i]; h *= 1099511628211ull; }
@@ -1430,7 +1435,7 @@ int kbo_index_serialize(const kbo_index* ix, const char* outfile_prefix) {
                   o.put64(h.n_sets) && o.put64(h.n_kmers);
         for (int c = 0; c < 4 && ok; ++c) ok = o.write(h.rows[c].data(), nw * 8);
         const uint64_t sum = o.h;
-        ok = ok && o.put64(sum) && std::fflush(o.f) == 0;
+        ok = ok && o.put64(sum) && o.close();
         if (!ok) return fail(KBO_ERR_IO, "write failed: " + sbwt_path);
     }
     {
@@ -1440,7 +1445,7 @@ int kbo_index_serialize(const kbo_index* ix, const char* outfile_prefix) {
         bool ok = o.write(IO_MAGIC, 8) && o.put32(IO_VERSION) && o.put32(h.k) && o.put64(h.n_sets) &&
                   o.write(h.lcs.data(), (size_t)h.n_sets);
         const uint64_t sum = o.h;
-        ok = ok && o.put64(sum) && std::fflush(o.f) == 0;
+        ok = ok && o.put64(sum) && o.close();
         if (!ok) return fail(KBO_ERR_IO, "write failed: " + lcs_path);
     }
     return KBO_OK;

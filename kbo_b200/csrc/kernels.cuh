@@ -1448,7 +1448,7 @@ __device__ __forceinline__ void rle_finish_blocks(T* blk, uint64_t n_blocks, uns
 // no prefix counts): also the START / END masks and their counts -- what rle_mark_kernel does in a second launch
 // for the gapped form.
 template <bool MARKS>
-__global__ void __launch_bounds__(RLE_BLOCK) rle_word_counts_kernel(RleParams p) {
+__global__ void __launch_bounds__(RLE_BLOCK, MARKS ? 6 : 5) rle_word_counts_kernel(RleParams p) {  // 40 / 48 registers, no spills
     const uint64_t w = (uint64_t)blockIdx.x * RLE_BLOCK + threadIdx.x;
     uint32_t c[MARKS ? 6 : 4], tot[MARKS ? 6 : 4];
 #pragma unroll
@@ -1478,7 +1478,20 @@ __global__ void __launch_bounds__(RLE_BLOCK) rle_word_counts_kernel(RleParams p)
             c[5] = __popc(en);
         }
     }
-    rle_block_scan<(MARKS ? 6 : 4)>(c, tot);
+    {   // a word adds at most 32 to a counter and a block has 256 words: two counters share one 32-bit scan value
+        // (half as many shuffles, and the registers that kept this kernel at 4 blocks per SM)
+        static_assert(RLE_BLOCK * 32 < 65536, "packed block scan: a block total must fit 16 bits");
+        constexpr int NP = MARKS ? 3 : 2;
+        uint32_t pk[NP], tp[NP];
+#pragma unroll
+        for (int i = 0; i < NP; ++i) pk[i] = c[2 * i] | (c[2 * i + 1] << 16);
+        rle_block_scan<NP>(pk, tp);
+#pragma unroll
+        for (int i = 0; i < NP; ++i) {
+            c[2 * i] = pk[i] & 0xffffu; c[2 * i + 1] = pk[i] >> 16;
+            tot[2 * i] = tp[i] & 0xffffu; tot[2 * i + 1] = tp[i] >> 16;
+        }
+    }
     if (w < p.n_words) {
         RleCounts before = {c[0], c[1], c[2], c[3]};
         p.cnt[w] = before;

@@ -244,3 +244,11 @@ def test_load_sbwt_validates_the_files_before_any_device_work(lib, tmp_path):
             api.load_sbwt(prefix)
         assert e.value.status == 8  # the files are fine; there is no device to upload to and no CPU fallback
     assert lib.kbo_index_serialize(None, b"x") == 7 and lib.kbo_index_load(None, 0, None) == 7
+
+
+def test_integration_doc_lists_every_entry_point():
+    """INTEGRATION.md shows the `-sys` extern block a maintainer of the reference would add: it has to name every
+    function the header declares."""
+    doc = open(os.path.join(ROOT, "INTEGRATION.md")).read()
+    missing = [n for n in header_functions() if ("fn " + n) not in doc]
+    assert not missing, missing

@@ -252,3 +252,15 @@ def test_integration_doc_lists_every_entry_point():
     doc = open(os.path.join(ROOT, "INTEGRATION.md")).read()
     missing = [n for n in header_functions() if ("fn " + n) not in doc]
     assert not missing, missing
+
+
+def test_header_is_plain_c(tmp_path):
+    """The boundary is a C ABI: the header has to compile as C99 (what cgo / bindgen / ctypes-style tools consume)."""
+    import shutil
+    import subprocess
+    if not shutil.which("gcc"):
+        pytest.skip("no gcc")
+    src = tmp_path / "hdr.c"
+    src.write_text('#include "kbo_b200.h"\nint main(void) { return KBO_ERR_FORMAT == 15 ? 0 : 1; }\n')
+    subprocess.check_call(["gcc", "-std=c99", "-Wall", "-Wextra", "-pedantic", "-Werror", "-I", os.path.join(ROOT, "include"),
+                           "-c", str(src), "-o", str(tmp_path / "hdr.o")])
